@@ -1,0 +1,147 @@
+// extern "C" entry points of libdsgcn_b200.so (see include/dsgcn_b200.h).
+#include "dsg_common.h"
+#include "conv_gemm.cuh"
+#include "graph_agg.cuh"
+#include "topology.cuh"
+#include "misc.cuh"
+#include <stdio.h>
+#include <string.h>
+
+static thread_local char g_err[512] = "";
+
+static int fail(const char* where, const char* msg) {
+    snprintf(g_err, sizeof(g_err), "%s: %s", where, msg);
+    return 1;
+}
+#define DSG_RET(where, expr) do { const char* e__ = (expr); return e__ ? fail(where, e__) : 0; } while (0)
+
+static bool dtype_ok(int d) { return d == DSG_F32 || d == DSG_BF16; }
+
+extern "C" {
+
+const char* dsg_last_error(void) { return g_err; }
+int dsg_abi_version(void) { return DSG_ABI_VERSION; }
+int dsg_is_device_build(void) {
+#ifdef DSG_EMU
+    return 0;
+#else
+    return 1;
+#endif
+}
+
+int dsg_conv_gemm(const dsg_conv_gemm_args* a, void* stream) {
+    if (!a || !dtype_ok(a->dtype)) return fail("dsg_conv_gemm", "bad arguments");
+    if (a->taps < 1 || a->t_div < 1 || a->Vin < 1 || a->K < 1) return fail("dsg_conv_gemm", "bad shape");
+    if ((a->stat_sum == nullptr) != (a->stat_sq == nullptr)) return fail("dsg_conv_gemm", "stat_sum and stat_sq go together");
+    if (a->dtype == DSG_BF16) DSG_RET("dsg_conv_gemm", dsg::launch_conv_gemm<bf16>(*a, (dsg_stream_t)stream));
+    DSG_RET("dsg_conv_gemm", dsg::launch_conv_gemm<float>(*a, (dsg_stream_t)stream));
+}
+
+int dsg_conv_wgrad(const dsg_conv_wgrad_args* a, void* stream) {
+    if (!a || !dtype_ok(a->dtype)) return fail("dsg_conv_wgrad", "bad arguments");
+    if (a->taps < 1 || a->t_div < 1 || a->Vin < 1 || a->K < 1 || a->N < 1) return fail("dsg_conv_wgrad", "bad shape");
+    if (a->dtype == DSG_BF16) DSG_RET("dsg_conv_wgrad", dsg::launch_conv_wgrad<bf16>(*a, (dsg_stream_t)stream));
+    DSG_RET("dsg_conv_wgrad", dsg::launch_conv_wgrad<float>(*a, (dsg_stream_t)stream));
+}
+
+int dsg_bn_finalize(const dsg_bn_job* jobs, int njobs, void* stream) {
+    if (njobs < 0 || (njobs > 0 && !jobs)) return fail("dsg_bn_finalize", "bad arguments");
+    for (int j0 = 0; j0 < njobs; j0 += dsg::BNF_MAX_JOBS) {
+        dsg::BnJobs pack;
+        memset(&pack, 0, sizeof(pack));
+        int nj = njobs - j0 < dsg::BNF_MAX_JOBS ? njobs - j0 : dsg::BNF_MAX_JOBS;
+        int cmax = 1;
+        for (int j = 0; j < nj; ++j) {
+            pack.j[j] = jobs[j0 + j];
+            if (pack.j[j].mode < 0 || pack.j[j].mode > 4) return fail("dsg_bn_finalize", "bad mode");
+            if (pack.j[j].C > cmax) cmax = pack.j[j].C;
+        }
+        dsg_launch(dsg::bn_finalize_kernel, dim3((cmax + 127) / 128, nj), dim3(128), 0, (dsg_stream_t)stream, pack);
+        const char* e = dsg_launch_error();
+        if (e) return fail("dsg_bn_finalize", e);
+    }
+    return 0;
+}
+
+int dsg_tmean(const void* x, int dtype, long long ld, int n_samples, int T, int V, int C, float* xm, void* stream) {
+    if (!dtype_ok(dtype) || T < 1) return fail("dsg_tmean", "bad arguments");
+    if (n_samples <= 0) return 0;
+    dim3 grid((V * C + 255) / 256, n_samples);
+    if (dtype == DSG_BF16) dsg_launch(dsg::tmean_kernel<bf16>, grid, dim3(256), 0, (dsg_stream_t)stream, (const bf16*)x, ld, T, V, C, xm);
+    else dsg_launch(dsg::tmean_kernel<float>, grid, dim3(256), 0, (dsg_stream_t)stream, (const float*)x, ld, T, V, C, xm);
+    DSG_RET("dsg_tmean", dsg_launch_error());
+}
+
+int dsg_topology_fwd(const dsg_topology_args* a, void* stream) {
+    if (!a || !dtype_ok(a->adyn_dtype)) return fail("dsg_topology_fwd", "bad arguments");
+    DSG_RET("dsg_topology_fwd", dsg::launch_topology(*a, false, (dsg_stream_t)stream));
+}
+int dsg_topology_bwd(const dsg_topology_args* a, void* stream) {
+    if (!a) return fail("dsg_topology_bwd", "bad arguments");
+    DSG_RET("dsg_topology_bwd", dsg::launch_topology(*a, true, (dsg_stream_t)stream));
+}
+
+int dsg_graph_agg(const dsg_graph_agg_args* a, void* stream) {
+    if (!a || !dtype_ok(a->dtype) || a->mode < 0 || a->mode > 3) return fail("dsg_graph_agg", "bad arguments");
+    if ((a->stat_sum == nullptr) != (a->stat_sq == nullptr)) return fail("dsg_graph_agg", "stat_sum and stat_sq go together");
+    if (a->dtype == DSG_BF16) DSG_RET("dsg_graph_agg", dsg::launch_agg<bf16>(*a, (dsg_stream_t)stream));
+    DSG_RET("dsg_graph_agg", dsg::launch_agg<float>(*a, (dsg_stream_t)stream));
+}
+
+int dsg_graph_agg_dadj(const dsg_graph_agg_dadj_args* a, void* stream) {
+    if (!a || !dtype_ok(a->dtype)) return fail("dsg_graph_agg_dadj", "bad arguments");
+    if (a->dtype == DSG_BF16) DSG_RET("dsg_graph_agg_dadj", dsg::launch_dadj<bf16>(*a, (dsg_stream_t)stream));
+    DSG_RET("dsg_graph_agg_dadj", dsg::launch_dadj<float>(*a, (dsg_stream_t)stream));
+}
+
+int dsg_ms_combine_fwd(const dsg_ms_combine_args* a, void* stream) {
+    if (!a || !dtype_ok(a->dtype) || a->V > 32) return fail("dsg_ms_combine_fwd", "bad arguments");
+    long long n_frames = (long long)a->n_samples * a->T_out;
+    if (n_frames <= 0) return 0;
+    dim3 grid((unsigned)((n_frames + 7) / 8), (a->C + dsg::PW_CT - 1) / dsg::PW_CT);
+    if (a->dtype == DSG_BF16) dsg_launch(dsg::ms_combine_fwd_kernel<bf16>, grid, dim3(dsg::PW_THREADS), 0, (dsg_stream_t)stream, *a);
+    else dsg_launch(dsg::ms_combine_fwd_kernel<float>, grid, dim3(dsg::PW_THREADS), 0, (dsg_stream_t)stream, *a);
+    DSG_RET("dsg_ms_combine_fwd", dsg_launch_error());
+}
+
+int dsg_ms_combine_bwd(const dsg_ms_combine_args* a, void* stream) {
+    if (!a || !dtype_ok(a->dtype) || a->V > 32) return fail("dsg_ms_combine_bwd", "bad arguments");
+    dsg_stream_t st = (dsg_stream_t)stream;
+    long long n_out = (long long)a->n_samples * a->T_out, n_in = (long long)a->n_samples * a->T_in;
+    if (n_out <= 0) return 0;
+    dim3 g1((unsigned)((n_out + 7) / 8), (a->C + dsg::PW_CT - 1) / dsg::PW_CT);
+    if (a->dtype == DSG_BF16) dsg_launch(dsg::ms_combine_bwd_o_kernel<bf16>, g1, dim3(dsg::PW_THREADS), 0, st, *a);
+    else dsg_launch(dsg::ms_combine_bwd_o_kernel<float>, g1, dim3(dsg::PW_THREADS), 0, st, *a);
+    const char* e = dsg_launch_error();
+    if (e) return fail("dsg_ms_combine_bwd", e);
+    const int lo[2] = {a->max_lo, a->pass_lo}, hi[2] = {a->max_hi, a->pass_hi};
+    for (int i = 0; i < 2; ++i) {
+        if (hi[i] <= lo[i]) continue;
+        dim3 g2((unsigned)((n_in + 7) / 8), (hi[i] - lo[i] + dsg::PW_CT - 1) / dsg::PW_CT);
+        if (a->dtype == DSG_BF16) dsg_launch(dsg::ms_combine_bwd_e_kernel<bf16>, g2, dim3(dsg::PW_THREADS), 0, st, *a, lo[i], hi[i]);
+        else dsg_launch(dsg::ms_combine_bwd_e_kernel<float>, g2, dim3(dsg::PW_THREADS), 0, st, *a, lo[i], hi[i]);
+        e = dsg_launch_error();
+        if (e) return fail("dsg_ms_combine_bwd", e);
+    }
+    return 0;
+}
+
+int dsg_pointwise(const dsg_pointwise_args* a, void* stream) {
+    if (!a || !dtype_ok(a->dtype) || !dtype_ok(a->out_dtype)) return fail("dsg_pointwise", "bad arguments");
+    if ((a->stat_sum == nullptr) != (a->stat_sq == nullptr)) return fail("dsg_pointwise", "stat_sum and stat_sq go together");
+    if (a->rows <= 0 || a->C <= 0) return 0;
+    dim3 grid((unsigned)((a->rows + dsg::PW_ROWS - 1) / dsg::PW_ROWS), (a->C + dsg::PW_CT - 1) / dsg::PW_CT);
+    if (a->dtype == DSG_BF16) dsg_launch(dsg::pointwise_kernel<bf16>, grid, dim3(dsg::PW_THREADS), 0, (dsg_stream_t)stream, *a);
+    else dsg_launch(dsg::pointwise_kernel<float>, grid, dim3(dsg::PW_THREADS), 0, (dsg_stream_t)stream, *a);
+    DSG_RET("dsg_pointwise", dsg_launch_error());
+}
+
+int dsg_sgd_step(float* p, const float* grad, float* buf, long long n, float lr, float momentum, float wd,
+                 int nesterov, float grad_scale, void* stream) {
+    if (n <= 0) return 0;
+    dsg_launch(dsg::sgd_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, (dsg_stream_t)stream, p, grad, buf, n, lr, momentum, wd,
+               nesterov, grad_scale);
+    DSG_RET("dsg_sgd_step", dsg_launch_error());
+}
+
+}  // extern "C"

@@ -1,0 +1,284 @@
+// Per-sample dynamic semantic adjacency of dgphgcn1 (reference gcn.py:2239-2337 with the
+// north-star flags) and its backward.  One CTA walks samples n = blockIdx.x, += gridDim.x;
+// everything for a sample lives in shared memory (V<=32, R<=32).
+//
+//   x1_k[c,v], x2_k[c,v] (k=0,1: conv1/conv2 halves; k=2: node-type-selected semantic feature, x1_2 == x2_2)
+//   arg_0 = x1_0[c,u]-x2_0[c,w];  arg_1 = We[et(u,w)] (x1_1[:,u]-x2_1[:,w]) + be[et(u,w)];  arg_2 = x1_2[c,u]-x1_2[c,w]
+//   S_k = softmax_u( sum_c x1_k[c,u] x2_k[c,w] )
+//   adyn[u,w,k*R+c] = A[k,u,w] + alpha_k*tanh(arg_k[c,u,w]) + beta_k*S_k[u,w]
+#pragma once
+#include "dsg_common.h"
+
+namespace dsg {
+
+constexpr int TP_THREADS = 256;
+
+struct TopoSmem {
+    float* x1;    // [3][R][V]
+    float* x2;    // [3][R][V]
+    float* S;     // [3][V][V]
+    float* G;     // [3][V][V]   fwd: gram; bwd: sum_c dadyn, then dG
+    __device__ TopoSmem(float* base, int R, int V) {
+        x1 = base;
+        x2 = x1 + 3 * R * V;
+        S = x2 + 3 * R * V;
+        G = S + 3 * V * V;
+    }
+    __host__ __device__ static size_t floats(int R, int V) { return (size_t)6 * R * V + 6 * V * V; }
+};
+
+DSG_D void topo_load_features(const dsg_topology_args& a, const TopoSmem& sm, int n) {
+    const int R = a.R, V = a.V;
+    const float* h = a.H + (long long)n * V * a.ld_h;
+    for (int idx = threadIdx.x; idx < 3 * R * V; idx += TP_THREADS) {
+        int c = idx % R, v = (idx / R) % V, k = idx / (R * V);
+        float f1, f2;
+        if (k < 2) {
+            f1 = h[(long long)v * a.ld_h + k * R + c];
+            f2 = h[(long long)v * a.ld_h + 2 * R + k * R + c];
+        } else {
+            f1 = f2 = h[(long long)v * a.ld_h + 4 * R + c * 5 + a.node_type[v]];
+        }
+        sm.x1[(k * R + c) * V + v] = f1;
+        sm.x2[(k * R + c) * V + v] = f2;
+    }
+}
+
+// pre-tanh argument for subset k, channel c, pair (u,w)
+DSG_D float topo_arg(const dsg_topology_args& a, const TopoSmem& sm, int k, int c, int u, int w) {
+    const int R = a.R, V = a.V;
+    if (k != 1) return sm.x1[(k * R + c) * V + u] - sm.x2[(k * R + c) * V + w];
+    const int e = a.edge_type[u * V + w];
+    const float* wr = a.We + (long long)(e * R + c) * R;
+    float s = a.be[e * R + c];
+    for (int i = 0; i < R; ++i) s = fmaf(wr[i], sm.x1[(R + i) * V + u] - sm.x2[(R + i) * V + w], s);
+    return s;
+}
+
+template <class T>
+__global__ void __launch_bounds__(TP_THREADS) topology_fwd_kernel(dsg_topology_args a) {
+    DSG_DYN_SMEM(smem_raw);
+    const int R = a.R, V = a.V, VV = V * V, KC = 3 * R;
+    TopoSmem sm(reinterpret_cast<float*>(smem_raw), R, V);
+    const int tid = threadIdx.x;
+    for (int n = blockIdx.x; n < a.n_samples; n += gridDim.x) {
+        __syncthreads();
+        topo_load_features(a, sm, n);
+        __syncthreads();
+        for (int idx = tid; idx < 3 * VV; idx += TP_THREADS) {
+            int w = idx % V, u = (idx / V) % V, k = idx / VV;
+            float s = 0.f;
+            for (int c = 0; c < R; ++c) s = fmaf(sm.x1[(k * R + c) * V + u], sm.x2[(k * R + c) * V + w], s);
+            sm.G[idx] = s;
+        }
+        __syncthreads();
+        for (int idx = tid; idx < 3 * V; idx += TP_THREADS) {     // column softmax over u
+            int w = idx % V, k = idx / V;
+            float m = -3.0e38f;
+            for (int u = 0; u < V; ++u) m = fmaxf(m, sm.G[(k * V + u) * V + w]);
+            float z = 0.f;
+            for (int u = 0; u < V; ++u) z += expf(sm.G[(k * V + u) * V + w] - m);
+            float iz = 1.f / z;
+            for (int u = 0; u < V; ++u) {
+                float s = expf(sm.G[(k * V + u) * V + w] - m) * iz;
+                sm.S[(k * V + u) * V + w] = s;
+                a.S[((long long)n * 3 + k) * VV + u * V + w] = s;
+            }
+        }
+        __syncthreads();
+        T* out = reinterpret_cast<T*>(a.adyn) + (long long)n * VV * KC;
+        for (int idx = tid; idx < VV * KC; idx += TP_THREADS) {
+            int kc = idx % KC, uw = idx / KC;
+            int k = kc / R, c = kc - k * R, u = uw / V, w = uw - u * V;
+            float th = tanhf(topo_arg(a, sm, k, c, u, w));
+            float v = a.A[k * VV + uw] + a.alpha[k] * th + a.beta[k] * sm.S[k * VV + uw];
+            stf<T>(out + idx, v);
+        }
+    }
+}
+
+// Backward.  Extra shared memory after TopoSmem:
+//   dx1,dx2 [3][R][V] each; dA_acc [3][V][V]; dWe_acc [15][R][R]; dbe_acc [15][R]; hbuf [V][R]; dbuf [V][R]; red[8]
+__global__ void __launch_bounds__(TP_THREADS) topology_bwd_kernel(dsg_topology_args a) {
+    DSG_DYN_SMEM(smem_raw);
+    const int R = a.R, V = a.V, VV = V * V, KC = 3 * R;
+    float* base = reinterpret_cast<float*>(smem_raw);
+    TopoSmem sm(base, R, V);
+    float* dx1 = base + TopoSmem::floats(R, V);
+    float* dx2 = dx1 + 3 * R * V;
+    float* dA_acc = dx2 + 3 * R * V;
+    float* dWe_acc = dA_acc + 3 * VV;
+    float* dbe_acc = dWe_acc + 15 * R * R;
+    float* hbuf = dbe_acc + 15 * R;
+    float* dbuf = hbuf + V * R;
+    float* red = dbuf + V * R;            // [8]: dalpha[3], dbeta[3]
+    const int tid = threadIdx.x;
+    for (int idx = tid; idx < 3 * VV + 15 * R * R + 15 * R; idx += TP_THREADS) dA_acc[idx] = 0.f;   // contiguous block
+    if (tid < 8) red[tid] = 0.f;
+
+    for (int n = blockIdx.x; n < a.n_samples; n += gridDim.x) {
+        __syncthreads();
+        topo_load_features(a, sm, n);
+        for (int idx = tid; idx < 3 * VV; idx += TP_THREADS) sm.S[idx] = a.S[(long long)n * 3 * VV + idx];
+        for (int idx = tid; idx < 6 * R * V; idx += TP_THREADS) dx1[idx] = 0.f;   // dx1 and dx2 are contiguous
+        const float* g = a.dadyn + (long long)n * VV * KC;
+        __syncthreads();
+        // (1) sS[k,u,w] = sum_c g[u,w,kR+c]  -> G ; dA accumulates it
+        for (int idx = tid; idx < 3 * VV; idx += TP_THREADS) {
+            int k = idx / VV, uw = idx - k * VV;
+            const float* gp = g + (long long)uw * KC + k * R;
+            float s = 0.f;
+            for (int c = 0; c < R; ++c) s += gp[c];
+            sm.G[idx] = s;
+            dA_acc[idx] += s;
+        }
+        __syncthreads();
+        // (2) softmax backward per column (k,w): dG = beta*S*(sS - sum_u sS*S); dbeta += sum sS*S
+        for (int idx = tid; idx < 3 * V; idx += TP_THREADS) {
+            int w = idx % V, k = idx / V;
+            float dot = 0.f;
+            for (int u = 0; u < V; ++u) dot = fmaf(sm.G[(k * V + u) * V + w], sm.S[(k * V + u) * V + w], dot);
+            atomicAdd(&red[3 + k], dot);
+            const float bk = a.beta[k];
+            for (int u = 0; u < V; ++u) {
+                int i = (k * V + u) * V + w;
+                sm.G[i] = bk * sm.S[i] * (sm.G[i] - dot);
+            }
+        }
+        __syncthreads();
+        // (3) gram backward + subsets 0 and 2 of the tanh branch; thread per (k,c,v), no atomics:
+        //     dx1[k,c,u] = sum_w dG[u,w] x2[c,w] + sum_w h[c,u,w];  dx2[k,c,w] = sum_u dG[u,w] x1[c,u] - sum_u h[c,u,w]
+        float my_dalpha0 = 0.f, my_dalpha2 = 0.f;
+        for (int idx = tid; idx < 3 * R * V; idx += TP_THREADS) {
+            int c = idx % R, v = (idx / R) % V, k = idx / (R * V);
+            float s1 = 0.f, s2 = 0.f;
+            const float* x1r = sm.x1 + (k * R + c) * V;
+            const float* x2r = sm.x2 + (k * R + c) * V;
+            for (int o = 0; o < V; ++o) {
+                s1 = fmaf(sm.G[(k * V + v) * V + o], x2r[o], s1);      // u=v, w=o
+                s2 = fmaf(sm.G[(k * V + o) * V + v], x1r[o], s2);      // u=o, w=v
+            }
+            if (k != 1) {
+                const float al = a.alpha[k];
+                float da = 0.f;
+                for (int o = 0; o < V; ++o) {
+                    float th = tanhf(x1r[v] - x2r[o]);                  // pair (u=v, w=o)
+                    float gg = g[(long long)(v * V + o) * KC + k * R + c];
+                    da = fmaf(gg, th, da);
+                    s1 = fmaf(al * (1.f - th * th), gg, s1);
+                    float th2 = tanhf(x1r[o] - x2r[v]);                 // pair (u=o, w=v)
+                    float gg2 = g[(long long)(o * V + v) * KC + k * R + c];
+                    s2 = fmaf(-al * (1.f - th2 * th2), gg2, s2);
+                }
+                if (k == 0) my_dalpha0 += da; else my_dalpha2 += da;
+            }
+            dx1[(k * R + c) * V + v] = s1;
+            dx2[(k * R + c) * V + v] = s2;
+        }
+        my_dalpha0 = warp_sum(my_dalpha0);
+        my_dalpha2 = warp_sum(my_dalpha2);
+        if ((tid & 31) == 0) { atomicAdd(&red[0], my_dalpha0); atomicAdd(&red[2], my_dalpha2); }
+        __syncthreads();
+        // (4) subset 1 (edge-typed linear), one source joint u at a time
+        float my_dalpha1 = 0.f;
+        const float al1 = a.alpha[1];
+        for (int u = 0; u < V; ++u) {
+            for (int idx = tid; idx < V * R; idx += TP_THREADS) {       // d1[w][i]
+                int i = idx % R, w = idx / R;
+                dbuf[idx] = sm.x1[(R + i) * V + u] - sm.x2[(R + i) * V + w];
+            }
+            __syncthreads();
+            for (int idx = tid; idx < V * R; idx += TP_THREADS) {       // h[w][o]
+                int o = idx % R, w = idx / R;
+                int e = a.edge_type[u * V + w];
+                const float* wr = a.We + (long long)(e * R + o) * R;
+                float s = a.be[e * R + o];
+                for (int i = 0; i < R; ++i) s = fmaf(wr[i], dbuf[w * R + i], s);
+                float th = tanhf(s);
+                float gg = g[(long long)(u * V + w) * KC + R + o];
+                my_dalpha1 = fmaf(gg, th, my_dalpha1);
+                float h = al1 * (1.f - th * th) * gg;
+                hbuf[idx] = h;
+                atomicAdd(&dbe_acc[e * R + o], h);
+            }
+            __syncthreads();
+            for (int idx = tid; idx < R * R; idx += TP_THREADS) {       // dWe[e][o][i] += h[w][o]*d1[w][i]
+                int i = idx % R, o = idx / R;
+                for (int w = 0; w < V; ++w) {
+                    int e = a.edge_type[u * V + w];
+                    dWe_acc[(e * R + o) * R + i] += hbuf[w * R + o] * dbuf[w * R + i];
+                }
+            }
+            __syncthreads();
+            for (int idx = tid; idx < V * R; idx += TP_THREADS) {       // dd1[w][i] = sum_o We[e][o][i] h[w][o]  (overwrites d1)
+                int i = idx % R, w = idx / R;
+                int e = a.edge_type[u * V + w];
+                const float* wc = a.We + (long long)e * R * R + i;
+                float s = 0.f;
+                for (int o = 0; o < R; ++o) s = fmaf(wc[(long long)o * R], hbuf[w * R + o], s);
+                dbuf[idx] = s;
+            }
+            __syncthreads();
+            for (int idx = tid; idx < V * R; idx += TP_THREADS) {       // scatter into dx1[1][i][u], dx2[1][i][w]
+                int i = idx % R, w = idx / R;
+                dx2[(R + i) * V + w] -= dbuf[w * R + i];
+                if (w == 0) {
+                    float s = 0.f;
+                    for (int ww = 0; ww < V; ++ww) s += dbuf[ww * R + i];
+                    dx1[(R + i) * V + u] += s;
+                }
+            }
+            __syncthreads();
+        }
+        my_dalpha1 = warp_sum(my_dalpha1);
+        if ((tid & 31) == 0) atomicAdd(&red[1], my_dalpha1);
+        __syncthreads();
+        // (5) write dH[n][v][9R]
+        float* dh = a.dH + (long long)n * V * a.ld_h;
+        for (int idx = tid; idx < V * 9 * R; idx += TP_THREADS) {
+            int col = idx % (9 * R), v = idx / (9 * R);
+            float val;
+            if (col < 2 * R) val = dx1[col * V + v];
+            else if (col < 4 * R) val = dx2[(col - 2 * R) * V + v];
+            else {
+                int q = col - 4 * R, c = q / 5, ty = q - c * 5;
+                val = (ty == a.node_type[v]) ? dx1[(2 * R + c) * V + v] + dx2[(2 * R + c) * V + v] : 0.f;
+            }
+            dh[(long long)v * a.ld_h + col] = val;
+        }
+    }
+    __syncthreads();
+    for (int idx = tid; idx < 3 * VV; idx += TP_THREADS) atomicAdd(a.dA + idx, dA_acc[idx]);
+    for (int idx = tid; idx < 15 * R * R; idx += TP_THREADS) atomicAdd(a.dWe + idx, dWe_acc[idx]);
+    for (int idx = tid; idx < 15 * R; idx += TP_THREADS) atomicAdd(a.dbe + idx, dbe_acc[idx]);
+    if (tid < 3) { atomicAdd(a.dalpha + tid, red[tid]); atomicAdd(a.dbeta + tid, red[3 + tid]); }
+}
+
+static inline size_t topo_bwd_smem_floats(int R, int V) {
+    return TopoSmem::floats(R, V) + (size_t)6 * R * V + 3 * V * V + 15 * R * R + 15 * R + 2 * V * R + 8;
+}
+
+static const char* launch_topology(const dsg_topology_args& a, bool bwd, dsg_stream_t st) {
+    if (a.V > 32 || a.R > 32 || a.R < 1) return "topology: needs V<=32 and 1<=R<=32";
+    if (a.n_samples <= 0) return nullptr;
+    int grid = a.n_samples < 2 * 148 ? a.n_samples : 2 * 148;
+    if (!bwd) {
+        size_t smem = TopoSmem::floats(a.R, a.V) * sizeof(float);
+        if (a.adyn_dtype == DSG_BF16) {
+            DSG_SET_SMEM(topology_fwd_kernel<bf16>, smem);
+            dsg_launch(topology_fwd_kernel<bf16>, dim3(grid), dim3(TP_THREADS), smem, st, a);
+        } else {
+            DSG_SET_SMEM(topology_fwd_kernel<float>, smem);
+            dsg_launch(topology_fwd_kernel<float>, dim3(grid), dim3(TP_THREADS), smem, st, a);
+        }
+    } else {
+        size_t smem = topo_bwd_smem_floats(a.R, a.V) * sizeof(float);
+        if (smem > 200 * 1024) return "topology_bwd: shared memory budget exceeded";
+        grid = a.n_samples < 148 ? a.n_samples : 148;
+        DSG_SET_SMEM(topology_bwd_kernel, smem);
+        dsg_launch(topology_bwd_kernel, dim3(grid), dim3(TP_THREADS), smem, st, a);
+    }
+    return dsg_launch_error();
+}
+
+}  // namespace dsg
