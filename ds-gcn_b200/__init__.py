@@ -1,0 +1,7 @@
+"""B200-native DS-GCN backbone (drop-in for the DS-STGCN path of davelailai/DS-GCN).
+
+Import as `import dsgcn_b200` (repo-root alias; the directory name `ds-gcn_b200` is not a
+Python identifier).  Host side: Python/PyTorch modules mirroring the reference API.
+Device side: hand-written sm_100a CUDA kernels behind a C ABI (include/dsgcn_b200.h).
+"""
+from . import _lib, ops  # noqa: F401

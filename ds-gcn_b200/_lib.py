@@ -1,0 +1,189 @@
+"""ctypes binding of libdsgcn_b200.so (include/dsgcn_b200.h).
+
+The product path loads exactly one library: the in-tree CUDA build
+`ds-gcn_b200/libdsgcn_b200.so` (sm_100a).  There is no CPU fallback: if the library
+is missing, or a tensor is not on a CUDA device, the call raises.  The CPU
+test-suite can point the binding at the host-side simulator build of the same
+sources (tests/emu) through `_testing_use_library`; nothing in the package does.
+"""
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libdsgcn_b200.so")
+
+F32, BF16 = 0, 1
+_DT = {torch.float32: F32, torch.bfloat16: BF16}
+
+c_ll, c_int, c_f, c_d, vp = C.c_longlong, C.c_int, C.c_float, C.c_double, C.c_void_p
+
+
+class ActSrc(C.Structure):
+    _fields_ = [("x1", vp), ("x2", vp), ("a1", vp), ("b1", vp), ("a2", vp), ("b2", vp),
+                ("ld1", c_ll), ("ld2", c_ll), ("relu", c_int), ("pad_", c_int)]
+
+
+class ConvGemmArgs(C.Structure):
+    _fields_ = [("src", ActSrc), ("dtype", c_int), ("K", c_int), ("N", c_int), ("W", vp),
+                ("ws_n", c_ll), ("ws_k", c_ll), ("ws_tap", c_ll), ("bias", vp),
+                ("taps", c_int), ("tap_step", c_int), ("tap_off", c_int), ("t_mul", c_int), ("t_div", c_int),
+                ("n_samples", c_int), ("T_in", c_int), ("T_out", c_int), ("Vin", c_int),
+                ("ext_in", c_int), ("contract_ext", c_int),
+                ("out", vp), ("ld_out", c_ll), ("add", vp), ("ld_add", c_ll),
+                ("bcast", vp), ("bcast_scale", c_f), ("has_mask", c_int), ("mask", ActSrc),
+                ("stat_sum", vp), ("stat_sq", vp), ("partner", vp), ("ld_partner", c_ll)]
+
+
+class ConvWgradArgs(C.Structure):
+    _fields_ = [("A", ActSrc), ("B", ActSrc), ("dtype", c_int), ("K", c_int), ("N", c_int), ("dW", vp),
+                ("ws_n", c_ll), ("ws_k", c_ll), ("ws_tap", c_ll), ("db", vp),
+                ("taps", c_int), ("tap_step", c_int), ("tap_off", c_int), ("t_mul", c_int), ("t_div", c_int),
+                ("n_samples", c_int), ("T_in", c_int), ("T_out", c_int), ("Vin", c_int), ("ext_in", c_int)]
+
+
+class BnJob(C.Structure):
+    _fields_ = [("mode", c_int), ("C", c_int), ("sum", vp), ("sq", vp), ("count", c_d),
+                ("gamma", vp), ("beta", vp), ("running_mean", vp), ("running_var", vp),
+                ("save_mean", vp), ("save_invstd", vp), ("a", vp), ("b", vp), ("c", vp),
+                ("dgamma", vp), ("dbeta", vp), ("momentum", c_f), ("eps", c_f)]
+
+
+class TopologyArgs(C.Structure):
+    _fields_ = [("H", vp), ("ld_h", c_ll), ("n_samples", c_int), ("V", c_int), ("R", c_int),
+                ("node_type", vp), ("edge_type", vp), ("A", vp), ("alpha", vp), ("beta", vp),
+                ("We", vp), ("be", vp), ("adyn", vp), ("adyn_dtype", c_int), ("S", vp),
+                ("dadyn", vp), ("dH", vp), ("dA", vp), ("dalpha", vp), ("dbeta", vp), ("dWe", vp), ("dbe", vp)]
+
+
+class GraphAggArgs(C.Structure):
+    _fields_ = [("src", ActSrc), ("dtype", c_int), ("mode", c_int),
+                ("n_samples", c_int), ("T", c_int), ("V", c_int), ("KC", c_int), ("Ksub", c_int),
+                ("adyn", vp), ("A", vp), ("out", vp), ("ld_out", c_ll), ("has_mask", c_int), ("mask", ActSrc),
+                ("stat_sum", vp), ("stat_sq", vp), ("partner", vp), ("ld_partner", c_ll)]
+
+
+class GraphAggDadjArgs(C.Structure):
+    _fields_ = [("p", ActSrc), ("dy", ActSrc), ("dtype", c_int), ("is_static", c_int),
+                ("n_samples", c_int), ("T", c_int), ("V", c_int), ("KC", c_int), ("Ksub", c_int), ("dadj", vp)]
+
+
+class MsCombineArgs(C.Structure):
+    _fields_ = [("dtype", c_int), ("n_samples", c_int), ("T_in", c_int), ("T_out", c_int), ("stride", c_int),
+                ("V", c_int), ("has_ext", c_int), ("C", c_int),
+                ("conv_lo", c_int), ("conv_hi", c_int), ("max_lo", c_int), ("max_hi", c_int),
+                ("pass_lo", c_int), ("pass_hi", c_int),
+                ("b", ActSrc), ("o", vp), ("ld_o", c_ll), ("add_coeff", vp), ("feat", vp), ("ld_feat", c_ll),
+                ("oglob", vp), ("stat_sum", vp), ("stat_sq", vp),
+                ("dfeat", ActSrc), ("d_o", vp), ("ld_do", c_ll), ("e", vp), ("ld_e", c_ll),
+                ("b_raw", vp), ("ld_b", c_ll), ("e_sum", vp), ("e_sq", vp), ("dadd_coeff", vp)]
+
+
+class PointwiseArgs(C.Structure):
+    _fields_ = [("src", ActSrc), ("dtype", c_int), ("C", c_int), ("rows", c_ll), ("out", vp), ("ld_out", c_ll),
+                ("out_dtype", c_int), ("has_mask", c_int), ("mask", ActSrc),
+                ("stat_sum", vp), ("stat_sq", vp), ("partner", vp), ("ld_partner", c_ll),
+                ("partner_dtype", c_int), ("pad_", c_int)]
+
+
+EXPORTS = {
+    # name: (restype, argtypes)
+    "dsg_conv_gemm": (c_int, [C.POINTER(ConvGemmArgs), vp]),
+    "dsg_conv_wgrad": (c_int, [C.POINTER(ConvWgradArgs), vp]),
+    "dsg_bn_finalize": (c_int, [C.POINTER(BnJob), c_int, vp]),
+    "dsg_tmean": (c_int, [vp, c_int, c_ll, c_int, c_int, c_int, c_int, vp, vp]),
+    "dsg_topology_fwd": (c_int, [C.POINTER(TopologyArgs), vp]),
+    "dsg_topology_bwd": (c_int, [C.POINTER(TopologyArgs), vp]),
+    "dsg_graph_agg": (c_int, [C.POINTER(GraphAggArgs), vp]),
+    "dsg_graph_agg_dadj": (c_int, [C.POINTER(GraphAggDadjArgs), vp]),
+    "dsg_ms_combine_fwd": (c_int, [C.POINTER(MsCombineArgs), vp]),
+    "dsg_ms_combine_bwd": (c_int, [C.POINTER(MsCombineArgs), vp]),
+    "dsg_pointwise": (c_int, [C.POINTER(PointwiseArgs), vp]),
+    "dsg_sgd_step": (c_int, [vp, vp, vp, c_ll, c_f, c_f, c_f, c_int, c_f, vp]),
+    "dsg_last_error": (C.c_char_p, []),
+    "dsg_abi_version": (c_int, []),
+    "dsg_is_device_build": (c_int, []),
+}
+
+ABI_VERSION = 1
+_lib = None
+_is_device = True
+launch_count = 0      # kernels-launching ABI calls made through this binding (bench.py reports it)
+
+
+class DsgError(RuntimeError):
+    pass
+
+
+def _bind(path):
+    lib = C.CDLL(path)
+    for name, (res, args) in EXPORTS.items():
+        fn = getattr(lib, name)          # AttributeError if the symbol is missing
+        fn.restype = res
+        fn.argtypes = args
+    if lib.dsg_abi_version() != ABI_VERSION:
+        raise DsgError(f"{path}: ABI version {lib.dsg_abi_version()} != {ABI_VERSION}")
+    return lib
+
+
+def lib():
+    """The CUDA library, loaded on first use.  Raises if it has not been built."""
+    global _lib, _is_device
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise DsgError(f"{LIB_PATH} not found: run `python build.py` (nvcc, sm_100a). "
+                           "There is no CPU fallback for the DS-GCN kernels.")
+        _lib = _bind(LIB_PATH)
+        _is_device = bool(_lib.dsg_is_device_build())
+    return _lib
+
+
+def _testing_use_library(path):
+    """CPU test-suite hook: bind the host-side simulator build of the kernel sources (tests/emu)."""
+    global _lib, _is_device
+    _lib = _bind(path) if path else None
+    _is_device = bool(_lib.dsg_is_device_build()) if _lib else True
+    return _lib
+
+
+def is_device_build():
+    lib()
+    return _is_device
+
+
+def check_tensor(t):
+    lib()
+    if _is_device and not t.is_cuda:
+        raise DsgError("DS-GCN kernels need CUDA tensors (no CPU fallback); got a CPU tensor")
+    if not _is_device and t.is_cuda:
+        raise DsgError("simulator build bound but a CUDA tensor was passed")
+
+
+def ptr(t):
+    if t is None:
+        return None
+    check_tensor(t)
+    return t.data_ptr()
+
+
+def stream():
+    if not _is_device:
+        return None
+    return torch.cuda.current_stream().cuda_stream
+
+
+def dt(t_or_dtype):
+    d = t_or_dtype.dtype if isinstance(t_or_dtype, torch.Tensor) else t_or_dtype
+    try:
+        return _DT[d]
+    except KeyError:
+        raise DsgError(f"unsupported activation dtype {d} (fp32 or bf16)")
+
+
+def call(name, *args):
+    global launch_count
+    rc = getattr(lib(), name)(*args)
+    if rc != 0:
+        raise DsgError(lib().dsg_last_error().decode())
+    launch_count += 1

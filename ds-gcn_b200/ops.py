@@ -1,0 +1,277 @@
+"""Tensor-level wrappers of the C ABI (one Python function per entry point).
+
+Activations are passed as 2-D (or N-D, flattened) tensors whose last dimension is the
+channel axis (stride 1) and whose rows have a uniform pitch `ld` — i.e. channels-last
+storage of the reference's logical [n, C, t, v] tensors, possibly a channel slice of a
+wider buffer.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib as L
+
+
+def _ld(t):
+    """row pitch (elements) of an activation tensor [..., C]"""
+    assert t.stride(-1) == 1 or t.shape[-1] == 1, "channel axis must be contiguous"
+    if t.dim() == 1:
+        return t.shape[0]
+    ld = t.stride(-2)
+    # every leading dim must be consistent with a single row pitch
+    exp = ld
+    for d in range(t.dim() - 2, -1, -1):
+        assert t.shape[d] == 1 or t.stride(d) == exp, f"activation is not row-uniform: {t.shape} {t.stride()}"
+        exp *= t.shape[d]
+    return ld
+
+
+def _nrows(t):
+    n = 1
+    for s in t.shape[:-1]:
+        n *= s
+    return n
+
+
+class Act:
+    """value = f(a1*x1 + b1 + a2*x2 + b2)   (include/dsgcn_b200.h: dsg_act_src)"""
+
+    def __init__(self, x1, a1=None, b1=None, x2=None, a2=None, b2=None, relu=False):
+        self.x1, self.a1, self.b1, self.x2, self.a2, self.b2, self.relu = x1, a1, b1, x2, a2, b2, relu
+        if x2 is not None:
+            assert x2.dtype == x1.dtype and x2.shape == x1.shape, (x1.shape, x2.shape)
+        for c in (a1, b1, a2, b2):
+            if c is not None:
+                assert c.dtype == torch.float32 and c.is_contiguous() and c.numel() == x1.shape[-1]
+
+    def struct(self):
+        s = L.ActSrc()
+        s.x1 = L.ptr(self.x1)
+        s.ld1 = _ld(self.x1)
+        s.x2 = L.ptr(self.x2)
+        s.ld2 = _ld(self.x2) if self.x2 is not None else 0
+        s.a1, s.b1, s.a2, s.b2 = L.ptr(self.a1), L.ptr(self.b1), L.ptr(self.a2), L.ptr(self.b2)
+        s.relu = int(self.relu)
+        return s
+
+    @property
+    def dtype(self):
+        return self.x1.dtype
+
+    @property
+    def C(self):
+        return self.x1.shape[-1]
+
+
+def as_act(x):
+    return x if isinstance(x, Act) else Act(x)
+
+
+def _f32(t):
+    assert t is None or (t.dtype == torch.float32 and t.is_contiguous()), "parameters must be contiguous fp32"
+    return t
+
+
+def conv_gemm(src, W, N, out, *, n_samples, T_in, T_out, Vin, ws=None, bias=None, taps=1, tap_step=0, tap_off=0,
+              t_mul=1, t_div=1, ext_in=False, contract_ext=False, add=None, bcast=None, bcast_scale=1.0,
+              mask=None, stat_sum=None, stat_sq=None, partner=None):
+    """dsg_conv_gemm.  W fp32 with strides ws=(ws_n, ws_k, ws_tap); default = PyTorch conv weight
+    [N, K, taps, 1] (or [N, K])."""
+    src = as_act(src)
+    a = L.ConvGemmArgs()
+    a.src = src.struct()
+    a.dtype = L.dt(src.dtype)
+    K = src.C
+    a.K, a.N = K, N
+    a.W = L.ptr(_f32(W))
+    if ws is None:
+        ws = (K * taps, taps, 1)
+    a.ws_n, a.ws_k, a.ws_tap = ws
+    a.bias = L.ptr(_f32(bias))
+    a.taps, a.tap_step, a.tap_off, a.t_mul, a.t_div = taps, tap_step, tap_off, t_mul, t_div
+    a.n_samples, a.T_in, a.T_out, a.Vin = n_samples, T_in, T_out, Vin
+    a.ext_in, a.contract_ext = int(ext_in), int(contract_ext)
+    assert out.dtype == src.dtype and out.shape[-1] == N
+    a.out, a.ld_out = L.ptr(out), _ld(out)
+    if add is not None:
+        assert add.dtype == src.dtype
+        a.add, a.ld_add = L.ptr(add), _ld(add)
+    if bcast is not None:
+        a.bcast, a.bcast_scale = L.ptr(_f32(bcast)), float(bcast_scale)
+    if mask is not None:
+        mask = as_act(mask)
+        assert mask.dtype == src.dtype
+        a.has_mask, a.mask = 1, mask.struct()
+    if stat_sum is not None:
+        assert stat_sum.dtype == torch.float64 and stat_sq.dtype == torch.float64
+        a.stat_sum, a.stat_sq = L.ptr(stat_sum), L.ptr(stat_sq)
+    if partner is not None:
+        assert partner.dtype == src.dtype
+        a.partner, a.ld_partner = L.ptr(partner), _ld(partner)
+    L.call("dsg_conv_gemm", C.byref(a), L.stream())
+    return out
+
+
+def conv_wgrad(A, B, dW, *, n_samples, T_in, T_out, Vin, ws=None, db=None, taps=1, tap_step=0, tap_off=0,
+               t_mul=1, t_div=1, ext_in=False):
+    A, B = as_act(A), as_act(B)
+    assert A.dtype == B.dtype
+    a = L.ConvWgradArgs()
+    a.A, a.B = A.struct(), B.struct()
+    a.dtype = L.dt(A.dtype)
+    a.K, a.N = A.C, B.C
+    a.dW = L.ptr(_f32(dW))
+    if ws is None:
+        ws = (a.K * taps, taps, 1)
+    a.ws_n, a.ws_k, a.ws_tap = ws
+    a.db = L.ptr(_f32(db))
+    a.taps, a.tap_step, a.tap_off, a.t_mul, a.t_div = taps, tap_step, tap_off, t_mul, t_div
+    a.n_samples, a.T_in, a.T_out, a.Vin, a.ext_in = n_samples, T_in, T_out, Vin, int(ext_in)
+    L.call("dsg_conv_wgrad", C.byref(a), L.stream())
+
+
+def bn_job(mode, Cn, *, sum=None, sq=None, count=1.0, gamma=None, beta=None, running_mean=None, running_var=None,
+           save_mean=None, save_invstd=None, a=None, b=None, c=None, dgamma=None, dbeta=None, momentum=0.1, eps=1e-5):
+    j = L.BnJob()
+    j.mode, j.C = mode, Cn
+    j.sum, j.sq, j.count = L.ptr(sum), L.ptr(sq), float(count)
+    j.gamma, j.beta = L.ptr(gamma), L.ptr(beta)
+    j.running_mean, j.running_var = L.ptr(running_mean), L.ptr(running_var)
+    j.save_mean, j.save_invstd = L.ptr(save_mean), L.ptr(save_invstd)
+    j.a, j.b, j.c = L.ptr(a), L.ptr(b), L.ptr(c)
+    j.dgamma, j.dbeta = L.ptr(dgamma), L.ptr(dbeta)
+    j.momentum, j.eps = momentum, eps
+    return j
+
+
+def bn_finalize(jobs):
+    if not jobs:
+        return
+    arr = (L.BnJob * len(jobs))(*jobs)
+    L.call("dsg_bn_finalize", arr, len(jobs), L.stream())
+
+
+def tmean(x, n_samples, T, V):
+    """x [n*T*V, C] -> xm [n, V, C] fp32"""
+    Cn = x.shape[-1]
+    xm = torch.empty((n_samples, V, Cn), dtype=torch.float32, device=x.device)
+    L.call("dsg_tmean", L.ptr(x), L.dt(x), _ld(x), n_samples, T, V, Cn, L.ptr(xm), L.stream())
+    return xm
+
+
+def topology_args(H, n, V, R, node_type, edge_type, A, alpha, beta, We, be, S):
+    a = L.TopologyArgs()
+    a.H, a.ld_h = L.ptr(H), _ld(H)
+    a.n_samples, a.V, a.R = n, V, R
+    assert node_type.dtype == torch.int32 and edge_type.dtype == torch.int32
+    a.node_type, a.edge_type = L.ptr(node_type), L.ptr(edge_type)
+    a.A, a.alpha, a.beta = L.ptr(_f32(A)), L.ptr(_f32(alpha)), L.ptr(_f32(beta))
+    a.We, a.be = L.ptr(_f32(We)), L.ptr(_f32(be))
+    a.S = L.ptr(S)
+    return a
+
+
+def topology_fwd(H, n, V, R, node_type, edge_type, A, alpha, beta, We, be, adyn, S):
+    a = topology_args(H, n, V, R, node_type, edge_type, A, alpha, beta, We, be, S)
+    a.adyn, a.adyn_dtype = L.ptr(adyn), L.dt(adyn)
+    L.call("dsg_topology_fwd", C.byref(a), L.stream())
+
+
+def topology_bwd(H, n, V, R, node_type, edge_type, A, alpha, beta, We, be, S, dadyn, dH, dA, dalpha, dbeta, dWe, dbe):
+    a = topology_args(H, n, V, R, node_type, edge_type, A, alpha, beta, We, be, S)
+    assert dadyn.dtype == torch.float32 and dH.dtype == torch.float32 and _ld(dH) == _ld(H)
+    a.dadyn, a.dH = L.ptr(dadyn), L.ptr(dH)
+    a.dA, a.dalpha, a.dbeta, a.dWe, a.dbe = L.ptr(_f32(dA)), L.ptr(_f32(dalpha)), L.ptr(_f32(dbeta)), L.ptr(_f32(dWe)), L.ptr(_f32(dbe))
+    L.call("dsg_topology_bwd", C.byref(a), L.stream())
+
+
+def graph_agg(src, out, *, mode, n_samples, T, V, KC, adyn=None, A=None, Ksub=0, mask=None, stat_sum=None, stat_sq=None,
+              partner=None):
+    src = as_act(src)
+    a = L.GraphAggArgs()
+    a.src, a.dtype, a.mode = src.struct(), L.dt(src.dtype), mode
+    a.n_samples, a.T, a.V, a.KC, a.Ksub = n_samples, T, V, KC, Ksub
+    if adyn is not None:
+        assert adyn.dtype == src.dtype and adyn.is_contiguous()
+    a.adyn, a.A = L.ptr(adyn), L.ptr(_f32(A))
+    assert out.dtype == src.dtype
+    a.out, a.ld_out = L.ptr(out), _ld(out)
+    if mask is not None:
+        mask = as_act(mask)
+        a.has_mask, a.mask = 1, mask.struct()
+    if stat_sum is not None:
+        a.stat_sum, a.stat_sq = L.ptr(stat_sum), L.ptr(stat_sq)
+    if partner is not None:
+        a.partner, a.ld_partner = L.ptr(partner), _ld(partner)
+    L.call("dsg_graph_agg", C.byref(a), L.stream())
+    return out
+
+
+def graph_agg_dadj(p, dy, dadj, *, n_samples, T, V, KC, is_static=False, Ksub=0):
+    p, dy = as_act(p), as_act(dy)
+    a = L.GraphAggDadjArgs()
+    a.p, a.dy, a.dtype, a.is_static = p.struct(), dy.struct(), L.dt(p.dtype), int(is_static)
+    a.n_samples, a.T, a.V, a.KC, a.Ksub = n_samples, T, V, KC, Ksub
+    assert dadj.dtype == torch.float32 and dadj.is_contiguous()
+    a.dadj = L.ptr(dadj)
+    L.call("dsg_graph_agg_dadj", C.byref(a), L.stream())
+
+
+def pointwise(src, out, *, out_dtype=None, mask=None, stat_sum=None, stat_sq=None, partner=None):
+    src = as_act(src)
+    a = L.PointwiseArgs()
+    a.src, a.dtype = src.struct(), L.dt(src.dtype)
+    a.C, a.rows = src.C, _nrows(src.x1)
+    if out is not None:
+        a.out, a.ld_out, a.out_dtype = L.ptr(out), _ld(out), L.dt(out)
+    else:
+        a.out_dtype = a.dtype
+    if mask is not None:
+        mask = as_act(mask)
+        assert mask.dtype == src.dtype
+        a.has_mask, a.mask = 1, mask.struct()
+    if stat_sum is not None:
+        a.stat_sum, a.stat_sq = L.ptr(stat_sum), L.ptr(stat_sq)
+    if partner is not None:
+        a.partner, a.ld_partner, a.partner_dtype = L.ptr(partner), _ld(partner), L.dt(partner)
+    L.call("dsg_pointwise", C.byref(a), L.stream())
+    return out
+
+
+def ms_combine_args(dtype, n, T_in, T_out, stride, V, has_ext, Cn, ranges, b, o, add_coeff):
+    a = L.MsCombineArgs()
+    a.dtype = L.dt(dtype)
+    a.n_samples, a.T_in, a.T_out, a.stride, a.V, a.has_ext, a.C = n, T_in, T_out, stride, V, int(has_ext), Cn
+    (a.conv_lo, a.conv_hi), (a.max_lo, a.max_hi), (a.pass_lo, a.pass_hi) = ranges
+    a.b = as_act(b).struct()
+    if o is not None:
+        a.o, a.ld_o = L.ptr(o), _ld(o)
+    a.add_coeff = L.ptr(_f32(add_coeff))
+    return a
+
+
+def ms_combine_fwd(b, o, feat, oglob, *, n, T_in, T_out, stride, V, has_ext, ranges, add_coeff, stat_sum=None, stat_sq=None):
+    a = ms_combine_args(feat.dtype, n, T_in, T_out, stride, V, has_ext, feat.shape[-1], ranges, b, o, add_coeff)
+    a.feat, a.ld_feat = L.ptr(feat), _ld(feat)
+    a.oglob = L.ptr(oglob)
+    if stat_sum is not None:
+        a.stat_sum, a.stat_sq = L.ptr(stat_sum), L.ptr(stat_sq)
+    L.call("dsg_ms_combine_fwd", C.byref(a), L.stream())
+
+
+def ms_combine_bwd(b, dfeat, d_o, e, oglob, b_raw, *, n, T_in, T_out, stride, V, has_ext, ranges, add_coeff, e_sum, e_sq, dadd_coeff):
+    dfeat = as_act(dfeat)
+    a = ms_combine_args(dfeat.dtype, n, T_in, T_out, stride, V, has_ext, dfeat.C, ranges, b, None, add_coeff)
+    a.dfeat = dfeat.struct()
+    a.d_o, a.ld_do = L.ptr(d_o), _ld(d_o)
+    a.e, a.ld_e = L.ptr(e), _ld(e)
+    a.oglob = L.ptr(oglob)
+    a.b_raw, a.ld_b = L.ptr(b_raw), _ld(b_raw)
+    a.e_sum, a.e_sq = L.ptr(e_sum), L.ptr(e_sq)
+    a.dadd_coeff = L.ptr(_f32(dadd_coeff))
+    L.call("dsg_ms_combine_bwd", C.byref(a), L.stream())
+
+
+def sgd_step(p, grad, buf, lr, momentum, wd, nesterov, grad_scale=1.0):
+    assert p.is_contiguous() and grad.is_contiguous() and buf.is_contiguous()
+    L.call("dsg_sgd_step", L.ptr(p), L.ptr(grad), L.ptr(buf), p.numel(), lr, momentum, wd, int(nesterov), grad_scale, L.stream())

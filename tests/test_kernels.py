@@ -1,0 +1,345 @@
+"""Primitive-level parity: every C-ABI entry point against a plain PyTorch fp32 restatement of the same op.
+
+Each test runs twice: `dev=sim` (the kernel sources on the host-side SIMT simulator — CPU-only container) and
+`dev=cuda` (marked gpu: the real sm_100a library on the B200).  Tolerances: fp32 path rel 1e-4 (north_star),
+bf16 path rel-L2 1e-2.
+"""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+import dsgcn_b200
+from dsgcn_b200 import ops
+from oracle import dsgcn_oracle as O
+
+DTYPES = [torch.float32, torch.bfloat16]
+
+
+def close(got, ref, dtype, what=""):
+    got, ref = got.detach().double().cpu(), ref.detach().double().cpu()
+    err = (got - ref).norm() / (ref.norm() + 1e-12)
+    tol = 1e-4 if dtype == torch.float32 else 1e-2
+    assert err < tol, f"{what}: rel-L2 {err:.3e} > {tol}"
+
+
+def rnd(*shape, dev, dtype=torch.float32, scale=1.0):
+    return (torch.randn(*shape) * scale).to(dtype).to(dev)
+
+
+def to_cl(x):
+    """logical [n,C,t,v] -> rows [(n,t,v), C]"""
+    n, c, t, v = x.shape
+    return x.permute(0, 2, 3, 1).reshape(n * t * v, c).contiguous()
+
+
+def from_cl(y, n, t, v):
+    return y.reshape(n, t, v, -1).permute(0, 3, 1, 2)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_conv_gemm_pointwise_prologue_epilogue(dev, dtype):
+    torch.manual_seed(0)
+    n, T, V, K, N = 2, 7, 5, 19, 70
+    x, x2 = rnd(n * T * V, K, dev=dev, dtype=dtype), rnd(n * T * V, K, dev=dev, dtype=dtype)
+    W, b = rnd(N, K, dev=dev, scale=0.3), rnd(N, dev=dev)
+    a1, b1, a2, b2 = (torch.rand(K, device=dev) + 0.5), rnd(K, dev=dev), (torch.rand(K, device=dev) + 0.5), rnd(K, dev=dev)
+    add = rnd(n * T * V, N, dev=dev, dtype=dtype)
+    bc = rnd(n, V, N, dev=dev)
+    mk = rnd(n * T * V, N, dev=dev, dtype=dtype)
+    partner = rnd(n * T * V, N, dev=dev, dtype=dtype)
+    out = torch.empty(n * T * V, N, dtype=dtype, device=dev)
+    ss, sq = torch.zeros(N, dtype=torch.float64, device=dev), torch.zeros(N, dtype=torch.float64, device=dev)
+    ops.conv_gemm(ops.Act(x, a1, b1, x2, a2, b2, relu=True), W, N, out, n_samples=n, T_in=T, T_out=T, Vin=V, bias=b,
+                  add=add, bcast=bc, bcast_scale=0.25, mask=mk, stat_sum=ss, stat_sq=sq, partner=partner)
+    src = torch.relu(x.float() * a1 + b1 + x2.float() * a2 + b2)
+    ref = src @ W.t() + b + add.float() + 0.25 * bc[:, None].expand(n, T, V, N).reshape(-1, N)
+    ref = ref * (mk.float() > 0)
+    close(out, ref, dtype, "out")
+    close(ss, ref.sum(0), dtype, "sum")
+    close(sq, (ref * partner.float()).sum(0), dtype, "sumprod")
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("k,stride,dil", [(3, 1, 1), (3, 1, 4), (3, 2, 2), (3, 2, 3), (9, 1, 1), (9, 2, 1), (1, 2, 1)])
+def test_conv_gemm_temporal_conv_and_grads(dev, dtype, k, stride, dil):
+    """forward = nn.Conv2d((k,1), stride, dilation, padding); dgrad via the transposed frame map; wgrad."""
+    torch.manual_seed(1)
+    n, T, V, K, N = 2, 11, 4, 10, 14
+    pad = (k + (k - 1) * (dil - 1) - 1) // 2
+    x = torch.randn(n, K, T, V)
+    w = torch.randn(N, K, k, 1) * 0.3
+    b = torch.randn(N)
+    xr, wr = x.clone().requires_grad_(), w.clone().requires_grad_()
+    br = b.clone().requires_grad_()
+    ref = F.conv2d(xr, wr, br, (stride, 1), (pad, 0), (dil, 1))
+    T_out = ref.shape[2]
+    gy = torch.randn_like(ref)
+    ref.backward(gy)
+    xc = to_cl(x).to(dtype).to(dev)
+    wd, bd = w.to(dev).contiguous(), b.to(dev)
+    out = torch.empty(n * T_out * V, N, dtype=dtype, device=dev)
+    ops.conv_gemm(xc, wd, N, out, n_samples=n, T_in=T, T_out=T_out, Vin=V, bias=bd, taps=k, tap_step=dil, tap_off=-pad, t_mul=stride)
+    close(from_cl(out, n, T_out, V), ref, dtype, "conv fwd")
+    gyc = to_cl(gy).to(dtype).to(dev)
+    dx = torch.empty(n * T * V, K, dtype=dtype, device=dev)
+    # dx[t] = sum_tap dy[(t + pad - tap*dil)/stride] W[:, :, tap]^T
+    ops.conv_gemm(gyc, wd, K, dx, n_samples=n, T_in=T_out, T_out=T, Vin=V, ws=(k, K * k, 1), taps=k, tap_step=-dil, tap_off=pad, t_div=stride)
+    close(from_cl(dx, n, T, V), xr.grad, dtype, "conv dgrad")
+    dW, db = torch.zeros_like(wd), torch.zeros_like(bd)
+    ops.conv_wgrad(xc, gyc, dW, db=db, n_samples=n, T_in=T, T_out=T_out, Vin=V, taps=k, tap_step=dil, tap_off=-pad, t_mul=stride)
+    close(dW, wr.grad, dtype, "conv wgrad")
+    close(db, br.grad, dtype, "conv bgrad")
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_conv_gemm_joint_mean_row(dev, dtype):
+    """ext_in appends mean_v (tcn.py:409); contract_ext is its gradient; wgrad sees the extended rows."""
+    torch.manual_seed(2)
+    n, T, V, K, N = 3, 5, 25, 12, 20
+    x = torch.randn(n, K, T, V)
+    w = torch.randn(N, K) * 0.3
+    xr, wr = x.clone().requires_grad_(), w.clone().requires_grad_()
+    xe = torch.cat([xr, xr.mean(-1, keepdim=True)], -1)
+    ref = torch.einsum("nctv,oc->notv", xe, wr)
+    gy = torch.randn_like(ref)
+    ref.backward(gy)
+    xc, wd = to_cl(x).to(dtype).to(dev), w.to(dev)
+    out = torch.empty(n * T * (V + 1), N, dtype=dtype, device=dev)
+    ops.conv_gemm(xc, wd, N, out, n_samples=n, T_in=T, T_out=T, Vin=V, ext_in=True)
+    close(from_cl(out, n, T, V + 1), ref, dtype, "ext fwd")
+    gyc = to_cl(gy).to(dtype).to(dev)
+    dx = torch.empty(n * T * V, K, dtype=dtype, device=dev)
+    ops.conv_gemm(gyc, wd, K, dx, n_samples=n, T_in=T, T_out=T, Vin=V + 1, ws=(1, K, 0), contract_ext=True)
+    close(from_cl(dx, n, T, V), xr.grad, dtype, "ext dgrad")
+    dW = torch.zeros_like(wd)
+    ops.conv_wgrad(xc, gyc, dW, n_samples=n, T_in=T, T_out=T, Vin=V, ext_in=True)
+    close(dW, wr.grad, dtype, "ext wgrad")
+
+
+def test_bn_finalize_matches_batch_norm(dev):
+    torch.manual_seed(3)
+    Cn, M = 37, 500
+    y = torch.randn(M, Cn) * 2 + 0.7
+    gamma, beta = torch.rand(Cn) + 0.5, torch.randn(Cn)
+    rm, rv = torch.randn(Cn) * 0.1, torch.rand(Cn) + 0.5
+    yr = y.clone().requires_grad_()
+    g_, b_ = gamma.clone().requires_grad_(), beta.clone().requires_grad_()
+    rm_ref, rv_ref = rm.clone(), rv.clone()
+    ref = F.batch_norm(yr, rm_ref, rv_ref, g_, b_, True, 0.1, 1e-5)
+    e = torch.randn_like(ref)
+    ref.backward(e)
+    d = lambda t: t.to(dev)
+    ss, sq = d(y.double().sum(0)), d((y.double() ** 2).sum(0))
+    a, b, sm, si = (torch.empty(Cn, device=dev) for _ in range(4))
+    rmd, rvd = d(rm.clone()), d(rv.clone())
+    ops.bn_finalize([ops.bn_job(0, Cn, sum=ss, sq=sq, count=M, gamma=d(gamma), beta=d(beta), running_mean=rmd, running_var=rvd,
+                                save_mean=sm, save_invstd=si, a=a, b=b)])
+    close(y.to(dev) * a + b, ref, torch.float32, "bn fwd")
+    close(rmd, rm_ref, torch.float32, "running_mean")
+    close(rvd, rv_ref, torch.float32, "running_var")
+    s1, s2 = d(e.double().sum(0)), d((e.double() * y.double()).sum(0))
+    ca, cb, cc, dg, db = (torch.empty(Cn, device=dev) for _ in range(5))
+    ops.bn_finalize([ops.bn_job(2, Cn, sum=s1, sq=s2, count=M, gamma=d(gamma), save_mean=sm, save_invstd=si, a=ca, b=cb, c=cc,
+                                dgamma=dg, dbeta=db)])
+    close(e.to(dev) * ca + y.to(dev) * cb + cc, yr.grad, torch.float32, "bn bwd dx")
+    close(dg, g_.grad, torch.float32, "dgamma")
+    close(db, b_.grad, torch.float32, "dbeta")
+    # eval mode
+    ops.bn_finalize([ops.bn_job(1, Cn, gamma=d(gamma), beta=d(beta), running_mean=d(rm), running_var=d(rv), a=a, b=b)])
+    close(y.to(dev) * a + b, F.batch_norm(y, rm, rv, gamma, beta, False, 0.1, 1e-5), torch.float32, "bn eval")
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_tmean_and_pointwise(dev, dtype):
+    torch.manual_seed(4)
+    n, T, V, Cn = 3, 9, 5, 70
+    x = rnd(n * T * V, Cn, dev=dev, dtype=dtype)
+    xm = ops.tmean(x, n, T, V)
+    close(xm, x.float().reshape(n, T, V, Cn).mean(1), torch.float32, "tmean")
+    x2 = rnd(n * T * V, Cn, dev=dev, dtype=dtype)
+    a1, b1 = torch.rand(Cn, device=dev) + 0.5, rnd(Cn, dev=dev)
+    mk = rnd(n * T * V, Cn, dev=dev, dtype=dtype)
+    partner = rnd(n * T * V, Cn, dev=dev)     # fp32 partner with a bf16 source is allowed
+    out = torch.empty(n * T * V, Cn, dtype=torch.float32, device=dev)
+    ss, sq = torch.zeros(Cn, dtype=torch.float64, device=dev), torch.zeros(Cn, dtype=torch.float64, device=dev)
+    ops.pointwise(ops.Act(x, a1, b1, x2, relu=True), out, mask=mk, stat_sum=ss, stat_sq=sq, partner=partner)
+    ref = torch.relu(x.float() * a1 + b1 + x2.float()) * (mk.float() > 0)
+    close(out, ref, dtype, "pointwise")
+    close(ss, ref.sum(0), dtype)
+    close(sq, (ref * partner).sum(0), dtype)
+
+
+def _topo_setup(layout, R, n, cin, seed):
+    torch.manual_seed(seed)
+    V, _, _, nt, et = O.graph_tables(layout)
+    sd = {"conv1.weight": torch.randn(2 * R, cin, 1, 1) * 0.3, "conv1.bias": torch.randn(2 * R) * 0.1,
+          "conv2.weight": torch.randn(2 * R, cin, 1, 1) * 0.3, "conv2.bias": torch.randn(2 * R) * 0.1,
+          "conv1_se.weight": torch.randn(5 * R, cin, 1, 1) * 0.3, "conv1_se.bias": torch.randn(5 * R) * 0.1,
+          "edge_linears.weight": torch.randn(15 * R, R, 1, 1) * 0.3, "edge_linears.bias": torch.randn(15 * R) * 0.1,
+          "alpha": torch.randn(3), "beta": torch.randn(3), "A": torch.randn(3, V, V) * 0.02 + 0.04}
+    xm = torch.randn(n, cin, V)
+    return V, nt, et, sd, xm
+
+
+@pytest.mark.parametrize("layout,R", [("nturgb+d", 8), ("coco", 16), ("nturgb+d", 32)])
+@pytest.mark.parametrize("adyn_dtype", DTYPES)
+def test_topology_fwd_bwd(dev, layout, R, adyn_dtype):
+    n, cin = 3, 12
+    V, nt, et, sd, xm = _topo_setup(layout, R, n, cin, 5)
+    for v in sd.values():
+        v.requires_grad_()
+    xmr = xm.clone().requires_grad_()
+    ref = O.dgphgcn1_topology(xmr, sd, nt, et, R)            # [n,3,R,V,V]
+    g = torch.randn_like(ref)
+    ref.backward(g)
+    d = lambda t: t.detach().to(dev).contiguous()
+    Wcat = torch.cat([sd["conv1.weight"], sd["conv2.weight"], sd["conv1_se.weight"]])[:, :, 0, 0]
+    bcat = torch.cat([sd["conv1.bias"], sd["conv2.bias"], sd["conv1_se.bias"]])
+    xm_rows = d(xm.permute(0, 2, 1).reshape(n * V, cin))
+    H = torch.empty(n * V, 9 * R, device=dev)
+    ops.conv_gemm(xm_rows, d(Wcat), 9 * R, H, n_samples=n, T_in=1, T_out=1, Vin=V, bias=d(bcat))
+    ntd = torch.tensor(nt, dtype=torch.int32, device=dev)
+    etd = torch.tensor(np.asarray(et), dtype=torch.int32, device=dev).reshape(-1)
+    adyn = torch.empty(n, V, V, 3 * R, dtype=adyn_dtype, device=dev)
+    S = torch.empty(n, 3, V, V, device=dev)
+    We, be = d(sd["edge_linears.weight"][:, :, 0, 0]), d(sd["edge_linears.bias"])
+    common = (H, n, V, R, ntd, etd, d(sd["A"]), d(sd["alpha"]), d(sd["beta"]), We, be)
+    ops.topology_fwd(*common, adyn, S)
+    ref_l = ref.detach().permute(0, 3, 4, 1, 2).reshape(n, V, V, 3 * R)
+    close(adyn, ref_l, adyn_dtype, "adyn")
+    if adyn_dtype != torch.float32:
+        return
+    dadyn = d(g.permute(0, 3, 4, 1, 2).reshape(n, V, V, 3 * R))
+    dH = torch.empty_like(H)
+    dA, dal, dbe_, dWe, dbe = (torch.zeros_like(t) for t in (d(sd["A"]), d(sd["alpha"]), d(sd["beta"]), We, be))
+    ops.topology_bwd(*common, S, dadyn, dH, dA, dal, dbe_, dWe, dbe)
+    close(dA, sd["A"].grad, torch.float32, "dA")
+    close(dal, sd["alpha"].grad, torch.float32, "dalpha")
+    close(dbe_, sd["beta"].grad, torch.float32, "dbeta")
+    close(dWe, sd["edge_linears.weight"].grad[:, :, 0, 0], torch.float32, "dWe")
+    close(dbe, sd["edge_linears.bias"].grad, torch.float32, "dbe")
+    # dH -> weight grads and dxm through the generic GEMMs
+    dW = torch.zeros(9 * R, cin, device=dev)
+    db = torch.zeros(9 * R, device=dev)
+    ops.conv_wgrad(xm_rows, dH, dW, db=db, n_samples=n, T_in=1, T_out=1, Vin=V)
+    close(dW[:2 * R], sd["conv1.weight"].grad[:, :, 0, 0], torch.float32, "dconv1")
+    close(dW[2 * R:4 * R], sd["conv2.weight"].grad[:, :, 0, 0], torch.float32, "dconv2")
+    close(dW[4 * R:], sd["conv1_se.weight"].grad[:, :, 0, 0], torch.float32, "dconv1_se")
+    close(db[4 * R:], sd["conv1_se.bias"].grad, torch.float32, "dconv1_se bias")
+    dxm = torch.empty(n * V, cin, device=dev)
+    ops.conv_gemm(dH, d(Wcat), cin, dxm, n_samples=n, T_in=1, T_out=1, Vin=V, ws=(1, cin, 0))
+    close(dxm.reshape(n, V, cin).permute(0, 2, 1), xmr.grad, torch.float32, "dxm")
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("V,KC", [(25, 24), (17, 48), (25, 96)])
+def test_graph_agg_dynamic(dev, dtype, V, KC):
+    torch.manual_seed(6)
+    n, T = 2, 10
+    p = torch.randn(n, T, V, KC)
+    adyn = torch.randn(n, V, V, KC) * 0.3
+    a1, b1 = torch.rand(KC) + 0.5, torch.randn(KC) * 0.2
+    pd, ad = p.to(dtype).to(dev).reshape(-1, KC), adyn.to(dtype).to(dev)
+    pq, aq = pd.float().cpu().reshape(n, T, V, KC), ad.float().cpu()
+    act = torch.relu(pq * a1 + b1)
+    ref = torch.einsum("ntuc,nuwc->ntwc", act, aq)
+    out = torch.empty(n * T * V, KC, dtype=dtype, device=dev)
+    ops.graph_agg(ops.Act(pd, a1.to(dev), b1.to(dev), relu=True), out, mode=0, n_samples=n, T=T, V=V, KC=KC, adyn=ad)
+    close(out.reshape(n, T, V, KC), ref, dtype, "agg fwd")
+    # transposed + mask + BN-backward sums
+    dy = torch.randn(n, T, V, KC).to(dtype).to(dev).reshape(-1, KC)
+    ss, sq = torch.zeros(KC, dtype=torch.float64, device=dev), torch.zeros(KC, dtype=torch.float64, device=dev)
+    e = torch.empty_like(dy)
+    ops.graph_agg(dy, e, mode=1, n_samples=n, T=T, V=V, KC=KC, adyn=ad, mask=ops.Act(pd, a1.to(dev), b1.to(dev)),
+                  stat_sum=ss, stat_sq=sq, partner=pd)
+    dyq = dy.float().cpu().reshape(n, T, V, KC)
+    ref_e = torch.einsum("ntwc,nuwc->ntuc", dyq, aq) * (act > 0)
+    close(e.reshape(n, T, V, KC), ref_e, dtype, "agg dP")
+    close(ss, ref_e.sum((0, 1, 2)), dtype)
+    close(sq, (ref_e * pq).sum((0, 1, 2)), dtype)
+    dadj = torch.empty(n, V, V, KC, device=dev)
+    ops.graph_agg_dadj(ops.Act(pd, a1.to(dev), b1.to(dev), relu=True), dy, dadj, n_samples=n, T=T, V=V, KC=KC)
+    close(dadj, torch.einsum("ntuc,ntwc->nuwc", act, dyq), dtype, "dadyn")
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_graph_agg_static(dev, dtype):
+    torch.manual_seed(7)
+    n, T, V, Cn, K = 2, 6, 25, 40, 3
+    x = torch.randn(n, T, V, K * Cn).to(dtype)
+    A = torch.randn(K, V, V) * 0.3
+    xq = x.float().reshape(n, T, V, K, Cn)
+    ref = torch.einsum("ntukc,kuw->ntwc", xq, A)
+    xd, Ad = x.to(dev).reshape(-1, K * Cn), A.to(dev)
+    out = torch.empty(n * T * V, Cn, dtype=dtype, device=dev)
+    ops.graph_agg(xd, out, mode=2, n_samples=n, T=T, V=V, KC=Cn, A=Ad, Ksub=K)
+    close(out.reshape(n, T, V, Cn), ref, dtype, "static agg")
+    dy = torch.randn(n, T, V, Cn).to(dtype)
+    dyd = dy.to(dev).reshape(-1, Cn)
+    dx = torch.empty(n * T * V, K * Cn, dtype=dtype, device=dev)
+    ops.graph_agg(dyd, dx, mode=3, n_samples=n, T=T, V=V, KC=Cn, A=Ad, Ksub=K)
+    close(dx.reshape(n, T, V, K, Cn), torch.einsum("ntwc,kuw->ntukc", dy.float(), A), dtype, "static agg dx")
+    dA = torch.zeros(K, V, V, device=dev)
+    ops.graph_agg_dadj(xd, dyd, dA, n_samples=n, T=T, V=V, KC=Cn, is_static=True, Ksub=K)
+    close(dA, torch.einsum("ntukc,ntwc->kuw", xq, dy.float()), dtype, "static dA")
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("stride,has_ext", [(1, True), (2, True), (1, False), (2, False)])
+def test_ms_combine(dev, dtype, stride, has_ext):
+    torch.manual_seed(8)
+    n, T, V, Cn = 2, 9, 5, 30
+    Vp = V + int(has_ext)
+    T_out = (T - 1) // stride + 1
+    ranges = ((0, 18), (18, 24), (24, 30))
+    B = torch.randn(n, T, Vp, Cn).to(dtype).float().requires_grad_()
+    Oc = torch.randn(n, T_out, Vp, Cn).to(dtype).float().requires_grad_()
+    a1 = torch.cat([torch.rand(24) + 0.5, torch.ones(6)])
+    b1 = torch.cat([torch.randn(24) * 0.3, torch.zeros(6)])
+    addc = torch.randn(V).requires_grad_()
+    h = B * a1 + b1
+    mx = F.max_pool2d(torch.relu(h[..., 18:24]).permute(0, 3, 1, 2), (3, 1), (stride, 1), (1, 0)).permute(0, 2, 3, 1)
+    ps = h[:, ::stride, :, 24:]
+    o_all = torch.cat([Oc[..., :18], mx, ps], -1)
+    feat_ref = o_all[:, :, :V] + (o_all[:, :, V:] * addc[None, None, :, None] if has_ext else 0)
+    gy = torch.randn_like(feat_ref).to(dtype).float()
+    feat_ref.backward(gy)
+    d = lambda t: t.detach().to(dtype).to(dev)
+    Bd, Od = d(B).reshape(-1, Cn), d(Oc).reshape(-1, Cn)
+    feat = torch.empty(n * T_out * V, Cn, dtype=dtype, device=dev)
+    oglob = torch.zeros(n * T_out, Cn, device=dev)
+    ss, sq = torch.zeros(Cn, dtype=torch.float64, device=dev), torch.zeros(Cn, dtype=torch.float64, device=dev)
+    bact = ops.Act(Bd, a1.to(dev), b1.to(dev))
+    kw = dict(n=n, T_in=T, T_out=T_out, stride=stride, V=V, has_ext=has_ext, ranges=ranges, add_coeff=addc.detach().to(dev))
+    ops.ms_combine_fwd(bact, Od, feat, oglob, stat_sum=ss, stat_sq=sq, **kw)
+    close(feat.reshape(n, T_out, V, Cn), feat_ref, dtype, "feat")
+    close(ss, feat_ref.sum((0, 1, 2)), dtype)
+    close(sq, (feat_ref ** 2).sum((0, 1, 2)), dtype)
+    d_o = torch.zeros(n * T_out * Vp, Cn, dtype=dtype, device=dev)
+    e = torch.zeros(n * T * Vp, Cn, dtype=dtype, device=dev)
+    es, eq = torch.zeros(Cn, dtype=torch.float64, device=dev), torch.zeros(Cn, dtype=torch.float64, device=dev)
+    dadd = torch.zeros(V, device=dev)
+    ops.ms_combine_bwd(bact, d(gy).reshape(-1, Cn), d_o, e, oglob, Bd, e_sum=es, e_sq=eq, dadd_coeff=dadd, **kw)
+    close(d_o.reshape(n, T_out, Vp, Cn)[..., :18], Oc.grad[..., :18], dtype, "d_o")
+    # E holds d/d(h) for max (masked by relu) and pass ranges: dB = E * a1
+    close(e.reshape(n, T, Vp, Cn)[..., 18:] * a1[18:].to(dev), B.grad[..., 18:], dtype, "E")
+    eref = (B.grad / a1)[..., 18:24]
+    close(es[18:24], eref.sum((0, 1, 2)), dtype)
+    close(eq[18:24], (eref * B.detach()[..., 18:24]).sum((0, 1, 2)), dtype)
+    if has_ext:
+        close(dadd, addc.grad, dtype, "dadd_coeff")
+
+
+def test_sgd_step_matches_torch(dev):
+    torch.manual_seed(9)
+    p = torch.randn(1000)
+    pr = p.clone().requires_grad_()
+    opt = torch.optim.SGD([pr], lr=0.1, momentum=0.9, weight_decay=5e-4, nesterov=True)
+    pd, buf = p.clone().to(dev), torch.zeros(1000, device=dev)
+    for _ in range(3):
+        g = torch.randn(1000)
+        pr.grad = g.clone()
+        opt.step()
+        ops.sgd_step(pd, g.to(dev), buf, 0.1, 0.9, 5e-4, True)
+    close(pd, pr, torch.float32, "sgd")
