@@ -5,3 +5,7 @@ Python identifier).  Host side: Python/PyTorch modules mirroring the reference A
 Device side: hand-written sm_100a CUDA kernels behind a C ABI (include/dsgcn_b200.h).
 """
 from . import _lib, ops  # noqa: F401
+from . import functional, graph, modules  # noqa: F401,E402
+from .graph import Graph  # noqa: F401,E402
+from .modules import (DGBlock, DGSTGCN, STGCN, STGCNBlock, dgmstcn, dgphgcn1, get_compute_dtype, mstcn,  # noqa: F401,E402
+                      set_compute_dtype, unit_gcn, unit_tcn)

@@ -31,7 +31,7 @@ class ConvGemmArgs(C.Structure):
                 ("taps", c_int), ("tap_step", c_int), ("tap_off", c_int), ("t_mul", c_int), ("t_div", c_int),
                 ("n_samples", c_int), ("T_in", c_int), ("T_out", c_int), ("Vin", c_int),
                 ("ext_in", c_int), ("contract_ext", c_int),
-                ("out", vp), ("ld_out", c_ll), ("add", vp), ("ld_add", c_ll),
+                ("out", vp), ("ld_out", c_ll), ("add", vp), ("ld_add", c_ll), ("add2", vp), ("ld_add2", c_ll),
                 ("bcast", vp), ("bcast_scale", c_f), ("has_mask", c_int), ("mask", ActSrc),
                 ("stat_sum", vp), ("stat_sq", vp), ("partner", vp), ("ld_partner", c_ll)]
 

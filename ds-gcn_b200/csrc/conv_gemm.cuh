@@ -136,6 +136,7 @@ __global__ void __launch_bounds__(CG_THREADS) conv_gemm_kernel(dsg_conv_gemm_arg
             v += bias;
             long long orow = f * Vout + j;
             if (a.add) v += ldf<T>(reinterpret_cast<const T*>(a.add) + orow * a.ld_add + cg);
+            if (a.add2) v += ldf<T>(reinterpret_cast<const T*>(a.add2) + orow * a.ld_add2 + cg);
             if (a.bcast) {
                 long long n = f / a.T_out;
                 v += a.bcast[(n * Vout + j) * a.N + cg] * a.bcast_scale;

@@ -1,0 +1,685 @@
+"""Forward / backward orchestration of the DS-GCN units on top of the C-ABI kernels.
+
+Every function works on channels-last 2-D activations `[n*T*V, C]` (compute dtype fp32 or bf16)
+and on the *modules'* own parameters (real nn.Conv2d / nn.BatchNorm2d children — SURVEY.md §8b
+attribute contract).  BatchNorm never runs as a separate pass: the producer kernel accumulates the
+batch statistics in its epilogue, `bn_finalize` turns them into per-channel coefficients and the
+consumer kernel applies `a*x+b` (+ReLU, +residual) in its prologue.  Backward mirrors that with
+the masked gradient `e` and `dy = ca*e + cb*y + cc`.
+
+Reference semantics: pyskl/models/gcns/utils/gcn.py:2217-2365 (dgphgcn1), :75-94 (unit_gcn),
+pyskl/models/gcns/utils/tcn.py:31-32 (unit_tcn), :162-177 (mstcn), :407-428 (dgmstcn),
+pyskl/models/gcns/dgstgcn.py:61-65 (DGBlock).
+"""
+import torch
+
+from . import ops
+from .ops import Act
+
+BN_EPS_DEFAULT = 1e-5
+
+
+# ------------------------------------------------------------------------------------------------
+# small helpers
+# ------------------------------------------------------------------------------------------------
+
+class _Pending:
+    """num_batches_tracked buffers to bump with one multi-tensor add at the end of a forward."""
+    stack = []
+
+    @classmethod
+    def add(cls, bn):
+        if bn.num_batches_tracked is None:
+            return
+        if cls.stack:
+            cls.stack[-1].append(bn.num_batches_tracked)
+        else:
+            bn.num_batches_tracked.add_(1)
+
+
+class defer_bn_counters:
+    """Context manager: collect the BatchNorm `num_batches_tracked` increments of a whole forward pass and
+    apply them with a single torch._foreach_add_ (one launch instead of ~100)."""
+
+    def __enter__(self):
+        self.items = []
+        _Pending.stack.append(self.items)
+        return self
+
+    def __exit__(self, *exc):
+        _Pending.stack.pop()
+        if self.items and exc[0] is None:
+            torch._foreach_add_(self.items, 1)
+        return False
+
+
+def _w2(conv):
+    return conv.weight
+
+
+def _zeros64(n, dev):
+    return torch.zeros(n, dtype=torch.float64, device=dev)
+
+
+def _empty32(n, dev):
+    return torch.empty(n, dtype=torch.float32, device=dev)
+
+
+class BNCoef:
+    """Per-channel coefficient arrays for a (possibly concatenated) set of BatchNorms over `C` channels."""
+
+    def __init__(self, C, dev, training):
+        self.C, self.dev, self.training = C, dev, training
+        self.a, self.b = _empty32(C, dev), _empty32(C, dev)
+        self.mean, self.invstd = _empty32(C, dev), _empty32(C, dev)
+        self.stats = torch.zeros(2, C, dtype=torch.float64, device=dev) if training else None
+        self.jobs = []
+
+    @property
+    def ssum(self):
+        return self.stats[0] if self.training else None
+
+    @property
+    def ssq(self):
+        return self.stats[1] if self.training else None
+
+    def add_bn(self, bn, lo, hi, count):
+        """forward job for nn.BatchNorm2d `bn` on channels [lo,hi)"""
+        use_batch = self.training
+        sl = slice(lo, hi)
+        if use_batch:
+            self.jobs.append(ops.bn_job(0, hi - lo, sum=self.stats[0, sl], sq=self.stats[1, sl], count=count, gamma=bn.weight,
+                                        beta=bn.bias, running_mean=bn.running_mean, running_var=bn.running_var,
+                                        save_mean=self.mean[sl], save_invstd=self.invstd[sl], a=self.a[sl], b=self.b[sl],
+                                        momentum=bn.momentum if bn.momentum is not None else 0.1, eps=bn.eps))
+            _Pending.add(bn)
+        else:
+            self.jobs.append(ops.bn_job(1, hi - lo, gamma=bn.weight, beta=bn.bias, running_mean=bn.running_mean,
+                                        running_var=bn.running_var, save_mean=self.mean[sl], save_invstd=self.invstd[sl],
+                                        a=self.a[sl], b=self.b[sl], eps=bn.eps))
+
+    def add_identity(self, lo, hi):
+        sl = slice(lo, hi)
+        self.jobs.append(ops.bn_job(4, hi - lo, a=self.a[sl], b=self.b[sl]))
+
+    def run(self):
+        ops.bn_finalize(self.jobs)
+        self.jobs = []
+
+
+class BNBack:
+    """Backward coefficient arrays (ca, cb, cc) for the same channel layout as a BNCoef."""
+
+    def __init__(self, fwd):
+        C, dev = fwd.C, fwd.dev
+        self.fwd = fwd
+        self.ca, self.cb, self.cc = _empty32(C, dev), _empty32(C, dev), _empty32(C, dev)
+        self.stats = torch.zeros(2, C, dtype=torch.float64, device=dev)
+        self.jobs = []
+
+    @property
+    def ssum(self):
+        return self.stats[0]
+
+    @property
+    def ssq(self):
+        return self.stats[1]
+
+    def add_bn(self, bn, lo, hi, count, grads):
+        sl = slice(lo, hi)
+        dg, db = torch.empty_like(bn.weight), torch.empty_like(bn.bias)
+        grads[bn.weight], grads[bn.bias] = dg, db
+        self.jobs.append(ops.bn_job(2 if self.fwd.training else 3, hi - lo, sum=self.stats[0, sl], sq=self.stats[1, sl], count=count,
+                                    gamma=bn.weight, save_mean=self.fwd.mean[sl], save_invstd=self.fwd.invstd[sl],
+                                    a=self.ca[sl], b=self.cb[sl], c=self.cc[sl], dgamma=dg, dbeta=db))
+
+    def add_identity(self, lo, hi):
+        sl = slice(lo, hi)
+        self.jobs.append(ops.bn_job(4, hi - lo, a=self.ca[sl], b=self.cb[sl], c=self.cc[sl]))
+
+    def run(self):
+        ops.bn_finalize(self.jobs)
+        self.jobs = []
+
+    def dy(self, e, y, lo=None, hi=None):
+        """activation source for dy = ca*e + cb*y + cc on channels [lo,hi) (e, y already sliced)"""
+        sl = slice(lo, hi)
+        return Act(e, self.ca[sl], self.cc[sl], y, self.cb[sl])
+
+
+def _bn_train(module_training, bn):
+    return module_training or not bn.track_running_stats
+
+
+# ------------------------------------------------------------------------------------------------
+# dgphgcn1  (spatial unit with the dynamic semantic adjacency)
+# ------------------------------------------------------------------------------------------------
+
+def dgphgcn1_forward(m, x, n, T, V, save):
+    """x [n*T*V, C_in] -> out [n*T*V, C_out].  `save`: dict filled for backward (or None)."""
+    dev, dt = x.device, x.dtype
+    rows = n * T * V
+    Cin, Cout, R = m.in_channels, m.out_channels, m.mid_channels
+    KC = 3 * R
+    has_down = m.has_down
+    training = m.training
+    nt, et = m._tables(dev)
+
+    # ---- topology branch: temporal mean -> 9R features per joint -> per-sample adjacency
+    xm = ops.tmean(x, n, T, V)                                                  # [n,V,Cin] fp32
+    Wt = torch.cat([m.conv1.weight, m.conv2.weight, m.conv1_se.weight]).view(9 * R, Cin)
+    bt = torch.cat([m.conv1.bias, m.conv2.bias, m.conv1_se.bias])
+    xm2 = xm.view(n * V, Cin)
+    H = torch.empty(n * V, 9 * R, dtype=torch.float32, device=dev)
+    ops.conv_gemm(xm2, Wt, 9 * R, H, n_samples=n, T_in=1, T_out=1, Vin=V, bias=bt)
+    adyn = torch.empty(n, V, V, KC, dtype=dt, device=dev)
+    S = torch.empty(n, 3, V, V, dtype=torch.float32, device=dev)
+    We, be = m.edge_linears.weight.view(15 * R, R), m.edge_linears.bias
+    ops.topology_fwd(H, n, V, R, nt, et, m.A, m.alpha, m.beta, We, be, adyn, S)
+
+    # ---- pre (+down) 1x1 convolutions in one GEMM, BatchNorm statistics in the epilogue
+    Npd = KC + (Cout if has_down else 0)
+    if has_down:
+        Wpd = torch.cat([m.pre[0].weight, m.down[0].weight]).view(Npd, Cin)
+        bpd = torch.cat([m.pre[0].bias, m.down[0].bias])
+    else:
+        Wpd, bpd = m.pre[0].weight.view(KC, Cin), m.pre[0].bias
+    PD = torch.empty(rows, Npd, dtype=dt, device=dev)
+    c_pd = BNCoef(Npd, dev, training)
+    ops.conv_gemm(x, Wpd, Npd, PD, n_samples=n, T_in=T, T_out=T, Vin=V, bias=bpd, stat_sum=c_pd.ssum, stat_sq=c_pd.ssq)
+    c_pd.add_bn(m.pre[1], 0, KC, rows)
+    if has_down:
+        c_pd.add_bn(m.down[1], KC, Npd, rows)
+    c_pd.run()
+
+    # ---- y[n,t,w,kc] = sum_u relu(bn(pre))[n,t,u,kc] * adyn[n,u,w,kc]
+    P_act = Act(PD[:, :KC], c_pd.a[:KC], c_pd.b[:KC], relu=True)
+    Y = torch.empty(rows, KC, dtype=dt, device=dev)
+    ops.graph_agg(P_act, Y, mode=0, n_samples=n, T=T, V=V, KC=KC, adyn=adyn)
+
+    # ---- post conv, BatchNorm statistics in the epilogue
+    Z = torch.empty(rows, Cout, dtype=dt, device=dev)
+    c_z = BNCoef(Cout, dev, training)
+    ops.conv_gemm(Y, m.post.weight.view(Cout, KC), Cout, Z, n_samples=n, T_in=T, T_out=T, Vin=V, bias=m.post.bias,
+                  stat_sum=c_z.ssum, stat_sq=c_z.ssq)
+    c_z.add_bn(m.bn, 0, Cout, rows)
+    c_z.run()
+
+    # ---- out = relu(bn(z) + down(x))
+    out = torch.empty(rows, Cout, dtype=dt, device=dev)
+    if has_down:
+        src = Act(Z, c_z.a, c_z.b, PD[:, KC:], c_pd.a[KC:], c_pd.b[KC:], relu=True)
+    else:
+        src = Act(Z, c_z.a, c_z.b, x, relu=True)
+    ops.pointwise(src, out)
+    if save is not None:
+        save.update(x=x, xm2=xm2, Wt=Wt, H=H, adyn=adyn, S=S, Wpd=Wpd, PD=PD, c_pd=c_pd, Y=Y, Z=Z, c_z=c_z, out=out,
+                    dims=(n, T, V))
+    return out
+
+
+def dgphgcn1_backward(m, sv, dout, grads, extra_add=None):
+    """dout: gradient w.r.t. the unit output [rows, C_out].  Fills `grads` {param: grad}; returns dx.
+    `extra_add` (optional, [rows, C_in]) is added to dx inside the last kernel's epilogue."""
+    n, T, V = sv["dims"]
+    x, PD, Y, Z, out, adyn = sv["x"], sv["PD"], sv["Y"], sv["Z"], sv["out"], sv["adyn"]
+    c_pd, c_z = sv["c_pd"], sv["c_z"]
+    dev, dt = x.device, x.dtype
+    rows = n * T * V
+    Cin, Cout, R = m.in_channels, m.out_channels, m.mid_channels
+    KC = 3 * R
+    has_down = m.has_down
+    Npd = KC + (Cout if has_down else 0)
+    nt, et = m._tables(dev)
+
+    # ---- e4 = dout * [out > 0], BatchNorm-backward sums for `bn` (and `down.1`)
+    E = torch.empty(rows, Npd, dtype=dt, device=dev) if has_down else None
+    E4 = E[:, KC:] if has_down else torch.empty(rows, Cout, dtype=dt, device=dev)
+    E5 = E[:, :KC] if has_down else torch.empty(rows, KC, dtype=dt, device=dev)
+    b_z, b_pd = BNBack(c_z), BNBack(c_pd)
+    ops.pointwise(dout, E4, mask=out, stat_sum=b_z.ssum, stat_sq=b_z.ssq, partner=Z)
+    b_z.add_bn(m.bn, 0, Cout, rows, grads)
+    if has_down:
+        ops.pointwise(E4, None, stat_sum=b_pd.ssum[KC:], stat_sq=b_pd.ssq[KC:], partner=PD[:, KC:])
+    b_z.run()
+    dZ = b_z.dy(E4, Z)
+
+    # ---- post conv backward
+    dY = torch.empty(rows, KC, dtype=dt, device=dev)
+    Wpost = m.post.weight.view(Cout, KC)
+    ops.conv_gemm(dZ, Wpost, KC, dY, n_samples=n, T_in=T, T_out=T, Vin=V, ws=(1, KC, 0))
+    dWpost, dbpost = torch.zeros_like(m.post.weight), torch.zeros_like(m.post.bias)
+    ops.conv_wgrad(Y, dZ, dWpost, db=dbpost, n_samples=n, T_in=T, T_out=T, Vin=V)
+    grads[m.post.weight], grads[m.post.bias] = dWpost, dbpost
+
+    # ---- adjacency contraction backward: dadyn, and e5 = dP * [P > 0] with BN-backward sums for pre.1
+    P_act = Act(PD[:, :KC], c_pd.a[:KC], c_pd.b[:KC], relu=True)
+    dadyn = torch.empty(n, V, V, KC, dtype=torch.float32, device=dev)
+    ops.graph_agg_dadj(P_act, dY, dadyn, n_samples=n, T=T, V=V, KC=KC)
+    ops.graph_agg(dY, E5, mode=1, n_samples=n, T=T, V=V, KC=KC, adyn=adyn, mask=Act(PD[:, :KC], c_pd.a[:KC], c_pd.b[:KC]),
+                  stat_sum=b_pd.ssum[:KC], stat_sq=b_pd.ssq[:KC], partner=PD[:, :KC])
+    b_pd.add_bn(m.pre[1], 0, KC, rows, grads)
+    if has_down:
+        b_pd.add_bn(m.down[1], KC, Npd, rows, grads)
+    b_pd.run()
+
+    # ---- topology backward
+    H, S, Wt, xm2 = sv["H"], sv["S"], sv["Wt"], sv["xm2"]
+    dH = torch.empty_like(H)
+    dA, dal, dbe = torch.zeros_like(m.A), torch.zeros_like(m.alpha), torch.zeros_like(m.beta)
+    dWe, dbe_l = torch.zeros_like(m.edge_linears.weight), torch.zeros_like(m.edge_linears.bias)
+    ops.topology_bwd(H, n, V, R, nt, et, m.A, m.alpha, m.beta, m.edge_linears.weight.view(15 * R, R), m.edge_linears.bias, S,
+                     dadyn, dH, dA, dal, dbe, dWe, dbe_l)
+    grads[m.A], grads[m.alpha], grads[m.beta] = dA, dal, dbe
+    grads[m.edge_linears.weight], grads[m.edge_linears.bias] = dWe, dbe_l
+    dWt = torch.zeros(9 * R, Cin, dtype=torch.float32, device=dev)
+    dbt = torch.zeros(9 * R, dtype=torch.float32, device=dev)
+    ops.conv_wgrad(xm2, dH, dWt, db=dbt, n_samples=n, T_in=1, T_out=1, Vin=V)
+    for conv, lo, hi in ((m.conv1, 0, 2 * R), (m.conv2, 2 * R, 4 * R), (m.conv1_se, 4 * R, 9 * R)):
+        grads[conv.weight], grads[conv.bias] = dWt[lo:hi].view_as(conv.weight), dbt[lo:hi]
+    dxm = torch.empty(n * V, Cin, dtype=torch.float32, device=dev)
+    ops.conv_gemm(dH, Wt, Cin, dxm, n_samples=n, T_in=1, T_out=1, Vin=V, ws=(1, Cin, 0))
+
+    # ---- dx = [dP_raw | dD_raw] @ [Wpre; Wdown] (+ e4 when the residual is the identity) + dxm/T (+ extra)
+    Wpd = sv["Wpd"]
+    dx = torch.empty(rows, Cin, dtype=dt, device=dev)
+    dWpd = torch.zeros(Npd, Cin, dtype=torch.float32, device=dev)
+    dbpd = torch.zeros(Npd, dtype=torch.float32, device=dev)
+    if has_down:
+        dPD = b_pd.dy(E, PD)
+        ops.conv_gemm(dPD, Wpd, Cin, dx, n_samples=n, T_in=T, T_out=T, Vin=V, ws=(1, Cin, 0), add=extra_add, bcast=dxm,
+                      bcast_scale=1.0 / T)
+    else:
+        dPD = b_pd.dy(E5, PD)
+        ops.conv_gemm(dPD, Wpd, Cin, dx, n_samples=n, T_in=T, T_out=T, Vin=V, ws=(1, Cin, 0), add=E4, add2=extra_add, bcast=dxm,
+                      bcast_scale=1.0 / T)
+    ops.conv_wgrad(x, dPD, dWpd, db=dbpd, n_samples=n, T_in=T, T_out=T, Vin=V)
+    grads[m.pre[0].weight], grads[m.pre[0].bias] = dWpd[:KC].view_as(m.pre[0].weight), dbpd[:KC]
+    if has_down:
+        grads[m.down[0].weight], grads[m.down[0].bias] = dWpd[KC:].view_as(m.down[0].weight), dbpd[KC:]
+    return dx
+
+
+# ------------------------------------------------------------------------------------------------
+# mstcn / dgmstcn  (multi-scale temporal unit)
+# ------------------------------------------------------------------------------------------------
+
+def ms_layout(m):
+    """channel ranges of the branches: [(kind, lo, hi, cfg)], kind in {'conv','max','1x1'}"""
+    out, lo = [], 0
+    for j, cfg in enumerate(m.ms_cfg):
+        w = m.rem_mid_channels if j == 0 else m.mid_channels
+        kind = "1x1" if cfg == "1x1" else ("max" if cfg[0] == "max" else "conv")
+        out.append((kind, lo, lo + w, cfg))
+        lo += w
+    return out, lo
+
+
+def _ms_ranges(layout):
+    def span(kind):
+        items = [(lo, hi) for k, lo, hi, _ in layout if k == kind]
+        if not items:
+            return (0, 0)
+        for (l0, h0), (l1, h1) in zip(items, items[1:]):
+            if h0 != l1:
+                raise NotImplementedError("ms_cfg: branches of one kind must be adjacent")
+        return (items[0][0], items[-1][1])
+    if sum(1 for k, *_ in layout if k == "max") > 1 or sum(1 for k, *_ in layout if k == "1x1") > 1:
+        raise NotImplementedError("ms_cfg: at most one 'max' and one '1x1' branch")
+    return (span("conv"), span("max"), span("1x1"))
+
+
+def mstcn_forward(m, g, n, T, V, save, res=None, final_relu=False):
+    """g [n*T*V, C_in] -> [n*T_out*V, C_out] = bn(transform(branches(g))) (+ res) (relu).
+    `res`: optional Act-like tuple (x, a, b) added before the final ReLU (DGBlock residual)."""
+    dev, dt = g.device, g.dtype
+    training = m.training
+    has_ext = m.has_ext
+    Vp, s = V + int(has_ext), m.stride
+    T_out = (T - 1) // s + 1
+    Cin, Cout = m.in_channels, m.out_channels
+    layout, Ct = ms_layout(m)
+    ranges = _ms_ranges(layout)
+
+    # ---- all branch 1x1 convolutions as one GEMM over the (V+1)-joint tensor
+    convs = [m.branches[j] if kind == "1x1" else m.branches[j][0] for j, (kind, *_) in enumerate(layout)]
+    Wbr = torch.cat([c.weight for c in convs]).view(Ct, Cin)
+    bbr = torch.cat([c.bias for c in convs])
+    rows_b = n * T * Vp
+    B = torch.empty(rows_b, Ct, dtype=dt, device=dev)
+    c_b = BNCoef(Ct, dev, training)
+    ops.conv_gemm(g, Wbr, Ct, B, n_samples=n, T_in=T, T_out=T, Vin=V, ext_in=has_ext, bias=bbr, stat_sum=c_b.ssum, stat_sq=c_b.ssq)
+    for j, (kind, lo, hi, _) in enumerate(layout):
+        if kind == "1x1":
+            c_b.add_identity(lo, hi)
+        else:
+            c_b.add_bn(m.branches[j][1], lo, hi, rows_b)
+    c_b.run()
+
+    # ---- dilated (k x 1) convolutions of the conv branches
+    rows_o = n * T_out * Vp
+    O = torch.empty(rows_o, Ct, dtype=dt, device=dev)
+    for j, (kind, lo, hi, cfg) in enumerate(layout):
+        if kind != "conv":
+            continue
+        k, d = cfg
+        pad = (k + (k - 1) * (d - 1) - 1) // 2
+        conv = m.branches[j][3].conv
+        ops.conv_gemm(Act(B[:, lo:hi], c_b.a[lo:hi], c_b.b[lo:hi], relu=True), conv.weight, hi - lo, O[:, lo:hi],
+                      n_samples=n, T_in=T, T_out=T_out, Vin=Vp, bias=conv.bias, taps=k, tap_step=d, tap_off=-pad, t_mul=s)
+
+    # ---- max-pool / pass-through branches, local + global*add_coeff, statistics for transform.0
+    rows_f = n * T_out * V
+    feat = torch.empty(rows_f, Ct, dtype=dt, device=dev)
+    oglob = torch.empty(n * T_out, Ct, dtype=torch.float32, device=dev) if has_ext else None
+    c_t = BNCoef(Ct, dev, training)
+    add_coeff = m.add_coeff if has_ext else None
+    if has_ext and add_coeff.numel() < V:
+        raise ValueError("add_coeff is shorter than the number of joints")
+    ops.ms_combine_fwd(Act(B, c_b.a, c_b.b), O, feat, oglob, n=n, T_in=T, T_out=T_out, stride=s, V=V, has_ext=has_ext,
+                       ranges=ranges, add_coeff=add_coeff, stat_sum=c_t.ssum, stat_sq=c_t.ssq)
+    c_t.add_bn(m.transform[0], 0, Ct, rows_f)
+    c_t.run()
+
+    # ---- transform conv + final BatchNorm (+ residual, ReLU)
+    U = torch.empty(rows_f, Cout, dtype=dt, device=dev)
+    c_u = BNCoef(Cout, dev, training)
+    ops.conv_gemm(Act(feat, c_t.a, c_t.b, relu=True), m.transform[2].weight.view(Cout, Ct), Cout, U, n_samples=n, T_in=T_out,
+                  T_out=T_out, Vin=V, bias=m.transform[2].bias, stat_sum=c_u.ssum, stat_sq=c_u.ssq)
+    c_u.add_bn(m.bn, 0, Cout, rows_f)
+    c_u.run()
+    out = torch.empty(rows_f, Cout, dtype=dt, device=dev)
+    if res is not None:
+        rx, ra, rb = res
+        src = Act(U, c_u.a, c_u.b, rx, ra, rb, relu=final_relu)
+    else:
+        src = Act(U, c_u.a, c_u.b, relu=final_relu)
+    ops.pointwise(src, out)
+    if save is not None:
+        save.update(g=g, Wbr=Wbr, B=B, c_b=c_b, feat=feat, oglob=oglob, c_t=c_t, U=U, c_u=c_u, out=out, dims=(n, T, V),
+                    final_relu=final_relu)
+    return out, T_out
+
+
+def mstcn_backward(m, sv, dout, grads):
+    """Returns (dg, E) where E is the gradient w.r.t. the pre-ReLU sum (what flows into the residual)."""
+    n, T, V = sv["dims"]
+    g, B, feat, U, out = sv["g"], sv["B"], sv["feat"], sv["U"], sv["out"]
+    c_b, c_t, c_u = sv["c_b"], sv["c_t"], sv["c_u"]
+    dev, dt = g.device, g.dtype
+    has_ext = m.has_ext
+    Vp, s = V + int(has_ext), m.stride
+    T_out = (T - 1) // s + 1
+    Cin, Cout = m.in_channels, m.out_channels
+    layout, Ct = ms_layout(m)
+    ranges = _ms_ranges(layout)
+    rows_b, rows_o, rows_f = n * T * Vp, n * T_out * Vp, n * T_out * V
+
+    # ---- final ReLU mask + BN-backward sums of `bn`
+    b_u = BNBack(c_u)
+    if sv["final_relu"]:
+        E = torch.empty(rows_f, Cout, dtype=dt, device=dev)
+        ops.pointwise(dout, E, mask=out, stat_sum=b_u.ssum, stat_sq=b_u.ssq, partner=U)
+    else:
+        E = dout
+        ops.pointwise(dout, None, stat_sum=b_u.ssum, stat_sq=b_u.ssq, partner=U)
+    b_u.add_bn(m.bn, 0, Cout, rows_f, grads)
+    b_u.run()
+    dU = b_u.dy(E, U)
+
+    # ---- transform conv backward; e2 = dfeat_act * [bn_t(feat) > 0] with sums for transform.0
+    tr = m.transform[2]
+    b_t = BNBack(c_t)
+    E2 = torch.empty(rows_f, Ct, dtype=dt, device=dev)
+    ops.conv_gemm(dU, tr.weight.view(Cout, Ct), Ct, E2, n_samples=n, T_in=T_out, T_out=T_out, Vin=V, ws=(1, Ct, 0),
+                  mask=Act(feat, c_t.a, c_t.b), stat_sum=b_t.ssum, stat_sq=b_t.ssq, partner=feat)
+    dWtr, dbtr = torch.zeros_like(tr.weight), torch.zeros_like(tr.bias)
+    ops.conv_wgrad(Act(feat, c_t.a, c_t.b, relu=True), dU, dWtr, db=dbtr, n_samples=n, T_in=T_out, T_out=T_out, Vin=V)
+    grads[tr.weight], grads[tr.bias] = dWtr, dbtr
+    b_t.add_bn(m.transform[0], 0, Ct, rows_f, grads)
+    b_t.run()
+    dfeat = b_t.dy(E2, feat)
+
+    # ---- combine backward: d_o for the conv branches, masked grads of max / pass branches, dadd_coeff
+    b_b = BNBack(c_b)
+    d_o = torch.empty(rows_o, Ct, dtype=dt, device=dev)
+    E3 = torch.empty(rows_b, Ct, dtype=dt, device=dev)
+    dadd = torch.zeros_like(m.add_coeff) if has_ext else None
+    ops.ms_combine_bwd(Act(B, c_b.a, c_b.b), dfeat, d_o, E3, sv["oglob"], B, n=n, T_in=T, T_out=T_out, stride=s, V=V,
+                       has_ext=has_ext, ranges=ranges, add_coeff=m.add_coeff if has_ext else None, e_sum=b_b.ssum, e_sq=b_b.ssq,
+                       dadd_coeff=dadd)
+    if has_ext:
+        grads[m.add_coeff] = dadd
+    for j, (kind, lo, hi, cfg) in enumerate(layout):
+        if kind != "conv":
+            continue
+        k, d = cfg
+        pad = (k + (k - 1) * (d - 1) - 1) // 2
+        w = hi - lo
+        conv = m.branches[j][3].conv
+        ops.conv_gemm(d_o[:, lo:hi], conv.weight, w, E3[:, lo:hi], n_samples=n, T_in=T_out, T_out=T, Vin=Vp, ws=(k, w * k, 1), taps=k,
+                      tap_step=-d, tap_off=pad, t_div=s, mask=Act(B[:, lo:hi], c_b.a[lo:hi], c_b.b[lo:hi]),
+                      stat_sum=b_b.ssum[lo:hi], stat_sq=b_b.ssq[lo:hi], partner=B[:, lo:hi])
+        dWc, dbc = torch.zeros_like(conv.weight), torch.zeros_like(conv.bias)
+        ops.conv_wgrad(Act(B[:, lo:hi], c_b.a[lo:hi], c_b.b[lo:hi], relu=True), d_o[:, lo:hi], dWc, db=dbc, n_samples=n, T_in=T,
+                       T_out=T_out, Vin=Vp, taps=k, tap_step=d, tap_off=-pad, t_mul=s)
+        grads[conv.weight], grads[conv.bias] = dWc, dbc
+    for j, (kind, lo, hi, _) in enumerate(layout):
+        if kind == "1x1":
+            b_b.add_identity(lo, hi)
+        else:
+            b_b.add_bn(m.branches[j][1], lo, hi, rows_b, grads)
+    b_b.run()
+    dB = b_b.dy(E3, B)
+
+    # ---- branch 1x1 convolutions backward (the joint-mean column folds back into the V joints)
+    dg = torch.empty(n * T * V, Cin, dtype=dt, device=dev)
+    ops.conv_gemm(dB, sv["Wbr"], Cin, dg, n_samples=n, T_in=T, T_out=T, Vin=Vp, ws=(1, Cin, 0), contract_ext=has_ext)
+    dWbr = torch.zeros(Ct, Cin, dtype=torch.float32, device=dev)
+    dbbr = torch.zeros(Ct, dtype=torch.float32, device=dev)
+    ops.conv_wgrad(g, dB, dWbr, db=dbbr, n_samples=n, T_in=T, T_out=T, Vin=V, ext_in=has_ext)
+    for j, (kind, lo, hi, _) in enumerate(layout):
+        conv = m.branches[j] if kind == "1x1" else m.branches[j][0]
+        grads[conv.weight], grads[conv.bias] = dWbr[lo:hi].view_as(conv.weight), dbbr[lo:hi]
+    return dg, E
+
+
+# ------------------------------------------------------------------------------------------------
+# unit_tcn  ((k x 1) conv + BatchNorm; also the strided 1x1 block residual)
+# ------------------------------------------------------------------------------------------------
+
+def unit_tcn_raw_forward(m, x, n, T, V, save):
+    """conv only: returns (R_raw, BNCoef or None, T_out).  The BatchNorm is applied by the consumer."""
+    dev, dt = x.device, x.dtype
+    k, s, d = m.kernel_size, m.stride, m.dilation
+    pad = (k + (k - 1) * (d - 1) - 1) // 2
+    T_out = (T + 2 * pad - d * (k - 1) - 1) // s + 1
+    Cout = m.out_channels
+    rows = n * T_out * V
+    Rr = torch.empty(rows, Cout, dtype=dt, device=dev)
+    has_bn = isinstance(m.bn, torch.nn.modules.batchnorm._BatchNorm)
+    c_r = BNCoef(Cout, dev, m.training) if has_bn else None
+    ops.conv_gemm(x, m.conv.weight, Cout, Rr, n_samples=n, T_in=T, T_out=T_out, Vin=V, bias=m.conv.bias, taps=k, tap_step=d,
+                  tap_off=-pad, t_mul=s, stat_sum=c_r.ssum if has_bn else None, stat_sq=c_r.ssq if has_bn else None)
+    if has_bn:
+        c_r.add_bn(m.bn, 0, Cout, rows)
+        c_r.run()
+    if save is not None:
+        save.update(x=x, R=Rr, c_r=c_r, dims=(n, T, V), T_out=T_out)
+    return Rr, c_r, T_out
+
+
+def unit_tcn_raw_backward(m, sv, E, grads, e_is_masked_sum_done=False):
+    """E: gradient w.r.t. bn(conv(x)).  Returns dx."""
+    n, T, V = sv["dims"]
+    x, Rr, c_r, T_out = sv["x"], sv["R"], sv["c_r"], sv["T_out"]
+    dev, dt = x.device, x.dtype
+    k, s, d = m.kernel_size, m.stride, m.dilation
+    pad = (k + (k - 1) * (d - 1) - 1) // 2
+    Cin, Cout = m.in_channels, m.out_channels
+    if c_r is not None:
+        b_r = BNBack(c_r)
+        ops.pointwise(E, None, stat_sum=b_r.ssum, stat_sq=b_r.ssq, partner=Rr)
+        b_r.add_bn(m.bn, 0, Cout, n * T_out * V, grads)
+        b_r.run()
+        dR = b_r.dy(E, Rr)
+    else:
+        dR = Act(E)
+    dx = torch.empty(n * T * V, Cin, dtype=dt, device=dev)
+    ops.conv_gemm(dR, m.conv.weight, Cin, dx, n_samples=n, T_in=T_out, T_out=T, Vin=V, ws=(k, Cin * k, 1), taps=k, tap_step=-d,
+                  tap_off=pad, t_div=s)
+    dW, db = torch.zeros_like(m.conv.weight), torch.zeros_like(m.conv.bias)
+    ops.conv_wgrad(x, dR, dW, db=db, n_samples=n, T_in=T, T_out=T_out, Vin=V, taps=k, tap_step=d, tap_off=-pad, t_mul=s)
+    grads[m.conv.weight], grads[m.conv.bias] = dW, db
+    return dx
+
+
+def unit_tcn_forward(m, x, n, T, V, save, res=None, final_relu=False):
+    """out = bn(conv(x)) (+ res) (relu) — unit_tcn as a block's temporal unit or stand-alone."""
+    rsave = {} if save is not None else None
+    Rr, c_r, T_out = unit_tcn_raw_forward(m, x, n, T, V, rsave)
+    a, b = (c_r.a, c_r.b) if c_r is not None else (None, None)
+    if res is None and not final_relu and c_r is None:
+        out = Rr
+    else:
+        out = torch.empty_like(Rr)
+        if res is not None:
+            rx, ra, rb = res
+            ops.pointwise(Act(Rr, a, b, rx, ra, rb, relu=final_relu), out)
+        else:
+            ops.pointwise(Act(Rr, a, b, relu=final_relu), out)
+    if save is not None:
+        save.update(raw=rsave, out=out, final_relu=final_relu)
+    return out, T_out
+
+
+def unit_tcn_backward(m, sv, dout, grads):
+    """Returns (dx, E) like mstcn_backward."""
+    if sv["final_relu"]:
+        E = torch.empty_like(dout)
+        ops.pointwise(dout, E, mask=sv["out"])
+    else:
+        E = dout
+    return unit_tcn_raw_backward(m, sv["raw"], E, grads), E
+
+
+# ------------------------------------------------------------------------------------------------
+# unit_gcn  (static adjacency; ST-GCN / ST-GCN++ spatial unit)
+# ------------------------------------------------------------------------------------------------
+
+def unit_gcn_A(m):
+    if m.adaptive == "offset":
+        return m.A + m.PA
+    if m.adaptive == "importance":
+        return m.A * m.PA
+    return m.A
+
+
+def unit_gcn_forward(m, x, n, T, V, save):
+    dev, dt = x.device, x.dtype
+    rows = n * T * V
+    Cin, Cout, K = m.in_channels, m.out_channels, m.num_subsets
+    training = m.training
+    A_eff = unit_gcn_A(m).detach().contiguous()
+    has_down = m.with_res and m.has_down
+    c_d = None
+    D = None
+    if has_down:
+        D = torch.empty(rows, Cout, dtype=dt, device=dev)
+        c_d = BNCoef(Cout, dev, training)
+        ops.conv_gemm(x, m.down[0].weight, Cout, D, n_samples=n, T_in=T, T_out=T, Vin=V, bias=m.down[0].bias,
+                      stat_sum=c_d.ssum, stat_sq=c_d.ssq)
+        c_d.add_bn(m.down[1], 0, Cout, rows)
+        c_d.run()
+    c_z = BNCoef(Cout, dev, training)
+    Z = torch.empty(rows, Cout, dtype=dt, device=dev)
+    if m.conv_pos == "pre":
+        mid = torch.empty(rows, K * Cout, dtype=dt, device=dev)
+        ops.conv_gemm(x, m.conv.weight, K * Cout, mid, n_samples=n, T_in=T, T_out=T, Vin=V, bias=m.conv.bias)
+        ops.graph_agg(mid, Z, mode=2, n_samples=n, T=T, V=V, KC=Cout, A=A_eff, Ksub=K, stat_sum=c_z.ssum, stat_sq=c_z.ssq)
+    else:
+        mid = torch.empty(rows, K * Cin, dtype=dt, device=dev)
+        ops.graph_agg(x, mid, mode=3, n_samples=n, T=T, V=V, KC=Cin, A=A_eff.transpose(1, 2).contiguous(), Ksub=K)
+        ops.conv_gemm(mid, m.conv.weight, Cout, Z, n_samples=n, T_in=T, T_out=T, Vin=V, bias=m.conv.bias,
+                      stat_sum=c_z.ssum, stat_sq=c_z.ssq)
+    c_z.add_bn(m.bn, 0, Cout, rows)
+    c_z.run()
+    out = torch.empty(rows, Cout, dtype=dt, device=dev)
+    if has_down:
+        src = Act(Z, c_z.a, c_z.b, D, c_d.a, c_d.b, relu=True)
+    elif m.with_res:
+        src = Act(Z, c_z.a, c_z.b, x, relu=True)
+    else:
+        src = Act(Z, c_z.a, c_z.b, relu=True)
+    ops.pointwise(src, out)
+    if save is not None:
+        save.update(x=x, D=D, c_d=c_d, mid=mid, Z=Z, c_z=c_z, out=out, A_eff=A_eff, dims=(n, T, V))
+    return out
+
+
+def unit_gcn_backward(m, sv, dout, grads, extra_add=None):
+    n, T, V = sv["dims"]
+    x, D, c_d, mid, Z, c_z, out, A_eff = sv["x"], sv["D"], sv["c_d"], sv["mid"], sv["Z"], sv["c_z"], sv["out"], sv["A_eff"]
+    dev, dt = x.device, x.dtype
+    rows = n * T * V
+    Cin, Cout, K = m.in_channels, m.out_channels, m.num_subsets
+    has_down = D is not None
+    b_z = BNBack(c_z)
+    E = torch.empty(rows, Cout, dtype=dt, device=dev)
+    ops.pointwise(dout, E, mask=out, stat_sum=b_z.ssum, stat_sq=b_z.ssq, partner=Z)
+    b_z.add_bn(m.bn, 0, Cout, rows, grads)
+    b_z.run()
+    dZ = b_z.dy(E, Z)
+    dA = torch.zeros_like(A_eff)
+    dx = torch.empty(rows, Cin, dtype=dt, device=dev)
+    dW, db = torch.zeros_like(m.conv.weight), torch.zeros_like(m.conv.bias)
+    add = E if (m.with_res and not has_down) else None
+    add2 = extra_add
+    if has_down:
+        b_d = BNBack(c_d)
+        ops.pointwise(E, None, stat_sum=b_d.ssum, stat_sq=b_d.ssq, partner=D)
+        b_d.add_bn(m.down[1], 0, Cout, rows, grads)
+        b_d.run()
+        dD = b_d.dy(E, D)
+        dxd = torch.empty(rows, Cin, dtype=dt, device=dev)
+        ops.conv_gemm(dD, m.down[0].weight, Cin, dxd, n_samples=n, T_in=T, T_out=T, Vin=V, ws=(1, Cin, 0))
+        dWd, dbd = torch.zeros_like(m.down[0].weight), torch.zeros_like(m.down[0].bias)
+        ops.conv_wgrad(x, dD, dWd, db=dbd, n_samples=n, T_in=T, T_out=T, Vin=V)
+        grads[m.down[0].weight], grads[m.down[0].bias] = dWd, dbd
+        add = dxd
+    if m.conv_pos == "pre":
+        # z = sum_k mid_k A_k ; mid = conv(x)
+        dmid = torch.empty(rows, K * Cout, dtype=dt, device=dev)
+        dZm = torch.empty(rows, Cout, dtype=dt, device=dev)
+        ops.pointwise(dZ, dZm)                       # materialise dz once: it feeds two contractions
+        ops.graph_agg(dZm, dmid, mode=3, n_samples=n, T=T, V=V, KC=Cout, A=A_eff, Ksub=K)
+        ops.graph_agg_dadj(mid, dZm, dA, n_samples=n, T=T, V=V, KC=Cout, is_static=True, Ksub=K)
+        ops.conv_gemm(dmid, m.conv.weight, Cin, dx, n_samples=n, T_in=T, T_out=T, Vin=V, ws=(1, Cin, 0), add=add, add2=add2)
+        ops.conv_wgrad(x, dmid, dW, db=db, n_samples=n, T_in=T, T_out=T, Vin=V)
+    else:
+        # mid_k = x A_k ; z = conv(mid)
+        dmid = torch.empty(rows, K * Cin, dtype=dt, device=dev)
+        ops.conv_gemm(dZ, m.conv.weight, K * Cin, dmid, n_samples=n, T_in=T, T_out=T, Vin=V, ws=(1, K * Cin, 0))
+        ops.conv_wgrad(mid, dZ, dW, db=db, n_samples=n, T_in=T, T_out=T, Vin=V)
+        At = A_eff.transpose(1, 2).contiguous()
+        dxa = torch.empty(rows, Cin, dtype=dt, device=dev)
+        ops.graph_agg(dmid, dxa, mode=2, n_samples=n, T=T, V=V, KC=Cin, A=At, Ksub=K)
+        # dA[k,u,w] = sum x[u,c] dmid[w,kC+c]  == static dadj with p := dmid (as [w, kC+c]) transposed roles
+        dAt = torch.zeros_like(A_eff)
+        ops.graph_agg_dadj(dmid, x, dAt, n_samples=n, T=T, V=V, KC=Cin, is_static=True, Ksub=K)
+        dA = dAt.transpose(1, 2).contiguous()
+        for extra in (add, add2):
+            if extra is not None:
+                nxt = torch.empty_like(dxa)
+                ops.pointwise(Act(dxa, x2=extra), nxt)
+                dxa = nxt
+        dx = dxa
+    grads[m.conv.weight], grads[m.conv.bias] = dW, db
+    # chain dA_eff into the learnable tensors
+    if m.adaptive == "init":
+        grads[m.A] = dA
+    elif m.adaptive == "offset":
+        grads[m.PA] = dA
+    elif m.adaptive == "importance":
+        grads[m.PA] = dA * m.A.detach()
+    return dx

@@ -73,7 +73,7 @@ def _f32(t):
 
 
 def conv_gemm(src, W, N, out, *, n_samples, T_in, T_out, Vin, ws=None, bias=None, taps=1, tap_step=0, tap_off=0,
-              t_mul=1, t_div=1, ext_in=False, contract_ext=False, add=None, bcast=None, bcast_scale=1.0,
+              t_mul=1, t_div=1, ext_in=False, contract_ext=False, add=None, add2=None, bcast=None, bcast_scale=1.0,
               mask=None, stat_sum=None, stat_sq=None, partner=None):
     """dsg_conv_gemm.  W fp32 with strides ws=(ws_n, ws_k, ws_tap); default = PyTorch conv weight
     [N, K, taps, 1] (or [N, K])."""
@@ -96,6 +96,9 @@ def conv_gemm(src, W, N, out, *, n_samples, T_in, T_out, Vin, ws=None, bias=None
     if add is not None:
         assert add.dtype == src.dtype
         a.add, a.ld_add = L.ptr(add), _ld(add)
+    if add2 is not None:
+        assert add2.dtype == src.dtype
+        a.add2, a.ld_add2 = L.ptr(add2), _ld(add2)
     if bcast is not None:
         a.bcast, a.bcast_scale = L.ptr(_f32(bcast)), float(bcast_scale)
     if mask is not None:

@@ -61,7 +61,7 @@ typedef struct dsg_act_src {
  *   rows      : Vin rows per source frame; ext_in appends the joint-mean row (tcn.py:409) so the
  *               output has Vin+1 rows per frame; contract_ext folds the last row back
  *               (out[j] = acc[j] + acc[Vin-1]/(Vin-1), rows Vin-1 per frame: gradient of that mean).
- *   epilogue  : + bias; + add (same shape as out, dtype); + bcast[n, j, c]*bcast_scale (fp32, per
+ *   epilogue  : + bias; + add + add2 (same shape as out, dtype); + bcast[n, j, c]*bcast_scale (fp32, per
  *               sample: gradient of the temporal mean, gcn.py:2246); * [mask > 0]; statistics
  *               stat_sum[c] += v, stat_sq[c] += v * partner(r,c) (partner NULL => v: BatchNorm batch
  *               statistics; partner = saved raw output: BatchNorm backward sums). */
@@ -79,6 +79,8 @@ typedef struct dsg_conv_gemm_args {
     long long ld_out;
     const void* add;
     long long ld_add;
+    const void* add2;     /* second addend, same conventions as add */
+    long long ld_add2;
     const float* bcast;   /* [n_samples, Vout, N] fp32 */
     float bcast_scale;
     int has_mask;

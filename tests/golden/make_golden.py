@@ -1,0 +1,97 @@
+"""Generates tests/golden/*.npz|json by running the UNMODIFIED reference (imported from /root/reference through
+oracle/ref_loader.py).  Run in the authoring container:  python tests/golden/make_golden.py
+The fixtures pin the oracle restatement (tests/test_oracle.py) and the CUDA path (tests/test_backbone.py) on
+machines where /root/reference is absent (the GPU box)."""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+from oracle import ref_loader as rl  # noqa: E402
+from oracle import dsgcn_oracle as O  # noqa: E402
+
+SMALL = dict(base_channels=16, gcn_ratio=0.25)   # small-width copy of the north-star backbone for fast fixtures
+
+
+def main():
+    ns = rl.load()
+    torch.set_num_threads(4)
+    # 1. graph tables (integers must be bit-exact)
+    tabs = {}
+    for layout in ("nturgb+d", "coco", "openpose"):
+        for mode, kw in (("spatial", {}), ("stgcn_spatial", {}), ("stgcn_spatial", {"max_hop": 2}), ("binary_adj", {})):
+            g = ns.Graph(layout=layout, mode=mode, **kw)
+            tabs[f"{layout}|{mode}|{kw.get('max_hop', 1)}|A"] = g.A
+        if layout != "openpose":
+            g = ns.Graph(layout=layout, mode="spatial")
+            tabs[f"{layout}|node_type"] = np.asarray(g.node_type, dtype=np.int64)
+            tabs[f"{layout}|edge_type"] = g.edge_type
+    np.random.seed(7)
+    tabs["nturgb+d|random|seed7"] = ns.Graph(layout="nturgb+d", mode="random", num_filter=3, init_off=.04, init_std=.02).A
+    np.savez_compressed(os.path.join(HERE, "graph_tables.npz"), **tabs)
+
+    # 2. state-dict contract of the north-star backbone
+    torch.manual_seed(0); np.random.seed(0)
+    full = ns.DGSTGCN(**rl.NORTH_STAR_BACKBONE)
+    keys = {k: list(v.shape) for k, v in full.state_dict().items()}
+    json.dump(dict(num_parameters=sum(p.numel() for p in full.parameters()), keys=keys),
+              open(os.path.join(HERE, "dgstgcn_state_dict_keys.json"), "w"), indent=0)
+
+    # 3. seeded forward/backward vectors of a small-width backbone (all branches live)
+    torch.manual_seed(1); np.random.seed(1)
+    cfg = dict(rl.NORTH_STAR_BACKBONE); cfg.update(SMALL)
+    m = ns.DGSTGCN(**cfg)
+    sd = m.state_dict(); O.randomize_state(sd, 3); m.load_state_dict(sd)
+    x = torch.randn(2, 2, 16, 25, 3)
+    out = {"x": x.numpy()}
+    for k, v in m.state_dict().items():
+        out["sd|" + k] = v.numpy().copy()
+    m.eval()
+    with torch.no_grad():
+        out["y_eval"] = m(x).numpy()
+    m.train()
+    y = m(x)
+    gy = torch.randn(y.shape, generator=torch.Generator().manual_seed(5))
+    y.backward(gy)
+    out["y_train"], out["gy"] = y.detach().numpy(), gy.numpy()
+    for k, p in m.named_parameters():
+        if p.grad is None:
+            out["nograd|" + k] = np.zeros(0)
+        elif k.split(".")[-1] in ("alpha", "beta", "add_coeff", "A") or k.startswith("data_bn") or "edge_linears" in k or k.startswith("gcn.0.") or k.startswith("gcn.9.tcn.transform"):
+            out["grad|" + k] = p.grad.numpy().copy()
+    for k, v in m.state_dict().items():
+        if k.endswith("running_mean") or k.endswith("running_var"):
+            if k.startswith("gcn.0.") or k.startswith("data_bn") or k.startswith("gcn.4."):
+                out["after|" + k] = v.numpy().copy()
+    np.savez_compressed(os.path.join(HERE, "dgstgcn_small.npz"), **out)
+
+    # 4. one full-width DGBlock (block 8 shape: 256->256, R=32) on a short clip
+    torch.manual_seed(2)
+    g = ns.Graph(layout="nturgb+d", mode="random")
+    A = torch.tensor(g.A, dtype=torch.float32)
+    blk = ns.DGBlock(256, 256, A, torch.tensor(g.edge_type, dtype=torch.float32), torch.tensor(g.node_type), 1,
+                     gcn_type="dgphgcn1", gcn_ratio=0.125, gcn_node_attention=True, gcn_edge_attention=True, gcn_decompose=True,
+                     gcn_subset_wise=True, gcn_ctr="T", gcn_ada="T", tcn_type="dgmstcn")
+    sd = blk.state_dict(); O.randomize_state(sd, 4)
+    for v in sd.values():          # big tensors are stored as fp16: make that lossless *before* running the reference
+        if v.dim() >= 2 and v.numel() > 20000:
+            v.copy_(v.half().float())
+    blk.load_state_dict(sd)
+    xb = torch.randn(2, 256, 6, 25)
+    blk.eval()
+    ob = {"x": xb.numpy()}
+    with torch.no_grad():
+        ob["y_eval"] = blk(xb).numpy()
+    for k, v in blk.state_dict().items():
+        ob["sd|" + k] = v.numpy().astype(np.float16 if v.dim() >= 2 and v.numel() > 20000 else v.numpy().dtype)
+    np.savez_compressed(os.path.join(HERE, "dgblock_256.npz"), **ob)
+    for f in os.listdir(HERE):
+        print(f, os.path.getsize(os.path.join(HERE, f)))
+
+
+if __name__ == "__main__":
+    main()
