@@ -1,0 +1,202 @@
+"""Whole-backbone parity: DGSTGCN (north-star config) against the golden vectors produced by the unmodified reference
+and against the live oracle, eval and train, fp32 and bf16; state-dict contract; which parameters get no gradient."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import dsgcn_b200
+from dsgcn_b200 import modules as M
+from oracle import dsgcn_oracle as O
+
+G = os.path.join(os.path.dirname(__file__), "golden")
+NORTH_STAR = dict(   # configs/dsstgcn/DSSTGCN_model.py:4-33
+    gcn_type="dgphgcn1", gcn_ratio=0.125, gcn_node_attention=True, gcn_edge_attention=True, gcn_decompose=True,
+    gcn_subset_wise=True, gcn_ctr="T", gcn_ada="T", tcn_type="dgmstcn",
+    graph_cfg=dict(layout="nturgb+d", mode="random", num_filter=3, init_off=.04, init_std=.02),
+    tcn_ms_cfg=[(3, 1), (3, 2), (3, 3), (3, 4), ("max", 3), "1x1"])
+DTYPES = [torch.float32, torch.bfloat16]
+
+
+def rel(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return float((a - b).norm() / (b.norm() + 1e-12))
+
+
+def test_state_dict_contract():
+    meta = json.load(open(os.path.join(G, "dgstgcn_state_dict_keys.json")))
+    np.random.seed(0)
+    m = M.DGSTGCN(**NORTH_STAR)
+    sd = m.state_dict()
+    assert list(sd.keys()) == list(meta["keys"].keys())
+    for k, v in sd.items():
+        assert list(v.shape) == meta["keys"][k], k
+    assert sum(p.numel() for p in m.parameters()) == meta["num_parameters"] == 1361530
+    # attribute contract used by the reference's analysis hooks (core/hooks/feature_hook.py:13-166)
+    u = m.gcn[4].gcn
+    for name in ("down", "pre", "conv1", "conv2", "conv1_se", "edge_linears", "tanh", "A", "alpha", "beta", "node_type", "edge_type",
+                 "semantic_num", "norm_num", "mid_channels", "num_subsets", "num_types", "edge_num", "ctr", "ada", "ctr_act",
+                 "decompose", "node_attention", "edge_attention", "target_specific", "subset_wise"):
+        assert hasattr(u, name), name
+    assert isinstance(m.gcn, torch.nn.ModuleList) and all(hasattr(b, a) for b in m.gcn for a in ("gcn", "tcn", "residual", "relu"))
+    with pytest.raises(AssertionError):
+        M.DGSTGCN(bogus_kwarg=1, **NORTH_STAR)          # dgstgcn.py:26-27
+
+
+def test_unbuilt_variants_fail_loudly():
+    with pytest.raises(NotImplementedError):
+        M.DGSTGCN(**{**NORTH_STAR, "gcn_type": "dggcn"})
+    with pytest.raises(NotImplementedError):
+        M.DGSTGCN(**{**NORTH_STAR, "tcn_type": "dgmsmlp"})
+    with pytest.raises(dsgcn_b200._lib.DsgError):       # no CPU fallback: CPU tensors are rejected by the CUDA binding
+        dsgcn_b200._lib._testing_use_library(None)
+        if not os.path.exists(dsgcn_b200._lib.LIB_PATH):
+            raise dsgcn_b200._lib.DsgError("library not built")
+        M.unit_tcn(4, 4)(torch.zeros(1, 4, 5, 17))
+
+
+def _small_model(dev):
+    z = np.load(os.path.join(G, "dgstgcn_small.npz"))
+    np.random.seed(0)
+    m = M.DGSTGCN(**{**NORTH_STAR, "base_channels": 16, "gcn_ratio": 0.25})
+    m.load_state_dict({k[3:]: torch.from_numpy(z[k].copy()) for k in z.files if k.startswith("sd|")})
+    return z, m.to(dev)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_dgstgcn_small_vs_golden(dev, dtype):
+    z, m = _small_model(dev)
+    x = torch.from_numpy(z["x"]).to(dev)
+    M.set_compute_dtype(dtype)
+    try:
+        m.eval()
+        with torch.no_grad():
+            y = m(x)
+        assert y.shape == z["y_eval"].shape
+        assert rel(y, torch.from_numpy(z["y_eval"])) < (1e-4 if dtype == torch.float32 else 1e-2)
+        m.train()
+        lim, cos_lim = 1e-4, 0.98
+        if dtype == torch.bfloat16:
+            # train-mode BN on a 4-sample, 16-channel toy batch amplifies bf16 rounding: calibrate against what
+            # PyTorch's own bf16 autocast does to the oracle on the same inputs (8e-2 here) and stay within 1.25x.
+            with torch.autocast("cpu", dtype=torch.bfloat16):
+                ya = O.dgstgcn_forward(torch.from_numpy(z["x"]), {k: v.detach().cpu().clone() for k, v in m.state_dict().items()},
+                                       training=True, base_channels=16)
+            lim = max(1.5e-2, 1.25 * rel(ya.float(), torch.from_numpy(z["y_train"])))
+            sda = {k: v.detach().cpu().clone() for k, v in m.state_dict().items()}
+            for k, _ in m.named_parameters():
+                sda[k].requires_grad_()
+            with torch.autocast("cpu", dtype=torch.bfloat16):
+                ya = O.dgstgcn_forward(torch.from_numpy(z["x"]), sda, training=True, base_channels=16)
+            ya.float().backward(torch.from_numpy(z["gy"]))
+            gk = [k[5:] for k in z.files if k.startswith("grad|")]
+            va = torch.cat([sda[k].grad.double().reshape(-1) for k in gk])
+            vr = torch.cat([torch.from_numpy(z["grad|" + k]).double().reshape(-1) for k in gk])
+            cos_lim = min(0.98, float(torch.dot(va, vr) / (va.norm() * vr.norm())))   # at least as good as torch autocast
+        y = m(x)
+        assert rel(y, torch.from_numpy(z["y_train"])) < lim
+        y.backward(torch.from_numpy(z["gy"]).to(dev).to(y.dtype))
+        params = dict(m.named_parameters())
+        nograd = {k[7:] for k in z.files if k.startswith("nograd|")}
+        assert {k for k, p in params.items() if p.grad is None} == nograd
+        gkeys = [k[5:] for k in z.files if k.startswith("grad|")]
+        gmax = max(float(np.linalg.norm(z["grad|" + k])) for k in gkeys)
+        if dtype == torch.float32:
+            for k in gkeys:
+                r = torch.from_numpy(z["grad|" + k])
+                err = float((params[k].grad.detach().cpu().double() - r.double()).norm())
+                assert err <= 1e-4 * float(r.norm()) + 1e-5 * gmax, f"{k}: {err:.3e} vs {float(r.norm()):.3e}"
+            for k in z.files:
+                if k.startswith("after|"):
+                    assert rel(m.state_dict()[k[6:]], torch.from_numpy(z[k])) < 1e-4, k
+        else:
+            mine = torch.cat([params[k].grad.detach().double().cpu().reshape(-1) for k in gkeys])
+            refv = torch.cat([torch.from_numpy(z["grad|" + k]).double().reshape(-1) for k in gkeys])
+            cos = float(torch.dot(mine, refv) / (mine.norm() * refv.norm()))
+            assert cos > cos_lim, f"bf16 gradient direction cosine {cos:.4f} (limit {cos_lim:.4f})"
+    finally:
+        M.set_compute_dtype(torch.bfloat16)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_dgblock_256_vs_golden(dev, dtype):
+    z = np.load(os.path.join(G, "dgblock_256.npz"))
+    V, _, _, nt, et = O.graph_tables("nturgb+d")
+    blk = M.DGBlock(256, 256, torch.zeros(3, V, V), torch.tensor(et, dtype=torch.float32), torch.tensor(nt), 1, gcn_type="dgphgcn1",
+                    gcn_ratio=0.125, gcn_node_attention=True, gcn_edge_attention=True, gcn_decompose=True, gcn_subset_wise=True,
+                    tcn_type="dgmstcn")
+    blk.load_state_dict({k[3:]: torch.from_numpy(z[k].astype(np.float32) if z[k].dtype == np.float16 else z[k].copy())
+                         for k in z.files if k.startswith("sd|")})
+    blk.to(dev).eval()
+    M.set_compute_dtype(dtype)
+    try:
+        with torch.no_grad():
+            y = blk(torch.from_numpy(z["x"]).to(dev))
+        assert rel(y, torch.from_numpy(z["y_eval"])) < (1e-4 if dtype == torch.float32 else 1e-2)
+    finally:
+        M.set_compute_dtype(torch.bfloat16)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_dgstgcn_full_vs_oracle(dtype):
+    """BASELINE config 1 shapes (M=2,T=100,V=25,C=3), N=4: kernels on the B200 vs the oracle on the host."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    dsgcn_b200._lib._testing_use_library(None)
+    dev = torch.device("cuda:0")
+    torch.manual_seed(0); np.random.seed(0)
+    m = M.DGSTGCN(**NORTH_STAR)
+    sd = m.state_dict(); O.randomize_state(sd, 1); m.load_state_dict(sd)
+    x = torch.randn(4, 2, 100, 25, 3)
+    M.set_compute_dtype(dtype)
+    try:
+        m.eval()
+        ref = O.dgstgcn_forward(x, {k: v.clone() for k, v in m.state_dict().items()}, training=False)
+        m.to(dev)
+        with torch.no_grad():
+            y = m(x.to(dev))
+        assert y.shape == (4, 2, 256, 25, 25)
+        e = rel(y, ref)
+        assert e < (1e-4 if dtype == torch.float32 else 1e-2), f"eval rel-L2 {e:.3e}"
+        pooled, pooled_ref = y.float().mean((3, 4)).mean(1).cpu(), ref.mean((3, 4)).mean(1)
+        assert rel(pooled, pooled_ref) < (1e-4 if dtype == torch.float32 else 1e-2)
+        # train mode: forward, BN buffers, gradients
+        m.train()
+        m.cpu()
+        sdt = {k: v.clone() for k, v in m.state_dict().items()}
+        pn = {k for k, _ in m.named_parameters()}
+        for k, v in sdt.items():
+            if k in pn:
+                v.requires_grad_()
+        ref = O.dgstgcn_forward(x, sdt, training=True)
+        gy = torch.randn(ref.shape, generator=torch.Generator().manual_seed(5))
+        ref.backward(gy)
+        m.to(dev)
+        y = m(x.to(dev))
+        e = rel(y, ref)
+        assert e < (1e-4 if dtype == torch.float32 else 1.5e-2), f"train rel-L2 {e:.3e}"
+        y.backward(gy.to(dev).to(y.dtype))
+        params = dict(m.named_parameters())
+        assert {k for k, p in params.items() if p.grad is None} == {k for k in pn if sdt[k].grad is None}
+        keys = [k for k in pn if sdt[k].grad is not None]
+        gmax = max(float(sdt[k].grad.norm()) for k in keys)
+        worst = 0.0
+        for k in keys:
+            r = sdt[k].grad
+            err = float((params[k].grad.detach().cpu().double() - r.double()).norm())
+            worst = max(worst, err / (float(r.norm()) + 1e-2 * gmax))
+            if dtype == torch.float32:
+                assert err <= 2e-4 * float(r.norm()) + 2e-5 * gmax, f"{k}: {err:.3e} vs {float(r.norm()):.3e}"
+        mine = torch.cat([params[k].grad.detach().double().cpu().reshape(-1) for k in keys])
+        refv = torch.cat([sdt[k].grad.double().reshape(-1) for k in keys])
+        cos = float(torch.dot(mine, refv) / (mine.norm() * refv.norm()))
+        assert cos > (0.99999 if dtype == torch.float32 else 0.98), f"gradient cosine {cos:.5f} (worst per-tensor {worst:.3e})"
+        if dtype == torch.float32:
+            for k, v in m.state_dict().items():
+                if k.endswith(("running_mean", "running_var")):
+                    assert rel(v, sdt[k]) < 1e-4, k
+    finally:
+        M.set_compute_dtype(torch.bfloat16)
