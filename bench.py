@@ -1,0 +1,387 @@
+"""Benchmark of the DS-GCN hot path (BASELINE.json): DS-GCN clips/sec, M=2, T=100, V=25, C=3.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--mode train|fwd] [--batch B] [--impl ours|reference]
+
+One "step" = one pass of the path over one synthetic batch: `train` = forward + loss + backward + SGD step of
+RecognizerGCN(DGSTGCN north-star config + GCNHead) on `--batch` clips per GPU (default 128 = videos_per_gpu of
+configs/_init_/lr_schedual.py:1-8, BASELINE configs[1]); `fwd` = eval forward.  N>1: one process per GPU under
+torchrun, batch sharded (weak scaling), gradient all-reduce over NCCL, per-rank BatchNorm statistics like the
+reference's DDP (broadcast_buffers=False, no SyncBN).
+
+Printed JSON line: see DESIGN.md "Measurement".  `value` = device-resident inputs, CUDA-graph replay;
+`e2e` = the public API (RecognizerGCN.train_step / forward) with host buffers: H2D of the batch from pinned memory and
+D2H of the loss inside the timed region.  `--impl reference` times the oracle port of the reference's CPU path
+(the reference itself is Python and cannot travel to the GPU box; oracle/ is the checker restatement) on a bounded
+sample, all host threads.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+NORTH_STAR = dict(gcn_type="dgphgcn1", gcn_ratio=0.125, gcn_node_attention=True, gcn_edge_attention=True, gcn_decompose=True,
+                  gcn_subset_wise=True, gcn_ctr="T", gcn_ada="T", tcn_type="dgmstcn",
+                  graph_cfg=dict(layout="nturgb+d", mode="random", num_filter=3, init_off=.04, init_std=.02),
+                  tcn_ms_cfg=[(3, 1), (3, 2), (3, 3), (3, 4), ("max", 3), "1x1"])
+M_, T_, V_, C_ = 2, 100, 25, 3
+NUM_CLASSES = 60
+SGD = dict(lr=0.1, momentum=0.9, weight_decay=5e-4, nesterov=True)     # configs/_init_/lr_schedual.py:11
+# stage-granular algorithmic elements per clip, forward; train = 3x (read x, read dy, write dx)
+ELEMS_PER_CLIP_FWD = 16.655e6
+
+
+def parse():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=20)
+    p.add_argument("--warmup", type=int, default=5)
+    p.add_argument("--mode", default="train", choices=["train", "fwd"])
+    p.add_argument("--batch", type=int, default=128, help="clips per GPU per step")
+    p.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    p.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
+    p.add_argument("--no-graph", action="store_true")
+    p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--ref-clips", type=int, default=4, help="clips per step of the CPU reference arm (bounded sample)")
+    return p.parse_args()
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference path (test infrastructure; the only place bench.py executes oracle/)
+# ----------------------------------------------------------------------------------------------------------------
+
+def cpu_reference(mode, clips, steps, warmup):
+    from oracle import dsgcn_oracle as O
+    torch.set_num_threads(os.cpu_count())
+    torch.manual_seed(0)
+    np.random.seed(0)
+    V = V_
+    # parameters with the reference's names/shapes and PyTorch default init, via the oracle's own table helpers
+    sd = _oracle_state(O)
+    O.randomize_state(sd, 1)
+    head_w = (torch.randn(NUM_CLASSES, 256) * 0.01).requires_grad_()
+    head_b = torch.zeros(NUM_CLASSES, requires_grad=True)
+    params = {k: v for k, v in sd.items() if v.is_floating_point() and not k.endswith(("running_mean", "running_var"))}
+    for v in params.values():
+        v.requires_grad_()
+    opt = torch.optim.SGD([v for k, v in params.items() if "conv2_se" not in k] + [head_w, head_b], **SGD)
+    x = torch.randn(clips, M_, T_, V, C_)
+    label = torch.randint(0, NUM_CLASSES, (clips,))
+
+    def step():
+        if mode == "fwd":
+            with torch.no_grad():
+                return O.dgstgcn_forward(x, sd, training=False)
+        feat = O.dgstgcn_forward(x, sd, training=True)
+        logits = O.gcn_head_forward(feat, {"fc_cls.weight": head_w, "fc_cls.bias": head_b})
+        loss = torch.nn.functional.cross_entropy(logits, label)
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        opt.step()
+        return loss
+
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / steps
+    return clips / dt, dt
+
+
+def _oracle_state(O):
+    """Random-init state dict with the reference layout (shapes from the oracle's plan; PyTorch conv default init scale)."""
+    import math
+    sd = {}
+    g = torch.Generator().manual_seed(0)
+
+    def conv(name, cout, cin, k=1):
+        bound = 1 / math.sqrt(cin * k)
+        sd[name + ".weight"] = (torch.rand(cout, cin, k, 1, generator=g) * 2 - 1) * bound
+        sd[name + ".bias"] = (torch.rand(cout, generator=g) * 2 - 1) * bound
+
+    def bn(name, c):
+        sd[name + ".weight"], sd[name + ".bias"] = torch.ones(c), torch.zeros(c)
+        sd[name + ".running_mean"], sd[name + ".running_var"] = torch.zeros(c), torch.ones(c)
+        sd[name + ".num_batches_tracked"] = torch.zeros((), dtype=torch.long)
+
+    bn("data_bn", V_ * C_)
+    for i, (cin, cout, stride, res) in enumerate(O.dgstgcn_plan()):
+        p = f"gcn.{i}.gcn."
+        R = int(0.125 * cout)
+        sd[p + "A"] = torch.randn(3, V_, V_, generator=g) * 0.02 + 0.04
+        sd[p + "alpha"], sd[p + "beta"] = torch.zeros(3), torch.zeros(3)
+        conv(p + "pre.0", 3 * R, cin); bn(p + "pre.1", 3 * R); conv(p + "post", cout, 3 * R)
+        conv(p + "conv1_se", 5 * R, cin); conv(p + "conv2_se", 5 * R, cin); conv(p + "conv1", 2 * R, cin); conv(p + "conv2", 2 * R, cin)
+        conv(p + "edge_linears", 15 * R, R)
+        if cin != cout:
+            conv(p + "down.0", cout, cin); bn(p + "down.1", cout)
+        bn(p + "bn", cout)
+        p = f"gcn.{i}.tcn."
+        sd[p + "add_coeff"] = torch.zeros(25)
+        mid = cout // 6
+        widths = [cout - 5 * mid] + [mid] * 5
+        for j, w in enumerate(widths):
+            if j == 5:
+                conv(p + "branches.5", w, cout)
+            else:
+                conv(p + f"branches.{j}.0", w, cout); bn(p + f"branches.{j}.1", w)
+                if j < 4:
+                    conv(p + f"branches.{j}.3.conv", w, w, 3)
+        bn(p + "transform.0", cout); conv(p + "transform.2", cout, cout); bn(p + "bn", cout)
+        if res == "conv":
+            conv(f"gcn.{i}.residual.conv", cout, cin); bn(f"gcn.{i}.residual.bn", cout)
+    return sd
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------------------------------------------
+
+class ClockSampler:
+    QUERY = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return None
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 3 + i and r[3 + i].lower().startswith("active") for r in self.rows)]
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None, reasons=reasons, samples=len(sm))
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    unit = "clips/s"
+    metric = f"DS-GCN {args.mode} clips/sec (M=2,T=100,V=25,C=3)"
+    workload = ("DS-GCN ntu60_xsub_3dkp joint training step (fwd+loss+bwd+SGD)" if args.mode == "train"
+                else "DS-GCN ntu60_xsub_3dkp joint eval forward")
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        val, dt = cpu_reference(args.mode, args.ref_clips, args.steps, args.warmup)
+        line = dict(impl="reference", metric=metric, value=val, unit=unit, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
+                    ms_per_step=dt * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
+                    config=dict(workload=workload, clips_per_step=args.ref_clips, device="cpu"),
+                    cpu_baseline=dict(value=val, unit=unit, cores=os.cpu_count(), kind="port",
+                                      sample=f"{args.ref_clips} clips/step x {args.steps} steps, oracle port of the reference CPU path, torch {torch.__version__}"),
+                    e2e=dict(value=val, unit=unit, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+        print(json.dumps(line))
+        return
+
+    import dsgcn_b200
+    from dsgcn_b200 import _lib as L
+    from dsgcn_b200 import modules as Mod
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        torch.distributed.init_process_group("nccl", device_id=dev)
+    dtype = torch.bfloat16 if args.dtype == "bf16" else torch.float32
+    Mod.set_compute_dtype(dtype)
+    torch.manual_seed(1234 + rank)
+    np.random.seed(0)
+    model = dsgcn_b200.RecognizerGCN(backbone=dict(type="DGSTGCN", **NORTH_STAR),
+                                    cls_head=dict(type="GCNHead", num_classes=NUM_CLASSES, in_channels=256)).to(dev)
+    with torch.no_grad():       # make the dynamic branches live (zero at init: SURVEY.md §0 item 6)
+        for n_, p in model.named_parameters():
+            if n_.rsplit(".", 1)[-1] in ("alpha", "beta", "add_coeff"):
+                p.normal_(0, 0.1)
+    if world > 1:
+        for p in model.parameters():
+            torch.distributed.broadcast(p.data, 0)
+    B = args.batch
+    train = args.mode == "train"
+    model.train(train)
+    params = [p for n_, p in model.named_parameters() if "conv2_se" not in n_]      # never receive gradients (gcn.py:2253-2254)
+    opt = torch.optim.SGD(params, foreach=True, **SGD) if train else None
+
+    # synthetic NTU-shaped data: a pool of pinned host batches (e2e) and device-resident batches (value)
+    g = torch.Generator().manual_seed(rank)
+    host_x = [torch.randn(B, 1, M_, T_, V_, C_, generator=g).pin_memory() for _ in range(2)]
+    host_y = [torch.randint(0, NUM_CLASSES, (B, 1), generator=g).pin_memory() for _ in range(2)]
+    dev_x = [h.to(dev) for h in host_x]
+    dev_y = [h.to(dev) for h in host_y]
+    sx, sy = dev_x[0].clone(), dev_y[0].clone()
+
+    def allreduce_grads():
+        if world > 1:
+            flat = [p.grad for p in params if p.grad is not None]
+            buf = torch._utils._flatten_dense_tensors(flat)
+            torch.distributed.all_reduce(buf)
+            buf.div_(world)
+            for gsrc, gdst in zip(torch._utils._unflatten_dense_tensors(buf, flat), flat):
+                gdst.copy_(gsrc)
+
+    def device_step(x, y):
+        if not train:
+            with torch.no_grad():
+                feat = model.extract_feat(x[:, 0])
+                return model.cls_head(feat)
+        losses = model(x, y, return_loss=True)
+        loss = losses["loss_cls"]
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        allreduce_grads()
+        opt.step()
+        return loss
+
+    # ---- warm-up (eager), then CUDA-graph capture of one whole step on static buffers
+    L.launch_count = 0
+    for i in range(max(args.warmup, 3)):
+        out = device_step(dev_x[i % 2], dev_y[i % 2])
+    torch.cuda.synchronize()
+    l0 = L.launch_count
+    device_step(sx, sy)
+    launches_per_step = L.launch_count - l0
+    graph = None
+    if not args.no_graph and world == 1:
+        try:
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                static_out = device_step(sx, sy)
+            graph.replay()
+            torch.cuda.synchronize()
+        except Exception as e:   # report, fall back to eager launches (still our kernels)
+            print(f"[bench] CUDA graph capture failed ({type(e).__name__}: {e}); timing eager launches", file=sys.stderr)
+            graph = None
+            torch.cuda.synchronize()
+
+    def run_step(i):
+        if graph is not None:
+            sx.copy_(dev_x[i % 2], non_blocking=True)       # device-to-device refresh of the static input (inputs differ per step)
+            sy.copy_(dev_y[i % 2], non_blocking=True)
+            graph.replay()
+        else:
+            device_step(dev_x[i % 2], dev_y[i % 2])
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(3):
+        run_step(i)
+    sampler = ClockSampler(local) if rank == 0 else None
+    barrier()
+    if sampler:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        run_step(i)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1) / args.steps
+    clocks = sampler.stop() if sampler else None
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        ms = float(t.item())
+    value = world * B / (ms * 1e-3)
+
+    # ---- e2e: public API with host buffers (H2D of the batch from pinned memory, D2H of the loss / scores)
+    def e2e_step(i):
+        x = host_x[i % 2].to(dev, non_blocking=True)
+        y = host_y[i % 2].to(dev, non_blocking=True)
+        if train:
+            out = model.train_step(dict(keypoint=x, label=y), opt)       # .item() of the loss inside = D2H
+            opt.zero_grad(set_to_none=True)
+            out["loss"].backward()
+            allreduce_grads()
+            opt.step()
+            return out["log_vars"]["loss"]
+        with torch.no_grad():
+            return model(x, return_loss=False)                           # numpy scores = D2H
+    for i in range(2):
+        e2e_step(i)
+    barrier()
+    t0 = time.perf_counter()
+    n_e2e = max(3, min(args.steps, 10))
+    for i in range(n_e2e):
+        e2e_step(i)
+    barrier()
+    e2e_ms = (time.perf_counter() - t0) / n_e2e * 1e3
+    if world > 1:
+        t = torch.tensor([e2e_ms], device=dev)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+    h2d = host_x[0].numel() * 4 + host_y[0].numel() * 8
+    d2h = 4 if train else B * NUM_CLASSES * 4
+
+    if rank != 0:
+        return
+    # ---- roofline leg: per-ABI-call CUDA events over extra eager steps (same shapes), dominant kernel
+    L.profile = []
+    for i in range(2):
+        device_step(dev_x[i % 2], dev_y[i % 2])
+    torch.cuda.synchronize()
+    prof, L.profile = L.profile, None
+    agg = {}
+    for name, nbytes, a, b in prof:
+        d = agg.setdefault(name, [0.0, 0, 0])
+        d[0] += a.elapsed_time(b)
+        d[1] += nbytes
+        d[2] += 1
+    total_ms = sum(v[0] for v in agg.values())
+    top = max(agg, key=lambda k: agg[k][0])
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = peaks.get("hbm_gbs", 6650.0)
+    achieved = agg[top][1] / (agg[top][0] * 1e-3) / 1e9
+    roofline = dict(bound="hbm", kernel=top, achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak, traffic=None,
+                    peak_source="MEASURED_PEAKS.json (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
+                    share_of_step=agg[top][0] / total_ms, launches_per_step=agg[top][2] // 2,
+                    per_kernel_ms_per_step={k: round(v[0] / 2, 4) for k, v in sorted(agg.items(), key=lambda kv: -kv[1][0])},
+                    per_kernel_gbs={k: round(v[1] / (v[0] * 1e-3) / 1e9, 1) for k, v in agg.items() if v[1] > 0 and v[0] > 0},
+                    step_algorithmic_gbs=ELEMS_PER_CLIP_FWD * (3 if train else 1) * (2 if dtype == torch.bfloat16 else 4) * B / (ms * 1e-3) / 1e9)
+    cpu = None
+    if not args.no_cpu_baseline:
+        cval, cdt = cpu_reference(args.mode, args.ref_clips, 3, 1)
+        cpu = dict(value=cval, unit=unit, cores=os.cpu_count(), kind="port",
+                   sample=f"{args.ref_clips} clips/step, 3 steps after 1 warm-up, oracle port of the reference path ({args.mode}), torch {torch.__version__} CPU")
+    line = dict(metric=metric, value=value, unit=unit, n_gpus=world, steps=args.steps, warmup=args.warmup, ms_per_step=ms,
+                higher_is_better=True, scaling="weak", vs_baseline=None, dtype=args.dtype, data="synthetic",
+                config=dict(workload=workload, clips_per_gpu=B, M=M_, T=T_, V=V_, C=C_, parallelism=f"dp{world}", cuda_graph=graph is not None,
+                            cache="inputs + activations per step (~GBs) exceed the 126 MB L2; two input batches alternate"),
+                e2e=dict(value=world * B / (e2e_ms * 1e-3), unit=unit, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, ms_per_step=e2e_ms),
+                gpu_launches=launches_per_step * args.steps, abi_calls_per_step=launches_per_step, clocks=clocks, roofline=roofline, cpu_baseline=cpu)
+    print(json.dumps(line))
+
+
+if __name__ == "__main__":
+    main()

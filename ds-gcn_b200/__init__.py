@@ -9,3 +9,6 @@ from . import functional, graph, modules  # noqa: F401,E402
 from .graph import Graph  # noqa: F401,E402
 from .modules import (DGBlock, DGSTGCN, STGCN, STGCNBlock, dgmstcn, dgphgcn1, get_compute_dtype, mstcn,  # noqa: F401,E402
                       set_compute_dtype, unit_gcn, unit_tcn)
+from . import recognizer  # noqa: F401,E402
+from .recognizer import (BACKBONES, HEADS, LOSSES, MODELS, RECOGNIZERS, CrossEntropyLoss, GCNHead, RecognizerGCN,  # noqa: F401,E402
+                         build_backbone, build_head, build_loss, build_model, build_recognizer)

@@ -181,9 +181,19 @@ def dt(t_or_dtype):
         raise DsgError(f"unsupported activation dtype {d} (fp32 or bf16)")
 
 
-def call(name, *args):
+profile = None        # when a list: (name, algorithmic_bytes, start_event, end_event) per ABI call (bench.py roofline leg)
+
+
+def call(name, *args, nbytes=0):
     global launch_count
-    rc = getattr(lib(), name)(*args)
+    if profile is not None and _is_device:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = getattr(lib(), name)(*args)
+        e1.record()
+        profile.append((name, nbytes, e0, e1))
+    else:
+        rc = getattr(lib(), name)(*args)
     if rc != 0:
         raise DsgError(lib().dsg_last_error().decode())
     launch_count += 1

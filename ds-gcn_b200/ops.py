@@ -111,7 +111,15 @@ def conv_gemm(src, W, N, out, *, n_samples, T_in, T_out, Vin, ws=None, bias=None
     if partner is not None:
         assert partner.dtype == src.dtype
         a.partner, a.ld_partner = L.ptr(partner), _ld(partner)
-    L.call("dsg_conv_gemm", C.byref(a), L.stream())
+    es = out.element_size()
+    rows_out = n_samples * T_out * (Vin + int(ext_in) - int(contract_ext))
+    nbytes = n_samples * T_in * Vin * K * es * (2 if src.x2 is not None else 1) + rows_out * N * es
+    for extra in (add, add2, partner):
+        if extra is not None:
+            nbytes += rows_out * N * es
+    if mask is not None:
+        nbytes += rows_out * N * es
+    L.call("dsg_conv_gemm", C.byref(a), L.stream(), nbytes=nbytes)
     return out
 
 
@@ -130,7 +138,10 @@ def conv_wgrad(A, B, dW, *, n_samples, T_in, T_out, Vin, ws=None, db=None, taps=
     a.db = L.ptr(_f32(db))
     a.taps, a.tap_step, a.tap_off, a.t_mul, a.t_div = taps, tap_step, tap_off, t_mul, t_div
     a.n_samples, a.T_in, a.T_out, a.Vin, a.ext_in = n_samples, T_in, T_out, Vin, int(ext_in)
-    L.call("dsg_conv_wgrad", C.byref(a), L.stream())
+    es = A.x1.element_size()
+    rows_out = n_samples * T_out * (Vin + int(ext_in))
+    nbytes = n_samples * T_in * Vin * a.K * es * (2 if A.x2 is not None else 1) + rows_out * a.N * es * (2 if B.x2 is not None else 1)
+    L.call("dsg_conv_wgrad", C.byref(a), L.stream(), nbytes=nbytes)
 
 
 def bn_job(mode, Cn, *, sum=None, sq=None, count=1.0, gamma=None, beta=None, running_mean=None, running_var=None,
@@ -206,7 +217,14 @@ def graph_agg(src, out, *, mode, n_samples, T, V, KC, adyn=None, A=None, Ksub=0,
         a.stat_sum, a.stat_sq = L.ptr(stat_sum), L.ptr(stat_sq)
     if partner is not None:
         a.partner, a.ld_partner = L.ptr(partner), _ld(partner)
-    L.call("dsg_graph_agg", C.byref(a), L.stream())
+    es = out.element_size()
+    rows = n_samples * T * V
+    nbytes = rows * src.C * es * (2 if src.x2 is not None else 1) + rows * out.shape[-1] * es
+    if adyn is not None:
+        nbytes += adyn.numel() * es
+    if mask is not None:
+        nbytes += rows * out.shape[-1] * es
+    L.call("dsg_graph_agg", C.byref(a), L.stream(), nbytes=nbytes)
     return out
 
 
@@ -237,7 +255,15 @@ def pointwise(src, out, *, out_dtype=None, mask=None, stat_sum=None, stat_sq=Non
         a.stat_sum, a.stat_sq = L.ptr(stat_sum), L.ptr(stat_sq)
     if partner is not None:
         a.partner, a.ld_partner, a.partner_dtype = L.ptr(partner), _ld(partner), L.dt(partner)
-    L.call("dsg_pointwise", C.byref(a), L.stream())
+    es = src.x1.element_size()
+    nbytes = a.rows * a.C * es * (2 if src.x2 is not None else 1)
+    if out is not None:
+        nbytes += a.rows * a.C * out.element_size()
+    if mask is not None:
+        nbytes += a.rows * a.C * es
+    if partner is not None:
+        nbytes += a.rows * a.C * partner.element_size()
+    L.call("dsg_pointwise", C.byref(a), L.stream(), nbytes=nbytes)
     return out
 
 
