@@ -256,25 +256,32 @@ def main():
         opt.step()
         return loss
 
-    # ---- warm-up (eager), then CUDA-graph capture of one whole step on static buffers
+    # ---- warm-up (eager, on a side stream so no autograd node is tied to the default stream), then CUDA-graph
+    #      capture of one whole step on static buffers
     L.launch_count = 0
-    for i in range(max(args.warmup, 3)):
-        out = device_step(dev_x[i % 2], dev_y[i % 2])
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for i in range(max(args.warmup, 3)):
+            device_step(dev_x[i % 2], dev_y[i % 2])
+        torch.cuda.synchronize()
+        l0 = L.launch_count
+        device_step(sx, sy)
+        launches_per_step = L.launch_count - l0
+    torch.cuda.current_stream().wait_stream(side)
     torch.cuda.synchronize()
-    l0 = L.launch_count
-    device_step(sx, sy)
-    launches_per_step = L.launch_count - l0
     graph = None
     if not args.no_graph and world == 1:
         try:
-            torch.cuda.synchronize()
             graph = torch.cuda.CUDAGraph()
+            if opt is not None:
+                opt.zero_grad(set_to_none=True)
             with torch.cuda.graph(graph):
-                static_out = device_step(sx, sy)
+                device_step(sx, sy)
             graph.replay()
             torch.cuda.synchronize()
         except Exception as e:   # report, fall back to eager launches (still our kernels)
-            print(f"[bench] CUDA graph capture failed ({type(e).__name__}: {e}); timing eager launches", file=sys.stderr)
+            print(f"[bench] CUDA graph capture failed ({type(e).__name__}: {str(e)[:300]}); timing eager launches", file=sys.stderr)
             graph = None
             torch.cuda.synchronize()
 
