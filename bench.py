@@ -356,11 +356,16 @@ def main():
     torch.cuda.synchronize()
     prof, L.profile = L.profile, None
     agg = {}
-    for name, nbytes, a, b in prof:
+    for name, nbytes, a, b, _tag in prof:
         d = agg.setdefault(name, [0.0, 0, 0])
         d[0] += a.elapsed_time(b)
         d[1] += nbytes
         d[2] += 1
+    if os.environ.get("DSG_BENCH_DUMP"):       # per-call dump for kernel work (name, ms, GB/s, shape tag)
+        with open(os.environ["DSG_BENCH_DUMP"], "w") as fh:
+            for name, nbytes, a_, b_, tag in prof[len(prof) // 2:]:
+                t_ = a_.elapsed_time(b_)
+                fh.write(json.dumps(dict(name=name, ms=round(t_, 4), gbs=round(nbytes / (t_ * 1e-3) / 1e9, 1) if t_ > 0 else 0, tag=tag)) + "\n")
     total_ms = sum(v[0] for v in agg.values())
     top = max(agg, key=lambda k: agg[k][0])
     peaks = {}

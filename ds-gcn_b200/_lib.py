@@ -80,6 +80,17 @@ class MsCombineArgs(C.Structure):
                 ("b_raw", vp), ("ld_b", c_ll), ("e_sum", vp), ("e_sq", vp), ("dadd_coeff", vp)]
 
 
+class MsBranch(C.Structure):
+    _fields_ = [("kind", c_int), ("lo", c_int), ("hi", c_int), ("dilation", c_int), ("W", vp), ("bias", vp), ("dW", vp), ("db", vp)]
+
+
+class MsTemporalArgs(C.Structure):
+    _fields_ = [("n_samples", c_int), ("T_in", c_int), ("T_out", c_int), ("stride", c_int), ("V", c_int), ("has_ext", c_int),
+                ("C", c_int), ("n_branches", c_int), ("br", MsBranch * 8), ("b", ActSrc), ("add_coeff", vp),
+                ("feat", vp), ("ld_feat", c_ll), ("oglob", vp), ("stat_sum", vp), ("stat_sq", vp),
+                ("dfeat", ActSrc), ("e", vp), ("ld_e", c_ll), ("e_sum", vp), ("e_sq", vp), ("dadd_coeff", vp)]
+
+
 class PointwiseArgs(C.Structure):
     _fields_ = [("src", ActSrc), ("dtype", c_int), ("C", c_int), ("rows", c_ll), ("out", vp), ("ld_out", c_ll),
                 ("out_dtype", c_int), ("has_mask", c_int), ("mask", ActSrc),
@@ -100,6 +111,10 @@ EXPORTS = {
     "dsg_ms_combine_fwd": (c_int, [C.POINTER(MsCombineArgs), vp]),
     "dsg_ms_combine_bwd": (c_int, [C.POINTER(MsCombineArgs), vp]),
     "dsg_pointwise": (c_int, [C.POINTER(PointwiseArgs), vp]),
+    "dsg_ms_temporal_supported": (c_int, [C.POINTER(MsTemporalArgs)]),
+    "dsg_ms_temporal_fwd": (c_int, [C.POINTER(MsTemporalArgs), vp]),
+    "dsg_ms_temporal_bwd_data": (c_int, [C.POINTER(MsTemporalArgs), vp]),
+    "dsg_ms_temporal_bwd_weight": (c_int, [C.POINTER(MsTemporalArgs), vp]),
     "dsg_sgd_step": (c_int, [vp, vp, vp, c_ll, c_f, c_f, c_f, c_int, c_f, vp]),
     "dsg_last_error": (C.c_char_p, []),
     "dsg_abi_version": (c_int, []),
@@ -184,14 +199,14 @@ def dt(t_or_dtype):
 profile = None        # when a list: (name, algorithmic_bytes, start_event, end_event) per ABI call (bench.py roofline leg)
 
 
-def call(name, *args, nbytes=0):
+def call(name, *args, nbytes=0, tag=None):
     global launch_count
     if profile is not None and _is_device:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         rc = getattr(lib(), name)(*args)
         e1.record()
-        profile.append((name, nbytes, e0, e1))
+        profile.append((name, nbytes, e0, e1, tag))
     else:
         rc = getattr(lib(), name)(*args)
     if rc != 0:

@@ -1,10 +1,13 @@
 // extern "C" entry points of libdsgcn_b200.so (see include/dsgcn_b200.h).
 #include "dsg_common.h"
 #include "conv_gemm.cuh"
+#include "conv_gemm_tc.cuh"
+#include "ms_temporal_tc.cuh"
 #include "graph_agg.cuh"
 #include "topology.cuh"
 #include "misc.cuh"
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 static thread_local char g_err[512] = "";
@@ -16,6 +19,13 @@ static int fail(const char* where, const char* msg) {
 #define DSG_RET(where, expr) do { const char* e__ = (expr); return e__ ? fail(where, e__) : 0; } while (0)
 
 static bool dtype_ok(int d) { return d == DSG_F32 || d == DSG_BF16; }
+
+// DSG_DISABLE_TC=1 routes bf16 GEMMs to the CUDA-core engine (debugging aid; both engines are sm_100a device code)
+static bool tc_enabled() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("DSG_DISABLE_TC"); v = (e && e[0] == '1') ? 0 : 1; }
+    return v == 1;
+}
 
 extern "C" {
 
@@ -33,6 +43,14 @@ int dsg_conv_gemm(const dsg_conv_gemm_args* a, void* stream) {
     if (!a || !dtype_ok(a->dtype)) return fail("dsg_conv_gemm", "bad arguments");
     if (a->taps < 1 || a->t_div < 1 || a->Vin < 1 || a->K < 1) return fail("dsg_conv_gemm", "bad shape");
     if ((a->stat_sum == nullptr) != (a->stat_sq == nullptr)) return fail("dsg_conv_gemm", "stat_sum and stat_sq go together");
+#ifndef DSG_EMU
+    if (a->dtype == DSG_BF16 && tc_enabled()) {      // tcgen05 engine (sm_100a); shapes it does not take fall through
+        bool handled = false;
+        const char* e = dsg::tc::launch_conv_gemm_tc(*a, (dsg_stream_t)stream, &handled);
+        if (e) return fail("dsg_conv_gemm", e);
+        if (handled) return 0;
+    }
+#endif
     if (a->dtype == DSG_BF16) DSG_RET("dsg_conv_gemm", dsg::launch_conv_gemm<bf16>(*a, (dsg_stream_t)stream));
     DSG_RET("dsg_conv_gemm", dsg::launch_conv_gemm<float>(*a, (dsg_stream_t)stream));
 }
@@ -40,6 +58,14 @@ int dsg_conv_gemm(const dsg_conv_gemm_args* a, void* stream) {
 int dsg_conv_wgrad(const dsg_conv_wgrad_args* a, void* stream) {
     if (!a || !dtype_ok(a->dtype)) return fail("dsg_conv_wgrad", "bad arguments");
     if (a->taps < 1 || a->t_div < 1 || a->Vin < 1 || a->K < 1 || a->N < 1) return fail("dsg_conv_wgrad", "bad shape");
+#ifndef DSG_EMU
+    if (a->dtype == DSG_BF16 && tc_enabled()) {
+        bool handled = false;
+        const char* e = dsg::tc::launch_conv_wgrad_tc(*a, (dsg_stream_t)stream, &handled);
+        if (e) return fail("dsg_conv_wgrad", e);
+        if (handled) return 0;
+    }
+#endif
     if (a->dtype == DSG_BF16) DSG_RET("dsg_conv_wgrad", dsg::launch_conv_wgrad<bf16>(*a, (dsg_stream_t)stream));
     DSG_RET("dsg_conv_wgrad", dsg::launch_conv_wgrad<float>(*a, (dsg_stream_t)stream));
 }
@@ -126,10 +152,55 @@ int dsg_ms_combine_bwd(const dsg_ms_combine_args* a, void* stream) {
     return 0;
 }
 
+int dsg_ms_temporal_supported(const dsg_ms_temporal_args* a) {
+#ifdef DSG_EMU
+    (void)a;
+    return 0;
+#else
+    if (!a || !tc_enabled()) return 0;
+    return (dsg::tc::ms_host_geom(*a, a->V + a->has_ext).ok && dsg::tc::ms_args_ok(*a)) ? 1 : 0;
+#endif
+}
+
+int dsg_ms_temporal_fwd(const dsg_ms_temporal_args* a, void* stream) {
+#ifdef DSG_EMU
+    (void)a; (void)stream;
+    return fail("dsg_ms_temporal_fwd", "tcgen05 kernel: not available in the host-side simulator build");
+#else
+    if (!a) return fail("dsg_ms_temporal_fwd", "bad arguments");
+    DSG_RET("dsg_ms_temporal_fwd", dsg::tc::launch_ms_temporal_fwd(*a, (dsg_stream_t)stream));
+#endif
+}
+
+int dsg_ms_temporal_bwd_data(const dsg_ms_temporal_args* a, void* stream) {
+#ifdef DSG_EMU
+    (void)a; (void)stream;
+    return fail("dsg_ms_temporal_bwd_data", "tcgen05 kernel: not available in the host-side simulator build");
+#else
+    if (!a) return fail("dsg_ms_temporal_bwd_data", "bad arguments");
+    DSG_RET("dsg_ms_temporal_bwd_data", dsg::tc::launch_ms_temporal_bwd_data(*a, (dsg_stream_t)stream));
+#endif
+}
+
+int dsg_ms_temporal_bwd_weight(const dsg_ms_temporal_args* a, void* stream) {
+#ifdef DSG_EMU
+    (void)a; (void)stream;
+    return fail("dsg_ms_temporal_bwd_weight", "tcgen05 kernel: not available in the host-side simulator build");
+#else
+    if (!a) return fail("dsg_ms_temporal_bwd_weight", "bad arguments");
+    DSG_RET("dsg_ms_temporal_bwd_weight", dsg::tc::launch_ms_temporal_bwd_weight(*a, (dsg_stream_t)stream));
+#endif
+}
+
 int dsg_pointwise(const dsg_pointwise_args* a, void* stream) {
     if (!a || !dtype_ok(a->dtype) || !dtype_ok(a->out_dtype)) return fail("dsg_pointwise", "bad arguments");
     if ((a->stat_sum == nullptr) != (a->stat_sq == nullptr)) return fail("dsg_pointwise", "stat_sum and stat_sq go together");
     if (a->rows <= 0 || a->C <= 0) return 0;
+    if (dsg::pointwise_vec_ok(*a)) {
+        dim3 gv((unsigned)((a->rows + dsg::PV_ROWS - 1) / dsg::PV_ROWS), (a->C + dsg::PW_CT - 1) / dsg::PW_CT);
+        dsg_launch(dsg::pointwise_vec_kernel, gv, dim3(dsg::PW_THREADS), 0, (dsg_stream_t)stream, *a);
+        DSG_RET("dsg_pointwise", dsg_launch_error());
+    }
     dim3 grid((unsigned)((a->rows + dsg::PW_ROWS - 1) / dsg::PW_ROWS), (a->C + dsg::PW_CT - 1) / dsg::PW_CT);
     if (a->dtype == DSG_BF16) dsg_launch(dsg::pointwise_kernel<bf16>, grid, dim3(dsg::PW_THREADS), 0, (dsg_stream_t)stream, *a);
     else dsg_launch(dsg::pointwise_kernel<float>, grid, dim3(dsg::PW_THREADS), 0, (dsg_stream_t)stream, *a);

@@ -26,6 +26,58 @@ DSG_D long long src_frame(const FrameMap& m, long long f, int tap) {
     return n * m.T_in + ti;
 }
 
+// Fused epilogue tail shared by the CUDA-core and the tcgen05 kernels: the fp32 accumulator tile is staged in
+// shared memory (Cs[row][col], pitch ldc); thread (c = tid % BN, row group = tid / BN) walks output rows.
+template <class T, int BN>
+DSG_D void gemm_tail(const dsg_conv_gemm_args& a, const float* Cs, int ldc, float* s_red /* [2][THREADS/BN][BN] */,
+                     long long f0, int Fr, int rpf, int n0, long long n_frames) {
+    constexpr int RG = CG_THREADS / BN;
+    const int tid = threadIdx.x;
+    const int Vout = rpf - a.contract_ext;
+    const int c = tid % BN, rgrp = tid / BN;
+    const int cg = n0 + c;
+    float s1 = 0.f, s2 = 0.f;
+    if (cg < a.N) {
+        const float bias = a.bias ? a.bias[cg] : 0.f;
+        const float inv_ext = a.contract_ext ? 1.f / (float)(rpf - 1) : 0.f;
+        T* out = reinterpret_cast<T*>(a.out);
+        for (int lr = rgrp; lr < Fr * Vout; lr += RG) {
+            int fl = lr / Vout, j = lr - fl * Vout;
+            long long f = f0 + fl;
+            if (f >= n_frames) break;
+            float v = Cs[(fl * rpf + j) * ldc + c];
+            if (a.contract_ext) v += Cs[(fl * rpf + rpf - 1) * ldc + c] * inv_ext;
+            v += bias;
+            long long orow = f * Vout + j;
+            if (a.add) v += ldf<T>(reinterpret_cast<const T*>(a.add) + orow * a.ld_add + cg);
+            if (a.add2) v += ldf<T>(reinterpret_cast<const T*>(a.add2) + orow * a.ld_add2 + cg);
+            if (a.bcast) {
+                long long n = f / a.T_out;
+                v += a.bcast[(n * Vout + j) * a.N + cg] * a.bcast_scale;
+            }
+            if (a.has_mask && !(act_value<T>(a.mask, orow, cg) > 0.f)) v = 0.f;
+            if (a.stat_sum) {
+                float p = a.partner ? ldf<T>(reinterpret_cast<const T*>(a.partner) + orow * a.ld_partner + cg) : v;
+                s1 += v;
+                s2 += v * p;
+            }
+            stf<T>(out + orow * a.ld_out + cg, v);
+        }
+    }
+    if (a.stat_sum) {
+        s_red[(0 * RG + rgrp) * BN + c] = s1;
+        s_red[(1 * RG + rgrp) * BN + c] = s2;
+        __syncthreads();
+        if (tid < BN && n0 + tid < a.N) {
+            float t1 = 0.f, t2 = 0.f;
+#pragma unroll
+            for (int g = 0; g < RG; ++g) { t1 += s_red[(0 * RG + g) * BN + tid]; t2 += s_red[(1 * RG + g) * BN + tid]; }
+            atomicAdd(a.stat_sum + n0 + tid, (double)t1);
+            atomicAdd(a.stat_sq + n0 + tid, (double)t2);
+        }
+    }
+}
+
 template <class T>
 __global__ void __launch_bounds__(CG_THREADS) conv_gemm_kernel(dsg_conv_gemm_args a) {
     // shared memory: operand chunks, re-used as the fp32 output staging tile in the epilogue
@@ -119,48 +171,7 @@ __global__ void __launch_bounds__(CG_THREADS) conv_gemm_kernel(dsg_conv_gemm_arg
         for (int j = 0; j < 4; ++j) Cs[(ty * 8 + i) * (CG_BN + 1) + tx * 4 + j] = acc[i][j];
     __syncthreads();
 
-    const int Vout = rpf - a.contract_ext;
-    const int c = tid % CG_BN, rgrp = tid / CG_BN;     // 4 row groups
-    const int cg = n0 + c;
-    float s1 = 0.f, s2 = 0.f;
-    if (cg < a.N) {
-        const float bias = a.bias ? a.bias[cg] : 0.f;
-        const float inv_ext = a.contract_ext ? 1.f / (float)(rpf - 1) : 0.f;
-        T* out = reinterpret_cast<T*>(a.out);
-        for (int lr = rgrp; lr < Fr * Vout; lr += CG_THREADS / CG_BN) {
-            int fl = lr / Vout, j = lr - fl * Vout;
-            long long f = f0 + fl;
-            if (f >= n_frames) break;
-            float v = Cs[(fl * rpf + j) * (CG_BN + 1) + c];
-            if (a.contract_ext) v += Cs[(fl * rpf + rpf - 1) * (CG_BN + 1) + c] * inv_ext;
-            v += bias;
-            long long orow = f * Vout + j;
-            if (a.add) v += ldf<T>(reinterpret_cast<const T*>(a.add) + orow * a.ld_add + cg);
-            if (a.add2) v += ldf<T>(reinterpret_cast<const T*>(a.add2) + orow * a.ld_add2 + cg);
-            if (a.bcast) {
-                long long n = f / a.T_out;
-                v += a.bcast[(n * Vout + j) * a.N + cg] * a.bcast_scale;
-            }
-            if (a.has_mask && !(act_value<T>(a.mask, orow, cg) > 0.f)) v = 0.f;
-            if (a.stat_sum) {
-                float p = a.partner ? ldf<T>(reinterpret_cast<const T*>(a.partner) + orow * a.ld_partner + cg) : v;
-                s1 += v;
-                s2 += v * p;
-            }
-            stf<T>(out + orow * a.ld_out + cg, v);
-        }
-    }
-    if (a.stat_sum) {
-        s_red[0][rgrp][c] = s1;
-        s_red[1][rgrp][c] = s2;
-        __syncthreads();
-        if (tid < CG_BN && n0 + tid < a.N) {
-            float t1 = s_red[0][0][tid] + s_red[0][1][tid] + s_red[0][2][tid] + s_red[0][3][tid];
-            float t2 = s_red[1][0][tid] + s_red[1][1][tid] + s_red[1][2][tid] + s_red[1][3][tid];
-            atomicAdd(a.stat_sum + n0 + tid, (double)t1);
-            atomicAdd(a.stat_sq + n0 + tid, (double)t2);
-        }
-    }
+    gemm_tail<T, CG_BN>(a, Cs, CG_BN + 1, &s_red[0][0][0], f0, Fr, rpf, n0, n_frames);
 }
 
 // ---------------------------------------------------------------------------------------------

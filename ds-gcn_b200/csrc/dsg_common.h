@@ -118,3 +118,68 @@ static inline bool act_src_vec4_ok(const ActSrc& s, int elem_bytes) {
     for (int i = 0; i < 4; ++i) if (cs[i]) ok = ok && ((uintptr_t)cs[i] % 16 == 0);
     return ok;
 }
+
+// ---- 8-channel (16-byte) vector helpers for bf16 activations -----------------------------------
+DSG_D void unpack8(const uint4& u, float* v) {
+    v[0] = __uint_as_float(u.x << 16); v[1] = __uint_as_float(u.x & 0xffff0000u);
+    v[2] = __uint_as_float(u.y << 16); v[3] = __uint_as_float(u.y & 0xffff0000u);
+    v[4] = __uint_as_float(u.z << 16); v[5] = __uint_as_float(u.z & 0xffff0000u);
+    v[6] = __uint_as_float(u.w << 16); v[7] = __uint_as_float(u.w & 0xffff0000u);
+}
+DSG_D uint4 pack8(const float* v) {
+    uint4 u;
+    u.x = dsg_pack_bf16x2(v[0], v[1]); u.y = dsg_pack_bf16x2(v[2], v[3]);
+    u.z = dsg_pack_bf16x2(v[4], v[5]); u.w = dsg_pack_bf16x2(v[6], v[7]);
+    return u;
+}
+DSG_D void load8f(const float* p, float* v, float dflt) {
+    if (p) {
+        float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = dflt;
+    }
+}
+// register-resident coefficients of an activation source for one 8-channel chunk
+struct Act8 {
+    float a1[8], b[8], a2[8];     // b = b1 + b2
+    const bf16* x1; const bf16* x2; long long ld1, ld2; int relu;
+    DSG_D void init(const ActSrc& s, int c) {
+        float t[8];
+        load8f(s.a1 ? s.a1 + c : nullptr, a1, 1.f);
+        load8f(s.b1 ? s.b1 + c : nullptr, b, 0.f);
+        load8f(s.b2 ? s.b2 + c : nullptr, t, 0.f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) b[j] += t[j];
+        load8f(s.a2 ? s.a2 + c : nullptr, a2, 1.f);
+        x1 = reinterpret_cast<const bf16*>(s.x1) + c;
+        x2 = s.x2 ? reinterpret_cast<const bf16*>(s.x2) + c : nullptr;
+        ld1 = s.ld1; ld2 = s.ld2; relu = s.relu;
+    }
+    DSG_D void eval(long long r, float* v) const {
+        float t[8];
+        unpack8(*reinterpret_cast<const uint4*>(x1 + r * ld1), t);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = fmaf(t[j], a1[j], b[j]);
+        if (x2) {
+            unpack8(*reinterpret_cast<const uint4*>(x2 + r * ld2), t);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = fmaf(t[j], a2[j], v[j]);
+        }
+        if (relu) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
+        }
+    }
+};
+
+static inline bool act8_ok(const ActSrc& s) {
+    bool ok = ((uintptr_t)s.x1 % 16 == 0) && (s.ld1 % 8 == 0);
+    if (s.x2) ok = ok && ((uintptr_t)s.x2 % 16 == 0) && (s.ld2 % 8 == 0);
+    const float* cs[4] = {s.a1, s.b1, s.a2, s.b2};
+    for (int i = 0; i < 4; ++i) if (cs[i]) ok = ok && ((uintptr_t)cs[i] % 16 == 0);
+    return ok;
+}
+
+

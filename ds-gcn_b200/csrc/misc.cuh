@@ -117,6 +117,65 @@ __global__ void __launch_bounds__(PW_THREADS) pointwise_kernel(dsg_pointwise_arg
     }
 }
 
+// Vectorised fast path (bf16 in / bf16 out, everything 16-byte aligned, C % 8 == 0): a thread owns one 8-channel
+// chunk (coefficients live in registers) and walks rows; 8 consecutive threads cover 64 channels = 128 B per row.
+constexpr int PV_ROWS = 256;     // rows per CTA
+__global__ void __launch_bounds__(PW_THREADS) pointwise_vec_kernel(dsg_pointwise_args a) {
+    DSG_SHARED float s_red[2][PW_THREADS / 8][PW_CT];
+    const int tid = threadIdx.x, cc = tid & 7, rl = tid >> 3;         // 8 chunks x 32 row lanes
+    const int c = blockIdx.y * PW_CT + cc * 8;
+    const long long r0 = (long long)blockIdx.x * PV_ROWS;
+    float s1[8], s2[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s1[j] = s2[j] = 0.f;
+    if (c < a.C) {
+        Act8 src, msk;
+        src.init(a.src, c);
+        if (a.has_mask) msk.init(a.mask, c);
+        const bf16* partner = a.partner ? reinterpret_cast<const bf16*>(a.partner) + c : nullptr;
+        bf16* out = a.out ? reinterpret_cast<bf16*>(a.out) + c : nullptr;
+#pragma unroll 2
+        for (int i = rl; i < PV_ROWS; i += PW_THREADS / 8) {
+            const long long r = r0 + i;
+            if (r >= a.rows) break;
+            float v[8];
+            src.eval(r, v);
+            if (a.has_mask) {
+                float m[8];
+                msk.eval(r, m);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] = m[j] > 0.f ? v[j] : 0.f;
+            }
+            if (a.stat_sum) {
+                float p[8];
+                if (partner) unpack8(*reinterpret_cast<const uint4*>(partner + r * a.ld_partner), p);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { s1[j] += v[j]; s2[j] += v[j] * (partner ? p[j] : v[j]); }
+            }
+            if (out) *reinterpret_cast<uint4*>(out + r * a.ld_out) = pack8(v);
+        }
+    }
+    if (a.stat_sum) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { s_red[0][rl][cc * 8 + j] = s1[j]; s_red[1][rl][cc * 8 + j] = s2[j]; }
+        __syncthreads();
+        if (tid < PW_CT && blockIdx.y * PW_CT + tid < a.C) {
+            float t1 = 0.f, t2 = 0.f;
+            for (int g = 0; g < PW_THREADS / 8; ++g) { t1 += s_red[0][g][tid]; t2 += s_red[1][g][tid]; }
+            atomicAdd(a.stat_sum + blockIdx.y * PW_CT + tid, (double)t1);
+            atomicAdd(a.stat_sq + blockIdx.y * PW_CT + tid, (double)t2);
+        }
+    }
+}
+
+static inline bool pointwise_vec_ok(const dsg_pointwise_args& a) {
+    if (a.dtype != DSG_BF16 || a.C % 8 != 0 || !act8_ok(a.src)) return false;
+    if (a.out && (a.out_dtype != DSG_BF16 || (uintptr_t)a.out % 16 != 0 || a.ld_out % 8 != 0)) return false;
+    if (a.has_mask && !act8_ok(a.mask)) return false;
+    if (a.partner && (a.partner_dtype != DSG_BF16 || (uintptr_t)a.partner % 16 != 0 || a.ld_partner % 8 != 0)) return false;
+    return true;
+}
+
 // ---------------------------------------------------------------------------------------------
 // multi-scale combine.  Channel c belongs to the conv range (value read from o), the max range
 // (3x1 max-pool over relu(a*B+b)) or the pass range (a*B+b at frame s*t').

@@ -1,0 +1,752 @@
+// Fused branch stage of the multi-scale temporal unit (mstcn / dgmstcn) on tcgen05 — reference tcn.py:383-396,
+// 407-420.  Implicit GEMM: for one sample and MS_TO = 4 output frames the post-BN-ReLU branch tile (with its temporal
+// halo) is staged ONCE in shared memory as a K-major no-swizzle UMMA operand whose rows are (frame, joint) with every
+// frame padded to 32 rows; tap dt of the dilated (3 x 1) convolution is then just a *shifted descriptor* into that
+// tile (frame shifts are multiples of 32 rows = 4 core-matrix groups), so nothing is re-staged per tap.  With a
+// temporal stride s the frames are staged de-interleaved in s planes (t = s*q + p) so every tap still addresses a
+// contiguous run of frames.  All conv branches accumulate into disjoint TMEM column ranges of one 128-lane
+// accumulator; the max-pool and pass-through branches run on the CUDA cores; the CTA assembles complete `feat`
+// rows in shared memory (local + global * add_coeff) and writes them with 16-byte stores, accumulating the
+// BatchNorm statistics of transform.0 on the way out.
+#pragma once
+#include "conv_gemm_tc.cuh"
+
+#ifndef DSG_EMU
+namespace dsg {
+namespace tc {
+
+constexpr int MS_TO = 4;            // output (fwd) / input (bwd) frames per CTA: M = 128 = 4 frames x 32 padded rows
+constexpr int MS_THREADS = 256;
+
+DSG_D int floordiv(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
+DSG_D int posmod(int a, int b) { int m = a % b; return m < 0 ? m + b : m; }
+
+struct MsBranchGeom {
+    int w, Kp, nch, d, qmin, Fq, col;     // width, padded width, 16B chunks, dilation, first plane frame offset, frames per plane, TMEM column
+};
+
+DSG_D MsBranchGeom ms_geom(const dsg_ms_temporal_args& a, int j, int s) {
+    MsBranchGeom g;
+    g.w = a.br[j].hi - a.br[j].lo;
+    g.Kp = (g.w + 15) & ~15;
+    g.nch = g.Kp >> 3;
+    g.d = a.br[j].dilation;
+    g.qmin = floordiv(-g.d, s);
+    g.Fq = MS_TO + floordiv(g.d, s) - g.qmin;
+    g.col = 0;
+    for (int i = 0; i < j; ++i)
+        if (a.br[i].kind == 0) g.col += ((a.br[i].hi - a.br[i].lo) + 15) & ~15;
+    return g;
+}
+
+// branch pre-activation (post BN, no ReLU) at (sample n, input frame t, column j, channel c)
+DSG_D float ms_preact(const dsg_ms_temporal_args& a, int n, int t, int j, int c, int Vp) {
+    const long long r = ((long long)n * a.T_in + t) * Vp + j;
+    return fmaf(__bfloat162float(reinterpret_cast<const bf16*>(a.b.x1)[r * a.b.ld1 + c]), a.b.a1[c], a.b.b1[c]);
+}
+// output of a max / pass branch at (n, output frame tp, column j, channel c)
+DSG_D float ms_mp_out(const dsg_ms_temporal_args& a, int kind, int n, int tp, int j, int c, int Vp) {
+    if (kind == 2) return ms_preact(a, n, tp * a.stride, j, c, Vp);
+    float m = -3.0e38f;
+#pragma unroll
+    for (int dt = -1; dt <= 1; ++dt) {
+        const int t = tp * a.stride + dt;
+        if (t < 0 || t >= a.T_in) continue;
+        m = fmaxf(m, fmaxf(ms_preact(a, n, t, j, c, Vp), 0.f));
+    }
+    return m;
+}
+
+__global__ void __launch_bounds__(MS_THREADS) ms_temporal_fwd_kernel(dsg_ms_temporal_args a, int h_bytes, int w_bytes, int tmem_cols) {
+    DSG_DYN_SMEM(smem);
+    __shared__ uint64_t mbar;
+    __shared__ uint32_t tmem_base_s;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int V = a.V, Vp = a.V + a.has_ext, s = a.stride, C = a.C;
+    const int n = blockIdx.y, tp0 = blockIdx.x * MS_TO;
+    unsigned char* Ht = smem;                                // staged branch tile (K-major no-swizzle, 32 rows / frame)
+    unsigned char* Wt = smem + h_bytes;                      // 3 taps x [Kp x Kp]
+    bf16* feat_s = reinterpret_cast<bf16*>(smem + h_bytes + w_bytes);      // [MS_TO*V][C]
+    const bf16* Bx = reinterpret_cast<const bf16*>(a.b.x1);
+
+    if (tid == 0) {
+        mbar_init(&mbar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) tmem_alloc(&tmem_base_s, (uint32_t)tmem_cols);
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_d = tmem_base_s;
+
+    uint32_t phase = 0;
+    int issued = 0;
+    for (int j = 0; j < a.n_branches; ++j) {
+        if (a.br[j].kind != 0) continue;
+        const MsBranchGeom g = ms_geom(a, j, s);
+        const int lo = a.br[j].lo;
+        if (issued) mbar_wait(&mbar, phase ^ 1);             // the previous branch's MMAs are done with Ht / Wt
+        // ---- zero the operand tiles (padding rows / channels must be exact zeros)
+        const int hb = s * g.Fq * 32 * g.Kp * 2, wb = 3 * g.Kp * g.Kp * 2;
+        for (int i = tid * 16; i < hb; i += MS_THREADS * 16) *reinterpret_cast<uint4*>(Ht + i) = make_uint4(0u, 0u, 0u, 0u);
+        for (int i = tid * 16; i < wb; i += MS_THREADS * 16) *reinterpret_cast<uint4*>(Wt + i) = make_uint4(0u, 0u, 0u, 0u);
+        __syncthreads();
+        // ---- stage relu(bn(B)) of this branch: item = (plane frame, joint row, aligned 8-channel chunk)
+        const int ac0 = lo >> 3, nac = ((a.br[j].hi + 7) >> 3) - ac0;
+        const int nfr = s * g.Fq;
+        for (int it = tid; it < nfr * Vp * nac; it += MS_THREADS) {
+            const int ac = it % nac, rv = it / nac;
+            const int v = rv % Vp, fi = rv / Vp;
+            const int p = fi / g.Fq, qi = fi - p * g.Fq;
+            const int t = s * (tp0 + g.qmin + qi) + p;
+            if (t < 0 || t >= a.T_in) continue;
+            const int c8 = (ac0 + ac) * 8;
+            const long long r = ((long long)n * a.T_in + t) * Vp + v;
+            float x[8];
+            unpack8(*reinterpret_cast<const uint4*>(Bx + r * a.b.ld1 + c8), x);
+            const int row = fi * 32 + v;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const int c = c8 + e, k = c - lo;
+                if (k >= 0 && k < g.w) {
+                    const float h = fmaxf(fmaf(x[e], a.b.a1[c], a.b.b1[c]), 0.f);
+                    *reinterpret_cast<bf16*>(Ht + op_off(row, k >> 3, g.nch) + (k & 7) * 2) = __float2bfloat16(h);
+                }
+            }
+        }
+        // ---- weights [co][ci][tap] fp32 -> three K-major [co][ci] bf16 tiles
+        for (int idx = tid; idx < g.w * g.w * 3; idx += MS_THREADS) {
+            const int dt = idx % 3, ci = (idx / 3) % g.w, co = idx / (3 * g.w);
+            *reinterpret_cast<bf16*>(Wt + dt * g.Kp * g.Kp * 2 + op_off(co, ci >> 3, g.nch) + (ci & 7) * 2) = __float2bfloat16(a.br[j].W[idx]);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (tid == 0) {
+            const uint32_t idesc = make_idesc(128, g.Kp);
+            const uint32_t sbo = (uint32_t)g.nch * 128u;
+            const uint32_t h0 = smem_u32(Ht), w0 = smem_u32(Wt);
+            for (int dt = 0; dt < 3; ++dt) {
+                const int o = (dt - 1) * g.d;
+                const int p = posmod(o, s);
+                const int qoff = (o - p) / s - g.qmin;                       // >= 0
+                const uint32_t abase = h0 + (uint32_t)((p * g.Fq + qoff) * 4) * sbo;   // 4 row groups per frame
+                const uint32_t bbase = w0 + (uint32_t)(dt * g.Kp * g.Kp * 2);
+                for (int ks = 0; ks < (g.Kp >> 4); ++ks)
+                    umma_f16(tmem_d + (uint32_t)g.col, make_desc(abase + ks * 256u, 128u, sbo), make_desc(bbase + ks * 256u, 128u, sbo), idesc,
+                             (dt == 0 && ks == 0) ? 0u : 1u);
+            }
+            umma_commit(&mbar);
+        }
+        issued = 1;
+        phase ^= 1;
+    }
+    // ---- max-pool / pass-through branches on the CUDA cores while the last MMAs drain
+    for (int j = 0; j < a.n_branches; ++j) {
+        const int kind = a.br[j].kind;
+        if (kind == 0) continue;
+        const int lo = a.br[j].lo, w = a.br[j].hi - lo;
+        for (int it = tid; it < MS_TO * w * (V + 1); it += MS_THREADS) {
+            const int c = lo + it % w, rest = it / w;
+            const int vv = rest % (V + 1), fl = rest / (V + 1);
+            const int tp = tp0 + fl;
+            if (tp >= a.T_out) continue;
+            if (vv == V) {                                   // the joint-mean column: only its own value is kept (oglob)
+                if (a.has_ext) a.oglob[((long long)n * a.T_out + tp) * C + c] = ms_mp_out(a, kind, n, tp, V, c, Vp);
+                continue;
+            }
+            float val = ms_mp_out(a, kind, n, tp, vv, c, Vp);
+            if (a.has_ext) val = fmaf(ms_mp_out(a, kind, n, tp, V, c, Vp), a.add_coeff[vv], val);
+            feat_s[(fl * V + vv) * C + c] = __float2bfloat16(val);
+        }
+    }
+    if (issued) {
+        mbar_wait(&mbar, phase ^ 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        // ---- conv branches: TMEM -> registers; warp w reads frame (w & 3); lanes are joints (lane V = joint-mean column)
+        const int fl = warp & 3, half = warp >> 2;
+        const int tp = tp0 + fl;
+        const float addv = (a.has_ext && lane < V) ? a.add_coeff[lane] : 0.f;
+        int gcount = 0;
+        for (int j = 0; j < a.n_branches; ++j) {
+            if (a.br[j].kind != 0) continue;
+            const MsBranchGeom g = ms_geom(a, j, s);
+            for (int c16 = 0; c16 < g.Kp; c16 += 16, ++gcount) {
+                if ((gcount & 1) != half) continue;
+                float v[16];
+                tmem_ld16(tmem_d + ((uint32_t)(fl * 32) << 16) + (uint32_t)(g.col + c16), v);
+#pragma unroll
+                for (int e = 0; e < 16; ++e) {
+                    const int k = c16 + e;
+                    float val = v[e] + ((k < g.w) ? a.br[j].bias[k] : 0.f);
+                    if (a.has_ext) {
+                        const float glob = __shfl_sync(0xffffffffu, val, V);
+                        if (lane == V && k < g.w && tp < a.T_out) a.oglob[((long long)n * a.T_out + tp) * C + a.br[j].lo + k] = val;
+                        val = fmaf(glob, addv, val);
+                    }
+                    if (lane < V && k < g.w && tp < a.T_out) feat_s[(fl * V + lane) * C + a.br[j].lo + k] = __float2bfloat16(val);
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_d, (uint32_t)tmem_cols);
+    // ---- write-out: complete rows, 16-byte stores, BatchNorm statistics of transform.0
+    {
+        const int nchunks = C >> 3, lanes = MS_THREADS / nchunks;
+        const int cc = tid % nchunks, rl = tid / nchunks;
+        float s1[8], s2[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) s1[e] = s2[e] = 0.f;
+        bf16* feat = reinterpret_cast<bf16*>(a.feat);
+        for (int r = rl; r < MS_TO * V; r += lanes) {
+            const int fl = r / V, vv = r - fl * V;
+            const int tp = tp0 + fl;
+            if (tp >= a.T_out) break;
+            const uint4 u = *reinterpret_cast<const uint4*>(feat_s + r * C + cc * 8);
+            *reinterpret_cast<uint4*>(feat + (((long long)n * a.T_out + tp) * V + vv) * a.ld_feat + cc * 8) = u;
+            if (a.stat_sum) {
+                float x[8];
+                unpack8(u, x);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) { s1[e] += x[e]; s2[e] += x[e] * x[e]; }
+            }
+        }
+        if (a.stat_sum) {
+            float* red = reinterpret_cast<float*>(smem);     // [2][lanes][C]  (operand tiles are dead)
+#pragma unroll
+            for (int e = 0; e < 8; ++e) { red[(0 * lanes + rl) * C + cc * 8 + e] = s1[e]; red[(1 * lanes + rl) * C + cc * 8 + e] = s2[e]; }
+            __syncthreads();
+            for (int c = tid; c < C; c += MS_THREADS) {
+                float t1 = 0.f, t2 = 0.f;
+                for (int l = 0; l < lanes; ++l) { t1 += red[(0 * lanes + l) * C + c]; t2 += red[(1 * lanes + l) * C + c]; }
+                atomicAdd(a.stat_sum + c, (double)t1);
+                atomicAdd(a.stat_sq + c, (double)t2);
+            }
+        }
+    }
+}
+
+struct MsHostGeom { int h_bytes, w_bytes, tmem_cols, feat_bytes; bool ok; };
+
+static MsHostGeom ms_host_geom(const dsg_ms_temporal_args& a, int out_rows_per_frame) {
+    MsHostGeom h{0, 0, 0, 0, true};
+    int Vp = a.V + a.has_ext, s = a.stride, cols = 0;
+    if (Vp > 32 || a.n_branches > 8 || a.n_branches < 1 || s < 1 || a.C % 8 != 0 || (MS_THREADS % (a.C / 8)) != 0 || a.C / 8 > MS_THREADS) h.ok = false;
+    for (int j = 0; j < a.n_branches && h.ok; ++j) {
+        if (a.br[j].kind != 0) continue;
+        int w = a.br[j].hi - a.br[j].lo, Kp = (w + 15) & ~15, d = a.br[j].dilation;
+        if (w < 1 || Kp > 128 || d < 1) { h.ok = false; break; }
+        int qmin = -((d + s - 1) / s), qmax = d / s;
+        int Fq = MS_TO + qmax - qmin;
+        int hb = s * Fq * 32 * Kp * 2, wb = 3 * Kp * Kp * 2;
+        if (hb > h.h_bytes) h.h_bytes = hb;
+        if (wb > h.w_bytes) h.w_bytes = wb;
+        cols += Kp;
+    }
+    if (cols > 512) h.ok = false;
+    h.tmem_cols = 32;
+    while (h.tmem_cols < cols) h.tmem_cols <<= 1;
+    h.feat_bytes = MS_TO * out_rows_per_frame * a.C * 2;
+    // the statistics scratch re-uses the operand region: [2][lanes][C] floats
+    int red = 2 * (MS_THREADS / (a.C / 8 > 0 ? a.C / 8 : 1)) * a.C * 4;
+    if (h.h_bytes + h.w_bytes < red) h.h_bytes = red - h.w_bytes > 0 ? red - h.w_bytes : h.h_bytes;
+    h.h_bytes = (h.h_bytes + 127) & ~127;
+    h.w_bytes = (h.w_bytes + 127) & ~127;
+    if ((size_t)h.h_bytes + h.w_bytes + h.feat_bytes > 200 * 1024) h.ok = false;
+    return h;
+}
+
+static bool ms_args_ok(const dsg_ms_temporal_args& a) {
+    if (!a.b.x1 || a.b.x2 || !a.b.a1 || !a.b.b1 || a.b.a2 || a.b.b2) return false;
+    if ((uintptr_t)a.b.x1 % 16 != 0 || a.b.ld1 % 8 != 0) return false;
+    return true;
+}
+
+static const char* launch_ms_temporal_fwd(const dsg_ms_temporal_args& a, dsg_stream_t st) {
+    MsHostGeom h = ms_host_geom(a, a.V);
+    if (!h.ok || !ms_args_ok(a)) return "ms_temporal_fwd: unsupported shape (use the per-branch path)";
+    if ((uintptr_t)a.feat % 16 != 0 || a.ld_feat % 8 != 0) return "ms_temporal_fwd: feat must be 16-byte aligned";
+    if (a.n_samples <= 0 || a.T_out <= 0) return nullptr;
+    size_t smem = (size_t)h.h_bytes + h.w_bytes + h.feat_bytes;
+    cudaFuncSetAttribute(ms_temporal_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    dim3 grid((a.T_out + MS_TO - 1) / MS_TO, a.n_samples);
+    ms_temporal_fwd_kernel<<<grid, dim3(MS_THREADS), smem, st>>>(a, h.h_bytes, h.w_bytes, h.tmem_cols);
+    return dsg_launch_error();
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Backward (data).  One CTA = one sample, one temporal plane p_in (t = s*q + p_in) and MS_TO input frames of it.
+// For a conv branch, tap dt (offset o = (dt-1)*d) reaches input frame t from output frame t' = (t - o)/s when
+// s | (p_in - o); for a fixed tap those t' are a contiguous run, so the staged dO tile (output-frame rows, 32 per
+// frame, joint-mean row = sum_v dfeat[v]*add_coeff[v]) is again addressed by shifted descriptors and the B operand
+// is W[:, :, dt]^T.  dH lands in TMEM; max-pool / pass-through gradients are routed on the CUDA cores; the write-out
+// pass applies the ReLU mask from the stored pre-activations and accumulates the BatchNorm-backward sums.
+struct MsBwdTaps { int n, sh[3], dt[3], shmin, Fq; };
+
+DSG_D MsBwdTaps ms_bwd_taps(int d, int s, int p_in) {
+    MsBwdTaps r;
+    r.n = 0; r.shmin = 1 << 20;
+    int shmax = -(1 << 20);
+    for (int dt = 0; dt < 3; ++dt) {
+        const int o = (dt - 1) * d;
+        if (posmod(p_in - o, s) != 0) continue;
+        const int sh = (p_in - o) / s;
+        r.sh[r.n] = sh; r.dt[r.n] = dt; ++r.n;
+        if (sh < r.shmin) r.shmin = sh;
+        if (sh > shmax) shmax = sh;
+    }
+    r.Fq = r.n ? MS_TO + shmax - r.shmin : 0;
+    return r;
+}
+
+// gradient w.r.t. the branch-stage output (before local+global mixing) for joint rows: dfeat itself
+DSG_D float ms_dfeat(const dsg_ms_temporal_args& a, int n, int tp, int v, int c) {
+    return act_value<bf16>(a.dfeat, ((long long)n * a.T_out + tp) * a.V + v, c);
+}
+
+__global__ void __launch_bounds__(MS_THREADS) ms_temporal_bwd_data_kernel(dsg_ms_temporal_args a, int h_bytes, int w_bytes, int tmem_cols,
+                                                                          int mp_lo, int mp_hi) {
+    DSG_DYN_SMEM(smem);
+    __shared__ uint64_t mbar;
+    __shared__ uint32_t tmem_base_s;
+    __shared__ float s_dadd[32];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int V = a.V, Vp = a.V + a.has_ext, s = a.stride, C = a.C;
+    const int n = blockIdx.y, p_in = blockIdx.z, q0 = blockIdx.x * MS_TO;
+    unsigned char* Dt = smem;                                 // staged dO tile
+    unsigned char* Wt = smem + h_bytes;
+    bf16* E_s = reinterpret_cast<bf16*>(smem + h_bytes + w_bytes);          // [MS_TO*Vp][C]
+    const int mpw = mp_hi - mp_lo;                            // channels of the max/pass ranges (contiguous span)
+    float* dg_s = reinterpret_cast<float*>(smem + h_bytes + w_bytes + MS_TO * Vp * C * 2);   // [6][mpw]
+    const bf16* X1 = reinterpret_cast<const bf16*>(a.dfeat.x1);
+    const bf16* X2 = reinterpret_cast<const bf16*>(a.dfeat.x2);
+
+    if (tid == 0) {
+        mbar_init(&mbar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) tmem_alloc(&tmem_base_s, (uint32_t)tmem_cols);
+    if (tid < 32) s_dadd[tid] = 0.f;
+    for (int i = tid * 8; i < MS_TO * Vp * C; i += MS_THREADS * 8) *reinterpret_cast<uint4*>(E_s + i) = make_uint4(0u, 0u, 0u, 0u);
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_d = tmem_base_s;
+
+    uint32_t phase = 0;
+    int issued = 0;
+    for (int j = 0; j < a.n_branches; ++j) {
+        if (a.br[j].kind != 0) continue;
+        const MsBranchGeom g = ms_geom(a, j, s);
+        const MsBwdTaps tp = ms_bwd_taps(g.d, s, p_in);
+        if (tp.n == 0) continue;
+        const int lo = a.br[j].lo;
+        if (issued) mbar_wait(&mbar, phase ^ 1);
+        const int hb = tp.Fq * 32 * g.Kp * 2, wb = 3 * g.Kp * g.Kp * 2;
+        for (int i = tid * 16; i < hb; i += MS_THREADS * 16) *reinterpret_cast<uint4*>(Dt + i) = make_uint4(0u, 0u, 0u, 0u);
+        for (int i = tid * 16; i < wb; i += MS_THREADS * 16) *reinterpret_cast<uint4*>(Wt + i) = make_uint4(0u, 0u, 0u, 0u);
+        __syncthreads();
+        // ---- stage dO (joint rows): item = (output frame, joint, aligned 8-channel chunk)
+        const int ac0 = lo >> 3, nac = ((a.br[j].hi + 7) >> 3) - ac0;
+        for (int it = tid; it < tp.Fq * V * nac; it += MS_THREADS) {
+            const int ac = it % nac, rv = it / nac;
+            const int v = rv % V, qi = rv / V;
+            const int tpo = q0 + tp.shmin + qi;
+            if (tpo < 0 || tpo >= a.T_out) continue;
+            const int c8 = (ac0 + ac) * 8;
+            const long long r = ((long long)n * a.T_out + tpo) * V + v;
+            float x[8], y[8];
+            unpack8(*reinterpret_cast<const uint4*>(X1 + r * a.dfeat.ld1 + c8), x);
+            if (X2) unpack8(*reinterpret_cast<const uint4*>(X2 + r * a.dfeat.ld2 + c8), y);
+            const int row = qi * 32 + v;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const int c = c8 + e, k = c - lo;
+                if (k >= 0 && k < g.w) {
+                    float d = x[e];
+                    if (a.dfeat.a1) d *= a.dfeat.a1[c];
+                    if (a.dfeat.b1) d += a.dfeat.b1[c];
+                    if (X2) d = fmaf(y[e], a.dfeat.a2 ? a.dfeat.a2[c] : 1.f, d);
+                    if (a.dfeat.b2) d += a.dfeat.b2[c];
+                    *reinterpret_cast<bf16*>(Dt + op_off(row, k >> 3, g.nch) + (k & 7) * 2) = __float2bfloat16(d);
+                }
+            }
+        }
+        // ---- W[co][ci][dt] -> B operand [ci][co] per tap
+        for (int idx = tid; idx < g.w * g.w * 3; idx += MS_THREADS) {
+            const int dt = idx % 3, ci = (idx / 3) % g.w, co = idx / (3 * g.w);
+            *reinterpret_cast<bf16*>(Wt + dt * g.Kp * g.Kp * 2 + op_off(ci, co >> 3, g.nch) + (co & 7) * 2) = __float2bfloat16(a.br[j].W[idx]);
+        }
+        if (a.has_ext) {
+            __syncthreads();
+            for (int it = tid; it < tp.Fq * g.w; it += MS_THREADS) {       // joint-mean row: sum_v dO[v] * add_coeff[v]
+                const int k = it % g.w, qi = it / g.w;
+                float sacc = 0.f;
+                for (int v = 0; v < V; ++v)
+                    sacc = fmaf(__bfloat162float(*reinterpret_cast<const bf16*>(Dt + op_off(qi * 32 + v, k >> 3, g.nch) + (k & 7) * 2)), a.add_coeff[v], sacc);
+                *reinterpret_cast<bf16*>(Dt + op_off(qi * 32 + V, k >> 3, g.nch) + (k & 7) * 2) = __float2bfloat16(sacc);
+            }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (tid == 0) {
+            const uint32_t idesc = make_idesc(128, g.Kp);
+            const uint32_t sbo = (uint32_t)g.nch * 128u;
+            const uint32_t h0 = smem_u32(Dt), w0 = smem_u32(Wt);
+            for (int ti = 0; ti < tp.n; ++ti) {
+                const uint32_t abase = h0 + (uint32_t)((tp.sh[ti] - tp.shmin) * 4) * sbo;
+                const uint32_t bbase = w0 + (uint32_t)(tp.dt[ti] * g.Kp * g.Kp * 2);
+                for (int ks = 0; ks < (g.Kp >> 4); ++ks)
+                    umma_f16(tmem_d + (uint32_t)g.col, make_desc(abase + ks * 256u, 128u, sbo), make_desc(bbase + ks * 256u, 128u, sbo), idesc,
+                             (ti == 0 && ks == 0) ? 0u : 1u);
+            }
+            umma_commit(&mbar);
+        }
+        issued |= (1 << j);
+        phase ^= 1;
+    }
+    // ---- max-pool / pass-through gradients on the CUDA cores
+    if (mpw > 0) {
+        const int t_first = s * q0 + p_in;
+        const int tp_lo = floordiv(t_first - 1, s);
+        if (a.has_ext) {
+            for (int it = tid; it < 6 * mpw; it += MS_THREADS) {        // dO of the joint-mean column for the frames in reach
+                const int c = mp_lo + it % mpw, fi = it / mpw;
+                const int tpo = tp_lo + fi;
+                float sacc = 0.f;
+                if (tpo >= 0 && tpo < a.T_out)
+                    for (int v = 0; v < V; ++v) sacc = fmaf(ms_dfeat(a, n, tpo, v, c), a.add_coeff[v], sacc);
+                dg_s[it] = sacc;
+            }
+            __syncthreads();
+        }
+        for (int j = 0; j < a.n_branches; ++j) {
+            const int kind = a.br[j].kind;
+            if (kind == 0) continue;
+            const int lo = a.br[j].lo, w = a.br[j].hi - lo;
+            for (int it = tid; it < MS_TO * Vp * w; it += MS_THREADS) {
+                const int c = lo + it % w, rest = it / w;
+                const int vv = rest % Vp, i = rest / Vp;
+                const int t = s * (q0 + i) + p_in;
+                if (t >= a.T_in) continue;
+                float e = 0.f;
+                if (kind == 2) {
+                    if (t % s == 0 && t / s < a.T_out) {
+                        const int tpo = t / s;
+                        e = (vv < V) ? ms_dfeat(a, n, tpo, vv, c) : dg_s[(tpo - tp_lo) * mpw + c - mp_lo];
+                    }
+                } else if (ms_preact(a, n, t, vv, c, Vp) > 0.f) {
+#pragma unroll
+                    for (int dt = -1; dt <= 1; ++dt) {                  // windows t' with s*t' + dt == t
+                        const int num = t - dt;
+                        if (num < 0 || num % s != 0) continue;
+                        const int tpo = num / s;
+                        if (tpo >= a.T_out) continue;
+                        float m = -3.0e38f;
+                        int am = -2;
+#pragma unroll
+                        for (int d2 = -1; d2 <= 1; ++d2) {              // first maximum wins (ATen max_pool2d)
+                            const int t2 = tpo * s + d2;
+                            if (t2 < 0 || t2 >= a.T_in) continue;
+                            const float h2 = fmaxf(ms_preact(a, n, t2, vv, c, Vp), 0.f);
+                            if (h2 > m) { m = h2; am = d2; }
+                        }
+                        if (am == dt) e += (vv < V) ? ms_dfeat(a, n, tpo, vv, c) : dg_s[(tpo - tp_lo) * mpw + c - mp_lo];
+                    }
+                }
+                E_s[(i * Vp + vv) * C + c] = __float2bfloat16(e);
+            }
+        }
+    }
+    // ---- dadd_coeff for the output frames this CTA owns (plane 0: t' = q0 + i)
+    if (a.has_ext && p_in == 0) {
+        for (int i = 0; i < MS_TO; ++i) {
+            const int tpo = q0 + i;
+            if (tpo >= a.T_out) break;
+            for (int v = 0; v < V; ++v) {
+                float part = 0.f;
+                for (int c = tid; c < C; c += MS_THREADS)
+                    part = fmaf(ms_dfeat(a, n, tpo, v, c), a.oglob[((long long)n * a.T_out + tpo) * C + c], part);
+                part = warp_sum(part);
+                if (lane == 0) atomicAdd(&s_dadd[v], part);
+            }
+        }
+    }
+    if (issued) {
+        mbar_wait(&mbar, phase ^ 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int i = warp & 3, half = warp >> 2;
+        int gcount = 0;
+        for (int j = 0; j < a.n_branches; ++j) {
+            if (!(issued & (1 << j))) continue;
+            const MsBranchGeom g = ms_geom(a, j, s);
+            for (int c16 = 0; c16 < g.Kp; c16 += 16, ++gcount) {
+                if ((gcount & 1) != half) continue;
+                float v[16];
+                tmem_ld16(tmem_d + ((uint32_t)(i * 32) << 16) + (uint32_t)(g.col + c16), v);
+                if (lane < Vp) {
+#pragma unroll
+                    for (int e = 0; e < 16; ++e)
+                        if (c16 + e < g.w) E_s[(i * Vp + lane) * C + a.br[j].lo + c16 + e] = __float2bfloat16(v[e]);
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_d, (uint32_t)tmem_cols);
+    if (a.has_ext && p_in == 0 && tid < V) atomicAdd(a.dadd_coeff + tid, s_dadd[tid]);
+    // ---- write-out: ReLU mask from the stored pre-activations (not on the pass range), BN-backward sums, 16-byte stores
+    {
+        const int nchunks = C >> 3, lanes = MS_THREADS / nchunks;
+        const int cc = tid % nchunks, rl = tid / nchunks;
+        const int c0 = cc * 8;
+        float s1[8], s2[8], ca[8], cb[8], msk[8];
+        load8f(a.b.a1 + c0, ca, 1.f);
+        load8f(a.b.b1 + c0, cb, 0.f);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            s1[e] = s2[e] = 0.f;
+            msk[e] = 1.f;
+            for (int j = 0; j < a.n_branches; ++j)
+                if (a.br[j].kind == 2 && c0 + e >= a.br[j].lo && c0 + e < a.br[j].hi) msk[e] = 0.f;     // pass range: no ReLU
+        }
+        bf16* E = reinterpret_cast<bf16*>(a.e);
+        const bf16* Bx = reinterpret_cast<const bf16*>(a.b.x1);
+        for (int r = rl; r < MS_TO * Vp; r += lanes) {
+            const int i = r / Vp, vv = r - i * Vp;
+            const int t = s * (q0 + i) + p_in;
+            if (t >= a.T_in) break;
+            const long long grow = ((long long)n * a.T_in + t) * Vp + vv;
+            float x[8], braw[8];
+            unpack8(*reinterpret_cast<const uint4*>(E_s + r * C + c0), x);
+            unpack8(*reinterpret_cast<const uint4*>(Bx + grow * a.b.ld1 + c0), braw);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                if (msk[e] != 0.f && !(fmaf(braw[e], ca[e], cb[e]) > 0.f)) x[e] = 0.f;
+                s1[e] += x[e];
+                s2[e] += x[e] * braw[e];
+            }
+            *reinterpret_cast<uint4*>(E + grow * a.ld_e + c0) = pack8(x);
+        }
+        if (a.e_sum) {
+            float* red = reinterpret_cast<float*>(smem);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) { red[(0 * lanes + rl) * C + c0 + e] = s1[e]; red[(1 * lanes + rl) * C + c0 + e] = s2[e]; }
+            __syncthreads();
+            for (int c = tid; c < C; c += MS_THREADS) {
+                float t1 = 0.f, t2 = 0.f;
+                for (int l = 0; l < lanes; ++l) { t1 += red[(0 * lanes + l) * C + c]; t2 += red[(1 * lanes + l) * C + c]; }
+                atomicAdd(a.e_sum + c, (double)t1);
+                atomicAdd(a.e_sq + c, (double)t2);
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Backward (weights).  Persistent CTAs, branch-outer: for conv branch j a CTA walks its share of (sample, 4 output
+// frames) tiles, stages relu(bn(B)) with halo (as forward) and dO (4 frames), and accumulates
+// dW[:, :, dt] (+)= dO^T * H_shift(dt) for the three taps in three TMEM column ranges.  Both operands are read as
+// MN-major (the reduction runs over rows): the staged tiles are byte-identical to the K-major ones, only the
+// descriptor strides swap (SBO = 128 B between 8-channel groups, LBO = 128 B * chunks between 8-row groups).
+__global__ void __launch_bounds__(MS_THREADS) ms_temporal_bwd_weight_kernel(dsg_ms_temporal_args a, int h_bytes, int d_bytes, int tmem_cols) {
+    DSG_DYN_SMEM(smem);
+    __shared__ uint64_t mbar;
+    __shared__ uint32_t tmem_base_s;
+    __shared__ float s_db[128];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int V = a.V, Vp = a.V + a.has_ext, s = a.stride;
+    unsigned char* Ht = smem;
+    unsigned char* Dt = smem + h_bytes;
+    const bf16* Bx = reinterpret_cast<const bf16*>(a.b.x1);
+    const bf16* X1 = reinterpret_cast<const bf16*>(a.dfeat.x1);
+    const bf16* X2 = reinterpret_cast<const bf16*>(a.dfeat.x2);
+    const int chunks_t = (a.T_out + MS_TO - 1) / MS_TO;
+    const int n_tiles = a.n_samples * chunks_t;
+
+    if (tid == 0) {
+        mbar_init(&mbar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) tmem_alloc(&tmem_base_s, (uint32_t)tmem_cols);
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_d = tmem_base_s;
+
+    uint32_t phase = 0;
+    int pending = 0;
+    for (int j = 0; j < a.n_branches; ++j) {
+        if (a.br[j].kind != 0) continue;
+        const MsBranchGeom g = ms_geom(a, j, s);
+        const int lo = a.br[j].lo;
+        const int ac0 = lo >> 3, nac = ((a.br[j].hi + 7) >> 3) - ac0;
+        if (tid < 128) s_db[tid] = 0.f;
+        int first = 1;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            const int n = tile / chunks_t, tp0 = (tile - n * chunks_t) * MS_TO;
+            if (pending) { mbar_wait(&mbar, phase ^ 1); pending = 0; }
+            const int hb = s * g.Fq * 32 * g.Kp * 2, db_ = MS_TO * 32 * g.Kp * 2;
+            for (int i = tid * 16; i < hb; i += MS_THREADS * 16) *reinterpret_cast<uint4*>(Ht + i) = make_uint4(0u, 0u, 0u, 0u);
+            for (int i = tid * 16; i < db_; i += MS_THREADS * 16) *reinterpret_cast<uint4*>(Dt + i) = make_uint4(0u, 0u, 0u, 0u);
+            __syncthreads();
+            const int nfr = s * g.Fq;
+            for (int it = tid; it < nfr * Vp * nac; it += MS_THREADS) {           // H = relu(bn(B)) with halo (as forward)
+                const int ac = it % nac, rv = it / nac;
+                const int v = rv % Vp, fi = rv / Vp;
+                const int p = fi / g.Fq, qi = fi - p * g.Fq;
+                const int t = s * (tp0 + g.qmin + qi) + p;
+                if (t < 0 || t >= a.T_in) continue;
+                const int c8 = (ac0 + ac) * 8;
+                const long long r = ((long long)n * a.T_in + t) * Vp + v;
+                float x[8];
+                unpack8(*reinterpret_cast<const uint4*>(Bx + r * a.b.ld1 + c8), x);
+                const int row = fi * 32 + v;
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const int c = c8 + e, k = c - lo;
+                    if (k >= 0 && k < g.w)
+                        *reinterpret_cast<bf16*>(Ht + op_off(row, k >> 3, g.nch) + (k & 7) * 2) =
+                            __float2bfloat16(fmaxf(fmaf(x[e], a.b.a1[c], a.b.b1[c]), 0.f));
+                }
+            }
+            for (int it = tid; it < MS_TO * V * nac; it += MS_THREADS) {          // dO joint rows
+                const int ac = it % nac, rv = it / nac;
+                const int v = rv % V, qi = rv / V;
+                const int tpo = tp0 + qi;
+                if (tpo >= a.T_out) continue;
+                const int c8 = (ac0 + ac) * 8;
+                const long long r = ((long long)n * a.T_out + tpo) * V + v;
+                float x[8], y[8];
+                unpack8(*reinterpret_cast<const uint4*>(X1 + r * a.dfeat.ld1 + c8), x);
+                if (X2) unpack8(*reinterpret_cast<const uint4*>(X2 + r * a.dfeat.ld2 + c8), y);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const int c = c8 + e, k = c - lo;
+                    if (k >= 0 && k < g.w) {
+                        float d = x[e];
+                        if (a.dfeat.a1) d *= a.dfeat.a1[c];
+                        if (a.dfeat.b1) d += a.dfeat.b1[c];
+                        if (X2) d = fmaf(y[e], a.dfeat.a2 ? a.dfeat.a2[c] : 1.f, d);
+                        if (a.dfeat.b2) d += a.dfeat.b2[c];
+                        *reinterpret_cast<bf16*>(Dt + op_off(qi * 32 + v, k >> 3, g.nch) + (k & 7) * 2) = __float2bfloat16(d);
+                    }
+                }
+            }
+            __syncthreads();
+            for (int it = tid; it < MS_TO * g.w; it += MS_THREADS) {              // joint-mean row of dO; bias gradient
+                const int k = it % g.w, qi = it / g.w;
+                float sacc = 0.f, tot = 0.f;
+                for (int v = 0; v < V; ++v) {
+                    const float d = __bfloat162float(*reinterpret_cast<const bf16*>(Dt + op_off(qi * 32 + v, k >> 3, g.nch) + (k & 7) * 2));
+                    sacc = fmaf(d, a.has_ext ? a.add_coeff[v] : 0.f, sacc);
+                    tot += d;
+                }
+                if (a.has_ext) *reinterpret_cast<bf16*>(Dt + op_off(qi * 32 + V, k >> 3, g.nch) + (k & 7) * 2) = __float2bfloat16(sacc);
+                atomicAdd(&s_db[k], tot + (a.has_ext ? sacc : 0.f));
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncthreads();
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (tid == 0) {
+                const uint32_t idesc = make_idesc_mn(128, g.Kp);
+                const uint32_t lbo = (uint32_t)g.nch * 128u;                       // between 8-row groups
+                const uint32_t h0 = smem_u32(Ht), d0 = smem_u32(Dt);
+                for (int dt = 0; dt < 3; ++dt) {
+                    const int o = (dt - 1) * g.d;
+                    const int p = posmod(o, s);
+                    const int qoff = (o - p) / s - g.qmin;
+                    const uint32_t hbase = h0 + (uint32_t)((p * g.Fq + qoff) * 4) * lbo;
+                    for (int ks = 0; ks < 8; ++ks)                                  // 128 rows = 8 x K16
+                        umma_f16(tmem_d + (uint32_t)(dt * g.Kp), make_desc(d0 + ks * 2u * lbo, lbo, 128u), make_desc(hbase + ks * 2u * lbo, lbo, 128u),
+                                 idesc, (first && ks == 0) ? 0u : 1u);
+                }
+                umma_commit(&mbar);
+            }
+            first = 0;
+            pending = 1;
+            phase ^= 1;
+        }
+        if (pending) { mbar_wait(&mbar, phase ^ 1); pending = 0; }
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (!first) {
+            // D rows = output channel co (lanes), columns = (tap, ci)
+            const int lq = warp & 3, half = warp >> 2;
+            const int co = lq * 32 + lane;
+            int gcount = 0;
+            for (int dt = 0; dt < 3; ++dt)
+                for (int c16 = 0; c16 < g.Kp; c16 += 16, ++gcount) {
+                    if ((gcount & 1) != half) continue;
+                    if (lq * 32 >= g.Kp) continue;                                  // warp-uniform: no live rows in this lane quarter
+                    float v[16];
+                    tmem_ld16(tmem_d + ((uint32_t)(lq * 32) << 16) + (uint32_t)(dt * g.Kp + c16), v);
+                    if (co < g.w) {
+#pragma unroll
+                        for (int e = 0; e < 16; ++e)
+                            if (c16 + e < g.w) atomicAdd(a.br[j].dW + ((long long)co * g.w + c16 + e) * 3 + dt, v[e]);
+                    }
+                }
+            if (tid < g.w && a.br[j].db) atomicAdd(a.br[j].db + tid, s_db[tid]);
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    }
+    if (warp == 0) tmem_dealloc(tmem_d, (uint32_t)tmem_cols);
+}
+
+static const char* launch_ms_temporal_bwd_data(const dsg_ms_temporal_args& a, dsg_stream_t st) {
+    const int Vp = a.V + a.has_ext;
+    MsHostGeom h = ms_host_geom(a, Vp);
+    if (!h.ok || !ms_args_ok(a)) return "ms_temporal_bwd_data: unsupported shape (use the per-branch path)";
+    if (!act8_ok(a.dfeat) || a.dfeat.relu) return "ms_temporal_bwd_data: dfeat must be 16-byte aligned";
+    if ((uintptr_t)a.e % 16 != 0 || a.ld_e % 8 != 0) return "ms_temporal_bwd_data: e must be 16-byte aligned";
+    if (a.n_samples <= 0 || a.T_in <= 0) return nullptr;
+    int mp_lo = 1 << 30, mp_hi = 0;
+    for (int j = 0; j < a.n_branches; ++j)
+        if (a.br[j].kind != 0) { if (a.br[j].lo < mp_lo) mp_lo = a.br[j].lo; if (a.br[j].hi > mp_hi) mp_hi = a.br[j].hi; }
+    if (mp_hi <= mp_lo) { mp_lo = 0; mp_hi = 0; }
+    size_t smem = (size_t)h.h_bytes + h.w_bytes + h.feat_bytes + (size_t)6 * (mp_hi - mp_lo) * 4 + 16;
+    if (smem > 200 * 1024) return "ms_temporal_bwd_data: shared memory budget exceeded";
+    cudaFuncSetAttribute(ms_temporal_bwd_data_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const int frames_per_plane = (a.T_in + a.stride - 1) / a.stride;
+    dim3 grid((frames_per_plane + MS_TO - 1) / MS_TO, a.n_samples, a.stride);
+    ms_temporal_bwd_data_kernel<<<grid, dim3(MS_THREADS), smem, st>>>(a, h.h_bytes, h.w_bytes, h.tmem_cols, mp_lo, mp_hi);
+    return dsg_launch_error();
+}
+
+static const char* launch_ms_temporal_bwd_weight(const dsg_ms_temporal_args& a, dsg_stream_t st) {
+    MsHostGeom h = ms_host_geom(a, a.V);
+    if (!h.ok || !ms_args_ok(a)) return "ms_temporal_bwd_weight: unsupported shape (use the per-branch path)";
+    if (!act8_ok(a.dfeat) || a.dfeat.relu) return "ms_temporal_bwd_weight: dfeat must be 16-byte aligned";
+    if (a.n_samples <= 0 || a.T_out <= 0) return nullptr;
+    int d_bytes = 0, cols = 32, kpmax = 0;
+    for (int j = 0; j < a.n_branches; ++j)
+        if (a.br[j].kind == 0) {
+            int Kp = ((a.br[j].hi - a.br[j].lo) + 15) & ~15;
+            if (Kp > kpmax) kpmax = Kp;
+            if (!a.br[j].dW) return "ms_temporal_bwd_weight: dW missing";
+        }
+    if (kpmax == 0) return nullptr;
+    // the A operand is read as M = 128 channel rows: reserve 16 channel groups per 8-row group even when Kp < 128
+    d_bytes = MS_TO * 32 * kpmax * 2 + 16 * 128;
+    while (cols < 3 * kpmax) cols <<= 1;
+    if (cols > 512) return "ms_temporal_bwd_weight: TMEM budget exceeded";
+    size_t smem = (size_t)h.h_bytes + d_bytes + 2048;
+    cudaFuncSetAttribute(ms_temporal_bwd_weight_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    int n_tiles = a.n_samples * ((a.T_out + MS_TO - 1) / MS_TO);
+    int grid = n_tiles < 2 * 148 ? n_tiles : 2 * 148;
+    ms_temporal_bwd_weight_kernel<<<dim3(grid), dim3(MS_THREADS), smem, st>>>(a, h.h_bytes, d_bytes, cols);
+    return dsg_launch_error();
+}
+
+}  // namespace tc
+}  // namespace dsg
+#endif

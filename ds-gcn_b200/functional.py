@@ -329,6 +329,24 @@ def _ms_ranges(layout):
     return (span("conv"), span("max"), span("1x1"))
 
 
+def _ms_fused_args(m, layout, b_act, n, T, T_out, s, V, has_ext, grads):
+    """Argument block of the fused tcgen05 branch-stage kernels, or None when the shape is not taken by them."""
+    if b_act.dtype != torch.bfloat16 or not ops.L.is_device_build():
+        return None
+    weights = {}
+    for j, (kind, lo, hi, cfg) in enumerate(layout):
+        if kind == "conv":
+            conv = m.branches[j][3].conv
+            dW = db = None
+            if grads is not None:
+                dW, db = torch.zeros_like(conv.weight), torch.zeros_like(conv.bias)
+                grads[conv.weight], grads[conv.bias] = dW, db
+            weights[j] = (conv.weight, conv.bias, dW, db)
+    a = ops.ms_temporal_args(b_act, layout, weights, n=n, T_in=T, T_out=T_out, stride=s, V=V, has_ext=has_ext,
+                             add_coeff=m.add_coeff if has_ext else None)
+    return a if ops.ms_temporal_supported(a) else None
+
+
 def mstcn_forward(m, g, n, T, V, save, res=None, final_relu=False):
     """g [n*T*V, C_in] -> [n*T_out*V, C_out] = bn(transform(branches(g))) (+ res) (relu).
     `res`: optional Act-like tuple (x, a, b) added before the final ReLU (DGBlock residual)."""
@@ -356,28 +374,31 @@ def mstcn_forward(m, g, n, T, V, save, res=None, final_relu=False):
             c_b.add_bn(m.branches[j][1], lo, hi, rows_b)
     c_b.run()
 
-    # ---- dilated (k x 1) convolutions of the conv branches
-    rows_o = n * T_out * Vp
-    O = torch.empty(rows_o, Ct, dtype=dt, device=dev)
-    for j, (kind, lo, hi, cfg) in enumerate(layout):
-        if kind != "conv":
-            continue
-        k, d = cfg
-        pad = (k + (k - 1) * (d - 1) - 1) // 2
-        conv = m.branches[j][3].conv
-        ops.conv_gemm(Act(B[:, lo:hi], c_b.a[lo:hi], c_b.b[lo:hi], relu=True), conv.weight, hi - lo, O[:, lo:hi],
-                      n_samples=n, T_in=T, T_out=T_out, Vin=Vp, bias=conv.bias, taps=k, tap_step=d, tap_off=-pad, t_mul=s)
-
-    # ---- max-pool / pass-through branches, local + global*add_coeff, statistics for transform.0
-    rows_f = n * T_out * V
+    rows_o, rows_f = n * T_out * Vp, n * T_out * V
     feat = torch.empty(rows_f, Ct, dtype=dt, device=dev)
     oglob = torch.empty(n * T_out, Ct, dtype=torch.float32, device=dev) if has_ext else None
     c_t = BNCoef(Ct, dev, training)
     add_coeff = m.add_coeff if has_ext else None
     if has_ext and add_coeff.numel() < V:
         raise ValueError("add_coeff is shorter than the number of joints")
-    ops.ms_combine_fwd(Act(B, c_b.a, c_b.b), O, feat, oglob, n=n, T_in=T, T_out=T_out, stride=s, V=V, has_ext=has_ext,
-                       ranges=ranges, add_coeff=add_coeff, stat_sum=c_t.ssum, stat_sq=c_t.ssq)
+    fused = _ms_fused_args(m, layout, Act(B, c_b.a, c_b.b), n, T, T_out, s, V, has_ext, None)
+    if fused is not None:
+        # ---- one tcgen05 kernel: dilated convs (implicit GEMM), max-pool, pass-through, local + global*add_coeff
+        ops.ms_temporal_fwd(fused, feat, oglob, c_t.ssum, c_t.ssq)
+    else:
+        # ---- per-branch path: dilated (k x 1) convolutions of the conv branches ...
+        O = torch.empty(rows_o, Ct, dtype=dt, device=dev)
+        for j, (kind, lo, hi, cfg) in enumerate(layout):
+            if kind != "conv":
+                continue
+            k, d = cfg
+            pad = (k + (k - 1) * (d - 1) - 1) // 2
+            conv = m.branches[j][3].conv
+            ops.conv_gemm(Act(B[:, lo:hi], c_b.a[lo:hi], c_b.b[lo:hi], relu=True), conv.weight, hi - lo, O[:, lo:hi],
+                          n_samples=n, T_in=T, T_out=T_out, Vin=Vp, bias=conv.bias, taps=k, tap_step=d, tap_off=-pad, t_mul=s)
+        # ---- ... then max-pool / pass-through branches, local + global*add_coeff, statistics for transform.0
+        ops.ms_combine_fwd(Act(B, c_b.a, c_b.b), O, feat, oglob, n=n, T_in=T, T_out=T_out, stride=s, V=V, has_ext=has_ext,
+                           ranges=ranges, add_coeff=add_coeff, stat_sum=c_t.ssum, stat_sq=c_t.ssq)
     c_t.add_bn(m.transform[0], 0, Ct, rows_f)
     c_t.run()
 
@@ -440,30 +461,36 @@ def mstcn_backward(m, sv, dout, grads):
     b_t.run()
     dfeat = b_t.dy(E2, feat)
 
-    # ---- combine backward: d_o for the conv branches, masked grads of max / pass branches, dadd_coeff
     b_b = BNBack(c_b)
-    d_o = torch.empty(rows_o, Ct, dtype=dt, device=dev)
     E3 = torch.empty(rows_b, Ct, dtype=dt, device=dev)
     dadd = torch.zeros_like(m.add_coeff) if has_ext else None
-    ops.ms_combine_bwd(Act(B, c_b.a, c_b.b), dfeat, d_o, E3, sv["oglob"], B, n=n, T_in=T, T_out=T_out, stride=s, V=V,
-                       has_ext=has_ext, ranges=ranges, add_coeff=m.add_coeff if has_ext else None, e_sum=b_b.ssum, e_sq=b_b.ssq,
-                       dadd_coeff=dadd)
     if has_ext:
         grads[m.add_coeff] = dadd
-    for j, (kind, lo, hi, cfg) in enumerate(layout):
-        if kind != "conv":
-            continue
-        k, d = cfg
-        pad = (k + (k - 1) * (d - 1) - 1) // 2
-        w = hi - lo
-        conv = m.branches[j][3].conv
-        ops.conv_gemm(d_o[:, lo:hi], conv.weight, w, E3[:, lo:hi], n_samples=n, T_in=T_out, T_out=T, Vin=Vp, ws=(k, w * k, 1), taps=k,
-                      tap_step=-d, tap_off=pad, t_div=s, mask=Act(B[:, lo:hi], c_b.a[lo:hi], c_b.b[lo:hi]),
-                      stat_sum=b_b.ssum[lo:hi], stat_sq=b_b.ssq[lo:hi], partner=B[:, lo:hi])
-        dWc, dbc = torch.zeros_like(conv.weight), torch.zeros_like(conv.bias)
-        ops.conv_wgrad(Act(B[:, lo:hi], c_b.a[lo:hi], c_b.b[lo:hi], relu=True), d_o[:, lo:hi], dWc, db=dbc, n_samples=n, T_in=T,
-                       T_out=T_out, Vin=Vp, taps=k, tap_step=d, tap_off=-pad, t_mul=s)
-        grads[conv.weight], grads[conv.bias] = dWc, dbc
+    fused = _ms_fused_args(m, layout, Act(B, c_b.a, c_b.b), n, T, T_out, s, V, has_ext, grads)
+    if fused is not None:
+        # ---- two tcgen05 kernels: data gradient of the whole branch stage (+ masks, BN-backward sums, dadd_coeff),
+        #      then the weight gradients of the dilated convolutions
+        ops.ms_temporal_bwd(fused, dfeat, E3, sv["oglob"], b_b.ssum, b_b.ssq, dadd)
+    else:
+        # ---- per-branch path: d_o for the conv branches, masked grads of max / pass branches, dadd_coeff
+        d_o = torch.empty(rows_o, Ct, dtype=dt, device=dev)
+        ops.ms_combine_bwd(Act(B, c_b.a, c_b.b), dfeat, d_o, E3, sv["oglob"], B, n=n, T_in=T, T_out=T_out, stride=s, V=V,
+                           has_ext=has_ext, ranges=ranges, add_coeff=m.add_coeff if has_ext else None, e_sum=b_b.ssum, e_sq=b_b.ssq,
+                           dadd_coeff=dadd)
+        for j, (kind, lo, hi, cfg) in enumerate(layout):
+            if kind != "conv":
+                continue
+            k, d = cfg
+            pad = (k + (k - 1) * (d - 1) - 1) // 2
+            w = hi - lo
+            conv = m.branches[j][3].conv
+            ops.conv_gemm(d_o[:, lo:hi], conv.weight, w, E3[:, lo:hi], n_samples=n, T_in=T_out, T_out=T, Vin=Vp, ws=(k, w * k, 1), taps=k,
+                          tap_step=-d, tap_off=pad, t_div=s, mask=Act(B[:, lo:hi], c_b.a[lo:hi], c_b.b[lo:hi]),
+                          stat_sum=b_b.ssum[lo:hi], stat_sq=b_b.ssq[lo:hi], partner=B[:, lo:hi])
+            dWc, dbc = torch.zeros_like(conv.weight), torch.zeros_like(conv.bias)
+            ops.conv_wgrad(Act(B[:, lo:hi], c_b.a[lo:hi], c_b.b[lo:hi], relu=True), d_o[:, lo:hi], dWc, db=dbc, n_samples=n, T_in=T,
+                           T_out=T_out, Vin=Vp, taps=k, tap_step=d, tap_off=-pad, t_mul=s)
+            grads[conv.weight], grads[conv.bias] = dWc, dbc
     for j, (kind, lo, hi, _) in enumerate(layout):
         if kind == "1x1":
             b_b.add_identity(lo, hi)

@@ -119,7 +119,11 @@ def conv_gemm(src, W, N, out, *, n_samples, T_in, T_out, Vin, ws=None, bias=None
             nbytes += rows_out * N * es
     if mask is not None:
         nbytes += rows_out * N * es
-    L.call("dsg_conv_gemm", C.byref(a), L.stream(), nbytes=nbytes)
+    tag = None
+    if L.profile is not None:
+        tag = dict(K=K, N=N, rows_out=rows_out, taps=taps, ext_in=int(ext_in), cext=int(contract_ext), x2=src.x2 is not None,
+                   mask=mask is not None, stats=stat_sum is not None, ws=tuple(ws), t_mul=t_mul, t_div=t_div, dt=str(src.dtype))
+    L.call("dsg_conv_gemm", C.byref(a), L.stream(), nbytes=nbytes, tag=tag)
     return out
 
 
@@ -141,7 +145,8 @@ def conv_wgrad(A, B, dW, *, n_samples, T_in, T_out, Vin, ws=None, db=None, taps=
     es = A.x1.element_size()
     rows_out = n_samples * T_out * (Vin + int(ext_in))
     nbytes = n_samples * T_in * Vin * a.K * es * (2 if A.x2 is not None else 1) + rows_out * a.N * es * (2 if B.x2 is not None else 1)
-    L.call("dsg_conv_wgrad", C.byref(a), L.stream(), nbytes=nbytes)
+    tag = dict(K=a.K, N=a.N, rows_out=rows_out, taps=taps, ext_in=int(ext_in)) if L.profile is not None else None
+    L.call("dsg_conv_wgrad", C.byref(a), L.stream(), nbytes=nbytes, tag=tag)
 
 
 def bn_job(mode, Cn, *, sum=None, sq=None, count=1.0, gamma=None, beta=None, running_mean=None, running_var=None,
@@ -299,6 +304,58 @@ def ms_combine_bwd(b, dfeat, d_o, e, oglob, b_raw, *, n, T_in, T_out, stride, V,
     a.e_sum, a.e_sq = L.ptr(e_sum), L.ptr(e_sq)
     a.dadd_coeff = L.ptr(_f32(dadd_coeff))
     L.call("dsg_ms_combine_bwd", C.byref(a), L.stream())
+
+
+def ms_temporal_args(b, layout, weights, *, n, T_in, T_out, stride, V, has_ext, add_coeff):
+    """layout: [(kind, lo, hi, cfg)] as functional.ms_layout; weights: {branch index: (W, bias, dW, db)} for conv branches."""
+    b = as_act(b)
+    a = L.MsTemporalArgs()
+    a.n_samples, a.T_in, a.T_out, a.stride, a.V, a.has_ext, a.C = n, T_in, T_out, stride, V, int(has_ext), b.C
+    if len(layout) > 8:
+        return None
+    a.n_branches = len(layout)
+    for j, (kind, lo, hi, cfg) in enumerate(layout):
+        br = a.br[j]
+        br.lo, br.hi = lo, hi
+        if kind == "conv":
+            if cfg[0] != 3:
+                return None
+            br.kind, br.dilation = 0, cfg[1]
+            W, bias, dW, db = weights[j]
+            br.W, br.bias, br.dW, br.db = L.ptr(_f32(W)), L.ptr(_f32(bias)), L.ptr(_f32(dW)), L.ptr(_f32(db))
+        else:
+            br.kind, br.dilation = (1 if kind == "max" else 2), 1
+    if b.dtype != torch.bfloat16:
+        return None
+    a.b = b.struct()
+    a.add_coeff = L.ptr(_f32(add_coeff))
+    return a
+
+
+def ms_temporal_supported(a):
+    return a is not None and bool(L.lib().dsg_ms_temporal_supported(C.byref(a)))
+
+
+def ms_temporal_fwd(a, feat, oglob, stat_sum, stat_sq):
+    a.feat, a.ld_feat = L.ptr(feat), _ld(feat)
+    a.oglob = L.ptr(oglob)
+    a.stat_sum, a.stat_sq = L.ptr(stat_sum), L.ptr(stat_sq)
+    es = feat.element_size()
+    nbytes = a.n_samples * (a.T_in * (a.V + a.has_ext) + a.T_out * a.V) * a.C * es
+    L.call("dsg_ms_temporal_fwd", C.byref(a), L.stream(), nbytes=nbytes)
+
+
+def ms_temporal_bwd(a, dfeat, e, oglob, e_sum, e_sq, dadd_coeff):
+    dfeat = as_act(dfeat)
+    a.dfeat = dfeat.struct()
+    a.e, a.ld_e = L.ptr(e), _ld(e)
+    a.oglob = L.ptr(oglob)
+    a.e_sum, a.e_sq = L.ptr(e_sum), L.ptr(e_sq)
+    a.dadd_coeff = L.ptr(_f32(dadd_coeff))
+    es = e.element_size()
+    nbytes = a.n_samples * (2 * a.T_in * (a.V + a.has_ext) + (2 if dfeat.x2 is not None else 1) * a.T_out * a.V) * a.C * es
+    L.call("dsg_ms_temporal_bwd_data", C.byref(a), L.stream(), nbytes=nbytes)
+    L.call("dsg_ms_temporal_bwd_weight", C.byref(a), L.stream(), nbytes=nbytes)
 
 
 def sgd_step(p, grad, buf, lr, momentum, wd, nesterov, grad_scale=1.0):

@@ -259,6 +259,49 @@ typedef struct dsg_ms_combine_args {
 int dsg_ms_combine_fwd(const dsg_ms_combine_args* a, void* stream);
 int dsg_ms_combine_bwd(const dsg_ms_combine_args* a, void* stream);
 
+/* ---- dsg_ms_temporal_fwd / _bwd_data / _bwd_weight -------------------------------------------------------------
+ * The whole branch stage of the multi-scale temporal unit in one kernel per direction (tcn.py:383-396, 407-420):
+ * dilated (3 x 1) convolutions of the conv branches as an implicit GEMM on tcgen05 (the post-BN-ReLU tile is staged
+ * once in shared memory, each tap is a shifted UMMA descriptor into it), the 3x1 max-pool branch, the strided
+ * pass-through branch and `local + global (x) add_coeff`, writing complete `feat` rows (and BatchNorm statistics for
+ * transform.0).  bf16 only; shapes it does not take (fp32, V+1 > 32, kernel size != 3, > 8 branches) are run by the
+ * per-branch path (dsg_conv_gemm + dsg_ms_combine_*).
+ *   fwd        : b (raw branch pre-activations + BN coefficients) -> feat [n,T_out,V,C], oglob [n,T_out,C]
+ *   bwd_data   : dfeat -> e [n,T_in,Vp,C] (gradient w.r.t. the pre-ReLU branch activations, masked; pass range: plain),
+ *                BN-backward sums e_sum/e_sq (partner = b raw), dadd_coeff
+ *   bwd_weight : dW/db of the temporal convolutions (atomic accumulation, zero-initialised by the caller) */
+typedef struct dsg_ms_branch {
+    int kind;             /* 0 = temporal conv, 1 = max-pool(3), 2 = pass-through ('1x1') */
+    int lo, hi;           /* channel range */
+    int dilation;
+    const float* W;       /* [w, w, 3, 1] */
+    const float* bias;    /* [w] */
+    float* dW;
+    float* db;
+} dsg_ms_branch;
+
+typedef struct dsg_ms_temporal_args {
+    int n_samples, T_in, T_out, stride, V, has_ext, C, n_branches;
+    dsg_ms_branch br[8];
+    dsg_act_src b;        /* [n,T_in,Vp,C] bf16; a1/b1 = BN coefficients (identity on the pass range) */
+    const float* add_coeff;
+    void* feat;
+    long long ld_feat;
+    float* oglob;
+    double* stat_sum;
+    double* stat_sq;
+    dsg_act_src dfeat;    /* [n,T_out,V,C] */
+    void* e;
+    long long ld_e;
+    double* e_sum;
+    double* e_sq;
+    float* dadd_coeff;
+} dsg_ms_temporal_args;
+int dsg_ms_temporal_supported(const dsg_ms_temporal_args* a);
+int dsg_ms_temporal_fwd(const dsg_ms_temporal_args* a, void* stream);
+int dsg_ms_temporal_bwd_data(const dsg_ms_temporal_args* a, void* stream);
+int dsg_ms_temporal_bwd_weight(const dsg_ms_temporal_args* a, void* stream);
+
 /* ---- dsg_pointwise --------------------------------------------------------------------------
  * out(r,c) = src(r,c) (any activation source: BN-apply, +residual, ReLU), optional mask
  * [mask(r,c) > 0], optional statistics (as in dsg_conv_gemm; partner may have its own dtype);

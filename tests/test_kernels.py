@@ -168,6 +168,21 @@ def test_tmean_and_pointwise(dev, dtype):
     close(out, ref, dtype, "pointwise")
     close(ss, ref.sum(0), dtype)
     close(sq, (ref * partner).sum(0), dtype)
+    # same op with everything in the activation dtype and 16-byte aligned (C % 8 == 0): the vectorised path for bf16
+    Cv = 72
+    xv, x2v, mkv, pv = (rnd(n * T * V, Cv, dev=dev, dtype=dtype) for _ in range(4))
+    av, bv, a2v, b2v = torch.rand(Cv, device=dev) + 0.5, rnd(Cv, dev=dev), torch.rand(Cv, device=dev) + 0.5, rnd(Cv, dev=dev)
+    outv = torch.empty(n * T * V, Cv, dtype=dtype, device=dev)
+    ss, sq = torch.zeros(Cv, dtype=torch.float64, device=dev), torch.zeros(Cv, dtype=torch.float64, device=dev)
+    ops.pointwise(ops.Act(xv, av, bv, x2v, a2v, b2v, relu=True), outv, mask=ops.Act(mkv, av, bv), stat_sum=ss, stat_sq=sq, partner=pv)
+    refv = torch.relu(xv.float() * av + bv + x2v.float() * a2v + b2v) * ((mkv.float() * av + bv) > 0)
+    close(outv, refv, dtype, "pointwise vec")
+    close(ss, refv.sum(0), dtype)
+    close(sq, (refv * pv.float()).sum(0), dtype)
+    ss.zero_(); sq.zero_()
+    ops.pointwise(xv, None, stat_sum=ss, stat_sq=sq)
+    close(ss, xv.float().sum(0), dtype)
+    close(sq, (xv.float() ** 2).sum(0), dtype)
 
 
 def _topo_setup(layout, R, n, cin, seed):
