@@ -217,13 +217,11 @@ def main():
         for n_, p in model.named_parameters():
             if n_.rsplit(".", 1)[-1] in ("alpha", "beta", "add_coeff"):
                 p.normal_(0, 0.1)
-    if world > 1:
-        for p in model.parameters():
-            torch.distributed.broadcast(p.data, 0)
+    dsgcn_b200.parallel.broadcast_parameters(model)
     B = args.batch
     train = args.mode == "train"
     model.train(train)
-    params = [p for n_, p in model.named_parameters() if "conv2_se" not in n_]      # never receive gradients (gcn.py:2253-2254)
+    params = dsgcn_b200.parallel.trainable_parameters(model)      # conv2_se never receives gradients (gcn.py:2253-2254)
     opt = torch.optim.SGD(params, foreach=True, **SGD) if train else None
 
     # synthetic NTU-shaped data: a pool of pinned host batches (e2e) and device-resident batches (value)
@@ -235,13 +233,7 @@ def main():
     sx, sy = dev_x[0].clone(), dev_y[0].clone()
 
     def allreduce_grads():
-        if world > 1:
-            flat = [p.grad for p in params if p.grad is not None]
-            buf = torch._utils._flatten_dense_tensors(flat)
-            torch.distributed.all_reduce(buf)
-            buf.div_(world)
-            for gsrc, gdst in zip(torch._utils._unflatten_dense_tensors(buf, flat), flat):
-                gdst.copy_(gsrc)
+        dsgcn_b200.parallel.allreduce_gradients(params, world)
 
     def device_step(x, y):
         if not train:

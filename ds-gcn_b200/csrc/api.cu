@@ -2,8 +2,8 @@
 #include "dsg_common.h"
 #include "conv_gemm.cuh"
 #include "conv_gemm_tc.cuh"
-#include "ms_temporal_tc.cuh"
 #include "graph_agg.cuh"
+#include "ms_temporal_tc.cuh"
 #include "topology.cuh"
 #include "misc.cuh"
 #include <stdio.h>

@@ -112,29 +112,43 @@ DSG_D void add8(float* v, const float* p) {
     v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w; v[4] += b.x; v[5] += b.y; v[6] += b.z; v[7] += b.w;
 }
 
+// Raw 16-byte loads of an activation source, issued early so several are in flight per thread
+struct Act8Raw { uint4 a, b; };
+DSG_D Act8Raw act8_issue(const ActSrc& s, long long row, int c) {
+    Act8Raw r;
+    r.a = *reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(s.x1) + row * s.ld1 + c);
+    r.b = s.x2 ? *reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(s.x2) + row * s.ld2 + c) : make_uint4(0u, 0u, 0u, 0u);
+    return r;
+}
+DSG_D void act8_finish_f(const ActSrc& s, const Act8Raw& r, int c, float* v) {
+    unpack8(r.a, v);
+    if (s.a1) mul8(v, s.a1 + c);
+    if (s.b1) add8(v, s.b1 + c);
+    if (s.x2) {
+        float w[8];
+        unpack8(r.b, w);
+        if (s.a2) mul8(w, s.a2 + c);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] += w[j];
+    }
+    if (s.b2) add8(v, s.b2 + c);
+    if (s.relu) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
+    }
+}
+DSG_D uint4 act8_finish(const ActSrc& s, const Act8Raw& r, int c) {
+    float v[8];
+    act8_finish_f(s, r, c, v);
+    return pack8(v);
+}
+
 // 8 consecutive channels of an activation source at (row, c) -> packed bf16x8 (vector path when aligned)
 DSG_D uint4 load_act8(const ActSrc& s, long long row, int c, int C, int vec_ok) {
+    if (vec_ok && c + 8 <= C) return act8_finish(s, act8_issue(s, row, c), c);
     float v[8];
-    if (vec_ok && c + 8 <= C) {
-        unpack8(*reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(s.x1) + row * s.ld1 + c), v);
-        if (s.a1) mul8(v, s.a1 + c);
-        if (s.b1) add8(v, s.b1 + c);
-        if (s.x2) {
-            float w[8];
-            unpack8(*reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(s.x2) + row * s.ld2 + c), w);
-            if (s.a2) mul8(w, s.a2 + c);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] += w[j];
-        }
-        if (s.b2) add8(v, s.b2 + c);
-        if (s.relu) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
-        }
-    } else {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = (c + j < C) ? act_value<bf16>(s, row, c + j) : 0.f;
-    }
+    for (int j = 0; j < 8; ++j) v[j] = (c + j < C) ? act_value<bf16>(s, row, c + j) : 0.f;
     return pack8(v);
 }
 
@@ -150,64 +164,81 @@ DSG_D void gemm_tail_vec(const dsg_conv_gemm_args& a, const float* Cs, const lon
     float s1[8], s2[8], bias[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) s1[j] = s2[j] = 0.f;
-    Act8 msk;
-    if (live) {
-        load8f(a.bias ? a.bias + c : nullptr, bias, 0.f);
-        if (a.has_mask) msk.init(a.mask, c);
-    }
+    if (live) load8f(a.bias ? a.bias + c : nullptr, bias, 0.f);
     const float inv_ext = a.contract_ext ? 1.f / (float)(rpf - 1) : 0.f;
     bf16* out = reinterpret_cast<bf16*>(a.out);
     if (live) {
-        for (int lr = rl; lr < n_out_rows; lr += 16) {
-            const long long r = orow[lr];
-            if (r < 0) continue;
-            const int fl = lr / Vout, j0 = lr - fl * Vout;
-            const float* cp = Cs + (fl * rpf + j0) * TC_LDC + cc * 8;
-            float v[8];
-            {
-                float4 x = *reinterpret_cast<const float4*>(cp), y = *reinterpret_cast<const float4*>(cp + 4);
-                v[0] = x.x; v[1] = x.y; v[2] = x.z; v[3] = x.w; v[4] = y.x; v[5] = y.y; v[6] = y.z; v[7] = y.w;
-            }
-            if (a.contract_ext) {
-                const float* ep = Cs + (fl * rpf + rpf - 1) * TC_LDC + cc * 8;
-                float4 x = *reinterpret_cast<const float4*>(ep), y = *reinterpret_cast<const float4*>(ep + 4);
-                v[0] = fmaf(x.x, inv_ext, v[0]); v[1] = fmaf(x.y, inv_ext, v[1]); v[2] = fmaf(x.z, inv_ext, v[2]); v[3] = fmaf(x.w, inv_ext, v[3]);
-                v[4] = fmaf(y.x, inv_ext, v[4]); v[5] = fmaf(y.y, inv_ext, v[5]); v[6] = fmaf(y.z, inv_ext, v[6]); v[7] = fmaf(y.w, inv_ext, v[7]);
+        constexpr int RB = 2;                                 // rows in flight per thread
+        const bf16* addp = reinterpret_cast<const bf16*>(a.add);
+        const bf16* add2p = reinterpret_cast<const bf16*>(a.add2);
+        const bf16* partp = reinterpret_cast<const bf16*>(a.partner);
+        for (int lr0 = rl; lr0 < n_out_rows; lr0 += 16 * RB) {
+            long long rr[RB];
+            uint4 ra[RB], ra2[RB], rp[RB];
+            Act8Raw rm[RB];
+#pragma unroll
+            for (int b = 0; b < RB; ++b) {
+                const int lr = lr0 + b * 16;
+                rr[b] = lr < n_out_rows ? orow[lr] : -1;
+                if (rr[b] < 0) continue;
+                if (addp) ra[b] = *reinterpret_cast<const uint4*>(addp + rr[b] * a.ld_add + c);
+                if (add2p) ra2[b] = *reinterpret_cast<const uint4*>(add2p + rr[b] * a.ld_add2 + c);
+                if (partp) rp[b] = *reinterpret_cast<const uint4*>(partp + rr[b] * a.ld_partner + c);
+                if (a.has_mask) rm[b] = act8_issue(a.mask, rr[b], c);
             }
 #pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] += bias[j];
-            if (a.add) {
-                float t[8];
-                unpack8(*reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(a.add) + r * a.ld_add + c), t);
+            for (int b = 0; b < RB; ++b) {
+                const long long r = rr[b];
+                if (r < 0) continue;
+                const int lr = lr0 + b * 16;
+                const int fl = lr / Vout, j0 = lr - fl * Vout;
+                const float* cp = Cs + (fl * rpf + j0) * TC_LDC + cc * 8;
+                float v[8];
+                {
+                    float4 x = *reinterpret_cast<const float4*>(cp), y = *reinterpret_cast<const float4*>(cp + 4);
+                    v[0] = x.x; v[1] = x.y; v[2] = x.z; v[3] = x.w; v[4] = y.x; v[5] = y.y; v[6] = y.z; v[7] = y.w;
+                }
+                if (a.contract_ext) {
+                    const float* ep = Cs + (fl * rpf + rpf - 1) * TC_LDC + cc * 8;
+                    float4 x = *reinterpret_cast<const float4*>(ep), y = *reinterpret_cast<const float4*>(ep + 4);
+                    v[0] = fmaf(x.x, inv_ext, v[0]); v[1] = fmaf(x.y, inv_ext, v[1]); v[2] = fmaf(x.z, inv_ext, v[2]); v[3] = fmaf(x.w, inv_ext, v[3]);
+                    v[4] = fmaf(y.x, inv_ext, v[4]); v[5] = fmaf(y.y, inv_ext, v[5]); v[6] = fmaf(y.z, inv_ext, v[6]); v[7] = fmaf(y.w, inv_ext, v[7]);
+                }
 #pragma unroll
-                for (int j = 0; j < 8; ++j) v[j] += t[j];
-            }
-            if (a.add2) {
-                float t[8];
-                unpack8(*reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(a.add2) + r * a.ld_add2 + c), t);
+                for (int j = 0; j < 8; ++j) v[j] += bias[j];
+                if (addp) {
+                    float t[8];
+                    unpack8(ra[b], t);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) v[j] += t[j];
-            }
-            if (a.bcast) {
-                const float* bp = a.bcast + ((long long)osamp[lr] * Vout + j0) * a.N + c;
-                float4 x = *reinterpret_cast<const float4*>(bp), y = *reinterpret_cast<const float4*>(bp + 4);
-                v[0] = fmaf(x.x, a.bcast_scale, v[0]); v[1] = fmaf(x.y, a.bcast_scale, v[1]); v[2] = fmaf(x.z, a.bcast_scale, v[2]);
-                v[3] = fmaf(x.w, a.bcast_scale, v[3]); v[4] = fmaf(y.x, a.bcast_scale, v[4]); v[5] = fmaf(y.y, a.bcast_scale, v[5]);
-                v[6] = fmaf(y.z, a.bcast_scale, v[6]); v[7] = fmaf(y.w, a.bcast_scale, v[7]);
-            }
-            if (a.has_mask) {
-                float m[8];
-                msk.eval(r, m);
+                    for (int j = 0; j < 8; ++j) v[j] += t[j];
+                }
+                if (add2p) {
+                    float t[8];
+                    unpack8(ra2[b], t);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) v[j] = m[j] > 0.f ? v[j] : 0.f;
-            }
-            if (a.stat_sum) {
-                float p[8];
-                if (a.partner) unpack8(*reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(a.partner) + r * a.ld_partner + c), p);
+                    for (int j = 0; j < 8; ++j) v[j] += t[j];
+                }
+                if (a.bcast) {
+                    const float* bp = a.bcast + ((long long)osamp[lr] * Vout + j0) * a.N + c;
+                    float4 x = *reinterpret_cast<const float4*>(bp), y = *reinterpret_cast<const float4*>(bp + 4);
+                    v[0] = fmaf(x.x, a.bcast_scale, v[0]); v[1] = fmaf(x.y, a.bcast_scale, v[1]); v[2] = fmaf(x.z, a.bcast_scale, v[2]);
+                    v[3] = fmaf(x.w, a.bcast_scale, v[3]); v[4] = fmaf(y.x, a.bcast_scale, v[4]); v[5] = fmaf(y.y, a.bcast_scale, v[5]);
+                    v[6] = fmaf(y.z, a.bcast_scale, v[6]); v[7] = fmaf(y.w, a.bcast_scale, v[7]);
+                }
+                if (a.has_mask) {
+                    float m[8];
+                    act8_finish_f(a.mask, rm[b], c, m);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) { s1[j] += v[j]; s2[j] += v[j] * (a.partner ? p[j] : v[j]); }
+                    for (int j = 0; j < 8; ++j) v[j] = m[j] > 0.f ? v[j] : 0.f;
+                }
+                if (a.stat_sum) {
+                    float p[8];
+                    if (partp) unpack8(rp[b], p);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) { s1[j] += v[j]; s2[j] += v[j] * (partp ? p[j] : v[j]); }
+                }
+                *reinterpret_cast<uint4*>(out + r * a.ld_out + c) = pack8(v);
             }
-            *reinterpret_cast<uint4*>(out + r * a.ld_out + c) = pack8(v);
         }
     }
     if (a.stat_sum) {
@@ -239,7 +270,7 @@ DSG_D void gemm_tail_vec(const dsg_conv_gemm_args& a, const float* Cs, const lon
 // wmode: 0 = weights contiguous along k (ws_k == 1, 16-byte aligned rows): K-major B, vector loads
 //        1 = weights contiguous along n (ws_n == 1): MN-major B, vector loads
 //        2 = anything else (temporal taps): K-major B, scalar loads
-__global__ void __launch_bounds__(CG_THREADS) conv_gemm_tc_kernel(dsg_conv_gemm_args a, int Kp, int vec_ok, int wmode, int vec_tail) {
+__global__ void __launch_bounds__(CG_THREADS, 2) conv_gemm_tc_kernel(dsg_conv_gemm_args a, int Kp, int vec_ok, int wmode, int vec_tail) {
     DSG_DYN_SMEM(smem);
     __shared__ uint64_t mbar;
     __shared__ uint32_t tmem_base_s;
@@ -311,16 +342,42 @@ __global__ void __launch_bounds__(CG_THREADS) conv_gemm_tc_kernel(dsg_conv_gemm_
         if (!first) mbar_wait(&mbar, phase ^ 1);           // previous pass's MMAs have finished reading A/B
         // ---- A operand: item = (row group of 8, 4 chunks) per warp-iteration; lane = (chunk%4)*8 + row%8
         const int groups4 = (nch + 3) >> 2;
-        for (int it = warp; it < (TC_BM / 8) * groups4; it += CG_THREADS / 32) {
-            const int rg = it / groups4, g4 = it - rg * groups4;
-            const int r = rg * 8 + (lane & 7), kc = g4 * 4 + (lane >> 3);
-            if (kc >= nch) continue;
-            const int kv = kv0 + kc * 8;
-            const int tap = kv / Kp, k = kv - tap * Kp;
-            const long long sr = rowsrc[tap * TC_BM + r];
-            uint4 pk = make_uint4(0u, 0u, 0u, 0u);
-            if (sr >= 0 && k < a.K) pk = load_act8(a.src, sr, k, a.K, vec_ok);
-            *reinterpret_cast<uint4*>(Abase + op_off(r, kc, nch)) = pk;
+        const int n_it = (TC_BM / 8) * groups4;
+        constexpr int AB = 4;                               // items in flight per thread
+        for (int it0 = warp; it0 < n_it; it0 += (CG_THREADS / 32) * AB) {
+            Act8Raw raw[AB];
+            long long srs[AB];
+            int ks[AB], offs[AB];
+#pragma unroll
+            for (int b = 0; b < AB; ++b) {
+                const int it = it0 + b * (CG_THREADS / 32);
+                offs[b] = -1; srs[b] = -1; ks[b] = 0;
+                if (it < n_it) {
+                    const int rg = it / groups4, g4 = it - rg * groups4;
+                    const int r = rg * 8 + (lane & 7), kc = g4 * 4 + (lane >> 3);
+                    if (kc < nch) {
+                        const int kv = kv0 + kc * 8;
+                        const int tap = kv / Kp, k = kv - tap * Kp;
+                        offs[b] = (int)op_off(r, kc, nch);
+                        ks[b] = k;
+                        const long long sr = rowsrc[tap * TC_BM + r];
+                        if (sr >= 0 && k < a.K) {
+                            srs[b] = sr;
+                            if (vec_ok && k + 8 <= a.K) raw[b] = act8_issue(a.src, sr, k);
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int b = 0; b < AB; ++b) {
+                if (offs[b] < 0) continue;
+                uint4 pk = make_uint4(0u, 0u, 0u, 0u);
+                if (srs[b] >= 0) {
+                    if (vec_ok && ks[b] + 8 <= a.K) pk = act8_finish(a.src, raw[b], ks[b]);
+                    else pk = load_act8(a.src, srs[b], ks[b], a.K, 0);
+                }
+                *reinterpret_cast<uint4*>(Abase + offs[b]) = pk;
+            }
         }
         // ---- B operand: weights fp32 -> bf16
         if (wmode == 0) {              // rows = output channels, 8 consecutive k per 16-byte item

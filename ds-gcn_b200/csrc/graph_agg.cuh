@@ -21,10 +21,53 @@ DSG_D void agg_store(const dsg_graph_agg_args& a, long long orow, int ch, float 
     stf<T>(reinterpret_cast<T*>(a.out) + orow * a.ld_out + ch, v);
 }
 
+// 8 consecutive channels of an activation source (vector path for aligned bf16, scalar otherwise) -> fp32
+template <class T> DSG_D void agg_load8(const ActSrc& s, long long row, int c, int C, bool vec, float* v);
+template <> DSG_D void agg_load8<bf16>(const ActSrc& s, long long row, int c, int C, bool vec, float* v) {
+    if (vec && c + 8 <= C) {
+        unpack8(*reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(s.x1) + row * s.ld1 + c), v);
+        if (s.a1) { float t[8]; load8f(s.a1 + c, t, 1.f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] *= t[j]; }
+        if (s.b1) { float t[8]; load8f(s.b1 + c, t, 0.f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] += t[j]; }
+        if (s.x2) {
+            float w[8];
+            unpack8(*reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(s.x2) + row * s.ld2 + c), w);
+            if (s.a2) { float t[8]; load8f(s.a2 + c, t, 1.f);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) w[j] *= t[j]; }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] += w[j];
+        }
+        if (s.b2) { float t[8]; load8f(s.b2 + c, t, 0.f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] += t[j]; }
+        if (s.relu) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = (c + j < C) ? act_value<bf16>(s, row, c + j) : 0.f;
+    }
+}
+template <> DSG_D void agg_load8<float>(const ActSrc& s, long long row, int c, int C, bool, float* v) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = (c + j < C) ? act_value<float>(s, row, c + j) : 0.f;
+}
+
+constexpr int AG_TCH = 8;      // frames staged per step
+
+// Dynamic contraction: the per-sample adjacency slice (32 channels) and AG_TCH frames of the operand live in shared
+// memory (fp32, channel fastest: conflict-free); a warp owns joints w, w+8, ... and keeps the adjacency column in
+// registers, so the inner loop is one shared load + FMA per (frame, source joint).
 template <class T, int V>
-__global__ void __launch_bounds__(AG_THREADS) agg_dyn_kernel(dsg_graph_agg_args a, int t_chunk) {
+__global__ void __launch_bounds__(AG_THREADS) agg_dyn_kernel(dsg_graph_agg_args a, int t_chunk, int vec) {
     DSG_DYN_SMEM(smem_raw);
     float* adj = reinterpret_cast<float*>(smem_raw);      // [V*V][32]
+    float* Ps = adj + V * V * 32;                         // [AG_TCH][V][32]
     DSG_SHARED float s_red[2][AG_THREADS / 32][32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n = blockIdx.x, kc0 = blockIdx.y * 32;
@@ -32,38 +75,50 @@ __global__ void __launch_bounds__(AG_THREADS) agg_dyn_kernel(dsg_graph_agg_args 
     const int tend = tbeg + t_chunk < a.T ? tbeg + t_chunk : a.T;
     const int ch = kc0 + lane;
     const bool ch_ok = ch < a.KC;
-    const T* adyn = reinterpret_cast<const T*>(a.adyn) + (long long)n * V * V * a.KC;
-    for (int idx = tid; idx < V * V * 32; idx += AG_THREADS) {
-        int l = idx & 31, uw = idx >> 5;
-        float v = (kc0 + l < a.KC) ? ldf<T>(adyn + (long long)uw * a.KC + kc0 + l) : 0.f;
-        int dst = uw;
-        if (a.mode == 1) { int u = uw / V, w = uw - u * V; dst = w * V + u; }
-        adj[dst * 32 + l] = v;
-    }
-    __syncthreads();
-    float s1 = 0.f, s2 = 0.f;
-    for (int tg = tbeg + warp * AG_TF; tg < tend; tg += (AG_THREADS / 32) * AG_TF) {
-        float p[AG_TF][V];
+    {   // adjacency slice (transposed on the fly for the gradient w.r.t. p)
+        const T* adyn = reinterpret_cast<const T*>(a.adyn) + (long long)n * V * V * a.KC;
+        ActSrc as{};
+        as.x1 = adyn; as.ld1 = a.KC;
+        const bool avec = vec && ((uintptr_t)a.adyn % 16 == 0) && (a.KC % 8 == 0);
+        for (int idx = tid; idx < V * V * 4; idx += AG_THREADS) {
+            const int q = idx & 3, uw = idx >> 2;
+            float v[8];
+            agg_load8<T>(as, uw, kc0 + q * 8, a.KC, avec, v);
+            int dst = uw;
+            if (a.mode == 1) { int u = uw / V, w = uw - u * V; dst = w * V + u; }
 #pragma unroll
-        for (int f = 0; f < AG_TF; ++f) {
-            const bool ok = ch_ok && (tg + f < tend);
-            const long long r0 = ((long long)n * a.T + tg + f) * V;
-#pragma unroll
-            for (int u = 0; u < V; ++u) p[f][u] = ok ? act_value<T>(a.src, r0 + u, ch) : 0.f;
+            for (int j = 0; j < 8; ++j) adj[dst * 32 + q * 8 + j] = v[j];
         }
-        for (int w = 0; w < V; ++w) {
-            float acc[AG_TF];
+    }
+    float s1 = 0.f, s2 = 0.f;
+    for (int t0 = tbeg; t0 < tend; t0 += AG_TCH) {
+        __syncthreads();
+        for (int idx = tid; idx < AG_TCH * V * 4; idx += AG_THREADS) {
+            const int q = idx & 3, rv = idx >> 2;          // rv = tt*V + u
+            const int tt = rv / V;
+            float v[8];
+            if (t0 + tt < tend) agg_load8<T>(a.src, ((long long)n * a.T + t0) * V + rv, kc0 + q * 8, a.KC, vec != 0, v);
+            else {
 #pragma unroll
-            for (int f = 0; f < AG_TF; ++f) acc[f] = 0.f;
-#pragma unroll
-            for (int u = 0; u < V; ++u) {
-                const float av = adj[(u * V + w) * 32 + lane];
-#pragma unroll
-                for (int f = 0; f < AG_TF; ++f) acc[f] = fmaf(p[f][u], av, acc[f]);
+                for (int j = 0; j < 8; ++j) v[j] = 0.f;
             }
+            float4* dst = reinterpret_cast<float4*>(Ps + rv * 32 + q * 8);
+            dst[0] = make_float4(v[0], v[1], v[2], v[3]);
+            dst[1] = make_float4(v[4], v[5], v[6], v[7]);
+        }
+        __syncthreads();
+        for (int w = warp; w < V; w += AG_THREADS / 32) {
+            float av[V];
 #pragma unroll
-            for (int f = 0; f < AG_TF; ++f)
-                if (ch_ok && tg + f < tend) agg_store<T>(a, ((long long)n * a.T + tg + f) * V + w, ch, acc[f], s1, s2);
+            for (int u = 0; u < V; ++u) av[u] = adj[(u * V + w) * 32 + lane];
+#pragma unroll 2
+            for (int tt = 0; tt < AG_TCH; ++tt) {
+                if (t0 + tt >= tend) break;
+                float acc = 0.f;
+#pragma unroll
+                for (int u = 0; u < V; ++u) acc = fmaf(Ps[(tt * V + u) * 32 + lane], av[u], acc);
+                if (ch_ok) agg_store<T>(a, ((long long)n * a.T + t0 + tt) * V + w, ch, acc, s1, s2);
+            }
         }
     }
     if (a.stat_sum) {
@@ -148,61 +203,67 @@ __global__ void __launch_bounds__(AG_THREADS) agg_static_kernel(dsg_graph_agg_ar
     }
 }
 
-// dadyn[n,u,w,kc] = sum_t p[n,t,u,kc] * dy[n,t,w,kc]
-constexpr int DA_TCH = 4;
+// dadyn[n,u,w,kc] = sum_t p[n,t,u,kc] * dy[n,t,w,kc]: both operands staged per AG_TCH frames (vector loads, fp32,
+// channel fastest); a warp owns target joints w, w+8, ..., w+24 and keeps their 25 source-joint accumulators in registers.
+constexpr int DA_TCH = AG_TCH;
 template <class T, int V>
-__global__ void __launch_bounds__(AG_THREADS) agg_dadj_dyn_kernel(dsg_graph_agg_dadj_args a) {
+__global__ void __launch_bounds__(AG_THREADS) agg_dadj_dyn_kernel(dsg_graph_agg_dadj_args a, int vec) {
     DSG_DYN_SMEM(smem_raw);
     float* ps = reinterpret_cast<float*>(smem_raw);        // [DA_TCH][V][32]
     float* ds = ps + DA_TCH * V * 32;                      // [DA_TCH][V][32]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n = blockIdx.x, kc0 = blockIdx.y * 32;
     constexpr int NW = AG_THREADS / 32;
-    constexpr int UPW = (V + NW - 1) / NW;                 // u's per warp
-    float acc[UPW][V];
+    constexpr int WPW = (V + NW - 1) / NW;                 // target joints per warp
+    float acc[WPW][V];
 #pragma unroll
-    for (int i = 0; i < UPW; ++i)
+    for (int i = 0; i < WPW; ++i)
 #pragma unroll
-        for (int w = 0; w < V; ++w) acc[i][w] = 0.f;
+        for (int u = 0; u < V; ++u) acc[i][u] = 0.f;
     for (int t0 = 0; t0 < a.T; t0 += DA_TCH) {
         __syncthreads();
-        for (int idx = tid; idx < DA_TCH * V * 32; idx += AG_THREADS) {
-            int l = idx & 31, rv = idx >> 5;              // rv = tt*V + v
-            int tt = rv / V;
-            float pv = 0.f, dv = 0.f;
-            if (t0 + tt < a.T && kc0 + l < a.KC) {
-                long long r = ((long long)n * a.T + t0) * V + rv;
-                pv = act_value<T>(a.p, r, kc0 + l);
-                dv = act_value<T>(a.dy, r, kc0 + l);
+        for (int idx = tid; idx < DA_TCH * V * 4; idx += AG_THREADS) {
+            const int q = idx & 3, rv = idx >> 2;
+            const int tt = rv / V;
+            float pv[8], dv[8];
+            if (t0 + tt < a.T) {
+                const long long r = ((long long)n * a.T + t0) * V + rv;
+                agg_load8<T>(a.p, r, kc0 + q * 8, a.KC, vec != 0, pv);
+                agg_load8<T>(a.dy, r, kc0 + q * 8, a.KC, vec != 0, dv);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) pv[j] = dv[j] = 0.f;
             }
-            ps[idx] = pv;
-            ds[idx] = dv;
+            float4* d0 = reinterpret_cast<float4*>(ps + rv * 32 + q * 8);
+            d0[0] = make_float4(pv[0], pv[1], pv[2], pv[3]); d0[1] = make_float4(pv[4], pv[5], pv[6], pv[7]);
+            float4* d1 = reinterpret_cast<float4*>(ds + rv * 32 + q * 8);
+            d1[0] = make_float4(dv[0], dv[1], dv[2], dv[3]); d1[1] = make_float4(dv[4], dv[5], dv[6], dv[7]);
         }
         __syncthreads();
-#pragma unroll
+#pragma unroll 1
         for (int tt = 0; tt < DA_TCH; ++tt) {
-            float pu[UPW];
+            float dw[WPW];
 #pragma unroll
-            for (int i = 0; i < UPW; ++i) {
-                int u = warp + i * NW;
-                pu[i] = u < V ? ps[(tt * V + u) * 32 + lane] : 0.f;
+            for (int i = 0; i < WPW; ++i) {
+                const int w = warp + i * NW;
+                dw[i] = w < V ? ds[(tt * V + w) * 32 + lane] : 0.f;
             }
 #pragma unroll
-            for (int w = 0; w < V; ++w) {
-                const float d = ds[(tt * V + w) * 32 + lane];
+            for (int u = 0; u < V; ++u) {
+                const float p = ps[(tt * V + u) * 32 + lane];
 #pragma unroll
-                for (int i = 0; i < UPW; ++i) acc[i][w] = fmaf(pu[i], d, acc[i][w]);
+                for (int i = 0; i < WPW; ++i) acc[i][u] = fmaf(p, dw[i], acc[i][u]);
             }
         }
     }
     if (kc0 + lane < a.KC) {
 #pragma unroll
-        for (int i = 0; i < UPW; ++i) {
-            int u = warp + i * NW;
-            if (u < V) {
+        for (int i = 0; i < WPW; ++i) {
+            const int w = warp + i * NW;
+            if (w < V) {
 #pragma unroll
-                for (int w = 0; w < V; ++w)
-                    a.dadj[(((long long)n * V + u) * V + w) * a.KC + kc0 + lane] = acc[i][w];
+                for (int u = 0; u < V; ++u)
+                    a.dadj[(((long long)n * V + u) * V + w) * a.KC + kc0 + lane] = acc[i][u];
             }
         }
     }
@@ -233,14 +294,15 @@ template <class T, int V> static const char* launch_agg_v(const dsg_graph_agg_ar
     int slices = (a.KC + 31) / 32;
     long long base = (long long)a.n_samples * slices;
     int tsplit = (int)((2 * 148 + base - 1) / base);
-    int unit = (a.mode <= 1) ? (AG_THREADS / 32) * AG_TF : (AG_THREADS / 32);
+    int unit = (a.mode <= 1) ? AG_TCH : (AG_THREADS / 32);
     int t_chunk = (a.T + tsplit - 1) / tsplit;
     t_chunk = (t_chunk + unit - 1) / unit * unit;
     dim3 grid(a.n_samples, slices, (a.T + t_chunk - 1) / t_chunk);
     if (a.mode <= 1) {
-        size_t smem = (size_t)V * V * 32 * sizeof(float);
+        size_t smem = (size_t)(V * V + AG_TCH * V) * 32 * sizeof(float);
+        int vec = (sizeof(T) == 2) && act8_ok(a.src) ? 1 : 0;
         DSG_SET_SMEM((agg_dyn_kernel<T, V>), smem);
-        dsg_launch(agg_dyn_kernel<T, V>, grid, dim3(AG_THREADS), smem, st, a, t_chunk);
+        dsg_launch(agg_dyn_kernel<T, V>, grid, dim3(AG_THREADS), smem, st, a, t_chunk, vec);
     } else {
         if (a.mode == 3 && a.stat_sum) return "graph_agg: statistics are not supported in mode 3";
         size_t smem = (size_t)a.Ksub * V * V * sizeof(float);
@@ -261,8 +323,9 @@ template <class T> static const char* launch_agg(const dsg_graph_agg_args& a, ds
 
 template <class T, int V> static const char* launch_dadj_v(const dsg_graph_agg_dadj_args& a, dsg_stream_t st) {
     size_t smem = (size_t)2 * DA_TCH * V * 32 * sizeof(float);
+    int vec = (sizeof(T) == 2) && act8_ok(a.p) && act8_ok(a.dy) ? 1 : 0;
     DSG_SET_SMEM((agg_dadj_dyn_kernel<T, V>), smem);
-    dsg_launch(agg_dadj_dyn_kernel<T, V>, dim3(a.n_samples, (a.KC + 31) / 32), dim3(AG_THREADS), smem, st, a);
+    dsg_launch(agg_dadj_dyn_kernel<T, V>, dim3(a.n_samples, (a.KC + 31) / 32), dim3(AG_THREADS), smem, st, a, vec);
     return dsg_launch_error();
 }
 

@@ -102,16 +102,16 @@ __global__ void __launch_bounds__(MS_THREADS) ms_temporal_fwd_kernel(dsg_ms_temp
             if (t < 0 || t >= a.T_in) continue;
             const int c8 = (ac0 + ac) * 8;
             const long long r = ((long long)n * a.T_in + t) * Vp + v;
-            float x[8];
+            float x[8], ca[8], cb[8];
             unpack8(*reinterpret_cast<const uint4*>(Bx + r * a.b.ld1 + c8), x);
+            load8f(a.b.a1 + c8, ca, 1.f);
+            load8f(a.b.b1 + c8, cb, 0.f);
             const int row = fi * 32 + v;
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
-                const int c = c8 + e, k = c - lo;
-                if (k >= 0 && k < g.w) {
-                    const float h = fmaxf(fmaf(x[e], a.b.a1[c], a.b.b1[c]), 0.f);
-                    *reinterpret_cast<bf16*>(Ht + op_off(row, k >> 3, g.nch) + (k & 7) * 2) = __float2bfloat16(h);
-                }
+                const int k = c8 + e - lo;
+                if (k >= 0 && k < g.w)
+                    *reinterpret_cast<bf16*>(Ht + op_off(row, k >> 3, g.nch) + (k & 7) * 2) = __float2bfloat16(fmaxf(fmaf(x[e], ca[e], cb[e]), 0.f));
             }
         }
         // ---- weights [co][ci][tap] fp32 -> three K-major [co][ci] bf16 tiles
@@ -321,8 +321,7 @@ __global__ void __launch_bounds__(MS_THREADS) ms_temporal_bwd_data_kernel(dsg_ms
     bf16* E_s = reinterpret_cast<bf16*>(smem + h_bytes + w_bytes);          // [MS_TO*Vp][C]
     const int mpw = mp_hi - mp_lo;                            // channels of the max/pass ranges (contiguous span)
     float* dg_s = reinterpret_cast<float*>(smem + h_bytes + w_bytes + MS_TO * Vp * C * 2);   // [6][mpw]
-    const bf16* X1 = reinterpret_cast<const bf16*>(a.dfeat.x1);
-    const bf16* X2 = reinterpret_cast<const bf16*>(a.dfeat.x2);
+    const bf16* Bx = reinterpret_cast<const bf16*>(a.b.x1);
 
     if (tid == 0) {
         mbar_init(&mbar, 1);
@@ -358,21 +357,13 @@ __global__ void __launch_bounds__(MS_THREADS) ms_temporal_bwd_data_kernel(dsg_ms
             if (tpo < 0 || tpo >= a.T_out) continue;
             const int c8 = (ac0 + ac) * 8;
             const long long r = ((long long)n * a.T_out + tpo) * V + v;
-            float x[8], y[8];
-            unpack8(*reinterpret_cast<const uint4*>(X1 + r * a.dfeat.ld1 + c8), x);
-            if (X2) unpack8(*reinterpret_cast<const uint4*>(X2 + r * a.dfeat.ld2 + c8), y);
+            float d[8];
+            agg_load8<bf16>(a.dfeat, r, c8, C, true, d);
             const int row = qi * 32 + v;
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
-                const int c = c8 + e, k = c - lo;
-                if (k >= 0 && k < g.w) {
-                    float d = x[e];
-                    if (a.dfeat.a1) d *= a.dfeat.a1[c];
-                    if (a.dfeat.b1) d += a.dfeat.b1[c];
-                    if (X2) d = fmaf(y[e], a.dfeat.a2 ? a.dfeat.a2[c] : 1.f, d);
-                    if (a.dfeat.b2) d += a.dfeat.b2[c];
-                    *reinterpret_cast<bf16*>(Dt + op_off(row, k >> 3, g.nch) + (k & 7) * 2) = __float2bfloat16(d);
-                }
+                const int k = c8 + e - lo;
+                if (k >= 0 && k < g.w) *reinterpret_cast<bf16*>(Dt + op_off(row, k >> 3, g.nch) + (k & 7) * 2) = __float2bfloat16(d[e]);
             }
         }
         // ---- W[co][ci][dt] -> B operand [ci][co] per tap
@@ -410,71 +401,114 @@ __global__ void __launch_bounds__(MS_THREADS) ms_temporal_bwd_data_kernel(dsg_ms
         issued |= (1 << j);
         phase ^= 1;
     }
-    // ---- max-pool / pass-through gradients on the CUDA cores
+    // ---- max-pool / pass-through gradients on the CUDA cores, 8 channels (one 16-byte chunk) per thread-item
     if (mpw > 0) {
         const int t_first = s * q0 + p_in;
         const int tp_lo = floordiv(t_first - 1, s);
+        const int ac0 = mp_lo >> 3, nac = ((mp_hi + 7) >> 3) - ac0;
         if (a.has_ext) {
-            for (int it = tid; it < 6 * mpw; it += MS_THREADS) {        // dO of the joint-mean column for the frames in reach
-                const int c = mp_lo + it % mpw, fi = it / mpw;
-                const int tpo = tp_lo + fi;
-                float sacc = 0.f;
+            for (int it = tid; it < 6 * nac; it += MS_THREADS) {         // dO of the joint-mean column for the frames in reach
+                const int ac = it % nac, fi = it / nac;
+                const int tpo = tp_lo + fi, c8 = (ac0 + ac) * 8;
+                float sacc[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) sacc[e] = 0.f;
                 if (tpo >= 0 && tpo < a.T_out)
-                    for (int v = 0; v < V; ++v) sacc = fmaf(ms_dfeat(a, n, tpo, v, c), a.add_coeff[v], sacc);
-                dg_s[it] = sacc;
+                    for (int v = 0; v < V; ++v) {
+                        float d[8];
+                        agg_load8<bf16>(a.dfeat, ((long long)n * a.T_out + tpo) * V + v, c8, C, true, d);
+                        const float w = a.add_coeff[v];
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) sacc[e] = fmaf(d[e], w, sacc[e]);
+                    }
+#pragma unroll
+                for (int e = 0; e < 8; ++e)
+                    if (c8 + e >= mp_lo && c8 + e < mp_hi) dg_s[fi * mpw + c8 + e - mp_lo] = sacc[e];
             }
             __syncthreads();
         }
-        for (int j = 0; j < a.n_branches; ++j) {
-            const int kind = a.br[j].kind;
-            if (kind == 0) continue;
-            const int lo = a.br[j].lo, w = a.br[j].hi - lo;
-            for (int it = tid; it < MS_TO * Vp * w; it += MS_THREADS) {
-                const int c = lo + it % w, rest = it / w;
-                const int vv = rest % Vp, i = rest / Vp;
-                const int t = s * (q0 + i) + p_in;
-                if (t >= a.T_in) continue;
-                float e = 0.f;
-                if (kind == 2) {
-                    if (t % s == 0 && t / s < a.T_out) {
-                        const int tpo = t / s;
-                        e = (vv < V) ? ms_dfeat(a, n, tpo, vv, c) : dg_s[(tpo - tp_lo) * mpw + c - mp_lo];
-                    }
-                } else if (ms_preact(a, n, t, vv, c, Vp) > 0.f) {
+        for (int it = tid; it < MS_TO * Vp * nac; it += MS_THREADS) {
+            const int ac = it % nac, rest = it / nac;
+            const int vv = rest % Vp, i = rest / Vp;
+            const int t = s * (q0 + i) + p_in, c8 = (ac0 + ac) * 8;
+            if (t >= a.T_in) continue;
+            int kind[8];
+            bool any_max = false;
 #pragma unroll
-                    for (int dt = -1; dt <= 1; ++dt) {                  // windows t' with s*t' + dt == t
-                        const int num = t - dt;
-                        if (num < 0 || num % s != 0) continue;
-                        const int tpo = num / s;
-                        if (tpo >= a.T_out) continue;
-                        float m = -3.0e38f;
-                        int am = -2;
-#pragma unroll
-                        for (int d2 = -1; d2 <= 1; ++d2) {              // first maximum wins (ATen max_pool2d)
-                            const int t2 = tpo * s + d2;
-                            if (t2 < 0 || t2 >= a.T_in) continue;
-                            const float h2 = fmaxf(ms_preact(a, n, t2, vv, c, Vp), 0.f);
-                            if (h2 > m) { m = h2; am = d2; }
-                        }
-                        if (am == dt) e += (vv < V) ? ms_dfeat(a, n, tpo, vv, c) : dg_s[(tpo - tp_lo) * mpw + c - mp_lo];
-                    }
-                }
-                E_s[(i * Vp + vv) * C + c] = __float2bfloat16(e);
+            for (int e = 0; e < 8; ++e) {
+                kind[e] = 3;
+                for (int j = 0; j < a.n_branches; ++j)
+                    if (a.br[j].kind != 0 && c8 + e >= a.br[j].lo && c8 + e < a.br[j].hi) kind[e] = a.br[j].kind;
+                any_max |= kind[e] == 1;
             }
+            float ca[8], cb[8];
+            load8f(a.b.a1 + c8, ca, 1.f);
+            load8f(a.b.b1 + c8, cb, 0.f);
+            float h[5][8];                                               // relu(bn(B)) at frames t-2 .. t+2 (-1: out of range)
+#pragma unroll
+            for (int dd = 0; dd < 5; ++dd) {
+                const int t2 = t + dd - 2;
+                if (any_max && t2 >= 0 && t2 < a.T_in) {
+                    float x[8];
+                    unpack8(*reinterpret_cast<const uint4*>(Bx + (((long long)n * a.T_in + t2) * Vp + vv) * a.b.ld1 + c8), x);
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) h[dd][e] = fmaxf(fmaf(x[e], ca[e], cb[e]), 0.f);
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) h[dd][e] = -1.f;
+                }
+            }
+            float eout[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) eout[e] = 0.f;
+#pragma unroll
+            for (int dt = -1; dt <= 1; ++dt) {                           // windows t' with s*t' + dt == t
+                const int num = t - dt;
+                if (num < 0 || num % s != 0) continue;
+                const int tpo = num / s;
+                if (tpo >= a.T_out) continue;
+                float d[8];
+                if (vv < V) agg_load8<bf16>(a.dfeat, ((long long)n * a.T_out + tpo) * V + vv, c8, C, true, d);
+                else {
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) d[e] = (c8 + e >= mp_lo && c8 + e < mp_hi) ? dg_s[(tpo - tp_lo) * mpw + c8 + e - mp_lo] : 0.f;
+                }
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    if (kind[e] == 2) { if (dt == 0) eout[e] = d[e]; continue; }
+                    if (kind[e] != 1) continue;
+                    // window tpo covers frames t-dt-1 .. t-dt+1 = h[1-dt .. 3-dt]; first maximum wins (ATen max_pool2d)
+                    float m = -3.0e38f;
+                    int am = -2;
+#pragma unroll
+                    for (int d2 = -1; d2 <= 1; ++d2) {
+                        const float hv = h[2 - dt + d2][e];
+                        if (hv >= 0.f && hv > m) { m = hv; am = d2; }
+                    }
+                    if (am == dt && h[2][e] > 0.f) eout[e] += d[e];
+                }
+            }
+#pragma unroll
+            for (int e = 0; e < 8; ++e)
+                if (kind[e] == 1 || kind[e] == 2) E_s[(i * Vp + vv) * C + c8 + e] = __float2bfloat16(eout[e]);
         }
     }
-    // ---- dadd_coeff for the output frames this CTA owns (plane 0: t' = q0 + i)
+    // ---- dadd_coeff for the output frames this CTA owns (plane 0: t' = q0 + i): thread = (8-channel chunk, joint)
     if (a.has_ext && p_in == 0) {
-        for (int i = 0; i < MS_TO; ++i) {
-            const int tpo = q0 + i;
-            if (tpo >= a.T_out) break;
-            for (int v = 0; v < V; ++v) {
-                float part = 0.f;
-                for (int c = tid; c < C; c += MS_THREADS)
-                    part = fmaf(ms_dfeat(a, n, tpo, v, c), a.oglob[((long long)n * a.T_out + tpo) * C + c], part);
-                part = warp_sum(part);
-                if (lane == 0) atomicAdd(&s_dadd[v], part);
+        const int nchunks = C >> 3;
+        for (int it = tid; it < nchunks * V; it += MS_THREADS) {
+            const int cc = it % nchunks, v = it / nchunks;
+            float part = 0.f;
+            for (int i = 0; i < MS_TO; ++i) {
+                const int tpo = q0 + i;
+                if (tpo >= a.T_out) break;
+                float d[8], og[8];
+                agg_load8<bf16>(a.dfeat, ((long long)n * a.T_out + tpo) * V + v, cc * 8, C, true, d);
+                load8f(a.oglob + ((long long)n * a.T_out + tpo) * C + cc * 8, og, 0.f);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) part = fmaf(d[e], og[e], part);
             }
+            atomicAdd(&s_dadd[v], part);
         }
     }
     if (issued) {
@@ -517,7 +551,6 @@ __global__ void __launch_bounds__(MS_THREADS) ms_temporal_bwd_data_kernel(dsg_ms
                 if (a.br[j].kind == 2 && c0 + e >= a.br[j].lo && c0 + e < a.br[j].hi) msk[e] = 0.f;     // pass range: no ReLU
         }
         bf16* E = reinterpret_cast<bf16*>(a.e);
-        const bf16* Bx = reinterpret_cast<const bf16*>(a.b.x1);
         for (int r = rl; r < MS_TO * Vp; r += lanes) {
             const int i = r / Vp, vv = r - i * Vp;
             const int t = s * (q0 + i) + p_in;
@@ -565,8 +598,6 @@ __global__ void __launch_bounds__(MS_THREADS) ms_temporal_bwd_weight_kernel(dsg_
     unsigned char* Ht = smem;
     unsigned char* Dt = smem + h_bytes;
     const bf16* Bx = reinterpret_cast<const bf16*>(a.b.x1);
-    const bf16* X1 = reinterpret_cast<const bf16*>(a.dfeat.x1);
-    const bf16* X2 = reinterpret_cast<const bf16*>(a.dfeat.x2);
     const int chunks_t = (a.T_out + MS_TO - 1) / MS_TO;
     const int n_tiles = a.n_samples * chunks_t;
 
@@ -605,15 +636,17 @@ __global__ void __launch_bounds__(MS_THREADS) ms_temporal_bwd_weight_kernel(dsg_
                 if (t < 0 || t >= a.T_in) continue;
                 const int c8 = (ac0 + ac) * 8;
                 const long long r = ((long long)n * a.T_in + t) * Vp + v;
-                float x[8];
+                float x[8], ca[8], cb[8];
                 unpack8(*reinterpret_cast<const uint4*>(Bx + r * a.b.ld1 + c8), x);
+                load8f(a.b.a1 + c8, ca, 1.f);
+                load8f(a.b.b1 + c8, cb, 0.f);
                 const int row = fi * 32 + v;
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
-                    const int c = c8 + e, k = c - lo;
+                    const int k = c8 + e - lo;
                     if (k >= 0 && k < g.w)
                         *reinterpret_cast<bf16*>(Ht + op_off(row, k >> 3, g.nch) + (k & 7) * 2) =
-                            __float2bfloat16(fmaxf(fmaf(x[e], a.b.a1[c], a.b.b1[c]), 0.f));
+                            __float2bfloat16(fmaxf(fmaf(x[e], ca[e], cb[e]), 0.f));
                 }
             }
             for (int it = tid; it < MS_TO * V * nac; it += MS_THREADS) {          // dO joint rows
@@ -623,20 +656,12 @@ __global__ void __launch_bounds__(MS_THREADS) ms_temporal_bwd_weight_kernel(dsg_
                 if (tpo >= a.T_out) continue;
                 const int c8 = (ac0 + ac) * 8;
                 const long long r = ((long long)n * a.T_out + tpo) * V + v;
-                float x[8], y[8];
-                unpack8(*reinterpret_cast<const uint4*>(X1 + r * a.dfeat.ld1 + c8), x);
-                if (X2) unpack8(*reinterpret_cast<const uint4*>(X2 + r * a.dfeat.ld2 + c8), y);
+                float d[8];
+                agg_load8<bf16>(a.dfeat, r, c8, a.C, true, d);
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
-                    const int c = c8 + e, k = c - lo;
-                    if (k >= 0 && k < g.w) {
-                        float d = x[e];
-                        if (a.dfeat.a1) d *= a.dfeat.a1[c];
-                        if (a.dfeat.b1) d += a.dfeat.b1[c];
-                        if (X2) d = fmaf(y[e], a.dfeat.a2 ? a.dfeat.a2[c] : 1.f, d);
-                        if (a.dfeat.b2) d += a.dfeat.b2[c];
-                        *reinterpret_cast<bf16*>(Dt + op_off(qi * 32 + v, k >> 3, g.nch) + (k & 7) * 2) = __float2bfloat16(d);
-                    }
+                    const int k = c8 + e - lo;
+                    if (k >= 0 && k < g.w) *reinterpret_cast<bf16*>(Dt + op_off(qi * 32 + v, k >> 3, g.nch) + (k & 7) * 2) = __float2bfloat16(d[e]);
                 }
             }
             __syncthreads();
