@@ -196,6 +196,50 @@ def dt(t_or_dtype):
         raise DsgError(f"unsupported activation dtype {d} (fp32 or bf16)")
 
 
+# ---- side stream: independent work (weight gradients) overlaps the data-gradient chain -------------------------
+side_enabled = os.environ.get("DSG_SIDE_STREAM", "1") != "0"
+_side_streams = {}
+_side_used = False
+keepalive = []        # tensors read by side-stream kernels stay referenced until join_side()
+
+
+class side_stream:
+    """`with side_stream():` launches the enclosed ABI calls on a second CUDA stream that first waits for everything
+    already queued on the current stream.  join_side() makes the current stream wait for it again.  Works under CUDA
+    graph capture (fork/join become graph edges)."""
+
+    def __enter__(self):
+        global _side_used
+        self.active = side_enabled and _is_device and torch.cuda.is_available()
+        if self.active:
+            main = torch.cuda.current_stream()
+            key = main.device.index
+            if key not in _side_streams:
+                _side_streams[key] = torch.cuda.Stream(device=main.device)
+            s = _side_streams[key]
+            s.wait_stream(main)
+            self.cm = torch.cuda.stream(s)
+            self.cm.__enter__()
+            _side_used = True
+        return self
+
+    def __exit__(self, *exc):
+        if self.active:
+            self.cm.__exit__(*exc)
+        return False
+
+
+def join_side():
+    global _side_used
+    if _side_used:
+        main = torch.cuda.current_stream()
+        s = _side_streams.get(main.device.index)
+        if s is not None:
+            main.wait_stream(s)
+        _side_used = False
+    keepalive.clear()
+
+
 profile = None        # when a list: (name, algorithmic_bytes, start_event, end_event) per ABI call (bench.py roofline leg)
 
 

@@ -152,6 +152,27 @@ DSG_D uint4 load_act8(const ActSrc& s, long long row, int c, int C, int vec_ok) 
     return pack8(v);
 }
 
+// v = relu?( x1*a1 + b + x2*a2 ) with the coefficients read from shared memory (16-byte broadcast loads)
+DSG_D void finish_smem(const Act8Raw& r, bool has_x2, int relu, const float* a1, const float* b, const float* a2, float* v) {
+    float x[8], c1[8], cb[8];
+    unpack8(r.a, x);
+    load8f(a1, c1, 1.f);
+    load8f(b, cb, 0.f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = fmaf(x[j], c1[j], cb[j]);
+    if (has_x2) {
+        float y[8], c2[8];
+        unpack8(r.b, y);
+        load8f(a2, c2, 1.f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = fmaf(y[j], c2[j], v[j]);
+    }
+    if (relu) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
+    }
+}
+
 constexpr int TC_LDC = TC_BN + 4;      // fp32 staging pitch: 33 x 16 B, conflict-free for 16-byte row-wise and column-wise access
 
 // Vectorised fused tail: thread = (8-column chunk, row lane); rows come from a per-CTA table (no per-element div/mod).
@@ -537,6 +558,21 @@ __global__ void __launch_bounds__(CG_THREADS) conv_wgrad_tc_kernel(dsg_conv_wgra
     FrameMap fm{a.taps, a.tap_step, a.tap_off, a.t_mul, a.t_div, a.T_in, a.T_out, a.Vin, a.ext_in};
     const bool do_bias = (a.db != nullptr) && kt == 0 && tap == 0;
 
+    __shared__ __align__(16) float cfA[3][WT_BK], cfB[3][WT_BN];      // staged per-channel coefficients (a1, b1+b2, a2) of both operands
+    for (int i = tid; i < WT_BK; i += CG_THREADS) {
+        const int ch = k0 + i;
+        const bool in = ch < a.K;
+        cfA[0][i] = (in && a.A.a1) ? a.A.a1[ch] : 1.f;
+        cfA[1][i] = ((in && a.A.b1) ? a.A.b1[ch] : 0.f) + ((in && a.A.b2) ? a.A.b2[ch] : 0.f);
+        cfA[2][i] = (in && a.A.a2) ? a.A.a2[ch] : 1.f;
+    }
+    for (int i = tid; i < WT_BN; i += CG_THREADS) {
+        const int ch = n0 + i;
+        const bool in = ch < a.N;
+        cfB[0][i] = (in && a.B.a1) ? a.B.a1[ch] : 1.f;
+        cfB[1][i] = ((in && a.B.b1) ? a.B.b1[ch] : 0.f) + ((in && a.B.b2) ? a.B.b2[ch] : 0.f);
+        cfB[2][i] = (in && a.B.a2) ? a.B.a2[ch] : 1.f;
+    }
     long long* rowsrc = reinterpret_cast<long long*>(smem);            // [WT_ROWS]
     long long* rowdst = rowsrc + WT_ROWS;                              // [WT_ROWS]
     unsigned char* Mop = smem + 2 * WT_ROWS * sizeof(long long);      // B side: [128 ch][rows_p]
@@ -580,7 +616,13 @@ __global__ void __launch_bounds__(CG_THREADS) conv_wgrad_tc_kernel(dsg_conv_wgra
             if (g8 >= gM) continue;
             uint4 pk = make_uint4(0u, 0u, 0u, 0u);
             const long long dr = rowdst[kk < WT_ROWS ? kk : 0];
-            if (kk < rows_tile && dr >= 0 && n0 + g8 * 8 < a.N) pk = load_act8(a.B, dr, n0 + g8 * 8, a.N, vecB);
+            if (kk < rows_tile && dr >= 0 && n0 + g8 * 8 < a.N) {
+                if (vecB && n0 + g8 * 8 + 8 <= a.N) {
+                    float v[8];
+                    finish_smem(act8_issue(a.B, dr, n0 + g8 * 8), a.B.x2 != nullptr, a.B.relu, &cfB[0][g8 * 8], &cfB[1][g8 * 8], &cfB[2][g8 * 8], v);
+                    pk = pack8(v);
+                } else pk = load_act8(a.B, dr, n0 + g8 * 8, a.N, 0);
+            }
             *reinterpret_cast<uint4*>(Mop + mn_off(g8, kk, gM)) = pk;
         }
         for (int it = warp; it < (rows_p / 8) * ((gN + 3) / 4); it += CG_THREADS / 32) {
@@ -589,7 +631,13 @@ __global__ void __launch_bounds__(CG_THREADS) conv_wgrad_tc_kernel(dsg_conv_wgra
             if (g8 >= gN) continue;
             uint4 pk = make_uint4(0u, 0u, 0u, 0u);
             const long long sr = rowsrc[kk < WT_ROWS ? kk : 0];
-            if (kk < rows_tile && sr >= 0 && k0 + g8 * 8 < a.K) pk = load_act8(a.A, sr, k0 + g8 * 8, a.K, vecA);
+            if (kk < rows_tile && sr >= 0 && k0 + g8 * 8 < a.K) {
+                if (vecA && k0 + g8 * 8 + 8 <= a.K) {
+                    float v[8];
+                    finish_smem(act8_issue(a.A, sr, k0 + g8 * 8), a.A.x2 != nullptr, a.A.relu, &cfA[0][g8 * 8], &cfA[1][g8 * 8], &cfA[2][g8 * 8], v);
+                    pk = pack8(v);
+                } else pk = load_act8(a.A, sr, k0 + g8 * 8, a.K, 0);
+            }
             *reinterpret_cast<uint4*>(Nop + mn_off(g8, kk, gN)) = pk;
         }
         if (a.ext_in || do_bias) __syncthreads();

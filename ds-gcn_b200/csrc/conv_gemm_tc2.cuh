@@ -64,6 +64,29 @@ __global__ void __launch_bounds__(T2_THREADS) conv_gemm_tc2_kernel(dsg_conv_gemm
     const int kpass = Kp < T2_KPASS ? Kp : T2_KPASS;
     unsigned char* Abase = smem;
     unsigned char* Bbase = smem + (size_t)128 * kpass * 2;
+    // per-channel coefficients staged once per CTA (defaults 1/0 filled in), so the per-chunk prologue never waits on
+    // a dependent global load: src: a1,b1(+b2),a2 over Kp channels; tail: bias, mask a1,b1(+b2),a2 over the 128-column tile
+    float* cf_a1 = reinterpret_cast<float*>(smem + (size_t)(128 + T2_BN) * kpass * 2);
+    float* cf_b = cf_a1 + Kp;
+    float* cf_a2 = cf_b + Kp;
+    float* tl_bias = cf_a2 + Kp;
+    float* tl_ma1 = tl_bias + T2_BN;
+    float* tl_mb = tl_ma1 + T2_BN;
+    float* tl_ma2 = tl_mb + T2_BN;
+    for (int k = tid; k < Kp; k += T2_THREADS) {
+        const bool in = k < a.K;
+        cf_a1[k] = (in && a.src.a1) ? a.src.a1[k] : 1.f;
+        cf_b[k] = ((in && a.src.b1) ? a.src.b1[k] : 0.f) + ((in && a.src.b2) ? a.src.b2[k] : 0.f);
+        cf_a2[k] = (in && a.src.a2) ? a.src.a2[k] : 1.f;
+    }
+    {
+        const int cch = n0 + tid;
+        const bool in = cch < a.N;
+        tl_bias[tid] = (in && a.bias) ? a.bias[cch] : 0.f;
+        tl_ma1[tid] = (in && a.has_mask && a.mask.a1) ? a.mask.a1[cch] : 1.f;
+        tl_mb[tid] = ((in && a.has_mask && a.mask.b1) ? a.mask.b1[cch] : 0.f) + ((in && a.has_mask && a.mask.b2) ? a.mask.b2[cch] : 0.f);
+        tl_ma2[tid] = (in && a.has_mask && a.mask.a2) ? a.mask.a2[cch] : 1.f;
+    }
 
     // ---- this thread's row
     const int fl = tid / rpf, j = tid - fl * rpf;
@@ -110,7 +133,11 @@ __global__ void __launch_bounds__(T2_THREADS) conv_gemm_tc2_kernel(dsg_conv_gemm
                 const int kc = kc0 + b, k = kv0 + kc * 8;
                 if (kc >= nch) continue;
                 uint4 pk = make_uint4(0u, 0u, 0u, 0u);
-                if (sr >= 0 && k < a.K) pk = act8_finish(a.src, raw[b], k);
+                if (sr >= 0 && k < a.K) {
+                    float v[8];
+                    finish_smem(raw[b], a.src.x2 != nullptr, a.src.relu, cf_a1 + k, cf_b + k, cf_a2 + k, v);
+                    pk = pack8(v);
+                }
                 *reinterpret_cast<uint4*>(Abase + op_off(tid, kc, nch)) = pk;
             }
         }
@@ -247,7 +274,7 @@ __global__ void __launch_bounds__(T2_THREADS) conv_gemm_tc2_kernel(dsg_conv_gemm
                 if (!(h ? live1 : live0)) continue;
                 float* vv = v + h * 8;
                 const int ch = c + h * 8;
-                if (a.bias) add8(vv, a.bias + ch);
+                add8(vv, tl_bias + c16 + h * 8);
                 if (addp) { float t[8]; unpack8(ra[h], t);
 #pragma unroll
                     for (int e = 0; e < 8; ++e) vv[e] += t[e]; }
@@ -262,7 +289,7 @@ __global__ void __launch_bounds__(T2_THREADS) conv_gemm_tc2_kernel(dsg_conv_gemm
                 }
                 if (a.has_mask) {
                     float m[8];
-                    act8_finish_f(a.mask, rm[h], ch, m);
+                    finish_smem(rm[h], a.mask.x2 != nullptr, 0, tl_ma1 + c16 + h * 8, tl_mb + c16 + h * 8, tl_ma2 + c16 + h * 8, m);
 #pragma unroll
                     for (int e = 0; e < 8; ++e) vv[e] = m[e] > 0.f ? vv[e] : 0.f;
                 }
@@ -312,7 +339,7 @@ static const char* launch_conv_gemm_tc2(const dsg_conv_gemm_args& a, dsg_stream_
     if (n_frames <= 0 || a.N <= 0) { *handled = true; return nullptr; }
     const int Kp = (a.K + 15) & ~15;
     const int kpass = Kp < T2_KPASS ? Kp : T2_KPASS;
-    const size_t smem = (size_t)(128 + T2_BN) * kpass * 2;
+    const size_t smem = (size_t)(128 + T2_BN) * kpass * 2 + (size_t)(3 * Kp + 4 * T2_BN) * sizeof(float);
     const int Fr = 128 / rpf;
     dim3 grid((unsigned)((n_frames + Fr - 1) / Fr), (unsigned)((a.N + T2_BN - 1) / T2_BN));
     cudaFuncSetAttribute(conv_gemm_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -58,6 +58,40 @@ template <> DSG_D void agg_load8<float>(const ActSrc& s, long long row, int c, i
     for (int j = 0; j < 8; ++j) v[j] = (c + j < C) ? act_value<float>(s, row, c + j) : 0.f;
 }
 
+// per-channel coefficients (a1, b1+b2, a2) of a source for the 32-channel slice starting at c0, staged in shared memory
+DSG_D void agg_stage_coefs(const ActSrc& s, int c0, int C, float* cf /* [3][32] */) {
+    const int l = threadIdx.x;
+    if (l < 32) {
+        const int ch = c0 + l;
+        const bool in = ch < C;
+        cf[l] = (in && s.a1) ? s.a1[ch] : 1.f;
+        cf[32 + l] = ((in && s.b1) ? s.b1[ch] : 0.f) + ((in && s.b2) ? s.b2[ch] : 0.f);
+        cf[64 + l] = (in && s.a2) ? s.a2[ch] : 1.f;
+    }
+}
+// 8 channels at slice offset q*8 with staged coefficients (vector path) or the generic path
+template <class T> DSG_D void agg_load8_s(const ActSrc& s, long long row, int c0, int q, int C, bool vec, const float* cf, float* v) {
+    agg_load8<T>(s, row, c0 + q * 8, C, vec, v);
+}
+template <> DSG_D void agg_load8_s<bf16>(const ActSrc& s, long long row, int c0, int q, int C, bool vec, const float* cf, float* v) {
+    const int c = c0 + q * 8;
+    if (vec && c + 8 <= C) {
+        float x[8];
+        unpack8(*reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(s.x1) + row * s.ld1 + c), x);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = fmaf(x[j], cf[q * 8 + j], cf[32 + q * 8 + j]);
+        if (s.x2) {
+            unpack8(*reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(s.x2) + row * s.ld2 + c), x);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = fmaf(x[j], cf[64 + q * 8 + j], v[j]);
+        }
+        if (s.relu) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
+        }
+    } else agg_load8<bf16>(s, row, c, C, false, v);
+}
+
 constexpr int AG_TCH = 8;      // frames staged per step
 
 // Dynamic contraction: the per-sample adjacency slice (32 channels) and AG_TCH frames of the operand live in shared
@@ -69,12 +103,22 @@ __global__ void __launch_bounds__(AG_THREADS) agg_dyn_kernel(dsg_graph_agg_args 
     float* adj = reinterpret_cast<float*>(smem_raw);      // [V*V][32]
     float* Ps = adj + V * V * 32;                         // [AG_TCH][V][32]
     DSG_SHARED float s_red[2][AG_THREADS / 32][32];
+    DSG_SHARED float cf_src[96];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n = blockIdx.x, kc0 = blockIdx.y * 32;
     const int tbeg = blockIdx.z * t_chunk;
     const int tend = tbeg + t_chunk < a.T ? tbeg + t_chunk : a.T;
     const int ch = kc0 + lane;
     const bool ch_ok = ch < a.KC;
+    agg_stage_coefs(a.src, kc0, a.KC, cf_src);
+    // this lane's mask coefficients (the mask is evaluated per output element of one channel)
+    float mk_a1 = 1.f, mk_b = 0.f, mk_a2 = 1.f;
+    if (a.has_mask && ch_ok) {
+        if (a.mask.a1) mk_a1 = a.mask.a1[ch];
+        if (a.mask.b1) mk_b += a.mask.b1[ch];
+        if (a.mask.b2) mk_b += a.mask.b2[ch];
+        if (a.mask.a2) mk_a2 = a.mask.a2[ch];
+    }
     {   // adjacency slice (transposed on the fly for the gradient w.r.t. p)
         const T* adyn = reinterpret_cast<const T*>(a.adyn) + (long long)n * V * V * a.KC;
         ActSrc as{};
@@ -97,7 +141,7 @@ __global__ void __launch_bounds__(AG_THREADS) agg_dyn_kernel(dsg_graph_agg_args 
             const int q = idx & 3, rv = idx >> 2;          // rv = tt*V + u
             const int tt = rv / V;
             float v[8];
-            if (t0 + tt < tend) agg_load8<T>(a.src, ((long long)n * a.T + t0) * V + rv, kc0 + q * 8, a.KC, vec != 0, v);
+            if (t0 + tt < tend) agg_load8_s<T>(a.src, ((long long)n * a.T + t0) * V + rv, kc0, q, a.KC, vec != 0, cf_src, v);
             else {
 #pragma unroll
                 for (int j = 0; j < 8; ++j) v[j] = 0.f;
@@ -117,7 +161,20 @@ __global__ void __launch_bounds__(AG_THREADS) agg_dyn_kernel(dsg_graph_agg_args 
                 float acc = 0.f;
 #pragma unroll
                 for (int u = 0; u < V; ++u) acc = fmaf(Ps[(tt * V + u) * 32 + lane], av[u], acc);
-                if (ch_ok) agg_store<T>(a, ((long long)n * a.T + t0 + tt) * V + w, ch, acc, s1, s2);
+                if (ch_ok) {
+                    const long long orow = ((long long)n * a.T + t0 + tt) * V + w;
+                    if (a.has_mask) {
+                        float mv = fmaf(ldf<T>(reinterpret_cast<const T*>(a.mask.x1) + orow * a.mask.ld1 + ch), mk_a1, mk_b);
+                        if (a.mask.x2) mv = fmaf(ldf<T>(reinterpret_cast<const T*>(a.mask.x2) + orow * a.mask.ld2 + ch), mk_a2, mv);
+                        if (!(mv > 0.f)) acc = 0.f;
+                    }
+                    if (a.stat_sum) {
+                        const float p = a.partner ? ldf<T>(reinterpret_cast<const T*>(a.partner) + orow * a.ld_partner + ch) : acc;
+                        s1 += acc;
+                        s2 += acc * p;
+                    }
+                    stf<T>(reinterpret_cast<T*>(a.out) + orow * a.ld_out + ch, acc);
+                }
             }
         }
     }
@@ -211,8 +268,11 @@ __global__ void __launch_bounds__(AG_THREADS) agg_dadj_dyn_kernel(dsg_graph_agg_
     DSG_DYN_SMEM(smem_raw);
     float* ps = reinterpret_cast<float*>(smem_raw);        // [DA_TCH][V][32]
     float* ds = ps + DA_TCH * V * 32;                      // [DA_TCH][V][32]
+    DSG_SHARED float cf_p[96], cf_d[96];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n = blockIdx.x, kc0 = blockIdx.y * 32;
+    agg_stage_coefs(a.p, kc0, a.KC, cf_p);
+    agg_stage_coefs(a.dy, kc0, a.KC, cf_d);
     constexpr int NW = AG_THREADS / 32;
     constexpr int WPW = (V + NW - 1) / NW;                 // target joints per warp
     float acc[WPW][V];
@@ -228,8 +288,8 @@ __global__ void __launch_bounds__(AG_THREADS) agg_dadj_dyn_kernel(dsg_graph_agg_
             float pv[8], dv[8];
             if (t0 + tt < a.T) {
                 const long long r = ((long long)n * a.T + t0) * V + rv;
-                agg_load8<T>(a.p, r, kc0 + q * 8, a.KC, vec != 0, pv);
-                agg_load8<T>(a.dy, r, kc0 + q * 8, a.KC, vec != 0, dv);
+                agg_load8_s<T>(a.p, r, kc0, q, a.KC, vec != 0, cf_p, pv);
+                agg_load8_s<T>(a.dy, r, kc0, q, a.KC, vec != 0, cf_d, dv);
             } else {
 #pragma unroll
                 for (int j = 0; j < 8; ++j) pv[j] = dv[j] = 0.f;

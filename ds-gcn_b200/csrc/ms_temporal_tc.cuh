@@ -57,6 +57,33 @@ DSG_D float ms_mp_out(const dsg_ms_temporal_args& a, int kind, int n, int tp, in
     return m;
 }
 
+constexpr int MS_CMAX = 512;        // channels the staged coefficient arrays hold
+
+// BN coefficients of the branch pre-activations, staged once per CTA
+DSG_D void ms_stage_b(const dsg_ms_temporal_args& a, float* cfa, float* cfb) {
+    for (int c = threadIdx.x; c < a.C; c += MS_THREADS) { cfa[c] = a.b.a1[c]; cfb[c] = a.b.b1[c]; }
+}
+// coefficients of the dfeat source (a1, b1+b2, a2)
+DSG_D void ms_stage_d(const dsg_ms_temporal_args& a, float* d1, float* db, float* d2) {
+    for (int c = threadIdx.x; c < a.C; c += MS_THREADS) {
+        d1[c] = a.dfeat.a1 ? a.dfeat.a1[c] : 1.f;
+        db[c] = (a.dfeat.b1 ? a.dfeat.b1[c] : 0.f) + (a.dfeat.b2 ? a.dfeat.b2[c] : 0.f);
+        d2[c] = a.dfeat.a2 ? a.dfeat.a2[c] : 1.f;
+    }
+}
+// 8 channels of dfeat at row r with staged coefficients
+DSG_D void ms_dfeat8(const dsg_ms_temporal_args& a, long long r, int c8, const float* d1, const float* db, const float* d2, float* v) {
+    float x[8];
+    unpack8(*reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(a.dfeat.x1) + r * a.dfeat.ld1 + c8), x);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = fmaf(x[e], d1[c8 + e], db[c8 + e]);
+    if (a.dfeat.x2) {
+        unpack8(*reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(a.dfeat.x2) + r * a.dfeat.ld2 + c8), x);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] = fmaf(x[e], d2[c8 + e], v[e]);
+    }
+}
+
 __global__ void __launch_bounds__(MS_THREADS) ms_temporal_fwd_kernel(dsg_ms_temporal_args a, int h_bytes, int w_bytes, int tmem_cols) {
     DSG_DYN_SMEM(smem);
     __shared__ uint64_t mbar;
@@ -68,6 +95,8 @@ __global__ void __launch_bounds__(MS_THREADS) ms_temporal_fwd_kernel(dsg_ms_temp
     unsigned char* Wt = smem + h_bytes;                      // 3 taps x [Kp x Kp]
     bf16* feat_s = reinterpret_cast<bf16*>(smem + h_bytes + w_bytes);      // [MS_TO*V][C]
     const bf16* Bx = reinterpret_cast<const bf16*>(a.b.x1);
+    __shared__ float cfa[MS_CMAX], cfb[MS_CMAX];
+    ms_stage_b(a, cfa, cfb);
 
     if (tid == 0) {
         mbar_init(&mbar, 1);
@@ -102,10 +131,10 @@ __global__ void __launch_bounds__(MS_THREADS) ms_temporal_fwd_kernel(dsg_ms_temp
             if (t < 0 || t >= a.T_in) continue;
             const int c8 = (ac0 + ac) * 8;
             const long long r = ((long long)n * a.T_in + t) * Vp + v;
-            float x[8], ca[8], cb[8];
+            float x[8];
             unpack8(*reinterpret_cast<const uint4*>(Bx + r * a.b.ld1 + c8), x);
-            load8f(a.b.a1 + c8, ca, 1.f);
-            load8f(a.b.b1 + c8, cb, 0.f);
+            const float* ca = cfa + c8;
+            const float* cb = cfb + c8;
             const int row = fi * 32 + v;
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
@@ -234,7 +263,7 @@ struct MsHostGeom { int h_bytes, w_bytes, tmem_cols, feat_bytes; bool ok; };
 static MsHostGeom ms_host_geom(const dsg_ms_temporal_args& a, int out_rows_per_frame) {
     MsHostGeom h{0, 0, 0, 0, true};
     int Vp = a.V + a.has_ext, s = a.stride, cols = 0;
-    if (Vp > 32 || a.n_branches > 8 || a.n_branches < 1 || s < 1 || a.C % 8 != 0 || (MS_THREADS % (a.C / 8)) != 0 || a.C / 8 > MS_THREADS) h.ok = false;
+    if (a.C > MS_CMAX || Vp > 32 || a.n_branches > 8 || a.n_branches < 1 || s < 1 || a.C % 8 != 0 || (MS_THREADS % (a.C / 8)) != 0 || a.C / 8 > MS_THREADS) h.ok = false;
     for (int j = 0; j < a.n_branches && h.ok; ++j) {
         if (a.br[j].kind != 0) continue;
         int w = a.br[j].hi - a.br[j].lo, Kp = (w + 15) & ~15, d = a.br[j].dilation;
@@ -322,6 +351,9 @@ __global__ void __launch_bounds__(MS_THREADS) ms_temporal_bwd_data_kernel(dsg_ms
     const int mpw = mp_hi - mp_lo;                            // channels of the max/pass ranges (contiguous span)
     float* dg_s = reinterpret_cast<float*>(smem + h_bytes + w_bytes + MS_TO * Vp * C * 2);   // [6][mpw]
     const bf16* Bx = reinterpret_cast<const bf16*>(a.b.x1);
+    __shared__ float cfa[MS_CMAX], cfb[MS_CMAX], dc1[MS_CMAX], dcb[MS_CMAX], dc2[MS_CMAX];
+    ms_stage_b(a, cfa, cfb);
+    ms_stage_d(a, dc1, dcb, dc2);
 
     if (tid == 0) {
         mbar_init(&mbar, 1);
@@ -358,7 +390,7 @@ __global__ void __launch_bounds__(MS_THREADS) ms_temporal_bwd_data_kernel(dsg_ms
             const int c8 = (ac0 + ac) * 8;
             const long long r = ((long long)n * a.T_out + tpo) * V + v;
             float d[8];
-            agg_load8<bf16>(a.dfeat, r, c8, C, true, d);
+            ms_dfeat8(a, r, c8, dc1, dcb, dc2, d);
             const int row = qi * 32 + v;
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
@@ -416,7 +448,7 @@ __global__ void __launch_bounds__(MS_THREADS) ms_temporal_bwd_data_kernel(dsg_ms
                 if (tpo >= 0 && tpo < a.T_out)
                     for (int v = 0; v < V; ++v) {
                         float d[8];
-                        agg_load8<bf16>(a.dfeat, ((long long)n * a.T_out + tpo) * V + v, c8, C, true, d);
+                        ms_dfeat8(a, ((long long)n * a.T_out + tpo) * V + v, c8, dc1, dcb, dc2, d);
                         const float w = a.add_coeff[v];
 #pragma unroll
                         for (int e = 0; e < 8; ++e) sacc[e] = fmaf(d[e], w, sacc[e]);
@@ -441,9 +473,8 @@ __global__ void __launch_bounds__(MS_THREADS) ms_temporal_bwd_data_kernel(dsg_ms
                     if (a.br[j].kind != 0 && c8 + e >= a.br[j].lo && c8 + e < a.br[j].hi) kind[e] = a.br[j].kind;
                 any_max |= kind[e] == 1;
             }
-            float ca[8], cb[8];
-            load8f(a.b.a1 + c8, ca, 1.f);
-            load8f(a.b.b1 + c8, cb, 0.f);
+            const float* ca = cfa + c8;
+            const float* cb = cfb + c8;
             float h[5][8];                                               // relu(bn(B)) at frames t-2 .. t+2 (-1: out of range)
 #pragma unroll
             for (int dd = 0; dd < 5; ++dd) {
@@ -468,7 +499,7 @@ __global__ void __launch_bounds__(MS_THREADS) ms_temporal_bwd_data_kernel(dsg_ms
                 const int tpo = num / s;
                 if (tpo >= a.T_out) continue;
                 float d[8];
-                if (vv < V) agg_load8<bf16>(a.dfeat, ((long long)n * a.T_out + tpo) * V + vv, c8, C, true, d);
+                if (vv < V) ms_dfeat8(a, ((long long)n * a.T_out + tpo) * V + vv, c8, dc1, dcb, dc2, d);
                 else {
 #pragma unroll
                     for (int e = 0; e < 8; ++e) d[e] = (c8 + e >= mp_lo && c8 + e < mp_hi) ? dg_s[(tpo - tp_lo) * mpw + c8 + e - mp_lo] : 0.f;
@@ -503,7 +534,7 @@ __global__ void __launch_bounds__(MS_THREADS) ms_temporal_bwd_data_kernel(dsg_ms
                 const int tpo = q0 + i;
                 if (tpo >= a.T_out) break;
                 float d[8], og[8];
-                agg_load8<bf16>(a.dfeat, ((long long)n * a.T_out + tpo) * V + v, cc * 8, C, true, d);
+                ms_dfeat8(a, ((long long)n * a.T_out + tpo) * V + v, cc * 8, dc1, dcb, dc2, d);
                 load8f(a.oglob + ((long long)n * a.T_out + tpo) * C + cc * 8, og, 0.f);
 #pragma unroll
                 for (int e = 0; e < 8; ++e) part = fmaf(d[e], og[e], part);
@@ -540,9 +571,9 @@ __global__ void __launch_bounds__(MS_THREADS) ms_temporal_bwd_data_kernel(dsg_ms
         const int nchunks = C >> 3, lanes = MS_THREADS / nchunks;
         const int cc = tid % nchunks, rl = tid / nchunks;
         const int c0 = cc * 8;
-        float s1[8], s2[8], ca[8], cb[8], msk[8];
-        load8f(a.b.a1 + c0, ca, 1.f);
-        load8f(a.b.b1 + c0, cb, 0.f);
+        float s1[8], s2[8], msk[8];
+        const float* ca = cfa + c0;
+        const float* cb = cfb + c0;
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
             s1[e] = s2[e] = 0.f;
@@ -598,6 +629,9 @@ __global__ void __launch_bounds__(MS_THREADS) ms_temporal_bwd_weight_kernel(dsg_
     unsigned char* Ht = smem;
     unsigned char* Dt = smem + h_bytes;
     const bf16* Bx = reinterpret_cast<const bf16*>(a.b.x1);
+    __shared__ float cfa[MS_CMAX], cfb[MS_CMAX], dc1[MS_CMAX], dcb[MS_CMAX], dc2[MS_CMAX];
+    ms_stage_b(a, cfa, cfb);
+    ms_stage_d(a, dc1, dcb, dc2);
     const int chunks_t = (a.T_out + MS_TO - 1) / MS_TO;
     const int n_tiles = a.n_samples * chunks_t;
 
@@ -636,10 +670,10 @@ __global__ void __launch_bounds__(MS_THREADS) ms_temporal_bwd_weight_kernel(dsg_
                 if (t < 0 || t >= a.T_in) continue;
                 const int c8 = (ac0 + ac) * 8;
                 const long long r = ((long long)n * a.T_in + t) * Vp + v;
-                float x[8], ca[8], cb[8];
+                float x[8];
                 unpack8(*reinterpret_cast<const uint4*>(Bx + r * a.b.ld1 + c8), x);
-                load8f(a.b.a1 + c8, ca, 1.f);
-                load8f(a.b.b1 + c8, cb, 0.f);
+                const float* ca = cfa + c8;
+                const float* cb = cfb + c8;
                 const int row = fi * 32 + v;
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
@@ -657,7 +691,7 @@ __global__ void __launch_bounds__(MS_THREADS) ms_temporal_bwd_weight_kernel(dsg_
                 const int c8 = (ac0 + ac) * 8;
                 const long long r = ((long long)n * a.T_out + tpo) * V + v;
                 float d[8];
-                agg_load8<bf16>(a.dfeat, r, c8, a.C, true, d);
+                ms_dfeat8(a, r, c8, dc1, dcb, dc2, d);
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
                     const int k = c8 + e - lo;

@@ -87,6 +87,7 @@ class _KernelFn(torch.autograd.Function):
         n, t, t_out, v = ctx.dims
         grads = {}
         dx = ctx.impl.bwd(ctx.save, to_rows(dout, _compute_dtype), grads)
+        ops.L.join_side()           # weight-gradient kernels ran on the side stream: rejoin before autograd sees them
         ctx.save = None
         dx = from_rows(dx, n, t, v)
         if dx.dtype != ctx.x_dtype:

@@ -146,7 +146,9 @@ def conv_wgrad(A, B, dW, *, n_samples, T_in, T_out, Vin, ws=None, db=None, taps=
     rows_out = n_samples * T_out * (Vin + int(ext_in))
     nbytes = n_samples * T_in * Vin * a.K * es * (2 if A.x2 is not None else 1) + rows_out * a.N * es * (2 if B.x2 is not None else 1)
     tag = dict(K=a.K, N=a.N, rows_out=rows_out, taps=taps, ext_in=int(ext_in)) if L.profile is not None else None
-    L.call("dsg_conv_wgrad", C.byref(a), L.stream(), nbytes=nbytes, tag=tag)
+    with L.side_stream():       # weight gradients are off the critical path: overlap them with the data-gradient chain
+        L.keepalive.extend((A, B, dW, db))
+        L.call("dsg_conv_wgrad", C.byref(a), L.stream(), nbytes=nbytes, tag=tag)
 
 
 def bn_job(mode, Cn, *, sum=None, sq=None, count=1.0, gamma=None, beta=None, running_mean=None, running_var=None,
@@ -355,7 +357,9 @@ def ms_temporal_bwd(a, dfeat, e, oglob, e_sum, e_sq, dadd_coeff):
     es = e.element_size()
     nbytes = a.n_samples * (2 * a.T_in * (a.V + a.has_ext) + (2 if dfeat.x2 is not None else 1) * a.T_out * a.V) * a.C * es
     L.call("dsg_ms_temporal_bwd_data", C.byref(a), L.stream(), nbytes=nbytes)
-    L.call("dsg_ms_temporal_bwd_weight", C.byref(a), L.stream(), nbytes=nbytes)
+    with L.side_stream():
+        L.keepalive.extend((a, dfeat, e, oglob))
+        L.call("dsg_ms_temporal_bwd_weight", C.byref(a), L.stream(), nbytes=nbytes)
 
 
 def sgd_step(p, grad, buf, lr, momentum, wd, nesterov, grad_scale=1.0):
