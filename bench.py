@@ -339,14 +339,18 @@ def main():
     h2d = host_x[0].numel() * 4 + host_y[0].numel() * 8
     d2h = 4 if train else B * NUM_CLASSES * 4
 
-    if rank != 0:
-        return
-    # ---- roofline leg: per-ABI-call CUDA events over extra eager steps (same shapes), dominant kernel
+    # ---- roofline leg: per-ABI-call CUDA events over extra eager steps (same shapes), dominant kernel.
+    #      Every rank runs the steps (they contain the gradient all-reduce); only rank 0 reports.
     L.profile = []
     for i in range(2):
         device_step(dev_x[i % 2], dev_y[i % 2])
     torch.cuda.synchronize()
     prof, L.profile = L.profile, None
+    if world > 1:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
+    if rank != 0:
+        return
     agg = {}
     for name, nbytes, a, b, _tag in prof:
         d = agg.setdefault(name, [0.0, 0, 0])
