@@ -88,7 +88,7 @@ class MsTemporalArgs(C.Structure):
     _fields_ = [("n_samples", c_int), ("T_in", c_int), ("T_out", c_int), ("stride", c_int), ("V", c_int), ("has_ext", c_int),
                 ("C", c_int), ("n_branches", c_int), ("br", MsBranch * 8), ("b", ActSrc), ("add_coeff", vp),
                 ("feat", vp), ("ld_feat", c_ll), ("oglob", vp), ("stat_sum", vp), ("stat_sq", vp),
-                ("dfeat", ActSrc), ("e", vp), ("ld_e", c_ll), ("e_sum", vp), ("e_sq", vp), ("dadd_coeff", vp)]
+                ("dfeat", ActSrc), ("e", vp), ("ld_e", c_ll), ("e_sum", vp), ("e_sq", vp), ("dadd_coeff", vp), ("wpack", vp)]
 
 
 class PointwiseArgs(C.Structure):
@@ -112,6 +112,7 @@ EXPORTS = {
     "dsg_ms_combine_bwd": (c_int, [C.POINTER(MsCombineArgs), vp]),
     "dsg_pointwise": (c_int, [C.POINTER(PointwiseArgs), vp]),
     "dsg_ms_temporal_supported": (c_int, [C.POINTER(MsTemporalArgs)]),
+    "dsg_ms_temporal_wpack_bytes": (c_ll, [C.POINTER(MsTemporalArgs)]),
     "dsg_ms_temporal_fwd": (c_int, [C.POINTER(MsTemporalArgs), vp]),
     "dsg_ms_temporal_bwd_data": (c_int, [C.POINTER(MsTemporalArgs), vp]),
     "dsg_ms_temporal_bwd_weight": (c_int, [C.POINTER(MsTemporalArgs), vp]),

@@ -171,6 +171,15 @@ int dsg_ms_temporal_supported(const dsg_ms_temporal_args* a) {
 #endif
 }
 
+long long dsg_ms_temporal_wpack_bytes(const dsg_ms_temporal_args* a) {
+#ifdef DSG_EMU
+    (void)a;
+    return 0;
+#else
+    return a ? dsg::tc::ms_wpack_bytes(*a) : 0;
+#endif
+}
+
 int dsg_ms_temporal_fwd(const dsg_ms_temporal_args* a, void* stream) {
 #ifdef DSG_EMU
     (void)a; (void)stream;

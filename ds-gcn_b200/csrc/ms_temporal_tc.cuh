@@ -21,22 +21,70 @@ constexpr int MS_THREADS = 256;
 DSG_D int floordiv(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
 DSG_D int posmod(int a, int b) { int m = a % b; return m < 0 ? m + b : m; }
 
+// A conv branch owns channels [lo,hi).  Its UMMA operands use the *8-aligned channel window* [lo8, lo8 + 8*nchw) that
+// covers it, so staging is whole 16-byte chunks; the few foreign channels inside the window meet zero weight rows.
 struct MsBranchGeom {
-    int w, Kp, nch, d, qmin, Fq, col;     // width, padded width, 16B chunks, dilation, first plane frame offset, frames per plane, TMEM column
+    int w, lo8, off, nchw, Kp, nch, d, qmin, Fq, col;   // width, window start, lo-lo8, window chunks, padded K (=N), chunks, dilation, ...
 };
+
+DSG_HD void ms_window(int lo, int hi, int& lo8, int& nchw, int& Kp) {
+    lo8 = lo & ~7;
+    nchw = ((hi + 7) >> 3) - (lo >> 3);
+    Kp = (nchw * 8 + 15) & ~15;
+}
 
 DSG_D MsBranchGeom ms_geom(const dsg_ms_temporal_args& a, int j, int s) {
     MsBranchGeom g;
     g.w = a.br[j].hi - a.br[j].lo;
-    g.Kp = (g.w + 15) & ~15;
+    ms_window(a.br[j].lo, a.br[j].hi, g.lo8, g.nchw, g.Kp);
+    g.off = a.br[j].lo - g.lo8;
     g.nch = g.Kp >> 3;
     g.d = a.br[j].dilation;
     g.qmin = floordiv(-g.d, s);
     g.Fq = MS_TO + floordiv(g.d, s) - g.qmin;
     g.col = 0;
     for (int i = 0; i < j; ++i)
-        if (a.br[i].kind == 0) g.col += ((a.br[i].hi - a.br[i].lo) + 15) & ~15;
+        if (a.br[i].kind == 0) { int l8, nw, kp; ms_window(a.br[i].lo, a.br[i].hi, l8, nw, kp); g.col += kp; }
     return g;
+}
+
+// byte offset of branch j's packed weight tiles inside wpack: [orientation 0: n=co,k=ci | 1: n=ci,k=co][tap][Kp x Kp] bf16
+DSG_HD long long ms_wpack_off(const dsg_ms_temporal_args& a, int j) {
+    long long o = 0;
+    for (int i = 0; i < j; ++i)
+        if (a.br[i].kind == 0) { int l8, nw, kp; ms_window(a.br[i].lo, a.br[i].hi, l8, nw, kp); o += 6LL * kp * kp * 2; }
+    return o;
+}
+
+// one CTA per (conv branch, orientation): zero-padded bf16 tiles in the K-major no-swizzle UMMA layout
+__global__ void ms_wpack_kernel(dsg_ms_temporal_args a) {
+    int j = -1, cnt = 0;
+    for (int i = 0; i < a.n_branches; ++i)
+        if (a.br[i].kind == 0) { if (cnt == (int)blockIdx.x) j = i; ++cnt; }
+    if (j < 0) return;
+    const int orient = blockIdx.y;
+    int lo8, nchw, Kp;
+    ms_window(a.br[j].lo, a.br[j].hi, lo8, nchw, Kp);
+    const int w = a.br[j].hi - a.br[j].lo, off = a.br[j].lo - lo8, nch = Kp >> 3;
+    unsigned char* dst = reinterpret_cast<unsigned char*>(a.wpack) + ms_wpack_off(a, j) + (long long)orient * 3 * Kp * Kp * 2;
+    for (int idx = threadIdx.x; idx < 3 * Kp * nch; idx += blockDim.x) {       // one 16-byte chunk (8 k) per item
+        const int kc = idx % nch, n = (idx / nch) % Kp, dt = idx / (nch * Kp);
+        float v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int k = kc * 8 + e;
+            const int co = (orient == 0 ? n : k) - off, ci = (orient == 0 ? k : n) - off;
+            v[e] = (co >= 0 && co < w && ci >= 0 && ci < w) ? a.br[j].W[((long long)co * w + ci) * 3 + dt] : 0.f;
+        }
+        *reinterpret_cast<uint4*>(dst + dt * Kp * Kp * 2 + op_off(n, kc, nch)) = pack8(v);
+    }
+}
+
+// copy branch j's three packed tiles (orientation o) into shared memory
+DSG_D void ms_load_w(const dsg_ms_temporal_args& a, int j, int orient, int Kp, unsigned char* Wt) {
+    const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const unsigned char*>(a.wpack) + ms_wpack_off(a, j) + (long long)orient * 3 * Kp * Kp * 2);
+    uint4* dst = reinterpret_cast<uint4*>(Wt);
+    for (int i = threadIdx.x; i < 3 * Kp * Kp * 2 / 16; i += MS_THREADS) dst[i] = src[i];
 }
 
 // branch pre-activation (post BN, no ReLU) at (sample n, input frame t, column j, channel c)
@@ -113,41 +161,28 @@ __global__ void __launch_bounds__(MS_THREADS) ms_temporal_fwd_kernel(dsg_ms_temp
     for (int j = 0; j < a.n_branches; ++j) {
         if (a.br[j].kind != 0) continue;
         const MsBranchGeom g = ms_geom(a, j, s);
-        const int lo = a.br[j].lo;
         if (issued) mbar_wait(&mbar, phase ^ 1);             // the previous branch's MMAs are done with Ht / Wt
-        // ---- zero the operand tiles (padding rows / channels must be exact zeros)
-        const int hb = s * g.Fq * 32 * g.Kp * 2, wb = 3 * g.Kp * g.Kp * 2;
-        for (int i = tid * 16; i < hb; i += MS_THREADS * 16) *reinterpret_cast<uint4*>(Ht + i) = make_uint4(0u, 0u, 0u, 0u);
-        for (int i = tid * 16; i < wb; i += MS_THREADS * 16) *reinterpret_cast<uint4*>(Wt + i) = make_uint4(0u, 0u, 0u, 0u);
-        __syncthreads();
-        // ---- stage relu(bn(B)) of this branch: item = (plane frame, joint row, aligned 8-channel chunk)
-        const int ac0 = lo >> 3, nac = ((a.br[j].hi + 7) >> 3) - ac0;
+        // ---- stage relu(bn(B)) over the branch's channel window: item = (plane frame, padded joint row, 16-byte chunk)
         const int nfr = s * g.Fq;
-        for (int it = tid; it < nfr * Vp * nac; it += MS_THREADS) {
-            const int ac = it % nac, rv = it / nac;
-            const int v = rv % Vp, fi = rv / Vp;
-            const int p = fi / g.Fq, qi = fi - p * g.Fq;
-            const int t = s * (tp0 + g.qmin + qi) + p;
-            if (t < 0 || t >= a.T_in) continue;
-            const int c8 = (ac0 + ac) * 8;
-            const long long r = ((long long)n * a.T_in + t) * Vp + v;
-            float x[8];
-            unpack8(*reinterpret_cast<const uint4*>(Bx + r * a.b.ld1 + c8), x);
-            const float* ca = cfa + c8;
-            const float* cb = cfb + c8;
-            const int row = fi * 32 + v;
+        for (int it = tid; it < nfr * 32 * g.nch; it += MS_THREADS) {
+            const int kc = it % g.nch, row = it / g.nch;
+            const int v = row & 31, fi = row >> 5;
+            uint4 pk = make_uint4(0u, 0u, 0u, 0u);
+            if (v < Vp && kc < g.nchw) {
+                const int p = fi / g.Fq, qi = fi - p * g.Fq;
+                const int t = s * (tp0 + g.qmin + qi) + p;
+                if (t >= 0 && t < a.T_in) {
+                    const int c8 = g.lo8 + kc * 8;
+                    float x[8];
+                    unpack8(*reinterpret_cast<const uint4*>(Bx + (((long long)n * a.T_in + t) * Vp + v) * a.b.ld1 + c8), x);
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-                const int k = c8 + e - lo;
-                if (k >= 0 && k < g.w)
-                    *reinterpret_cast<bf16*>(Ht + op_off(row, k >> 3, g.nch) + (k & 7) * 2) = __float2bfloat16(fmaxf(fmaf(x[e], ca[e], cb[e]), 0.f));
+                    for (int e = 0; e < 8; ++e) x[e] = fmaxf(fmaf(x[e], cfa[c8 + e], cfb[c8 + e]), 0.f);
+                    pk = pack8(x);
+                }
             }
+            *reinterpret_cast<uint4*>(Ht + op_off(row, kc, g.nch)) = pk;
         }
-        // ---- weights [co][ci][tap] fp32 -> three K-major [co][ci] bf16 tiles
-        for (int idx = tid; idx < g.w * g.w * 3; idx += MS_THREADS) {
-            const int dt = idx % 3, ci = (idx / 3) % g.w, co = idx / (3 * g.w);
-            *reinterpret_cast<bf16*>(Wt + dt * g.Kp * g.Kp * 2 + op_off(co, ci >> 3, g.nch) + (ci & 7) * 2) = __float2bfloat16(a.br[j].W[idx]);
-        }
+        ms_load_w(a, j, 0, g.Kp, Wt);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncthreads();
@@ -207,14 +242,15 @@ __global__ void __launch_bounds__(MS_THREADS) ms_temporal_fwd_kernel(dsg_ms_temp
                 tmem_ld16(tmem_d + ((uint32_t)(fl * 32) << 16) + (uint32_t)(g.col + c16), v);
 #pragma unroll
                 for (int e = 0; e < 16; ++e) {
-                    const int k = c16 + e;
-                    float val = v[e] + ((k < g.w) ? a.br[j].bias[k] : 0.f);
+                    const int k = c16 + e - g.off;                          // channel inside the branch (window column - offset)
+                    const bool in = k >= 0 && k < g.w;
+                    float val = v[e] + (in ? a.br[j].bias[k] : 0.f);
                     if (a.has_ext) {
                         const float glob = __shfl_sync(0xffffffffu, val, V);
-                        if (lane == V && k < g.w && tp < a.T_out) a.oglob[((long long)n * a.T_out + tp) * C + a.br[j].lo + k] = val;
+                        if (lane == V && in && tp < a.T_out) a.oglob[((long long)n * a.T_out + tp) * C + a.br[j].lo + k] = val;
                         val = fmaf(glob, addv, val);
                     }
-                    if (lane < V && k < g.w && tp < a.T_out) feat_s[(fl * V + lane) * C + a.br[j].lo + k] = __float2bfloat16(val);
+                    if (lane < V && in && tp < a.T_out) feat_s[(fl * V + lane) * C + a.br[j].lo + k] = __float2bfloat16(val);
                 }
             }
         }
@@ -266,8 +302,9 @@ static MsHostGeom ms_host_geom(const dsg_ms_temporal_args& a, int out_rows_per_f
     if (a.C > MS_CMAX || Vp > 32 || a.n_branches > 8 || a.n_branches < 1 || s < 1 || a.C % 8 != 0 || (MS_THREADS % (a.C / 8)) != 0 || a.C / 8 > MS_THREADS) h.ok = false;
     for (int j = 0; j < a.n_branches && h.ok; ++j) {
         if (a.br[j].kind != 0) continue;
-        int w = a.br[j].hi - a.br[j].lo, Kp = (w + 15) & ~15, d = a.br[j].dilation;
-        if (w < 1 || Kp > 128 || d < 1) { h.ok = false; break; }
+        int w = a.br[j].hi - a.br[j].lo, d = a.br[j].dilation, lo8, nchw, Kp;
+        ms_window(a.br[j].lo, a.br[j].hi, lo8, nchw, Kp);
+        if (w < 1 || Kp > 128 || d < 1 || !a.br[j].W || !a.br[j].bias) { h.ok = false; break; }
         int qmin = -((d + s - 1) / s), qmax = d / s;
         int Fq = MS_TO + qmax - qmin;
         int hb = s * Fq * 32 * Kp * 2, wb = 3 * Kp * Kp * 2;
@@ -288,6 +325,17 @@ static MsHostGeom ms_host_geom(const dsg_ms_temporal_args& a, int out_rows_per_f
     return h;
 }
 
+static long long ms_wpack_bytes(const dsg_ms_temporal_args& a) { return ms_wpack_off(a, a.n_branches); }
+
+static const char* ms_launch_wpack(const dsg_ms_temporal_args& a, dsg_stream_t st) {
+    int nconv = 0;
+    for (int j = 0; j < a.n_branches; ++j) nconv += a.br[j].kind == 0;
+    if (nconv == 0) return nullptr;
+    if (!a.wpack || (uintptr_t)a.wpack % 16 != 0) return "ms_temporal: wpack workspace missing or misaligned";
+    ms_wpack_kernel<<<dim3(nconv, 2), dim3(256), 0, st>>>(a);
+    return dsg_launch_error();
+}
+
 static bool ms_args_ok(const dsg_ms_temporal_args& a) {
     if (!a.b.x1 || a.b.x2 || !a.b.a1 || !a.b.b1 || a.b.a2 || a.b.b2) return false;
     if ((uintptr_t)a.b.x1 % 16 != 0 || a.b.ld1 % 8 != 0) return false;
@@ -300,6 +348,7 @@ static const char* launch_ms_temporal_fwd(const dsg_ms_temporal_args& a, dsg_str
     if ((uintptr_t)a.feat % 16 != 0 || a.ld_feat % 8 != 0) return "ms_temporal_fwd: feat must be 16-byte aligned";
     if (a.n_samples <= 0 || a.T_out <= 0) return nullptr;
     size_t smem = (size_t)h.h_bytes + h.w_bytes + h.feat_bytes;
+    if (const char* e = ms_launch_wpack(a, st)) return e;
     cudaFuncSetAttribute(ms_temporal_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     dim3 grid((a.T_out + MS_TO - 1) / MS_TO, a.n_samples);
     ms_temporal_fwd_kernel<<<grid, dim3(MS_THREADS), smem, st>>>(a, h.h_bytes, h.w_bytes, h.tmem_cols);
@@ -374,43 +423,36 @@ __global__ void __launch_bounds__(MS_THREADS) ms_temporal_bwd_data_kernel(dsg_ms
         const MsBranchGeom g = ms_geom(a, j, s);
         const MsBwdTaps tp = ms_bwd_taps(g.d, s, p_in);
         if (tp.n == 0) continue;
-        const int lo = a.br[j].lo;
         if (issued) mbar_wait(&mbar, phase ^ 1);
-        const int hb = tp.Fq * 32 * g.Kp * 2, wb = 3 * g.Kp * g.Kp * 2;
-        for (int i = tid * 16; i < hb; i += MS_THREADS * 16) *reinterpret_cast<uint4*>(Dt + i) = make_uint4(0u, 0u, 0u, 0u);
-        for (int i = tid * 16; i < wb; i += MS_THREADS * 16) *reinterpret_cast<uint4*>(Wt + i) = make_uint4(0u, 0u, 0u, 0u);
-        __syncthreads();
-        // ---- stage dO (joint rows): item = (output frame, joint, aligned 8-channel chunk)
-        const int ac0 = lo >> 3, nac = ((a.br[j].hi + 7) >> 3) - ac0;
-        for (int it = tid; it < tp.Fq * V * nac; it += MS_THREADS) {
-            const int ac = it % nac, rv = it / nac;
-            const int v = rv % V, qi = rv / V;
+        // ---- stage dO over the channel window (joint rows; padding rows and the joint-mean row start as zeros)
+        for (int it = tid; it < tp.Fq * 32 * g.nch; it += MS_THREADS) {
+            const int kc = it % g.nch, row = it / g.nch;
+            const int v = row & 31, qi = row >> 5;
+            uint4 pk = make_uint4(0u, 0u, 0u, 0u);
             const int tpo = q0 + tp.shmin + qi;
-            if (tpo < 0 || tpo >= a.T_out) continue;
-            const int c8 = (ac0 + ac) * 8;
-            const long long r = ((long long)n * a.T_out + tpo) * V + v;
-            float d[8];
-            ms_dfeat8(a, r, c8, dc1, dcb, dc2, d);
-            const int row = qi * 32 + v;
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-                const int k = c8 + e - lo;
-                if (k >= 0 && k < g.w) *reinterpret_cast<bf16*>(Dt + op_off(row, k >> 3, g.nch) + (k & 7) * 2) = __float2bfloat16(d[e]);
+            if (v < V && kc < g.nchw && tpo >= 0 && tpo < a.T_out) {
+                float d[8];
+                ms_dfeat8(a, ((long long)n * a.T_out + tpo) * V + v, g.lo8 + kc * 8, dc1, dcb, dc2, d);
+                pk = pack8(d);
             }
+            *reinterpret_cast<uint4*>(Dt + op_off(row, kc, g.nch)) = pk;
         }
-        // ---- W[co][ci][dt] -> B operand [ci][co] per tap
-        for (int idx = tid; idx < g.w * g.w * 3; idx += MS_THREADS) {
-            const int dt = idx % 3, ci = (idx / 3) % g.w, co = idx / (3 * g.w);
-            *reinterpret_cast<bf16*>(Wt + dt * g.Kp * g.Kp * 2 + op_off(ci, co >> 3, g.nch) + (co & 7) * 2) = __float2bfloat16(a.br[j].W[idx]);
-        }
+        ms_load_w(a, j, 1, g.Kp, Wt);                                   // B operand [n = ci][k = co]
         if (a.has_ext) {
             __syncthreads();
-            for (int it = tid; it < tp.Fq * g.w; it += MS_THREADS) {       // joint-mean row: sum_v dO[v] * add_coeff[v]
-                const int k = it % g.w, qi = it / g.w;
-                float sacc = 0.f;
-                for (int v = 0; v < V; ++v)
-                    sacc = fmaf(__bfloat162float(*reinterpret_cast<const bf16*>(Dt + op_off(qi * 32 + v, k >> 3, g.nch) + (k & 7) * 2)), a.add_coeff[v], sacc);
-                *reinterpret_cast<bf16*>(Dt + op_off(qi * 32 + V, k >> 3, g.nch) + (k & 7) * 2) = __float2bfloat16(sacc);
+            for (int it = tid; it < tp.Fq * g.nchw; it += MS_THREADS) {   // joint-mean row: sum_v dO[v] * add_coeff[v], 8 channels per item
+                const int kc = it % g.nchw, qi = it / g.nchw;
+                float sacc[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) sacc[e] = 0.f;
+                for (int v = 0; v < V; ++v) {
+                    float d[8];
+                    unpack8(*reinterpret_cast<const uint4*>(Dt + op_off(qi * 32 + v, kc, g.nch)), d);
+                    const float wv = a.add_coeff[v];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) sacc[e] = fmaf(d[e], wv, sacc[e]);
+                }
+                *reinterpret_cast<uint4*>(Dt + op_off(qi * 32 + V, kc, g.nch)) = pack8(sacc);
             }
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -556,8 +598,10 @@ __global__ void __launch_bounds__(MS_THREADS) ms_temporal_bwd_data_kernel(dsg_ms
                 tmem_ld16(tmem_d + ((uint32_t)(i * 32) << 16) + (uint32_t)(g.col + c16), v);
                 if (lane < Vp) {
 #pragma unroll
-                    for (int e = 0; e < 16; ++e)
-                        if (c16 + e < g.w) E_s[(i * Vp + lane) * C + a.br[j].lo + c16 + e] = __float2bfloat16(v[e]);
+                    for (int e = 0; e < 16; ++e) {
+                        const int k = c16 + e - g.off;
+                        if (k >= 0 && k < g.w) E_s[(i * Vp + lane) * C + a.br[j].lo + k] = __float2bfloat16(v[e]);
+                    }
                 }
             }
         }
@@ -650,65 +694,58 @@ __global__ void __launch_bounds__(MS_THREADS) ms_temporal_bwd_weight_kernel(dsg_
     for (int j = 0; j < a.n_branches; ++j) {
         if (a.br[j].kind != 0) continue;
         const MsBranchGeom g = ms_geom(a, j, s);
-        const int lo = a.br[j].lo;
-        const int ac0 = lo >> 3, nac = ((a.br[j].hi + 7) >> 3) - ac0;
         if (tid < 128) s_db[tid] = 0.f;
         int first = 1;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             const int n = tile / chunks_t, tp0 = (tile - n * chunks_t) * MS_TO;
             if (pending) { mbar_wait(&mbar, phase ^ 1); pending = 0; }
-            const int hb = s * g.Fq * 32 * g.Kp * 2, db_ = MS_TO * 32 * g.Kp * 2;
-            for (int i = tid * 16; i < hb; i += MS_THREADS * 16) *reinterpret_cast<uint4*>(Ht + i) = make_uint4(0u, 0u, 0u, 0u);
-            for (int i = tid * 16; i < db_; i += MS_THREADS * 16) *reinterpret_cast<uint4*>(Dt + i) = make_uint4(0u, 0u, 0u, 0u);
-            __syncthreads();
             const int nfr = s * g.Fq;
-            for (int it = tid; it < nfr * Vp * nac; it += MS_THREADS) {           // H = relu(bn(B)) with halo (as forward)
-                const int ac = it % nac, rv = it / nac;
-                const int v = rv % Vp, fi = rv / Vp;
-                const int p = fi / g.Fq, qi = fi - p * g.Fq;
-                const int t = s * (tp0 + g.qmin + qi) + p;
-                if (t < 0 || t >= a.T_in) continue;
-                const int c8 = (ac0 + ac) * 8;
-                const long long r = ((long long)n * a.T_in + t) * Vp + v;
-                float x[8];
-                unpack8(*reinterpret_cast<const uint4*>(Bx + r * a.b.ld1 + c8), x);
-                const float* ca = cfa + c8;
-                const float* cb = cfb + c8;
-                const int row = fi * 32 + v;
+            for (int it = tid; it < nfr * 32 * g.nch; it += MS_THREADS) {         // H = relu(bn(B)) with halo (as forward)
+                const int kc = it % g.nch, row = it / g.nch;
+                const int v = row & 31, fi = row >> 5;
+                uint4 pk = make_uint4(0u, 0u, 0u, 0u);
+                if (v < Vp && kc < g.nchw) {
+                    const int p = fi / g.Fq, qi = fi - p * g.Fq;
+                    const int t = s * (tp0 + g.qmin + qi) + p;
+                    if (t >= 0 && t < a.T_in) {
+                        const int c8 = g.lo8 + kc * 8;
+                        float x[8];
+                        unpack8(*reinterpret_cast<const uint4*>(Bx + (((long long)n * a.T_in + t) * Vp + v) * a.b.ld1 + c8), x);
 #pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                    const int k = c8 + e - lo;
-                    if (k >= 0 && k < g.w)
-                        *reinterpret_cast<bf16*>(Ht + op_off(row, k >> 3, g.nch) + (k & 7) * 2) =
-                            __float2bfloat16(fmaxf(fmaf(x[e], ca[e], cb[e]), 0.f));
+                        for (int e = 0; e < 8; ++e) x[e] = fmaxf(fmaf(x[e], cfa[c8 + e], cfb[c8 + e]), 0.f);
+                        pk = pack8(x);
+                    }
                 }
+                *reinterpret_cast<uint4*>(Ht + op_off(row, kc, g.nch)) = pk;
             }
-            for (int it = tid; it < MS_TO * V * nac; it += MS_THREADS) {          // dO joint rows
-                const int ac = it % nac, rv = it / nac;
-                const int v = rv % V, qi = rv / V;
+            for (int it = tid; it < MS_TO * 32 * g.nch; it += MS_THREADS) {       // dO joint rows (others zero)
+                const int kc = it % g.nch, row = it / g.nch;
+                const int v = row & 31, qi = row >> 5;
+                uint4 pk = make_uint4(0u, 0u, 0u, 0u);
                 const int tpo = tp0 + qi;
-                if (tpo >= a.T_out) continue;
-                const int c8 = (ac0 + ac) * 8;
-                const long long r = ((long long)n * a.T_out + tpo) * V + v;
-                float d[8];
-                ms_dfeat8(a, r, c8, dc1, dcb, dc2, d);
-#pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                    const int k = c8 + e - lo;
-                    if (k >= 0 && k < g.w) *reinterpret_cast<bf16*>(Dt + op_off(qi * 32 + v, k >> 3, g.nch) + (k & 7) * 2) = __float2bfloat16(d[e]);
+                if (v < V && kc < g.nchw && tpo < a.T_out) {
+                    float d[8];
+                    ms_dfeat8(a, ((long long)n * a.T_out + tpo) * V + v, g.lo8 + kc * 8, dc1, dcb, dc2, d);
+                    pk = pack8(d);
                 }
+                *reinterpret_cast<uint4*>(Dt + op_off(row, kc, g.nch)) = pk;
             }
             __syncthreads();
-            for (int it = tid; it < MS_TO * g.w; it += MS_THREADS) {              // joint-mean row of dO; bias gradient
-                const int k = it % g.w, qi = it / g.w;
-                float sacc = 0.f, tot = 0.f;
+            for (int it = tid; it < MS_TO * g.nchw; it += MS_THREADS) {           // joint-mean row of dO; bias gradient
+                const int kc = it % g.nchw, qi = it / g.nchw;
+                float sacc[8], tot[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) sacc[e] = tot[e] = 0.f;
                 for (int v = 0; v < V; ++v) {
-                    const float d = __bfloat162float(*reinterpret_cast<const bf16*>(Dt + op_off(qi * 32 + v, k >> 3, g.nch) + (k & 7) * 2));
-                    sacc = fmaf(d, a.has_ext ? a.add_coeff[v] : 0.f, sacc);
-                    tot += d;
+                    float d[8];
+                    unpack8(*reinterpret_cast<const uint4*>(Dt + op_off(qi * 32 + v, kc, g.nch)), d);
+                    const float wv = a.has_ext ? a.add_coeff[v] : 0.f;
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) { sacc[e] = fmaf(d[e], wv, sacc[e]); tot[e] += d[e]; }
                 }
-                if (a.has_ext) *reinterpret_cast<bf16*>(Dt + op_off(qi * 32 + V, k >> 3, g.nch) + (k & 7) * 2) = __float2bfloat16(sacc);
-                atomicAdd(&s_db[k], tot + (a.has_ext ? sacc : 0.f));
+                if (a.has_ext) *reinterpret_cast<uint4*>(Dt + op_off(qi * 32 + V, kc, g.nch)) = pack8(sacc);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) atomicAdd(&s_db[kc * 8 + e], tot[e] + (a.has_ext ? sacc[e] : 0.f));
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -746,13 +783,16 @@ __global__ void __launch_bounds__(MS_THREADS) ms_temporal_bwd_weight_kernel(dsg_
                     if (lq * 32 >= g.Kp) continue;                                  // warp-uniform: no live rows in this lane quarter
                     float v[16];
                     tmem_ld16(tmem_d + ((uint32_t)(lq * 32) << 16) + (uint32_t)(dt * g.Kp + c16), v);
-                    if (co < g.w) {
+                    const int cor = co - g.off;                                   // window row -> output channel of the branch
+                    if (cor >= 0 && cor < g.w) {
 #pragma unroll
-                        for (int e = 0; e < 16; ++e)
-                            if (c16 + e < g.w) atomicAdd(a.br[j].dW + ((long long)co * g.w + c16 + e) * 3 + dt, v[e]);
+                        for (int e = 0; e < 16; ++e) {
+                            const int ci = c16 + e - g.off;
+                            if (ci >= 0 && ci < g.w) atomicAdd(a.br[j].dW + ((long long)cor * g.w + ci) * 3 + dt, v[e]);
+                        }
                     }
                 }
-            if (tid < g.w && a.br[j].db) atomicAdd(a.br[j].db + tid, s_db[tid]);
+            if (tid < g.w && a.br[j].db) atomicAdd(a.br[j].db + tid, s_db[tid + g.off]);
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncthreads();
@@ -774,6 +814,7 @@ static const char* launch_ms_temporal_bwd_data(const dsg_ms_temporal_args& a, ds
     if (mp_hi <= mp_lo) { mp_lo = 0; mp_hi = 0; }
     size_t smem = (size_t)h.h_bytes + h.w_bytes + h.feat_bytes + (size_t)6 * (mp_hi - mp_lo) * 4 + 16;
     if (smem > 200 * 1024) return "ms_temporal_bwd_data: shared memory budget exceeded";
+    if (const char* e = ms_launch_wpack(a, st)) return e;
     cudaFuncSetAttribute(ms_temporal_bwd_data_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const int frames_per_plane = (a.T_in + a.stride - 1) / a.stride;
     dim3 grid((frames_per_plane + MS_TO - 1) / MS_TO, a.n_samples, a.stride);
@@ -789,7 +830,8 @@ static const char* launch_ms_temporal_bwd_weight(const dsg_ms_temporal_args& a, 
     int d_bytes = 0, cols = 32, kpmax = 0;
     for (int j = 0; j < a.n_branches; ++j)
         if (a.br[j].kind == 0) {
-            int Kp = ((a.br[j].hi - a.br[j].lo) + 15) & ~15;
+            int lo8, nchw, Kp;
+            ms_window(a.br[j].lo, a.br[j].hi, lo8, nchw, Kp);
             if (Kp > kpmax) kpmax = Kp;
             if (!a.br[j].dW) return "ms_temporal_bwd_weight: dW missing";
         }

@@ -335,7 +335,12 @@ def ms_temporal_args(b, layout, weights, *, n, T_in, T_out, stride, V, has_ext, 
 
 
 def ms_temporal_supported(a):
-    return a is not None and bool(L.lib().dsg_ms_temporal_supported(C.byref(a)))
+    if a is None or not L.lib().dsg_ms_temporal_supported(C.byref(a)):
+        return False
+    nb = int(L.lib().dsg_ms_temporal_wpack_bytes(C.byref(a)))
+    a._wpack = torch.empty(max(nb, 16), dtype=torch.uint8, device=torch.device("cuda", torch.cuda.current_device()))
+    a.wpack = L.ptr(a._wpack)
+    return True
 
 
 def ms_temporal_fwd(a, feat, oglob, stat_sum, stat_sq):

@@ -296,8 +296,11 @@ typedef struct dsg_ms_temporal_args {
     double* e_sum;
     double* e_sq;
     float* dadd_coeff;
+    void* wpack;          /* caller-owned workspace of dsg_ms_temporal_wpack_bytes(): bf16 UMMA-ready weight tiles,
+                             (re)written by _fwd and _bwd_data before use */
 } dsg_ms_temporal_args;
 int dsg_ms_temporal_supported(const dsg_ms_temporal_args* a);
+long long dsg_ms_temporal_wpack_bytes(const dsg_ms_temporal_args* a);
 int dsg_ms_temporal_fwd(const dsg_ms_temporal_args* a, void* stream);
 int dsg_ms_temporal_bwd_data(const dsg_ms_temporal_args* a, void* stream);
 int dsg_ms_temporal_bwd_weight(const dsg_ms_temporal_args* a, void* stream);

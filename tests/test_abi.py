@@ -14,7 +14,7 @@ HEADER = os.path.join(ROOT, "include", "dsgcn_b200.h")
 
 def _declared():
     src = open(HEADER).read()
-    names = re.findall(r"^(?:int|const char\*)\s+(dsg_\w+)\s*\(", src, flags=re.M)
+    names = re.findall(r"^(?:int|long long|const char\*)\s+(dsg_\w+)\s*\(", src, flags=re.M)
     assert len(names) >= 18
     return names
 
