@@ -132,6 +132,95 @@ DSG_D void ms_dfeat8(const dsg_ms_temporal_args& a, long long r, int c8, const f
     }
 }
 
+// ---- batched staging: 4 items per thread in flight (loads first, then prologue + 16-byte shared store) -------------
+// H tile: relu(bn(B)) of input frames t = s*(tq0 + qi) + p, for planes p in [0,s) and qi in [0,Fq); 32 rows per frame.
+DSG_D void ms_stage_H(const dsg_ms_temporal_args& a, const MsBranchGeom& g, int n, int tq0, int s, int Vp, unsigned char* Ht,
+                      const float* cfa, const float* cfb) {
+    const bf16* Bx = reinterpret_cast<const bf16*>(a.b.x1);
+    const int total = s * g.Fq * 32 * g.nch;
+    for (int it0 = threadIdx.x; it0 < total; it0 += MS_THREADS * 4) {
+        uint4 raw[4];
+        int off[4], c8s[4];
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const int it = it0 + b * MS_THREADS;
+            off[b] = -1; c8s[b] = -1;
+            if (it < total) {
+                const int kc = it % g.nch, row = it / g.nch;
+                const int v = row & 31, fi = row >> 5;
+                off[b] = (int)op_off(row, kc, g.nch);
+                if (v < Vp && kc < g.nchw) {
+                    const int p = fi / g.Fq, qi = fi - p * g.Fq;
+                    const int t = s * (tq0 + qi) + p;
+                    if (t >= 0 && t < a.T_in) {
+                        c8s[b] = g.lo8 + kc * 8;
+                        raw[b] = *reinterpret_cast<const uint4*>(Bx + (((long long)n * a.T_in + t) * Vp + v) * a.b.ld1 + c8s[b]);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            if (off[b] < 0) continue;
+            uint4 pk = make_uint4(0u, 0u, 0u, 0u);
+            if (c8s[b] >= 0) {
+                float x[8];
+                unpack8(raw[b], x);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) x[e] = fmaxf(fmaf(x[e], cfa[c8s[b] + e], cfb[c8s[b] + e]), 0.f);
+                pk = pack8(x);
+            }
+            *reinterpret_cast<uint4*>(Ht + off[b]) = pk;
+        }
+    }
+}
+// dO tile: dfeat of output frames tpo0 + qi (qi in [0,nfr)), joint rows only (padding rows and the joint-mean row zero)
+DSG_D void ms_stage_dO(const dsg_ms_temporal_args& a, const MsBranchGeom& g, int n, int tpo0, int nfr, int V, unsigned char* Dt,
+                       const float* d1, const float* db, const float* d2) {
+    const bf16* X1 = reinterpret_cast<const bf16*>(a.dfeat.x1);
+    const bf16* X2 = reinterpret_cast<const bf16*>(a.dfeat.x2);
+    const int total = nfr * 32 * g.nch;
+    for (int it0 = threadIdx.x; it0 < total; it0 += MS_THREADS * 4) {
+        uint4 r1[4], r2[4];
+        int off[4], c8s[4];
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const int it = it0 + b * MS_THREADS;
+            off[b] = -1; c8s[b] = -1;
+            if (it < total) {
+                const int kc = it % g.nch, row = it / g.nch;
+                const int v = row & 31, qi = row >> 5;
+                off[b] = (int)op_off(row, kc, g.nch);
+                const int tpo = tpo0 + qi;
+                if (v < V && kc < g.nchw && tpo >= 0 && tpo < a.T_out) {
+                    c8s[b] = g.lo8 + kc * 8;
+                    const long long r = ((long long)n * a.T_out + tpo) * V + v;
+                    r1[b] = *reinterpret_cast<const uint4*>(X1 + r * a.dfeat.ld1 + c8s[b]);
+                    if (X2) r2[b] = *reinterpret_cast<const uint4*>(X2 + r * a.dfeat.ld2 + c8s[b]);
+                }
+            }
+        }
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            if (off[b] < 0) continue;
+            uint4 pk = make_uint4(0u, 0u, 0u, 0u);
+            if (c8s[b] >= 0) {
+                float x[8], v[8];
+                unpack8(r1[b], x);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) v[e] = fmaf(x[e], d1[c8s[b] + e], db[c8s[b] + e]);
+                if (X2) {
+                    unpack8(r2[b], x);
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) v[e] = fmaf(x[e], d2[c8s[b] + e], v[e]);
+                }
+                pk = pack8(v);
+            }
+            *reinterpret_cast<uint4*>(Dt + off[b]) = pk;
+        }
+    }
+}
+
 __global__ void __launch_bounds__(MS_THREADS) ms_temporal_fwd_kernel(dsg_ms_temporal_args a, int h_bytes, int w_bytes, int tmem_cols) {
     DSG_DYN_SMEM(smem);
     __shared__ uint64_t mbar;
@@ -162,26 +251,8 @@ __global__ void __launch_bounds__(MS_THREADS) ms_temporal_fwd_kernel(dsg_ms_temp
         if (a.br[j].kind != 0) continue;
         const MsBranchGeom g = ms_geom(a, j, s);
         if (issued) mbar_wait(&mbar, phase ^ 1);             // the previous branch's MMAs are done with Ht / Wt
-        // ---- stage relu(bn(B)) over the branch's channel window: item = (plane frame, padded joint row, 16-byte chunk)
-        const int nfr = s * g.Fq;
-        for (int it = tid; it < nfr * 32 * g.nch; it += MS_THREADS) {
-            const int kc = it % g.nch, row = it / g.nch;
-            const int v = row & 31, fi = row >> 5;
-            uint4 pk = make_uint4(0u, 0u, 0u, 0u);
-            if (v < Vp && kc < g.nchw) {
-                const int p = fi / g.Fq, qi = fi - p * g.Fq;
-                const int t = s * (tp0 + g.qmin + qi) + p;
-                if (t >= 0 && t < a.T_in) {
-                    const int c8 = g.lo8 + kc * 8;
-                    float x[8];
-                    unpack8(*reinterpret_cast<const uint4*>(Bx + (((long long)n * a.T_in + t) * Vp + v) * a.b.ld1 + c8), x);
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) x[e] = fmaxf(fmaf(x[e], cfa[c8 + e], cfb[c8 + e]), 0.f);
-                    pk = pack8(x);
-                }
-            }
-            *reinterpret_cast<uint4*>(Ht + op_off(row, kc, g.nch)) = pk;
-        }
+        // ---- stage relu(bn(B)) over the branch's channel window (with the temporal halo)
+        ms_stage_H(a, g, n, tp0 + g.qmin, s, Vp, Ht, cfa, cfb);
         ms_load_w(a, j, 0, g.Kp, Wt);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -401,8 +472,15 @@ __global__ void __launch_bounds__(MS_THREADS) ms_temporal_bwd_data_kernel(dsg_ms
     float* dg_s = reinterpret_cast<float*>(smem + h_bytes + w_bytes + MS_TO * Vp * C * 2);   // [6][mpw]
     const bf16* Bx = reinterpret_cast<const bf16*>(a.b.x1);
     __shared__ float cfa[MS_CMAX], cfb[MS_CMAX], dc1[MS_CMAX], dcb[MS_CMAX], dc2[MS_CMAX];
+    __shared__ unsigned char kind_s[MS_CMAX];                // branch kind per channel (0 conv, 1 max, 2 pass, 3 none)
     ms_stage_b(a, cfa, cfb);
     ms_stage_d(a, dc1, dcb, dc2);
+    for (int c = tid; c < C; c += MS_THREADS) {
+        int k = 3;
+        for (int j = 0; j < a.n_branches; ++j)
+            if (c >= a.br[j].lo && c < a.br[j].hi) k = a.br[j].kind;
+        kind_s[c] = (unsigned char)k;
+    }
 
     if (tid == 0) {
         mbar_init(&mbar, 1);
@@ -425,18 +503,7 @@ __global__ void __launch_bounds__(MS_THREADS) ms_temporal_bwd_data_kernel(dsg_ms
         if (tp.n == 0) continue;
         if (issued) mbar_wait(&mbar, phase ^ 1);
         // ---- stage dO over the channel window (joint rows; padding rows and the joint-mean row start as zeros)
-        for (int it = tid; it < tp.Fq * 32 * g.nch; it += MS_THREADS) {
-            const int kc = it % g.nch, row = it / g.nch;
-            const int v = row & 31, qi = row >> 5;
-            uint4 pk = make_uint4(0u, 0u, 0u, 0u);
-            const int tpo = q0 + tp.shmin + qi;
-            if (v < V && kc < g.nchw && tpo >= 0 && tpo < a.T_out) {
-                float d[8];
-                ms_dfeat8(a, ((long long)n * a.T_out + tpo) * V + v, g.lo8 + kc * 8, dc1, dcb, dc2, d);
-                pk = pack8(d);
-            }
-            *reinterpret_cast<uint4*>(Dt + op_off(row, kc, g.nch)) = pk;
-        }
+        ms_stage_dO(a, g, n, q0 + tp.shmin, tp.Fq, V, Dt, dc1, dcb, dc2);
         ms_load_w(a, j, 1, g.Kp, Wt);                                   // B operand [n = ci][k = co]
         if (a.has_ext) {
             __syncthreads();
@@ -510,9 +577,7 @@ __global__ void __launch_bounds__(MS_THREADS) ms_temporal_bwd_data_kernel(dsg_ms
             bool any_max = false;
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
-                kind[e] = 3;
-                for (int j = 0; j < a.n_branches; ++j)
-                    if (a.br[j].kind != 0 && c8 + e >= a.br[j].lo && c8 + e < a.br[j].hi) kind[e] = a.br[j].kind;
+                kind[e] = kind_s[c8 + e];
                 any_max |= kind[e] == 1;
             }
             const float* ca = cfa + c8;
@@ -621,9 +686,7 @@ __global__ void __launch_bounds__(MS_THREADS) ms_temporal_bwd_data_kernel(dsg_ms
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
             s1[e] = s2[e] = 0.f;
-            msk[e] = 1.f;
-            for (int j = 0; j < a.n_branches; ++j)
-                if (a.br[j].kind == 2 && c0 + e >= a.br[j].lo && c0 + e < a.br[j].hi) msk[e] = 0.f;     // pass range: no ReLU
+            msk[e] = kind_s[c0 + e] == 2 ? 0.f : 1.f;            // pass range: no ReLU
         }
         bf16* E = reinterpret_cast<bf16*>(a.e);
         for (int r = rl; r < MS_TO * Vp; r += lanes) {
@@ -699,37 +762,8 @@ __global__ void __launch_bounds__(MS_THREADS) ms_temporal_bwd_weight_kernel(dsg_
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             const int n = tile / chunks_t, tp0 = (tile - n * chunks_t) * MS_TO;
             if (pending) { mbar_wait(&mbar, phase ^ 1); pending = 0; }
-            const int nfr = s * g.Fq;
-            for (int it = tid; it < nfr * 32 * g.nch; it += MS_THREADS) {         // H = relu(bn(B)) with halo (as forward)
-                const int kc = it % g.nch, row = it / g.nch;
-                const int v = row & 31, fi = row >> 5;
-                uint4 pk = make_uint4(0u, 0u, 0u, 0u);
-                if (v < Vp && kc < g.nchw) {
-                    const int p = fi / g.Fq, qi = fi - p * g.Fq;
-                    const int t = s * (tp0 + g.qmin + qi) + p;
-                    if (t >= 0 && t < a.T_in) {
-                        const int c8 = g.lo8 + kc * 8;
-                        float x[8];
-                        unpack8(*reinterpret_cast<const uint4*>(Bx + (((long long)n * a.T_in + t) * Vp + v) * a.b.ld1 + c8), x);
-#pragma unroll
-                        for (int e = 0; e < 8; ++e) x[e] = fmaxf(fmaf(x[e], cfa[c8 + e], cfb[c8 + e]), 0.f);
-                        pk = pack8(x);
-                    }
-                }
-                *reinterpret_cast<uint4*>(Ht + op_off(row, kc, g.nch)) = pk;
-            }
-            for (int it = tid; it < MS_TO * 32 * g.nch; it += MS_THREADS) {       // dO joint rows (others zero)
-                const int kc = it % g.nch, row = it / g.nch;
-                const int v = row & 31, qi = row >> 5;
-                uint4 pk = make_uint4(0u, 0u, 0u, 0u);
-                const int tpo = tp0 + qi;
-                if (v < V && kc < g.nchw && tpo < a.T_out) {
-                    float d[8];
-                    ms_dfeat8(a, ((long long)n * a.T_out + tpo) * V + v, g.lo8 + kc * 8, dc1, dcb, dc2, d);
-                    pk = pack8(d);
-                }
-                *reinterpret_cast<uint4*>(Dt + op_off(row, kc, g.nch)) = pk;
-            }
+            ms_stage_H(a, g, n, tp0 + g.qmin, s, Vp, Ht, cfa, cfb);
+            ms_stage_dO(a, g, n, tp0, MS_TO, V, Dt, dc1, dcb, dc2);
             __syncthreads();
             for (int it = tid; it < MS_TO * g.nchw; it += MS_THREADS) {           // joint-mean row of dO; bias gradient
                 const int kc = it % g.nchw, qi = it / g.nchw;
