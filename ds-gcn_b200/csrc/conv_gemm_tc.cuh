@@ -529,11 +529,16 @@ __global__ void __launch_bounds__(CG_THREADS, 2) conv_gemm_tc_kernel(dsg_conv_ge
 // frame range, then added to dW with atomics (one CTA per SM-slot => ~1e2 partial sums per weight).
 constexpr int WT_ROWS = 128;       // rows (reduction length) per pass
 constexpr int WT_BN = 128;         // output channels per CTA   (MMA M)
-constexpr int WT_BK = 256;         // input channels per CTA    (MMA N)
+constexpr int WT_U = 4;            // independent operand loads in flight per thread while staging
+
+DSG_D void red_add_v4(float* p, float x, float y, float z, float w) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
+}
+constexpr int WT_BK = 128;         // input channels per CTA    (MMA N)
 
 DSG_D uint32_t make_idesc_mn(int M, int N) { return make_idesc(M, N) | (1u << 15) | (1u << 16); }
 
-__global__ void __launch_bounds__(CG_THREADS) conv_wgrad_tc_kernel(dsg_conv_wgrad_args a, int frames_per_cta, int vecA, int vecB) {
+__global__ void __launch_bounds__(CG_THREADS, 3) conv_wgrad_tc_kernel(dsg_conv_wgrad_args a, int frames_per_cta, int vecA, int vecB, int vecW) {
     DSG_DYN_SMEM(smem);
     __shared__ uint64_t mbar;
     __shared__ uint32_t tmem_base_s;
@@ -557,6 +562,7 @@ __global__ void __launch_bounds__(CG_THREADS) conv_wgrad_tc_kernel(dsg_conv_wgra
     if (fend > n_frames) fend = n_frames;
     FrameMap fm{a.taps, a.tap_step, a.tap_off, a.t_mul, a.t_div, a.T_in, a.T_out, a.Vin, a.ext_in};
     const bool do_bias = (a.db != nullptr) && kt == 0 && tap == 0;
+    const bool fastA = vecA && (a.K % 8 == 0), fastB = vecB && (a.N % 8 == 0);
 
     __shared__ __align__(16) float cfA[3][WT_BK], cfB[3][WT_BN];      // staged per-channel coefficients (a1, b1+b2, a2) of both operands
     for (int i = tid; i < WT_BK; i += CG_THREADS) {
@@ -591,7 +597,7 @@ __global__ void __launch_bounds__(CG_THREADS) conv_wgrad_tc_kernel(dsg_conv_wgra
 
     uint32_t phase = 0;
     int first = 1;
-    float bsum = 0.f;
+    float bs[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // bias-gradient partials of this thread's 8 output channels
     for (long long f0 = fbeg; f0 < fend; f0 += Fr) {
         if (!first) mbar_wait(&mbar, phase ^ 1);               // MMAs of the previous pass are done with Mop/Nop
         if (tid < WT_ROWS) {
@@ -609,52 +615,132 @@ __global__ void __launch_bounds__(CG_THREADS) conv_wgrad_tc_kernel(dsg_conv_wgra
             rowdst[tid] = dr;
         }
         __syncthreads();
-        // ---- stage both operands: lane = (row % 8) + 8 * (channel group % 4)
-        for (int it = warp; it < (rows_p / 8) * ((gM + 3) / 4); it += CG_THREADS / 32) {
-            const int rg = it / ((gM + 3) / 4), g4 = it - rg * ((gM + 3) / 4);
-            const int kk = rg * 8 + (lane & 7), g8 = g4 * 4 + (lane >> 3);
-            if (g8 >= gM) continue;
-            uint4 pk = make_uint4(0u, 0u, 0u, 0u);
-            const long long dr = rowdst[kk < WT_ROWS ? kk : 0];
-            if (kk < rows_tile && dr >= 0 && n0 + g8 * 8 < a.N) {
-                if (vecB && n0 + g8 * 8 + 8 <= a.N) {
-                    float v[8];
-                    finish_smem(act8_issue(a.B, dr, n0 + g8 * 8), a.B.x2 != nullptr, a.B.relu, &cfB[0][g8 * 8], &cfB[1][g8 * 8], &cfB[2][g8 * 8], v);
-                    pk = pack8(v);
-                } else pk = load_act8(a.B, dr, n0 + g8 * 8, a.N, 0);
+        // ---- stage both operands: lane = (row % 8) + 8 * (channel group % 4).  Fast path (16-byte loads, channel counts
+        //      that are multiples of 8): WT_U independent loads in flight per thread.  The B side has 16 channel groups, so
+        //      a thread keeps the same group on every iteration and the bias gradient accumulates in registers.
+        {
+            const int g8 = (warp & 3) * 4 + (lane >> 3);
+            const int cB = n0 + g8 * 8;
+            const int nI = rows_p >> 4;                        // iterations per warp: row group (warp >> 2) + 2 * i
+            if (fastB) {
+                for (int i0 = 0; i0 < nI; i0 += WT_U) {
+                    Act8Raw q[WT_U];
+                    bool ok[WT_U];
+#pragma unroll
+                    for (int u = 0; u < WT_U; ++u) {
+                        const int kk = ((warp >> 2) + 2 * (i0 + u)) * 8 + (lane & 7);
+                        ok[u] = false;
+                        q[u].a = q[u].b = make_uint4(0u, 0u, 0u, 0u);
+                        if (i0 + u < nI) {
+                            const long long dr = rowdst[kk];
+                            ok[u] = kk < rows_tile && dr >= 0 && cB < a.N;
+                            if (ok[u]) q[u] = act8_issue(a.B, dr, cB);
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < WT_U; ++u) {
+                        const int kk = ((warp >> 2) + 2 * (i0 + u)) * 8 + (lane & 7);
+                        if (i0 + u < nI) {
+                            uint4 pk = make_uint4(0u, 0u, 0u, 0u);
+                            if (ok[u]) {
+                                float v[8];
+                                finish_smem(q[u], a.B.x2 != nullptr, a.B.relu, &cfB[0][g8 * 8], &cfB[1][g8 * 8], &cfB[2][g8 * 8], v);
+                                pk = pack8(v);
+                                if (do_bias) {
+                                    unpack8(pk, v);
+#pragma unroll
+                                    for (int j = 0; j < 8; ++j) bs[j] += v[j];
+                                }
+                            }
+                            *reinterpret_cast<uint4*>(Mop + mn_off(g8, kk, gM)) = pk;
+                        }
+                    }
+                }
+            } else {
+                for (int i = 0; i < nI; ++i) {
+                    const int kk = ((warp >> 2) + 2 * i) * 8 + (lane & 7);
+                    uint4 pk = make_uint4(0u, 0u, 0u, 0u);
+                    const long long dr = rowdst[kk];
+                    if (kk < rows_tile && dr >= 0 && cB < a.N) {
+                        pk = load_act8(a.B, dr, cB, a.N, 0);
+                        if (do_bias) {
+                            float v[8];
+                            unpack8(pk, v);
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) bs[j] += v[j];
+                        }
+                    }
+                    *reinterpret_cast<uint4*>(Mop + mn_off(g8, kk, gM)) = pk;
+                }
             }
-            *reinterpret_cast<uint4*>(Mop + mn_off(g8, kk, gM)) = pk;
         }
-        for (int it = warp; it < (rows_p / 8) * ((gN + 3) / 4); it += CG_THREADS / 32) {
-            const int rg = it / ((gN + 3) / 4), g4 = it - rg * ((gN + 3) / 4);
-            const int kk = rg * 8 + (lane & 7), g8 = g4 * 4 + (lane >> 3);
-            if (g8 >= gN) continue;
-            uint4 pk = make_uint4(0u, 0u, 0u, 0u);
-            const long long sr = rowsrc[kk < WT_ROWS ? kk : 0];
-            if (kk < rows_tile && sr >= 0 && k0 + g8 * 8 < a.K) {
-                if (vecA && k0 + g8 * 8 + 8 <= a.K) {
-                    float v[8];
-                    finish_smem(act8_issue(a.A, sr, k0 + g8 * 8), a.A.x2 != nullptr, a.A.relu, &cfA[0][g8 * 8], &cfA[1][g8 * 8], &cfA[2][g8 * 8], v);
-                    pk = pack8(v);
-                } else pk = load_act8(a.A, sr, k0 + g8 * 8, a.K, 0);
+        {
+            const int g4n = (gN + 3) / 4;
+            const int total = (rows_p / 8) * g4n;
+            if (fastA) {
+                for (int it0 = warp; it0 < total; it0 += (CG_THREADS / 32) * WT_U) {
+                    Act8Raw q[WT_U];
+                    bool ok[WT_U];
+#pragma unroll
+                    for (int u = 0; u < WT_U; ++u) {
+                        const int it = it0 + u * (CG_THREADS / 32);
+                        const int rg = it / g4n, g8 = (it - rg * g4n) * 4 + (lane >> 3);
+                        const int kk = rg * 8 + (lane & 7);
+                        ok[u] = false;
+                        q[u].a = q[u].b = make_uint4(0u, 0u, 0u, 0u);
+                        if (it < total) {
+                            const long long sr = rowsrc[kk];
+                            ok[u] = g8 < gN && kk < rows_tile && sr >= 0 && k0 + g8 * 8 < a.K;
+                            if (ok[u]) q[u] = act8_issue(a.A, sr, k0 + g8 * 8);
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < WT_U; ++u) {
+                        const int it = it0 + u * (CG_THREADS / 32);
+                        const int rg = it / g4n, g8 = (it - rg * g4n) * 4 + (lane >> 3);
+                        const int kk = rg * 8 + (lane & 7);
+                        if (it < total && g8 < gN) {
+                            uint4 pk = make_uint4(0u, 0u, 0u, 0u);
+                            if (ok[u]) {
+                                float v[8];
+                                finish_smem(q[u], a.A.x2 != nullptr, a.A.relu, &cfA[0][g8 * 8], &cfA[1][g8 * 8], &cfA[2][g8 * 8], v);
+                                pk = pack8(v);
+                            }
+                            *reinterpret_cast<uint4*>(Nop + mn_off(g8, kk, gN)) = pk;
+                        }
+                    }
+                }
+            } else {
+                for (int it = warp; it < total; it += CG_THREADS / 32) {
+                    const int rg = it / g4n, g8 = (it - rg * g4n) * 4 + (lane >> 3);
+                    const int kk = rg * 8 + (lane & 7);
+                    if (g8 >= gN) continue;
+                    uint4 pk = make_uint4(0u, 0u, 0u, 0u);
+                    const long long sr = rowsrc[kk];
+                    if (kk < rows_tile && sr >= 0 && k0 + g8 * 8 < a.K) pk = load_act8(a.A, sr, k0 + g8 * 8, a.K, 0);
+                    *reinterpret_cast<uint4*>(Nop + mn_off(g8, kk, gN)) = pk;
+                }
             }
-            *reinterpret_cast<uint4*>(Nop + mn_off(g8, kk, gN)) = pk;
         }
-        if (a.ext_in || do_bias) __syncthreads();
         if (a.ext_in) {
-            for (int idx = tid; idx < Fr * Ktp; idx += CG_THREADS) {
-                const int c = idx % Ktp, fl = idx / Ktp;
+            // joint-mean row of every frame, from the staged tile: one thread per (frame, 8-channel group)
+            __syncthreads();
+            for (int idx = tid; idx < Fr * gN; idx += CG_THREADS) {
+                const int g = idx % gN, fl = idx / gN;
                 const int mr = fl * rpf + a.Vin;
                 if (rowsrc[mr] != -2) continue;
-                float s = 0.f;
-                for (int j = 0; j < a.Vin; ++j)
-                    s += __bfloat162float(*reinterpret_cast<const bf16*>(Nop + mn_off(c >> 3, fl * rpf + j, gN) + (c & 7) * 2));
-                *reinterpret_cast<bf16*>(Nop + mn_off(c >> 3, mr, gN) + (c & 7) * 2) = __float2bfloat16(s / (float)a.Vin);
+                float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                for (int j = 0; j < a.Vin; ++j) {
+                    float v[8];
+                    unpack8(*reinterpret_cast<const uint4*>(Nop + mn_off(g, fl * rpf + j, gN)), v);
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) s[c] += v[c];
+                }
+                const float inv = 1.f / (float)a.Vin;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) s[c] *= inv;
+                *reinterpret_cast<uint4*>(Nop + mn_off(g, mr, gN)) = pack8(s);
             }
-        }
-        if (do_bias && tid < WT_BN) {
-            for (int kk = 0; kk < rows_tile; ++kk)
-                bsum += __bfloat162float(*reinterpret_cast<const bf16*>(Mop + mn_off(tid >> 3, kk, gM) + (tid & 7) * 2));
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -684,14 +770,31 @@ __global__ void __launch_bounds__(CG_THREADS) conv_wgrad_tc_kernel(dsg_conv_wgra
             float v[16];
             tmem_ld16(tmem_d + ((uint32_t)(lq * 32) << 16) + (uint32_t)(g * 16), v);
             if (n < Nt) {
+                float* dst = a.dW + (long long)(n0 + n) * a.ws_n + (long long)(k0 + g * 16) * a.ws_k + (long long)tap * a.ws_tap;
+                if (vecW && g * 16 + 16 <= Kt) {
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const int k = g * 16 + j;
-                    if (k < Kt) atomicAdd(a.dW + (long long)(n0 + n) * a.ws_n + (long long)(k0 + k) * a.ws_k + (long long)tap * a.ws_tap, v[j]);
+                    for (int j = 0; j < 16; j += 4) red_add_v4(dst + j, v[j], v[j + 1], v[j + 2], v[j + 3]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        if (g * 16 + j < Kt) atomicAdd(dst + (long long)j * a.ws_k, v[j]);
                 }
             }
         }
-        if (do_bias && tid < Nt) atomicAdd(a.db + n0 + tid, bsum);
+        if (do_bias) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                bs[j] += __shfl_xor_sync(0xffffffffu, bs[j], 1);
+                bs[j] += __shfl_xor_sync(0xffffffffu, bs[j], 2);
+                bs[j] += __shfl_xor_sync(0xffffffffu, bs[j], 4);
+            }
+            const int g8 = (warp & 3) * 4 + (lane >> 3);
+            if ((lane & 7) == 0) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    if (g8 * 8 + j < Nt) atomicAdd(a.db + n0 + g8 * 8 + j, bs[j]);
+            }
+        }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -708,14 +811,19 @@ static const char* launch_conv_wgrad_tc(const dsg_conv_wgrad_args& a, dsg_stream
     int ktiles = (a.K + WT_BK - 1) / WT_BK, ntiles = (a.N + WT_BN - 1) / WT_BN;
     int Fr = WT_ROWS / rpf;
     long long per = (long long)ktiles * ntiles * a.taps;
-    long long want = (2 * 148 + per - 1) / per;                  // ~2 CTAs per SM in total
+    int Ktp = a.K < WT_BK ? (a.K + 15) & ~15 : WT_BK;
+    size_t smem = 2 * WT_ROWS * sizeof(long long) + (size_t)(WT_BN + Ktp) * WT_ROWS * 2;
+    int occ = (int)((200 * 1024) / (smem + 4096));                // CTAs one SM holds (TMEM: <=128 columns each)
+    if (occ > 4) occ = 4;
+    if (occ < 1) occ = 1;
+    long long want = ((long long)occ * 148 + per - 1) / per;      // one wave of resident CTAs
     long long fpc = (n_frames + want - 1) / want;
     fpc = (fpc + Fr - 1) / Fr * Fr;
     if (fpc < Fr) fpc = Fr;
-    size_t smem = 2 * WT_ROWS * sizeof(long long) + (size_t)(WT_BN + WT_BK) * WT_ROWS * 2;
+    int vecW = a.ws_k == 1 && a.ws_n % 4 == 0 && a.ws_tap % 4 == 0 && (uintptr_t)a.dW % 16 == 0;
     dim3 grid((unsigned)((n_frames + fpc - 1) / fpc), (unsigned)ntiles, (unsigned)(ktiles * a.taps));
     cudaFuncSetAttribute(conv_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    conv_wgrad_tc_kernel<<<grid, dim3(CG_THREADS), smem, st>>>(a, (int)fpc, vec(a.A), vec(a.B));
+    conv_wgrad_tc_kernel<<<grid, dim3(CG_THREADS), smem, st>>>(a, (int)fpc, vec(a.A), vec(a.B), vecW);
     *handled = true;
     return dsg_launch_error();
 }

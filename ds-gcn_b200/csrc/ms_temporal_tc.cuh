@@ -221,7 +221,7 @@ DSG_D void ms_stage_dO(const dsg_ms_temporal_args& a, const MsBranchGeom& g, int
     }
 }
 
-__global__ void __launch_bounds__(MS_THREADS) ms_temporal_fwd_kernel(dsg_ms_temporal_args a, int h_bytes, int w_bytes, int tmem_cols) {
+__global__ void __launch_bounds__(MS_THREADS, 4) ms_temporal_fwd_kernel(dsg_ms_temporal_args a, int h_bytes, int w_bytes, int tmem_cols) {
     DSG_DYN_SMEM(smem);
     __shared__ uint64_t mbar;
     __shared__ uint32_t tmem_base_s;
@@ -456,7 +456,7 @@ DSG_D float ms_dfeat(const dsg_ms_temporal_args& a, int n, int tp, int v, int c)
     return act_value<bf16>(a.dfeat, ((long long)n * a.T_out + tp) * a.V + v, c);
 }
 
-__global__ void __launch_bounds__(MS_THREADS) ms_temporal_bwd_data_kernel(dsg_ms_temporal_args a, int h_bytes, int w_bytes, int tmem_cols,
+__global__ void __launch_bounds__(MS_THREADS, 3) ms_temporal_bwd_data_kernel(dsg_ms_temporal_args a, int h_bytes, int w_bytes, int tmem_cols,
                                                                           int mp_lo, int mp_hi) {
     DSG_DYN_SMEM(smem);
     __shared__ uint64_t mbar;
