@@ -216,7 +216,9 @@ int dsg_pointwise(const dsg_pointwise_args* a, void* stream) {
     if (a->rows <= 0 || a->C <= 0) return 0;
     if (dsg::pointwise_vec_ok(*a)) {
         dim3 gv((unsigned)((a->rows + dsg::PV_ROWS - 1) / dsg::PV_ROWS), (a->C + dsg::PW_CT - 1) / dsg::PW_CT);
-        dsg_launch(dsg::pointwise_vec_kernel, gv, dim3(dsg::PW_THREADS), 0, (dsg_stream_t)stream, *a);
+        const bool simple = a->src.x2 == nullptr && !(a->has_mask && a->mask.x2 != nullptr);
+        if (simple) dsg_launch(dsg::pointwise_vec_kernel<true>, gv, dim3(dsg::PW_THREADS), 0, (dsg_stream_t)stream, *a);
+        else dsg_launch(dsg::pointwise_vec_kernel<false>, gv, dim3(dsg::PW_THREADS), 0, (dsg_stream_t)stream, *a);
         DSG_RET("dsg_pointwise", dsg_launch_error());
     }
     dim3 grid((unsigned)((a->rows + dsg::PW_ROWS - 1) / dsg::PW_ROWS), (a->C + dsg::PW_CT - 1) / dsg::PW_CT);

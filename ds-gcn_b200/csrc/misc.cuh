@@ -118,41 +118,99 @@ __global__ void __launch_bounds__(PW_THREADS) pointwise_kernel(dsg_pointwise_arg
 }
 
 // Vectorised fast path (bf16 in / bf16 out, everything 16-byte aligned, C % 8 == 0): a thread owns one 8-channel
-// chunk (coefficients live in registers) and walks rows; 8 consecutive threads cover 64 channels = 128 B per row.
+// chunk and walks rows; 8 consecutive threads cover 64 channels = 128 B per row.  A pure streaming kernel, so what
+// matters is bytes in flight: per-channel coefficients live in shared memory (registers are for data), the loads of U
+// rows are issued before any of them is used, and the register budget keeps 3 (SIMPLE: one tensor per source) or 2
+// CTAs per SM resident (2 for both variants).
 constexpr int PV_ROWS = 256;     // rows per CTA
-__global__ void __launch_bounds__(PW_THREADS) pointwise_vec_kernel(dsg_pointwise_args a) {
+DSG_D void pv_eval(const uint4& x1, const uint4& x2, bool has_x2, int relu, const float* cf /* [3][PW_CT] */, int c8, float* v) {
+    float t[8], c1[8], cb[8];
+    unpack8(x1, t);
+    load8f(cf + c8, c1, 1.f);
+    load8f(cf + PW_CT + c8, cb, 0.f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = fmaf(t[j], c1[j], cb[j]);
+    if (has_x2) {
+        unpack8(x2, t);
+        load8f(cf + 2 * PW_CT + c8, c1, 1.f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = fmaf(t[j], c1[j], v[j]);
+    }
+    if (relu) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
+    }
+}
+DSG_D void pv_stage_coefs(const ActSrc& s, bool on, int c0, int C, float* cf /* [3][PW_CT] */) {
+    for (int i = threadIdx.x; i < PW_CT; i += PW_THREADS) {
+        const int ch = c0 + i;
+        const bool in = on && ch < C;
+        cf[i] = (in && s.a1) ? s.a1[ch] : 1.f;
+        cf[PW_CT + i] = ((in && s.b1) ? s.b1[ch] : 0.f) + ((in && s.b2) ? s.b2[ch] : 0.f);
+        cf[2 * PW_CT + i] = (in && s.a2) ? s.a2[ch] : 1.f;
+    }
+}
+
+template <bool SIMPLE>
+__global__ void __launch_bounds__(PW_THREADS, 2) pointwise_vec_kernel(dsg_pointwise_args a) {
+    constexpr int U = SIMPLE ? 4 : 2;
     DSG_SHARED float s_red[2][PW_THREADS / 8][PW_CT];
+    DSG_SHARED __align__(16) float cf_s[3 * PW_CT];
+    DSG_SHARED __align__(16) float cf_m[3 * PW_CT];
     const int tid = threadIdx.x, cc = tid & 7, rl = tid >> 3;         // 8 chunks x 32 row lanes
-    const int c = blockIdx.y * PW_CT + cc * 8;
+    const int c0 = blockIdx.y * PW_CT, c = c0 + cc * 8;
     const long long r0 = (long long)blockIdx.x * PV_ROWS;
+    pv_stage_coefs(a.src, true, c0, a.C, cf_s);
+    pv_stage_coefs(a.mask, a.has_mask != 0, c0, a.C, cf_m);
+    __syncthreads();
     float s1[8], s2[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) s1[j] = s2[j] = 0.f;
     if (c < a.C) {
-        Act8 src, msk;
-        src.init(a.src, c);
-        if (a.has_mask) msk.init(a.mask, c);
+        const bf16* x1p = reinterpret_cast<const bf16*>(a.src.x1) + c;
+        const bf16* x2p = (!SIMPLE && a.src.x2) ? reinterpret_cast<const bf16*>(a.src.x2) + c : nullptr;
+        const bf16* m1p = a.has_mask ? reinterpret_cast<const bf16*>(a.mask.x1) + c : nullptr;
+        const bf16* m2p = (!SIMPLE && a.has_mask && a.mask.x2) ? reinterpret_cast<const bf16*>(a.mask.x2) + c : nullptr;
         const bf16* partner = a.partner ? reinterpret_cast<const bf16*>(a.partner) + c : nullptr;
         bf16* out = a.out ? reinterpret_cast<bf16*>(a.out) + c : nullptr;
-#pragma unroll 2
-        for (int i = rl; i < PV_ROWS; i += PW_THREADS / 8) {
-            const long long r = r0 + i;
-            if (r >= a.rows) break;
-            float v[8];
-            src.eval(r, v);
-            if (a.has_mask) {
-                float m[8];
-                msk.eval(r, m);
+        uint4 z4;
+        z4.x = z4.y = z4.z = z4.w = 0u;
+        for (int i0 = 0; i0 < PV_ROWS / (PW_THREADS / 8); i0 += U) {
+            uint4 x1[U], x2[U], m1[U], m2[U], pp[U];
+            bool ok[U];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) v[j] = m[j] > 0.f ? v[j] : 0.f;
+            for (int u = 0; u < U; ++u) {
+                const long long r = r0 + rl + (long long)(i0 + u) * (PW_THREADS / 8);
+                ok[u] = r < a.rows;
+                x1[u] = x2[u] = m1[u] = m2[u] = pp[u] = z4;
+                if (ok[u]) {
+                    x1[u] = *reinterpret_cast<const uint4*>(x1p + r * a.src.ld1);
+                    if (!SIMPLE && x2p) x2[u] = *reinterpret_cast<const uint4*>(x2p + r * a.src.ld2);
+                    if (m1p) m1[u] = *reinterpret_cast<const uint4*>(m1p + r * a.mask.ld1);
+                    if (!SIMPLE && m2p) m2[u] = *reinterpret_cast<const uint4*>(m2p + r * a.mask.ld2);
+                    if (partner) pp[u] = *reinterpret_cast<const uint4*>(partner + r * a.ld_partner);
+                }
             }
-            if (a.stat_sum) {
-                float p[8];
-                if (partner) unpack8(*reinterpret_cast<const uint4*>(partner + r * a.ld_partner), p);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) { s1[j] += v[j]; s2[j] += v[j] * (partner ? p[j] : v[j]); }
+            for (int u = 0; u < U; ++u) {
+                if (!ok[u]) continue;
+                const long long r = r0 + rl + (long long)(i0 + u) * (PW_THREADS / 8);
+                float v[8];
+                pv_eval(x1[u], x2[u], !SIMPLE && x2p != nullptr, a.src.relu, cf_s, cc * 8, v);
+                if (m1p) {
+                    float m[8];
+                    pv_eval(m1[u], m2[u], !SIMPLE && m2p != nullptr, a.mask.relu, cf_m, cc * 8, m);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) v[j] = m[j] > 0.f ? v[j] : 0.f;
+                }
+                if (a.stat_sum) {
+                    float p[8];
+                    if (partner) unpack8(pp[u], p);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) { s1[j] += v[j]; s2[j] += v[j] * (partner ? p[j] : v[j]); }
+                }
+                if (out) *reinterpret_cast<uint4*>(out + r * a.ld_out) = pack8(v);
             }
-            if (out) *reinterpret_cast<uint4*>(out + r * a.ld_out) = pack8(v);
         }
     }
     if (a.stat_sum) {
