@@ -18,14 +18,17 @@ namespace tc {
 constexpr int MS_TO = 4;            // output (fwd) / input (bwd) frames per CTA: M = 128 = 4 frames x 32 padded rows
 constexpr int MS_THREADS = 256;
 
-DSG_D int floordiv(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
-DSG_D int posmod(int a, int b) { int m = a % b; return m < 0 ? m + b : m; }
+DSG_HD int floordiv(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
+DSG_HD int posmod(int a, int b) { int m = a % b; return m < 0 ? m + b : m; }
 
 // A conv branch owns channels [lo,hi).  Its UMMA operands use the *8-aligned channel window* [lo8, lo8 + 8*nchw) that
 // covers it, so staging is whole 16-byte chunks; the few foreign channels inside the window meet zero weight rows.
 struct MsBranchGeom {
     int w, lo8, off, nchw, Kp, nch, d, qmin, Fq, col;   // width, window start, lo-lo8, window chunks, padded K (=N), chunks, dilation, ...
+    int nsh;                                            // log2(nch) when nch is a power of two, else -1
 };
+// geometry of every branch, computed once on the host and passed by value (no per-thread recomputation)
+struct MsGeomPack { MsBranchGeom g[8]; };
 
 DSG_HD void ms_window(int lo, int hi, int& lo8, int& nchw, int& Kp) {
     lo8 = lo & ~7;
@@ -33,7 +36,7 @@ DSG_HD void ms_window(int lo, int hi, int& lo8, int& nchw, int& Kp) {
     Kp = (nchw * 8 + 15) & ~15;
 }
 
-DSG_D MsBranchGeom ms_geom(const dsg_ms_temporal_args& a, int j, int s) {
+DSG_HD MsBranchGeom ms_geom(const dsg_ms_temporal_args& a, int j, int s) {
     MsBranchGeom g;
     g.w = a.br[j].hi - a.br[j].lo;
     ms_window(a.br[j].lo, a.br[j].hi, g.lo8, g.nchw, g.Kp);
@@ -45,7 +48,20 @@ DSG_D MsBranchGeom ms_geom(const dsg_ms_temporal_args& a, int j, int s) {
     g.col = 0;
     for (int i = 0; i < j; ++i)
         if (a.br[i].kind == 0) { int l8, nw, kp; ms_window(a.br[i].lo, a.br[i].hi, l8, nw, kp); g.col += kp; }
+    g.nsh = -1;
+    for (int b = 0; b < 8; ++b) if ((1 << b) == g.nch) g.nsh = b;
     return g;
+}
+static MsGeomPack ms_geom_pack(const dsg_ms_temporal_args& a) {
+    MsGeomPack p{};
+    for (int j = 0; j < a.n_branches && j < 8; ++j)
+        if (a.br[j].kind == 0) p.g[j] = ms_geom(a, j, a.stride);
+    return p;
+}
+// item -> (row, chunk) without an integer division when the chunk count is a power of two
+DSG_D void ms_split(const MsBranchGeom& g, int it, int& row, int& kc) {
+    if (g.nsh >= 0) { row = it >> g.nsh; kc = it & (g.nch - 1); }
+    else { row = it / g.nch; kc = it - row * g.nch; }
 }
 
 // byte offset of branch j's packed weight tiles inside wpack: [orientation 0: n=co,k=ci | 1: n=ci,k=co][tap][Kp x Kp] bf16
@@ -146,11 +162,13 @@ DSG_D void ms_stage_H(const dsg_ms_temporal_args& a, const MsBranchGeom& g, int 
             const int it = it0 + b * MS_THREADS;
             off[b] = -1; c8s[b] = -1;
             if (it < total) {
-                const int kc = it % g.nch, row = it / g.nch;
+                int kc, row;
+                ms_split(g, it, row, kc);
                 const int v = row & 31, fi = row >> 5;
                 off[b] = (int)op_off(row, kc, g.nch);
                 if (v < Vp && kc < g.nchw) {
-                    const int p = fi / g.Fq, qi = fi - p * g.Fq;
+                    int p = 0, qi = fi;
+                    while (qi >= g.Fq) { qi -= g.Fq; ++p; }
                     const int t = s * (tq0 + qi) + p;
                     if (t >= 0 && t < a.T_in) {
                         c8s[b] = g.lo8 + kc * 8;
@@ -188,7 +206,8 @@ DSG_D void ms_stage_dO(const dsg_ms_temporal_args& a, const MsBranchGeom& g, int
             const int it = it0 + b * MS_THREADS;
             off[b] = -1; c8s[b] = -1;
             if (it < total) {
-                const int kc = it % g.nch, row = it / g.nch;
+                int kc, row;
+                ms_split(g, it, row, kc);
                 const int v = row & 31, qi = row >> 5;
                 off[b] = (int)op_off(row, kc, g.nch);
                 const int tpo = tpo0 + qi;
@@ -221,7 +240,7 @@ DSG_D void ms_stage_dO(const dsg_ms_temporal_args& a, const MsBranchGeom& g, int
     }
 }
 
-__global__ void __launch_bounds__(MS_THREADS, 4) ms_temporal_fwd_kernel(dsg_ms_temporal_args a, int h_bytes, int w_bytes, int tmem_cols) {
+__global__ void __launch_bounds__(MS_THREADS, 4) ms_temporal_fwd_kernel(dsg_ms_temporal_args a, MsGeomPack gp, int h_bytes, int w_bytes, int tmem_cols) {
     DSG_DYN_SMEM(smem);
     __shared__ uint64_t mbar;
     __shared__ uint32_t tmem_base_s;
@@ -232,8 +251,13 @@ __global__ void __launch_bounds__(MS_THREADS, 4) ms_temporal_fwd_kernel(dsg_ms_t
     unsigned char* Wt = smem + h_bytes;                      // 3 taps x [Kp x Kp]
     bf16* feat_s = reinterpret_cast<bf16*>(smem + h_bytes + w_bytes);      // [MS_TO*V][C]
     const bf16* Bx = reinterpret_cast<const bf16*>(a.b.x1);
-    __shared__ float cfa[MS_CMAX], cfb[MS_CMAX];
+    __shared__ float cfa[MS_CMAX], cfb[MS_CMAX], bias_s[MS_CMAX], addc_s[32];
+    const int CS = C + 8;                                    // feat_s row pitch: 16-byte aligned rows, bank-staggered
     ms_stage_b(a, cfa, cfb);
+    for (int j = 0; j < a.n_branches; ++j)
+        if (a.br[j].kind == 0)
+            for (int k = tid; k < a.br[j].hi - a.br[j].lo; k += MS_THREADS) bias_s[a.br[j].lo + k] = a.br[j].bias[k];
+    if (tid < 32) addc_s[tid] = (a.has_ext && tid < V) ? a.add_coeff[tid] : 0.f;
 
     if (tid == 0) {
         mbar_init(&mbar, 1);
@@ -249,7 +273,7 @@ __global__ void __launch_bounds__(MS_THREADS, 4) ms_temporal_fwd_kernel(dsg_ms_t
     int issued = 0;
     for (int j = 0; j < a.n_branches; ++j) {
         if (a.br[j].kind != 0) continue;
-        const MsBranchGeom g = ms_geom(a, j, s);
+        const MsBranchGeom& g = gp.g[j];
         if (issued) mbar_wait(&mbar, phase ^ 1);             // the previous branch's MMAs are done with Ht / Wt
         // ---- stage relu(bn(B)) over the branch's channel window (with the temporal halo)
         ms_stage_H(a, g, n, tp0 + g.qmin, s, Vp, Ht, cfa, cfb);
@@ -277,23 +301,43 @@ __global__ void __launch_bounds__(MS_THREADS, 4) ms_temporal_fwd_kernel(dsg_ms_t
         issued = 1;
         phase ^= 1;
     }
-    // ---- max-pool / pass-through branches on the CUDA cores while the last MMAs drain
-    for (int j = 0; j < a.n_branches; ++j) {
-        const int kind = a.br[j].kind;
-        if (kind == 0) continue;
-        const int lo = a.br[j].lo, w = a.br[j].hi - lo;
-        for (int it = tid; it < MS_TO * w * (V + 1); it += MS_THREADS) {
-            const int c = lo + it % w, rest = it / w;
-            const int vv = rest % (V + 1), fl = rest / (V + 1);
-            const int tp = tp0 + fl;
-            if (tp >= a.T_out) continue;
-            if (vv == V) {                                   // the joint-mean column: only its own value is kept (oglob)
-                if (a.has_ext) a.oglob[((long long)n * a.T_out + tp) * C + c] = ms_mp_out(a, kind, n, tp, V, c, Vp);
-                continue;
+    // ---- max-pool / pass-through branches on the CUDA cores while the last MMAs drain: warp = (frame, half of the joints),
+    //      lanes walk the channels of the range; the joint-mean column is evaluated first and stays in a register
+    {
+        const int fl = warp & 3, half = warp >> 2;
+        const int tp = tp0 + fl;
+        const int v0 = half ? (V + 1) / 2 : 0, v1 = half ? V : (V + 1) / 2;
+        for (int j = 0; j < a.n_branches; ++j) {
+            const int kind = a.br[j].kind;
+            if (kind == 0 || tp >= a.T_out) continue;
+            const int lo = a.br[j].lo, w = a.br[j].hi - lo;
+            const int tc = tp * s;                                           // centre input frame
+            const bool has_m = tc - 1 >= 0, has_p = tc + 1 < a.T_in;
+            for (int c0 = 0; c0 < w; c0 += 32) {
+                if (c0 + lane >= w) continue;
+                const int c = lo + c0 + lane;
+                const float ca = cfa[c], cb = cfb[c];
+                const bf16* col = Bx + ((long long)n * a.T_in + tc) * Vp * a.b.ld1 + c;     // (frame tc, column 0, channel c)
+                const long long fstep = (long long)Vp * a.b.ld1;
+                float glob = 0.f;
+                for (int vv = a.has_ext ? -1 : v0; vv < v1; vv = (vv < 0 ? v0 : vv + 1)) {
+                    const int cv = vv < 0 ? V : vv;                          // -1: the joint-mean column
+                    const bf16* q = col + (long long)cv * a.b.ld1;
+                    float val = fmaf(__bfloat162float(q[0]), ca, cb);
+                    if (kind == 1) {
+                        val = fmaxf(val, 0.f);
+                        if (has_m) val = fmaxf(val, fmaf(__bfloat162float(q[-fstep]), ca, cb));
+                        if (has_p) val = fmaxf(val, fmaf(__bfloat162float(q[fstep]), ca, cb));
+                    }
+                    if (vv < 0) {
+                        glob = val;
+                        if (half == 0) a.oglob[((long long)n * a.T_out + tp) * C + c] = val;
+                        continue;
+                    }
+                    if (a.has_ext) val = fmaf(glob, addc_s[vv], val);
+                    feat_s[(fl * V + vv) * CS + c] = __float2bfloat16(val);
+                }
             }
-            float val = ms_mp_out(a, kind, n, tp, vv, c, Vp);
-            if (a.has_ext) val = fmaf(ms_mp_out(a, kind, n, tp, V, c, Vp), a.add_coeff[vv], val);
-            feat_s[(fl * V + vv) * C + c] = __float2bfloat16(val);
         }
     }
     if (issued) {
@@ -302,26 +346,31 @@ __global__ void __launch_bounds__(MS_THREADS, 4) ms_temporal_fwd_kernel(dsg_ms_t
         // ---- conv branches: TMEM -> registers; warp w reads frame (w & 3); lanes are joints (lane V = joint-mean column)
         const int fl = warp & 3, half = warp >> 2;
         const int tp = tp0 + fl;
-        const float addv = (a.has_ext && lane < V) ? a.add_coeff[lane] : 0.f;
+        const float addv = (a.has_ext && lane < V) ? addc_s[lane] : 0.f;
+        const bool row_live = lane < V && tp < a.T_out, glob_live = lane == V && tp < a.T_out;
+        bf16* frow = feat_s + (fl * V + lane) * CS;
+        float* grow = a.oglob + ((long long)n * a.T_out + tp) * C;
         int gcount = 0;
         for (int j = 0; j < a.n_branches; ++j) {
             if (a.br[j].kind != 0) continue;
-            const MsBranchGeom g = ms_geom(a, j, s);
+            const MsBranchGeom& g = gp.g[j];
+            const int blo = a.br[j].lo, bhi = a.br[j].hi;
             for (int c16 = 0; c16 < g.Kp; c16 += 16, ++gcount) {
                 if ((gcount & 1) != half) continue;
                 float v[16];
                 tmem_ld16(tmem_d + ((uint32_t)(fl * 32) << 16) + (uint32_t)(g.col + c16), v);
+                const int ch0 = g.lo8 + c16;                                 // absolute channel of window column c16
 #pragma unroll
                 for (int e = 0; e < 16; ++e) {
-                    const int k = c16 + e - g.off;                          // channel inside the branch (window column - offset)
-                    const bool in = k >= 0 && k < g.w;
-                    float val = v[e] + (in ? a.br[j].bias[k] : 0.f);
+                    const int ch = ch0 + e;
+                    if (ch < blo || ch >= bhi) continue;                     // warp-uniform
+                    float val = v[e] + bias_s[ch];
                     if (a.has_ext) {
                         const float glob = __shfl_sync(0xffffffffu, val, V);
-                        if (lane == V && in && tp < a.T_out) a.oglob[((long long)n * a.T_out + tp) * C + a.br[j].lo + k] = val;
+                        if (glob_live) grow[ch] = val;
                         val = fmaf(glob, addv, val);
                     }
-                    if (lane < V && in && tp < a.T_out) feat_s[(fl * V + lane) * C + a.br[j].lo + k] = __float2bfloat16(val);
+                    if (row_live) frow[ch] = __float2bfloat16(val);
                 }
             }
         }
@@ -341,7 +390,7 @@ __global__ void __launch_bounds__(MS_THREADS, 4) ms_temporal_fwd_kernel(dsg_ms_t
             const int fl = r / V, vv = r - fl * V;
             const int tp = tp0 + fl;
             if (tp >= a.T_out) break;
-            const uint4 u = *reinterpret_cast<const uint4*>(feat_s + r * C + cc * 8);
+            const uint4 u = *reinterpret_cast<const uint4*>(feat_s + r * CS + cc * 8);
             *reinterpret_cast<uint4*>(feat + (((long long)n * a.T_out + tp) * V + vv) * a.ld_feat + cc * 8) = u;
             if (a.stat_sum) {
                 float x[8];
@@ -418,11 +467,12 @@ static const char* launch_ms_temporal_fwd(const dsg_ms_temporal_args& a, dsg_str
     if (!h.ok || !ms_args_ok(a)) return "ms_temporal_fwd: unsupported shape (use the per-branch path)";
     if ((uintptr_t)a.feat % 16 != 0 || a.ld_feat % 8 != 0) return "ms_temporal_fwd: feat must be 16-byte aligned";
     if (a.n_samples <= 0 || a.T_out <= 0) return nullptr;
-    size_t smem = (size_t)h.h_bytes + h.w_bytes + h.feat_bytes;
+    size_t smem = (size_t)h.h_bytes + h.w_bytes + (size_t)MS_TO * a.V * (a.C + 8) * 2;
+    if (smem > 200 * 1024) return "ms_temporal_fwd: shared memory budget exceeded";
     if (const char* e = ms_launch_wpack(a, st)) return e;
     cudaFuncSetAttribute(ms_temporal_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     dim3 grid((a.T_out + MS_TO - 1) / MS_TO, a.n_samples);
-    ms_temporal_fwd_kernel<<<grid, dim3(MS_THREADS), smem, st>>>(a, h.h_bytes, h.w_bytes, h.tmem_cols);
+    ms_temporal_fwd_kernel<<<grid, dim3(MS_THREADS), smem, st>>>(a, ms_geom_pack(a), h.h_bytes, h.w_bytes, h.tmem_cols);
     return dsg_launch_error();
 }
 
@@ -456,7 +506,7 @@ DSG_D float ms_dfeat(const dsg_ms_temporal_args& a, int n, int tp, int v, int c)
     return act_value<bf16>(a.dfeat, ((long long)n * a.T_out + tp) * a.V + v, c);
 }
 
-__global__ void __launch_bounds__(MS_THREADS, 3) ms_temporal_bwd_data_kernel(dsg_ms_temporal_args a, int h_bytes, int w_bytes, int tmem_cols,
+__global__ void __launch_bounds__(MS_THREADS, 3) ms_temporal_bwd_data_kernel(dsg_ms_temporal_args a, MsGeomPack gp, int h_bytes, int w_bytes, int tmem_cols,
                                                                           int mp_lo, int mp_hi) {
     DSG_DYN_SMEM(smem);
     __shared__ uint64_t mbar;
@@ -498,7 +548,7 @@ __global__ void __launch_bounds__(MS_THREADS, 3) ms_temporal_bwd_data_kernel(dsg
     int issued = 0;
     for (int j = 0; j < a.n_branches; ++j) {
         if (a.br[j].kind != 0) continue;
-        const MsBranchGeom g = ms_geom(a, j, s);
+        const MsBranchGeom& g = gp.g[j];
         const MsBwdTaps tp = ms_bwd_taps(g.d, s, p_in);
         if (tp.n == 0) continue;
         if (issued) mbar_wait(&mbar, phase ^ 1);
@@ -656,7 +706,7 @@ __global__ void __launch_bounds__(MS_THREADS, 3) ms_temporal_bwd_data_kernel(dsg
         int gcount = 0;
         for (int j = 0; j < a.n_branches; ++j) {
             if (!(issued & (1 << j))) continue;
-            const MsBranchGeom g = ms_geom(a, j, s);
+            const MsBranchGeom& g = gp.g[j];
             for (int c16 = 0; c16 < g.Kp; c16 += 16, ++gcount) {
                 if ((gcount & 1) != half) continue;
                 float v[16];
@@ -726,7 +776,7 @@ __global__ void __launch_bounds__(MS_THREADS, 3) ms_temporal_bwd_data_kernel(dsg
 // dW[:, :, dt] (+)= dO^T * H_shift(dt) for the three taps in three TMEM column ranges.  Both operands are read as
 // MN-major (the reduction runs over rows): the staged tiles are byte-identical to the K-major ones, only the
 // descriptor strides swap (SBO = 128 B between 8-channel groups, LBO = 128 B * chunks between 8-row groups).
-__global__ void __launch_bounds__(MS_THREADS) ms_temporal_bwd_weight_kernel(dsg_ms_temporal_args a, int h_bytes, int d_bytes, int tmem_cols) {
+__global__ void __launch_bounds__(MS_THREADS) ms_temporal_bwd_weight_kernel(dsg_ms_temporal_args a, MsGeomPack gp, int h_bytes, int d_bytes, int tmem_cols) {
     DSG_DYN_SMEM(smem);
     __shared__ uint64_t mbar;
     __shared__ uint32_t tmem_base_s;
@@ -756,7 +806,7 @@ __global__ void __launch_bounds__(MS_THREADS) ms_temporal_bwd_weight_kernel(dsg_
     int pending = 0;
     for (int j = 0; j < a.n_branches; ++j) {
         if (a.br[j].kind != 0) continue;
-        const MsBranchGeom g = ms_geom(a, j, s);
+        const MsBranchGeom& g = gp.g[j];
         if (tid < 128) s_db[tid] = 0.f;
         int first = 1;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -852,7 +902,7 @@ static const char* launch_ms_temporal_bwd_data(const dsg_ms_temporal_args& a, ds
     cudaFuncSetAttribute(ms_temporal_bwd_data_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const int frames_per_plane = (a.T_in + a.stride - 1) / a.stride;
     dim3 grid((frames_per_plane + MS_TO - 1) / MS_TO, a.n_samples, a.stride);
-    ms_temporal_bwd_data_kernel<<<grid, dim3(MS_THREADS), smem, st>>>(a, h.h_bytes, h.w_bytes, h.tmem_cols, mp_lo, mp_hi);
+    ms_temporal_bwd_data_kernel<<<grid, dim3(MS_THREADS), smem, st>>>(a, ms_geom_pack(a), h.h_bytes, h.w_bytes, h.tmem_cols, mp_lo, mp_hi);
     return dsg_launch_error();
 }
 
@@ -878,7 +928,7 @@ static const char* launch_ms_temporal_bwd_weight(const dsg_ms_temporal_args& a, 
     cudaFuncSetAttribute(ms_temporal_bwd_weight_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     int n_tiles = a.n_samples * ((a.T_out + MS_TO - 1) / MS_TO);
     int grid = n_tiles < 2 * 148 ? n_tiles : 2 * 148;
-    ms_temporal_bwd_weight_kernel<<<dim3(grid), dim3(MS_THREADS), smem, st>>>(a, h.h_bytes, d_bytes, cols);
+    ms_temporal_bwd_weight_kernel<<<dim3(grid), dim3(MS_THREADS), smem, st>>>(a, ms_geom_pack(a), h.h_bytes, d_bytes, cols);
     return dsg_launch_error();
 }
 
