@@ -44,14 +44,23 @@ DSG_D void topo_load_features(const dsg_topology_args& a, const TopoSmem& sm, in
     }
 }
 
-// pre-tanh argument for subset k, channel c, pair (u,w)
-DSG_D float topo_arg(const dsg_topology_args& a, const TopoSmem& sm, int k, int c, int u, int w) {
-    const int R = a.R, V = a.V;
-    if (k != 1) return sm.x1[(k * R + c) * V + u] - sm.x2[(k * R + c) * V + w];
-    const int e = a.edge_type[u * V + w];
-    const float* wr = a.We + (long long)(e * R + c) * R;
-    float s = a.be[e * R + c];
-    for (int i = 0; i < R; ++i) s = fmaf(wr[i], sm.x1[(R + i) * V + u] - sm.x2[(R + i) * V + w], s);
+// edge_linears weight staged in shared memory with rows padded to R+1 floats: conflict-free both for lanes that walk
+// the output channel o (stride R+1) and for lanes that walk the input channel i (stride 1)
+DSG_D void topo_stage_we(const dsg_topology_args& a, float* We_s, float* be_s) {
+    const int R = a.R;
+    for (int idx = threadIdx.x; idx < 15 * R * R; idx += TP_THREADS) {
+        const int i = idx % R, eo = idx / R;
+        We_s[eo * (R + 1) + i] = a.We[idx];
+    }
+    for (int idx = threadIdx.x; idx < 15 * R; idx += TP_THREADS) be_s[idx] = a.be[idx];
+}
+// subset-1 pre-tanh argument from the staged weights: We[e][o][:] . (x1[1][:,u] - x2[1][:,w]) + be[e][o]
+DSG_D float topo_arg1(const TopoSmem& sm, const float* We_s, const float* be_s, int R, int V, int e, int o, int u, int w) {
+    const float* wr = We_s + (e * R + o) * (R + 1);
+    const float* x1 = sm.x1 + R * V + u;
+    const float* x2 = sm.x2 + R * V + w;
+    float s = be_s[e * R + o];
+    for (int i = 0; i < R; ++i) s = fmaf(wr[i], x1[i * V] - x2[i * V], s);
     return s;
 }
 
@@ -60,7 +69,12 @@ __global__ void __launch_bounds__(TP_THREADS) topology_fwd_kernel(dsg_topology_a
     DSG_DYN_SMEM(smem_raw);
     const int R = a.R, V = a.V, VV = V * V, KC = 3 * R;
     TopoSmem sm(reinterpret_cast<float*>(smem_raw), R, V);
+    float* We_s = reinterpret_cast<float*>(smem_raw) + TopoSmem::floats(R, V);
+    float* be_s = We_s + 15 * R * (R + 1);
     const int tid = threadIdx.x;
+    topo_stage_we(a, We_s, be_s);
+    const float al0 = a.alpha[0], al1 = a.alpha[1], al2 = a.alpha[2];
+    const float be0 = a.beta[0], be1 = a.beta[1], be2 = a.beta[2];
     for (int n = blockIdx.x; n < a.n_samples; n += gridDim.x) {
         __syncthreads();
         topo_load_features(a, sm, n);
@@ -87,18 +101,29 @@ __global__ void __launch_bounds__(TP_THREADS) topology_fwd_kernel(dsg_topology_a
         }
         __syncthreads();
         T* out = reinterpret_cast<T*>(a.adyn) + (long long)n * VV * KC;
-        for (int idx = tid; idx < VV * KC; idx += TP_THREADS) {
-            int kc = idx % KC, uw = idx / KC;
-            int k = kc / R, c = kc - k * R, u = uw / V, w = uw - u * V;
-            float th = tanhf(topo_arg(a, sm, k, c, u, w));
-            float v = a.A[k * VV + uw] + a.alpha[k] * th + a.beta[k] * sm.S[k * VV + uw];
-            stf<T>(out + idx, v);
+        // subsets 0 and 2: tanh of a feature difference; thread = (pair, channel), channel fastest
+        for (int idx = tid; idx < VV * 2 * R; idx += TP_THREADS) {
+            const int cc = idx % (2 * R), uw = idx / (2 * R);
+            const int k = cc < R ? 0 : 2, c = cc < R ? cc : cc - R;
+            const int u = uw / V, w = uw - u * V;
+            const float th = tanhf(sm.x1[(k * R + c) * V + u] - sm.x2[(k * R + c) * V + w]);
+            const float v = a.A[k * VV + uw] + (k ? al2 : al0) * th + (k ? be2 : be0) * sm.S[k * VV + uw];
+            stf<T>(out + (long long)uw * KC + k * R + c, v);
+        }
+        // subset 1: edge-typed linear; consecutive threads = consecutive output channels of one pair
+        for (int idx = tid; idx < VV * R; idx += TP_THREADS) {
+            const int c = idx % R, uw = idx / R;
+            const int u = uw / V, w = uw - u * V;
+            const float th = tanhf(topo_arg1(sm, We_s, be_s, R, V, a.edge_type[uw], c, u, w));
+            const float v = a.A[VV + uw] + al1 * th + be1 * sm.S[VV + uw];
+            stf<T>(out + (long long)uw * KC + R + c, v);
         }
     }
 }
 
 // Backward.  Extra shared memory after TopoSmem:
-//   dx1,dx2 [3][R][V] each; dA_acc [3][V][V]; dWe_acc [15][R][R]; dbe_acc [15][R]; hbuf [V][R]; dbuf [V][R]; red[8]
+//   dx1,dx2 [3][R][V] each; dA_acc [3][V][V]; dWe_acc [15][R][R]; dbe_acc [15][R]; hbuf [V][R]; dbuf [V][R]; red[8];
+//   We_s [15][R][R+1] (row-padded weights); be_s [15][R]
 __global__ void __launch_bounds__(TP_THREADS) topology_bwd_kernel(dsg_topology_args a) {
     DSG_DYN_SMEM(smem_raw);
     const int R = a.R, V = a.V, VV = V * V, KC = 3 * R;
@@ -112,7 +137,10 @@ __global__ void __launch_bounds__(TP_THREADS) topology_bwd_kernel(dsg_topology_a
     float* hbuf = dbe_acc + 15 * R;
     float* dbuf = hbuf + V * R;
     float* red = dbuf + V * R;            // [8]: dalpha[3], dbeta[3]
-    const int tid = threadIdx.x;
+    float* We_s = red + 8;
+    float* be_s = We_s + 15 * R * (R + 1);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    topo_stage_we(a, We_s, be_s);
     for (int idx = tid; idx < 3 * VV + 15 * R * R + 15 * R; idx += TP_THREADS) dA_acc[idx] = 0.f;   // contiguous block
     if (tid < 8) red[tid] = 0.f;
 
@@ -123,14 +151,16 @@ __global__ void __launch_bounds__(TP_THREADS) topology_bwd_kernel(dsg_topology_a
         for (int idx = tid; idx < 6 * R * V; idx += TP_THREADS) dx1[idx] = 0.f;   // dx1 and dx2 are contiguous
         const float* g = a.dadyn + (long long)n * VV * KC;
         __syncthreads();
-        // (1) sS[k,u,w] = sum_c g[u,w,kR+c]  -> G ; dA accumulates it
-        for (int idx = tid; idx < 3 * VV; idx += TP_THREADS) {
-            int k = idx / VV, uw = idx - k * VV;
-            const float* gp = g + (long long)uw * KC + k * R;
-            float s = 0.f;
-            for (int c = 0; c < R; ++c) s += gp[c];
-            sm.G[idx] = s;
-            dA_acc[idx] += s;
+        // (1) sS[k,u,w] = sum_c g[u,w,kR+c]  -> G ; dA accumulates it.  A warp owns a pair (u,w): lanes read its 3R
+        //     gradients contiguously and reduce per subset
+        for (int uw = warp; uw < VV; uw += TP_THREADS / 32) {
+            const float* gp = g + (long long)uw * KC;
+            for (int k = 0; k < 3; ++k) {
+                float s = 0.f;
+                for (int c = lane; c < R; c += 32) s += gp[k * R + c];
+                s = warp_sum(s);
+                if (lane == 0) { sm.G[k * VV + uw] = s; dA_acc[k * VV + uw] += s; }
+            }
         }
         __syncthreads();
         // (2) softmax backward per column (k,w): dG = beta*S*(sS - sum_u sS*S); dbeta += sum sS*S
@@ -179,54 +209,49 @@ __global__ void __launch_bounds__(TP_THREADS) topology_bwd_kernel(dsg_topology_a
         my_dalpha2 = warp_sum(my_dalpha2);
         if ((tid & 31) == 0) { atomicAdd(&red[0], my_dalpha0); atomicAdd(&red[2], my_dalpha2); }
         __syncthreads();
-        // (4) subset 1 (edge-typed linear), one source joint u at a time
+        // (4) subset 1 (edge-typed linear), one source joint u at a time, two barriers per joint:
+        //     (a) h[w][o] = alpha1 * (1 - tanh^2) * g   (+ the dx1 column of the previous joint, from dbuf)
+        //     (b) dWe[e][o][i] += h[w][o] * d1[w][i], dbe[e][o] += h[w][o]   (thread owns (o,i): no atomics)
+        //         dd1[w][i] = sum_o We[e][o][i] h[w][o] -> dx2[1][i][w] -= dd1, dbuf = dd1
+        //     with d1[w][i] = x1[1][i][u] - x2[1][i][w] formed on the fly
         float my_dalpha1 = 0.f;
         const float al1 = a.alpha[1];
-        for (int u = 0; u < V; ++u) {
-            for (int idx = tid; idx < V * R; idx += TP_THREADS) {       // d1[w][i]
-                int i = idx % R, w = idx / R;
-                dbuf[idx] = sm.x1[(R + i) * V + u] - sm.x2[(R + i) * V + w];
+        const float* x1b = sm.x1 + R * V;
+        const float* x2b = sm.x2 + R * V;
+        for (int u = 0; u <= V; ++u) {
+            if (u > 0 && tid < R) {                                     // dx1[1][i][u-1] += sum_w dd1[w][i]
+                float sacc = 0.f;
+                for (int ww = 0; ww < V; ++ww) sacc += dbuf[ww * R + tid];
+                dx1[(R + tid) * V + u - 1] += sacc;
             }
-            __syncthreads();
-            for (int idx = tid; idx < V * R; idx += TP_THREADS) {       // h[w][o]
-                int o = idx % R, w = idx / R;
-                int e = a.edge_type[u * V + w];
-                const float* wr = a.We + (long long)(e * R + o) * R;
-                float s = a.be[e * R + o];
-                for (int i = 0; i < R; ++i) s = fmaf(wr[i], dbuf[w * R + i], s);
-                float th = tanhf(s);
-                float gg = g[(long long)(u * V + w) * KC + R + o];
+            if (u == V) break;
+            for (int idx = tid; idx < V * R; idx += TP_THREADS) {       // (a)
+                const int o = idx % R, w = idx / R;
+                const int e = a.edge_type[u * V + w];
+                const float th = tanhf(topo_arg1(sm, We_s, be_s, R, V, e, o, u, w));
+                const float gg = g[(long long)(u * V + w) * KC + R + o];
                 my_dalpha1 = fmaf(gg, th, my_dalpha1);
-                float h = al1 * (1.f - th * th) * gg;
-                hbuf[idx] = h;
-                atomicAdd(&dbe_acc[e * R + o], h);
+                hbuf[idx] = al1 * (1.f - th * th) * gg;
             }
             __syncthreads();
-            for (int idx = tid; idx < R * R; idx += TP_THREADS) {       // dWe[e][o][i] += h[w][o]*d1[w][i]
-                int i = idx % R, o = idx / R;
+            for (int idx = tid; idx < R * R; idx += TP_THREADS) {       // (b) dWe, dbe
+                const int i = idx % R, o = idx / R;
+                const float x1u = x1b[i * V + u];
                 for (int w = 0; w < V; ++w) {
-                    int e = a.edge_type[u * V + w];
-                    dWe_acc[(e * R + o) * R + i] += hbuf[w * R + o] * dbuf[w * R + i];
+                    const int e = a.edge_type[u * V + w];
+                    const float h = hbuf[w * R + o];
+                    dWe_acc[(e * R + o) * R + i] = fmaf(h, x1u - x2b[i * V + w], dWe_acc[(e * R + o) * R + i]);
+                    if (i == 0) dbe_acc[e * R + o] += h;
                 }
             }
-            __syncthreads();
-            for (int idx = tid; idx < V * R; idx += TP_THREADS) {       // dd1[w][i] = sum_o We[e][o][i] h[w][o]  (overwrites d1)
-                int i = idx % R, w = idx / R;
-                int e = a.edge_type[u * V + w];
-                const float* wc = a.We + (long long)e * R * R + i;
-                float s = 0.f;
-                for (int o = 0; o < R; ++o) s = fmaf(wc[(long long)o * R], hbuf[w * R + o], s);
-                dbuf[idx] = s;
-            }
-            __syncthreads();
-            for (int idx = tid; idx < V * R; idx += TP_THREADS) {       // scatter into dx1[1][i][u], dx2[1][i][w]
-                int i = idx % R, w = idx / R;
-                dx2[(R + i) * V + w] -= dbuf[w * R + i];
-                if (w == 0) {
-                    float s = 0.f;
-                    for (int ww = 0; ww < V; ++ww) s += dbuf[ww * R + i];
-                    dx1[(R + i) * V + u] += s;
-                }
+            for (int idx = tid; idx < V * R; idx += TP_THREADS) {       // (b) dd1
+                const int i = idx % R, w = idx / R;
+                const int e = a.edge_type[u * V + w];
+                const float* wc = We_s + e * R * (R + 1) + i;
+                float sacc = 0.f;
+                for (int o = 0; o < R; ++o) sacc = fmaf(wc[o * (R + 1)], hbuf[w * R + o], sacc);
+                dbuf[idx] = sacc;
+                dx2[(R + i) * V + w] -= sacc;
             }
             __syncthreads();
         }
@@ -255,7 +280,7 @@ __global__ void __launch_bounds__(TP_THREADS) topology_bwd_kernel(dsg_topology_a
 }
 
 static inline size_t topo_bwd_smem_floats(int R, int V) {
-    return TopoSmem::floats(R, V) + (size_t)6 * R * V + 3 * V * V + 15 * R * R + 15 * R + 2 * V * R + 8;
+    return TopoSmem::floats(R, V) + (size_t)6 * R * V + 3 * V * V + 15 * R * R + 15 * R + 2 * V * R + 8 + 15 * R * (R + 1) + 15 * R;
 }
 
 static const char* launch_topology(const dsg_topology_args& a, bool bwd, dsg_stream_t st) {
@@ -263,7 +288,7 @@ static const char* launch_topology(const dsg_topology_args& a, bool bwd, dsg_str
     if (a.n_samples <= 0) return nullptr;
     int grid = a.n_samples < 2 * 148 ? a.n_samples : 2 * 148;
     if (!bwd) {
-        size_t smem = TopoSmem::floats(a.R, a.V) * sizeof(float);
+        size_t smem = (TopoSmem::floats(a.R, a.V) + (size_t)15 * a.R * (a.R + 1) + 15 * a.R) * sizeof(float);
         if (a.adyn_dtype == DSG_BF16) {
             DSG_SET_SMEM(topology_fwd_kernel<bf16>, smem);
             dsg_launch(topology_fwd_kernel<bf16>, dim3(grid), dim3(TP_THREADS), smem, st, a);
