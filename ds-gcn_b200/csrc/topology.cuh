@@ -11,7 +11,8 @@
 
 namespace dsg {
 
-constexpr int TP_THREADS = 256;
+constexpr int TP_THREADS = 256;        // forward
+constexpr int TP_BWD_THREADS = 1024;   // backward: one CTA per SM (its accumulators fill shared memory), so many warps
 
 struct TopoSmem {
     float* x1;    // [3][R][V]
@@ -30,7 +31,7 @@ struct TopoSmem {
 DSG_D void topo_load_features(const dsg_topology_args& a, const TopoSmem& sm, int n) {
     const int R = a.R, V = a.V;
     const float* h = a.H + (long long)n * V * a.ld_h;
-    for (int idx = threadIdx.x; idx < 3 * R * V; idx += TP_THREADS) {
+    for (int idx = threadIdx.x; idx < 3 * R * V; idx += blockDim.x) {
         int c = idx % R, v = (idx / R) % V, k = idx / (R * V);
         float f1, f2;
         if (k < 2) {
@@ -48,11 +49,11 @@ DSG_D void topo_load_features(const dsg_topology_args& a, const TopoSmem& sm, in
 // the output channel o (stride R+1) and for lanes that walk the input channel i (stride 1)
 DSG_D void topo_stage_we(const dsg_topology_args& a, float* We_s, float* be_s) {
     const int R = a.R;
-    for (int idx = threadIdx.x; idx < 15 * R * R; idx += TP_THREADS) {
+    for (int idx = threadIdx.x; idx < 15 * R * R; idx += blockDim.x) {
         const int i = idx % R, eo = idx / R;
         We_s[eo * (R + 1) + i] = a.We[idx];
     }
-    for (int idx = threadIdx.x; idx < 15 * R; idx += TP_THREADS) be_s[idx] = a.be[idx];
+    for (int idx = threadIdx.x; idx < 15 * R; idx += blockDim.x) be_s[idx] = a.be[idx];
 }
 // subset-1 pre-tanh argument from the staged weights: We[e][o][:] . (x1[1][:,u] - x2[1][:,w]) + be[e][o]
 DSG_D float topo_arg1(const TopoSmem& sm, const float* We_s, const float* be_s, int R, int V, int e, int o, int u, int w) {
@@ -124,7 +125,7 @@ __global__ void __launch_bounds__(TP_THREADS) topology_fwd_kernel(dsg_topology_a
 // Backward.  Extra shared memory after TopoSmem:
 //   dx1,dx2 [3][R][V] each; dA_acc [3][V][V]; dWe_acc [15][R][R]; dbe_acc [15][R]; hbuf [V][R]; dbuf [V][R]; red[8];
 //   We_s [15][R][R+1] (row-padded weights); be_s [15][R]
-__global__ void __launch_bounds__(TP_THREADS) topology_bwd_kernel(dsg_topology_args a) {
+__global__ void __launch_bounds__(TP_BWD_THREADS) topology_bwd_kernel(dsg_topology_args a) {
     DSG_DYN_SMEM(smem_raw);
     const int R = a.R, V = a.V, VV = V * V, KC = 3 * R;
     float* base = reinterpret_cast<float*>(smem_raw);
@@ -139,32 +140,41 @@ __global__ void __launch_bounds__(TP_THREADS) topology_bwd_kernel(dsg_topology_a
     float* red = dbuf + V * R;            // [8]: dalpha[3], dbeta[3]
     float* We_s = red + 8;
     float* be_s = We_s + 15 * R * (R + 1);
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, NT = blockDim.x;
+    unsigned char* et_s = reinterpret_cast<unsigned char*>(be_s + 15 * R);   // [V*V] edge types
     topo_stage_we(a, We_s, be_s);
-    for (int idx = tid; idx < 3 * VV + 15 * R * R + 15 * R; idx += TP_THREADS) dA_acc[idx] = 0.f;   // contiguous block
+    for (int idx = tid; idx < VV; idx += NT) et_s[idx] = (unsigned char)a.edge_type[idx];
+    for (int idx = tid; idx < 3 * VV + 15 * R * R + 15 * R; idx += NT) dA_acc[idx] = 0.f;   // contiguous block
     if (tid < 8) red[tid] = 0.f;
 
     for (int n = blockIdx.x; n < a.n_samples; n += gridDim.x) {
         __syncthreads();
         topo_load_features(a, sm, n);
-        for (int idx = tid; idx < 3 * VV; idx += TP_THREADS) sm.S[idx] = a.S[(long long)n * 3 * VV + idx];
-        for (int idx = tid; idx < 6 * R * V; idx += TP_THREADS) dx1[idx] = 0.f;   // dx1 and dx2 are contiguous
+        for (int idx = tid; idx < 3 * VV; idx += NT) sm.S[idx] = a.S[(long long)n * 3 * VV + idx];
+        for (int idx = tid; idx < 6 * R * V; idx += NT) dx1[idx] = 0.f;   // dx1 and dx2 are contiguous
         const float* g = a.dadyn + (long long)n * VV * KC;
         __syncthreads();
-        // (1) sS[k,u,w] = sum_c g[u,w,kR+c]  -> G ; dA accumulates it.  A warp owns a pair (u,w): lanes read its 3R
-        //     gradients contiguously and reduce per subset
-        for (int uw = warp; uw < VV; uw += TP_THREADS / 32) {
-            const float* gp = g + (long long)uw * KC;
-            for (int k = 0; k < 3; ++k) {
-                float s = 0.f;
-                for (int c = lane; c < R; c += 32) s += gp[k * R + c];
-                s = warp_sum(s);
-                if (lane == 0) { sm.G[k * VV + uw] = s; dA_acc[k * VV + uw] += s; }
+        // (1) sS[k,u,w] = sum_c g[u,w,kR+c]  -> G ; dA accumulates it.  Thread per (pair, subset): R/4 independent
+        //     16-byte loads in flight
+        const bool g_vec = (R % 4 == 0) && ((uintptr_t)g % 16 == 0);
+        for (int idx = tid; idx < 3 * VV; idx += NT) {
+            const int k = idx % 3, uw = idx / 3;
+            const float* gp = g + (long long)uw * KC + k * R;
+            float s = 0.f;
+            if (g_vec) {
+                for (int c = 0; c < R; c += 4) {
+                    const float4 q = *reinterpret_cast<const float4*>(gp + c);
+                    s += (q.x + q.y) + (q.z + q.w);
+                }
+            } else {
+                for (int c = 0; c < R; ++c) s += gp[c];
             }
+            sm.G[k * VV + uw] = s;
+            dA_acc[k * VV + uw] += s;
         }
         __syncthreads();
         // (2) softmax backward per column (k,w): dG = beta*S*(sS - sum_u sS*S); dbeta += sum sS*S
-        for (int idx = tid; idx < 3 * V; idx += TP_THREADS) {
+        for (int idx = tid; idx < 3 * V; idx += NT) {
             int w = idx % V, k = idx / V;
             float dot = 0.f;
             for (int u = 0; u < V; ++u) dot = fmaf(sm.G[(k * V + u) * V + w], sm.S[(k * V + u) * V + w], dot);
@@ -179,7 +189,7 @@ __global__ void __launch_bounds__(TP_THREADS) topology_bwd_kernel(dsg_topology_a
         // (3) gram backward + subsets 0 and 2 of the tanh branch; thread per (k,c,v), no atomics:
         //     dx1[k,c,u] = sum_w dG[u,w] x2[c,w] + sum_w h[c,u,w];  dx2[k,c,w] = sum_u dG[u,w] x1[c,u] - sum_u h[c,u,w]
         float my_dalpha0 = 0.f, my_dalpha2 = 0.f;
-        for (int idx = tid; idx < 3 * R * V; idx += TP_THREADS) {
+        for (int idx = tid; idx < 3 * R * V; idx += NT) {
             int c = idx % R, v = (idx / R) % V, k = idx / (R * V);
             float s1 = 0.f, s2 = 0.f;
             const float* x1r = sm.x1 + (k * R + c) * V;
@@ -225,28 +235,28 @@ __global__ void __launch_bounds__(TP_THREADS) topology_bwd_kernel(dsg_topology_a
                 dx1[(R + tid) * V + u - 1] += sacc;
             }
             if (u == V) break;
-            for (int idx = tid; idx < V * R; idx += TP_THREADS) {       // (a)
+            for (int idx = tid; idx < V * R; idx += NT) {       // (a)
                 const int o = idx % R, w = idx / R;
-                const int e = a.edge_type[u * V + w];
+                const int e = (int)et_s[u * V + w];
                 const float th = tanhf(topo_arg1(sm, We_s, be_s, R, V, e, o, u, w));
                 const float gg = g[(long long)(u * V + w) * KC + R + o];
                 my_dalpha1 = fmaf(gg, th, my_dalpha1);
                 hbuf[idx] = al1 * (1.f - th * th) * gg;
             }
             __syncthreads();
-            for (int idx = tid; idx < R * R; idx += TP_THREADS) {       // (b) dWe, dbe
+            for (int idx = tid; idx < R * R; idx += NT) {       // (b) dWe, dbe
                 const int i = idx % R, o = idx / R;
                 const float x1u = x1b[i * V + u];
                 for (int w = 0; w < V; ++w) {
-                    const int e = a.edge_type[u * V + w];
+                    const int e = (int)et_s[u * V + w];
                     const float h = hbuf[w * R + o];
                     dWe_acc[(e * R + o) * R + i] = fmaf(h, x1u - x2b[i * V + w], dWe_acc[(e * R + o) * R + i]);
                     if (i == 0) dbe_acc[e * R + o] += h;
                 }
             }
-            for (int idx = tid; idx < V * R; idx += TP_THREADS) {       // (b) dd1
+            for (int idx = tid; idx < V * R; idx += NT) {       // (b) dd1
                 const int i = idx % R, w = idx / R;
-                const int e = a.edge_type[u * V + w];
+                const int e = (int)et_s[u * V + w];
                 const float* wc = We_s + e * R * (R + 1) + i;
                 float sacc = 0.f;
                 for (int o = 0; o < R; ++o) sacc = fmaf(wc[o * (R + 1)], hbuf[w * R + o], sacc);
@@ -260,7 +270,7 @@ __global__ void __launch_bounds__(TP_THREADS) topology_bwd_kernel(dsg_topology_a
         __syncthreads();
         // (5) write dH[n][v][9R]
         float* dh = a.dH + (long long)n * V * a.ld_h;
-        for (int idx = tid; idx < V * 9 * R; idx += TP_THREADS) {
+        for (int idx = tid; idx < V * 9 * R; idx += NT) {
             int col = idx % (9 * R), v = idx / (9 * R);
             float val;
             if (col < 2 * R) val = dx1[col * V + v];
@@ -273,14 +283,14 @@ __global__ void __launch_bounds__(TP_THREADS) topology_bwd_kernel(dsg_topology_a
         }
     }
     __syncthreads();
-    for (int idx = tid; idx < 3 * VV; idx += TP_THREADS) atomicAdd(a.dA + idx, dA_acc[idx]);
-    for (int idx = tid; idx < 15 * R * R; idx += TP_THREADS) atomicAdd(a.dWe + idx, dWe_acc[idx]);
-    for (int idx = tid; idx < 15 * R; idx += TP_THREADS) atomicAdd(a.dbe + idx, dbe_acc[idx]);
+    for (int idx = tid; idx < 3 * VV; idx += NT) atomicAdd(a.dA + idx, dA_acc[idx]);
+    for (int idx = tid; idx < 15 * R * R; idx += NT) atomicAdd(a.dWe + idx, dWe_acc[idx]);
+    for (int idx = tid; idx < 15 * R; idx += NT) atomicAdd(a.dbe + idx, dbe_acc[idx]);
     if (tid < 3) { atomicAdd(a.dalpha + tid, red[tid]); atomicAdd(a.dbeta + tid, red[3 + tid]); }
 }
 
 static inline size_t topo_bwd_smem_floats(int R, int V) {
-    return TopoSmem::floats(R, V) + (size_t)6 * R * V + 3 * V * V + 15 * R * R + 15 * R + 2 * V * R + 8 + 15 * R * (R + 1) + 15 * R;
+    return TopoSmem::floats(R, V) + (size_t)6 * R * V + 3 * V * V + 15 * R * R + 15 * R + 2 * V * R + 8 + 15 * R * (R + 1) + 15 * R + (V * V + 3) / 4;
 }
 
 static const char* launch_topology(const dsg_topology_args& a, bool bwd, dsg_stream_t st) {
@@ -301,7 +311,7 @@ static const char* launch_topology(const dsg_topology_args& a, bool bwd, dsg_str
         if (smem > 200 * 1024) return "topology_bwd: shared memory budget exceeded";
         grid = a.n_samples < 148 ? a.n_samples : 148;
         DSG_SET_SMEM(topology_bwd_kernel, smem);
-        dsg_launch(topology_bwd_kernel, dim3(grid), dim3(TP_THREADS), smem, st, a);
+        dsg_launch(topology_bwd_kernel, dim3(grid), dim3(TP_BWD_THREADS), smem, st, a);
     }
     return dsg_launch_error();
 }
