@@ -33,7 +33,7 @@ class ConvGemmArgs(C.Structure):
                 ("ext_in", c_int), ("contract_ext", c_int),
                 ("out", vp), ("ld_out", c_ll), ("add", vp), ("ld_add", c_ll), ("add2", vp), ("ld_add2", c_ll),
                 ("bcast", vp), ("bcast_scale", c_f), ("has_mask", c_int), ("mask", ActSrc),
-                ("stat_sum", vp), ("stat_sq", vp), ("partner", vp), ("ld_partner", c_ll)]
+                ("stat_sum", vp), ("stat_sq", vp), ("partner", vp), ("ld_partner", c_ll), ("wpack", vp)]
 
 
 class ConvWgradArgs(C.Structure):
@@ -101,6 +101,7 @@ class PointwiseArgs(C.Structure):
 EXPORTS = {
     # name: (restype, argtypes)
     "dsg_conv_gemm": (c_int, [C.POINTER(ConvGemmArgs), vp]),
+    "dsg_conv_gemm_wpack_bytes": (c_ll, [c_int, c_int]),
     "dsg_conv_wgrad": (c_int, [C.POINTER(ConvWgradArgs), vp]),
     "dsg_bn_finalize": (c_int, [C.POINTER(BnJob), c_int, vp]),
     "dsg_tmean": (c_int, [vp, c_int, c_ll, c_int, c_int, c_int, c_int, vp, vp]),

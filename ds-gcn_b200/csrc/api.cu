@@ -64,6 +64,15 @@ int dsg_conv_gemm(const dsg_conv_gemm_args* a, void* stream) {
     DSG_RET("dsg_conv_gemm", dsg::launch_conv_gemm<float>(*a, (dsg_stream_t)stream));
 }
 
+long long dsg_conv_gemm_wpack_bytes(int K, int N) {
+#ifdef DSG_EMU
+    (void)K; (void)N;
+    return 0;
+#else
+    return (K > 0 && N > 0) ? dsg::tc::conv_wpack_bytes(K, N) : 0;
+#endif
+}
+
 int dsg_conv_wgrad(const dsg_conv_wgrad_args* a, void* stream) {
     if (!a || !dtype_ok(a->dtype)) return fail("dsg_conv_wgrad", "bad arguments");
     if (a->taps < 1 || a->t_div < 1 || a->Vin < 1 || a->K < 1 || a->N < 1) return fail("dsg_conv_wgrad", "bad shape");

@@ -44,9 +44,43 @@ DSG_D float warp_colsum16(const float* v, int lane) {
     return w1 + __shfl_xor_sync(0xffffffffu, w1, 1);
 }
 
+// ---- pre-packed weights: bf16 tiles in the K-major no-swizzle UMMA layout, one per (128-column tile j, K pass p):
+//      tile (j, p) starts at byte j * 128 * Kp * 2 + 128 * (p * T2_KPASS) * 2 and holds Ntp(j) * kv_len(p) * 2 bytes
+static inline long long conv_wpack_bytes(int K, int N) {
+    const long long Kp = (K + 15) & ~15, ntiles = (N + T2_BN - 1) / T2_BN;
+    return ntiles * 128LL * Kp * 2;
+}
+__global__ void __launch_bounds__(256) conv_wpack_kernel(const float* W, long long ws_n, long long ws_k, int K, int N, unsigned char* out) {
+    const int Kp = (K + 15) & ~15;
+    const int kpass = Kp < T2_KPASS ? Kp : T2_KPASS;
+    const int n0 = blockIdx.x * T2_BN, kv0 = blockIdx.y * kpass;
+    const int Nt = N - n0 < T2_BN ? N - n0 : T2_BN, Ntp = (Nt + 15) & ~15;
+    const int kv_len = Kp - kv0 < kpass ? Kp - kv0 : kpass, nch = kv_len >> 3;
+    unsigned char* dst = out + (long long)blockIdx.x * 128 * Kp * 2 + 128LL * kv0 * 2;
+    for (int idx = threadIdx.x; idx < Ntp * nch; idx += 256) {
+        int n, kc;
+        if (ws_k == 1) { kc = idx % nch; n = idx / nch; } else { n = idx % Ntp; kc = idx / Ntp; }
+        float v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int k = kv0 + kc * 8 + e;
+            v[e] = (n < Nt && k < K) ? W[(long long)(n0 + n) * ws_n + (long long)k * ws_k] : 0.f;
+        }
+        *reinterpret_cast<uint4*>(dst + op_off(n, kc, nch)) = pack8(v);
+    }
+}
+DSG_D void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+DSG_D void bulk_g2s(void* dst_smem, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst_smem)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+// wmode 0: W[n][k] rows contiguous in k; 1: contiguous in n (MN-major B); 3: pre-packed tiles in a.wpack (bulk copy)
 __global__ void __launch_bounds__(T2_THREADS) conv_gemm_tc2_kernel(dsg_conv_gemm_args a, int wmode) {
     DSG_DYN_SMEM(smem);
-    __shared__ uint64_t mbar;
+    __shared__ uint64_t mbar, wbar;
     __shared__ uint32_t tmem_base_s;
     __shared__ float ext_s[2][8][16];                    // joint-mean accumulator rows of up to 8 frames, double-buffered
     __shared__ float s_acc[2][4][T2_BN];                 // per-warp column sums
@@ -104,6 +138,7 @@ __global__ void __launch_bounds__(T2_THREADS) conv_gemm_tc2_kernel(dsg_conv_gemm
 
     if (tid == 0) {
         mbar_init(&mbar, 1);
+        mbar_init(&wbar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) tmem_alloc(&tmem_base_s, tmem_cols);
@@ -114,12 +149,17 @@ __global__ void __launch_bounds__(T2_THREADS) conv_gemm_tc2_kernel(dsg_conv_gemm
     const uint32_t tmem_d = tmem_base_s;
     const uint32_t idesc = wmode == 1 ? make_idesc_bmn(128, Ntp) : make_idesc(128, Ntp);
 
-    uint32_t phase = 0;
+    uint32_t phase = 0, wphase = 0;
     int first = 1;
     for (int kv0 = 0; kv0 < Kp; kv0 += kpass) {
         const int kv_len = Kp - kv0 < kpass ? Kp - kv0 : kpass;
         const int nch = kv_len >> 3;
         if (!first) mbar_wait(&mbar, phase ^ 1);
+        if (wmode == 3 && tid == 0) {                        // this pass's weight tile: one bulk copy, overlapped with the A staging
+            const uint32_t bytes = (uint32_t)(Ntp * kv_len * 2);
+            mbar_expect_tx(&wbar, bytes);
+            bulk_g2s(Bbase, reinterpret_cast<const unsigned char*>(a.wpack) + (long long)blockIdx.y * 128 * Kp * 2 + 128LL * kv0 * 2, bytes, &wbar);
+        }
         // ---- A: my row, chunks in batches of 4 (loads first, then prologue + store)
         for (int kc0 = 0; kc0 < nch; kc0 += 4) {
             Act8Raw raw[4];
@@ -163,7 +203,7 @@ __global__ void __launch_bounds__(T2_THREADS) conv_gemm_tc2_kernel(dsg_conv_gemm
                     }
                 }
             }
-        } else {                                          // MN-major: my k row, all 8-channel groups
+        } else if (wmode == 1) {                          // MN-major: my k row, all 8-channel groups
             const int gN = Ntp >> 3;
             if (tid < kv_len) {
                 const int k = kv0 + tid;
@@ -215,6 +255,7 @@ __global__ void __launch_bounds__(T2_THREADS) conv_gemm_tc2_kernel(dsg_conv_gemm
             const uint32_t sbo = (uint32_t)nch * 128u;
             const uint32_t a0 = smem_u32(Abase), b0 = smem_u32(Bbase);
             const uint32_t gN = (uint32_t)(Ntp >> 3);
+            if (wmode == 3) { mbar_wait(&wbar, wphase); wphase ^= 1; }
             for (int ks = 0; ks < (kv_len >> 4); ++ks) {
                 const uint64_t ad = make_desc(a0 + ks * 256u, 128u, sbo);
                 const uint64_t bd = wmode == 1 ? make_desc(b0 + ks * 2u * gN * 128u, gN * 128u, 128u) : make_desc(b0 + ks * 256u, 128u, sbo);
@@ -326,9 +367,10 @@ static const char* launch_conv_gemm_tc2(const dsg_conv_gemm_args& a, dsg_stream_
     const int rpf = a.Vin + a.ext_in;
     if (a.dtype != DSG_BF16 || a.taps != 1 || rpf > 128 || a.K % 8 != 0 || a.N % 8 != 0) return nullptr;
     if (a.contract_ext && (a.ext_in || a.Vin < 2 || 128 / rpf > 8)) return nullptr;
-    if (!act8_ok(a.src) || (uintptr_t)a.W % 16 != 0) return nullptr;
+    if (!act8_ok(a.src) || (!a.wpack && (uintptr_t)a.W % 16 != 0)) return nullptr;
     int wmode;
-    if (a.ws_k == 1 && a.ws_n % 4 == 0) wmode = 0;
+    if (a.wpack && (uintptr_t)a.wpack % 128 == 0) wmode = 3;
+    else if (a.ws_k == 1 && a.ws_n % 4 == 0) wmode = 0;
     else if (a.ws_n == 1 && a.ws_k % 4 == 0) wmode = 1;
     else return nullptr;
     auto al16 = [](const void* p, long long ld) { return p == nullptr || ((uintptr_t)p % 16 == 0 && ld % 8 == 0); };
@@ -342,6 +384,10 @@ static const char* launch_conv_gemm_tc2(const dsg_conv_gemm_args& a, dsg_stream_
     const size_t smem = (size_t)(128 + T2_BN) * kpass * 2 + (size_t)(3 * Kp + 4 * T2_BN) * sizeof(float);
     const int Fr = 128 / rpf;
     dim3 grid((unsigned)((n_frames + Fr - 1) / Fr), (unsigned)((a.N + T2_BN - 1) / T2_BN));
+    if (wmode == 3) {
+        conv_wpack_kernel<<<dim3(grid.y, (unsigned)((Kp + kpass - 1) / kpass)), dim3(256), 0, st>>>(a.W, a.ws_n, a.ws_k, a.K, a.N, reinterpret_cast<unsigned char*>(a.wpack));
+        if (const char* e = dsg_launch_error()) return e;
+    }
     cudaFuncSetAttribute(conv_gemm_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     conv_gemm_tc2_kernel<<<grid, dim3(T2_THREADS), smem, st>>>(a, wmode);
     *handled = true;

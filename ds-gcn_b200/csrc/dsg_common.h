@@ -54,8 +54,14 @@ template <> DSG_D float4 ldf4<bf16>(const bf16* p) {
 template <class T> DSG_D void stf4(T* p, float4 v);
 template <> DSG_D void stf4<float>(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
 DSG_D uint32_t dsg_pack_bf16x2(float lo, float hi) {
+#ifndef DSG_EMU
+    uint32_t r;                                                    // one packed conversion (round-to-nearest-even both halves)
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+#else
     bf16 a = __float2bfloat16(lo), b = __float2bfloat16(hi);
     return (uint32_t)(*reinterpret_cast<uint16_t*>(&a)) | ((uint32_t)(*reinterpret_cast<uint16_t*>(&b)) << 16);
+#endif
 }
 template <> DSG_D void stf4<bf16>(bf16* p, float4 v) {
     uint2 u;

@@ -111,6 +111,12 @@ def conv_gemm(src, W, N, out, *, n_samples, T_in, T_out, Vin, ws=None, bias=None
     if partner is not None:
         assert partner.dtype == src.dtype
         a.partner, a.ld_partner = L.ptr(partner), _ld(partner)
+    wpack = None
+    if src.dtype == torch.bfloat16 and taps == 1 and K % 8 == 0 and N % 8 == 0:
+        nb = int(L.lib().dsg_conv_gemm_wpack_bytes(K, N))       # 0 in the simulator build
+        if nb > 0:
+            wpack = torch.empty(nb, dtype=torch.uint8, device=out.device)     # stream-ordered: free to die after the call
+            a.wpack = L.ptr(wpack)
     es = out.element_size()
     rows_out = n_samples * T_out * (Vin + int(ext_in) - int(contract_ext))
     nbytes = n_samples * T_in * Vin * K * es * (2 if src.x2 is not None else 1) + rows_out * N * es

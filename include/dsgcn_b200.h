@@ -89,8 +89,12 @@ typedef struct dsg_conv_gemm_args {
     double* stat_sq;
     const void* partner;
     long long ld_partner;
+    void* wpack;          /* optional caller-owned workspace of dsg_conv_gemm_wpack_bytes(K, N) bytes (256-byte aligned): the
+                             call first rewrites it with bf16 UMMA-ready weight tiles, which every CTA of the tcgen05 engine
+                             then pulls with one bulk copy instead of converting fp32 weights itself; NULL = convert in-kernel */
 } dsg_conv_gemm_args;
 int dsg_conv_gemm(const dsg_conv_gemm_args* a, void* stream);
+long long dsg_conv_gemm_wpack_bytes(int K, int N);
 
 /* ---- dsg_conv_wgrad -------------------------------------------------------------------------
  * dW[n*ws_n + k*ws_k + tap*ws_tap] += sum_{f',j} A[frame(f',tap), j, k] * B[f', j, n];  db[n] += sum B.
