@@ -44,6 +44,37 @@ DSG_D float warp_colsum16(const float* v, int lane) {
     return w1 + __shfl_xor_sync(0xffffffffu, w1, 1);
 }
 
+template <int NB, bool DUAL>
+DSG_D void t2_stage_a(const dsg_conv_gemm_args& a, long long sr, int tid, int kv0, int nch, unsigned char* Abase,
+                      const float* cf_a1, const float* cf_b, const float* cf_a2) {
+    const bf16* x1 = reinterpret_cast<const bf16*>(a.src.x1) + sr * a.src.ld1;
+    const bf16* x2 = DUAL ? reinterpret_cast<const bf16*>(a.src.x2) + sr * a.src.ld2 : nullptr;
+    for (int kc0 = 0; kc0 < nch; kc0 += NB) {
+        Act8Raw raw[NB];
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+            const int k = kv0 + (kc0 + b) * 8;
+            raw[b].a = raw[b].b = make_uint4(0u, 0u, 0u, 0u);
+            if (kc0 + b < nch && sr >= 0 && k < a.K) {
+                raw[b].a = *reinterpret_cast<const uint4*>(x1 + k);
+                if (DUAL) raw[b].b = *reinterpret_cast<const uint4*>(x2 + k);
+            }
+        }
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+            const int kc = kc0 + b, k = kv0 + kc * 8;
+            if (kc >= nch) continue;
+            uint4 pk = make_uint4(0u, 0u, 0u, 0u);
+            if (sr >= 0 && k < a.K) {
+                float v[8];
+                finish_smem(raw[b], DUAL, a.src.relu, cf_a1 + k, cf_b + k, cf_a2 + k, v);
+                pk = pack8(v);
+            }
+            *reinterpret_cast<uint4*>(Abase + op_off(tid, kc, nch)) = pk;
+        }
+    }
+}
+
 // ---- pre-packed weights: bf16 tiles in the K-major no-swizzle UMMA layout, one per (128-column tile j, K pass p):
 //      tile (j, p) starts at byte j * 128 * Kp * 2 + 128 * (p * T2_KPASS) * 2 and holds Ntp(j) * kv_len(p) * 2 bytes
 static inline long long conv_wpack_bytes(int K, int N) {
@@ -160,27 +191,9 @@ __global__ void __launch_bounds__(T2_THREADS) conv_gemm_tc2_kernel(dsg_conv_gemm
             mbar_expect_tx(&wbar, bytes);
             bulk_g2s(Bbase, reinterpret_cast<const unsigned char*>(a.wpack) + (long long)blockIdx.y * 128 * Kp * 2 + 128LL * kv0 * 2, bytes, &wbar);
         }
-        // ---- A: my row, chunks in batches of 4 (loads first, then prologue + store)
-        for (int kc0 = 0; kc0 < nch; kc0 += 4) {
-            Act8Raw raw[4];
-#pragma unroll
-            for (int b = 0; b < 4; ++b) {
-                const int k = kv0 + (kc0 + b) * 8;
-                if (kc0 + b < nch && sr >= 0 && k < a.K) raw[b] = act8_issue(a.src, sr, k);
-            }
-#pragma unroll
-            for (int b = 0; b < 4; ++b) {
-                const int kc = kc0 + b, k = kv0 + kc * 8;
-                if (kc >= nch) continue;
-                uint4 pk = make_uint4(0u, 0u, 0u, 0u);
-                if (sr >= 0 && k < a.K) {
-                    float v[8];
-                    finish_smem(raw[b], a.src.x2 != nullptr, a.src.relu, cf_a1 + k, cf_b + k, cf_a2 + k, v);
-                    pk = pack8(v);
-                }
-                *reinterpret_cast<uint4*>(Abase + op_off(tid, kc, nch)) = pk;
-            }
-        }
+        // ---- A: my row; NB independent 16-byte loads in flight per source (8 with one source, 4 + 4 with two)
+        if (a.src.x2 == nullptr) t2_stage_a<8, false>(a, sr, tid, kv0, nch, Abase, cf_a1, cf_b, cf_a2);
+        else t2_stage_a<4, true>(a, sr, tid, kv0, nch, Abase, cf_a1, cf_b, cf_a2);
         // ---- B: weights fp32 -> bf16
         if (wmode == 0) {
             if (tid < Ntp) {

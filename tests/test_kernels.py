@@ -11,12 +11,14 @@ import torch.nn.functional as F
 
 import dsgcn_b200
 from dsgcn_b200 import ops
+_lib = ops.L
 from oracle import dsgcn_oracle as O
 
 DTYPES = [torch.float32, torch.bfloat16]
 
 
 def close(got, ref, dtype, what=""):
+    _lib.join_side()      # weight-gradient kernels run on the side stream: make the current stream wait for them
     got, ref = got.detach().double().cpu(), ref.detach().double().cpu()
     err = (got - ref).norm() / (ref.norm() + 1e-12)
     tol = 1e-4 if dtype == torch.float32 else 1e-2
