@@ -771,24 +771,31 @@ __global__ void __launch_bounds__(MS_THREADS, 3) ms_temporal_bwd_data_kernel(dsg
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// Backward (weights).  Persistent CTAs, branch-outer: for conv branch j a CTA walks its share of (sample, 4 output
-// frames) tiles, stages relu(bn(B)) with halo (as forward) and dO (4 frames), and accumulates
-// dW[:, :, dt] (+)= dO^T * H_shift(dt) for the three taps in three TMEM column ranges.  Both operands are read as
-// MN-major (the reduction runs over rows): the staged tiles are byte-identical to the K-major ones, only the
-// descriptor strides swap (SBO = 128 B between 8-channel groups, LBO = 128 B * chunks between 8-row groups).
-__global__ void __launch_bounds__(MS_THREADS) ms_temporal_bwd_weight_kernel(dsg_ms_temporal_args a, MsGeomPack gp, int h_bytes, int d_bytes, int tmem_cols) {
+// Backward (weights).  Persistent CTAs, tile-outer: a CTA walks its share of (sample, 4 output frames) tiles; for every
+// tile it stages relu(bn(B)) with halo (as forward) and dO (4 frames) for ALL conv branches of the current group at
+// once — every byte of B and dfeat is read once per tile, all the loads of a tile are in flight together, and there
+// is one barrier / MMA round per tile — then accumulates dW_j[:, :, dt] (+)= dO_j^T * H_j,shift(dt) for every branch
+// and tap into disjoint TMEM column ranges.  Both operands are read as MN-major (the reduction runs over rows): the
+// staged tiles are byte-identical to the K-major ones, only the descriptor strides swap (SBO = 128 B between
+// 8-channel groups, LBO = 128 B * chunks between 8-row groups).  Branch groups exist because TMEM has 512 columns
+// (3 * Kp per branch, at most 256 per CTA so two CTAs share an SM) and shared memory is finite: 64-channel layers run
+// one group, 128-channel layers two, 256-channel layers one branch per group.
+struct MsBwPlan {
+    int ngroups, gstart[9];            // group g = conv branches with ordinal in [gstart[g], gstart[g+1])
+    int hoff[8], doff[8], col[8];      // per branch j: byte offsets of its H / dO tiles, first TMEM column
+};
+
+__global__ void __launch_bounds__(MS_THREADS) ms_temporal_bwd_weight_kernel(dsg_ms_temporal_args a, MsGeomPack gp, MsBwPlan pl, int tmem_cols) {
     DSG_DYN_SMEM(smem);
     __shared__ uint64_t mbar;
     __shared__ uint32_t tmem_base_s;
-    __shared__ float s_db[128];
+    __shared__ float s_db[8][128];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int V = a.V, Vp = a.V + a.has_ext, s = a.stride;
-    unsigned char* Ht = smem;
-    unsigned char* Dt = smem + h_bytes;
-    const bf16* Bx = reinterpret_cast<const bf16*>(a.b.x1);
-    __shared__ float cfa[MS_CMAX], cfb[MS_CMAX], dc1[MS_CMAX], dcb[MS_CMAX], dc2[MS_CMAX];
+    __shared__ float cfa[MS_CMAX], cfb[MS_CMAX], dc1[MS_CMAX], dcb[MS_CMAX], dc2[MS_CMAX], addc_s[32];
     ms_stage_b(a, cfa, cfb);
     ms_stage_d(a, dc1, dcb, dc2);
+    if (tid < 32) addc_s[tid] = (a.has_ext && tid < V) ? a.add_coeff[tid] : 0.f;
     const int chunks_t = (a.T_out + MS_TO - 1) / MS_TO;
     const int n_tiles = a.n_samples * chunks_t;
 
@@ -802,51 +809,77 @@ __global__ void __launch_bounds__(MS_THREADS) ms_temporal_bwd_weight_kernel(dsg_
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_d = tmem_base_s;
 
+    // conv branches in order
+    int cj[8], ncj = 0;
+    for (int j = 0; j < a.n_branches; ++j)
+        if (a.br[j].kind == 0) cj[ncj++] = j;
+
     uint32_t phase = 0;
     int pending = 0;
-    for (int j = 0; j < a.n_branches; ++j) {
-        if (a.br[j].kind != 0) continue;
-        const MsBranchGeom& g = gp.g[j];
-        if (tid < 128) s_db[tid] = 0.f;
+    for (int grp = 0; grp < pl.ngroups; ++grp) {
+        const int b0 = pl.gstart[grp], b1 = pl.gstart[grp + 1];
+        for (int i = tid; i < 8 * 128; i += MS_THREADS) (&s_db[0][0])[i] = 0.f;
+        // this thread's (branch, frame, chunk) item of the joint-mean / bias pass: fixed for the whole group
+        int my_j = -1, my_qi = 0, my_kc = 0;
+        {
+            int base = 0;
+            for (int bi = b0; bi < b1; ++bi) {
+                const int j = cj[bi], cnt = MS_TO * gp.g[j].nchw;
+                if (my_j < 0 && tid >= base && tid < base + cnt) { my_j = j; my_kc = (tid - base) % gp.g[j].nchw; my_qi = (tid - base) / gp.g[j].nchw; }
+                base += cnt;
+            }
+        }
+        float dbacc[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) dbacc[e] = 0.f;
         int first = 1;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             const int n = tile / chunks_t, tp0 = (tile - n * chunks_t) * MS_TO;
             if (pending) { mbar_wait(&mbar, phase ^ 1); pending = 0; }
-            ms_stage_H(a, g, n, tp0 + g.qmin, s, Vp, Ht, cfa, cfb);
-            ms_stage_dO(a, g, n, tp0, MS_TO, V, Dt, dc1, dcb, dc2);
+            for (int bi = b0; bi < b1; ++bi) {
+                const int j = cj[bi];
+                const MsBranchGeom& g = gp.g[j];
+                ms_stage_H(a, g, n, tp0 + g.qmin, s, Vp, smem + pl.hoff[j], cfa, cfb);
+                ms_stage_dO(a, g, n, tp0, MS_TO, V, smem + pl.doff[j], dc1, dcb, dc2);
+            }
             __syncthreads();
-            for (int it = tid; it < MS_TO * g.nchw; it += MS_THREADS) {           // joint-mean row of dO; bias gradient
-                const int kc = it % g.nchw, qi = it / g.nchw;
+            if (my_j >= 0) {                                                  // joint-mean row of dO; bias gradient
+                const MsBranchGeom& g = gp.g[my_j];
+                unsigned char* Dt = smem + pl.doff[my_j];
                 float sacc[8], tot[8];
 #pragma unroll
                 for (int e = 0; e < 8; ++e) sacc[e] = tot[e] = 0.f;
                 for (int v = 0; v < V; ++v) {
                     float d[8];
-                    unpack8(*reinterpret_cast<const uint4*>(Dt + op_off(qi * 32 + v, kc, g.nch)), d);
-                    const float wv = a.has_ext ? a.add_coeff[v] : 0.f;
+                    unpack8(*reinterpret_cast<const uint4*>(Dt + op_off(my_qi * 32 + v, my_kc, g.nch)), d);
+                    const float wv = addc_s[v];
 #pragma unroll
                     for (int e = 0; e < 8; ++e) { sacc[e] = fmaf(d[e], wv, sacc[e]); tot[e] += d[e]; }
                 }
-                if (a.has_ext) *reinterpret_cast<uint4*>(Dt + op_off(qi * 32 + V, kc, g.nch)) = pack8(sacc);
+                if (a.has_ext) *reinterpret_cast<uint4*>(Dt + op_off(my_qi * 32 + V, my_kc, g.nch)) = pack8(sacc);
 #pragma unroll
-                for (int e = 0; e < 8; ++e) atomicAdd(&s_db[kc * 8 + e], tot[e] + (a.has_ext ? sacc[e] : 0.f));
+                for (int e = 0; e < 8; ++e) dbacc[e] += tot[e] + (a.has_ext ? sacc[e] : 0.f);
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncthreads();
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             if (tid == 0) {
-                const uint32_t idesc = make_idesc_mn(128, g.Kp);
-                const uint32_t lbo = (uint32_t)g.nch * 128u;                       // between 8-row groups
-                const uint32_t h0 = smem_u32(Ht), d0 = smem_u32(Dt);
-                for (int dt = 0; dt < 3; ++dt) {
-                    const int o = (dt - 1) * g.d;
-                    const int p = posmod(o, s);
-                    const int qoff = (o - p) / s - g.qmin;
-                    const uint32_t hbase = h0 + (uint32_t)((p * g.Fq + qoff) * 4) * lbo;
-                    for (int ks = 0; ks < 8; ++ks)                                  // 128 rows = 8 x K16
-                        umma_f16(tmem_d + (uint32_t)(dt * g.Kp), make_desc(d0 + ks * 2u * lbo, lbo, 128u), make_desc(hbase + ks * 2u * lbo, lbo, 128u),
-                                 idesc, (first && ks == 0) ? 0u : 1u);
+                for (int bi = b0; bi < b1; ++bi) {
+                    const int j = cj[bi];
+                    const MsBranchGeom& g = gp.g[j];
+                    const uint32_t idesc = make_idesc_mn(128, g.Kp);
+                    const uint32_t lbo = (uint32_t)g.nch * 128u;                   // between 8-row groups
+                    const uint32_t h0 = smem_u32(smem + pl.hoff[j]), d0 = smem_u32(smem + pl.doff[j]);
+                    for (int dt = 0; dt < 3; ++dt) {
+                        const int o = (dt - 1) * g.d;
+                        const int p = posmod(o, s);
+                        const int qoff = (o - p) / s - g.qmin;
+                        const uint32_t hbase = h0 + (uint32_t)((p * g.Fq + qoff) * 4) * lbo;
+                        for (int ks = 0; ks < 8; ++ks)                              // 128 rows = 8 x K16
+                            umma_f16(tmem_d + (uint32_t)(pl.col[j] + dt * g.Kp), make_desc(d0 + ks * 2u * lbo, lbo, 128u),
+                                     make_desc(hbase + ks * 2u * lbo, lbo, 128u), idesc, (first && ks == 0) ? 0u : 1u);
+                    }
                 }
                 umma_commit(&mbar);
             }
@@ -856,27 +889,36 @@ __global__ void __launch_bounds__(MS_THREADS) ms_temporal_bwd_weight_kernel(dsg_
         }
         if (pending) { mbar_wait(&mbar, phase ^ 1); pending = 0; }
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (my_j >= 0) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) atomicAdd(&s_db[my_j][my_kc * 8 + e], dbacc[e]);
+        }
+        __syncthreads();
         if (!first) {
             // D rows = output channel co (lanes), columns = (tap, ci)
             const int lq = warp & 3, half = warp >> 2;
             const int co = lq * 32 + lane;
             int gcount = 0;
-            for (int dt = 0; dt < 3; ++dt)
-                for (int c16 = 0; c16 < g.Kp; c16 += 16, ++gcount) {
-                    if ((gcount & 1) != half) continue;
-                    if (lq * 32 >= g.Kp) continue;                                  // warp-uniform: no live rows in this lane quarter
-                    float v[16];
-                    tmem_ld16(tmem_d + ((uint32_t)(lq * 32) << 16) + (uint32_t)(dt * g.Kp + c16), v);
-                    const int cor = co - g.off;                                   // window row -> output channel of the branch
-                    if (cor >= 0 && cor < g.w) {
+            for (int bi = b0; bi < b1; ++bi) {
+                const int j = cj[bi];
+                const MsBranchGeom& g = gp.g[j];
+                for (int dt = 0; dt < 3; ++dt)
+                    for (int c16 = 0; c16 < g.Kp; c16 += 16, ++gcount) {
+                        if ((gcount & 1) != half) continue;
+                        if (lq * 32 >= g.Kp) continue;                              // warp-uniform: no live rows in this lane quarter
+                        float v[16];
+                        tmem_ld16(tmem_d + ((uint32_t)(lq * 32) << 16) + (uint32_t)(pl.col[j] + dt * g.Kp + c16), v);
+                        const int cor = co - g.off;                               // window row -> output channel of the branch
+                        if (cor >= 0 && cor < g.w) {
 #pragma unroll
-                        for (int e = 0; e < 16; ++e) {
-                            const int ci = c16 + e - g.off;
-                            if (ci >= 0 && ci < g.w) atomicAdd(a.br[j].dW + ((long long)cor * g.w + ci) * 3 + dt, v[e]);
+                            for (int e = 0; e < 16; ++e) {
+                                const int ci = c16 + e - g.off;
+                                if (ci >= 0 && ci < g.w) atomicAdd(a.br[j].dW + ((long long)cor * g.w + ci) * 3 + dt, v[e]);
+                            }
                         }
                     }
-                }
-            if (tid < g.w && a.br[j].db) atomicAdd(a.br[j].db + tid, s_db[tid + g.off]);
+                if (tid < g.w && a.br[j].db) atomicAdd(a.br[j].db + tid, s_db[j][tid + g.off]);
+            }
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncthreads();
@@ -911,24 +953,55 @@ static const char* launch_ms_temporal_bwd_weight(const dsg_ms_temporal_args& a, 
     if (!h.ok || !ms_args_ok(a)) return "ms_temporal_bwd_weight: unsupported shape (use the per-branch path)";
     if (!act8_ok(a.dfeat) || a.dfeat.relu) return "ms_temporal_bwd_weight: dfeat must be 16-byte aligned";
     if (a.n_samples <= 0 || a.T_out <= 0) return nullptr;
-    int d_bytes = 0, cols = 32, kpmax = 0;
+    const MsGeomPack gp = ms_geom_pack(a);
+    int cj[8], ncj = 0;
     for (int j = 0; j < a.n_branches; ++j)
         if (a.br[j].kind == 0) {
-            int lo8, nchw, Kp;
-            ms_window(a.br[j].lo, a.br[j].hi, lo8, nchw, Kp);
-            if (Kp > kpmax) kpmax = Kp;
             if (!a.br[j].dW) return "ms_temporal_bwd_weight: dW missing";
+            cj[ncj++] = j;
         }
-    if (kpmax == 0) return nullptr;
-    // the A operand is read as M = 128 channel rows: reserve 16 channel groups per 8-row group even when Kp < 128
-    d_bytes = MS_TO * 32 * kpmax * 2 + 16 * 128;
-    while (cols < 3 * kpmax) cols <<= 1;
-    if (cols > 512) return "ms_temporal_bwd_weight: TMEM budget exceeded";
-    size_t smem = (size_t)h.h_bytes + d_bytes + 2048;
+    if (ncj == 0) return nullptr;
+    // greedy grouping: a group fits 256 TMEM columns (3 * Kp per branch; two CTAs per SM stay resident and other
+    // tcgen05 kernels can still allocate), ~96 KB of operand tiles and 256 bias items
+    MsBwPlan pl{};
+    const int smem_budget = 96 * 1024;
+    int maxcols = 0, maxbytes = 0, cols = 0, bytes = 0, items = 0;
+    pl.ngroups = 0;
+    pl.gstart[0] = 0;
+    for (int bi = 0; bi < ncj; ++bi) {
+        const int j = cj[bi];
+        const MsBranchGeom& g = gp.g[j];
+        const int hb = (a.stride * g.Fq * 32 * g.Kp * 2 + 127) & ~127;
+        // the A operand is read as M = 128 channel rows: reserve 16 channel groups per 8-row group even when Kp < 128
+        const int db = (MS_TO * 32 * g.Kp * 2 + 16 * 128 + 127) & ~127;
+        const int it = MS_TO * g.nchw;
+        if (3 * g.Kp > 512 || it > MS_THREADS) return "ms_temporal_bwd_weight: TMEM budget exceeded";
+        if (bi > pl.gstart[pl.ngroups] && (cols + 3 * g.Kp > 256 || bytes + hb + db > smem_budget || items + it > MS_THREADS)) {
+            pl.gstart[++pl.ngroups] = bi;
+            cols = bytes = items = 0;
+        }
+        pl.col[j] = cols;
+        pl.hoff[j] = bytes;
+        pl.doff[j] = bytes + hb;
+        cols += 3 * g.Kp;
+        bytes += hb + db;
+        items += it;
+        if (cols > maxcols) maxcols = cols;
+        if (bytes > maxbytes) maxbytes = bytes;
+    }
+    pl.gstart[++pl.ngroups] = ncj;
+    int tcols = 32;
+    while (tcols < maxcols) tcols <<= 1;
+    size_t smem = (size_t)maxbytes + 2048;
+    if (smem > 200 * 1024) return "ms_temporal_bwd_weight: shared memory budget exceeded";
     cudaFuncSetAttribute(ms_temporal_bwd_weight_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     int n_tiles = a.n_samples * ((a.T_out + MS_TO - 1) / MS_TO);
-    int grid = n_tiles < 2 * 148 ? n_tiles : 2 * 148;
-    ms_temporal_bwd_weight_kernel<<<dim3(grid), dim3(MS_THREADS), smem, st>>>(a, ms_geom_pack(a), h.h_bytes, d_bytes, cols);
+    int per_sm = (int)((200 * 1024) / (smem + 16 * 1024));
+    if (per_sm < 1) per_sm = 1;
+    if (per_sm > 2) per_sm = 2;                          // register-limited
+    if (per_sm * tcols > 512) per_sm = 512 / tcols;
+    int grid = n_tiles < per_sm * 148 ? n_tiles : per_sm * 148;
+    ms_temporal_bwd_weight_kernel<<<dim3(grid), dim3(MS_THREADS), smem, st>>>(a, gp, pl, tcols);
     return dsg_launch_error();
 }
 
