@@ -3,6 +3,7 @@
 #include "conv_gemm.cuh"
 #include "conv_gemm_tc.cuh"
 #include "conv_gemm_tc2.cuh"
+#include "conv_gemm_tc3.cuh"
 #include "graph_agg.cuh"
 #include "ms_temporal_tc.cuh"
 #include "topology.cuh"
@@ -22,6 +23,11 @@ static int fail(const char* where, const char* msg) {
 static bool dtype_ok(int d) { return d == DSG_F32 || d == DSG_BF16; }
 
 // DSG_DISABLE_TC=1 routes bf16 GEMMs to the CUDA-core engine (debugging aid; both engines are sm_100a device code)
+static bool tc3_enabled() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("DSG_DISABLE_TC3"); v = (e && e[0] == '1') ? 0 : 1; }
+    return v == 1;
+}
 static bool tc2_enabled() {
     static int v = -1;
     if (v < 0) { const char* e = getenv("DSG_DISABLE_TC2"); v = (e && e[0] == '1') ? 0 : 1; }
@@ -52,7 +58,10 @@ int dsg_conv_gemm(const dsg_conv_gemm_args* a, void* stream) {
 #ifndef DSG_EMU
     if (a->dtype == DSG_BF16 && tc_enabled()) {      // tcgen05 engine (sm_100a); shapes it does not take fall through
         bool handled = false;
-        const char* e = tc2_enabled() ? dsg::tc::launch_conv_gemm_tc2(*a, (dsg_stream_t)stream, &handled) : nullptr;   // row-per-thread engine
+        const char* e = tc3_enabled() ? dsg::tc::launch_conv_gemm_tc3(*a, (dsg_stream_t)stream, &handled) : nullptr;   // persistent pipelined engine
+        if (e) return fail("dsg_conv_gemm", e);
+        if (handled) return 0;
+        e = tc2_enabled() ? dsg::tc::launch_conv_gemm_tc2(*a, (dsg_stream_t)stream, &handled) : nullptr;               // row-per-thread engine
         if (e) return fail("dsg_conv_gemm", e);
         if (handled) return 0;
         e = dsg::tc::launch_conv_gemm_tc(*a, (dsg_stream_t)stream, &handled);
