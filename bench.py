@@ -371,7 +371,22 @@ def main():
         pass
     peak = peaks.get("hbm_gbs", 6650.0)
     achieved = agg[top][1] / (agg[top][0] * 1e-3) / 1e9
-    roofline = dict(bound="hbm", kernel=top, achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak, traffic=None,
+    # DRAM traffic of the dominant entry point, from the committed ncu launch list of this exact workload (bytes per launch,
+    # to set against the algorithmic bytes per launch); null for any other workload
+    traffic, traffic_src, own_kernels = None, None, None
+    if train and B == 128 and dtype == torch.bfloat16:
+        try:
+            ll = json.load(open(os.path.join(ROOT, "profiles", "r01_launch_list_train_b128.json")))
+            stem = top.replace("dsg_", "")
+            ks = [k for k in ll["kernels"] if stem in k["kernel"] and "wpack" not in k["kernel"] and ("wgrad" in stem) == ("wgrad" in k["kernel"])]
+            if ks:
+                traffic = sum(k["dram_read_mb"] + k["dram_write_mb"] for k in ks) * 1e6 / sum(k["launches"] for k in ks)
+                traffic_src = "profiles/r01_launch_list_train_b128.json (ncu dram__bytes_read.sum + dram__bytes_write.sum, mean per launch)"
+            own_kernels = sum(k["launches"] for k in ll["kernels"] if not k["kernel"].startswith("void at::"))
+        except Exception:
+            pass
+    roofline = dict(bound="hbm", kernel=top, achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak, traffic=traffic,
+                    traffic_unit="bytes per launch", algorithmic_bytes_per_launch=agg[top][1] / agg[top][2], traffic_source=traffic_src,
                     peak_source="MEASURED_PEAKS.json (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
                     share_of_step=agg[top][0] / total_ms, launches_per_step=agg[top][2] // 2,
                     per_kernel_ms_per_step={k: round(v[0] / 2, 4) for k, v in sorted(agg.items(), key=lambda kv: -kv[1][0])},
@@ -387,7 +402,7 @@ def main():
                 config=dict(workload=workload, clips_per_gpu=B, M=M_, T=T_, V=V_, C=C_, parallelism=f"dp{world}", cuda_graph=graph is not None,
                             cache="inputs + activations per step (~GBs) exceed the 126 MB L2; two input batches alternate"),
                 e2e=dict(value=world * B / (e2e_ms * 1e-3), unit=unit, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, ms_per_step=e2e_ms),
-                gpu_launches=launches_per_step * args.steps, abi_calls_per_step=launches_per_step, clocks=clocks, roofline=roofline, cpu_baseline=cpu)
+                gpu_launches=launches_per_step * args.steps, abi_calls_per_step=launches_per_step, kernels_per_step_ncu=own_kernels, clocks=clocks, roofline=roofline, cpu_baseline=cpu)
     print(json.dumps(line))
 
 
