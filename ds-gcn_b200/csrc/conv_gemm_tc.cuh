@@ -814,7 +814,7 @@ static const char* launch_conv_wgrad_tc(const dsg_conv_wgrad_args& a, dsg_stream
     int Ktp = a.K < WT_BK ? (a.K + 15) & ~15 : WT_BK;
     size_t smem = 2 * WT_ROWS * sizeof(long long) + (size_t)(WT_BN + Ktp) * WT_ROWS * 2;
     int occ = (int)((200 * 1024) / (smem + 4096));                // CTAs one SM holds (TMEM: <=128 columns each)
-    if (occ > 4) occ = 4;
+    if (occ > 3) occ = 3;                                         // 80 registers x 256 threads: three CTAs per SM
     if (occ < 1) occ = 1;
     long long want = ((long long)occ * 148 + per - 1) / per;      // one wave of resident CTAs
     long long fpc = (n_frames + want - 1) / want;
