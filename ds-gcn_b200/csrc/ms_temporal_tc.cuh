@@ -517,20 +517,19 @@ __global__ void __launch_bounds__(MS_THREADS, 3) ms_temporal_bwd_data_kernel(dsg
     const int n = blockIdx.y, p_in = blockIdx.z, q0 = blockIdx.x * MS_TO;
     unsigned char* Dt = smem;                                 // staged dO tile
     unsigned char* Wt = smem + h_bytes;
-    bf16* E_s = reinterpret_cast<bf16*>(smem + h_bytes + w_bytes);          // [MS_TO*Vp][C]
+    const int CS = C + 8;                                     // E_s row pitch: 16-byte aligned rows, bank-staggered
+    bf16* E_s = reinterpret_cast<bf16*>(smem + h_bytes + w_bytes);          // [MS_TO*Vp][CS]
     const int mpw = mp_hi - mp_lo;                            // channels of the max/pass ranges (contiguous span)
-    float* dg_s = reinterpret_cast<float*>(smem + h_bytes + w_bytes + MS_TO * Vp * C * 2);   // [6][mpw]
+    float* dg_s = reinterpret_cast<float*>(smem + h_bytes + w_bytes + MS_TO * Vp * CS * 2);   // [6][mpw]
     const bf16* Bx = reinterpret_cast<const bf16*>(a.b.x1);
     __shared__ float cfa[MS_CMAX], cfb[MS_CMAX], dc1[MS_CMAX], dcb[MS_CMAX], dc2[MS_CMAX];
     __shared__ unsigned char kind_s[MS_CMAX];                // branch kind per channel (0 conv, 1 max, 2 pass, 3 none)
+    __shared__ MsBwdTaps taps_s[8];                          // per conv branch: the taps that reach this plane (once per CTA)
     ms_stage_b(a, cfa, cfb);
     ms_stage_d(a, dc1, dcb, dc2);
-    for (int c = tid; c < C; c += MS_THREADS) {
-        int k = 3;
-        for (int j = 0; j < a.n_branches; ++j)
-            if (c >= a.br[j].lo && c < a.br[j].hi) k = a.br[j].kind;
-        kind_s[c] = (unsigned char)k;
-    }
+    for (int j = 0; j < a.n_branches; ++j)
+        for (int c = a.br[j].lo + tid; c < a.br[j].hi; c += MS_THREADS) kind_s[c] = (unsigned char)a.br[j].kind;
+    if (tid < a.n_branches && a.br[tid].kind == 0) taps_s[tid] = ms_bwd_taps(gp.g[tid].d, s, p_in);
 
     if (tid == 0) {
         mbar_init(&mbar, 1);
@@ -538,7 +537,7 @@ __global__ void __launch_bounds__(MS_THREADS, 3) ms_temporal_bwd_data_kernel(dsg
     }
     if (warp == 0) tmem_alloc(&tmem_base_s, (uint32_t)tmem_cols);
     if (tid < 32) s_dadd[tid] = 0.f;
-    for (int i = tid * 8; i < MS_TO * Vp * C; i += MS_THREADS * 8) *reinterpret_cast<uint4*>(E_s + i) = make_uint4(0u, 0u, 0u, 0u);
+    for (int i = tid * 8; i < MS_TO * Vp * CS; i += MS_THREADS * 8) *reinterpret_cast<uint4*>(E_s + i) = make_uint4(0u, 0u, 0u, 0u);
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -549,7 +548,7 @@ __global__ void __launch_bounds__(MS_THREADS, 3) ms_temporal_bwd_data_kernel(dsg
     for (int j = 0; j < a.n_branches; ++j) {
         if (a.br[j].kind != 0) continue;
         const MsBranchGeom& g = gp.g[j];
-        const MsBwdTaps tp = ms_bwd_taps(g.d, s, p_in);
+        const MsBwdTaps& tp = taps_s[j];
         if (tp.n == 0) continue;
         if (issued) mbar_wait(&mbar, phase ^ 1);
         // ---- stage dO over the channel window (joint rows; padding rows and the joint-mean row start as zeros)
@@ -652,8 +651,12 @@ __global__ void __launch_bounds__(MS_THREADS, 3) ms_temporal_bwd_data_kernel(dsg
 #pragma unroll
             for (int dt = -1; dt <= 1; ++dt) {                           // windows t' with s*t' + dt == t
                 const int num = t - dt;
-                if (num < 0 || num % s != 0) continue;
-                const int tpo = num / s;
+                if (num < 0) continue;
+                int tpo = num;
+                if (s != 1) {                                            // stride 1 (eight layers of ten) divides nothing
+                    if (num % s != 0) continue;
+                    tpo = num / s;
+                }
                 if (tpo >= a.T_out) continue;
                 float d[8];
                 if (vv < V) ms_dfeat8(a, ((long long)n * a.T_out + tpo) * V + vv, c8, dc1, dcb, dc2, d);
@@ -678,7 +681,7 @@ __global__ void __launch_bounds__(MS_THREADS, 3) ms_temporal_bwd_data_kernel(dsg
             }
 #pragma unroll
             for (int e = 0; e < 8; ++e)
-                if (kind[e] == 1 || kind[e] == 2) E_s[(i * Vp + vv) * C + c8 + e] = __float2bfloat16(eout[e]);
+                if (kind[e] == 1 || kind[e] == 2) E_s[(i * Vp + vv) * CS + c8 + e] = __float2bfloat16(eout[e]);
         }
     }
     // ---- dadd_coeff for the output frames this CTA owns (plane 0: t' = q0 + i): thread = (8-channel chunk, joint)
@@ -715,7 +718,7 @@ __global__ void __launch_bounds__(MS_THREADS, 3) ms_temporal_bwd_data_kernel(dsg
 #pragma unroll
                     for (int e = 0; e < 16; ++e) {
                         const int k = c16 + e - g.off;
-                        if (k >= 0 && k < g.w) E_s[(i * Vp + lane) * C + a.br[j].lo + k] = __float2bfloat16(v[e]);
+                        if (k >= 0 && k < g.w) E_s[(i * Vp + lane) * CS + a.br[j].lo + k] = __float2bfloat16(v[e]);
                     }
                 }
             }
@@ -745,7 +748,7 @@ __global__ void __launch_bounds__(MS_THREADS, 3) ms_temporal_bwd_data_kernel(dsg
             if (t >= a.T_in) break;
             const long long grow = ((long long)n * a.T_in + t) * Vp + vv;
             float x[8], braw[8];
-            unpack8(*reinterpret_cast<const uint4*>(E_s + r * C + c0), x);
+            unpack8(*reinterpret_cast<const uint4*>(E_s + r * CS + c0), x);
             unpack8(*reinterpret_cast<const uint4*>(Bx + grow * a.b.ld1 + c0), braw);
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
@@ -938,7 +941,7 @@ static const char* launch_ms_temporal_bwd_data(const dsg_ms_temporal_args& a, ds
     for (int j = 0; j < a.n_branches; ++j)
         if (a.br[j].kind != 0) { if (a.br[j].lo < mp_lo) mp_lo = a.br[j].lo; if (a.br[j].hi > mp_hi) mp_hi = a.br[j].hi; }
     if (mp_hi <= mp_lo) { mp_lo = 0; mp_hi = 0; }
-    size_t smem = (size_t)h.h_bytes + h.w_bytes + h.feat_bytes + (size_t)6 * (mp_hi - mp_lo) * 4 + 16;
+    size_t smem = (size_t)h.h_bytes + h.w_bytes + (size_t)MS_TO * Vp * (a.C + 8) * 2 + (size_t)6 * (mp_hi - mp_lo) * 4 + 16;
     if (smem > 200 * 1024) return "ms_temporal_bwd_data: shared memory budget exceeded";
     if (const char* e = ms_launch_wpack(a, st)) return e;
     cudaFuncSetAttribute(ms_temporal_bwd_data_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
