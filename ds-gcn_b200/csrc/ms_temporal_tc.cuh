@@ -137,14 +137,20 @@ DSG_D void ms_stage_d(const dsg_ms_temporal_args& a, float* d1, float* db, float
 }
 // 8 channels of dfeat at row r with staged coefficients
 DSG_D void ms_dfeat8(const dsg_ms_temporal_args& a, long long r, int c8, const float* d1, const float* db, const float* d2, float* v) {
-    float x[8];
-    unpack8(*reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(a.dfeat.x1) + r * a.dfeat.ld1 + c8), x);
+    float x[8], k1[8], kb[8], k2[8];
+    const uint4 r1 = *reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(a.dfeat.x1) + r * a.dfeat.ld1 + c8);
+    uint4 r2 = make_uint4(0u, 0u, 0u, 0u);
+    if (a.dfeat.x2) r2 = *reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(a.dfeat.x2) + r * a.dfeat.ld2 + c8);
+    load8f(d1 + c8, k1, 1.f);                                  // 16-byte shared loads (c8 % 8 == 0, arrays 16-byte aligned)
+    load8f(db + c8, kb, 0.f);
+    unpack8(r1, x);
 #pragma unroll
-    for (int e = 0; e < 8; ++e) v[e] = fmaf(x[e], d1[c8 + e], db[c8 + e]);
+    for (int e = 0; e < 8; ++e) v[e] = fmaf(x[e], k1[e], kb[e]);
     if (a.dfeat.x2) {
-        unpack8(*reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(a.dfeat.x2) + r * a.dfeat.ld2 + c8), x);
+        load8f(d2 + c8, k2, 1.f);
+        unpack8(r2, x);
 #pragma unroll
-        for (int e = 0; e < 8; ++e) v[e] = fmaf(x[e], d2[c8 + e], v[e]);
+        for (int e = 0; e < 8; ++e) v[e] = fmaf(x[e], k2[e], v[e]);
     }
 }
 
@@ -182,10 +188,12 @@ DSG_D void ms_stage_H(const dsg_ms_temporal_args& a, const MsBranchGeom& g, int 
             if (off[b] < 0) continue;
             uint4 pk = make_uint4(0u, 0u, 0u, 0u);
             if (c8s[b] >= 0) {
-                float x[8];
+                float x[8], ka[8], kb[8];
                 unpack8(raw[b], x);
+                load8f(cfa + c8s[b], ka, 1.f);
+                load8f(cfb + c8s[b], kb, 0.f);
 #pragma unroll
-                for (int e = 0; e < 8; ++e) x[e] = fmaxf(fmaf(x[e], cfa[c8s[b] + e], cfb[c8s[b] + e]), 0.f);
+                for (int e = 0; e < 8; ++e) x[e] = fmaxf(fmaf(x[e], ka[e], kb[e]), 0.f);
                 pk = pack8(x);
             }
             *reinterpret_cast<uint4*>(Ht + off[b]) = pk;
@@ -224,14 +232,18 @@ DSG_D void ms_stage_dO(const dsg_ms_temporal_args& a, const MsBranchGeom& g, int
             if (off[b] < 0) continue;
             uint4 pk = make_uint4(0u, 0u, 0u, 0u);
             if (c8s[b] >= 0) {
-                float x[8], v[8];
+                float x[8], v[8], k1[8], kb[8];
                 unpack8(r1[b], x);
+                load8f(d1 + c8s[b], k1, 1.f);
+                load8f(db + c8s[b], kb, 0.f);
 #pragma unroll
-                for (int e = 0; e < 8; ++e) v[e] = fmaf(x[e], d1[c8s[b] + e], db[c8s[b] + e]);
+                for (int e = 0; e < 8; ++e) v[e] = fmaf(x[e], k1[e], kb[e]);
                 if (X2) {
+                    float k2[8];
                     unpack8(r2[b], x);
+                    load8f(d2 + c8s[b], k2, 1.f);
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) v[e] = fmaf(x[e], d2[c8s[b] + e], v[e]);
+                    for (int e = 0; e < 8; ++e) v[e] = fmaf(x[e], k2[e], v[e]);
                 }
                 pk = pack8(v);
             }
@@ -251,7 +263,7 @@ __global__ void __launch_bounds__(MS_THREADS, 4) ms_temporal_fwd_kernel(dsg_ms_t
     unsigned char* Wt = smem + h_bytes;                      // 3 taps x [Kp x Kp]
     bf16* feat_s = reinterpret_cast<bf16*>(smem + h_bytes + w_bytes);      // [MS_TO*V][C]
     const bf16* Bx = reinterpret_cast<const bf16*>(a.b.x1);
-    __shared__ float cfa[MS_CMAX], cfb[MS_CMAX], bias_s[MS_CMAX], addc_s[32];
+    __shared__ __align__(16) float cfa[MS_CMAX], cfb[MS_CMAX], bias_s[MS_CMAX], addc_s[32];
     const int CS = C + 8;                                    // feat_s row pitch: 16-byte aligned rows, bank-staggered
     ms_stage_b(a, cfa, cfb);
     for (int j = 0; j < a.n_branches; ++j)
@@ -522,7 +534,7 @@ __global__ void __launch_bounds__(MS_THREADS, 3) ms_temporal_bwd_data_kernel(dsg
     const int mpw = mp_hi - mp_lo;                            // channels of the max/pass ranges (contiguous span)
     float* dg_s = reinterpret_cast<float*>(smem + h_bytes + w_bytes + MS_TO * Vp * CS * 2);   // [6][mpw]
     const bf16* Bx = reinterpret_cast<const bf16*>(a.b.x1);
-    __shared__ float cfa[MS_CMAX], cfb[MS_CMAX], dc1[MS_CMAX], dcb[MS_CMAX], dc2[MS_CMAX];
+    __shared__ __align__(16) float cfa[MS_CMAX], cfb[MS_CMAX], dc1[MS_CMAX], dcb[MS_CMAX], dc2[MS_CMAX];
     __shared__ unsigned char kind_s[MS_CMAX];                // branch kind per channel (0 conv, 1 max, 2 pass, 3 none)
     __shared__ MsBwdTaps taps_s[8];                          // per conv branch: the taps that reach this plane (once per CTA)
     ms_stage_b(a, cfa, cfb);
@@ -687,19 +699,28 @@ __global__ void __launch_bounds__(MS_THREADS, 3) ms_temporal_bwd_data_kernel(dsg
     // ---- dadd_coeff for the output frames this CTA owns (plane 0: t' = q0 + i): thread = (8-channel chunk, joint)
     if (a.has_ext && p_in == 0) {
         const int nchunks = C >> 3;
-        for (int it = tid; it < nchunks * V; it += MS_THREADS) {
-            const int cc = it % nchunks, v = it / nchunks;
+        const bool pow2 = (nchunks & (nchunks - 1)) == 0 && nchunks <= 32;      // a joint's chunks = one aligned lane group
+        const int total = nchunks * V;
+        for (int it0 = 0; it0 < total; it0 += MS_THREADS) {                     // every lane iterates: warp shuffles below
+            const int it = it0 + tid;
+            const bool valid = it < total;
+            const int cc = valid ? it % nchunks : 0, v = valid ? it / nchunks : 0;
             float part = 0.f;
-            for (int i = 0; i < MS_TO; ++i) {
-                const int tpo = q0 + i;
-                if (tpo >= a.T_out) break;
-                float d[8], og[8];
-                ms_dfeat8(a, ((long long)n * a.T_out + tpo) * V + v, cc * 8, dc1, dcb, dc2, d);
-                load8f(a.oglob + ((long long)n * a.T_out + tpo) * C + cc * 8, og, 0.f);
+            if (valid) {
+                for (int i = 0; i < MS_TO; ++i) {
+                    const int tpo = q0 + i;
+                    if (tpo >= a.T_out) break;
+                    float d[8], og[8];
+                    ms_dfeat8(a, ((long long)n * a.T_out + tpo) * V + v, cc * 8, dc1, dcb, dc2, d);
+                    load8f(a.oglob + ((long long)n * a.T_out + tpo) * C + cc * 8, og, 0.f);
 #pragma unroll
-                for (int e = 0; e < 8; ++e) part = fmaf(d[e], og[e], part);
+                    for (int e = 0; e < 8; ++e) part = fmaf(d[e], og[e], part);
+                }
             }
-            atomicAdd(&s_dadd[v], part);
+            if (pow2) {
+                for (int o = nchunks >> 1; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+                if (valid && cc == 0) s_dadd[v] += part;                        // one writer per joint
+            } else if (valid) atomicAdd(&s_dadd[v], part);
         }
     }
     if (issued) {
@@ -795,7 +816,7 @@ __global__ void __launch_bounds__(MS_THREADS) ms_temporal_bwd_weight_kernel(dsg_
     __shared__ float s_db[8][128];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int V = a.V, Vp = a.V + a.has_ext, s = a.stride;
-    __shared__ float cfa[MS_CMAX], cfb[MS_CMAX], dc1[MS_CMAX], dcb[MS_CMAX], dc2[MS_CMAX], addc_s[32];
+    __shared__ __align__(16) float cfa[MS_CMAX], cfb[MS_CMAX], dc1[MS_CMAX], dcb[MS_CMAX], dc2[MS_CMAX], addc_s[32];
     ms_stage_b(a, cfa, cfb);
     ms_stage_d(a, dc1, dcb, dc2);
     if (tid < 32) addc_s[tid] = (a.has_ext && tid < V) ? a.add_coeff[tid] : 0.f;
