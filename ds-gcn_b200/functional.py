@@ -11,6 +11,8 @@ Reference semantics: pyskl/models/gcns/utils/gcn.py:2217-2365 (dgphgcn1), :75-94
 pyskl/models/gcns/utils/tcn.py:31-32 (unit_tcn), :162-177 (mstcn), :407-428 (dgmstcn),
 pyskl/models/gcns/dgstgcn.py:61-65 (DGBlock).
 """
+import math
+
 import torch
 
 from . import ops
@@ -218,6 +220,18 @@ def dgphgcn1_forward(m, x, n, T, V, save):
     return out
 
 
+def _zeros_f32(dev, *shapes):
+    """Several zero-initialised fp32 gradient accumulators carved from ONE buffer (one fill launch instead of one per
+    tensor); every view starts on a 256-byte boundary, as the vectorised reductions of the kernels want."""
+    sizes = [int(math.prod(sh)) for sh in shapes]
+    offs, tot = [], 0
+    for nel in sizes:
+        offs.append(tot)
+        tot += (nel + 63) // 64 * 64
+    flat = torch.zeros(tot, dtype=torch.float32, device=dev)
+    return [flat[o:o + nel].view(sh) for o, nel, sh in zip(offs, sizes, shapes)]
+
+
 def dgphgcn1_backward(m, sv, dout, grads, extra_add=None):
     """dout: gradient w.r.t. the unit output [rows, C_out].  Fills `grads` {param: grad}; returns dx.
     `extra_add` (optional, [rows, C_in]) is added to dx inside the last kernel's epilogue."""
@@ -244,11 +258,15 @@ def dgphgcn1_backward(m, sv, dout, grads, extra_add=None):
     b_z.run()
     dZ = b_z.dy(E4, Z)
 
+    # every parameter-gradient accumulator of the unit: one buffer, one fill
+    dWpost, dbpost, dA, dal, dbe, dWe, dbe_l, dWt, dbt, dWpd, dbpd = _zeros_f32(
+        dev, m.post.weight.shape, m.post.bias.shape, m.A.shape, m.alpha.shape, m.beta.shape, m.edge_linears.weight.shape,
+        m.edge_linears.bias.shape, (9 * R, Cin), (9 * R,), (Npd, Cin), (Npd,))
+
     # ---- post conv backward
     dY = torch.empty(rows, KC, dtype=dt, device=dev)
     Wpost = m.post.weight.view(Cout, KC)
     ops.conv_gemm(dZ, Wpost, KC, dY, n_samples=n, T_in=T, T_out=T, Vin=V, ws=(1, KC, 0))
-    dWpost, dbpost = torch.zeros_like(m.post.weight), torch.zeros_like(m.post.bias)
     ops.conv_wgrad(Y, dZ, dWpost, db=dbpost, n_samples=n, T_in=T, T_out=T, Vin=V)
     grads[m.post.weight], grads[m.post.bias] = dWpost, dbpost
 
@@ -266,14 +284,10 @@ def dgphgcn1_backward(m, sv, dout, grads, extra_add=None):
     # ---- topology backward
     H, S, Wt, xm2 = sv["H"], sv["S"], sv["Wt"], sv["xm2"]
     dH = torch.empty_like(H)
-    dA, dal, dbe = torch.zeros_like(m.A), torch.zeros_like(m.alpha), torch.zeros_like(m.beta)
-    dWe, dbe_l = torch.zeros_like(m.edge_linears.weight), torch.zeros_like(m.edge_linears.bias)
     ops.topology_bwd(H, n, V, R, nt, et, m.A, m.alpha, m.beta, m.edge_linears.weight.view(15 * R, R), m.edge_linears.bias, S,
                      dadyn, dH, dA, dal, dbe, dWe, dbe_l)
     grads[m.A], grads[m.alpha], grads[m.beta] = dA, dal, dbe
     grads[m.edge_linears.weight], grads[m.edge_linears.bias] = dWe, dbe_l
-    dWt = torch.zeros(9 * R, Cin, dtype=torch.float32, device=dev)
-    dbt = torch.zeros(9 * R, dtype=torch.float32, device=dev)
     ops.conv_wgrad(xm2, dH, dWt, db=dbt, n_samples=n, T_in=1, T_out=1, Vin=V)
     for conv, lo, hi in ((m.conv1, 0, 2 * R), (m.conv2, 2 * R, 4 * R), (m.conv1_se, 4 * R, 9 * R)):
         grads[conv.weight], grads[conv.bias] = dWt[lo:hi].view_as(conv.weight), dbt[lo:hi]
@@ -283,8 +297,6 @@ def dgphgcn1_backward(m, sv, dout, grads, extra_add=None):
     # ---- dx = [dP_raw | dD_raw] @ [Wpre; Wdown] (+ e4 when the residual is the identity) + dxm/T (+ extra)
     Wpd = sv["Wpd"]
     dx = torch.empty(rows, Cin, dtype=dt, device=dev)
-    dWpd = torch.zeros(Npd, Cin, dtype=torch.float32, device=dev)
-    dbpd = torch.zeros(Npd, dtype=torch.float32, device=dev)
     if has_down:
         dPD = b_pd.dy(E, PD)
         ops.conv_gemm(dPD, Wpd, Cin, dx, n_samples=n, T_in=T, T_out=T, Vin=V, ws=(1, Cin, 0), add=extra_add, bcast=dxm,
@@ -454,7 +466,7 @@ def mstcn_backward(m, sv, dout, grads):
     E2 = torch.empty(rows_f, Ct, dtype=dt, device=dev)
     ops.conv_gemm(dU, tr.weight.view(Cout, Ct), Ct, E2, n_samples=n, T_in=T_out, T_out=T_out, Vin=V, ws=(1, Ct, 0),
                   mask=Act(feat, c_t.a, c_t.b), stat_sum=b_t.ssum, stat_sq=b_t.ssq, partner=feat)
-    dWtr, dbtr = torch.zeros_like(tr.weight), torch.zeros_like(tr.bias)
+    dWtr, dbtr, dWbr, dbbr = _zeros_f32(dev, tr.weight.shape, tr.bias.shape, (Ct, Cin), (Ct,))
     ops.conv_wgrad(Act(feat, c_t.a, c_t.b, relu=True), dU, dWtr, db=dbtr, n_samples=n, T_in=T_out, T_out=T_out, Vin=V)
     grads[tr.weight], grads[tr.bias] = dWtr, dbtr
     b_t.add_bn(m.transform[0], 0, Ct, rows_f, grads)
@@ -502,8 +514,6 @@ def mstcn_backward(m, sv, dout, grads):
     # ---- branch 1x1 convolutions backward (the joint-mean column folds back into the V joints)
     dg = torch.empty(n * T * V, Cin, dtype=dt, device=dev)
     ops.conv_gemm(dB, sv["Wbr"], Cin, dg, n_samples=n, T_in=T, T_out=T, Vin=Vp, ws=(1, Cin, 0), contract_ext=has_ext)
-    dWbr = torch.zeros(Ct, Cin, dtype=torch.float32, device=dev)
-    dbbr = torch.zeros(Ct, dtype=torch.float32, device=dev)
     ops.conv_wgrad(g, dB, dWbr, db=dbbr, n_samples=n, T_in=T, T_out=T, Vin=V, ext_in=has_ext)
     for j, (kind, lo, hi, _) in enumerate(layout):
         conv = m.branches[j] if kind == "1x1" else m.branches[j][0]

@@ -34,7 +34,10 @@ def allreduce_gradients(params, world_size=None):
     if not grads:
         return
     flat = _flatten_dense_tensors(grads)
-    dist.all_reduce(flat)
-    flat.div_(world_size)
-    for g, synced in zip(grads, _unflatten_dense_tensors(flat, grads)):
-        g.copy_(synced)
+    if dist.get_backend() == "nccl":
+        dist.all_reduce(flat, op=dist.ReduceOp.AVG)          # the mean is taken inside the collective
+    else:
+        dist.all_reduce(flat)
+        flat.div_(world_size)
+    # scatter back with multi-tensor copies (a handful of launches instead of one per parameter)
+    torch._foreach_copy_(grads, list(_unflatten_dense_tensors(flat, grads)))
