@@ -93,12 +93,13 @@ template <> DSG_D void agg_load8_s<bf16>(const ActSrc& s, long long row, int c0,
 }
 
 constexpr int AG_TCH = 8;      // frames staged per step
+constexpr int AG_WB = 2;       // joints contracted together by a warp (adjacency columns in registers)
 
 // Dynamic contraction: the per-sample adjacency slice (32 channels) and AG_TCH frames of the operand live in shared
 // memory (fp32, channel fastest: conflict-free); a warp owns joints w, w+8, ... and keeps the adjacency column in
 // registers, so the inner loop is one shared load + FMA per (frame, source joint).
 template <class T, int V>
-__global__ void __launch_bounds__(AG_THREADS) agg_dyn_kernel(dsg_graph_agg_args a, int t_chunk, int vec) {
+__global__ void __launch_bounds__(AG_THREADS, 2) agg_dyn_kernel(dsg_graph_agg_args a, int t_chunk, int vec) {
     DSG_DYN_SMEM(smem_raw);
     float* adj = reinterpret_cast<float*>(smem_raw);      // [V*V][32]
     float* Ps = adj + V * V * 32;                         // [AG_TCH][V][32]
@@ -151,29 +152,47 @@ __global__ void __launch_bounds__(AG_THREADS) agg_dyn_kernel(dsg_graph_agg_args 
             dst[1] = make_float4(v[4], v[5], v[6], v[7]);
         }
         __syncthreads();
-        for (int w = warp; w < V; w += AG_THREADS / 32) {
-            float av[V];
+        // a warp owns AG_WB joints at a time and keeps their adjacency columns in registers: one shared load of
+        // p[tt][u] feeds AG_WB FMAs (the loop is bound by shared-memory bandwidth, one 128-byte wavefront per load)
+        for (int g = warp; g < (V + AG_WB - 1) / AG_WB; g += AG_THREADS / 32) {
+            const int w0 = g * AG_WB;
+            float av[AG_WB][V];
 #pragma unroll
-            for (int u = 0; u < V; ++u) av[u] = adj[(u * V + w) * 32 + lane];
+            for (int bq = 0; bq < AG_WB; ++bq) {
+#pragma unroll
+                for (int u = 0; u < V; ++u) av[bq][u] = (w0 + bq < V) ? adj[(u * V + w0 + bq) * 32 + lane] : 0.f;
+            }
 #pragma unroll 2
             for (int tt = 0; tt < AG_TCH; ++tt) {
                 if (t0 + tt >= tend) break;
-                float acc = 0.f;
+                float accv[AG_WB];
 #pragma unroll
-                for (int u = 0; u < V; ++u) acc = fmaf(Ps[(tt * V + u) * 32 + lane], av[u], acc);
+                for (int bq = 0; bq < AG_WB; ++bq) accv[bq] = 0.f;
+#pragma unroll
+                for (int u = 0; u < V; ++u) {
+                    const float pv = Ps[(tt * V + u) * 32 + lane];
+#pragma unroll
+                    for (int bq = 0; bq < AG_WB; ++bq) accv[bq] = fmaf(pv, av[bq][u], accv[bq]);
+                }
                 if (ch_ok) {
-                    const long long orow = ((long long)n * a.T + t0 + tt) * V + w;
-                    if (a.has_mask) {
-                        float mv = fmaf(ldf<T>(reinterpret_cast<const T*>(a.mask.x1) + orow * a.mask.ld1 + ch), mk_a1, mk_b);
-                        if (a.mask.x2) mv = fmaf(ldf<T>(reinterpret_cast<const T*>(a.mask.x2) + orow * a.mask.ld2 + ch), mk_a2, mv);
-                        if (!(mv > 0.f)) acc = 0.f;
+#pragma unroll
+                    for (int bq = 0; bq < AG_WB; ++bq) {
+                        const int w = w0 + bq;
+                        if (w >= V) continue;
+                        float acc = accv[bq];
+                        const long long orow = ((long long)n * a.T + t0 + tt) * V + w;
+                        if (a.has_mask) {
+                            float mv = fmaf(ldf<T>(reinterpret_cast<const T*>(a.mask.x1) + orow * a.mask.ld1 + ch), mk_a1, mk_b);
+                            if (a.mask.x2) mv = fmaf(ldf<T>(reinterpret_cast<const T*>(a.mask.x2) + orow * a.mask.ld2 + ch), mk_a2, mv);
+                            if (!(mv > 0.f)) acc = 0.f;
+                        }
+                        if (a.stat_sum) {
+                            const float p = a.partner ? ldf<T>(reinterpret_cast<const T*>(a.partner) + orow * a.ld_partner + ch) : acc;
+                            s1 += acc;
+                            s2 += acc * p;
+                        }
+                        stf<T>(reinterpret_cast<T*>(a.out) + orow * a.ld_out + ch, acc);
                     }
-                    if (a.stat_sum) {
-                        const float p = a.partner ? ldf<T>(reinterpret_cast<const T*>(a.partner) + orow * a.ld_partner + ch) : acc;
-                        s1 += acc;
-                        s2 += acc * p;
-                    }
-                    stf<T>(reinterpret_cast<T*>(a.out) + orow * a.ld_out + ch, acc);
                 }
             }
         }
