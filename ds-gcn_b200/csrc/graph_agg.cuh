@@ -125,31 +125,93 @@ __global__ void __launch_bounds__(AG_THREADS, 2) agg_dyn_kernel(dsg_graph_agg_ar
         ActSrc as{};
         as.x1 = adyn; as.ld1 = a.KC;
         const bool avec = vec && ((uintptr_t)a.adyn % 16 == 0) && (a.KC % 8 == 0);
-        for (int idx = tid; idx < V * V * 4; idx += AG_THREADS) {
-            const int q = idx & 3, uw = idx >> 2;
-            float v[8];
-            agg_load8<T>(as, uw, kc0 + q * 8, a.KC, avec, v);
-            int dst = uw;
-            if (a.mode == 1) { int u = uw / V, w = uw - u * V; dst = w * V + u; }
+        for (int idx0 = tid; idx0 < V * V * 4; idx0 += AG_THREADS * 4) {      // 4 independent loads in flight
+            float v[4][8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) adj[dst * 32 + q * 8 + j] = v[j];
+            for (int b = 0; b < 4; ++b) {
+                const int idx = idx0 + b * AG_THREADS;
+                if (idx < V * V * 4) agg_load8<T>(as, idx >> 2, kc0 + (idx & 3) * 8, a.KC, avec, v[b]);
+            }
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                const int idx = idx0 + b * AG_THREADS;
+                if (idx >= V * V * 4) continue;
+                const int q = idx & 3, uw = idx >> 2;
+                int dst = uw;
+                if (a.mode == 1) { int u = uw / V, w = uw - u * V; dst = w * V + u; }
+                float4* d4 = reinterpret_cast<float4*>(adj + dst * 32 + q * 8);
+                d4[0] = make_float4(v[b][0], v[b][1], v[b][2], v[b][3]);
+                d4[1] = make_float4(v[b][4], v[b][5], v[b][6], v[b][7]);
+            }
         }
     }
     float s1 = 0.f, s2 = 0.f;
     for (int t0 = tbeg; t0 < tend; t0 += AG_TCH) {
         __syncthreads();
-        for (int idx = tid; idx < AG_TCH * V * 4; idx += AG_THREADS) {
-            const int q = idx & 3, rv = idx >> 2;          // rv = tt*V + u
-            const int tt = rv / V;
-            float v[8];
-            if (t0 + tt < tend) agg_load8_s<T>(a.src, ((long long)n * a.T + t0) * V + rv, kc0, q, a.KC, vec != 0, cf_src, v);
-            else {
+        if (sizeof(T) == 2 && vec) {
+            // vector path: all of this thread's 16-byte loads of the chunk are issued before the first one is used
+            constexpr int NIT = (AG_TCH * V * 4 + AG_THREADS - 1) / AG_THREADS;
+            const bf16* X1 = reinterpret_cast<const bf16*>(a.src.x1);
+            const bf16* X2 = reinterpret_cast<const bf16*>(a.src.x2);
+            uint4 rx1[NIT], rx2[NIT];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) v[j] = 0.f;
+            for (int i = 0; i < NIT; ++i) {
+                const int idx = tid + i * AG_THREADS;
+                const int q = idx & 3, rv = idx >> 2, tt = rv / V, c = kc0 + q * 8;
+                rx1[i] = rx2[i] = make_uint4(0u, 0u, 0u, 0u);
+                if (idx < AG_TCH * V * 4 && t0 + tt < tend && c + 8 <= a.KC) {
+                    const long long row = ((long long)n * a.T + t0) * V + rv;
+                    rx1[i] = *reinterpret_cast<const uint4*>(X1 + row * a.src.ld1 + c);
+                    if (X2) rx2[i] = *reinterpret_cast<const uint4*>(X2 + row * a.src.ld2 + c);
+                }
             }
-            float4* dst = reinterpret_cast<float4*>(Ps + rv * 32 + q * 8);
-            dst[0] = make_float4(v[0], v[1], v[2], v[3]);
-            dst[1] = make_float4(v[4], v[5], v[6], v[7]);
+#pragma unroll
+            for (int i = 0; i < NIT; ++i) {
+                const int idx = tid + i * AG_THREADS;
+                if (idx >= AG_TCH * V * 4) continue;
+                const int q = idx & 3, rv = idx >> 2, tt = rv / V, c = kc0 + q * 8;
+                float v[8];
+                if (c + 8 <= a.KC) {
+                    float x[8];
+                    unpack8(rx1[i], x);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) v[j] = fmaf(x[j], cf_src[q * 8 + j], cf_src[32 + q * 8 + j]);
+                    if (X2) {
+                        unpack8(rx2[i], x);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) v[j] = fmaf(x[j], cf_src[64 + q * 8 + j], v[j]);
+                    }
+                    if (a.src.relu) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
+                    }
+                    if (t0 + tt >= tend) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) v[j] = 0.f;
+                    }
+                } else if (t0 + tt < tend) agg_load8_s<T>(a.src, ((long long)n * a.T + t0) * V + rv, kc0, q, a.KC, true, cf_src, v);
+                else {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) v[j] = 0.f;
+                }
+                float4* dst = reinterpret_cast<float4*>(Ps + rv * 32 + q * 8);
+                dst[0] = make_float4(v[0], v[1], v[2], v[3]);
+                dst[1] = make_float4(v[4], v[5], v[6], v[7]);
+            }
+        } else {
+            for (int idx = tid; idx < AG_TCH * V * 4; idx += AG_THREADS) {
+                const int q = idx & 3, rv = idx >> 2;          // rv = tt*V + u
+                const int tt = rv / V;
+                float v[8];
+                if (t0 + tt < tend) agg_load8_s<T>(a.src, ((long long)n * a.T + t0) * V + rv, kc0, q, a.KC, vec != 0, cf_src, v);
+                else {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) v[j] = 0.f;
+                }
+                float4* dst = reinterpret_cast<float4*>(Ps + rv * 32 + q * 8);
+                dst[0] = make_float4(v[0], v[1], v[2], v[3]);
+                dst[1] = make_float4(v[4], v[5], v[6], v[7]);
+            }
         }
         __syncthreads();
         // a warp owns AG_WB joints at a time and keeps their adjacency columns in registers: one shared load of
