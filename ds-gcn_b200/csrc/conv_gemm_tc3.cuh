@@ -1,5 +1,8 @@
-// Persistent, warp-specialised tcgen05 engine for the hot 1x1 convolutions (same shapes as conv_gemm_tc2_kernel, packed
-// weights required).  One CTA = 256 threads = two role groups that run two tiles apart:
+// Persistent tcgen05 engine for the hot 1x1 convolutions (same shapes as conv_gemm_tc2_kernel, packed weights required).
+// One CTA = 256 threads = two groups of 128; two shared-memory stages, two TMEM accumulators, weights resident.
+// Default schedule (pp = 1, "ping-pong"): each group produces AND drains its own tiles (tile i -> group i & 1), the two
+// groups running out of phase, so the loads of one tile overlap the MMAs and the tail of the other and no warp idles
+// whichever side is the bottleneck (measured 1 % better over the step than fixed roles; DSG_TC3_PP=0 selects those):
 //
 //   producers (warps 0-3)  row-per-thread: load the thread's own input row of tile i (8 independent 16-byte loads in
 //                          flight), fused prologue, bf16 chunks into stage i&1 of the K-major no-swizzle UMMA tile;
@@ -27,12 +30,12 @@ DSG_D void group_sync(int id) {               // named barrier over one 128-thre
     asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory");
 }
 
-__global__ void __launch_bounds__(T3_THREADS) conv_gemm_tc3_kernel(dsg_conv_gemm_args a, int n_tiles) {
+__global__ void __launch_bounds__(T3_THREADS) conv_gemm_tc3_kernel(dsg_conv_gemm_args a, int n_tiles, int pp) {
     DSG_DYN_SMEM(smem);
     __shared__ uint64_t a_free[2], acc_full[2], acc_free[2], wbar;
     __shared__ uint32_t tmem_base_s;
-    __shared__ float ext_s[2][8][16];                    // joint-mean accumulator rows of up to 8 frames, double-buffered
-    __shared__ float s_acc[2][4][T2_BN];                 // per-warp column sums, accumulated over all tiles of this CTA
+    __shared__ float ext_sg[2][2][8][16];                // per group: joint-mean accumulator rows of up to 8 frames, double-buffered
+    __shared__ float s_acc[2][8][T2_BN];                 // per-warp column sums, accumulated over all tiles of this CTA
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int role = tid >> 7, rtid = tid & 127;         // 0: producer, 1: epilogue; rtid = row of the tile = TMEM lane
     const int rpf = a.Vin + a.ext_in;
@@ -69,7 +72,7 @@ __global__ void __launch_bounds__(T3_THREADS) conv_gemm_tc3_kernel(dsg_conv_gemm
         tl_mb[tid] = ((in && a.has_mask && a.mask.b1) ? a.mask.b1[cch] : 0.f) + ((in && a.has_mask && a.mask.b2) ? a.mask.b2[cch] : 0.f);
         tl_ma2[tid] = (in && a.has_mask && a.mask.a2) ? a.mask.a2[cch] : 1.f;
     }
-    for (int i = tid; i < 2 * 4 * T2_BN; i += T3_THREADS) (&s_acc[0][0][0])[i] = 0.f;
+    for (int i = tid; i < 2 * 8 * T2_BN; i += T3_THREADS) (&s_acc[0][0][0])[i] = 0.f;
 
     if (tid == 0) {
         for (int i = 0; i < 2; ++i) {
@@ -91,8 +94,13 @@ __global__ void __launch_bounds__(T3_THREADS) conv_gemm_tc3_kernel(dsg_conv_gemm
     const int Vout = rpf - a.contract_ext;
     const bool is_ext_row = a.contract_ext && j == rpf - 1;
 
-    if (role == 0) {
-        // ================================ producers ================================
+    // pp == 0: fixed roles (group 0 produces every tile, group 1 drains it).  pp == 1: ping-pong — each group produces
+    // AND drains its own tiles (it = group, group + 2, ...), the two groups running out of phase, so no warp idles when
+    // one side of the pipeline is the bottleneck.  Stage / accumulator index it & 1 and use count it >> 1 hold for both.
+    float (*ext_s)[8][16] = ext_sg[role];
+    const bool do_prod = pp || role == 0, do_epi = pp || role == 1;
+    const int bar_p = pp ? 1 + role : 1, bar_e = pp ? 3 + role : 2;
+    {
         if (tid == 0) {                                   // the CTA's weight tile, all passes: one bulk copy
             const uint32_t bytes = (uint32_t)(Ntp * Kp * 2);
             mbar_expect_tx(&wbar, bytes);
@@ -108,11 +116,23 @@ __global__ void __launch_bounds__(T3_THREADS) conv_gemm_tc3_kernel(dsg_conv_gemm
                 }
             }
         }
-        const uint32_t idesc = make_idesc(128, Ntp);
-        FrameMap fm{1, a.tap_step, a.tap_off, a.t_mul, a.t_div, a.T_in, a.T_out, a.Vin, a.ext_in};
-        int it = 0;
-        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-            const int st = it & 1, use = it >> 1;
+    }
+    const uint32_t idesc = make_idesc(128, Ntp);
+    FrameMap fm{1, a.tap_step, a.tap_off, a.t_mul, a.t_div, a.T_in, a.T_out, a.Vin, a.ext_in};
+    const int ew = warp & 3;
+    const float inv_ext = a.contract_ext ? 1.f / (float)(rpf - 1) : 0.f;
+    bf16* out = reinterpret_cast<bf16*>(a.out);
+    const bf16* addp = reinterpret_cast<const bf16*>(a.add);
+    const bf16* add2p = reinterpret_cast<const bf16*>(a.add2);
+    const bf16* partp = reinterpret_cast<const bf16*>(a.partner);
+    const int it0 = pp ? role : 0, its = pp ? 2 : 1;
+    for (int it = it0; ; it += its) {
+        const long long tile_ll = (long long)blockIdx.x + (long long)it * gridDim.x;
+        if (tile_ll >= n_tiles) break;
+        const int tile = (int)tile_ll;
+        const int st = it & 1, use = it >> 1;
+        if (do_prod) {
+            // ================================ produce ================================
             unsigned char* Abase = Abase0 + st * a_bytes;
             const long long f = (long long)tile * Fr + fl;
             long long sr = -1;                               // source row (-2: joint-mean row)
@@ -128,7 +148,7 @@ __global__ void __launch_bounds__(T3_THREADS) conv_gemm_tc3_kernel(dsg_conv_gemm
                 else t2_stage_a<4, true>(a, sr, rtid, kv0, kv_len >> 3, Ap, cf_a1, cf_b, cf_a2);
             }
             if (a.ext_in) {
-                group_sync(1);
+                group_sync(bar_p);
                 const int nchT = Kp >> 3;
                 for (int idx = rtid; idx < Fr * nchT; idx += 128) {        // joint-mean rows, averaged in fp32
                     const int kcT = idx % nchT, ff = idx / nchT;
@@ -153,9 +173,9 @@ __global__ void __launch_bounds__(T3_THREADS) conv_gemm_tc3_kernel(dsg_conv_gemm
                 }
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            group_sync(1);
-            if (tid == 0) {
-                if (it == 0) mbar_wait(&wbar, 0);
+            group_sync(bar_p);
+            if (rtid == 0) {
+                if (use == 0) mbar_wait(&wbar, 0);
                 if (use > 0) mbar_wait(&acc_free[st], (uint32_t)((use - 1) & 1));   // the epilogue has drained this accumulator
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t acc = tmem_d + (uint32_t)st * acc_cols;
@@ -175,17 +195,8 @@ __global__ void __launch_bounds__(T3_THREADS) conv_gemm_tc3_kernel(dsg_conv_gemm
                 umma_commit(&acc_full[st]);
             }
         }
-    } else {
-        // ================================ epilogue ================================
-        const int ew = warp & 3;
-        const float inv_ext = a.contract_ext ? 1.f / (float)(rpf - 1) : 0.f;
-        bf16* out = reinterpret_cast<bf16*>(a.out);
-        const bf16* addp = reinterpret_cast<const bf16*>(a.add);
-        const bf16* add2p = reinterpret_cast<const bf16*>(a.add2);
-        const bf16* partp = reinterpret_cast<const bf16*>(a.partner);
-        int it = 0;
-        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-            const int st = it & 1, use = it >> 1;
+        if (do_epi) {
+            // ================================ drain ================================
             const long long f = (long long)tile * Fr + fl;
             const bool row_ok = fl < Fr && f < n_frames;
             const long long orow = (row_ok && !is_ext_row) ? f * Vout + j : -1;
@@ -217,7 +228,7 @@ __global__ void __launch_bounds__(T3_THREADS) conv_gemm_tc3_kernel(dsg_conv_gemm
 #pragma unroll
                         for (int e = 0; e < 16; ++e) ext_s[buf][fl][e] = v[e];
                     }
-                    group_sync(2);
+                    group_sync(bar_e);
                     if (orow >= 0) {
 #pragma unroll
                         for (int e = 0; e < 16; ++e) v[e] = fmaf(ext_s[buf][fl][e], inv_ext, v[e]);
@@ -263,8 +274,8 @@ __global__ void __launch_bounds__(T3_THREADS) conv_gemm_tc3_kernel(dsg_conv_gemm
                 if (a.stat_sum) {                                               // warp-uniform: every lane takes part in the shuffles
                     const float t1 = warp_colsum16(s1, lane), t2 = warp_colsum16(s2, lane);
                     if ((lane & 1) == 0) {
-                        s_acc[0][ew][c16 + (lane >> 1)] += t1;
-                        s_acc[1][ew][c16 + (lane >> 1)] += t2;
+                        s_acc[0][warp][c16 + (lane >> 1)] += t1;
+                        s_acc[1][warp][c16 + (lane >> 1)] += t2;
                     }
                 }
             }
@@ -276,8 +287,9 @@ __global__ void __launch_bounds__(T3_THREADS) conv_gemm_tc3_kernel(dsg_conv_gemm
     __syncthreads();
     if (warp == 0) tmem_dealloc(tmem_d, 2 * acc_cols);
     if (a.stat_sum && tid < Nt) {
-        const float t1 = s_acc[0][0][tid] + s_acc[0][1][tid] + s_acc[0][2][tid] + s_acc[0][3][tid];
-        const float t2 = s_acc[1][0][tid] + s_acc[1][1][tid] + s_acc[1][2][tid] + s_acc[1][3][tid];
+        float t1 = 0.f, t2 = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) { t1 += s_acc[0][w][tid]; t2 += s_acc[1][w][tid]; }
         atomicAdd(a.stat_sum + n0 + tid, (double)t1);
         atomicAdd(a.stat_sq + n0 + tid, (double)t2);
     }
@@ -303,7 +315,8 @@ static const char* launch_conv_gemm_tc3(const dsg_conv_gemm_args& a, dsg_stream_
     // (Kp <= 192: the weight tile and two stages leave room for two CTAs per SM or the tail dominates) and the CTA's
     // columns are the whole output (one column tile) or the rows are cheap to re-read (Kp <= 96); wider shapes are
     // load-bound on the producers and run faster on conv_gemm_tc2_kernel (3 CTAs per SM, every thread loads).
-    if (Kp > 192 || (a.N > T2_BN && Kp > 96)) return nullptr;
+    static const int all_shapes = [] { const char* e = getenv("DSG_TC3_ALL"); return (e && e[0] == '1') ? 1 : 0; }();      // experiments
+    if (!all_shapes && (Kp > 192 || (a.N > T2_BN && Kp > 96))) return nullptr;
     const int Fr = 128 / rpf;
     const long long tiles = (n_frames + Fr - 1) / Fr;
     if (tiles > 0x7fffffff) return nullptr;
@@ -317,7 +330,8 @@ static const char* launch_conv_gemm_tc3(const dsg_conv_gemm_args& a, dsg_stream_
     conv_wpack_kernel<<<dim3(ny, (unsigned)((Kp + kpass - 1) / kpass)), dim3(256), 0, st>>>(a.W, a.ws_n, a.ws_k, a.K, a.N, reinterpret_cast<unsigned char*>(a.wpack));
     if (const char* e = dsg_launch_error()) return e;
     cudaFuncSetAttribute(conv_gemm_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    conv_gemm_tc3_kernel<<<dim3((unsigned)gx, ny), dim3(T3_THREADS), smem, st>>>(a, (int)tiles);
+    static const int pp = [] { const char* e = getenv("DSG_TC3_PP"); return (e && e[0] == '0') ? 0 : 1; }();             // 0: fixed roles
+    conv_gemm_tc3_kernel<<<dim3((unsigned)gx, ny), dim3(T3_THREADS), smem, st>>>(a, (int)tiles, pp);
     *handled = true;
     return dsg_launch_error();
 }
