@@ -94,6 +94,61 @@ def test_conv_gemm_temporal_conv_and_grads(dev, dtype, k, stride, dil):
     close(db, br.grad, dtype, "conv bgrad")
 
 
+@pytest.mark.parametrize("K,N", [(64, 64), (24, 64), (64, 24), (176, 64), (96, 256), (128, 352), (256, 256), (128, 128)])
+@pytest.mark.parametrize("variant", ["fwd", "bwd", "ext_in", "contract"])
+def test_conv_gemm_fast_engines(dev, K, N, variant):
+    """bf16 shapes of the network (channels % 8 == 0) take the tcgen05 engines: the persistent ping-pong engine (several
+    tiles per CTA, both accumulator phases, one or two K passes, narrow and multiple column tiles, per-pass weight copies)
+    or the one-tile-per-CTA engine for wide K.  Every fused prologue / epilogue feature against plain PyTorch."""
+    dtype = torch.bfloat16
+    big = dev.type == "cuda"
+    torch.manual_seed(K * 1000 + N)
+    V = 25
+    n, T = (96, 52) if big else (2, 3)                  # 124 800 rows = ~1000 tiles on the GPU; tiny on the simulator
+    if not big and (K > 64 or N > 64):
+        pytest.skip("simulator: small shapes only")
+    ext_in, cext = variant == "ext_in", variant == "contract"
+    Vin = V + 1 if cext else V
+    rows_in = n * T * Vin
+    rows_out = n * T * (V + 1 if ext_in else V)
+    x = rnd(rows_in, K, dev=dev, dtype=dtype)
+    W, b = rnd(N, K, dev=dev, scale=0.2), rnd(N, dev=dev)
+    a1, b1 = torch.rand(K, device=dev) + 0.5, rnd(K, dev=dev, scale=0.2)
+    out = torch.empty(rows_out, N, dtype=dtype, device=dev)
+    kw = dict(n_samples=n, T_in=T, T_out=T, Vin=Vin)
+    if variant == "fwd":
+        ss, sq = torch.zeros(N, dtype=torch.float64, device=dev), torch.zeros(N, dtype=torch.float64, device=dev)
+        add = rnd(rows_out, N, dev=dev, dtype=dtype)
+        ops.conv_gemm(ops.Act(x, a1, b1, relu=True), W, N, out, bias=b, add=add, stat_sum=ss, stat_sq=sq, **kw)
+        ref = torch.relu(x.float() * a1 + b1) @ W.t() + b + add.float()
+        close(ss, ref.sum(0), dtype, "sum")
+        close(sq, (ref * ref).sum(0), dtype, "sumsq")
+    elif variant == "bwd":
+        x2 = rnd(rows_in, K, dev=dev, dtype=dtype)
+        a2, b2 = torch.rand(K, device=dev) + 0.5, rnd(K, dev=dev, scale=0.2)
+        mk, partner = rnd(rows_out, N, dev=dev, dtype=dtype), rnd(rows_out, N, dev=dev, dtype=dtype)
+        ma, mb = torch.rand(N, device=dev) + 0.5, rnd(N, dev=dev, scale=0.2)
+        ss, sq = torch.zeros(N, dtype=torch.float64, device=dev), torch.zeros(N, dtype=torch.float64, device=dev)
+        Wt = W.t().contiguous()                              # [K, N] read with ws = (1, N, 0): the data-gradient orientation
+        ops.conv_gemm(ops.Act(x, a1, b1, x2, a2, b2), Wt, N, out, ws=(1, N, 0), mask=ops.Act(mk, ma, mb), stat_sum=ss, stat_sq=sq,
+                      partner=partner, **kw)
+        ref = (x.float() * a1 + b1 + x2.float() * a2 + b2) @ W.t()
+        ref = ref * ((mk.float() * ma + mb) > 0)
+        close(ss, ref.sum(0), dtype, "sum")
+        close(sq, (ref * partner.float()).sum(0), dtype, "sumprod")
+    elif variant == "ext_in":
+        ops.conv_gemm(ops.Act(x, a1, b1, relu=True), W, N, out, bias=b, ext_in=True, **kw)
+        h = torch.relu(x.float() * a1 + b1).to(dtype).float().view(n * T, V, K)       # the mean is taken over the staged bf16 rows
+        h = torch.cat([h, h.mean(1, keepdim=True)], 1).reshape(-1, K)
+        ref = h @ W.t() + b
+    else:
+        bc = rnd(n, V, N, dev=dev)
+        ops.conv_gemm(x, W, N, out, contract_ext=True, bcast=bc, bcast_scale=0.5, **kw)
+        y = (x.float() @ W.t()).view(n * T, V + 1, N)
+        ref = (y[:, :V] + y[:, V:] / V).reshape(-1, N) + 0.5 * bc[:, None].expand(n, T, V, N).reshape(-1, N)
+    close(out, ref, dtype, f"{variant} out")
+
+
 @pytest.mark.parametrize("dtype", DTYPES)
 def test_conv_gemm_joint_mean_row(dev, dtype):
     """ext_in appends mean_v (tcn.py:409); contract_ext is its gradient; wgrad sees the extended rows."""
