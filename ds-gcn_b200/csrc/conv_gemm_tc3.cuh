@@ -30,6 +30,54 @@ DSG_D void group_sync(int id) {               // named barrier over one 128-thre
     asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory");
 }
 
+// K-major SWIZZLE_128B operand: rows of 128 bytes (64 bf16 of the reduction axis), 8-row groups 1024 bytes apart, the
+// 16-byte chunk index XOR-ed with (row & 7); one "atom" = 128 rows x 64 channels = 16 KB, 1024-byte aligned.
+DSG_D uint64_t make_desc_sw128(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)(1024u >> 4) << 32;                   // SBO: next 8-row group
+    d |= (uint64_t)1 << 46;                              // descriptor version (sm_100)
+    d |= (uint64_t)2 << 61;                              // layout type SWIZZLE_128B
+    return d;
+}
+DSG_D uint32_t sw128_off(int row, int chunk) { return (uint32_t)(row * 128 + ((chunk ^ (row & 7)) << 4)); }
+
+// Coalesced staging of one 64-channel atom: lane = (row % 4, chunk) so a warp reads 4 whole 128-byte rows per load and
+// writes 4 whole swizzled rows per store (conflict-free both ways); NB loads in flight per source.
+template <int NB, bool DUAL>
+DSG_D void t3_stage_sw128(const dsg_conv_gemm_args& a, const long long* rowsrc, int rtid, int k0, unsigned char* atom,
+                          const float* cf_a1, const float* cf_b, const float* cf_a2) {
+    const int chunk = rtid & 7, r0 = rtid >> 3;          // rows r0, r0 + 16, ...
+    const int k = k0 + chunk * 8;
+    const bf16* x1 = reinterpret_cast<const bf16*>(a.src.x1) + k;
+    const bf16* x2 = DUAL ? reinterpret_cast<const bf16*>(a.src.x2) + k : nullptr;
+    const bool kin = k < a.K;
+    for (int i0 = 0; i0 < 8; i0 += NB) {
+        Act8Raw raw[NB];
+        long long sr[NB];
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+            sr[b] = rowsrc[(i0 + b) * 16 + r0];
+            raw[b].a = raw[b].b = make_uint4(0u, 0u, 0u, 0u);
+            if (sr[b] >= 0 && kin) {
+                raw[b].a = *reinterpret_cast<const uint4*>(x1 + sr[b] * a.src.ld1);
+                if (DUAL) raw[b].b = *reinterpret_cast<const uint4*>(x2 + sr[b] * a.src.ld2);
+            }
+        }
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+            const int row = (i0 + b) * 16 + r0;
+            uint4 pk = make_uint4(0u, 0u, 0u, 0u);
+            if (sr[b] >= 0 && kin) {
+                float v[8];
+                finish_smem(raw[b], DUAL, a.src.relu, cf_a1 + k, cf_b + k, cf_a2 + k, v);
+                pk = pack8(v);
+            }
+            *reinterpret_cast<uint4*>(atom + sw128_off(row, chunk)) = pk;
+        }
+    }
+}
+
 __global__ void __launch_bounds__(T3_THREADS) conv_gemm_tc3_kernel(dsg_conv_gemm_args a, int n_tiles, int pp) {
     DSG_DYN_SMEM(smem);
     __shared__ uint64_t a_free[2], acc_full[2], acc_free[2], wbar;
@@ -49,8 +97,11 @@ __global__ void __launch_bounds__(T3_THREADS) conv_gemm_tc3_kernel(dsg_conv_gemm
     const int Kp = (a.K + 15) & ~15;
     const int kpass = Kp < T2_KPASS ? Kp : T2_KPASS;
     const size_t a_bytes = (size_t)128 * Kp * 2;         // one stage: the pass tiles back to back
-    unsigned char* Wbase = smem;                         // [pass][Ntp x kv_len]
-    unsigned char* Abase0 = smem + (size_t)128 * Kp * 2;
+    __shared__ long long rowsrc_s[2][128];               // per group: source row of every tile row (-1 zero row, -2 joint-mean row)
+    const bool sw = (Kp & 63) == 0;                      // reduction axis in whole 64-channel atoms: coalesced swizzled staging
+    unsigned char* smem_al = smem + ((1024u - (smem_u32(smem) & 1023u)) & 1023u);      // SWIZZLE_128B atoms need 1024-byte alignment
+    unsigned char* Wbase = smem_al;                      // [pass][Ntp x kv_len]
+    unsigned char* Abase0 = smem_al + (size_t)128 * Kp * 2;
     float* cf_a1 = reinterpret_cast<float*>(Abase0 + 2 * a_bytes);
     float* cf_b = cf_a1 + Kp;
     float* cf_a2 = cf_b + Kp;
@@ -141,13 +192,45 @@ __global__ void __launch_bounds__(T3_THREADS) conv_gemm_tc3_kernel(dsg_conv_gemm
                 if (sf >= 0) sr = (j < a.Vin) ? sf * a.Vin + j : -2;
             }
             if (use > 0) mbar_wait(&a_free[st], (uint32_t)((use - 1) & 1));     // the MMAs that read this stage are done
-            for (int kv0 = 0; kv0 < Kp; kv0 += kpass) {
-                const int kv_len = Kp - kv0 < kpass ? Kp - kv0 : kpass;
-                unsigned char* Ap = Abase + (size_t)128 * kv0 * 2;
-                if (a.src.x2 == nullptr) t2_stage_a<8, false>(a, sr, rtid, kv0, kv_len >> 3, Ap, cf_a1, cf_b, cf_a2);
-                else t2_stage_a<4, true>(a, sr, rtid, kv0, kv_len >> 3, Ap, cf_a1, cf_b, cf_a2);
+            if (sw) {
+                rowsrc_s[role][rtid] = sr;
+                group_sync(bar_p);
+                for (int k0 = 0; k0 < Kp; k0 += 64) {
+                    unsigned char* atom = Abase + (size_t)128 * k0 * 2;
+                    if (a.src.x2 == nullptr) t3_stage_sw128<8, false>(a, rowsrc_s[role], rtid, k0, atom, cf_a1, cf_b, cf_a2);
+                    else t3_stage_sw128<4, true>(a, rowsrc_s[role], rtid, k0, atom, cf_a1, cf_b, cf_a2);
+                }
+            } else {
+                for (int kv0 = 0; kv0 < Kp; kv0 += kpass) {
+                    const int kv_len = Kp - kv0 < kpass ? Kp - kv0 : kpass;
+                    unsigned char* Ap = Abase + (size_t)128 * kv0 * 2;
+                    if (a.src.x2 == nullptr) t2_stage_a<8, false>(a, sr, rtid, kv0, kv_len >> 3, Ap, cf_a1, cf_b, cf_a2);
+                    else t2_stage_a<4, true>(a, sr, rtid, kv0, kv_len >> 3, Ap, cf_a1, cf_b, cf_a2);
+                }
             }
-            if (a.ext_in) {
+            if (a.ext_in && sw) {
+                group_sync(bar_p);
+                const int nchT = Kp >> 3;
+                for (int idx = rtid; idx < Fr * nchT; idx += 128) {        // joint-mean rows, averaged in fp32
+                    const int kcT = idx % nchT, ff = idx / nchT;
+                    if ((long long)tile * Fr + ff >= n_frames) continue;
+                    unsigned char* atom = Abase + (size_t)128 * ((kcT >> 3) * 64) * 2;
+                    const int kc = kcT & 7;
+                    float s8[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) s8[e] = 0.f;
+                    for (int v = 0; v < a.Vin; ++v) {
+                        float t[8];
+                        unpack8(*reinterpret_cast<const uint4*>(atom + sw128_off(ff * rpf + v, kc)), t);
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) s8[e] += t[e];
+                    }
+                    const float inv = 1.f / (float)a.Vin;
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) s8[e] *= inv;
+                    *reinterpret_cast<uint4*>(atom + sw128_off(ff * rpf + a.Vin, kc)) = pack8(s8);
+                }
+            } else if (a.ext_in) {
                 group_sync(bar_p);
                 const int nchT = Kp >> 3;
                 for (int idx = rtid; idx < Fr * nchT; idx += 128) {        // joint-mean rows, averaged in fp32
@@ -186,7 +269,10 @@ __global__ void __launch_bounds__(T3_THREADS) conv_gemm_tc3_kernel(dsg_conv_gemm
                     const uint32_t sbo = (uint32_t)(kv_len >> 3) * 128u;
                     const uint32_t a0 = smem_u32(Abase + (size_t)128 * kv0 * 2), b0 = smem_u32(Wbase + woff);
                     for (int ks = 0; ks < (kv_len >> 4); ++ks) {
-                        umma_f16(acc, make_desc(a0 + ks * 256u, 128u, sbo), make_desc(b0 + ks * 256u, 128u, sbo), idesc, firstmma ? 0u : 1u);
+                        // swizzled A: atom (ks >> 2) of this pass, 32 bytes per K = 16 step inside the atom's 128-byte rows
+                        const uint64_t ad = sw ? make_desc_sw128(a0 + (uint32_t)(ks >> 2) * 16384u + (uint32_t)(ks & 3) * 32u)
+                                               : make_desc(a0 + ks * 256u, 128u, sbo);
+                        umma_f16(acc, ad, make_desc(b0 + ks * 256u, 128u, sbo), idesc, firstmma ? 0u : 1u);
                         firstmma = 0;
                     }
                     woff += (uint32_t)(Ntp * kv_len * 2);
@@ -309,7 +395,7 @@ static const char* launch_conv_gemm_tc3(const dsg_conv_gemm_args& a, dsg_stream_
     if (n_frames <= 0 || a.N <= 0) { *handled = true; return nullptr; }
     const int Kp = (a.K + 15) & ~15;
     const int kpass = Kp < T2_KPASS ? Kp : T2_KPASS;
-    const size_t smem = (size_t)3 * 128 * Kp * 2 + (size_t)(3 * Kp + 4 * T2_BN) * sizeof(float);
+    const size_t smem = (size_t)3 * 128 * Kp * 2 + (size_t)(3 * Kp + 4 * T2_BN) * sizeof(float) + 1024;   // + alignment slack
     if (smem > 200 * 1024) return nullptr;
     // Measured on B200 (profiles/): with one producer group per CTA this engine wins while the reduction axis is short
     // (Kp <= 192: the weight tile and two stages leave room for two CTAs per SM or the tail dominates) and the CTA's

@@ -149,6 +149,34 @@ def test_conv_gemm_fast_engines(dev, K, N, variant):
     close(out, ref, dtype, f"{variant} out")
 
 
+@pytest.mark.parametrize("K,N", [(64, 64), (24, 64), (64, 176), (256, 96), (128, 288), (256, 256)])
+@pytest.mark.parametrize("ext_in", [False, True])
+def test_conv_wgrad_fast_engine(dev, K, N, ext_in):
+    """bf16 weight / bias gradient on the tcgen05 engine: batched operand staging, register bias sums, vector reductions,
+    K and N tiling, the joint-mean row, both operands with fused prologues (A: BN + ReLU; B: two-tensor BN-backward form)."""
+    dtype = torch.bfloat16
+    big = dev.type == "cuda"
+    torch.manual_seed(K * 7 + N)
+    V = 25
+    n, T = (64, 40) if big else (2, 3)
+    if not big and (K > 64 or N > 64):
+        pytest.skip("simulator: small shapes only")
+    rows_in, rows_out = n * T * V, n * T * (V + 1 if ext_in else V)
+    x = rnd(rows_in, K, dev=dev, dtype=dtype)
+    a1, b1 = torch.rand(K, device=dev) + 0.5, rnd(K, dev=dev, scale=0.2)
+    e, y = rnd(rows_out, N, dev=dev, dtype=dtype), rnd(rows_out, N, dev=dev, dtype=dtype)
+    ca, cb, cc = torch.rand(N, device=dev) + 0.5, rnd(N, dev=dev, scale=0.3), rnd(N, dev=dev, scale=0.1)
+    dW, db = torch.zeros(N, K, device=dev), torch.zeros(N, device=dev)
+    ops.conv_wgrad(ops.Act(x, a1, b1, relu=True), ops.Act(e, ca, cc, y, cb), dW, db=db, n_samples=n, T_in=T, T_out=T, Vin=V, ext_in=ext_in)
+    A = torch.relu(x.float() * a1 + b1)
+    if ext_in:
+        A = A.to(dtype).float().view(n * T, V, K)
+        A = torch.cat([A, A.mean(1, keepdim=True)], 1).reshape(-1, K)
+    B = e.float() * ca + cc + y.float() * cb
+    close(dW, B.t() @ A, dtype, "dW")
+    close(db, B.sum(0), dtype, "db")
+
+
 @pytest.mark.parametrize("dtype", DTYPES)
 def test_conv_gemm_joint_mean_row(dev, dtype):
     """ext_in appends mean_v (tcn.py:409); contract_ext is its gradient; wgrad sees the extended rows."""
