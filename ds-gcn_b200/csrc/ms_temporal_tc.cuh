@@ -103,24 +103,6 @@ DSG_D void ms_load_w(const dsg_ms_temporal_args& a, int j, int orient, int Kp, u
     for (int i = threadIdx.x; i < 3 * Kp * Kp * 2 / 16; i += MS_THREADS) dst[i] = src[i];
 }
 
-// branch pre-activation (post BN, no ReLU) at (sample n, input frame t, column j, channel c)
-DSG_D float ms_preact(const dsg_ms_temporal_args& a, int n, int t, int j, int c, int Vp) {
-    const long long r = ((long long)n * a.T_in + t) * Vp + j;
-    return fmaf(__bfloat162float(reinterpret_cast<const bf16*>(a.b.x1)[r * a.b.ld1 + c]), a.b.a1[c], a.b.b1[c]);
-}
-// output of a max / pass branch at (n, output frame tp, column j, channel c)
-DSG_D float ms_mp_out(const dsg_ms_temporal_args& a, int kind, int n, int tp, int j, int c, int Vp) {
-    if (kind == 2) return ms_preact(a, n, tp * a.stride, j, c, Vp);
-    float m = -3.0e38f;
-#pragma unroll
-    for (int dt = -1; dt <= 1; ++dt) {
-        const int t = tp * a.stride + dt;
-        if (t < 0 || t >= a.T_in) continue;
-        m = fmaxf(m, fmaxf(ms_preact(a, n, t, j, c, Vp), 0.f));
-    }
-    return m;
-}
-
 constexpr int MS_CMAX = 512;        // channels the staged coefficient arrays hold
 
 // BN coefficients of the branch pre-activations, staged once per CTA
@@ -511,11 +493,6 @@ DSG_D MsBwdTaps ms_bwd_taps(int d, int s, int p_in) {
     }
     r.Fq = r.n ? MS_TO + shmax - r.shmin : 0;
     return r;
-}
-
-// gradient w.r.t. the branch-stage output (before local+global mixing) for joint rows: dfeat itself
-DSG_D float ms_dfeat(const dsg_ms_temporal_args& a, int n, int tp, int v, int c) {
-    return act_value<bf16>(a.dfeat, ((long long)n * a.T_out + tp) * a.V + v, c);
 }
 
 __global__ void __launch_bounds__(MS_THREADS, 3) ms_temporal_bwd_data_kernel(dsg_ms_temporal_args a, MsGeomPack gp, int h_bytes, int w_bytes, int tmem_cols,
