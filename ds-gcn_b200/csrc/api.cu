@@ -55,6 +55,10 @@ int dsg_conv_gemm(const dsg_conv_gemm_args* a, void* stream) {
     if (!a || !dtype_ok(a->dtype)) return fail("dsg_conv_gemm", "bad arguments");
     if (a->taps < 1 || a->t_div < 1 || a->Vin < 1 || a->K < 1) return fail("dsg_conv_gemm", "bad shape");
     if ((a->stat_sum == nullptr) != (a->stat_sq == nullptr)) return fail("dsg_conv_gemm", "stat_sum and stat_sq go together");
+    if (dsg::conv_gemm_skinny_ok(*a)) {               // N <= 8: a stream over the input rows, no GEMM tile
+        if (a->dtype == DSG_BF16) DSG_RET("dsg_conv_gemm", dsg::launch_conv_gemm_skinny<bf16>(*a, (dsg_stream_t)stream));
+        DSG_RET("dsg_conv_gemm", dsg::launch_conv_gemm_skinny<float>(*a, (dsg_stream_t)stream));
+    }
 #ifndef DSG_EMU
     if (a->dtype == DSG_BF16 && tc_enabled()) {      // tcgen05 engine (sm_100a); shapes it does not take fall through
         bool handled = false;
@@ -120,6 +124,10 @@ int dsg_tmean(const void* x, int dtype, long long ld, int n_samples, int T, int 
     if (!dtype_ok(dtype) || T < 1) return fail("dsg_tmean", "bad arguments");
     if (n_samples <= 0) return 0;
     dim3 grid((V * C + 255) / 256, n_samples);
+    if (dtype == DSG_BF16 && C % 8 == 0 && ld % 8 == 0 && (uintptr_t)x % 16 == 0) {
+        dsg_launch(dsg::tmean_vec_kernel, dim3((V * (C / 8) + 127) / 128, n_samples), dim3(128), 0, (dsg_stream_t)stream, (const bf16*)x, ld, T, V, C, xm);
+        DSG_RET("dsg_tmean", dsg_launch_error());
+    }
     if (dtype == DSG_BF16) dsg_launch(dsg::tmean_kernel<bf16>, grid, dim3(256), 0, (dsg_stream_t)stream, (const bf16*)x, ld, T, V, C, xm);
     else dsg_launch(dsg::tmean_kernel<float>, grid, dim3(256), 0, (dsg_stream_t)stream, (const float*)x, ld, T, V, C, xm);
     DSG_RET("dsg_tmean", dsg_launch_error());

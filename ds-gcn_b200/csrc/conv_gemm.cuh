@@ -175,6 +175,98 @@ __global__ void __launch_bounds__(CG_THREADS) conv_gemm_kernel(dsg_conv_gemm_arg
 }
 
 // ---------------------------------------------------------------------------------------------
+// Skinny outputs (N <= 8: the data gradient towards the 3-channel network input): a GEMM tile would idle, the op is a
+// pure stream over the input rows.  Thread = output row; weights and prologue coefficients in shared memory; bf16 rows
+// are read with 4 independent 16-byte loads in flight.  Epilogue: bias, addends, per-sample broadcast.
+constexpr int SK_KMAX = 512;
+template <class T>
+__global__ void __launch_bounds__(256) conv_gemm_skinny_kernel(dsg_conv_gemm_args a, int vec) {
+    DSG_SHARED __align__(16) float Ws[8 * SK_KMAX];          // [n][k]
+    DSG_SHARED __align__(16) float cf[3][SK_KMAX];           // a1, b1 + b2, a2
+    const int tid = threadIdx.x, K = a.K, N = a.N;
+    for (int idx = tid; idx < N * K; idx += 256) {
+        const int k = idx % K, n = idx / K;
+        Ws[n * K + k] = a.W[(long long)n * a.ws_n + (long long)k * a.ws_k];
+    }
+    for (int k = tid; k < K; k += 256) {
+        cf[0][k] = a.src.a1 ? a.src.a1[k] : 1.f;
+        cf[1][k] = (a.src.b1 ? a.src.b1[k] : 0.f) + (a.src.b2 ? a.src.b2[k] : 0.f);
+        cf[2][k] = a.src.a2 ? a.src.a2[k] : 1.f;
+    }
+    __syncthreads();
+    const long long rows_out = (long long)a.n_samples * a.T_out * a.Vin;
+    const long long row = (long long)blockIdx.x * 256 + tid;
+    if (row >= rows_out) return;
+    const long long f = row / a.Vin;
+    const int j = (int)(row - f * a.Vin);
+    FrameMap fm{1, a.tap_step, a.tap_off, a.t_mul, a.t_div, a.T_in, a.T_out, a.Vin, 0};
+    const long long sf = src_frame(fm, f, 0);
+    float acc[8];
+#pragma unroll
+    for (int n = 0; n < 8; ++n) acc[n] = (n < N && a.bias) ? a.bias[n] : 0.f;
+    if (sf >= 0) {
+        const long long sr = sf * a.Vin + j;
+        int k0 = 0;
+        if (vec) {                                               // bf16, 16-byte aligned rows
+            const bf16* x1 = reinterpret_cast<const bf16*>(a.src.x1) + sr * a.src.ld1;
+            const bf16* x2 = a.src.x2 ? reinterpret_cast<const bf16*>(a.src.x2) + sr * a.src.ld2 : nullptr;
+            for (; k0 + 8 <= K; k0 += 32) {
+                uint4 r1[4], r2[4];
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    const int k = k0 + b * 8;
+                    if (k + 8 <= K) {
+                        r1[b] = *reinterpret_cast<const uint4*>(x1 + k);
+                        if (x2) r2[b] = *reinterpret_cast<const uint4*>(x2 + k);
+                    }
+                }
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    const int k = k0 + b * 8;
+                    if (k + 8 > K) continue;
+                    float x[8], v[8];
+                    unpack8(r1[b], x);
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) v[e] = fmaf(x[e], cf[0][k + e], cf[1][k + e]);
+                    if (x2) {
+                        unpack8(r2[b], x);
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) v[e] = fmaf(x[e], cf[2][k + e], v[e]);
+                    }
+                    if (a.src.relu) {
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e], 0.f);
+                    }
+#pragma unroll
+                    for (int n = 0; n < 8; ++n) {
+                        if (n >= N) break;
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) acc[n] = fmaf(v[e], Ws[n * K + k + e], acc[n]);
+                    }
+                }
+            }
+            k0 = K & ~7;                                         // leftover channels (K % 8) on the scalar path
+        }
+        for (int k = k0; k < K; ++k) {
+            const float v = act_value<T>(a.src, sr, k);
+#pragma unroll
+            for (int n = 0; n < 8; ++n)
+                if (n < N) acc[n] = fmaf(v, Ws[n * K + k], acc[n]);
+        }
+    }
+    const int samp = (int)(f / a.T_out);
+#pragma unroll
+    for (int n = 0; n < 8; ++n) {
+        if (n >= N) break;
+        float v = acc[n];
+        if (a.add) v += ldf<T>(reinterpret_cast<const T*>(a.add) + row * a.ld_add + n);
+        if (a.add2) v += ldf<T>(reinterpret_cast<const T*>(a.add2) + row * a.ld_add2 + n);
+        if (a.bcast) v = fmaf(a.bcast[((long long)samp * a.Vin + j) * N + n], a.bcast_scale, v);
+        stf<T>(reinterpret_cast<T*>(a.out) + row * a.ld_out + n, v);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 constexpr int WG_BK = 64;    // dW tile: input channels
 constexpr int WG_BN = 64;    // dW tile: output channels
 constexpr int WG_BR = 64;    // GEMM rows per inner step (whole frames)
@@ -276,6 +368,18 @@ __global__ void __launch_bounds__(CG_THREADS) conv_wgrad_kernel(dsg_conv_wgrad_a
         }
     }
     if (do_bias && tid < WG_BN && n0 + tid < a.N) atomicAdd(a.db + n0 + tid, bsum);
+}
+
+// shapes the skinny kernel takes
+static inline bool conv_gemm_skinny_ok(const dsg_conv_gemm_args& a) {
+    return a.N <= 8 && a.K <= SK_KMAX && a.taps == 1 && !a.ext_in && !a.contract_ext && !a.has_mask && !a.stat_sum && !a.partner;
+}
+template <class T> static const char* launch_conv_gemm_skinny(const dsg_conv_gemm_args& a, dsg_stream_t st) {
+    const long long rows_out = (long long)a.n_samples * a.T_out * a.Vin;
+    if (rows_out <= 0 || a.N <= 0) return nullptr;
+    const int vec = (sizeof(T) == 2) && act8_ok(a.src) ? 1 : 0;
+    dsg_launch(conv_gemm_skinny_kernel<T>, dim3((unsigned)((rows_out + 255) / 256)), dim3(256), 0, st, a, vec);
+    return dsg_launch_error();
 }
 
 template <class T> static const char* launch_conv_gemm(const dsg_conv_gemm_args& a, dsg_stream_t st) {

@@ -78,6 +78,43 @@ __global__ void tmean_kernel(const T* x, long long ld, int T_, int V, int C, flo
     xm[(long long)n * V * C + idx] = s / (float)T_;
 }
 
+// bf16 fast path: a thread owns (joint, 8 channels) and walks the frames with 4 independent 16-byte loads in flight
+__global__ void tmean_vec_kernel(const bf16* x, long long ld, int T_, int V, int C, float* xm) {
+    const int n = blockIdx.y;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;   // v*(C/8) + chunk
+    const int nch = C >> 3;
+    if (idx >= V * nch) return;
+    const int ch = idx % nch, v = idx / nch;
+    const bf16* p = x + ((long long)n * T_ * V + v) * ld + ch * 8;
+    const long long fstep = (long long)V * ld;
+    float s[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) s[e] = 0.f;
+    int t = 0;
+    for (; t + 4 <= T_; t += 4) {
+        uint4 r[4];
+#pragma unroll
+        for (int b = 0; b < 4; ++b) r[b] = *reinterpret_cast<const uint4*>(p + (t + b) * fstep);
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            float f[8];
+            unpack8(r[b], f);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) s[e] += f[e];
+        }
+    }
+    for (; t < T_; ++t) {
+        float f[8];
+        unpack8(*reinterpret_cast<const uint4*>(p + t * fstep), f);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) s[e] += f[e];
+    }
+    float* dst = xm + (long long)n * V * C + v * C + ch * 8;
+    const float inv = 1.f / (float)T_;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) dst[e] = s[e] * inv;
+}
+
 // ---------------------------------------------------------------------------------------------
 constexpr int PW_THREADS = 256;
 constexpr int PW_CT = 64;        // channels per CTA

@@ -178,6 +178,25 @@ def test_conv_wgrad_fast_engine(dev, K, N, ext_in):
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("K,N", [(88, 3), (19, 5), (64, 8)])
+def test_conv_gemm_skinny_output(dev, dtype, K, N):
+    """N <= 8 (the data gradient towards the 3-channel network input, gcn.py:2165 backward) runs as a row stream."""
+    torch.manual_seed(K + N)
+    n, T, V = 3, 7, 25
+    rows = n * T * V
+    x, x2 = rnd(rows, K, dev=dev, dtype=dtype), rnd(rows, K, dev=dev, dtype=dtype)
+    a1, b1 = torch.rand(K, device=dev) + 0.5, rnd(K, dev=dev, scale=0.2)
+    a2, b2 = torch.rand(K, device=dev) + 0.5, rnd(K, dev=dev, scale=0.2)
+    Wt = rnd(K, N, dev=dev, scale=0.3)                       # [K, N]: the transposed (data-gradient) orientation
+    add, bc = rnd(rows, N, dev=dev, dtype=dtype), rnd(n, V, N, dev=dev)
+    out = torch.empty(rows, N, dtype=dtype, device=dev)
+    ops.conv_gemm(ops.Act(x, a1, b1, x2, a2, b2), Wt, N, out, n_samples=n, T_in=T, T_out=T, Vin=V, ws=(1, N, 0), add=add, bcast=bc,
+                  bcast_scale=1.0 / T)
+    ref = (x.float() * a1 + b1 + x2.float() * a2 + b2) @ Wt + add.float() + bc[:, None].expand(n, T, V, N).reshape(-1, N) / T
+    close(out, ref, dtype, "skinny out")
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
 def test_conv_gemm_joint_mean_row(dev, dtype):
     """ext_in appends mean_v (tcn.py:409); contract_ext is its gradient; wgrad sees the extended rows."""
     torch.manual_seed(2)
@@ -242,6 +261,8 @@ def test_tmean_and_pointwise(dev, dtype):
     x = rnd(n * T * V, Cn, dev=dev, dtype=dtype)
     xm = ops.tmean(x, n, T, V)
     close(xm, x.float().reshape(n, T, V, Cn).mean(1), torch.float32, "tmean")
+    xv = rnd(n * 11 * V, 72, dev=dev, dtype=dtype)[:, :64]            # 16-byte path: channel slice of a wider buffer, T % 4 != 0
+    close(ops.tmean(xv, n, 11, V), xv.float().reshape(n, 11, V, 64).mean(1), torch.float32, "tmean vec")
     x2 = rnd(n * T * V, Cn, dev=dev, dtype=dtype)
     a1, b1 = torch.rand(Cn, device=dev) + 0.5, rnd(Cn, dev=dev)
     mk = rnd(n * T * V, Cn, dev=dev, dtype=dtype)
