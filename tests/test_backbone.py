@@ -219,3 +219,39 @@ def test_dgstgcn_full_vs_oracle(dtype):
                     assert rel(v, sdt[k]) < 1e-4, k
     finally:
         M.set_compute_dtype(torch.bfloat16)
+
+
+@pytest.mark.gpu
+def test_bench_size_properties():
+    """BENCH workload size (128 clips, M=2, T=100, V=25, C=3, bf16), where the CPU oracle is too slow: properties that do
+    not depend on the size.  (1) eval-mode outputs are independent across clips: the first 32 clips of the 128-clip batch
+    equal a 32-clip run bit for bit (every row's dot products are accumulated in the same order whatever tile it lands in).
+    (2) checksum of checksums: in train mode the running mean that `data_bn` derives from the statistics accumulated by
+    the kernels equals the directly computed mean of its input."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    dsgcn_b200._lib._testing_use_library(None)
+    dev = torch.device("cuda:0")
+    torch.manual_seed(0); np.random.seed(0)
+    m = M.DGSTGCN(**NORTH_STAR)
+    sd = m.state_dict(); O.randomize_state(sd, 1); m.load_state_dict(sd)
+    M.set_compute_dtype(torch.bfloat16)
+    try:
+        m.to(dev).eval()
+        x = torch.randn(128, 2, 100, 25, 3, device=dev)
+        with torch.no_grad():
+            y_all = m(x)
+            y_part = m(x[:32].contiguous())
+        assert y_all.shape == (128, 2, 256, 25, 25)
+        assert torch.isfinite(y_all.float()).all()
+        assert torch.equal(y_all[:32], y_part), "eval outputs depend on the batch composition"
+        m.train()
+        rm0 = m.data_bn.running_mean.clone()
+        with torch.no_grad():
+            m(x)
+        mom = m.data_bn.momentum if m.data_bn.momentum is not None else 0.1
+        batch_mean = (m.data_bn.running_mean - (1 - mom) * rm0) / mom                 # data_bn_type 'VC': [V*C]
+        direct = x.permute(0, 1, 3, 4, 2).reshape(256, 75, 100).mean((0, 2))          # dgstgcn.py:158-161
+        assert float((batch_mean.cpu() - direct.cpu()).abs().max()) < 1e-4
+    finally:
+        M.set_compute_dtype(torch.bfloat16)
