@@ -100,18 +100,18 @@ __global__ void ms_wpack_kernel(dsg_ms_temporal_args a) {
 DSG_D void ms_load_w(const dsg_ms_temporal_args& a, int j, int orient, int Kp, unsigned char* Wt) {
     const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const unsigned char*>(a.wpack) + ms_wpack_off(a, j) + (long long)orient * 3 * Kp * Kp * 2);
     uint4* dst = reinterpret_cast<uint4*>(Wt);
-    for (int i = threadIdx.x; i < 3 * Kp * Kp * 2 / 16; i += MS_THREADS) dst[i] = src[i];
+    for (int i = threadIdx.x; i < 3 * Kp * Kp * 2 / 16; i += (int)blockDim.x) dst[i] = src[i];
 }
 
 constexpr int MS_CMAX = 512;        // channels the staged coefficient arrays hold
 
 // BN coefficients of the branch pre-activations, staged once per CTA
 DSG_D void ms_stage_b(const dsg_ms_temporal_args& a, float* cfa, float* cfb) {
-    for (int c = threadIdx.x; c < a.C; c += MS_THREADS) { cfa[c] = a.b.a1[c]; cfb[c] = a.b.b1[c]; }
+    for (int c = threadIdx.x; c < a.C; c += (int)blockDim.x) { cfa[c] = a.b.a1[c]; cfb[c] = a.b.b1[c]; }
 }
 // coefficients of the dfeat source (a1, b1+b2, a2)
 DSG_D void ms_stage_d(const dsg_ms_temporal_args& a, float* d1, float* db, float* d2) {
-    for (int c = threadIdx.x; c < a.C; c += MS_THREADS) {
+    for (int c = threadIdx.x; c < a.C; c += (int)blockDim.x) {
         d1[c] = a.dfeat.a1 ? a.dfeat.a1[c] : 1.f;
         db[c] = (a.dfeat.b1 ? a.dfeat.b1[c] : 0.f) + (a.dfeat.b2 ? a.dfeat.b2[c] : 0.f);
         d2[c] = a.dfeat.a2 ? a.dfeat.a2[c] : 1.f;
@@ -142,12 +142,12 @@ DSG_D void ms_stage_H(const dsg_ms_temporal_args& a, const MsBranchGeom& g, int 
                       const float* cfa, const float* cfb) {
     const bf16* Bx = reinterpret_cast<const bf16*>(a.b.x1);
     const int total = s * g.Fq * 32 * g.nch;
-    for (int it0 = threadIdx.x; it0 < total; it0 += MS_THREADS * 4) {
+    for (int it0 = threadIdx.x; it0 < total; it0 += (int)blockDim.x * 4) {
         uint4 raw[4];
         int off[4], c8s[4];
 #pragma unroll
         for (int b = 0; b < 4; ++b) {
-            const int it = it0 + b * MS_THREADS;
+            const int it = it0 + b * (int)blockDim.x;
             off[b] = -1; c8s[b] = -1;
             if (it < total) {
                 int kc, row;
@@ -188,12 +188,12 @@ DSG_D void ms_stage_dO(const dsg_ms_temporal_args& a, const MsBranchGeom& g, int
     const bf16* X1 = reinterpret_cast<const bf16*>(a.dfeat.x1);
     const bf16* X2 = reinterpret_cast<const bf16*>(a.dfeat.x2);
     const int total = nfr * 32 * g.nch;
-    for (int it0 = threadIdx.x; it0 < total; it0 += MS_THREADS * 4) {
+    for (int it0 = threadIdx.x; it0 < total; it0 += (int)blockDim.x * 4) {
         uint4 r1[4], r2[4];
         int off[4], c8s[4];
 #pragma unroll
         for (int b = 0; b < 4; ++b) {
-            const int it = it0 + b * MS_THREADS;
+            const int it = it0 + b * (int)blockDim.x;
             off[b] = -1; c8s[b] = -1;
             if (it < total) {
                 int kc, row;
@@ -234,7 +234,9 @@ DSG_D void ms_stage_dO(const dsg_ms_temporal_args& a, const MsBranchGeom& g, int
     }
 }
 
-__global__ void __launch_bounds__(MS_THREADS, 4) ms_temporal_fwd_kernel(dsg_ms_temporal_args a, MsGeomPack gp, int h_bytes, int w_bytes, int tmem_cols) {
+// NT = 256 (up to 4 CTAs per SM) or 512 (wide layers whose tiles leave room for one CTA per SM only: twice the warps)
+template <int NT>
+__global__ void __launch_bounds__(NT, NT == 256 ? 4 : 1) ms_temporal_fwd_kernel(dsg_ms_temporal_args a, MsGeomPack gp, int h_bytes, int w_bytes, int tmem_cols) {
     DSG_DYN_SMEM(smem);
     __shared__ uint64_t mbar;
     __shared__ uint32_t tmem_base_s;
@@ -250,7 +252,7 @@ __global__ void __launch_bounds__(MS_THREADS, 4) ms_temporal_fwd_kernel(dsg_ms_t
     ms_stage_b(a, cfa, cfb);
     for (int j = 0; j < a.n_branches; ++j)
         if (a.br[j].kind == 0)
-            for (int k = tid; k < a.br[j].hi - a.br[j].lo; k += MS_THREADS) bias_s[a.br[j].lo + k] = a.br[j].bias[k];
+            for (int k = tid; k < a.br[j].hi - a.br[j].lo; k += NT) bias_s[a.br[j].lo + k] = a.br[j].bias[k];
     if (tid < 32) addc_s[tid] = (a.has_ext && tid < V) ? a.add_coeff[tid] : 0.f;
 
     if (tid == 0) {
@@ -298,9 +300,10 @@ __global__ void __launch_bounds__(MS_THREADS, 4) ms_temporal_fwd_kernel(dsg_ms_t
     // ---- max-pool / pass-through branches on the CUDA cores while the last MMAs drain: warp = (frame, half of the joints),
     //      lanes walk the channels of the range; the joint-mean column is evaluated first and stays in a register
     {
-        const int fl = warp & 3, half = warp >> 2;
+        constexpr int NP = NT / 128;                         // warps per frame
+        const int fl = warp & 3, half = warp >> 2;           // frame, share of the joints
         const int tp = tp0 + fl;
-        const int v0 = half ? (V + 1) / 2 : 0, v1 = half ? V : (V + 1) / 2;
+        const int v0 = half * V / NP, v1 = (half + 1) * V / NP;
         for (int j = 0; j < a.n_branches; ++j) {
             const int kind = a.br[j].kind;
             if (kind == 0 || tp >= a.T_out) continue;
@@ -350,7 +353,7 @@ __global__ void __launch_bounds__(MS_THREADS, 4) ms_temporal_fwd_kernel(dsg_ms_t
             const MsBranchGeom& g = gp.g[j];
             const int blo = a.br[j].lo, bhi = a.br[j].hi;
             for (int c16 = 0; c16 < g.Kp; c16 += 16, ++gcount) {
-                if ((gcount & 1) != half) continue;
+                if ((gcount % (NT / 128)) != half) continue;
                 float v[16];
                 tmem_ld16(tmem_d + ((uint32_t)(fl * 32) << 16) + (uint32_t)(g.col + c16), v);
                 const int ch0 = g.lo8 + c16;                                 // absolute channel of window column c16
@@ -374,7 +377,7 @@ __global__ void __launch_bounds__(MS_THREADS, 4) ms_temporal_fwd_kernel(dsg_ms_t
     if (warp == 0) tmem_dealloc(tmem_d, (uint32_t)tmem_cols);
     // ---- write-out: complete rows, 16-byte stores, BatchNorm statistics of transform.0
     {
-        const int nchunks = C >> 3, lanes = MS_THREADS / nchunks;
+        const int nchunks = C >> 3, lanes = NT / nchunks;
         const int cc = tid % nchunks, rl = tid / nchunks;
         float s1[8], s2[8];
 #pragma unroll
@@ -398,7 +401,7 @@ __global__ void __launch_bounds__(MS_THREADS, 4) ms_temporal_fwd_kernel(dsg_ms_t
 #pragma unroll
             for (int e = 0; e < 8; ++e) { red[(0 * lanes + rl) * C + cc * 8 + e] = s1[e]; red[(1 * lanes + rl) * C + cc * 8 + e] = s2[e]; }
             __syncthreads();
-            for (int c = tid; c < C; c += MS_THREADS) {
+            for (int c = tid; c < C; c += NT) {
                 float t1 = 0.f, t2 = 0.f;
                 for (int l = 0; l < lanes; ++l) { t1 += red[(0 * lanes + l) * C + c]; t2 += red[(1 * lanes + l) * C + c]; }
                 atomicAdd(a.stat_sum + c, (double)t1);
@@ -431,7 +434,7 @@ static MsHostGeom ms_host_geom(const dsg_ms_temporal_args& a, int out_rows_per_f
     while (h.tmem_cols < cols) h.tmem_cols <<= 1;
     h.feat_bytes = MS_TO * out_rows_per_frame * a.C * 2;
     // the statistics scratch re-uses the operand region: [2][lanes][C] floats
-    int red = 2 * (MS_THREADS / (a.C / 8 > 0 ? a.C / 8 : 1)) * a.C * 4;
+    int red = 2 * (512 / (a.C / 8 > 0 ? a.C / 8 : 1)) * a.C * 4;      // sized for the 512-thread variant
     if (h.h_bytes + h.w_bytes < red) h.h_bytes = red - h.w_bytes > 0 ? red - h.w_bytes : h.h_bytes;
     h.h_bytes = (h.h_bytes + 127) & ~127;
     h.w_bytes = (h.w_bytes + 127) & ~127;
@@ -464,9 +467,14 @@ static const char* launch_ms_temporal_fwd(const dsg_ms_temporal_args& a, dsg_str
     size_t smem = (size_t)h.h_bytes + h.w_bytes + (size_t)MS_TO * a.V * (a.C + 8) * 2;
     if (smem > 200 * 1024) return "ms_temporal_fwd: shared memory budget exceeded";
     if (const char* e = ms_launch_wpack(a, st)) return e;
-    cudaFuncSetAttribute(ms_temporal_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     dim3 grid((a.T_out + MS_TO - 1) / MS_TO, a.n_samples);
-    ms_temporal_fwd_kernel<<<grid, dim3(MS_THREADS), smem, st>>>(a, ms_geom_pack(a), h.h_bytes, h.w_bytes, h.tmem_cols);
+    if (smem > 100 * 1024) {                               // one CTA per SM anyway: give it 16 warps
+        cudaFuncSetAttribute(ms_temporal_fwd_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        ms_temporal_fwd_kernel<512><<<grid, dim3(512), smem, st>>>(a, ms_geom_pack(a), h.h_bytes, h.w_bytes, h.tmem_cols);
+    } else {
+        cudaFuncSetAttribute(ms_temporal_fwd_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        ms_temporal_fwd_kernel<256><<<grid, dim3(256), smem, st>>>(a, ms_geom_pack(a), h.h_bytes, h.w_bytes, h.tmem_cols);
+    }
     return dsg_launch_error();
 }
 
@@ -495,7 +503,8 @@ DSG_D MsBwdTaps ms_bwd_taps(int d, int s, int p_in) {
     return r;
 }
 
-__global__ void __launch_bounds__(MS_THREADS, 3) ms_temporal_bwd_data_kernel(dsg_ms_temporal_args a, MsGeomPack gp, int h_bytes, int w_bytes, int tmem_cols,
+template <int NT>
+__global__ void __launch_bounds__(NT, NT == 256 ? 3 : 1) ms_temporal_bwd_data_kernel(dsg_ms_temporal_args a, MsGeomPack gp, int h_bytes, int w_bytes, int tmem_cols,
                                                                           int mp_lo, int mp_hi) {
     DSG_DYN_SMEM(smem);
     __shared__ uint64_t mbar;
@@ -517,7 +526,7 @@ __global__ void __launch_bounds__(MS_THREADS, 3) ms_temporal_bwd_data_kernel(dsg
     ms_stage_b(a, cfa, cfb);
     ms_stage_d(a, dc1, dcb, dc2);
     for (int j = 0; j < a.n_branches; ++j)
-        for (int c = a.br[j].lo + tid; c < a.br[j].hi; c += MS_THREADS) kind_s[c] = (unsigned char)a.br[j].kind;
+        for (int c = a.br[j].lo + tid; c < a.br[j].hi; c += NT) kind_s[c] = (unsigned char)a.br[j].kind;
     if (tid < a.n_branches && a.br[tid].kind == 0) taps_s[tid] = ms_bwd_taps(gp.g[tid].d, s, p_in);
 
     if (tid == 0) {
@@ -526,7 +535,7 @@ __global__ void __launch_bounds__(MS_THREADS, 3) ms_temporal_bwd_data_kernel(dsg
     }
     if (warp == 0) tmem_alloc(&tmem_base_s, (uint32_t)tmem_cols);
     if (tid < 32) s_dadd[tid] = 0.f;
-    for (int i = tid * 8; i < MS_TO * Vp * CS; i += MS_THREADS * 8) *reinterpret_cast<uint4*>(E_s + i) = make_uint4(0u, 0u, 0u, 0u);
+    for (int i = tid * 8; i < MS_TO * Vp * CS; i += NT * 8) *reinterpret_cast<uint4*>(E_s + i) = make_uint4(0u, 0u, 0u, 0u);
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -545,7 +554,7 @@ __global__ void __launch_bounds__(MS_THREADS, 3) ms_temporal_bwd_data_kernel(dsg
         ms_load_w(a, j, 1, g.Kp, Wt);                                   // B operand [n = ci][k = co]
         if (a.has_ext) {
             __syncthreads();
-            for (int it = tid; it < tp.Fq * g.nchw; it += MS_THREADS) {   // joint-mean row: sum_v dO[v] * add_coeff[v], 8 channels per item
+            for (int it = tid; it < tp.Fq * g.nchw; it += NT) {   // joint-mean row: sum_v dO[v] * add_coeff[v], 8 channels per item
                 const int kc = it % g.nchw, qi = it / g.nchw;
                 float sacc[8];
 #pragma unroll
@@ -586,7 +595,7 @@ __global__ void __launch_bounds__(MS_THREADS, 3) ms_temporal_bwd_data_kernel(dsg
         const int tp_lo = floordiv(t_first - 1, s);
         const int ac0 = mp_lo >> 3, nac = ((mp_hi + 7) >> 3) - ac0;
         if (a.has_ext) {
-            for (int it = tid; it < 6 * nac; it += MS_THREADS) {         // dO of the joint-mean column for the frames in reach
+            for (int it = tid; it < 6 * nac; it += NT) {         // dO of the joint-mean column for the frames in reach
                 const int ac = it % nac, fi = it / nac;
                 const int tpo = tp_lo + fi, c8 = (ac0 + ac) * 8;
                 float sacc[8];
@@ -606,7 +615,7 @@ __global__ void __launch_bounds__(MS_THREADS, 3) ms_temporal_bwd_data_kernel(dsg
             }
             __syncthreads();
         }
-        for (int it = tid; it < MS_TO * Vp * nac; it += MS_THREADS) {
+        for (int it = tid; it < MS_TO * Vp * nac; it += NT) {
             const int ac = it % nac, rest = it / nac;
             const int vv = rest % Vp, i = rest / Vp;
             const int t = s * (q0 + i) + p_in, c8 = (ac0 + ac) * 8;
@@ -678,7 +687,7 @@ __global__ void __launch_bounds__(MS_THREADS, 3) ms_temporal_bwd_data_kernel(dsg
         const int nchunks = C >> 3;
         const bool pow2 = (nchunks & (nchunks - 1)) == 0 && nchunks <= 32;      // a joint's chunks = one aligned lane group
         const int total = nchunks * V;
-        for (int it0 = 0; it0 < total; it0 += MS_THREADS) {                     // every lane iterates: warp shuffles below
+        for (int it0 = 0; it0 < total; it0 += NT) {                     // every lane iterates: warp shuffles below
             const int it = it0 + tid;
             const bool valid = it < total;
             const int cc = valid ? it % nchunks : 0, v = valid ? it / nchunks : 0;
@@ -709,7 +718,7 @@ __global__ void __launch_bounds__(MS_THREADS, 3) ms_temporal_bwd_data_kernel(dsg
             if (!(issued & (1 << j))) continue;
             const MsBranchGeom& g = gp.g[j];
             for (int c16 = 0; c16 < g.Kp; c16 += 16, ++gcount) {
-                if ((gcount & 1) != half) continue;
+                if ((gcount % (NT / 128)) != half) continue;
                 float v[16];
                 tmem_ld16(tmem_d + ((uint32_t)(i * 32) << 16) + (uint32_t)(g.col + c16), v);
                 if (lane < Vp) {
@@ -728,7 +737,7 @@ __global__ void __launch_bounds__(MS_THREADS, 3) ms_temporal_bwd_data_kernel(dsg
     if (a.has_ext && p_in == 0 && tid < V) atomicAdd(a.dadd_coeff + tid, s_dadd[tid]);
     // ---- write-out: ReLU mask from the stored pre-activations (not on the pass range), BN-backward sums, 16-byte stores
     {
-        const int nchunks = C >> 3, lanes = MS_THREADS / nchunks;
+        const int nchunks = C >> 3, lanes = NT / nchunks;
         const int cc = tid % nchunks, rl = tid / nchunks;
         const int c0 = cc * 8;
         float s1[8], s2[8], msk[8];
@@ -761,7 +770,7 @@ __global__ void __launch_bounds__(MS_THREADS, 3) ms_temporal_bwd_data_kernel(dsg
 #pragma unroll
             for (int e = 0; e < 8; ++e) { red[(0 * lanes + rl) * C + c0 + e] = s1[e]; red[(1 * lanes + rl) * C + c0 + e] = s2[e]; }
             __syncthreads();
-            for (int c = tid; c < C; c += MS_THREADS) {
+            for (int c = tid; c < C; c += NT) {
                 float t1 = 0.f, t2 = 0.f;
                 for (int l = 0; l < lanes; ++l) { t1 += red[(0 * lanes + l) * C + c]; t2 += red[(1 * lanes + l) * C + c]; }
                 atomicAdd(a.e_sum + c, (double)t1);
@@ -942,10 +951,16 @@ static const char* launch_ms_temporal_bwd_data(const dsg_ms_temporal_args& a, ds
     size_t smem = (size_t)h.h_bytes + h.w_bytes + (size_t)MS_TO * Vp * (a.C + 8) * 2 + (size_t)6 * (mp_hi - mp_lo) * 4 + 16;
     if (smem > 200 * 1024) return "ms_temporal_bwd_data: shared memory budget exceeded";
     if (const char* e = ms_launch_wpack(a, st)) return e;
-    cudaFuncSetAttribute(ms_temporal_bwd_data_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+
     const int frames_per_plane = (a.T_in + a.stride - 1) / a.stride;
     dim3 grid((frames_per_plane + MS_TO - 1) / MS_TO, a.n_samples, a.stride);
-    ms_temporal_bwd_data_kernel<<<grid, dim3(MS_THREADS), smem, st>>>(a, ms_geom_pack(a), h.h_bytes, h.w_bytes, h.tmem_cols, mp_lo, mp_hi);
+    if (smem > 100 * 1024) {                               // one CTA per SM anyway: give it 16 warps
+        cudaFuncSetAttribute(ms_temporal_bwd_data_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        ms_temporal_bwd_data_kernel<512><<<grid, dim3(512), smem, st>>>(a, ms_geom_pack(a), h.h_bytes, h.w_bytes, h.tmem_cols, mp_lo, mp_hi);
+    } else {
+        cudaFuncSetAttribute(ms_temporal_bwd_data_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        ms_temporal_bwd_data_kernel<256><<<grid, dim3(256), smem, st>>>(a, ms_geom_pack(a), h.h_bytes, h.w_bytes, h.tmem_cols, mp_lo, mp_hi);
+    }
     return dsg_launch_error();
 }
 
