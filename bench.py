@@ -342,9 +342,11 @@ def main():
     # ---- roofline leg: per-ABI-call CUDA events over extra eager steps (same shapes), dominant kernel.
     #      Every rank runs the steps (they contain the gradient all-reduce); only rank 0 reports.
     L.profile = []
+    side_was, L.side_enabled = L.side_enabled, False     # per-call events must not time kernels that overlap a side-stream kernel
     for i in range(2):
         device_step(dev_x[i % 2], dev_y[i % 2])
     torch.cuda.synchronize()
+    L.side_enabled = side_was
     prof, L.profile = L.profile, None
     if world > 1:
         torch.distributed.barrier()
