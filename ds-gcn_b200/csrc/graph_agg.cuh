@@ -345,8 +345,9 @@ __global__ void __launch_bounds__(AG_THREADS) agg_static_kernel(dsg_graph_agg_ar
 // dadyn[n,u,w,kc] = sum_t p[n,t,u,kc] * dy[n,t,w,kc]: both operands staged per AG_TCH frames (vector loads, fp32,
 // channel fastest); a warp owns target joints w, w+8, ..., w+24 and keeps their 25 source-joint accumulators in registers.
 constexpr int DA_TCH = AG_TCH;
-template <class T, int V>
-__global__ void __launch_bounds__(AG_THREADS) agg_dadj_dyn_kernel(dsg_graph_agg_dadj_args a, int vec) {
+constexpr int DA_THREADS = 1024;  // 32 warps, one target joint each (25 accumulators per thread)
+template <class T, int V, int NT>
+__global__ void __launch_bounds__(NT, 1) agg_dadj_dyn_kernel(dsg_graph_agg_dadj_args a, int vec) {
     DSG_DYN_SMEM(smem_raw);
     float* ps = reinterpret_cast<float*>(smem_raw);        // [DA_TCH][V][32]
     float* ds = ps + DA_TCH * V * 32;                      // [DA_TCH][V][32]
@@ -355,7 +356,7 @@ __global__ void __launch_bounds__(AG_THREADS) agg_dadj_dyn_kernel(dsg_graph_agg_
     const int n = blockIdx.x, kc0 = blockIdx.y * 32;
     agg_stage_coefs(a.p, kc0, a.KC, cf_p);
     agg_stage_coefs(a.dy, kc0, a.KC, cf_d);
-    constexpr int NW = AG_THREADS / 32;
+    constexpr int NW = NT / 32;
     constexpr int WPW = (V + NW - 1) / NW;                 // target joints per warp
     float acc[WPW][V];
 #pragma unroll
@@ -364,7 +365,7 @@ __global__ void __launch_bounds__(AG_THREADS) agg_dadj_dyn_kernel(dsg_graph_agg_
         for (int u = 0; u < V; ++u) acc[i][u] = 0.f;
     for (int t0 = 0; t0 < a.T; t0 += DA_TCH) {
         __syncthreads();
-        for (int idx = tid; idx < DA_TCH * V * 4; idx += AG_THREADS) {
+        for (int idx = tid; idx < DA_TCH * V * 4; idx += NT) {
             const int q = idx & 3, rv = idx >> 2;
             const int tt = rv / V;
             float pv[8], dv[8];
@@ -468,8 +469,8 @@ template <class T> static const char* launch_agg(const dsg_graph_agg_args& a, ds
 template <class T, int V> static const char* launch_dadj_v(const dsg_graph_agg_dadj_args& a, dsg_stream_t st) {
     size_t smem = (size_t)2 * DA_TCH * V * 32 * sizeof(float);
     int vec = (sizeof(T) == 2) && act8_ok(a.p) && act8_ok(a.dy) ? 1 : 0;
-    DSG_SET_SMEM((agg_dadj_dyn_kernel<T, V>), smem);
-    dsg_launch(agg_dadj_dyn_kernel<T, V>, dim3(a.n_samples, (a.KC + 31) / 32), dim3(AG_THREADS), smem, st, a, vec);
+    DSG_SET_SMEM((agg_dadj_dyn_kernel<T, V, DA_THREADS>), smem);
+    dsg_launch((agg_dadj_dyn_kernel<T, V, DA_THREADS>), dim3(a.n_samples, (a.KC + 31) / 32), dim3(DA_THREADS), smem, st, a, vec);
     return dsg_launch_error();
 }
 
