@@ -93,7 +93,6 @@ template <> DSG_D void agg_load8_s<bf16>(const ActSrc& s, long long row, int c0,
 }
 
 constexpr int AG_TCH = 8;      // frames staged per step
-constexpr int AG_WB = 1;       // joints contracted together by a warp (adjacency columns in registers)
 constexpr int AG_DYN_THREADS = 512;
 
 // Dynamic contraction: the per-sample adjacency slice (32 channels) and AG_TCH frames of the operand live in shared
@@ -444,10 +443,16 @@ template <class T, int V> static const char* launch_agg_v(const dsg_graph_agg_ar
     if (a.mode <= 1) {
         size_t smem = (size_t)(V * V + AG_TCH * V) * 32 * sizeof(float);
         int vec = (sizeof(T) == 2) && act8_ok(a.src) ? 1 : 0;
-        // 512 threads, one joint per warp pass: 59 registers, so the two CTAs that fit an SM's shared memory bring 32 warps
-        // (measured 4.35 -> 3.55 ms per step against 256 threads x two joints per pass at 103 registers = 16 warps)
-        DSG_SET_SMEM((agg_dyn_kernel<T, V, AG_DYN_THREADS, AG_WB>), smem);
-        dsg_launch((agg_dyn_kernel<T, V, AG_DYN_THREADS, AG_WB>), grid, dim3(AG_DYN_THREADS), smem, st, a, t_chunk, vec);
+        if (a.has_mask || a.stat_sum) {
+            // backward-type calls (mask / partner loads per output): 512 threads, one joint per warp pass: 59 registers, so the
+            // two CTAs that fit an SM's shared memory bring 32 warps (measured 4.35 -> 3.55 ms per training step)
+            DSG_SET_SMEM((agg_dyn_kernel<T, V, AG_DYN_THREADS, 1>), smem);
+            dsg_launch((agg_dyn_kernel<T, V, AG_DYN_THREADS, 1>), grid, dim3(AG_DYN_THREADS), smem, st, a, t_chunk, vec);
+        } else {
+            // plain forward contraction: 256 threads, two joints per warp pass (one shared load feeds two FMAs)
+            DSG_SET_SMEM((agg_dyn_kernel<T, V, AG_THREADS, 2>), smem);
+            dsg_launch((agg_dyn_kernel<T, V, AG_THREADS, 2>), grid, dim3(AG_THREADS), smem, st, a, t_chunk, vec);
+        }
     } else {
         if (a.mode == 3 && a.stat_sum) return "graph_agg: statistics are not supported in mode 3";
         size_t smem = (size_t)a.Ksub * V * V * sizeof(float);
