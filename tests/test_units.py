@@ -6,7 +6,6 @@ parameter gradient (and which parameters get *no* gradient), BatchNorm running s
 Tolerances (north_star): fp32 rel 1e-4 (rel-L2 per tensor), bf16 rel-L2 1e-2 (gradients 6e-2: they chain
 several bf16-rounded activations).
 """
-import numpy as np
 import pytest
 import torch
 
