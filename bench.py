@@ -10,9 +10,9 @@ reference's DDP (broadcast_buffers=False, no SyncBN).
 
 Printed JSON line: see DESIGN.md "Measurement".  `value` = device-resident inputs, CUDA-graph replay;
 `e2e` = the public API (RecognizerGCN.train_step / forward) with host buffers: H2D of the batch from pinned memory and
-D2H of the loss inside the timed region.  `--impl reference` times the oracle port of the reference's CPU path
-(the reference itself is Python and cannot travel to the GPU box; oracle/ is the checker restatement) on a bounded
-sample, all host threads.
+D2H of the loss inside the timed region.  `--impl reference` times the UNMODIFIED reference (imported by path from
+/root/reference, or from baseline/_ref = tools/install_ref.py copies on the GPU box) on the host cores at N=16 clips per
+step, all host threads; `cpu_baseline` in the product line is the same thing on a shorter sample.
 """
 import argparse
 import json
@@ -50,15 +50,96 @@ def parse():
     p.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
     p.add_argument("--no-graph", action="store_true")
     p.add_argument("--no-cpu-baseline", action="store_true")
-    p.add_argument("--ref-clips", type=int, default=4, help="clips per step of the CPU reference arm (bounded sample)")
+    p.add_argument("--ref-clips", type=int, default=REF_CLIPS, help="clips per step of the CPU reference arm (N=16: SURVEY 8d)")
+    p.add_argument("--ref-budget", type=float, default=240.0, help="seconds the whole reference run may take (the batch shrinks to fit)")
+    p.add_argument("--no-ref-gpu", action="store_true", help="skip the reference-eager-on-this-GPU context number")
     return p.parse_args()
 
 
 # ----------------------------------------------------------------------------------------------------------------
-# CPU arm: the oracle port of the reference path (test infrastructure; the only place bench.py executes oracle/)
+# Reference arm: the UNMODIFIED reference (pyskl DGSTGCN, imported by path from /root/reference or, on the GPU box, from
+# baseline/_ref = byte-identical copies made by tools/install_ref.py) on the box's host cores.  oracle/ref_loader.py only
+# stubs the mmcv names those files import; none of this repo's models or kernels are on this path.  If no reference tree
+# is present the oracle port is timed instead and the line says kind "port".
 # ----------------------------------------------------------------------------------------------------------------
 
+REF_CLIPS = 16          # SURVEY.md §8(d) / BASELINE.md §4: N=16 for the CPU point
+
+
+def _reference_model(device):
+    """(backbone, head, params) of the unmodified reference, north-star config, reference default init + live dynamic branches."""
+    from oracle import ref_loader as RL
+    if not RL.available():
+        return None
+    ns = RL.load()
+    torch.manual_seed(0)
+    np.random.seed(0)
+    backbone = ns.DGSTGCN(**RL.NORTH_STAR_BACKBONE)
+    head = torch.nn.Linear(256, NUM_CLASSES)           # GCNHead.fc_cls (heads/simple_head.py:83-97): pool(T,V), mean(M), Linear
+    torch.nn.init.normal_(head.weight, 0, 0.01)
+    torch.nn.init.constant_(head.bias, 0)
+    with torch.no_grad():
+        for n_, p in backbone.named_parameters():
+            if n_.rsplit(".", 1)[-1] in ("alpha", "beta", "add_coeff"):
+                p.normal_(0, 0.1)
+    return backbone.to(device), head.to(device), RL.REF_ROOT
+
+
+def reference_arm(mode, clips, steps, warmup, device="cpu", budget_s=None):
+    """Times `steps` steps of the reference itself after `warmup`; returns (clips/s, s/step, clips, description) or None."""
+    built = _reference_model(device)
+    if built is None:
+        return None
+    backbone, head, root = built
+    if device == "cpu":
+        torch.set_num_threads(os.cpu_count())
+    train = mode == "train"
+    backbone.train(train)
+    params = [p for n_, p in backbone.named_parameters() if "conv2_se" not in n_] + list(head.parameters())
+    opt = torch.optim.SGD(params, **SGD) if train else None
+
+    def make(n):
+        g = torch.Generator().manual_seed(0)
+        return (torch.randn(n, M_, T_, V_, C_, generator=g).to(device), torch.randint(0, NUM_CLASSES, (n,), generator=g).to(device))
+
+    def step(x, y):
+        if not train:
+            with torch.no_grad():
+                return head(backbone(x).mean((3, 4)).mean(1))
+        feat = backbone(x)
+        loss = torch.nn.functional.cross_entropy(head(feat.mean((3, 4)).mean(1)), y)
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        opt.step()
+        return loss
+
+    def sync():
+        if device != "cpu":
+            torch.cuda.synchronize()
+
+    x, y = make(clips)
+    t0 = time.perf_counter()
+    step(x, y)
+    sync()
+    t1 = time.perf_counter() - t0
+    if budget_s is not None and t1 * (steps + warmup) > budget_s and clips > 2:      # bounded sample: shrink the batch, not the step count
+        clips = max(2, int(clips * budget_s / (t1 * (steps + warmup))))
+        x, y = make(clips)
+    for _ in range(max(warmup - 1, 0)):
+        step(x, y)
+    sync()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step(x, y)
+    sync()
+    dt = (time.perf_counter() - t0) / steps
+    what = (f"unmodified reference DGSTGCN ({root}) + Linear head, {mode}, {clips} clips/step x {steps} steps after {warmup} warm-up, "
+            f"fp32, torch {torch.__version__} {device}")
+    return clips / dt, dt, clips, what
+
+
 def cpu_reference(mode, clips, steps, warmup):
+    """Oracle port (only used when no reference tree is present)."""
     from oracle import dsgcn_oracle as O
     torch.set_num_threads(os.cpu_count())
     torch.manual_seed(0)
@@ -95,6 +176,24 @@ def cpu_reference(mode, clips, steps, warmup):
         step()
     dt = (time.perf_counter() - t0) / steps
     return clips / dt, dt
+
+
+def cpu_baseline_leg(mode, clips, steps, warmup, budget_s=None):
+    """dict for the `cpu_baseline` key: the reference itself when a reference tree is present, else the oracle port."""
+    unit = "clips/s"
+    try:
+        r = reference_arm(mode, clips, steps, warmup, "cpu", budget_s)
+    except Exception as e:                       # never lose the GPU line to the baseline leg
+        print(f"[bench] reference arm failed ({type(e).__name__}: {str(e)[:200]}); timing the oracle port", file=sys.stderr)
+        r = None
+    if r is not None:
+        val, dt, n, what = r
+        return dict(value=val, unit=unit, cores=os.cpu_count(), kind="reference", sample=what, clips_per_step=n, ms_per_step=dt * 1e3,
+                    dtype="f32", note="reference = fp32 on host cores at N=16 (SURVEY 8d); product arm = bf16 at 128 clips/GPU")
+    n = min(clips, 4)
+    val, dt = cpu_reference(mode, n, steps, warmup)
+    return dict(value=val, unit=unit, cores=os.cpu_count(), kind="port", clips_per_step=n, ms_per_step=dt * 1e3, dtype="f32",
+                sample=f"no reference tree present: oracle port of the reference path ({mode}), {n} clips/step x {steps} steps, torch {torch.__version__} CPU")
 
 
 def _oracle_state(O):
@@ -189,13 +288,13 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        val, dt = cpu_reference(args.mode, args.ref_clips, args.steps, args.warmup)
+        cb = cpu_baseline_leg(args.mode, args.ref_clips, args.steps, args.warmup, budget_s=args.ref_budget)
+        val, dt = cb["value"], cb["ms_per_step"] * 1e-3
         line = dict(impl="reference", metric=metric, value=val, unit=unit, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
                     ms_per_step=dt * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
-                    config=dict(workload=workload, clips_per_step=args.ref_clips, device="cpu"),
-                    cpu_baseline=dict(value=val, unit=unit, cores=os.cpu_count(), kind="port",
-                                      sample=f"{args.ref_clips} clips/step x {args.steps} steps, oracle port of the reference CPU path, torch {torch.__version__}"),
-                    e2e=dict(value=val, unit=unit, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+                    config=dict(workload=workload, clips_per_step=cb["clips_per_step"], M=M_, T=T_, V=V_, C=C_, device="cpu",
+                                note="reference's own CPU implementation: fp32, N=16 clips/step (SURVEY 8d); the product arm runs bf16 at 128 clips/GPU"),
+                    cpu_baseline=cb, e2e=dict(value=val, unit=unit, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
         print(json.dumps(line))
         return
 
@@ -395,16 +494,25 @@ def main():
                     per_kernel_gbs={k: round(v[1] / (v[0] * 1e-3) / 1e9, 1) for k, v in agg.items() if v[1] > 0 and v[0] > 0},
                     step_algorithmic_gbs=ELEMS_PER_CLIP_FWD * (3 if train else 1) * (2 if dtype == torch.bfloat16 else 4) * B / (ms * 1e-3) / 1e9)
     cpu = None
+    extra = {}
     if not args.no_cpu_baseline:
-        cval, cdt = cpu_reference(args.mode, args.ref_clips, 3, 1)
-        cpu = dict(value=cval, unit=unit, cores=os.cpu_count(), kind="port",
-                   sample=f"{args.ref_clips} clips/step, 3 steps after 1 warm-up, oracle port of the reference path ({args.mode}), torch {torch.__version__} CPU")
+        cpu = cpu_baseline_leg(args.mode, args.ref_clips, 2, 1, budget_s=40.0)
+    if not args.no_ref_gpu and world == 1:
+        # context only (never a denominator): the unmodified reference run eagerly on this GPU, same batch as the product arm
+        try:
+            del model, opt
+            torch.cuda.empty_cache()
+            r = reference_arm(args.mode, B, 3, 2, device=f"cuda:{local}")
+            if r is not None:
+                extra["reference_gpu_eager"] = dict(value=r[0], unit=unit, ms_per_step=r[1] * 1e3, clips_per_step=r[2], sample=r[3])
+        except Exception as e:
+            extra["reference_gpu_eager"] = dict(unavailable=f"{type(e).__name__}: {str(e)[:200]}")
     line = dict(metric=metric, value=value, unit=unit, n_gpus=world, steps=args.steps, warmup=args.warmup, ms_per_step=ms,
                 higher_is_better=True, scaling="weak", vs_baseline=None, dtype=args.dtype, data="synthetic",
                 config=dict(workload=workload, clips_per_gpu=B, M=M_, T=T_, V=V_, C=C_, parallelism=f"dp{world}", cuda_graph=graph is not None,
                             cache="inputs + activations per step (~GBs) exceed the 126 MB L2; two input batches alternate"),
                 e2e=dict(value=world * B / (e2e_ms * 1e-3), unit=unit, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, ms_per_step=e2e_ms),
-                gpu_launches=launches_per_step * args.steps, abi_calls_per_step=launches_per_step, kernels_per_step_ncu=own_kernels, clocks=clocks, roofline=roofline, cpu_baseline=cpu)
+                gpu_launches=launches_per_step * args.steps, abi_calls_per_step=launches_per_step, kernels_per_step_ncu=own_kernels, clocks=clocks, roofline=roofline, cpu_baseline=cpu, extra=extra)
     print(json.dumps(line))
 
 

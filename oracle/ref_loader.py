@@ -3,8 +3,10 @@
 against them and golden vectors can be generated (tests/golden/make_golden.py).
 
 Nothing in the product package imports this file.  /root/reference does not
-exist on the GPU box, so nothing here may be used by `-m gpu` tests, smoke() or
-bench.py at run time; `available()` says whether the reference tree is mounted.
+exist on the GPU box; there the loader falls back to baseline/_ref/ — byte-identical
+copies of the same files made by tools/install_ref.py (git-ignored, shipped with the
+gpurun snapshot) — which is what bench.py's reference arm times.  `available()` says
+whether either tree is present.
 
 The reference imports mmcv (absent) and three junk modules (tkinter, turtle,
 matplotlib: pyskl/models/gcns/utils/gcn.py:5-9).  We register tiny stand-ins in
@@ -18,13 +20,25 @@ import types
 
 import torch.nn as nn
 
-REF_ROOT = os.environ.get("DSGCN_REFERENCE_ROOT", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_PROBE = "pyskl/models/gcns/dgstgcn.py"
+
+
+def _find_root():
+    cands = [os.environ.get("DSGCN_REFERENCE_ROOT"), "/root/reference", os.path.join(os.path.dirname(_HERE), "baseline", "_ref")]
+    for c in cands:
+        if c and os.path.isfile(os.path.join(c, _PROBE)):
+            return c
+    return cands[0] or "/root/reference"
+
+
+REF_ROOT = _find_root()
 _PKG = "refpyskl"
 _loaded = {}
 
 
 def available():
-    return os.path.isfile(os.path.join(REF_ROOT, "pyskl/models/gcns/dgstgcn.py"))
+    return os.path.isfile(os.path.join(REF_ROOT, _PROBE))
 
 
 def _mod(name, **attrs):

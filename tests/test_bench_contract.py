@@ -1,4 +1,5 @@
-"""bench.py contract on a machine without a GPU: the reference arm (CPU, oracle port of the reference path) prints one
+"""bench.py contract on a machine without a GPU: the reference arm (CPU: the unmodified reference when a reference tree is
+present — /root/reference or baseline/_ref — else the oracle port) prints one
 JSON line with the driver's keys; the product arm refuses to run without a CUDA device (there is no CPU fallback)."""
 import json
 import os
@@ -24,7 +25,12 @@ def test_reference_arm_json_line():
     assert line["impl"] == "reference" and line["unit"] == "clips/s" and line["higher_is_better"] is True
     assert line["value"] > 0 and line["vs_baseline"] is None and line["data"] == "synthetic"
     assert "workload" in line["config"]
-    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1 and line["cpu_baseline"]["value"] == line["value"]
+    sys.path.insert(0, ROOT)
+    from oracle import ref_loader
+    want = "reference" if ref_loader.available() else "port"
+    assert line["cpu_baseline"]["kind"] == want and line["cpu_baseline"]["cores"] >= 1 and line["cpu_baseline"]["value"] == line["value"]
+    if want == "reference":
+        assert "unmodified reference" in line["cpu_baseline"]["sample"]
     assert line["e2e"] == dict(value=line["value"], unit="clips/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0)
 
 
