@@ -67,11 +67,21 @@ def _empty32(n, dev):
     return torch.empty(n, dtype=torch.float32, device=dev)
 
 
-class BNCoef:
-    """Per-channel coefficient arrays for a (possibly concatenated) set of BatchNorms over `C` channels."""
+def bn_uses_batch_stats(bn):
+    """nn.BatchNorm semantics (torch/nn/modules/batchnorm.py): batch statistics iff the BatchNorm ITSELF is in training mode or keeps
+    no running estimates — the flags of the real child module decide, not the parent unit's (frozen-BN fine-tuning calls
+    bn.eval() on individual layers)."""
+    return bn.training or bn.running_mean is None
 
-    def __init__(self, C, dev, training):
+
+class BNCoef:
+    """Per-channel coefficient arrays for a (possibly concatenated) set of BatchNorms over `C` channels.
+    `bns`: the BatchNorm modules whose channels the buffer covers (statistics are accumulated iff any of them needs them)."""
+
+    def __init__(self, C, dev, bns):
+        training = any(bn_uses_batch_stats(b) for b in bns)
         self.C, self.dev, self.training = C, dev, training
+        self.batch = {}                  # (lo, hi) -> this slice normalised with batch statistics
         self.a, self.b = _empty32(C, dev), _empty32(C, dev)
         self.mean, self.invstd = _empty32(C, dev), _empty32(C, dev)
         self.stats = torch.zeros(2, C, dtype=torch.float64, device=dev) if training else None
@@ -87,14 +97,18 @@ class BNCoef:
 
     def add_bn(self, bn, lo, hi, count):
         """forward job for nn.BatchNorm2d `bn` on channels [lo,hi)"""
-        use_batch = self.training
+        use_batch = bn_uses_batch_stats(bn)
+        self.batch[(lo, hi)] = use_batch
         sl = slice(lo, hi)
         if use_batch:
+            if bn.momentum is None and bn.running_mean is not None:
+                raise NotImplementedError("BatchNorm momentum=None (cumulative moving average) is not built; the DS-GCN configs use 0.1")
             self.jobs.append(ops.bn_job(0, hi - lo, sum=self.stats[0, sl], sq=self.stats[1, sl], count=count, gamma=bn.weight,
                                         beta=bn.bias, running_mean=bn.running_mean, running_var=bn.running_var,
                                         save_mean=self.mean[sl], save_invstd=self.invstd[sl], a=self.a[sl], b=self.b[sl],
                                         momentum=bn.momentum if bn.momentum is not None else 0.1, eps=bn.eps))
-            _Pending.add(bn)
+            if bn.running_mean is not None:
+                _Pending.add(bn)
         else:
             self.jobs.append(ops.bn_job(1, hi - lo, gamma=bn.weight, beta=bn.bias, running_mean=bn.running_mean,
                                         running_var=bn.running_var, save_mean=self.mean[sl], save_invstd=self.invstd[sl],
@@ -131,7 +145,7 @@ class BNBack:
         sl = slice(lo, hi)
         dg, db = torch.empty_like(bn.weight), torch.empty_like(bn.bias)
         grads[bn.weight], grads[bn.bias] = dg, db
-        self.jobs.append(ops.bn_job(2 if self.fwd.training else 3, hi - lo, sum=self.stats[0, sl], sq=self.stats[1, sl], count=count,
+        self.jobs.append(ops.bn_job(2 if self.fwd.batch[(lo, hi)] else 3, hi - lo, sum=self.stats[0, sl], sq=self.stats[1, sl], count=count,
                                     gamma=bn.weight, save_mean=self.fwd.mean[sl], save_invstd=self.fwd.invstd[sl],
                                     a=self.ca[sl], b=self.cb[sl], c=self.cc[sl], dgamma=dg, dbeta=db))
 
@@ -147,10 +161,6 @@ class BNBack:
         """activation source for dy = ca*e + cb*y + cc on channels [lo,hi) (e, y already sliced)"""
         sl = slice(lo, hi)
         return Act(e, self.ca[sl], self.cc[sl], y, self.cb[sl])
-
-
-def _bn_train(module_training, bn):
-    return module_training or not bn.track_running_stats
 
 
 # ------------------------------------------------------------------------------------------------
@@ -187,7 +197,7 @@ def dgphgcn1_forward(m, x, n, T, V, save):
     else:
         Wpd, bpd = m.pre[0].weight.view(KC, Cin), m.pre[0].bias
     PD = torch.empty(rows, Npd, dtype=dt, device=dev)
-    c_pd = BNCoef(Npd, dev, training)
+    c_pd = BNCoef(Npd, dev, [m.pre[1]] + ([m.down[1]] if has_down else []))
     ops.conv_gemm(x, Wpd, Npd, PD, n_samples=n, T_in=T, T_out=T, Vin=V, bias=bpd, stat_sum=c_pd.ssum, stat_sq=c_pd.ssq)
     c_pd.add_bn(m.pre[1], 0, KC, rows)
     if has_down:
@@ -201,7 +211,7 @@ def dgphgcn1_forward(m, x, n, T, V, save):
 
     # ---- post conv, BatchNorm statistics in the epilogue
     Z = torch.empty(rows, Cout, dtype=dt, device=dev)
-    c_z = BNCoef(Cout, dev, training)
+    c_z = BNCoef(Cout, dev, [m.bn])
     ops.conv_gemm(Y, m.post.weight.view(Cout, KC), Cout, Z, n_samples=n, T_in=T, T_out=T, Vin=V, bias=m.post.bias,
                   stat_sum=c_z.ssum, stat_sq=c_z.ssq)
     c_z.add_bn(m.bn, 0, Cout, rows)
@@ -377,7 +387,7 @@ def mstcn_forward(m, g, n, T, V, save, res=None, final_relu=False):
     bbr = torch.cat([c.bias for c in convs])
     rows_b = n * T * Vp
     B = torch.empty(rows_b, Ct, dtype=dt, device=dev)
-    c_b = BNCoef(Ct, dev, training)
+    c_b = BNCoef(Ct, dev, [m.branches[j][1] for j, (kind, *_) in enumerate(layout) if kind != "1x1"])
     ops.conv_gemm(g, Wbr, Ct, B, n_samples=n, T_in=T, T_out=T, Vin=V, ext_in=has_ext, bias=bbr, stat_sum=c_b.ssum, stat_sq=c_b.ssq)
     for j, (kind, lo, hi, _) in enumerate(layout):
         if kind == "1x1":
@@ -389,7 +399,7 @@ def mstcn_forward(m, g, n, T, V, save, res=None, final_relu=False):
     rows_o, rows_f = n * T_out * Vp, n * T_out * V
     feat = torch.empty(rows_f, Ct, dtype=dt, device=dev)
     oglob = torch.empty(n * T_out, Ct, dtype=torch.float32, device=dev) if has_ext else None
-    c_t = BNCoef(Ct, dev, training)
+    c_t = BNCoef(Ct, dev, [m.transform[0]])
     add_coeff = m.add_coeff if has_ext else None
     if has_ext and add_coeff.numel() < V:
         raise ValueError("add_coeff is shorter than the number of joints")
@@ -416,7 +426,7 @@ def mstcn_forward(m, g, n, T, V, save, res=None, final_relu=False):
 
     # ---- transform conv + final BatchNorm (+ residual, ReLU)
     U = torch.empty(rows_f, Cout, dtype=dt, device=dev)
-    c_u = BNCoef(Cout, dev, training)
+    c_u = BNCoef(Cout, dev, [m.bn])
     ops.conv_gemm(Act(feat, c_t.a, c_t.b, relu=True), m.transform[2].weight.view(Cout, Ct), Cout, U, n_samples=n, T_in=T_out,
                   T_out=T_out, Vin=V, bias=m.transform[2].bias, stat_sum=c_u.ssum, stat_sq=c_u.ssq)
     c_u.add_bn(m.bn, 0, Cout, rows_f)
@@ -535,7 +545,7 @@ def unit_tcn_raw_forward(m, x, n, T, V, save):
     rows = n * T_out * V
     Rr = torch.empty(rows, Cout, dtype=dt, device=dev)
     has_bn = isinstance(m.bn, torch.nn.modules.batchnorm._BatchNorm)
-    c_r = BNCoef(Cout, dev, m.training) if has_bn else None
+    c_r = BNCoef(Cout, dev, [m.bn]) if has_bn else None
     ops.conv_gemm(x, m.conv.weight, Cout, Rr, n_samples=n, T_in=T, T_out=T_out, Vin=V, bias=m.conv.bias, taps=k, tap_step=d,
                   tap_off=-pad, t_mul=s, stat_sum=c_r.ssum if has_bn else None, stat_sq=c_r.ssq if has_bn else None)
     if has_bn:
@@ -623,12 +633,12 @@ def unit_gcn_forward(m, x, n, T, V, save):
     D = None
     if has_down:
         D = torch.empty(rows, Cout, dtype=dt, device=dev)
-        c_d = BNCoef(Cout, dev, training)
+        c_d = BNCoef(Cout, dev, [m.down[1]])
         ops.conv_gemm(x, m.down[0].weight, Cout, D, n_samples=n, T_in=T, T_out=T, Vin=V, bias=m.down[0].bias,
                       stat_sum=c_d.ssum, stat_sq=c_d.ssq)
         c_d.add_bn(m.down[1], 0, Cout, rows)
         c_d.run()
-    c_z = BNCoef(Cout, dev, training)
+    c_z = BNCoef(Cout, dev, [m.bn])
     Z = torch.empty(rows, Cout, dtype=dt, device=dev)
     if m.conv_pos == "pre":
         mid = torch.empty(rows, K * Cout, dtype=dt, device=dev)

@@ -468,8 +468,8 @@ class _DataBNFn(torch.autograd.Function):
         xin = x.detach().contiguous().view(N * M * T, V * C)
         if xin.dtype != torch.float32:
             xin = xin.float()
-        coef = Fn.BNCoef(V * C, dev, bn.training)
-        if bn.training:
+        coef = Fn.BNCoef(V * C, dev, [bn])
+        if coef.training:
             ops.pointwise(xin, None, stat_sum=coef.ssum, stat_sq=coef.ssq)
         coef.add_bn(bn, 0, V * C, N * M * T)
         coef.run()

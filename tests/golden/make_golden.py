@@ -20,6 +20,14 @@ SMALL = dict(base_channels=16, gcn_ratio=0.25)   # small-width copy of the north
 def main():
     ns = rl.load()
     torch.set_num_threads(4)
+    only_new = "--only-new" in sys.argv       # keep committed fixtures byte-identical, add the missing ones
+    _savez = np.savez_compressed
+
+    def savez(path, **kw):
+        if only_new and os.path.exists(path):
+            return
+        _savez(path, **kw)
+    np.savez_compressed = savez
     # 1. graph tables (integers must be bit-exact)
     tabs = {}
     for layout in ("nturgb+d", "coco", "openpose"):
@@ -89,6 +97,29 @@ def main():
     for k, v in blk.state_dict().items():
         ob["sd|" + k] = v.numpy().astype(np.float16 if v.dim() >= 2 and v.numel() > 20000 else v.numpy().dtype)
     np.savez_compressed(os.path.join(HERE, "dgblock_256.npz"), **ob)
+    # 5. config 5: small-width ST-GCN++ (configs/stgcn++/STGCN++_model.py:1-9) and vanilla ST-GCN (k=9 unit_tcn), fwd + bwd
+    for name, kw in (("stgcnpp", dict(gcn_adaptive="init", gcn_with_res=True, tcn_type="mstcn", graph_cfg=dict(layout="nturgb+d", mode="spatial"))),
+                     ("stgcn", dict(graph_cfg=dict(layout="coco", mode="stgcn_spatial")))):
+        torch.manual_seed(6)
+        ms = ns.STGCN(base_channels=12, **kw)
+        sd = ms.state_dict(); O.randomize_state(sd, 7); ms.load_state_dict(sd)
+        V = ms.gcn[0].gcn.A.shape[-1]
+        xs = torch.randn(2, 2, 12, V, 3)
+        og = {"x": xs.numpy()}
+        for k, v in ms.state_dict().items():
+            og["sd|" + k] = v.numpy().copy()
+        ms.eval()
+        with torch.no_grad():
+            og["y_eval"] = ms(xs).numpy()
+        ms.train()
+        y = ms(xs)
+        gy = torch.randn(y.shape, generator=torch.Generator().manual_seed(8))
+        y.backward(gy)
+        og["y_train"], og["gy"] = y.detach().numpy(), gy.numpy()
+        for k, p in ms.named_parameters():
+            if p.grad is not None and (k.startswith("gcn.0.") or k.startswith("gcn.4.") or k.startswith("gcn.8.gcn") or k.startswith("data_bn")):
+                og["grad|" + k] = p.grad.numpy().copy()
+        np.savez_compressed(os.path.join(HERE, f"{name}_small.npz"), **og)
     for f in os.listdir(HERE):
         print(f, os.path.getsize(os.path.join(HERE, f)))
 

@@ -185,3 +185,84 @@ def test_dgblock(dev, dtype, cin, cout, stride, residual):
     kind = "none" if not residual else ("identity" if cin == cout and stride == 1 else "conv")
     fn = lambda xx, sd, tr: O.dgblock_forward(xx, sd, nt.tolist(), et.numpy(), stride, kind, training=tr)
     check_unit(m, fn, x, dtype, dev, True, grad_tol_scale=2.0)
+
+
+# ---- BatchNorm mode is decided per child BatchNorm (nn.BatchNorm semantics), not by the parent unit's flag -----------------
+def test_frozen_child_bn_unit_tcn(dev):
+    """unit.train() with unit.bn.eval(): running statistics are used and not updated (frozen-BN fine-tuning)."""
+    torch.manual_seed(5)
+    m = M.unit_tcn(10, 14, kernel_size=3, stride=1)
+    randomize(m, 6)
+    ref_conv = torch.nn.Conv2d(10, 14, (3, 1), padding=(1, 0))
+    ref_bn = torch.nn.BatchNorm2d(14)
+    ref_conv.load_state_dict(m.conv.state_dict()); ref_bn.load_state_dict(m.bn.state_dict())
+    x = torch.randn(2, 10, 7, 17)
+    M.set_compute_dtype(torch.float32)
+    try:
+        m.train(); m.bn.eval()
+        ref_bn.eval()
+        xr = x.clone().requires_grad_()
+        yr = ref_bn(ref_conv(xr))
+        gy = torch.randn(yr.shape, generator=torch.Generator().manual_seed(1))
+        yr.backward(gy)
+        rm0 = m.bn.running_mean.clone()
+        m.to(dev)
+        xk = x.clone().to(dev).requires_grad_()
+        y = m(xk)
+        assert rel(y, yr) < 1e-4
+        y.backward(gy.to(dev))
+        assert rel(xk.grad, xr.grad) < 1e-4
+        assert rel(m.conv.weight.grad, ref_conv.weight.grad) < 1e-4 and rel(m.bn.weight.grad, ref_bn.weight.grad) < 1e-4
+        assert rel(m.conv.bias.grad, ref_conv.bias.grad) < 1e-4           # not zero: an eval-mode BN does not remove the mean
+        assert torch.equal(m.bn.running_mean.cpu(), rm0) and int(m.bn.num_batches_tracked) == 0
+        # the other way round: unit.eval() with a BatchNorm that keeps no running estimates uses batch statistics
+        m2 = M.unit_tcn(10, 14, kernel_size=3)
+        m2.bn = torch.nn.BatchNorm2d(14, track_running_stats=False)
+        m2.eval().to(dev)
+        r2 = torch.nn.BatchNorm2d(14, track_running_stats=False).eval()
+        c2 = torch.nn.Conv2d(10, 14, (3, 1), padding=(1, 0)); c2.load_state_dict({k: v.cpu() for k, v in m2.conv.state_dict().items()})
+        with torch.no_grad():
+            assert rel(m2(x.to(dev)), r2(c2(x))) < 1e-4
+        m3 = M.unit_tcn(10, 14, kernel_size=3)
+        m3.bn.momentum = None
+        with pytest.raises(NotImplementedError):
+            m3.train().to(dev)(x.to(dev))
+    finally:
+        M.set_compute_dtype(torch.bfloat16)
+
+
+def test_frozen_child_bn_vs_live_reference():
+    """A multi-BatchNorm unit (dgmstcn) with one branch BatchNorm and the final BatchNorm in eval mode, against the reference module."""
+    from oracle import ref_loader as rl
+    if not rl.available():
+        pytest.skip("no reference tree")
+    import sys, os
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "emu"))
+    import build_emu
+    dsgcn_b200._lib._testing_use_library(build_emu.build())
+    ns = rl.load()
+    torch.manual_seed(7)
+    r = ns.dgmstcn(24, 24, stride=1)
+    sd = r.state_dict(); O.randomize_state(sd, 8); r.load_state_dict(sd)
+    m = M.dgmstcn(24, 24, stride=1)
+    m.load_state_dict(sd)
+    for mod in (r, m):
+        mod.train()
+        mod.branches[1][1].eval(); mod.bn.eval()
+    x = torch.randn(2, 24, 9, 25)
+    M.set_compute_dtype(torch.float32)
+    try:
+        xr, xk = x.clone().requires_grad_(), x.clone().requires_grad_()
+        yr, y = r(xr), m(xk)
+        assert rel(y, yr) < 1e-4
+        gy = torch.randn(yr.shape, generator=torch.Generator().manual_seed(2))
+        yr.backward(gy); y.backward(gy)
+        assert rel(xk.grad, xr.grad) < 1e-4
+        pr = dict(r.named_parameters())
+        gmax = max(float(p.grad.norm()) for p in pr.values())
+        for k, p in m.named_parameters():       # analytically-zero bias gradients are rounding noise on both sides: absolute term
+            assert float((p.grad - pr[k].grad).norm()) < 2e-4 * float(pr[k].grad.norm()) + 1e-5 * gmax, k
+        for k, v in m.state_dict().items():
+            assert torch.allclose(v.float(), r.state_dict()[k].float(), rtol=1e-4, atol=1e-6), k
+    finally:
+        M.set_compute_dtype(torch.bfloat16)
