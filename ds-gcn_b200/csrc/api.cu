@@ -4,6 +4,7 @@
 #include "conv_gemm_tc.cuh"
 #include "conv_gemm_tc2.cuh"
 #include "conv_gemm_tc3.cuh"
+#include "tc4_gemm.cuh"
 #include "graph_agg.cuh"
 #include "ms_temporal_tc.cuh"
 #include "topology.cuh"
@@ -13,6 +14,7 @@
 #include <string.h>
 
 static thread_local char g_err[512] = "";
+static long long g_counters[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 
 static int fail(const char* where, const char* msg) {
     snprintf(g_err, sizeof(g_err), "%s: %s", where, msg);
@@ -42,6 +44,7 @@ static bool tc_enabled() {
 extern "C" {
 
 const char* dsg_last_error(void) { return g_err; }
+long long dsg_debug_counter(int id) { return (id >= 0 && id < 8) ? g_counters[id] : -1; }
 int dsg_abi_version(void) { return DSG_ABI_VERSION; }
 int dsg_is_device_build(void) {
 #ifdef DSG_EMU
@@ -62,7 +65,10 @@ int dsg_conv_gemm(const dsg_conv_gemm_args* a, void* stream) {
 #ifndef DSG_EMU
     if (a->dtype == DSG_BF16 && tc_enabled()) {      // tcgen05 engine (sm_100a); shapes it does not take fall through
         bool handled = false;
-        const char* e = tc3_enabled() ? dsg::tc::launch_conv_gemm_tc3(*a, (dsg_stream_t)stream, &handled) : nullptr;   // persistent pipelined engine
+        const char* e = dsg::tc4::launch_conv_gemm_tc4(*a, (dsg_stream_t)stream, &handled);                            // TMA-fed warp-specialised engine
+        if (e) return fail("dsg_conv_gemm", e);
+        if (handled) { ++g_counters[0]; return 0; }
+        e = tc3_enabled() ? dsg::tc::launch_conv_gemm_tc3(*a, (dsg_stream_t)stream, &handled) : nullptr;               // persistent pipelined engine
         if (e) return fail("dsg_conv_gemm", e);
         if (handled) return 0;
         e = tc2_enabled() ? dsg::tc::launch_conv_gemm_tc2(*a, (dsg_stream_t)stream, &handled) : nullptr;               // row-per-thread engine
@@ -82,7 +88,9 @@ long long dsg_conv_gemm_wpack_bytes(int K, int N) {
     (void)K; (void)N;
     return 0;
 #else
-    return (K > 0 && N > 0) ? dsg::tc::conv_wpack_bytes(K, N) : 0;
+    if (K <= 0 || N <= 0) return 0;
+    const long long a_ = dsg::tc::conv_wpack_bytes(K, N), b_ = dsg::tc4::tc4_wpack_bytes(K, N);
+    return a_ > b_ ? a_ : b_;
 #endif
 }
 

@@ -1,0 +1,622 @@
+// tc4: TMA-fed, warp-specialised, persistent tcgen05 engine of dsg_conv_gemm for the 1x1 convolutions (taps == 1, no frame
+// remap) — north-star kernels (a)/(c): "1x1 channel GEMM on tcgen05 tensor cores fed by TMA".
+//
+//   warp 0        TMA producer: one elected thread streams the A operand as SWIZZLE_128B atoms ([128 rows x 64 channels],
+//                 cp.async.bulk.tensor, S-stage mbarrier ring, 64-96 KB in flight per SM) and brings the CTA's packed weight
+//                 tile once (cp.async.bulk).  No thread ever touches an input row: out-of-bounds rows/channels are
+//                 zero-filled by the TMA unit.
+//   warp 1        MMA issuer: tcgen05.mma kind::f16 (M = 128, N <= 128) straight from the TMA-written atoms into one of two
+//                 TMEM accumulators; tcgen05.commit frees the stage / publishes the accumulator.  It also issues the
+//                 BatchNorm-statistics MMAs (below).
+//   warps 2-5     transform warps (only when the operand is not a plain tensor): BN-affine + ReLU prologue in place, the
+//                 joint-mean row of dgmstcn (tcn.py:409) or its gradient fold-back, then fence.proxy.async + arrive.
+//   warps 6-13    epilogue: thread = accumulator row.  tcgen05.ld, bias / addends / per-sample broadcast / ReLU mask, bf16 pack,
+//                 16-byte conflict-free stores into a SWIZZLE_128B out tile in shared memory; one thread then issues the TMA
+//                 store (boundary clipping by the TMA unit).
+//
+// Two algebraic moves keep CUDA cores off the data path:
+//  * BatchNorm-backward prologue dy = ca*e + cb*y + cc (dsg_act_src with two tensors, no ReLU) is folded into the GEMM:
+//    A = [e | y] (two tensor maps, K concatenated), W' = [diag(ca) W ; diag(cb) W], bias' = cc^T W — computed by the weight
+//    pack kernel in fp32 and rounded once to bf16; e and y go from HBM to the tensor core untouched.
+//  * BatchNorm statistics (sum v, sum v*partner) are column sums of the bf16 out tile and of a bf16 product tile the
+//    epilogue writes next to it: two tcgen05.mma per 16 rows with a constant "ones" B operand (A = tile, MN-major) accumulate
+//    them in 16 TMEM columns over all tiles of the CTA; one fp64 atomic per channel per CTA at the end.  (The shuffle
+//    transpose-reduce of the older engines cost ~150 instructions per 16 columns per thread.)
+#pragma once
+#include "tc4_common.cuh"
+
+#ifndef DSG_EMU
+namespace dsg {
+namespace tc4 {
+
+constexpr int G4_XF_WARPS = 4, G4_EPI_WARPS = 8;
+constexpr int G4_THREADS = 32 * (2 + G4_XF_WARPS + G4_EPI_WARPS);      // 448
+constexpr int G4_XF_T0 = 64, G4_EPI_T0 = 64 + 32 * G4_XF_WARPS;         // first thread of the transform / epilogue groups
+constexpr int G4_EPI_THREADS = 32 * G4_EPI_WARPS;                       // 256
+constexpr int G4_MAX_ATOMS = 12, G4_MAX_STAGES = 6;
+constexpr int G4_BAR_XF = 1, G4_BAR_EPI = 2;                            // named barriers
+
+struct G4Plan {
+    int mode;                    // 0: plain rows; 1: ext_in (joint-mean row appended per frame); 2: contract_ext (mean row folded back)
+    int V, slot, F;              // joints per frame (without the mean row), rows per frame slot in the tile (8-aligned), frames per tile
+    int n_tiles;
+    long long rows_out, n_frames;
+    int natoms, natoms1;         // A atoms per tile; atoms [0, natoms1) come from x1, the rest from x2
+    int ksteps[G4_MAX_ATOMS];    // K = 16 MMA steps per atom (live channels only)
+    int K1p;                     // natoms1 * 64
+    int Ntile, S, OB;            // output columns per CTA, A stages, out/stat buffers
+    int xf, act, has_stats;
+    unsigned off_w, off_a, off_out, off_stat, off_ones, off_cf;       // byte offsets from the 1024-aligned base
+    unsigned w_tile_bytes, out_bytes, smem_total;
+    int acc_cols, stat_col, tmem_cols;
+};
+
+// ---- packed weights: per column tile j, per atom a: [Ntile rows (n) x 64 k] bf16 in the K-major SWIZZLE_128B layout, scaled
+//      per k when a BatchNorm-backward / affine prologue is folded in; cbias[n] = bias[n] + sum_k (c1[k] + c2[k]) W[n,k]
+__global__ void __launch_bounds__(256) tc4_wpack_kernel(const float* W, long long ws_n, long long ws_k, int K, int N, int natoms1, int natoms,
+                                                        int Ntile, const float* s1, const float* s2, const float* c1, const float* c2,
+                                                        const float* bias, unsigned char* out, float* cbias) {
+    const int j = blockIdx.x, a = blockIdx.y;
+    if (a == natoms) {                                  // folded bias for this column tile
+        for (int nl = threadIdx.x; nl < Ntile; nl += 256) {
+            const int n = j * Ntile + nl;
+            if (n >= N) continue;
+            float acc = bias ? bias[n] : 0.f;
+            if (c1 || c2)
+                for (int k = 0; k < K; ++k) {
+                    const float c = (c1 ? c1[k] : 0.f) + (c2 ? c2[k] : 0.f);
+                    acc = fmaf(c, W[(long long)n * ws_n + (long long)k * ws_k], acc);
+                }
+            cbias[n] = acc;
+        }
+        return;
+    }
+    const bool second = a >= natoms1;
+    const int k0 = (second ? a - natoms1 : a) * ATOM_CH;
+    const float* sc = second ? s2 : s1;
+    unsigned char* dst = out + ((size_t)j * natoms + a) * (size_t)Ntile * 128;
+    for (int idx = threadIdx.x; idx < Ntile * 8; idx += 256) {
+        int nl, ch;
+        if (ws_k == 1) { ch = idx & 7; nl = idx >> 3; } else { nl = idx % Ntile; ch = idx / Ntile; }
+        const int n = j * Ntile + nl;
+        float v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int k = k0 + ch * 8 + e;
+            float w = (n < N && k < K) ? W[(long long)n * ws_n + (long long)k * ws_k] : 0.f;
+            if (sc && k < K) w *= sc[k];
+            v[e] = w;
+        }
+        *reinterpret_cast<uint4*>(dst + atom_off(nl, ch)) = pack8(v);
+    }
+}
+
+struct G4Bars {
+    uint64_t full[G4_MAX_STAGES], empty[G4_MAX_STAGES], ready[G4_MAX_STAGES];
+    uint64_t wbar, acc_full[2], acc_free[2], stat_ready[2], stat_done[2], out_free[2];
+};
+
+// XF: transform warps active; TAILS: any of add / add2 / bcast / mask / partner; STATS: BatchNorm statistics requested
+template <bool XF, bool TAILS, bool STATS>
+__global__ void __launch_bounds__(G4_THREADS, 1)
+tc4_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUtensorMap mapO,
+                const dsg_conv_gemm_args a, const G4Plan p, const float* __restrict__ cbias) {
+    DSG_DYN_SMEM(smem_raw);
+    __shared__ G4Bars bars;
+    __shared__ uint32_t tmem_base_s;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    unsigned char* sm = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    unsigned char* Wsm = sm + p.off_w;
+    unsigned char* Asm = sm + p.off_a;
+    unsigned char* Osm = sm + p.off_out;
+    unsigned char* Ssm = sm + p.off_stat;
+    unsigned char* ones = sm + p.off_ones;
+    float* tl_bias = reinterpret_cast<float*>(sm + p.off_cf);
+    float* tl_ma1 = tl_bias + 128;
+    float* tl_mb = tl_ma1 + 128;
+    float* tl_ma2 = tl_mb + 128;
+    float* cf_a = tl_ma2 + 128;                         // [K1p] prologue coefficients of x1 (act mode)
+    float* cf_b = cf_a + p.K1p;
+    const int n0 = blockIdx.y * p.Ntile;
+    const int Nt = a.N - n0 < p.Ntile ? a.N - n0 : p.Ntile;
+    const int Ntp = (Nt + 15) & ~15;
+    const int n_oatoms = (Ntp + ATOM_CH - 1) / ATOM_CH;
+
+    // ---- one-time setup
+    if (tid < 128) {
+        const int cch = n0 + tid;
+        const bool in = cch < a.N;
+        tl_bias[tid] = in ? cbias[cch] : 0.f;
+        tl_ma1[tid] = (in && a.has_mask && a.mask.a1) ? a.mask.a1[cch] : 1.f;
+        tl_mb[tid] = ((in && a.has_mask && a.mask.b1) ? a.mask.b1[cch] : 0.f) + ((in && a.has_mask && a.mask.b2) ? a.mask.b2[cch] : 0.f);
+        tl_ma2[tid] = (in && a.has_mask && a.mask.a2) ? a.mask.a2[cch] : 1.f;
+    }
+    if (XF && p.act)
+        for (int k = tid; k < p.K1p; k += G4_THREADS) {
+            const bool in = k < a.K;
+            cf_a[k] = (in && a.src.a1) ? a.src.a1[k] : 1.f;
+            cf_b[k] = ((in && a.src.b1) ? a.src.b1[k] : 0.f) + ((in && a.src.b2) ? a.src.b2[k] : 0.f);
+        }
+    for (int i = tid; i < 256; i += G4_THREADS) reinterpret_cast<uint16_t*>(ones)[i] = 0x3F80;      // bf16 1.0
+    if (tid == 0) {
+        for (int s = 0; s < G4_MAX_STAGES; ++s) { mbar_init(&bars.full[s], 1); mbar_init(&bars.empty[s], 1); mbar_init(&bars.ready[s], 32 * G4_XF_WARPS); }
+        mbar_init(&bars.wbar, 1);
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&bars.acc_full[b], 1); mbar_init(&bars.acc_free[b], G4_EPI_WARPS);
+            mbar_init(&bars.stat_ready[b], 1); mbar_init(&bars.stat_done[b], 1); mbar_init(&bars.out_free[b], 1);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) tmem_alloc(&tmem_base_s, (uint32_t)p.tmem_cols);
+    fence_async_smem();                                  // the ones tile is read by the tensor core (async proxy)
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_base_s;
+    const int n_my = ((int)blockIdx.x < p.n_tiles) ? (p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    const uint32_t box_bytes = p.mode == 0 ? (uint32_t)ATOM_BYTES : (uint32_t)(p.F * (p.mode == 1 ? p.V : p.V + 1) * 128);
+
+    if (warp == 0) {
+        // ================================================= TMA producer =================================================
+        if (lane == 0) {
+            prefetch_map(&mapA0);
+            if (p.natoms > p.natoms1) prefetch_map(&mapA1);
+            mbar_expect_tx(&bars.wbar, p.w_tile_bytes);
+            bulk_g2s(Wsm, reinterpret_cast<const unsigned char*>(a.wpack) + (size_t)blockIdx.y * p.w_tile_bytes, p.w_tile_bytes, &bars.wbar);
+            int stage = 0;
+            uint32_t ph = 0;
+            for (int i = 0; i < n_my; ++i) {
+                const int tile = (int)blockIdx.x + i * (int)gridDim.x;
+                for (int ai = 0; ai < p.natoms; ++ai) {
+                    mbar_wait(&bars.empty[stage], ph ^ 1);
+                    mbar_expect_tx(&bars.full[stage], box_bytes);
+                    const CUtensorMap* m = ai < p.natoms1 ? &mapA0 : &mapA1;
+                    const int c0 = (ai < p.natoms1 ? ai : ai - p.natoms1) * ATOM_CH;
+                    unsigned char* dst = Asm + (size_t)stage * ATOM_BYTES;
+                    if (p.mode == 0) tma_load_2d(dst, m, c0, tile * ATOM_ROWS, &bars.full[stage]);
+                    else
+                        for (int f = 0; f < p.F; ++f) tma_load_3d(dst + (size_t)f * p.slot * 128, m, c0, 0, tile * p.F + f, &bars.full[stage]);
+                    if (++stage == p.S) { stage = 0; ph ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================================================== MMA issuer ==================================================
+        if (lane == 0) {
+            mbar_wait(&bars.wbar, 0);
+            const uint32_t idesc = make_idesc(128, Ntp);
+            const int Ms = Ntp <= 64 ? 64 : 128;
+            const uint32_t idesc_s = idesc_major(Ms, 8, 1, 0);
+            const uint32_t ones_d = smem_u32(ones);
+            int stage = 0, stat_first = 1;
+            uint32_t ph = 0;
+            auto issue_stats = [&](int j) {
+                const int ob = j % p.OB, useo = j / p.OB;
+                mbar_wait(&bars.stat_ready[ob], (uint32_t)(useo & 1));
+                tc_fence_after();
+                const uint32_t o0 = smem_u32(Osm + (size_t)ob * p.out_bytes), s0 = smem_u32(Ssm + (size_t)ob * p.out_bytes);
+                for (int ks = 0; ks < 8; ++ks)
+                    umma_f16(tmem + (uint32_t)p.stat_col, desc_mn_sw128(o0 + ks * 2048u, ATOM_BYTES), desc_ones(ones_d), idesc_s, (stat_first && ks == 0) ? 0u : 1u);
+                for (int ks = 0; ks < 8; ++ks)
+                    umma_f16(tmem + (uint32_t)p.stat_col + 8u, desc_mn_sw128(s0 + ks * 2048u, ATOM_BYTES), desc_ones(ones_d), idesc_s, (stat_first && ks == 0) ? 0u : 1u);
+                stat_first = 0;
+                umma_commit(&bars.stat_done[ob]);
+            };
+            for (int i = 0; i < n_my; ++i) {
+                const int buf = i & 1, use = i >> 1;
+                if (use > 0) mbar_wait(&bars.acc_free[buf], (uint32_t)((use - 1) & 1));
+                tc_fence_after();
+                const uint32_t acc = tmem + (uint32_t)(buf * p.acc_cols);
+                int first = 1;
+                for (int ai = 0; ai < p.natoms; ++ai) {
+                    mbar_wait(XF ? &bars.ready[stage] : &bars.full[stage], ph);
+                    tc_fence_after();
+                    const uint32_t a0 = smem_u32(Asm + (size_t)stage * ATOM_BYTES), w0 = smem_u32(Wsm + (size_t)ai * p.Ntile * 128);
+                    for (int ks = 0; ks < p.ksteps[ai]; ++ks) {
+                        umma_f16(acc, desc_k_sw128(a0 + ks * 32u), desc_k_sw128(w0 + ks * 32u), idesc, first ? 0u : 1u);
+                        first = 0;
+                    }
+                    umma_commit(&bars.empty[stage]);
+                    if (++stage == p.S) { stage = 0; ph ^= 1; }
+                }
+                umma_commit(&bars.acc_full[buf]);
+                if (STATS && i > 0) issue_stats(i - 1);
+            }
+            if (STATS && n_my > 0) issue_stats(n_my - 1);
+        }
+    } else if (warp < 2 + G4_XF_WARPS) {
+        // ================================================ transform warps ===============================================
+        if (XF) {
+            const int t = tid - G4_XF_T0;                 // 0..127
+            const int Vr = p.mode == 2 ? p.V + 1 : p.V;   // rows the TMA wrote per frame slot
+            int stage = 0;
+            uint32_t ph = 0;
+            for (int i = 0; i < n_my; ++i) {
+                for (int ai = 0; ai < p.natoms; ++ai) {
+                    mbar_wait(&bars.full[stage], ph);
+                    unsigned char* atom = Asm + (size_t)stage * ATOM_BYTES;
+                    const int kbase = (ai < p.natoms1 ? ai : ai - p.natoms1) * ATOM_CH;
+                    if (p.act && ai < p.natoms1) {
+                        // BN-affine (+ReLU) in place: thread = row; the logical chunk is uniform per step (broadcast coefficient loads,
+                        // conflict-free 16-byte data accesses)
+                        const bool live = p.mode == 0 ? true : ((t % p.slot) < Vr && t / p.slot < p.F);
+                        if (live) {
+#pragma unroll 2
+                            for (int c = 0; c < 8; ++c) {
+                                const int k = kbase + c * 8;
+                                if (k >= a.K) break;
+                                uint4* q = reinterpret_cast<uint4*>(atom + atom_off(t, c));
+                                float x[8], ka[8], kb[8];
+                                unpack8(*q, x);
+                                load8f(cf_a + k, ka, 1.f);
+                                load8f(cf_b + k, kb, 0.f);
+#pragma unroll
+                                for (int e = 0; e < 8; ++e) x[e] = fmaf(x[e], ka[e], kb[e]);
+                                if (a.src.relu) {
+#pragma unroll
+                                    for (int e = 0; e < 8; ++e) x[e] = fmaxf(x[e], 0.f);
+                                }
+                                *q = pack8(x);
+                            }
+                        }
+                        if (p.mode != 0) named_sync(G4_BAR_XF, 32 * G4_XF_WARPS);
+                    }
+                    if (p.mode == 1) {
+                        // joint-mean row of every frame: item = (frame, chunk), 4 lanes per item split the joints
+                        const int items = p.F * 8 * 4;
+                        for (int base = 0; base < items; base += 32 * G4_XF_WARPS) {
+                            const int idx = base + t;
+                            const bool ok = idx < items;
+                            const int part = idx & 3, c = (idx >> 2) & 7, f = idx >> 5;
+                            float s8[8];
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) s8[e] = 0.f;
+                            if (ok && kbase + c * 8 < a.K)
+                                for (int v = part; v < p.V; v += 4) {
+                                    float x[8];
+                                    unpack8(*reinterpret_cast<const uint4*>(atom + atom_off(f * p.slot + v, c)), x);
+#pragma unroll
+                                    for (int e = 0; e < 8; ++e) s8[e] += x[e];
+                                }
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) {
+                                s8[e] += __shfl_xor_sync(0xffffffffu, s8[e], 1);
+                                s8[e] += __shfl_xor_sync(0xffffffffu, s8[e], 2);
+                            }
+                            if (ok && part == 0) {
+                                const float inv = 1.f / (float)p.V;
+#pragma unroll
+                                for (int e = 0; e < 8; ++e) s8[e] *= inv;
+                                *reinterpret_cast<uint4*>(atom + atom_off(f * p.slot + p.V, c)) = pack8(s8);
+                            }
+                        }
+                    } else if (p.mode == 2) {
+                        // gradient of the joint mean: every joint row += mean row / V (linear, so it is applied to e and y alike)
+                        const int items = p.F * 8 * 4;
+                        const float inv = 1.f / (float)p.V;
+                        for (int idx = t; idx < items; idx += 32 * G4_XF_WARPS) {
+                            const int part = idx & 3, c = (idx >> 2) & 7, f = idx >> 5;
+                            if (kbase + c * 8 >= a.K) continue;
+                            float g[8];
+                            unpack8(*reinterpret_cast<const uint4*>(atom + atom_off(f * p.slot + p.V, c)), g);
+                            for (int v = part; v < p.V; v += 4) {
+                                uint4* q = reinterpret_cast<uint4*>(atom + atom_off(f * p.slot + v, c));
+                                float x[8];
+                                unpack8(*q, x);
+#pragma unroll
+                                for (int e = 0; e < 8; ++e) x[e] = fmaf(g[e], inv, x[e]);
+                                *q = pack8(x);
+                            }
+                        }
+                    }
+                    fence_async_smem();
+                    mbar_arrive(&bars.ready[stage]);
+                    if (++stage == p.S) { stage = 0; ph ^= 1; }
+                }
+            }
+        }
+    } else {
+        // =================================================== epilogue ===================================================
+        const int et = tid - G4_EPI_T0;                   // 0..255
+        const int q = warp & 3, half = (warp - 2 - G4_XF_WARPS) >> 2;      // TMEM lane quarter of this warp, column half
+        const int r = q * 32 + lane;                      // accumulator row = tile row
+        const int nc16 = Ntp >> 4;
+        const int cbeg = half ? (nc16 + 1) >> 1 : 0, cend = half ? nc16 : (nc16 + 1) >> 1;
+        const int Vout = a.Vin + a.ext_in - a.contract_ext;
+        const bf16* addp = reinterpret_cast<const bf16*>(a.add);
+        const bf16* add2p = reinterpret_cast<const bf16*>(a.add2);
+        const bf16* partp = reinterpret_cast<const bf16*>(a.partner);
+        for (int i = 0; i < n_my; ++i) {
+            const int tile = (int)blockIdx.x + i * (int)gridDim.x;
+            const int buf = i & 1, use = i >> 1, ob = i % p.OB, useo = i / p.OB;
+            // ---- this thread's output row
+            long long gr = -1;
+            int jrow = 0, samp = 0;
+            if (p.mode == 0) {
+                const long long g = (long long)tile * ATOM_ROWS + r;
+                if (g < p.rows_out) gr = g;
+                if (TAILS && a.bcast && gr >= 0) { const long long fr = gr / Vout; jrow = (int)(gr - fr * Vout); samp = (int)(fr / a.T_out); }
+            } else {
+                const int f = r / p.slot, v = r - f * p.slot;
+                const long long frame = (long long)tile * p.F + f;
+                if (f < p.F && v < Vout && frame < p.n_frames) { gr = frame * Vout + v; jrow = v; samp = (int)(frame / a.T_out); }
+            }
+            mbar_wait(&bars.acc_full[buf], (uint32_t)(use & 1));
+            tc_fence_after();
+            if (i >= p.OB) mbar_wait(&bars.out_free[ob], (uint32_t)((useo - 1) & 1));     // out / product tiles of `OB` tiles ago have been read
+            unsigned char* Ot = Osm + (size_t)ob * p.out_bytes;
+            unsigned char* St = Ssm + (size_t)ob * p.out_bytes;
+            const uint32_t acc = tmem + (uint32_t)(buf * p.acc_cols) + ((uint32_t)(q * 32) << 16);
+            const bool row_ok = gr >= 0;
+            for (int cc = cbeg; cc < cend; ++cc) {
+                const int c16 = cc * 16;
+                float v[16];
+                if (!TAILS) {
+                    // ---- lean path: bias, bf16 pack, (square for the statistics), conflict-free 16-byte stores
+                    tmem_ld16(acc + (uint32_t)c16, v);
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int col = c16 + h * 8;
+                        float* vv = v + h * 8;
+                        tc::add8(vv, tl_bias + col);
+                        if (!row_ok) {
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) vv[e] = 0.f;
+                        }
+                        const uint32_t off = (uint32_t)(col >> 6) * ATOM_BYTES + atom_off(r, (col & 63) >> 3);
+                        *reinterpret_cast<uint4*>(Ot + off) = pack8(vv);
+                        if (STATS) {
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) vv[e] *= vv[e];
+                            *reinterpret_cast<uint4*>(St + off) = pack8(vv);
+                        }
+                    }
+                } else {
+                    const int c = n0 + c16;
+                    const bool live0 = c < a.N, live1 = c + 8 < a.N;
+                    uint4 ra[2], ra2[2], rp[2];
+                    tc::Act8Raw rm[2];
+                    if (row_ok) {
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            if (!(h ? live1 : live0)) continue;
+                            if (addp) ra[h] = *reinterpret_cast<const uint4*>(addp + gr * a.ld_add + c + h * 8);
+                            if (add2p) ra2[h] = *reinterpret_cast<const uint4*>(add2p + gr * a.ld_add2 + c + h * 8);
+                            if (partp) rp[h] = *reinterpret_cast<const uint4*>(partp + gr * a.ld_partner + c + h * 8);
+                            if (a.has_mask) rm[h] = tc::act8_issue(a.mask, gr, c + h * 8);
+                        }
+                    }
+                    tmem_ld16(acc + (uint32_t)c16, v);
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int col = c16 + h * 8;                     // column inside the CTA tile
+                        float* vv = v + h * 8;
+                        uint4 o = make_uint4(0u, 0u, 0u, 0u), pr = make_uint4(0u, 0u, 0u, 0u);
+                        if (row_ok && (h ? live1 : live0)) {
+                            tc::add8(vv, tl_bias + col);
+                            if (addp) { float t8[8]; unpack8(ra[h], t8);
+#pragma unroll
+                                for (int e = 0; e < 8; ++e) vv[e] += t8[e]; }
+                            if (add2p) { float t8[8]; unpack8(ra2[h], t8);
+#pragma unroll
+                                for (int e = 0; e < 8; ++e) vv[e] += t8[e]; }
+                            if (a.bcast) {
+                                float t8[8];
+                                load8f(a.bcast + ((long long)samp * Vout + jrow) * a.N + c + h * 8, t8, 0.f);
+#pragma unroll
+                                for (int e = 0; e < 8; ++e) vv[e] = fmaf(t8[e], a.bcast_scale, vv[e]);
+                            }
+                            if (a.has_mask) {
+                                float m8[8];
+                                tc::finish_smem(rm[h], a.mask.x2 != nullptr, 0, tl_ma1 + col, tl_mb + col, tl_ma2 + col, m8);
+#pragma unroll
+                                for (int e = 0; e < 8; ++e) vv[e] = m8[e] > 0.f ? vv[e] : 0.f;
+                            }
+                            o = pack8(vv);
+                            if (STATS) {
+                                float pp[8];
+                                if (partp) unpack8(rp[h], pp);
+#pragma unroll
+                                for (int e = 0; e < 8; ++e) vv[e] *= partp ? pp[e] : vv[e];
+                                pr = pack8(vv);
+                            }
+                        }
+                        const uint32_t off = (uint32_t)(col >> 6) * ATOM_BYTES + atom_off(r, (col & 63) >> 3);
+                        *reinterpret_cast<uint4*>(Ot + off) = o;
+                        if (STATS) *reinterpret_cast<uint4*>(St + off) = pr;
+                    }
+                }
+            }
+            tc_fence_before();
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bars.acc_free[buf]);
+            named_sync(G4_BAR_EPI, G4_EPI_THREADS);
+            if (et == 0) {
+                for (int oa = 0; oa < n_oatoms; ++oa) {
+                    const unsigned char* src = Ot + (size_t)oa * ATOM_BYTES;
+                    if (p.mode == 0) tma_store_2d(&mapO, src, n0 + oa * ATOM_CH, tile * ATOM_ROWS);
+                    else
+                        for (int f = 0; f < p.F; ++f)
+                            if ((long long)tile * p.F + f < p.n_frames) tma_store_3d(&mapO, src + (size_t)f * p.slot * 128, n0 + oa * ATOM_CH, 0, tile * p.F + f);
+                }
+                tma_store_commit();
+                if (STATS) mbar_arrive(&bars.stat_ready[ob]);
+                // release this buffer for tile i + OB once its readers are done: the TMA store (read side) and the statistics MMAs
+                if (i + p.OB < n_my) {
+                    tma_store_wait_read<0>();
+                    if (STATS) mbar_wait(&bars.stat_done[ob], (uint32_t)(useo & 1));
+                    mbar_arrive(&bars.out_free[ob]);
+                }
+            }
+        }
+        if (et == 0) tma_store_wait_all<0>();
+        if (STATS && n_my > 0) {
+            // ---- per-channel sums of this CTA: lane (= channel) reads column 0 of the two statistics accumulators
+            const int last = n_my - 1;
+            mbar_wait(&bars.stat_done[last % p.OB], (uint32_t)((last / p.OB) & 1));
+            tc_fence_after();
+            if (half == 0) {
+                float s1[8], s2[8];
+                tmem_ld8(tmem + (uint32_t)p.stat_col + ((uint32_t)(q * 32) << 16), s1);
+                tmem_ld8(tmem + (uint32_t)p.stat_col + 8u + ((uint32_t)(q * 32) << 16), s2);
+                int ch = -1;
+                if (Ntp <= 64) { if (lane < 16) ch = q * 16 + lane; } else ch = q * 32 + lane;
+                if (ch >= 0 && ch < Nt) {
+                    atomicAdd(a.stat_sum + n0 + ch, (double)s1[0]);
+                    atomicAdd(a.stat_sq + n0 + ch, (double)s2[0]);
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem, (uint32_t)p.tmem_cols);
+}
+
+// ---- host side -----------------------------------------------------------------------------------------------------
+static inline long long tc4_wpack_bytes(int K, int N) {
+    const long long kat = 2LL * ((K + ATOM_CH - 1) / ATOM_CH), t64 = (N + 63) / 64;
+    return t64 * kat * 64 * 128 + (long long)((N + 63) & ~63) * 4 + 512;
+}
+
+static bool tc4_plan(const dsg_conv_gemm_args& a, G4Plan& p, bool fold) {
+    p = G4Plan{};
+    const int Vout = a.Vin + a.ext_in - a.contract_ext;
+    p.mode = a.ext_in ? 1 : (a.contract_ext ? 2 : 0);
+    p.V = a.ext_in ? a.Vin : (a.contract_ext ? a.Vin - 1 : a.Vin);
+    p.n_frames = (long long)a.n_samples * a.T_out;
+    p.rows_out = p.n_frames * Vout;
+    if (p.mode == 0) {
+        p.slot = 0; p.F = 0;
+        const long long nt = (p.rows_out + ATOM_ROWS - 1) / ATOM_ROWS;
+        if (nt > 0x3fffffff) return false;
+        p.n_tiles = (int)nt;
+    } else {
+        if (p.V + 1 > 32 || p.V < 2) return false;
+        p.slot = (p.V + 1 + 7) & ~7;
+        p.F = ATOM_ROWS / p.slot;
+        const long long nt = (p.n_frames + p.F - 1) / p.F;
+        if (nt > 0x3fffffff) return false;
+        p.n_tiles = (int)nt;
+    }
+    const int kat = (a.K + ATOM_CH - 1) / ATOM_CH;
+    p.natoms1 = kat;
+    p.natoms = (fold && a.src.x2) ? 2 * kat : kat;
+    if (p.natoms > G4_MAX_ATOMS) return false;
+    for (int i = 0; i < p.natoms; ++i) {
+        const int k0 = (i % kat) * ATOM_CH;
+        const int live = a.K - k0 < ATOM_CH ? a.K - k0 : ATOM_CH;
+        p.ksteps[i] = (live + 15) / 16;
+    }
+    p.K1p = kat * ATOM_CH;
+    p.act = (!fold) ? 1 : 0;                              // ReLU sources (one tensor): CUDA-core prologue in place
+    p.xf = (p.act || p.mode != 0) ? 1 : 0;
+    p.has_stats = a.stat_sum != nullptr;
+    const unsigned cf_bytes = (unsigned)((4 * 128 + 2 * p.K1p) * sizeof(float));
+    const unsigned budget = 227u * 1024u - 2048u;         // dynamic shared memory we may ask for (static barriers + alignment slack kept)
+    const int cand_nt[2] = {128, 64};
+    for (int ci = (a.N <= 64 ? 1 : 0); ci < 2; ++ci) {
+        const int Ntile = cand_nt[ci];
+        const unsigned wb = (unsigned)p.natoms * Ntile * 128;
+        const unsigned ob1 = (unsigned)(Ntile / ATOM_CH) * ATOM_BYTES;
+        for (int OB = 2; OB >= 1; --OB) {
+            const unsigned fixed = wb + OB * ob1 * (p.has_stats ? 2u : 1u) + 1024u + ((cf_bytes + 1023u) & ~1023u) + 1024u;
+            if (fixed + 3u * ATOM_BYTES > budget) continue;
+            int S = (int)((budget - fixed) / ATOM_BYTES);
+            if (S > G4_MAX_STAGES) S = G4_MAX_STAGES;
+            if (OB == 2 && S < 4 && ci == 0) continue;    // prefer a deeper ring over double-buffered out tiles
+            p.Ntile = Ntile; p.S = S; p.OB = OB;
+            p.off_w = 0;
+            p.off_a = wb;                                  // multiples of 1024 throughout
+            p.off_out = p.off_a + (unsigned)S * ATOM_BYTES;
+            p.out_bytes = ob1;
+            p.off_stat = p.off_out + OB * ob1;
+            p.off_ones = p.off_stat + (p.has_stats ? OB * ob1 : 0u);
+            p.off_cf = p.off_ones + 1024u;
+            p.smem_total = p.off_cf + ((cf_bytes + 1023u) & ~1023u) + 1024u;
+            p.w_tile_bytes = wb;
+            p.acc_cols = Ntile <= 32 ? 32 : (Ntile <= 64 ? 64 : 128);
+            p.stat_col = 2 * p.acc_cols;
+            const int need = 2 * p.acc_cols + (p.has_stats ? 16 : 0);
+            p.tmem_cols = 32;
+            while (p.tmem_cols < need) p.tmem_cols <<= 1;
+            return true;
+        }
+    }
+    return false;
+}
+
+static const char* launch_conv_gemm_tc4(const dsg_conv_gemm_args& a, dsg_stream_t st, bool* handled) {
+    *handled = false;
+    if (!tc4_enabled() || a.dtype != DSG_BF16 || a.taps != 1 || a.t_mul != 1 || a.t_div != 1 || a.tap_off != 0) return nullptr;
+    if (a.K % 8 != 0 || a.N % 8 != 0 || a.N < 16 || a.T_in != a.T_out) return nullptr;
+    if (a.ext_in && a.contract_ext) return nullptr;
+    if (!a.wpack || (uintptr_t)a.wpack % 128 != 0) return nullptr;
+    if (!tma_ptr_ok(a.src.x1, a.src.ld1) || (a.src.x2 && !tma_ptr_ok(a.src.x2, a.src.ld2)) || !tma_ptr_ok(a.out, a.ld_out)) return nullptr;
+    const bool fold = !a.src.relu;                        // affine / two-tensor BN-backward prologue folds into the weights
+    if (!fold && a.src.x2) return nullptr;                // ReLU over two tensors: older engines
+    auto al16 = [](const void* p, long long ld) { return p == nullptr || ((uintptr_t)p % 16 == 0 && ld % 8 == 0); };
+    if (!(al16(a.add, a.ld_add) && al16(a.add2, a.ld_add2) && al16(a.partner, a.ld_partner) && (!a.has_mask || act8_ok(a.mask)) &&
+          (!a.bcast || (uintptr_t)a.bcast % 16 == 0)))
+        return nullptr;
+    const long long n_frames = (long long)a.n_samples * a.T_out;
+    if (n_frames <= 0) { *handled = true; return nullptr; }
+    G4Plan p;
+    if (!tc4_plan(a, p, fold)) return nullptr;
+    if (!encode_fn()) return nullptr;
+    CUtensorMap mA0, mA1, mO;
+    const long long rows_in = n_frames * a.Vin;
+    bool ok;
+    if (p.mode == 0) {
+        ok = make_map_2d(&mA0, a.src.x1, rows_in, a.K, a.src.ld1, ATOM_ROWS);
+        mA1 = mA0;
+        if (ok && p.natoms > p.natoms1) ok = make_map_2d(&mA1, a.src.x2, rows_in, a.K, a.src.ld2, ATOM_ROWS);
+        ok = ok && make_map_2d(&mO, a.out, p.rows_out, a.N, a.ld_out, ATOM_ROWS);
+    } else {
+        const int rin = a.Vin, rout = a.Vin + a.ext_in - a.contract_ext;
+        ok = make_map_3d(&mA0, a.src.x1, n_frames, rin, a.K, a.src.ld1, rin, 1);
+        mA1 = mA0;
+        if (ok && p.natoms > p.natoms1) ok = make_map_3d(&mA1, a.src.x2, n_frames, rin, a.K, a.src.ld2, rin, 1);
+        ok = ok && make_map_3d(&mO, a.out, n_frames, rout, a.N, a.ld_out, rout, 1);
+    }
+    if (!ok) return nullptr;
+    const unsigned gy = (unsigned)((a.N + p.Ntile - 1) / p.Ntile);
+    const size_t wtot = (size_t)gy * p.w_tile_bytes;
+    if ((long long)(wtot + (size_t)a.N * 4 + 256) > tc4_wpack_bytes(a.K, a.N)) return nullptr;
+    float* cbias = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(a.wpack) + ((wtot + 255) & ~(size_t)255));
+    const float* s1 = fold ? a.src.a1 : nullptr;
+    const float* s2 = fold ? a.src.a2 : nullptr;
+    const float* c1 = fold ? a.src.b1 : nullptr;
+    const float* c2 = fold ? a.src.b2 : nullptr;
+    tc4_wpack_kernel<<<dim3(gy, (unsigned)p.natoms + 1), dim3(256), 0, st>>>(a.W, a.ws_n, a.ws_k, a.K, a.N, p.natoms1, p.natoms, p.Ntile, s1, s2, c1, c2,
+                                                                            a.bias, reinterpret_cast<unsigned char*>(a.wpack), cbias);
+    if (const char* e = dsg_launch_error()) return e;
+    int gx = num_sms() / (int)gy;
+    if (gx < 1) gx = 1;
+    if (gx > p.n_tiles) gx = p.n_tiles;
+    const bool tails = a.add || a.add2 || a.bcast || a.has_mask || a.partner;
+    const int variant = (p.xf ? 4 : 0) | (tails ? 2 : 0) | (p.has_stats ? 1 : 0);
+#define DSG_T4_LAUNCH(XF_, TL_, ST_)                                                                                              \
+    do {                                                                                                                          \
+        cudaFuncSetAttribute(tc4_gemm_kernel<XF_, TL_, ST_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_total);     \
+        tc4_gemm_kernel<XF_, TL_, ST_><<<dim3((unsigned)gx, gy), dim3(G4_THREADS), p.smem_total, st>>>(mA0, mA1, mO, a, p, cbias); \
+    } while (0)
+    switch (variant) {
+        case 0: DSG_T4_LAUNCH(false, false, false); break;
+        case 1: DSG_T4_LAUNCH(false, false, true); break;
+        case 2: DSG_T4_LAUNCH(false, true, false); break;
+        case 3: DSG_T4_LAUNCH(false, true, true); break;
+        case 4: DSG_T4_LAUNCH(true, false, false); break;
+        case 5: DSG_T4_LAUNCH(true, false, true); break;
+        case 6: DSG_T4_LAUNCH(true, true, false); break;
+        default: DSG_T4_LAUNCH(true, true, true); break;
+    }
+#undef DSG_T4_LAUNCH
+    *handled = true;
+    return dsg_launch_error();
+}
+
+}  // namespace tc4
+}  // namespace dsg
+#endif

@@ -343,6 +343,11 @@ int dsg_pointwise(const dsg_pointwise_args* a, void* stream);
 int dsg_sgd_step(float* p, const float* grad, float* buf, long long n, float lr, float momentum, float wd,
                  int nesterov, float grad_scale, void* stream);
 
+/* Launch counters of the engines behind the entry points (diagnostics for the tests and bench.py: which engine ran).
+ * id 0: TMA-fed tcgen05 GEMM (tc4)   1: TMA-fed tcgen05 weight gradient (tc4w)   2: fused adjacency-contraction + post GEMM.
+ * Monotonic, process-wide, never read by the kernels. */
+long long dsg_debug_counter(int id);
+
 const char* dsg_last_error(void);
 int dsg_abi_version(void);
 /* 1 when built for the GPU (sm_100a), 0 for the host-side simulator used by the CPU test-suite. */

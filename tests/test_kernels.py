@@ -4,6 +4,8 @@ Each test runs twice: `dev=sim` (the kernel sources on the host-side SIMT simula
 `dev=cuda` (marked gpu: the real sm_100a library on the B200).  Tolerances: fp32 path rel 1e-4 (north_star),
 bf16 path rel-L2 1e-2.
 """
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -109,6 +111,7 @@ def test_conv_gemm_fast_engines(dev, K, N, variant):
         pytest.skip("simulator: small shapes only")
     ext_in, cext = variant == "ext_in", variant == "contract"
     Vin = V + 1 if cext else V
+    tc4_before = _lib.lib().dsg_debug_counter(0)
     rows_in = n * T * Vin
     rows_out = n * T * (V + 1 if ext_in else V)
     x = rnd(rows_in, K, dev=dev, dtype=dtype)
@@ -147,6 +150,8 @@ def test_conv_gemm_fast_engines(dev, K, N, variant):
         y = (x.float() @ W.t()).view(n * T, V + 1, N)
         ref = (y[:, :V] + y[:, V:] / V).reshape(-1, N) + 0.5 * bc[:, None].expand(n, T, V, N).reshape(-1, N)
     close(out, ref, dtype, f"{variant} out")
+    if big and os.environ.get("DSG_DISABLE_TC4") != "1":
+        assert _lib.lib().dsg_debug_counter(0) == tc4_before + 1, "the TMA-fed engine (tc4) declined a network shape"
 
 
 @pytest.mark.parametrize("K,N", [(64, 64), (24, 64), (64, 176), (256, 96), (128, 288), (256, 256)])
