@@ -11,16 +11,19 @@
 //   warps 2-5     transform warps (only when the operand is not a plain tensor): BN-affine + ReLU prologue in place, the
 //                 joint-mean row of dgmstcn (tcn.py:409) or its gradient fold-back, then fence.proxy.async + arrive.
 //   warps 6-13    epilogue: thread = accumulator row.  tcgen05.ld, bias / addends / per-sample broadcast / ReLU mask, bf16 pack,
-//                 16-byte conflict-free stores into a SWIZZLE_128B out tile in shared memory; one thread then issues the TMA
-//                 store (boundary clipping by the TMA unit).
+//                 16-byte conflict-free stores into a SWIZZLE_128B out tile in shared memory.  They never wait on anything but
+//                 "accumulator full" and "out tile free".
+//   warp 14       drain: one thread issues the TMA store of the finished out tile (boundary clipping by the TMA unit) and the
+//                 BatchNorm-statistics MMAs over it, waits for both to have read the tile and hands it back.
 //
 // Two algebraic moves keep CUDA cores off the data path:
 //  * BatchNorm-backward prologue dy = ca*e + cb*y + cc (dsg_act_src with two tensors, no ReLU) is folded into the GEMM:
 //    A = [e | y] (two tensor maps, K concatenated), W' = [diag(ca) W ; diag(cb) W], bias' = cc^T W — computed by the weight
 //    pack kernel in fp32 and rounded once to bf16; e and y go from HBM to the tensor core untouched.
-//  * BatchNorm statistics (sum v, sum v*partner) are column sums of the bf16 out tile and of a bf16 product tile the
-//    epilogue writes next to it: two tcgen05.mma per 16 rows with a constant "ones" B operand (A = tile, MN-major) accumulate
-//    them in 16 TMEM columns over all tiles of the CTA; one fp64 atomic per channel per CTA at the end.  (The shuffle
+//  * BatchNorm statistics run on the tensor core over the bf16 out tile (A operand, MN-major: reduction over the tile rows):
+//    sum v = tile^T x ones (N = 8 "ones" B operand); sum v^2 = diagonal of the Gram matrix tile^T x tile (forward), or
+//    sum v*partner = column sums of a bf16 product tile the epilogue writes next to it (BatchNorm backward).  The sums
+//    accumulate in TMEM over all tiles of the CTA; one fp64 atomic per channel per CTA at the end.  (The shuffle
 //    transpose-reduce of the older engines cost ~150 instructions per 16 columns per thread.)
 #pragma once
 #include "tc4_common.cuh"
@@ -30,7 +33,8 @@ namespace dsg {
 namespace tc4 {
 
 constexpr int G4_XF_WARPS = 4, G4_EPI_WARPS = 8;
-constexpr int G4_THREADS = 32 * (2 + G4_XF_WARPS + G4_EPI_WARPS);      // 448
+constexpr int G4_DRAIN_WARP = 2 + G4_XF_WARPS + G4_EPI_WARPS;            // warp 14: TMA stores + statistics MMAs
+constexpr int G4_THREADS = 32 * (G4_DRAIN_WARP + 1);                     // 480
 constexpr int G4_XF_T0 = 64, G4_EPI_T0 = 64 + 32 * G4_XF_WARPS;         // first thread of the transform / epilogue groups
 constexpr int G4_EPI_THREADS = 32 * G4_EPI_WARPS;                       // 256
 constexpr int G4_MAX_ATOMS = 12, G4_MAX_STAGES = 6;
@@ -45,10 +49,10 @@ struct G4Plan {
     int ksteps[G4_MAX_ATOMS];    // K = 16 MMA steps per atom (live channels only)
     int K1p;                     // natoms1 * 64
     int Ntile, S, OB;            // output columns per CTA, A stages, out/stat buffers
-    int xf, act, has_stats;
+    int xf, act, stats;          // stats: 0 none, 1 Gram (sum v, sum v^2), 2 product tile (sum v, sum v*partner)
     unsigned off_w, off_a, off_out, off_stat, off_ones, off_cf;       // byte offsets from the 1024-aligned base
     unsigned w_tile_bytes, out_bytes, smem_total;
-    int acc_cols, stat_col, tmem_cols;
+    int acc_cols, stat_col, sum_col, tmem_cols;   // stat_col: Gram / product sums; sum_col: plain sums (8 columns)
 };
 
 // ---- packed weights: per column tile j, per atom a: [Ntile rows (n) x 64 k] bf16 in the K-major SWIZZLE_128B layout, scaled
@@ -93,11 +97,11 @@ __global__ void __launch_bounds__(256) tc4_wpack_kernel(const float* W, long lon
 
 struct G4Bars {
     uint64_t full[G4_MAX_STAGES], empty[G4_MAX_STAGES], ready[G4_MAX_STAGES];
-    uint64_t wbar, acc_full[2], acc_free[2], stat_ready[2], stat_done[2], out_free[2];
+    uint64_t wbar, acc_full[2], acc_free[2], out_ready[2], stat_done[2], out_free[2];
 };
 
-// XF: transform warps active; TAILS: any of add / add2 / bcast / mask / partner; STATS: BatchNorm statistics requested
-template <bool XF, bool TAILS, bool STATS>
+// XF: transform warps active; TAILS: any of add / add2 / bcast / mask / partner; STATS: 0 none, 1 Gram, 2 product tile
+template <bool XF, bool TAILS, int STATS>
 __global__ void __launch_bounds__(G4_THREADS, 1)
 tc4_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUtensorMap mapO,
                 const dsg_conv_gemm_args a, const G4Plan p, const float* __restrict__ cbias) {
@@ -143,7 +147,7 @@ tc4_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
         mbar_init(&bars.wbar, 1);
         for (int b = 0; b < 2; ++b) {
             mbar_init(&bars.acc_full[b], 1); mbar_init(&bars.acc_free[b], G4_EPI_WARPS);
-            mbar_init(&bars.stat_ready[b], 1); mbar_init(&bars.stat_done[b], 1); mbar_init(&bars.out_free[b], 1);
+            mbar_init(&bars.out_ready[b], G4_EPI_WARPS); mbar_init(&bars.stat_done[b], 1); mbar_init(&bars.out_free[b], 1);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -185,23 +189,8 @@ tc4_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
         if (lane == 0) {
             mbar_wait(&bars.wbar, 0);
             const uint32_t idesc = make_idesc(128, Ntp);
-            const int Ms = Ntp <= 64 ? 64 : 128;
-            const uint32_t idesc_s = idesc_major(Ms, 8, 1, 0);
-            const uint32_t ones_d = smem_u32(ones);
-            int stage = 0, stat_first = 1;
+            int stage = 0;
             uint32_t ph = 0;
-            auto issue_stats = [&](int j) {
-                const int ob = j % p.OB, useo = j / p.OB;
-                mbar_wait(&bars.stat_ready[ob], (uint32_t)(useo & 1));
-                tc_fence_after();
-                const uint32_t o0 = smem_u32(Osm + (size_t)ob * p.out_bytes), s0 = smem_u32(Ssm + (size_t)ob * p.out_bytes);
-                for (int ks = 0; ks < 8; ++ks)
-                    umma_f16(tmem + (uint32_t)p.stat_col, desc_mn_sw128(o0 + ks * 2048u, ATOM_BYTES), desc_ones(ones_d), idesc_s, (stat_first && ks == 0) ? 0u : 1u);
-                for (int ks = 0; ks < 8; ++ks)
-                    umma_f16(tmem + (uint32_t)p.stat_col + 8u, desc_mn_sw128(s0 + ks * 2048u, ATOM_BYTES), desc_ones(ones_d), idesc_s, (stat_first && ks == 0) ? 0u : 1u);
-                stat_first = 0;
-                umma_commit(&bars.stat_done[ob]);
-            };
             for (int i = 0; i < n_my; ++i) {
                 const int buf = i & 1, use = i >> 1;
                 if (use > 0) mbar_wait(&bars.acc_free[buf], (uint32_t)((use - 1) & 1));
@@ -220,9 +209,7 @@ tc4_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
                     if (++stage == p.S) { stage = 0; ph ^= 1; }
                 }
                 umma_commit(&bars.acc_full[buf]);
-                if (STATS && i > 0) issue_stats(i - 1);
             }
-            if (STATS && n_my > 0) issue_stats(n_my - 1);
         }
     } else if (warp < 2 + G4_XF_WARPS) {
         // ================================================ transform warps ===============================================
@@ -315,9 +302,8 @@ tc4_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
                 }
             }
         }
-    } else {
+    } else if (warp < G4_DRAIN_WARP) {
         // =================================================== epilogue ===================================================
-        const int et = tid - G4_EPI_T0;                   // 0..255
         const int q = warp & 3, half = (warp - 2 - G4_XF_WARPS) >> 2;      // TMEM lane quarter of this warp, column half
         const int r = q * 32 + lane;                      // accumulator row = tile row
         const int nc16 = Ntp >> 4;
@@ -365,7 +351,7 @@ tc4_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
                         }
                         const uint32_t off = (uint32_t)(col >> 6) * ATOM_BYTES + atom_off(r, (col & 63) >> 3);
                         *reinterpret_cast<uint4*>(Ot + off) = pack8(vv);
-                        if (STATS) {
+                        if (STATS == 2) {
 #pragma unroll
                             for (int e = 0; e < 8; ++e) vv[e] *= vv[e];
                             *reinterpret_cast<uint4*>(St + off) = pack8(vv);
@@ -413,7 +399,7 @@ tc4_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
                                 for (int e = 0; e < 8; ++e) vv[e] = m8[e] > 0.f ? vv[e] : 0.f;
                             }
                             o = pack8(vv);
-                            if (STATS) {
+                            if (STATS == 2) {
                                 float pp[8];
                                 if (partp) unpack8(rp[h], pp);
 #pragma unroll
@@ -423,51 +409,92 @@ tc4_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
                         }
                         const uint32_t off = (uint32_t)(col >> 6) * ATOM_BYTES + atom_off(r, (col & 63) >> 3);
                         *reinterpret_cast<uint4*>(Ot + off) = o;
-                        if (STATS) *reinterpret_cast<uint4*>(St + off) = pr;
+                        if (STATS == 2) *reinterpret_cast<uint4*>(St + off) = pr;
                     }
                 }
             }
             tc_fence_before();
             fence_async_smem();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&bars.acc_free[buf]);
-            named_sync(G4_BAR_EPI, G4_EPI_THREADS);
-            if (et == 0) {
-                for (int oa = 0; oa < n_oatoms; ++oa) {
-                    const unsigned char* src = Ot + (size_t)oa * ATOM_BYTES;
-                    if (p.mode == 0) tma_store_2d(&mapO, src, n0 + oa * ATOM_CH, tile * ATOM_ROWS);
-                    else
-                        for (int f = 0; f < p.F; ++f)
-                            if ((long long)tile * p.F + f < p.n_frames) tma_store_3d(&mapO, src + (size_t)f * p.slot * 128, n0 + oa * ATOM_CH, 0, tile * p.F + f);
-                }
-                tma_store_commit();
-                if (STATS) mbar_arrive(&bars.stat_ready[ob]);
-                // release this buffer for tile i + OB once its readers are done: the TMA store (read side) and the statistics MMAs
-                if (i + p.OB < n_my) {
-                    tma_store_wait_read<0>();
-                    if (STATS) mbar_wait(&bars.stat_done[ob], (uint32_t)(useo & 1));
-                    mbar_arrive(&bars.out_free[ob]);
-                }
+            if (lane == 0) {
+                mbar_arrive(&bars.acc_free[buf]);
+                mbar_arrive(&bars.out_ready[ob]);
             }
         }
-        if (et == 0) tma_store_wait_all<0>();
-        if (STATS && n_my > 0) {
-            // ---- per-channel sums of this CTA: lane (= channel) reads column 0 of the two statistics accumulators
+        if (STATS != 0 && n_my > 0) {
+            // ---- per-channel sums of this CTA (lane = channel): out_free of the last tile = its statistics MMAs are complete
             const int last = n_my - 1;
-            mbar_wait(&bars.stat_done[last % p.OB], (uint32_t)((last / p.OB) & 1));
+            mbar_wait(&bars.out_free[last % p.OB], (uint32_t)((last / p.OB) & 1));
+            if (p.OB == 2 && n_my > 1) mbar_wait(&bars.out_free[(last - 1) % 2], (uint32_t)(((last - 1) / 2) & 1));
             tc_fence_after();
             if (half == 0) {
-                float s1[8], s2[8];
-                tmem_ld8(tmem + (uint32_t)p.stat_col + ((uint32_t)(q * 32) << 16), s1);
-                tmem_ld8(tmem + (uint32_t)p.stat_col + 8u + ((uint32_t)(q * 32) << 16), s2);
+                const bool m64 = Ntp <= 64;
                 int ch = -1;
-                if (Ntp <= 64) { if (lane < 16) ch = q * 16 + lane; } else ch = q * 32 + lane;
+                if (m64) { if (lane < 16) ch = q * 16 + lane; } else ch = q * 32 + lane;
+                const uint32_t lanes = (uint32_t)(q * 32) << 16;
+                float s1[8], s2v = 0.f;
+                tmem_ld8(tmem + (uint32_t)p.sum_col + lanes, s1);
+                if (STATS == 2) {
+                    float s2[8];
+                    tmem_ld8(tmem + (uint32_t)p.stat_col + lanes, s2);
+                    s2v = s2[0];
+                } else {
+                    // diagonal of the Gram matrix: accumulator row = channel (this lane), column = the same channel
+                    float g[32];
+                    const int cb = m64 ? q * 16 : q * 32;
+                    tmem_ld16(tmem + (uint32_t)p.stat_col + (uint32_t)cb + lanes, g);
+                    if (!m64) tmem_ld16(tmem + (uint32_t)p.stat_col + (uint32_t)cb + 16u + lanes, g + 16);
+#pragma unroll
+                    for (int e = 0; e < 32; ++e)
+                        if (e == lane && (e < 16 || !m64)) s2v = g[e];
+                }
                 if (ch >= 0 && ch < Nt) {
                     atomicAdd(a.stat_sum + n0 + ch, (double)s1[0]);
-                    atomicAdd(a.stat_sq + n0 + ch, (double)s2[0]);
+                    atomicAdd(a.stat_sq + n0 + ch, (double)s2v);
                 }
             }
         }
+    }
+    if (warp == G4_DRAIN_WARP && lane == 0) {
+        // ==================================================== drain =====================================================
+        const int Ms = Ntp <= 64 ? 64 : 128;
+        const uint32_t ones_d = smem_u32(ones);
+        for (int i = 0; i < n_my; ++i) {
+            const int tile = (int)blockIdx.x + i * (int)gridDim.x;
+            const int ob = i % p.OB, useo = i / p.OB;
+            mbar_wait(&bars.out_ready[ob], (uint32_t)(useo & 1));
+            tc_fence_after();
+            const unsigned char* Ot = Osm + (size_t)ob * p.out_bytes;
+            for (int oa = 0; oa < n_oatoms; ++oa) {
+                const unsigned char* src = Ot + (size_t)oa * ATOM_BYTES;
+                if (p.mode == 0) tma_store_2d(&mapO, src, n0 + oa * ATOM_CH, tile * ATOM_ROWS);
+                else
+                    for (int f = 0; f < p.F; ++f)
+                        if ((long long)tile * p.F + f < p.n_frames) tma_store_3d(&mapO, src + (size_t)f * p.slot * 128, n0 + oa * ATOM_CH, 0, tile * p.F + f);
+            }
+            tma_store_commit();
+            if (STATS != 0) {
+                const uint32_t o0 = smem_u32(Ot), acc0 = i == 0 ? 0u : 1u;
+                const uint32_t idesc_1 = idesc_major(Ms, 8, 1, 0);
+                for (int ks = 0; ks < 8; ++ks)
+                    umma_f16(tmem + (uint32_t)p.sum_col, desc_mn_sw128(o0 + ks * 2048u, ATOM_BYTES), desc_ones(ones_d), idesc_1, (acc0 | (uint32_t)ks) ? 1u : 0u);
+                if (STATS == 2) {
+                    const uint32_t s0 = smem_u32(Ssm + (size_t)ob * p.out_bytes);
+                    for (int ks = 0; ks < 8; ++ks)
+                        umma_f16(tmem + (uint32_t)p.stat_col, desc_mn_sw128(s0 + ks * 2048u, ATOM_BYTES), desc_ones(ones_d), idesc_1, (acc0 | (uint32_t)ks) ? 1u : 0u);
+                } else {
+                    const uint32_t idesc_g = idesc_major(Ms, Ntp, 1, 1);
+                    for (int ks = 0; ks < 8; ++ks)
+                        umma_f16(tmem + (uint32_t)p.stat_col, desc_mn_sw128(o0 + ks * 2048u, ATOM_BYTES), desc_mn_sw128(o0 + ks * 2048u, ATOM_BYTES), idesc_g,
+                                 (acc0 | (uint32_t)ks) ? 1u : 0u);
+                }
+                umma_commit(&bars.stat_done[ob]);
+            }
+            tma_store_wait_read<0>();
+            if (STATS != 0) mbar_wait(&bars.stat_done[ob], (uint32_t)(useo & 1));
+            mbar_arrive(&bars.out_free[ob]);
+        }
+        tma_store_wait_all<0>();
     }
     tc_fence_before();
     __syncthreads();
@@ -512,7 +539,7 @@ static bool tc4_plan(const dsg_conv_gemm_args& a, G4Plan& p, bool fold) {
     p.K1p = kat * ATOM_CH;
     p.act = (!fold) ? 1 : 0;                              // ReLU sources (one tensor): CUDA-core prologue in place
     p.xf = (p.act || p.mode != 0) ? 1 : 0;
-    p.has_stats = a.stat_sum != nullptr;
+    p.stats = a.stat_sum == nullptr ? 0 : (a.partner ? 2 : 1);
     const unsigned cf_bytes = (unsigned)((4 * 128 + 2 * p.K1p) * sizeof(float));
     const unsigned budget = 227u * 1024u - 2048u;         // dynamic shared memory we may ask for (static barriers + alignment slack kept)
     const int cand_nt[2] = {128, 64};
@@ -521,7 +548,7 @@ static bool tc4_plan(const dsg_conv_gemm_args& a, G4Plan& p, bool fold) {
         const unsigned wb = (unsigned)p.natoms * Ntile * 128;
         const unsigned ob1 = (unsigned)(Ntile / ATOM_CH) * ATOM_BYTES;
         for (int OB = 2; OB >= 1; --OB) {
-            const unsigned fixed = wb + OB * ob1 * (p.has_stats ? 2u : 1u) + 1024u + ((cf_bytes + 1023u) & ~1023u) + 1024u;
+            const unsigned fixed = wb + OB * ob1 * (p.stats == 2 ? 2u : 1u) + 1024u + ((cf_bytes + 1023u) & ~1023u) + 1024u;
             if (fixed + 3u * ATOM_BYTES > budget) continue;
             int S = (int)((budget - fixed) / ATOM_BYTES);
             if (S > G4_MAX_STAGES) S = G4_MAX_STAGES;
@@ -532,13 +559,14 @@ static bool tc4_plan(const dsg_conv_gemm_args& a, G4Plan& p, bool fold) {
             p.off_out = p.off_a + (unsigned)S * ATOM_BYTES;
             p.out_bytes = ob1;
             p.off_stat = p.off_out + OB * ob1;
-            p.off_ones = p.off_stat + (p.has_stats ? OB * ob1 : 0u);
+            p.off_ones = p.off_stat + (p.stats == 2 ? OB * ob1 : 0u);
             p.off_cf = p.off_ones + 1024u;
             p.smem_total = p.off_cf + ((cf_bytes + 1023u) & ~1023u) + 1024u;
             p.w_tile_bytes = wb;
             p.acc_cols = Ntile <= 32 ? 32 : (Ntile <= 64 ? 64 : 128);
-            p.stat_col = 2 * p.acc_cols;
-            const int need = 2 * p.acc_cols + (p.has_stats ? 16 : 0);
+            p.stat_col = 2 * p.acc_cols;                                   // Gram: acc_cols columns; product sums: 8
+            p.sum_col = p.stat_col + (p.stats == 1 ? p.acc_cols : 8);
+            const int need = p.stats ? p.sum_col + 8 : 2 * p.acc_cols;
             p.tmem_cols = 32;
             while (p.tmem_cols < need) p.tmem_cols <<= 1;
             return true;
@@ -596,21 +624,24 @@ static const char* launch_conv_gemm_tc4(const dsg_conv_gemm_args& a, dsg_stream_
     if (gx < 1) gx = 1;
     if (gx > p.n_tiles) gx = p.n_tiles;
     const bool tails = a.add || a.add2 || a.bcast || a.has_mask || a.partner;
-    const int variant = (p.xf ? 4 : 0) | (tails ? 2 : 0) | (p.has_stats ? 1 : 0);
+    const int variant = (p.xf ? 6 : 0) + (tails ? 3 : 0) + p.stats;
 #define DSG_T4_LAUNCH(XF_, TL_, ST_)                                                                                              \
     do {                                                                                                                          \
         cudaFuncSetAttribute(tc4_gemm_kernel<XF_, TL_, ST_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_total);     \
         tc4_gemm_kernel<XF_, TL_, ST_><<<dim3((unsigned)gx, gy), dim3(G4_THREADS), p.smem_total, st>>>(mA0, mA1, mO, a, p, cbias); \
     } while (0)
     switch (variant) {
-        case 0: DSG_T4_LAUNCH(false, false, false); break;
-        case 1: DSG_T4_LAUNCH(false, false, true); break;
-        case 2: DSG_T4_LAUNCH(false, true, false); break;
-        case 3: DSG_T4_LAUNCH(false, true, true); break;
-        case 4: DSG_T4_LAUNCH(true, false, false); break;
-        case 5: DSG_T4_LAUNCH(true, false, true); break;
-        case 6: DSG_T4_LAUNCH(true, true, false); break;
-        default: DSG_T4_LAUNCH(true, true, true); break;
+        case 0: DSG_T4_LAUNCH(false, false, 0); break;
+        case 1: DSG_T4_LAUNCH(false, false, 1); break;
+        case 3: DSG_T4_LAUNCH(false, true, 0); break;
+        case 4: DSG_T4_LAUNCH(false, true, 1); break;
+        case 5: DSG_T4_LAUNCH(false, true, 2); break;
+        case 6: DSG_T4_LAUNCH(true, false, 0); break;
+        case 7: DSG_T4_LAUNCH(true, false, 1); break;
+        case 9: DSG_T4_LAUNCH(true, true, 0); break;
+        case 10: DSG_T4_LAUNCH(true, true, 1); break;
+        case 11: DSG_T4_LAUNCH(true, true, 2); break;
+        default: return "tc4: statistics with a partner need a tail operand";
     }
 #undef DSG_T4_LAUNCH
     *handled = true;
