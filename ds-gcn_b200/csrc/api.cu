@@ -5,6 +5,7 @@
 #include "conv_gemm_tc2.cuh"
 #include "conv_gemm_tc3.cuh"
 #include "tc4_gemm.cuh"
+#include "tc4_wgrad.cuh"
 #include "graph_agg.cuh"
 #include "ms_temporal_tc.cuh"
 #include "topology.cuh"
@@ -100,7 +101,10 @@ int dsg_conv_wgrad(const dsg_conv_wgrad_args* a, void* stream) {
 #ifndef DSG_EMU
     if (a->dtype == DSG_BF16 && tc_enabled()) {
         bool handled = false;
-        const char* e = dsg::tc::launch_conv_wgrad_tc(*a, (dsg_stream_t)stream, &handled);
+        const char* e = dsg::tc4::launch_conv_wgrad_tc4(*a, (dsg_stream_t)stream, &handled);                           // TMA-fed engine (1x1 convolutions)
+        if (e) return fail("dsg_conv_wgrad", e);
+        if (handled) { ++g_counters[1]; return 0; }
+        e = dsg::tc::launch_conv_wgrad_tc(*a, (dsg_stream_t)stream, &handled);
         if (e) return fail("dsg_conv_wgrad", e);
         if (handled) return 0;
     }

@@ -182,6 +182,45 @@ def test_conv_wgrad_fast_engine(dev, K, N, ext_in):
     close(db, B.sum(0), dtype, "db")
 
 
+@pytest.mark.parametrize("K,N", [(64, 64), (24, 64), (64, 24), (96, 256), (256, 96), (128, 352), (256, 256), (64, 88)])
+@pytest.mark.parametrize("variant", ["plain", "plain1", "act", "ext", "stride2"])
+def test_conv_wgrad_tma_engine(dev, K, N, variant):
+    """The TMA-fed weight-gradient engine (tc4_wgrad.cuh) on the network's 1x1 shapes: e^T x / y^T x accumulators combined with the
+    BatchNorm-backward coefficients after the reduction, ones-MMA column sums (db, the cc term), plain / BN+ReLU / joint-mean /
+    strided-frame x operands, partial last tiles, K and N tiling."""
+    dtype = torch.bfloat16
+    big = dev.type == "cuda"
+    if not big:
+        pytest.skip("tcgen05 + TMA kernel: GPU only (the simulator build runs the CUDA-core engine, covered above)")
+    torch.manual_seed(K * 13 + N)
+    V = 25
+    n, T = 48, 37                                        # 44 400 rows: the last 128-row tile is partial
+    stride = 2 if variant == "stride2" else 1
+    ext_in = variant == "ext"
+    T_in = T * stride
+    rows_in, rows_out = n * T_in * V, n * T * (V + 1 if ext_in else V)
+    x = rnd(rows_in, K, dev=dev, dtype=dtype)
+    a1, b1 = torch.rand(K, device=dev) + 0.5, rnd(K, dev=dev, scale=0.2)
+    e, y = rnd(rows_out, N, dev=dev, dtype=dtype), rnd(rows_out, N, dev=dev, dtype=dtype)
+    ca, cb, cc = torch.rand(N, device=dev) + 0.5, rnd(N, dev=dev, scale=0.3), rnd(N, dev=dev, scale=0.1)
+    dW, db = torch.zeros(N, K, device=dev), torch.zeros(N, device=dev)
+    A_src = ops.Act(x, a1, b1, relu=True) if variant in ("act", "ext") else x
+    B_src = e if variant == "plain1" else ops.Act(e, ca, cc, y, cb)
+    before = _lib.lib().dsg_debug_counter(1)
+    ops.conv_wgrad(A_src, B_src, dW, db=db, n_samples=n, T_in=T_in, T_out=T, Vin=V, ext_in=ext_in, t_mul=stride)
+    A = torch.relu(x.float() * a1 + b1) if variant in ("act", "ext") else x.float()
+    if ext_in:
+        A = A.to(dtype).float().view(n * T, V, K)
+        A = torch.cat([A, A.mean(1, keepdim=True)], 1).reshape(-1, K)
+    if stride == 2:
+        A = A.view(n, T_in, V, K)[:, ::2].reshape(-1, K)
+    B = e.float() if variant == "plain1" else e.float() * ca + cc + y.float() * cb
+    close(dW, B.t() @ A, dtype, "dW")
+    close(db, B.sum(0), dtype, "db")
+    if os.environ.get("DSG_DISABLE_TC4") != "1":
+        assert _lib.lib().dsg_debug_counter(1) == before + 1, "the TMA-fed weight-gradient engine declined a network shape"
+
+
 @pytest.mark.parametrize("dtype", DTYPES)
 @pytest.mark.parametrize("K,N", [(88, 3), (19, 5), (64, 8)])
 def test_conv_gemm_skinny_output(dev, dtype, K, N):
