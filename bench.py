@@ -49,6 +49,7 @@ def parse():
     p.add_argument("--impl", default="ours", choices=["ours", "reference"])
     p.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
     p.add_argument("--no-graph", action="store_true")
+    p.add_argument("--buckets", type=int, default=3, help="gradient buckets (all-reduce overlapped with backward)")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--ref-clips", type=int, default=REF_CLIPS, help="clips per step of the CPU reference arm (N=16: SURVEY 8d)")
     p.add_argument("--ref-budget", type=float, default=240.0, help="seconds the whole reference run may take (the batch shrinks to fit)")
@@ -275,6 +276,11 @@ class ClockSampler:
         return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None, reasons=reasons, samples=len(sm))
 
 
+def _trace(msg):
+    if os.environ.get("DSG_BENCH_TRACE"):
+        print(f"[bench r{os.environ.get('RANK', 0)} {time.strftime('%H:%M:%S')}] {msg}", file=sys.stderr, flush=True)
+
+
 def main():
     args = parse()
     rank = int(os.environ.get("RANK", 0))
@@ -320,8 +326,10 @@ def main():
     B = args.batch
     train = args.mode == "train"
     model.train(train)
-    params = dsgcn_b200.parallel.trainable_parameters(model)      # conv2_se never receives gradients (gcn.py:2253-2254)
-    opt = torch.optim.SGD(params, foreach=True, **SGD) if train else None
+    # flat parameter / gradient buckets in gradient-ready order (conv2_se never receives gradients, gcn.py:2253-2254, and stays
+    # outside); per-bucket all-reduce launched from autograd hooks while backward is still running; one fused SGD launch per bucket
+    gb = dsgcn_b200.parallel.GradBuckets(model, n_buckets=args.buckets) if train else None
+    opt = dsgcn_b200.parallel.FlatSGD(gb, **SGD) if train else None
 
     # synthetic NTU-shaped data: a pool of pinned host batches (e2e) and device-resident batches (value)
     g = torch.Generator().manual_seed(rank)
@@ -331,9 +339,6 @@ def main():
     dev_y = [h.to(dev) for h in host_y]
     sx, sy = dev_x[0].clone(), dev_y[0].clone()
 
-    def allreduce_grads():
-        dsgcn_b200.parallel.allreduce_gradients(params, world)
-
     def device_step(x, y):
         if not train:
             with torch.no_grad():
@@ -341,10 +346,9 @@ def main():
                 return model.cls_head(feat)
         losses = model(x, y, return_loss=True)
         loss = losses["loss_cls"]
-        opt.zero_grad(set_to_none=True)
-        loss.backward()
-        allreduce_grads()
-        opt.step()
+        opt.zero_grad()
+        loss.backward()                  # bucket all-reduces start inside (hooks), overlapped with the remaining backward
+        opt.step()                       # waits for the collectives, then one fused update per bucket
         return loss
 
     # ---- warm-up (eager, on a side stream so no autograd node is tied to the default stream), then CUDA-graph
@@ -361,16 +365,17 @@ def main():
         launches_per_step = L.launch_count - l0
     torch.cuda.current_stream().wait_stream(side)
     torch.cuda.synchronize()
+    _trace("eager warm-up done")
     graph = None
-    if not args.no_graph and world == 1:
+    if not args.no_graph:
         try:
             graph = torch.cuda.CUDAGraph()
-            if opt is not None:
-                opt.zero_grad(set_to_none=True)
-            with torch.cuda.graph(graph):
+            with torch.cuda.graph(graph):            # at N > 1 the NCCL collectives of the step are captured too
                 device_step(sx, sy)
+            _trace("captured")
             graph.replay()
             torch.cuda.synchronize()
+            _trace("first replay done")
         except Exception as e:   # report, fall back to eager launches (still our kernels)
             print(f"[bench] CUDA graph capture failed ({type(e).__name__}: {str(e)[:300]}); timing eager launches", file=sys.stderr)
             graph = None
@@ -403,6 +408,7 @@ def main():
     barrier()
     ms = e0.elapsed_time(e1) / args.steps
     clocks = sampler.stop() if sampler else None
+    _trace(f"timed region done: {ms:.2f} ms/step")
     if world > 1:
         t = torch.tensor([ms], device=dev)
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
@@ -414,10 +420,9 @@ def main():
         x = host_x[i % 2].to(dev, non_blocking=True)
         y = host_y[i % 2].to(dev, non_blocking=True)
         if train:
-            out = model.train_step(dict(keypoint=x, label=y), opt)       # .item() of the loss inside = D2H
-            opt.zero_grad(set_to_none=True)
+            opt.zero_grad()
+            out = model.train_step(dict(keypoint=x, label=y), opt)       # the logged scalars come back to the host inside = D2H
             out["loss"].backward()
-            allreduce_grads()
             opt.step()
             return out["log_vars"]["loss"]
         with torch.no_grad():
@@ -435,8 +440,9 @@ def main():
         t = torch.tensor([e2e_ms], device=dev)
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
         e2e_ms = float(t.item())
+    _trace("e2e done")
     h2d = host_x[0].numel() * 4 + host_y[0].numel() * 8
-    d2h = 4 if train else B * NUM_CLASSES * 4
+    d2h = 16 if train else B * NUM_CLASSES * 4      # train: top1, top5, loss_cls, loss (one packed copy)
 
     # ---- roofline leg: per-ABI-call CUDA events over extra eager steps (same shapes), dominant kernel.
     #      Every rank runs the steps (they contain the gradient all-reduce); only rank 0 reports.
@@ -447,9 +453,16 @@ def main():
     torch.cuda.synchronize()
     L.side_enabled = side_was
     prof, L.profile = L.profile, None
+    _trace("roofline leg done")
     if world > 1:
         torch.distributed.barrier()
+        torch.cuda.synchronize()
+        if graph is not None:            # the captured NCCL kernels hold the communicator: release the graph before tearing it down
+            graph.reset()
+            graph = None
+        _trace("graph released")
         torch.distributed.destroy_process_group()
+        _trace("process group destroyed")
     if rank != 0:
         return
     agg = {}
@@ -510,6 +523,8 @@ def main():
     line = dict(metric=metric, value=value, unit=unit, n_gpus=world, steps=args.steps, warmup=args.warmup, ms_per_step=ms,
                 higher_is_better=True, scaling="weak", vs_baseline=None, dtype=args.dtype, data="synthetic",
                 config=dict(workload=workload, clips_per_gpu=B, M=M_, T=T_, V=V_, C=C_, parallelism=f"dp{world}", cuda_graph=graph is not None,
+                            allreduce=(f"{len(gb.buckets)} flat buckets ({gb.grad_bytes()} B), NCCL AVG launched from autograd hooks during backward"
+                                       if (train and world > 1) else None),
                             cache="inputs + activations per step (~GBs) exceed the 126 MB L2; two input batches alternate"),
                 e2e=dict(value=world * B / (e2e_ms * 1e-3), unit=unit, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, ms_per_step=e2e_ms),
                 gpu_launches=launches_per_step * args.steps, abi_calls_per_step=launches_per_step, kernels_per_step_ncu=own_kernels, clocks=clocks, roofline=roofline, cpu_baseline=cpu, extra=extra)

@@ -118,6 +118,7 @@ EXPORTS = {
     "dsg_ms_temporal_bwd_data": (c_int, [C.POINTER(MsTemporalArgs), vp]),
     "dsg_ms_temporal_bwd_weight": (c_int, [C.POINTER(MsTemporalArgs), vp]),
     "dsg_sgd_step": (c_int, [vp, vp, vp, c_ll, c_f, c_f, c_f, c_int, c_f, vp]),
+    "dsg_sgd_step_dev": (c_int, [vp, vp, vp, c_ll, vp, c_f, c_f, c_int, c_f, vp]),
     "dsg_debug_counter": (c_ll, [c_int]),
     "dsg_last_error": (C.c_char_p, []),
     "dsg_abi_version": (c_int, []),

@@ -268,9 +268,18 @@ int dsg_pointwise(const dsg_pointwise_args* a, void* stream) {
 int dsg_sgd_step(float* p, const float* grad, float* buf, long long n, float lr, float momentum, float wd,
                  int nesterov, float grad_scale, void* stream) {
     if (n <= 0) return 0;
-    dsg_launch(dsg::sgd_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, (dsg_stream_t)stream, p, grad, buf, n, lr, momentum, wd,
-               nesterov, grad_scale);
+    dsg_launch(dsg::sgd_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, (dsg_stream_t)stream, p, grad, buf, n, lr, (const float*)nullptr,
+               momentum, wd, nesterov, grad_scale);
     DSG_RET("dsg_sgd_step", dsg_launch_error());
+}
+
+int dsg_sgd_step_dev(float* p, const float* grad, float* buf, long long n, const float* lr_dev, float momentum, float wd,
+                     int nesterov, float grad_scale, void* stream) {
+    if (n <= 0) return 0;
+    if (!lr_dev) return fail("dsg_sgd_step_dev", "lr_dev is null");
+    dsg_launch(dsg::sgd_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, (dsg_stream_t)stream, p, grad, buf, n, 0.f, lr_dev, momentum, wd,
+               nesterov, grad_scale);
+    DSG_RET("dsg_sgd_step_dev", dsg_launch_error());
 }
 
 }  // extern "C"

@@ -440,9 +440,10 @@ __global__ void __launch_bounds__(PW_THREADS) ms_combine_bwd_e_kernel(dsg_ms_com
 }
 
 // ---------------------------------------------------------------------------------------------
-__global__ void sgd_kernel(float* p, const float* g, float* buf, long long n, float lr, float mom, float wd, int nesterov, float gscale) {
+__global__ void sgd_kernel(float* p, const float* g, float* buf, long long n, float lr, const float* lr_dev, float mom, float wd, int nesterov, float gscale) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    if (lr_dev) lr = lr_dev[0];
     float gr = g[i] * gscale + wd * p[i];
     float b = mom * buf[i] + gr;
     buf[i] = b;

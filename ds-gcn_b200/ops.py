@@ -374,5 +374,11 @@ def ms_temporal_bwd(a, dfeat, e, oglob, e_sum, e_sq, dadd_coeff):
 
 
 def sgd_step(p, grad, buf, lr, momentum, wd, nesterov, grad_scale=1.0):
+    """`lr`: a Python float, or a one-element fp32 tensor on the device (read by the kernel: CUDA-graph friendly schedules)."""
     assert p.is_contiguous() and grad.is_contiguous() and buf.is_contiguous()
-    L.call("dsg_sgd_step", L.ptr(p), L.ptr(grad), L.ptr(buf), p.numel(), lr, momentum, wd, int(nesterov), grad_scale, L.stream())
+    assert p.dtype == grad.dtype == buf.dtype == torch.float32 and p.numel() == grad.numel() == buf.numel()
+    if isinstance(lr, torch.Tensor):
+        assert lr.dtype == torch.float32 and lr.numel() == 1
+        L.call("dsg_sgd_step_dev", L.ptr(p), L.ptr(grad), L.ptr(buf), p.numel(), L.ptr(lr), momentum, wd, int(nesterov), grad_scale, L.stream())
+    else:
+        L.call("dsg_sgd_step", L.ptr(p), L.ptr(grad), L.ptr(buf), p.numel(), lr, momentum, wd, int(nesterov), grad_scale, L.stream())

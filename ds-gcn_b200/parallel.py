@@ -1,13 +1,29 @@
-"""Data-parallel plumbing for the DS-GCN path.
+"""Data-parallel plumbing for the DS-GCN path and the step that follows it (SGD, schedule).
 
 The reference trains under DDP with plain (per-rank) BatchNorm statistics and `broadcast_buffers=False`
 (pyskl/apis/train.py:93-104): every op on the hot path is independent across clips, so the only collective is the
-gradient all-reduce (mean) once per step.  Parameters that never receive a gradient (`conv2_se.*`,
-gcn.py:2253-2254) are skipped, which keeps SGD from touching them — the same as the reference, whose optimizer skips
-`grad is None`.  One flat buffer, one NCCL launch (5.5 MB: latency-bound, not bandwidth-bound)."""
+gradient all-reduce (mean).  DDP's reducer buckets the gradients and launches each bucket's all-reduce as soon as its
+last gradient has been produced, so the collective overlaps the rest of backward; `GradBuckets` does the same with
+
+  * pre-registered FLAT buffers: the parameters of a bucket and their gradients are views of one fp32 buffer each
+    (`p.data`, `p.grad`), so there is no flatten / unflatten copy around the collective and the optimizer update is ONE
+    kernel launch per bucket (`dsg_sgd_step_dev`, learning rate read from device memory);
+  * buckets in gradient-ready order (head, blocks 9..0, data_bn): blocks 7-9 hold ~74 % of the parameters but only the
+    first quarter of the backward time, so with three buckets only the small last one (shallow blocks, ~0.1 MB) is exposed;
+  * one NCCL all-reduce (`ReduceOp.AVG`) per bucket, launched from a post-accumulate-grad hook with `async_op=True` (NCCL's own
+    stream; the current stream only waits in `synchronize()`, right before the update).  All of it is CUDA-graph capturable:
+    bench.py captures forward + backward + collectives + update in one graph per rank at every N.
+
+Parameters that never receive a gradient (`conv2_se.*`, gcn.py:2253-2254) stay outside the buckets, which keeps SGD from touching
+them — the same as the reference, whose optimizer skips `grad is None`.
+"""
+import math
+
 import torch
 import torch.distributed as dist
 from torch._utils import _flatten_dense_tensors, _unflatten_dense_tensors
+
+from . import ops
 
 
 def trainable_parameters(model):
@@ -15,21 +31,24 @@ def trainable_parameters(model):
     return [p for n, p in model.named_parameters() if "conv2_se" not in n and p.requires_grad]
 
 
+def _dist_on():
+    return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+
+
 def broadcast_parameters(model, src=0):
     """Replicate rank `src`'s parameters and buffers (DDP does this once at construction)."""
-    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+    if not _dist_on():
         return
     for t in list(model.parameters()) + list(model.buffers()):
         dist.broadcast(t.data, src)
 
 
 def allreduce_gradients(params, world_size=None):
-    """Mean of the per-rank gradients, in place, with a single collective over one flat buffer."""
-    if not (dist.is_available() and dist.is_initialized()):
+    """Mean of the per-rank gradients, in place, with a single collective over one flat buffer (the simple, un-overlapped
+    form; `GradBuckets` is the one the benchmark uses)."""
+    if not _dist_on():
         return
     world_size = world_size or dist.get_world_size()
-    if world_size == 1:
-        return
     grads = [p.grad for p in params if p.grad is not None]
     if not grads:
         return
@@ -39,5 +58,183 @@ def allreduce_gradients(params, world_size=None):
     else:
         dist.all_reduce(flat)
         flat.div_(world_size)
-    # scatter back with multi-tensor copies (a handful of launches instead of one per parameter)
     torch._foreach_copy_(grads, list(_unflatten_dense_tensors(flat, grads)))
+
+
+def _group_key(name):
+    """Bucket granularity: 'backbone.gcn.7.tcn.bn.weight' -> 'backbone.gcn.7' (one block); 'backbone.data_bn.weight' ->
+    'backbone.data_bn'; 'cls_head.fc_cls.weight' -> 'cls_head'."""
+    parts = name.split(".")
+    for i in range(len(parts) - 1):
+        if parts[i] == "gcn" and parts[i + 1].isdigit():
+            return ".".join(parts[:i + 2])
+    if parts[0] == "backbone" and len(parts) > 2:
+        return ".".join(parts[:2])
+    return parts[0]
+
+
+class _Bucket:
+    __slots__ = ("params", "names", "flat_p", "flat_g", "flat_m", "pending", "work")
+
+
+class GradBuckets:
+    """Flat parameter / gradient buffers in gradient-ready order + overlapped per-bucket all-reduce.
+
+        gb = GradBuckets(model, n_buckets=3)        # after model.to(device) and broadcast_parameters
+        gb.zero_grad(); loss.backward(); gb.synchronize(); <update reading gb.buckets[i].flat_p / flat_g>
+    """
+    ALIGN = 64          # floats: every parameter view starts on a 256-byte boundary (vectorised reductions, TMA-able slices)
+
+    def __init__(self, model, n_buckets=3, overlap=True):
+        named = [(n, p) for n, p in model.named_parameters() if "conv2_se" not in n and p.requires_grad]
+        if not named:
+            raise ValueError("no trainable parameters")
+        dev = named[0][1].device
+        for n, p in named:
+            if p.dtype != torch.float32 or p.device != dev:
+                raise ValueError(f"{n}: parameters must be fp32 on one device")
+        ready = list(reversed(named))                 # autograd produces gradients from the head back to data_bn
+        groups, cur = [], None
+        for n, p in ready:
+            k = _group_key(n)
+            if k != cur:
+                groups.append([])
+                cur = k
+            groups[-1].append((n, p))
+        n_buckets = max(1, min(n_buckets, len(groups)))
+        per = math.ceil(len(groups) / n_buckets)
+        self.buckets = []
+        for b in range(n_buckets):
+            items = [it for g in groups[b * per:(b + 1) * per] for it in g]
+            if not items:
+                continue
+            bk = _Bucket()
+            bk.names = [n for n, _ in items]
+            bk.params = [p for _, p in items]
+            offs, tot = [], 0
+            for p in bk.params:
+                offs.append(tot)
+                tot += (p.numel() + self.ALIGN - 1) // self.ALIGN * self.ALIGN
+            bk.flat_p = torch.zeros(tot, dtype=torch.float32, device=dev)
+            bk.flat_g = torch.zeros(tot, dtype=torch.float32, device=dev)
+            bk.flat_m = None
+            with torch.no_grad():
+                for p, o in zip(bk.params, offs):
+                    view = bk.flat_p[o:o + p.numel()].view(p.shape)
+                    view.copy_(p.data)
+                    p.data = view                                   # the module's parameter now lives in the flat buffer
+                    p.grad = bk.flat_g[o:o + p.numel()].view(p.shape)
+            bk.pending, bk.work = len(bk.params), None
+            self.buckets.append(bk)
+        self.params = [p for bk in self.buckets for p in bk.params]
+        self.world = dist.get_world_size() if _dist_on() else 1
+        self.overlap = overlap
+        self._avg_in_collective = _dist_on() and dist.get_backend() == "nccl"
+        self._hooks = []
+        if self.world > 1 and overlap:
+            for bk in self.buckets:
+                for p in bk.params:
+                    self._hooks.append(p.register_post_accumulate_grad_hook(self._make_hook(bk)))
+
+    def _make_hook(self, bk):
+        def hook(_p):
+            bk.pending -= 1
+            if bk.pending == 0:
+                self._launch(bk)
+        return hook
+
+    def _launch(self, bk):
+        if self._avg_in_collective:
+            bk.work = dist.all_reduce(bk.flat_g, op=dist.ReduceOp.AVG, async_op=True)
+        else:
+            bk.work = dist.all_reduce(bk.flat_g, async_op=True)
+
+    def zero_grad(self):
+        """One memset per bucket; gradients stay views of the flat buffers (never set to None)."""
+        for bk in self.buckets:
+            bk.flat_g.zero_()
+            bk.pending, bk.work = len(bk.params), None
+            for p in bk.params:                                      # a foreign zero_grad(set_to_none=True) would detach the views
+                if p.grad is None or p.grad.data_ptr() < bk.flat_g.data_ptr() or p.grad.data_ptr() >= bk.flat_g.data_ptr() + bk.flat_g.numel() * 4:
+                    self._reattach(bk)
+                    break
+
+    def _reattach(self, bk):
+        o = 0
+        for p in bk.params:
+            p.grad = bk.flat_g[o:o + p.numel()].view(p.shape)
+            o += (p.numel() + self.ALIGN - 1) // self.ALIGN * self.ALIGN
+
+    def synchronize(self):
+        """After backward: make the current stream wait for every bucket's collective (launching the ones whose hooks did
+        not fire, e.g. overlap=False or a parameter that received no gradient this step)."""
+        if self.world == 1:
+            return
+        for bk in self.buckets:
+            if bk.work is None:
+                self._launch(bk)
+        for bk in self.buckets:
+            bk.work.wait()
+            if not self._avg_in_collective:
+                bk.flat_g.div_(self.world)
+            bk.work = None
+            bk.pending = len(bk.params)
+
+    def grad_bytes(self):
+        return sum(bk.flat_g.numel() * 4 for bk in self.buckets)
+
+
+class FlatSGD:
+    """SGD with momentum / weight decay / Nesterov (torch.optim.SGD semantics, dampening 0) over GradBuckets: one
+    `dsg_sgd_step_dev` launch per bucket.  Reference: optimizer = dict(type='SGD', lr=0.1, momentum=0.9, weight_decay=5e-4,
+    nesterov=True) (configs/_init_/lr_schedual.py:11), driven by mmcv's OptimizerHook as zero_grad() / backward / step().
+    `param_groups[0]['lr']` is what a scheduler sets; the kernel reads it from device memory (`set_lr`), so a captured step
+    follows the schedule without re-capture."""
+
+    def __init__(self, buckets, lr=0.1, momentum=0.9, weight_decay=0.0, nesterov=False, dampening=0):
+        if dampening != 0:
+            raise NotImplementedError("dampening != 0")
+        if nesterov and momentum <= 0:
+            raise ValueError("Nesterov momentum requires a momentum")
+        self.gb = buckets
+        self.param_groups = [dict(params=buckets.params, lr=lr, initial_lr=lr, momentum=momentum, weight_decay=weight_decay,
+                                  nesterov=nesterov, dampening=0)]
+        dev = buckets.buckets[0].flat_p.device
+        self._lr_dev = torch.full((1,), float(lr), dtype=torch.float32, device=dev)
+        self._lr_host = float(lr)
+        for bk in buckets.buckets:
+            bk.flat_m = torch.zeros_like(bk.flat_p)
+
+    def set_lr(self, lr):
+        """Host -> device refresh of the learning rate (call outside a captured region)."""
+        self.param_groups[0]["lr"] = float(lr)
+        if float(lr) != self._lr_host:
+            self._lr_dev.fill_(float(lr))
+            self._lr_host = float(lr)
+
+    def zero_grad(self, set_to_none=False):
+        self.gb.zero_grad()
+
+    def step(self):
+        g = self.param_groups[0]
+        if g["lr"] != self._lr_host and not (self._lr_dev.is_cuda and torch.cuda.is_current_stream_capturing()):
+            self.set_lr(g["lr"])
+        self.gb.synchronize()
+        for bk in self.gb.buckets:
+            ops.sgd_step(bk.flat_p, bk.flat_g, bk.flat_m, self._lr_dev, g["momentum"], g["weight_decay"], g["nesterov"])
+
+    def state_dict(self):
+        return dict(param_groups=[{k: v for k, v in self.param_groups[0].items() if k != "params"}],
+                    momentum=[bk.flat_m.clone() for bk in self.gb.buckets])
+
+    def load_state_dict(self, sd):
+        self.param_groups[0].update(sd["param_groups"][0])
+        for bk, m in zip(self.gb.buckets, sd["momentum"]):
+            bk.flat_m.copy_(m)
+        self.set_lr(self.param_groups[0]["lr"])
+
+
+def cosine_lr(base_lr, it, total_iters, min_lr=0.0):
+    """mmcv CosineAnnealingLrUpdaterHook with by_epoch=False (configs/_init_/lr_schedual.py:12): annealing_cos(base, min, it/total)."""
+    f = min(max(it / max(total_iters, 1), 0.0), 1.0)
+    return min_lr + 0.5 * (base_lr - min_lr) * (1.0 + math.cos(math.pi * f))

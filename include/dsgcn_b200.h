@@ -342,6 +342,10 @@ int dsg_pointwise(const dsg_pointwise_args* a, void* stream);
  * p -= lr*(nesterov ? g + mom*buf : buf). */
 int dsg_sgd_step(float* p, const float* grad, float* buf, long long n, float lr, float momentum, float wd,
                  int nesterov, float grad_scale, void* stream);
+/* The same update with the learning rate read from device memory (`lr_dev[0]`), so a CUDA-graph-captured step follows
+ * the cosine schedule (configs/_init_/lr_schedual.py:12: CosineAnnealing, by_epoch=False) without re-capture. */
+int dsg_sgd_step_dev(float* p, const float* grad, float* buf, long long n, const float* lr_dev, float momentum, float wd,
+                     int nesterov, float grad_scale, void* stream);
 
 /* Launch counters of the engines behind the entry points (diagnostics for the tests and bench.py: which engine ran).
  * id 0: TMA-fed tcgen05 GEMM (tc4)   1: TMA-fed tcgen05 weight gradient (tc4w)   2: fused adjacency-contraction + post GEMM.
