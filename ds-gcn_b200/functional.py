@@ -67,6 +67,51 @@ def _empty32(n, dev):
     return torch.empty(n, dtype=torch.float32, device=dev)
 
 
+# ---- parameter packing hooks (parallel.GradBuckets) -------------------------------------------------------------------
+# When GradBuckets has packed a model, a parameter's gradient lives in a pre-zeroed flat buffer (`p.grad` is a view of it and
+# the parameter carries `_dsg_sink`), and parameters that are always used concatenated (pre|down, conv1|conv2|conv1_se, the
+# branch 1x1 convolutions) are adjacent in the flat buffers, so the concatenation and the gradient of the concatenation are
+# zero-copy views (`module._dsg_flat[key] = (param_view, grad_view)`).  The kernels then accumulate straight into the flat
+# gradient buffer: no torch.cat, no per-parameter zero fill, no accumulate-add, no flatten before the all-reduce.
+# Without GradBuckets (unit tests, plain torch optimizers) every helper falls back to fresh tensors.
+
+def cat_params(m, key, params, shape):
+    fl = getattr(m, "_dsg_flat", None)
+    if fl is not None and key in fl:
+        return fl[key][0]
+    if len(params) == 1:
+        return params[0].view(shape)
+    return torch.cat([p.reshape(-1) for p in params]).view(shape)
+
+
+def _sink(p):
+    return p.grad if (getattr(p, "_dsg_sink", False) and p.grad is not None) else None
+
+
+def grad_like(p, zero=True):
+    """gradient accumulator for parameter `p`: its flat-buffer view (pre-zeroed by GradBuckets.zero_grad) or a fresh tensor"""
+    g = _sink(p)
+    if g is not None:
+        return g
+    return torch.zeros_like(p) if zero else torch.empty_like(p)
+
+
+def grad_cat(m, key, params, shape, grads):
+    """gradient accumulator for cat(params) viewed as `shape`; registers the per-parameter views in `grads`"""
+    fl = getattr(m, "_dsg_flat", None)
+    if fl is not None and key in fl and all(_sink(p) is not None for p in params):
+        g = fl[key][1]
+        for p in params:
+            grads[p] = p.grad
+        return g
+    g = torch.zeros(shape, dtype=torch.float32, device=params[0].device)
+    flat, o = g.view(-1), 0
+    for p in params:
+        grads[p] = flat[o:o + p.numel()].view(p.shape)
+        o += p.numel()
+    return g
+
+
 def bn_uses_batch_stats(bn):
     """nn.BatchNorm semantics (torch/nn/modules/batchnorm.py): batch statistics iff the BatchNorm ITSELF is in training mode or keeps
     no running estimates — the flags of the real child module decide, not the parent unit's (frozen-BN fine-tuning calls
@@ -143,7 +188,7 @@ class BNBack:
 
     def add_bn(self, bn, lo, hi, count, grads):
         sl = slice(lo, hi)
-        dg, db = torch.empty_like(bn.weight), torch.empty_like(bn.bias)
+        dg, db = grad_like(bn.weight, zero=False), grad_like(bn.bias, zero=False)
         grads[bn.weight], grads[bn.bias] = dg, db
         self.jobs.append(ops.bn_job(2 if self.fwd.batch[(lo, hi)] else 3, hi - lo, sum=self.stats[0, sl], sq=self.stats[1, sl], count=count,
                                     gamma=bn.weight, save_mean=self.fwd.mean[sl], save_invstd=self.fwd.invstd[sl],
@@ -179,8 +224,8 @@ def dgphgcn1_forward(m, x, n, T, V, save):
 
     # ---- topology branch: temporal mean -> 9R features per joint -> per-sample adjacency
     xm = ops.tmean(x, n, T, V)                                                  # [n,V,Cin] fp32
-    Wt = torch.cat([m.conv1.weight, m.conv2.weight, m.conv1_se.weight]).view(9 * R, Cin)
-    bt = torch.cat([m.conv1.bias, m.conv2.bias, m.conv1_se.bias])
+    Wt = cat_params(m, "Wt", [m.conv1.weight, m.conv2.weight, m.conv1_se.weight], (9 * R, Cin))
+    bt = cat_params(m, "bt", [m.conv1.bias, m.conv2.bias, m.conv1_se.bias], (9 * R,))
     xm2 = xm.view(n * V, Cin)
     H = torch.empty(n * V, 9 * R, dtype=torch.float32, device=dev)
     ops.conv_gemm(xm2, Wt, 9 * R, H, n_samples=n, T_in=1, T_out=1, Vin=V, bias=bt)
@@ -192,8 +237,8 @@ def dgphgcn1_forward(m, x, n, T, V, save):
     # ---- pre (+down) 1x1 convolutions in one GEMM, BatchNorm statistics in the epilogue
     Npd = KC + (Cout if has_down else 0)
     if has_down:
-        Wpd = torch.cat([m.pre[0].weight, m.down[0].weight]).view(Npd, Cin)
-        bpd = torch.cat([m.pre[0].bias, m.down[0].bias])
+        Wpd = cat_params(m, "Wpd", [m.pre[0].weight, m.down[0].weight], (Npd, Cin))
+        bpd = cat_params(m, "bpd", [m.pre[0].bias, m.down[0].bias], (Npd,))
     else:
         Wpd, bpd = m.pre[0].weight.view(KC, Cin), m.pre[0].bias
     PD = torch.empty(rows, Npd, dtype=dt, device=dev)
@@ -230,18 +275,6 @@ def dgphgcn1_forward(m, x, n, T, V, save):
     return out
 
 
-def _zeros_f32(dev, *shapes):
-    """Several zero-initialised fp32 gradient accumulators carved from ONE buffer (one fill launch instead of one per
-    tensor); every view starts on a 256-byte boundary, as the vectorised reductions of the kernels want."""
-    sizes = [int(math.prod(sh)) for sh in shapes]
-    offs, tot = [], 0
-    for nel in sizes:
-        offs.append(tot)
-        tot += (nel + 63) // 64 * 64
-    flat = torch.zeros(tot, dtype=torch.float32, device=dev)
-    return [flat[o:o + nel].view(sh) for o, nel, sh in zip(offs, sizes, shapes)]
-
-
 def dgphgcn1_backward(m, sv, dout, grads, extra_add=None):
     """dout: gradient w.r.t. the unit output [rows, C_out].  Fills `grads` {param: grad}; returns dx.
     `extra_add` (optional, [rows, C_in]) is added to dx inside the last kernel's epilogue."""
@@ -268,10 +301,15 @@ def dgphgcn1_backward(m, sv, dout, grads, extra_add=None):
     b_z.run()
     dZ = b_z.dy(E4, Z)
 
-    # every parameter-gradient accumulator of the unit: one buffer, one fill
-    dWpost, dbpost, dA, dal, dbe, dWe, dbe_l, dWt, dbt, dWpd, dbpd = _zeros_f32(
-        dev, m.post.weight.shape, m.post.bias.shape, m.A.shape, m.alpha.shape, m.beta.shape, m.edge_linears.weight.shape,
-        m.edge_linears.bias.shape, (9 * R, Cin), (9 * R,), (Npd, Cin), (Npd,))
+    # every parameter-gradient accumulator of the unit: views of the flat gradient buffer when the model is packed
+    # (GradBuckets), else fresh zeros
+    dWpost, dbpost, dA, dal, dbe = (grad_like(q) for q in (m.post.weight, m.post.bias, m.A, m.alpha, m.beta))
+    dWe, dbe_l = grad_like(m.edge_linears.weight), grad_like(m.edge_linears.bias)
+    dWt = grad_cat(m, "Wt", [m.conv1.weight, m.conv2.weight, m.conv1_se.weight], (9 * R, Cin), grads)
+    dbt = grad_cat(m, "bt", [m.conv1.bias, m.conv2.bias, m.conv1_se.bias], (9 * R,), grads)
+    pd_w = [m.pre[0].weight] + ([m.down[0].weight] if has_down else [])
+    pd_b = [m.pre[0].bias] + ([m.down[0].bias] if has_down else [])
+    dWpd, dbpd = grad_cat(m, "Wpd", pd_w, (Npd, Cin), grads), grad_cat(m, "bpd", pd_b, (Npd,), grads)
 
     # ---- post conv backward
     dY = torch.empty(rows, KC, dtype=dt, device=dev)
@@ -299,8 +337,6 @@ def dgphgcn1_backward(m, sv, dout, grads, extra_add=None):
     grads[m.A], grads[m.alpha], grads[m.beta] = dA, dal, dbe
     grads[m.edge_linears.weight], grads[m.edge_linears.bias] = dWe, dbe_l
     ops.conv_wgrad(xm2, dH, dWt, db=dbt, n_samples=n, T_in=1, T_out=1, Vin=V)
-    for conv, lo, hi in ((m.conv1, 0, 2 * R), (m.conv2, 2 * R, 4 * R), (m.conv1_se, 4 * R, 9 * R)):
-        grads[conv.weight], grads[conv.bias] = dWt[lo:hi].view_as(conv.weight), dbt[lo:hi]
     dxm = torch.empty(n * V, Cin, dtype=torch.float32, device=dev)
     ops.conv_gemm(dH, Wt, Cin, dxm, n_samples=n, T_in=1, T_out=1, Vin=V, ws=(1, Cin, 0))
 
@@ -316,9 +352,6 @@ def dgphgcn1_backward(m, sv, dout, grads, extra_add=None):
         ops.conv_gemm(dPD, Wpd, Cin, dx, n_samples=n, T_in=T, T_out=T, Vin=V, ws=(1, Cin, 0), add=E4, add2=extra_add, bcast=dxm,
                       bcast_scale=1.0 / T)
     ops.conv_wgrad(x, dPD, dWpd, db=dbpd, n_samples=n, T_in=T, T_out=T, Vin=V)
-    grads[m.pre[0].weight], grads[m.pre[0].bias] = dWpd[:KC].view_as(m.pre[0].weight), dbpd[:KC]
-    if has_down:
-        grads[m.down[0].weight], grads[m.down[0].bias] = dWpd[KC:].view_as(m.down[0].weight), dbpd[KC:]
     return dx
 
 
@@ -361,7 +394,7 @@ def _ms_fused_args(m, layout, b_act, n, T, T_out, s, V, has_ext, grads):
             conv = m.branches[j][3].conv
             dW = db = None
             if grads is not None:
-                dW, db = torch.zeros_like(conv.weight), torch.zeros_like(conv.bias)
+                dW, db = grad_like(conv.weight), grad_like(conv.bias)
                 grads[conv.weight], grads[conv.bias] = dW, db
             weights[j] = (conv.weight, conv.bias, dW, db)
     a = ops.ms_temporal_args(b_act, layout, weights, n=n, T_in=T, T_out=T_out, stride=s, V=V, has_ext=has_ext,
@@ -383,8 +416,8 @@ def mstcn_forward(m, g, n, T, V, save, res=None, final_relu=False):
 
     # ---- all branch 1x1 convolutions as one GEMM over the (V+1)-joint tensor
     convs = [m.branches[j] if kind == "1x1" else m.branches[j][0] for j, (kind, *_) in enumerate(layout)]
-    Wbr = torch.cat([c.weight for c in convs]).view(Ct, Cin)
-    bbr = torch.cat([c.bias for c in convs])
+    Wbr = cat_params(m, "Wbr", [c.weight for c in convs], (Ct, Cin))
+    bbr = cat_params(m, "bbr", [c.bias for c in convs], (Ct,))
     rows_b = n * T * Vp
     B = torch.empty(rows_b, Ct, dtype=dt, device=dev)
     c_b = BNCoef(Ct, dev, [m.branches[j][1] for j, (kind, *_) in enumerate(layout) if kind != "1x1"])
@@ -476,7 +509,10 @@ def mstcn_backward(m, sv, dout, grads):
     E2 = torch.empty(rows_f, Ct, dtype=dt, device=dev)
     ops.conv_gemm(dU, tr.weight.view(Cout, Ct), Ct, E2, n_samples=n, T_in=T_out, T_out=T_out, Vin=V, ws=(1, Ct, 0),
                   mask=Act(feat, c_t.a, c_t.b), stat_sum=b_t.ssum, stat_sq=b_t.ssq, partner=feat)
-    dWtr, dbtr, dWbr, dbbr = _zeros_f32(dev, tr.weight.shape, tr.bias.shape, (Ct, Cin), (Ct,))
+    dWtr, dbtr = grad_like(tr.weight), grad_like(tr.bias)
+    convs = [m.branches[j] if kind == "1x1" else m.branches[j][0] for j, (kind, *_) in enumerate(layout)]
+    dWbr = grad_cat(m, "Wbr", [c.weight for c in convs], (Ct, Cin), grads)
+    dbbr = grad_cat(m, "bbr", [c.bias for c in convs], (Ct,), grads)
     ops.conv_wgrad(Act(feat, c_t.a, c_t.b, relu=True), dU, dWtr, db=dbtr, n_samples=n, T_in=T_out, T_out=T_out, Vin=V)
     grads[tr.weight], grads[tr.bias] = dWtr, dbtr
     b_t.add_bn(m.transform[0], 0, Ct, rows_f, grads)
@@ -485,7 +521,7 @@ def mstcn_backward(m, sv, dout, grads):
 
     b_b = BNBack(c_b)
     E3 = torch.empty(rows_b, Ct, dtype=dt, device=dev)
-    dadd = torch.zeros_like(m.add_coeff) if has_ext else None
+    dadd = grad_like(m.add_coeff) if has_ext else None
     if has_ext:
         grads[m.add_coeff] = dadd
     fused = _ms_fused_args(m, layout, Act(B, c_b.a, c_b.b), n, T, T_out, s, V, has_ext, grads)
@@ -509,7 +545,7 @@ def mstcn_backward(m, sv, dout, grads):
             ops.conv_gemm(d_o[:, lo:hi], conv.weight, w, E3[:, lo:hi], n_samples=n, T_in=T_out, T_out=T, Vin=Vp, ws=(k, w * k, 1), taps=k,
                           tap_step=-d, tap_off=pad, t_div=s, mask=Act(B[:, lo:hi], c_b.a[lo:hi], c_b.b[lo:hi]),
                           stat_sum=b_b.ssum[lo:hi], stat_sq=b_b.ssq[lo:hi], partner=B[:, lo:hi])
-            dWc, dbc = torch.zeros_like(conv.weight), torch.zeros_like(conv.bias)
+            dWc, dbc = grad_like(conv.weight), grad_like(conv.bias)
             ops.conv_wgrad(Act(B[:, lo:hi], c_b.a[lo:hi], c_b.b[lo:hi], relu=True), d_o[:, lo:hi], dWc, db=dbc, n_samples=n, T_in=T,
                            T_out=T_out, Vin=Vp, taps=k, tap_step=d, tap_off=-pad, t_mul=s)
             grads[conv.weight], grads[conv.bias] = dWc, dbc
@@ -525,9 +561,6 @@ def mstcn_backward(m, sv, dout, grads):
     dg = torch.empty(n * T * V, Cin, dtype=dt, device=dev)
     ops.conv_gemm(dB, sv["Wbr"], Cin, dg, n_samples=n, T_in=T, T_out=T, Vin=Vp, ws=(1, Cin, 0), contract_ext=has_ext)
     ops.conv_wgrad(g, dB, dWbr, db=dbbr, n_samples=n, T_in=T, T_out=T, Vin=V, ext_in=has_ext)
-    for j, (kind, lo, hi, _) in enumerate(layout):
-        conv = m.branches[j] if kind == "1x1" else m.branches[j][0]
-        grads[conv.weight], grads[conv.bias] = dWbr[lo:hi].view_as(conv.weight), dbbr[lo:hi]
     return dg, E
 
 
@@ -575,7 +608,7 @@ def unit_tcn_raw_backward(m, sv, E, grads, e_is_masked_sum_done=False):
     dx = torch.empty(n * T * V, Cin, dtype=dt, device=dev)
     ops.conv_gemm(dR, m.conv.weight, Cin, dx, n_samples=n, T_in=T_out, T_out=T, Vin=V, ws=(k, Cin * k, 1), taps=k, tap_step=-d,
                   tap_off=pad, t_div=s)
-    dW, db = torch.zeros_like(m.conv.weight), torch.zeros_like(m.conv.bias)
+    dW, db = grad_like(m.conv.weight), grad_like(m.conv.bias)
     ops.conv_wgrad(x, dR, dW, db=db, n_samples=n, T_in=T, T_out=T_out, Vin=V, taps=k, tap_step=d, tap_off=-pad, t_mul=s)
     grads[m.conv.weight], grads[m.conv.bias] = dW, db
     return dx
@@ -679,7 +712,7 @@ def unit_gcn_backward(m, sv, dout, grads, extra_add=None):
     dZ = b_z.dy(E, Z)
     dA = torch.zeros_like(A_eff)
     dx = torch.empty(rows, Cin, dtype=dt, device=dev)
-    dW, db = torch.zeros_like(m.conv.weight), torch.zeros_like(m.conv.bias)
+    dW, db = grad_like(m.conv.weight), grad_like(m.conv.bias)
     add = E if (m.with_res and not has_down) else None
     add2 = extra_add
     if has_down:
@@ -690,7 +723,7 @@ def unit_gcn_backward(m, sv, dout, grads, extra_add=None):
         dD = b_d.dy(E, D)
         dxd = torch.empty(rows, Cin, dtype=dt, device=dev)
         ops.conv_gemm(dD, m.down[0].weight, Cin, dxd, n_samples=n, T_in=T, T_out=T, Vin=V, ws=(1, Cin, 0))
-        dWd, dbd = torch.zeros_like(m.down[0].weight), torch.zeros_like(m.down[0].bias)
+        dWd, dbd = grad_like(m.down[0].weight), grad_like(m.down[0].bias)
         ops.conv_wgrad(x, dD, dWd, db=dbd, n_samples=n, T_in=T, T_out=T, Vin=V)
         grads[m.down[0].weight], grads[m.down[0].bias] = dWd, dbd
         add = dxd

@@ -92,7 +92,20 @@ class _KernelFn(torch.autograd.Function):
         dx = from_rows(dx, n, t, v)
         if dx.dtype != ctx.x_dtype:
             dx = dx.to(ctx.x_dtype)
-        return (dx, None) + tuple(grads.get(p) for p in ctx.params)
+        # gradients the kernels accumulated straight into the packed flat buffer (parallel.GradBuckets: p.grad is a view of it)
+        # are complete here: autograd gets None for them and the bucket is told directly
+        out, ready = [], []
+        for p in ctx.params:
+            g = grads.get(p)
+            if g is not None and p.grad is not None and g.data_ptr() == p.grad.data_ptr():
+                ready.append(p)
+                g = None
+            out.append(g)
+        for p in ready:
+            cb = getattr(p, "_dsg_ready", None)
+            if cb is not None:
+                cb(p)
+        return (dx, None) + tuple(out)
 
 
 class _Impl:
@@ -236,6 +249,14 @@ class dgphgcn1(nn.Module):
             self._tab[key] = (nt.to(dev).contiguous(), et.to(dev).contiguous())
         return self._tab[key]
 
+    def _flat_groups(self):
+        """parameters the kernels always use concatenated (one GEMM): parallel.GradBuckets lays them out adjacently"""
+        g = {"Wt": [self.conv1.weight, self.conv2.weight, self.conv1_se.weight], "bt": [self.conv1.bias, self.conv2.bias, self.conv1_se.bias]}
+        if self.has_down:
+            g["Wpd"] = [self.pre[0].weight, self.down[0].weight]
+            g["bpd"] = [self.pre[0].bias, self.down[0].bias]
+        return g
+
     def _fwd(self, x, n, t, v, save):
         return Fn.dgphgcn1_forward(self, x, n, t, v, save), t
 
@@ -327,6 +348,10 @@ class mstcn(nn.Module):
         if dropout:
             raise NotImplementedError("dropout > 0 is not on the DS-GCN path (configs use 0)")
         self.drop = nn.Dropout(dropout, inplace=True)
+
+    def _flat_groups(self):
+        convs = [b if isinstance(b, nn.Conv2d) else b[0] for b in self.branches]
+        return {"Wbr": [c.weight for c in convs], "bbr": [c.bias for c in convs]}
 
     def _fwd(self, x, n, t, v, save, res=None, final_relu=False):
         return Fn.mstcn_forward(self, x, n, t, v, save, res, final_relu)
@@ -496,7 +521,17 @@ class _DataBNFn(torch.autograd.Function):
             dx = torch.empty(N * M * T, V * C, dtype=torch.float32, device=d.device)
             ops.pointwise(ops.Act(d32, back.ca, back.cc, xin, back.cb), dx)
             dx = dx.view(N, M, T, V, C).to(ctx.x_dtype)
-        return dx, None, grads[bn.weight], grads[bn.bias]
+        gw, gb_ = grads[bn.weight], grads[bn.bias]
+        for q in (bn.weight, bn.bias):          # written in place into the packed flat gradient buffer (see _KernelFn.backward)
+            if q.grad is not None and grads[q].data_ptr() == q.grad.data_ptr():
+                cb = getattr(q, "_dsg_ready", None)
+                if cb is not None:
+                    cb(q)
+        if bn.weight.grad is not None and gw.data_ptr() == bn.weight.grad.data_ptr():
+            gw = None
+        if bn.bias.grad is not None and gb_.data_ptr() == bn.bias.grad.data_ptr():
+            gb_ = None
+        return dx, None, gw, gb_
 
 
 class _Backbone(nn.Module):

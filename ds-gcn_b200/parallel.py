@@ -74,7 +74,7 @@ def _group_key(name):
 
 
 class _Bucket:
-    __slots__ = ("params", "names", "flat_p", "flat_g", "flat_m", "pending", "work")
+    __slots__ = ("params", "names", "offsets", "flat_p", "flat_g", "flat_m", "pending", "work")
 
 
 class GradBuckets:
@@ -82,10 +82,14 @@ class GradBuckets:
 
         gb = GradBuckets(model, n_buckets=3)        # after model.to(device) and broadcast_parameters
         gb.zero_grad(); loss.backward(); gb.synchronize(); <update reading gb.buckets[i].flat_p / flat_g>
-    """
-    ALIGN = 64          # floats: every parameter view starts on a 256-byte boundary (vectorised reductions, TMA-able slices)
 
-    def __init__(self, model, n_buckets=3, overlap=True):
+    `direct=True` (default): the kernels accumulate parameter gradients straight into the flat gradient buffer (functional.py
+    `grad_like` / `grad_cat`; exactly one backward per zero_grad), and parameters a unit always uses concatenated
+    (`module._flat_groups()`) are laid out adjacently so the concatenation is a view (`module._dsg_flat`).
+    """
+    ALIGN = 64          # floats: every parameter (group) starts on a 256-byte boundary (vectorised reductions, TMA-able slices)
+
+    def __init__(self, model, n_buckets=3, overlap=True, direct=True):
         named = [(n, p) for n, p in model.named_parameters() if "conv2_se" not in n and p.requires_grad]
         if not named:
             raise ValueError("no trainable parameters")
@@ -93,7 +97,19 @@ class GradBuckets:
         for n, p in named:
             if p.dtype != torch.float32 or p.device != dev:
                 raise ValueError(f"{n}: parameters must be fp32 on one device")
+        trainable = {id(p) for _, p in named}
+        group_of = {}                                 # id(param) -> (module, key, [params])
+        if direct:
+            for mod in model.modules():
+                fg = getattr(mod, "_flat_groups", None)
+                if fg is None:
+                    continue
+                for key, plist in fg().items():
+                    if len(plist) > 1 and all(id(q) in trainable for q in plist):
+                        for q in plist:
+                            group_of[id(q)] = (mod, key, plist)
         ready = list(reversed(named))                 # autograd produces gradients from the head back to data_bn
+        name_of = {id(p): n for n, p in named}
         groups, cur = [], None
         for n, p in ready:
             k = _group_key(n)
@@ -103,27 +119,50 @@ class GradBuckets:
             groups[-1].append((n, p))
         n_buckets = max(1, min(n_buckets, len(groups)))
         per = math.ceil(len(groups) / n_buckets)
+        pad = lambda nel: (nel + self.ALIGN - 1) // self.ALIGN * self.ALIGN
         self.buckets = []
         for b in range(n_buckets):
             items = [it for g in groups[b * per:(b + 1) * per] for it in g]
             if not items:
                 continue
+            in_bucket = {id(p) for _, p in items}
             bk = _Bucket()
-            bk.names = [n for n, _ in items]
-            bk.params = [p for _, p in items]
-            offs, tot = [], 0
-            for p in bk.params:
-                offs.append(tot)
-                tot += (p.numel() + self.ALIGN - 1) // self.ALIGN * self.ALIGN
+            bk.names, bk.params, bk.offsets = [], [], []
+            placed, tot, cat_views = set(), 0, []
+            for n, p in items:
+                if id(p) in placed:
+                    continue
+                members = [p]
+                if id(p) in group_of:
+                    mod, key, members = group_of[id(p)]
+                    if not all(id(q) in in_bucket for q in members):
+                        raise ValueError(f"concatenated parameter group {key} of {type(mod).__name__} spans two buckets")
+                    cat_views.append((mod, key, members, tot))
+                for q in members:
+                    bk.names.append(name_of[id(q)])
+                    bk.params.append(q)
+                    bk.offsets.append(tot)
+                    placed.add(id(q))
+                    tot += q.numel()
+                tot = pad(tot)
             bk.flat_p = torch.zeros(tot, dtype=torch.float32, device=dev)
             bk.flat_g = torch.zeros(tot, dtype=torch.float32, device=dev)
             bk.flat_m = None
             with torch.no_grad():
-                for p, o in zip(bk.params, offs):
+                for p, o in zip(bk.params, bk.offsets):
                     view = bk.flat_p[o:o + p.numel()].view(p.shape)
                     view.copy_(p.data)
                     p.data = view                                   # the module's parameter now lives in the flat buffer
                     p.grad = bk.flat_g[o:o + p.numel()].view(p.shape)
+                    if direct:
+                        p._dsg_sink = True
+            for mod, key, members, o in cat_views:
+                nel = sum(q.numel() for q in members)
+                rows = sum(q.shape[0] for q in members)
+                shape = (rows,) if members[0].dim() == 1 else (rows, nel // rows)
+                if not hasattr(mod, "_dsg_flat"):
+                    mod._dsg_flat = {}
+                mod._dsg_flat[key] = (bk.flat_p[o:o + nel].view(shape), bk.flat_g[o:o + nel].view(shape))
             bk.pending, bk.work = len(bk.params), None
             self.buckets.append(bk)
         self.params = [p for bk in self.buckets for p in bk.params]
@@ -133,8 +172,10 @@ class GradBuckets:
         self._hooks = []
         if self.world > 1 and overlap:
             for bk in self.buckets:
+                hook = self._make_hook(bk)
                 for p in bk.params:
-                    self._hooks.append(p.register_post_accumulate_grad_hook(self._make_hook(bk)))
+                    self._hooks.append(p.register_post_accumulate_grad_hook(hook))    # gradients that arrive through autograd
+                    p._dsg_ready = hook                                               # gradients the kernels wrote in place
 
     def _make_hook(self, bk):
         def hook(_p):
@@ -160,10 +201,8 @@ class GradBuckets:
                     break
 
     def _reattach(self, bk):
-        o = 0
-        for p in bk.params:
+        for p, o in zip(bk.params, bk.offsets):
             p.grad = bk.flat_g[o:o + p.numel()].view(p.shape)
-            o += (p.numel() + self.ALIGN - 1) // self.ALIGN * self.ALIGN
 
     def synchronize(self):
         """After backward: make the current stream wait for every bucket's collective (launching the ones whose hooks did

@@ -255,3 +255,46 @@ def test_bench_size_properties():
         assert float((batch_mean.cpu() - direct.cpu()).abs().max()) < 1e-4
     finally:
         M.set_compute_dtype(torch.bfloat16)
+
+
+def test_packed_parameters_give_identical_gradients_and_update(dev):
+    """parallel.GradBuckets packs parameters / gradients into flat buffers (adjacent concat groups, kernels accumulating in place,
+    autograd bypassed) and FlatSGD updates a bucket with one kernel: same numbers as the unpacked modules + torch.optim.SGD."""
+    from dsgcn_b200 import parallel
+    z, m1 = _small_model(dev)
+    _, m2 = _small_model(dev)
+    x = torch.from_numpy(z["x"]).to(dev)
+    gy = torch.from_numpy(z["gy"]).to(dev)
+    M.set_compute_dtype(torch.float32)
+    try:
+        m1.train(); m2.train()
+        sgd = dict(lr=1e-4, momentum=0.9, weight_decay=5e-4, nesterov=True)     # small steps: the toy model's gradients are O(10)
+        o1 = torch.optim.SGD(parallel.trainable_parameters(m1), **sgd)
+        gb = parallel.GradBuckets(m2, n_buckets=3)
+        o2 = parallel.FlatSGD(gb, **sgd)
+        u = m2.gcn[4].gcn
+        assert u._dsg_flat["Wpd"][0].data_ptr() == u.pre[0].weight.data_ptr()            # pre|down are adjacent: the concatenation is a view
+        assert torch.equal(u._dsg_flat["Wpd"][0], torch.cat([u.pre[0].weight, u.down[0].weight]).view(u._dsg_flat["Wpd"][0].shape))
+        for it in range(2):
+            o1.zero_grad(set_to_none=True)
+            y1 = m1(x)
+            y1.backward(gy.to(y1.dtype))
+            o2.zero_grad()
+            y2 = m2(x)
+            y2.backward(gy.to(y2.dtype))
+            assert rel(y2, y1) < (1e-6 if it == 0 else 1e-3), it
+            p1, p2 = dict(m1.named_parameters()), dict(m2.named_parameters())
+            gmax = max(float(q.grad.norm()) for q in p1.values() if q.grad is not None)
+            for k in p1:
+                if "conv2_se" in k:
+                    assert p2[k].grad is None
+                    continue
+                # (biases in front of a BatchNorm have a zero gradient: rounding noise only, hence the absolute term)
+                err = float((p2[k].grad - p1[k].grad).norm())
+                assert err <= (1e-5 if it == 0 else 3e-2) * float(p1[k].grad.norm()) + 1e-5 * gmax, (it, k, err)
+            o1.step()
+            o2.step()
+            for k in p1:
+                assert rel(p2[k], p1[k]) < (1e-5 if it == 0 else 1e-3), (it, k)
+    finally:
+        M.set_compute_dtype(torch.bfloat16)
