@@ -91,6 +91,13 @@ class MsTemporalArgs(C.Structure):
                 ("dfeat", ActSrc), ("e", vp), ("ld_e", c_ll), ("e_sum", vp), ("e_sq", vp), ("dadd_coeff", vp), ("wpack", vp)]
 
 
+class MsConvArgs(C.Structure):
+    _fields_ = [("n_samples", c_int), ("T_in", c_int), ("T_out", c_int), ("stride", c_int), ("Vr", c_int), ("transposed", c_int),
+                ("n_branches", c_int), ("br", MsBranch * 8), ("src", vp), ("ld_src", c_ll), ("out", vp), ("ld_out", c_ll),
+                ("has_mask", c_int), ("mask", ActSrc), ("partner", vp), ("ld_partner", c_ll), ("stat_sum", vp), ("stat_sq", vp),
+                ("wpack", vp)]
+
+
 class PointwiseArgs(C.Structure):
     _fields_ = [("src", ActSrc), ("dtype", c_int), ("C", c_int), ("rows", c_ll), ("out", vp), ("ld_out", c_ll),
                 ("out_dtype", c_int), ("has_mask", c_int), ("mask", ActSrc),
@@ -111,12 +118,15 @@ EXPORTS = {
     "dsg_graph_agg_dadj": (c_int, [C.POINTER(GraphAggDadjArgs), vp]),
     "dsg_ms_combine_fwd": (c_int, [C.POINTER(MsCombineArgs), vp]),
     "dsg_ms_combine_bwd": (c_int, [C.POINTER(MsCombineArgs), vp]),
+    "dsg_ms_combine_bwd_part": (c_int, [C.POINTER(MsCombineArgs), c_int, vp]),
     "dsg_pointwise": (c_int, [C.POINTER(PointwiseArgs), vp]),
     "dsg_ms_temporal_supported": (c_int, [C.POINTER(MsTemporalArgs)]),
     "dsg_ms_temporal_wpack_bytes": (c_ll, [C.POINTER(MsTemporalArgs)]),
     "dsg_ms_temporal_fwd": (c_int, [C.POINTER(MsTemporalArgs), vp]),
     "dsg_ms_temporal_bwd_data": (c_int, [C.POINTER(MsTemporalArgs), vp]),
     "dsg_ms_temporal_bwd_weight": (c_int, [C.POINTER(MsTemporalArgs), vp]),
+    "dsg_ms_conv_wpack_bytes": (c_ll, [C.POINTER(MsConvArgs)]),
+    "dsg_ms_conv": (c_int, [C.POINTER(MsConvArgs), C.POINTER(c_int), vp]),
     "dsg_sgd_step": (c_int, [vp, vp, vp, c_ll, c_f, c_f, c_f, c_int, c_f, vp]),
     "dsg_sgd_step_dev": (c_int, [vp, vp, vp, c_ll, vp, c_f, c_f, c_int, c_f, vp]),
     "dsg_debug_counter": (c_ll, [c_int]),

@@ -6,6 +6,7 @@
 #include "conv_gemm_tc3.cuh"
 #include "tc4_gemm.cuh"
 #include "tc4_wgrad.cuh"
+#include "tc4_tconv.cuh"
 #include "graph_agg.cuh"
 #include "ms_temporal_tc.cuh"
 #include "topology.cuh"
@@ -177,26 +178,36 @@ int dsg_ms_combine_fwd(const dsg_ms_combine_args* a, void* stream) {
     DSG_RET("dsg_ms_combine_fwd", dsg_launch_error());
 }
 
-int dsg_ms_combine_bwd(const dsg_ms_combine_args* a, void* stream) {
+static int ms_combine_bwd_impl(const dsg_ms_combine_args* a, int parts, void* stream) {
     if (!a || !dtype_ok(a->dtype) || a->V > 32) return fail("dsg_ms_combine_bwd", "bad arguments");
     dsg_stream_t st = (dsg_stream_t)stream;
     long long n_out = (long long)a->n_samples * a->T_out, n_in = (long long)a->n_samples * a->T_in;
     if (n_out <= 0) return 0;
-    dim3 g1((unsigned)((n_out + 7) / 8), (a->C + dsg::PW_CT - 1) / dsg::PW_CT);
-    if (a->dtype == DSG_BF16) dsg_launch(dsg::ms_combine_bwd_o_kernel<bf16>, g1, dim3(dsg::PW_THREADS), 0, st, *a);
-    else dsg_launch(dsg::ms_combine_bwd_o_kernel<float>, g1, dim3(dsg::PW_THREADS), 0, st, *a);
-    const char* e = dsg_launch_error();
-    if (e) return fail("dsg_ms_combine_bwd", e);
-    const int lo[2] = {a->max_lo, a->pass_lo}, hi[2] = {a->max_hi, a->pass_hi};
-    for (int i = 0; i < 2; ++i) {
-        if (hi[i] <= lo[i]) continue;
-        dim3 g2((unsigned)((n_in + 7) / 8), (hi[i] - lo[i] + dsg::PW_CT - 1) / dsg::PW_CT);
-        if (a->dtype == DSG_BF16) dsg_launch(dsg::ms_combine_bwd_e_kernel<bf16>, g2, dim3(dsg::PW_THREADS), 0, st, *a, lo[i], hi[i]);
-        else dsg_launch(dsg::ms_combine_bwd_e_kernel<float>, g2, dim3(dsg::PW_THREADS), 0, st, *a, lo[i], hi[i]);
-        e = dsg_launch_error();
+    if (parts & 1) {
+        dim3 g1((unsigned)((n_out + 7) / 8), (a->C + dsg::PW_CT - 1) / dsg::PW_CT);
+        if (a->dtype == DSG_BF16) dsg_launch(dsg::ms_combine_bwd_o_kernel<bf16>, g1, dim3(dsg::PW_THREADS), 0, st, *a);
+        else dsg_launch(dsg::ms_combine_bwd_o_kernel<float>, g1, dim3(dsg::PW_THREADS), 0, st, *a);
+        const char* e = dsg_launch_error();
         if (e) return fail("dsg_ms_combine_bwd", e);
     }
+    if (parts & 2) {
+        const int lo[2] = {a->max_lo, a->pass_lo}, hi[2] = {a->max_hi, a->pass_hi};
+        for (int i = 0; i < 2; ++i) {
+            if (hi[i] <= lo[i]) continue;
+            dim3 g2((unsigned)((n_in + 7) / 8), (hi[i] - lo[i] + dsg::PW_CT - 1) / dsg::PW_CT);
+            if (a->dtype == DSG_BF16) dsg_launch(dsg::ms_combine_bwd_e_kernel<bf16>, g2, dim3(dsg::PW_THREADS), 0, st, *a, lo[i], hi[i]);
+            else dsg_launch(dsg::ms_combine_bwd_e_kernel<float>, g2, dim3(dsg::PW_THREADS), 0, st, *a, lo[i], hi[i]);
+            const char* e = dsg_launch_error();
+            if (e) return fail("dsg_ms_combine_bwd", e);
+        }
+    }
     return 0;
+}
+
+int dsg_ms_combine_bwd(const dsg_ms_combine_args* a, void* stream) { return ms_combine_bwd_impl(a, 3, stream); }
+int dsg_ms_combine_bwd_part(const dsg_ms_combine_args* a, int parts, void* stream) {
+    if (parts < 1 || parts > 3) return fail("dsg_ms_combine_bwd_part", "parts must be 1 (branch-output gradient), 2 (max / pass ranges) or 3");
+    return ms_combine_bwd_impl(a, parts, stream);
 }
 
 int dsg_ms_temporal_supported(const dsg_ms_temporal_args* a) {
@@ -245,6 +256,31 @@ int dsg_ms_temporal_bwd_weight(const dsg_ms_temporal_args* a, void* stream) {
 #else
     if (!a) return fail("dsg_ms_temporal_bwd_weight", "bad arguments");
     DSG_RET("dsg_ms_temporal_bwd_weight", dsg::tc::launch_ms_temporal_bwd_weight(*a, (dsg_stream_t)stream));
+#endif
+}
+
+long long dsg_ms_conv_wpack_bytes(const dsg_ms_conv_args* a) {
+#ifdef DSG_EMU
+    (void)a;
+    return 0;
+#else
+    return a ? 2 * dsg::tc4::tc4_tconv_wpack_bytes(*a) : 0;          // two parity planes for a strided data gradient
+#endif
+}
+
+int dsg_ms_conv(const dsg_ms_conv_args* a, int* handled, void* stream) {
+    if (!a || !handled) return fail("dsg_ms_conv", "bad arguments");
+    *handled = 0;
+#ifdef DSG_EMU
+    (void)stream;
+    return 0;                                                         // tcgen05 + TMA kernel: the simulator build always declines
+#else
+    if (!tc_enabled()) return 0;
+    bool h = false;
+    const char* e = dsg::tc4::launch_ms_conv_tc4(*a, (dsg_stream_t)stream, &h);
+    if (e) return fail("dsg_ms_conv", e);
+    if (h) { *handled = 1; ++g_counters[3]; }
+    return 0;
 #endif
 }
 

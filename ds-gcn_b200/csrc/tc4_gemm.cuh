@@ -53,6 +53,15 @@ struct G4Plan {
     unsigned off_w, off_a, off_out, off_stat, off_ones, off_cf;       // byte offsets from the 1024-aligned base
     unsigned w_tile_bytes, out_bytes, smem_total;
     int acc_cols, stat_col, sum_col, tmem_cols;   // stat_col: Gram / product sums; sum_col: plain sums (8 columns)
+    // ---- mode 3: the dilated temporal convolutions of a multi-scale unit (tcn.py:383-396) as tap-shifted atoms.  A tile is F
+    //      frames of ONE sample; atom = (branch, tap): the branch's 64-channel window of the source at frame + shift (4-D tensor
+    //      map: frames outside the sample are zero-filled = the convolution's zero padding), multiplied into the branch's
+    //      column window of the accumulator.  Per column tile y: t_n[y] atoms.
+    int tps, qs, qp, Tq, Tdst;   // tiles per sample; frame stride / parity of the destination plane; its frames; T of the destination
+    int t_n[2];
+    short t_map[2][G4_MAX_ATOMS], t_tsh[2][G4_MAX_ATOMS], t_ks[2][G4_MAX_ATOMS], t_ncol[2][G4_MAX_ATOMS], t_nw[2][G4_MAX_ATOMS];
+    int t_c0[2][G4_MAX_ATOMS];
+    unsigned t_woff[2][G4_MAX_ATOMS], t_wbytes[2];
 };
 
 // ---- packed weights: per column tile j, per atom a: [Ntile rows (n) x 64 k] bf16 in the K-major SWIZZLE_128B layout, scaled
@@ -158,28 +167,39 @@ tc4_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
     tc_fence_after();
     const uint32_t tmem = tmem_base_s;
     const int n_my = ((int)blockIdx.x < p.n_tiles) ? (p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
-    const uint32_t box_bytes = p.mode == 0 ? (uint32_t)ATOM_BYTES : (uint32_t)(p.F * (p.mode == 1 ? p.V : p.V + 1) * 128);
+    const uint32_t box_bytes = p.mode == 0 ? (uint32_t)ATOM_BYTES : (uint32_t)(p.F * (p.mode == 1 ? p.V : (p.mode == 2 ? p.V + 1 : a.Vin)) * 128);
+    const int yy = p.mode == 3 ? (int)blockIdx.y : 0;
+    const int natoms = p.mode == 3 ? p.t_n[yy] : p.natoms;
 
     if (warp == 0) {
         // ================================================= TMA producer =================================================
         if (lane == 0) {
             prefetch_map(&mapA0);
             if (p.natoms > p.natoms1) prefetch_map(&mapA1);
-            mbar_expect_tx(&bars.wbar, p.w_tile_bytes);
-            bulk_g2s(Wsm, reinterpret_cast<const unsigned char*>(a.wpack) + (size_t)blockIdx.y * p.w_tile_bytes, p.w_tile_bytes, &bars.wbar);
+            const uint32_t wbytes = p.mode == 3 ? p.t_wbytes[yy] : p.w_tile_bytes;
+            const size_t wsrc = p.mode == 3 ? (yy ? (size_t)p.t_wbytes[0] : 0) : (size_t)blockIdx.y * p.w_tile_bytes;
+            mbar_expect_tx(&bars.wbar, wbytes);
+            bulk_g2s(Wsm, reinterpret_cast<const unsigned char*>(a.wpack) + wsrc, wbytes, &bars.wbar);
             int stage = 0;
             uint32_t ph = 0;
             for (int i = 0; i < n_my; ++i) {
                 const int tile = (int)blockIdx.x + i * (int)gridDim.x;
-                for (int ai = 0; ai < p.natoms; ++ai) {
+                const int smp = p.mode == 3 ? tile / p.tps : 0, q0 = p.mode == 3 ? (tile - smp * p.tps) * p.F : 0;
+                for (int ai = 0; ai < natoms; ++ai) {
                     mbar_wait(&bars.empty[stage], ph ^ 1);
                     mbar_expect_tx(&bars.full[stage], box_bytes);
-                    const CUtensorMap* m = ai < p.natoms1 ? &mapA0 : &mapA1;
-                    const int c0 = (ai < p.natoms1 ? ai : ai - p.natoms1) * ATOM_CH;
                     unsigned char* dst = Asm + (size_t)stage * ATOM_BYTES;
-                    if (p.mode == 0) tma_load_2d(dst, m, c0, tile * ATOM_ROWS, &bars.full[stage]);
-                    else
-                        for (int f = 0; f < p.F; ++f) tma_load_3d(dst + (size_t)f * p.slot * 128, m, c0, 0, tile * p.F + f, &bars.full[stage]);
+                    if (p.mode == 3) {
+                        const CUtensorMap* m = p.t_map[yy][ai] ? &mapA1 : &mapA0;
+                        for (int f = 0; f < p.F; ++f)
+                            tma_load_4d(dst + (size_t)f * p.slot * 128, m, p.t_c0[yy][ai], 0, q0 + f + p.t_tsh[yy][ai], smp, &bars.full[stage]);
+                    } else {
+                        const CUtensorMap* m = ai < p.natoms1 ? &mapA0 : &mapA1;
+                        const int c0 = (ai < p.natoms1 ? ai : ai - p.natoms1) * ATOM_CH;
+                        if (p.mode == 0) tma_load_2d(dst, m, c0, tile * ATOM_ROWS, &bars.full[stage]);
+                        else
+                            for (int f = 0; f < p.F; ++f) tma_load_3d(dst + (size_t)f * p.slot * 128, m, c0, 0, tile * p.F + f, &bars.full[stage]);
+                    }
                     if (++stage == p.S) { stage = 0; ph ^= 1; }
                 }
             }
@@ -197,13 +217,23 @@ tc4_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
                 tc_fence_after();
                 const uint32_t acc = tmem + (uint32_t)(buf * p.acc_cols);
                 int first = 1;
-                for (int ai = 0; ai < p.natoms; ++ai) {
+                for (int ai = 0; ai < natoms; ++ai) {
                     mbar_wait(XF ? &bars.ready[stage] : &bars.full[stage], ph);
                     tc_fence_after();
-                    const uint32_t a0 = smem_u32(Asm + (size_t)stage * ATOM_BYTES), w0 = smem_u32(Wsm + (size_t)ai * p.Ntile * 128);
-                    for (int ks = 0; ks < p.ksteps[ai]; ++ks) {
-                        umma_f16(acc, desc_k_sw128(a0 + ks * 32u), desc_k_sw128(w0 + ks * 32u), idesc, first ? 0u : 1u);
-                        first = 0;
+                    const uint32_t a0 = smem_u32(Asm + (size_t)stage * ATOM_BYTES);
+                    if (p.mode == 3) {
+                        // the branch's column window of the accumulator (atom 0 spans the whole tile and initialises it)
+                        const uint32_t w0 = smem_u32(Wsm + p.t_woff[yy][ai]), idw = make_idesc(128, p.t_nw[yy][ai]);
+                        const uint32_t dcol = acc + (uint32_t)p.t_ncol[yy][ai];
+                        for (int ks = 0; ks < p.t_ks[yy][ai]; ++ks) {
+                            umma_f16(dcol, desc_k_sw128(a0 + ks * 32u), desc_k_sw128(w0 + ks * 32u), idw, (ai | ks) ? 1u : 0u);
+                        }
+                    } else {
+                        const uint32_t w0 = smem_u32(Wsm + (size_t)ai * p.Ntile * 128);
+                        for (int ks = 0; ks < p.ksteps[ai]; ++ks) {
+                            umma_f16(acc, desc_k_sw128(a0 + ks * 32u), desc_k_sw128(w0 + ks * 32u), idesc, first ? 0u : 1u);
+                            first = 0;
+                        }
                     }
                     umma_commit(&bars.empty[stage]);
                     if (++stage == p.S) { stage = 0; ph ^= 1; }
@@ -322,6 +352,9 @@ tc4_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
                 const long long g = (long long)tile * ATOM_ROWS + r;
                 if (g < p.rows_out) gr = g;
                 if (TAILS && a.bcast && gr >= 0) { const long long fr = gr / Vout; jrow = (int)(gr - fr * Vout); samp = (int)(fr / a.T_out); }
+            } else if (p.mode == 3) {
+                const int smp = tile / p.tps, q = (tile - smp * p.tps) * p.F + r / p.slot, v = r % p.slot;
+                if (r / p.slot < p.F && v < Vout && q < p.Tq) { gr = ((long long)smp * p.Tdst + (long long)q * p.qs + p.qp) * Vout + v; jrow = v; samp = smp; }
             } else {
                 const int f = r / p.slot, v = r - f * p.slot;
                 const long long frame = (long long)tile * p.F + f;
@@ -468,7 +501,11 @@ tc4_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
             for (int oa = 0; oa < n_oatoms; ++oa) {
                 const unsigned char* src = Ot + (size_t)oa * ATOM_BYTES;
                 if (p.mode == 0) tma_store_2d(&mapO, src, n0 + oa * ATOM_CH, tile * ATOM_ROWS);
-                else
+                else if (p.mode == 3) {
+                    const int smp = tile / p.tps, q0 = (tile - smp * p.tps) * p.F;
+                    for (int f = 0; f < p.F; ++f)
+                        if (q0 + f < p.Tq) tma_store_4d(&mapO, src + (size_t)f * p.slot * 128, n0 + oa * ATOM_CH, 0, q0 + f, smp);
+                } else
                     for (int f = 0; f < p.F; ++f)
                         if ((long long)tile * p.F + f < p.n_frames) tma_store_3d(&mapO, src + (size_t)f * p.slot * 128, n0 + oa * ATOM_CH, 0, tile * p.F + f);
             }

@@ -12,6 +12,7 @@ pyskl/models/gcns/utils/tcn.py:31-32 (unit_tcn), :162-177 (mstcn), :407-428 (dgm
 pyskl/models/gcns/dgstgcn.py:61-65 (DGBlock).
 """
 import math
+import os
 
 import torch
 
@@ -402,6 +403,26 @@ def _ms_fused_args(m, layout, b_act, n, T, T_out, s, V, has_ext, grads):
     return a if ops.ms_temporal_supported(a) else None
 
 
+MS_TAP = os.environ.get("DSG_MS_TAP", "1") != "0"      # 0: the staged single-kernel branch stage (ms_temporal_tc.cuh) instead
+
+
+def _ms_tap_path(m, layout, ranges, dt):
+    """(conv channel width rounded up to 8, {branch: (W, bias)}) when the tap-shifted TMA path applies, else None."""
+    if not MS_TAP or dt != torch.bfloat16 or not ops.L.is_device_build():
+        return None
+    (clo, chi), _, _ = ranges
+    if chi <= clo or clo != 0 or m.stride > 2:
+        return None
+    weights = {}
+    for j, (kind, lo, hi, cfg) in enumerate(layout):
+        if kind == "conv":
+            if cfg[0] != 3:
+                return None
+            conv = m.branches[j][3].conv
+            weights[j] = (conv.weight, conv.bias)
+    return (chi + 7) & ~7, weights
+
+
 def mstcn_forward(m, g, n, T, V, save, res=None, final_relu=False):
     """g [n*T*V, C_in] -> [n*T_out*V, C_out] = bn(transform(branches(g))) (+ res) (relu).
     `res`: optional Act-like tuple (x, a, b) added before the final ReLU (DGBlock residual)."""
@@ -436,8 +457,25 @@ def mstcn_forward(m, g, n, T, V, save, res=None, final_relu=False):
     add_coeff = m.add_coeff if has_ext else None
     if has_ext and add_coeff.numel() < V:
         raise ValueError("add_coeff is shorter than the number of joints")
-    fused = _ms_fused_args(m, layout, Act(B, c_b.a, c_b.b), n, T, T_out, s, V, has_ext, None)
-    if fused is not None:
+    H = None
+    tap = _ms_tap_path(m, layout, ranges, dt)
+    if tap is not None:
+        # ---- tap-shifted TMA path: relu(bn(B)) of the conv channels is materialised once (the 4-D tensor map's zero fill then
+        #      IS the convolution's zero padding), all conv branches run as one tcgen05 launch, and a streaming pass adds the
+        #      max-pool / pass-through branches, local + global * add_coeff and the statistics of transform.0
+        chw, weights = tap
+        H = torch.empty(rows_b, chw, dtype=dt, device=dev)
+        ops.pointwise(Act(B[:, :chw], c_b.a[:chw], c_b.b[:chw], relu=True), H)
+        O = torch.empty(rows_o, chw, dtype=dt, device=dev)
+        if ops.ms_conv(H, O, layout, weights, n=n, T_in=T, T_out=T_out, stride=s, Vr=Vp, transposed=False):
+            ops.ms_combine_fwd(Act(B, c_b.a, c_b.b), O, feat, oglob, n=n, T_in=T, T_out=T_out, stride=s, V=V, has_ext=has_ext,
+                               ranges=ranges, add_coeff=add_coeff, stat_sum=c_t.ssum, stat_sq=c_t.ssq)
+        else:
+            tap = H = None
+    fused = _ms_fused_args(m, layout, Act(B, c_b.a, c_b.b), n, T, T_out, s, V, has_ext, None) if tap is None else None
+    if tap is not None:
+        pass
+    elif fused is not None:
         # ---- one tcgen05 kernel: dilated convs (implicit GEMM), max-pool, pass-through, local + global*add_coeff
         ops.ms_temporal_fwd(fused, feat, oglob, c_t.ssum, c_t.ssq)
     else:
@@ -473,7 +511,7 @@ def mstcn_forward(m, g, n, T, V, save, res=None, final_relu=False):
     ops.pointwise(src, out)
     if save is not None:
         save.update(g=g, Wbr=Wbr, B=B, c_b=c_b, feat=feat, oglob=oglob, c_t=c_t, U=U, c_u=c_u, out=out, dims=(n, T, V),
-                    final_relu=final_relu)
+                    final_relu=final_relu, H=H)
     return out, T_out
 
 
@@ -525,7 +563,26 @@ def mstcn_backward(m, sv, dout, grads):
     if has_ext:
         grads[m.add_coeff] = dadd
     fused = _ms_fused_args(m, layout, Act(B, c_b.a, c_b.b), n, T, T_out, s, V, has_ext, grads)
-    if fused is not None:
+    H = sv.get("H")
+    tap_done = False
+    if H is not None and fused is not None:
+        # ---- tap-shifted TMA path: a streaming pass routes dfeat to the branch outputs (d_o of the conv range incl. the
+        #      joint-mean row, masked gradients of the max / pass ranges, dadd_coeff), then every conv branch's data gradient is
+        #      one tcgen05 launch with the ReLU mask (H > 0) and the BN-backward sums in its epilogue
+        chw = H.shape[1]
+        tap = _ms_tap_path(m, layout, ranges, dt)
+        d_o = torch.empty(rows_o, chw, dtype=dt, device=dev)
+        ckw = dict(n=n, T_in=T, T_out=T_out, stride=s, V=V, has_ext=has_ext, ranges=ranges, add_coeff=m.add_coeff if has_ext else None,
+                   e_sum=b_b.ssum, e_sq=b_b.ssq, dadd_coeff=dadd)
+        ops.ms_combine_bwd(Act(B, c_b.a, c_b.b), dfeat, d_o, E3, sv["oglob"], B, parts=1, **ckw)
+        tap_done = tap is not None and ops.ms_conv(d_o, E3, layout, tap[1], n=n, T_in=T, T_out=T_out, stride=s, Vr=Vp, transposed=True,
+                                                   mask=H, partner=B, stat_sum=b_b.ssum, stat_sq=b_b.ssq)
+        if not tap_done:
+            raise RuntimeError("dsg_ms_conv took the forward of this shape but declined its data gradient")
+        # (after the conv branches: dsg_ms_conv pads its last 16-byte channel chunk with zeros, the max range starts inside it)
+        ops.ms_combine_bwd(Act(B, c_b.a, c_b.b), dfeat, d_o, E3, sv["oglob"], B, parts=2, **ckw)
+        ops.ms_temporal_bwd(fused, dfeat, E3, sv["oglob"], b_b.ssum, b_b.ssq, dadd, data=False)      # weight gradients of the conv branches
+    elif fused is not None:
         # ---- two tcgen05 kernels: data gradient of the whole branch stage (+ masks, BN-backward sums, dadd_coeff),
         #      then the weight gradients of the dilated convolutions
         ops.ms_temporal_bwd(fused, dfeat, E3, sv["oglob"], b_b.ssum, b_b.ssq, dadd)

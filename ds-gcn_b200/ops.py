@@ -301,7 +301,7 @@ def ms_combine_fwd(b, o, feat, oglob, *, n, T_in, T_out, stride, V, has_ext, ran
     L.call("dsg_ms_combine_fwd", C.byref(a), L.stream())
 
 
-def ms_combine_bwd(b, dfeat, d_o, e, oglob, b_raw, *, n, T_in, T_out, stride, V, has_ext, ranges, add_coeff, e_sum, e_sq, dadd_coeff):
+def ms_combine_bwd(b, dfeat, d_o, e, oglob, b_raw, *, n, T_in, T_out, stride, V, has_ext, ranges, add_coeff, e_sum, e_sq, dadd_coeff, parts=3):
     dfeat = as_act(dfeat)
     a = ms_combine_args(dfeat.dtype, n, T_in, T_out, stride, V, has_ext, dfeat.C, ranges, b, None, add_coeff)
     a.dfeat = dfeat.struct()
@@ -311,7 +311,10 @@ def ms_combine_bwd(b, dfeat, d_o, e, oglob, b_raw, *, n, T_in, T_out, stride, V,
     a.b_raw, a.ld_b = L.ptr(b_raw), _ld(b_raw)
     a.e_sum, a.e_sq = L.ptr(e_sum), L.ptr(e_sq)
     a.dadd_coeff = L.ptr(_f32(dadd_coeff))
-    L.call("dsg_ms_combine_bwd", C.byref(a), L.stream())
+    if parts == 3:
+        L.call("dsg_ms_combine_bwd", C.byref(a), L.stream())
+    else:
+        L.call("dsg_ms_combine_bwd_part", C.byref(a), parts, L.stream())
 
 
 def ms_temporal_args(b, layout, weights, *, n, T_in, T_out, stride, V, has_ext, add_coeff):
@@ -358,7 +361,7 @@ def ms_temporal_fwd(a, feat, oglob, stat_sum, stat_sq):
     L.call("dsg_ms_temporal_fwd", C.byref(a), L.stream(), nbytes=nbytes)
 
 
-def ms_temporal_bwd(a, dfeat, e, oglob, e_sum, e_sq, dadd_coeff):
+def ms_temporal_bwd(a, dfeat, e, oglob, e_sum, e_sq, dadd_coeff, data=True):
     dfeat = as_act(dfeat)
     a.dfeat = dfeat.struct()
     a.e, a.ld_e = L.ptr(e), _ld(e)
@@ -367,10 +370,57 @@ def ms_temporal_bwd(a, dfeat, e, oglob, e_sum, e_sq, dadd_coeff):
     a.dadd_coeff = L.ptr(_f32(dadd_coeff))
     es = e.element_size()
     nbytes = a.n_samples * (2 * a.T_in * (a.V + a.has_ext) + (2 if dfeat.x2 is not None else 1) * a.T_out * a.V) * a.C * es
-    L.call("dsg_ms_temporal_bwd_data", C.byref(a), L.stream(), nbytes=nbytes)
+    if data:
+        L.call("dsg_ms_temporal_bwd_data", C.byref(a), L.stream(), nbytes=nbytes)
     with L.side_stream():
         L.keepalive.extend((a, dfeat, e, oglob))
         L.call("dsg_ms_temporal_bwd_weight", C.byref(a), L.stream(), nbytes=nbytes)
+
+
+def ms_conv(src, out, layout, weights, *, n, T_in, T_out, stride, Vr, transposed, mask=None, partner=None, stat_sum=None, stat_sq=None):
+    """dsg_ms_conv: every dilated (3 x 1) conv branch of a multi-scale unit in one launch (or their data gradient).
+    `layout`/`weights` as ms_temporal_args; src/out [n*T*Vr, >= conv span] bf16 with absolute channel indexing.
+    Returns False when the engine declines the shape (the caller runs the per-branch path)."""
+    if src.dtype != torch.bfloat16 or not L.is_device_build():
+        return False
+    a = L.MsConvArgs()
+    a.n_samples, a.T_in, a.T_out, a.stride, a.Vr, a.transposed = n, T_in, T_out, stride, Vr, int(transposed)
+    nb = 0
+    for j, (kind, lo, hi, cfg) in enumerate(layout):
+        if kind != "conv":
+            continue
+        if cfg[0] != 3 or nb >= 8:
+            return False
+        br = a.br[nb]
+        br.kind, br.lo, br.hi, br.dilation = 0, lo, hi, cfg[1]
+        W, bias = weights[j][0], weights[j][1]
+        br.W, br.bias = L.ptr(_f32(W)), L.ptr(_f32(bias))
+        nb += 1
+    if nb == 0:
+        return False
+    a.n_branches = nb
+    a.src, a.ld_src = L.ptr(src), _ld(src)
+    a.out, a.ld_out = L.ptr(out), _ld(out)
+    if mask is not None:
+        mask = as_act(mask)
+        a.has_mask, a.mask = 1, mask.struct()
+    if partner is not None:
+        a.partner, a.ld_partner = L.ptr(partner), _ld(partner)
+    if stat_sum is not None:
+        a.stat_sum, a.stat_sq = L.ptr(stat_sum), L.ptr(stat_sq)
+    nbytes_w = int(L.lib().dsg_ms_conv_wpack_bytes(C.byref(a)))
+    if nbytes_w <= 0:
+        return False
+    wpack = torch.empty(nbytes_w, dtype=torch.uint8, device=out.device)
+    a.wpack = L.ptr(wpack)
+    handled = C.c_int(0)
+    span = a.br[nb - 1].hi - a.br[0].lo
+    es = 2
+    rows_src = n * (T_out if transposed else T_in) * Vr
+    rows_dst = n * (T_in if transposed else T_out) * Vr
+    nbytes = (rows_src + rows_dst * (1 + int(mask is not None) + int(partner is not None))) * span * es
+    L.call("dsg_ms_conv", C.byref(a), C.byref(handled), L.stream(), nbytes=nbytes)
+    return bool(handled.value)
 
 
 def sgd_step(p, grad, buf, lr, momentum, wd, nesterov, grad_scale=1.0):

@@ -262,6 +262,10 @@ typedef struct dsg_ms_combine_args {
 } dsg_ms_combine_args;
 int dsg_ms_combine_fwd(const dsg_ms_combine_args* a, void* stream);
 int dsg_ms_combine_bwd(const dsg_ms_combine_args* a, void* stream);
+/* parts: 1 = the per-output-frame pass only (d_o of the conv range incl. the joint-mean row, dadd_coeff); 2 = the per-input-frame
+ * pass only (e of the max / pass ranges + their sums); 3 = both.  The split lets the conv branches' data gradient (dsg_ms_conv,
+ * which pads its last 16-byte channel chunk with zeros) run between the two. */
+int dsg_ms_combine_bwd_part(const dsg_ms_combine_args* a, int parts, void* stream);
 
 /* ---- dsg_ms_temporal_fwd / _bwd_data / _bwd_weight -------------------------------------------------------------
  * The whole branch stage of the multi-scale temporal unit in one kernel per direction (tcn.py:383-396, 407-420):
@@ -309,6 +313,36 @@ int dsg_ms_temporal_fwd(const dsg_ms_temporal_args* a, void* stream);
 int dsg_ms_temporal_bwd_data(const dsg_ms_temporal_args* a, void* stream);
 int dsg_ms_temporal_bwd_weight(const dsg_ms_temporal_args* a, void* stream);
 
+/* ---- dsg_ms_conv ----------------------------------------------------------------------------
+ * All dilated (3 x 1) temporal convolutions of a multi-scale unit (the `unit_tcn(norm=None)` tails of the conv branches,
+ * tcn.py:383-391) in ONE launch on the TMA-fed tcgen05 engine, or their data gradient:
+ *   transposed = 0:  out[n,t',r,co] = bias[co] + sum_tap sum_ci W[co,ci,tap] * src[n, s*t' + (tap-1)*d, r, ci]   (zero padding in t)
+ *                    src [n,T_in,Vr,.], out [n,T_out,Vr,.]
+ *   transposed = 1:  out[n,t,r,ci]  = sum_tap sum_co W[co,ci,tap] * src[n, (t - (tap-1)*d)/s, r, co] where s divides,
+ *                    src [n,T_out,Vr,.], out [n,T_in,Vr,.]; epilogue as dsg_conv_gemm: ReLU mask, BN-backward sums with partner
+ * Branch j maps channels [lo,hi) of src to the same channels of out (block-diagonal); every tap is a tap-shifted TMA load of
+ * the branch's channel window (4-D tensor map: frames outside a sample are zero-filled = the zero padding), so src must be a
+ * plain bf16 tensor (the caller materialises relu(bn(.)) / the branch-output gradient once).  Channels of out outside every
+ * branch range but inside [br[0].lo, br[last].hi) are written as zeros (+0 bias).  Returns 0 and sets *handled = 0 when the
+ * shape is not taken (caller falls back to per-branch dsg_conv_gemm calls). */
+typedef struct dsg_ms_conv_args {
+    int n_samples, T_in, T_out, stride, Vr, transposed, n_branches;
+    dsg_ms_branch br[8];  /* conv branches only (kind 0), ascending adjacent channel ranges, br[0].lo % 8 == 0 */
+    const void* src;      /* bf16, channel 0 = absolute channel 0 of the branch layout */
+    long long ld_src;
+    void* out;
+    long long ld_out;
+    int has_mask;
+    dsg_act_src mask;     /* absolute channels, like src */
+    const void* partner;
+    long long ld_partner;
+    double* stat_sum;     /* absolute channels */
+    double* stat_sq;
+    void* wpack;          /* caller-owned workspace of dsg_ms_conv_wpack_bytes() */
+} dsg_ms_conv_args;
+long long dsg_ms_conv_wpack_bytes(const dsg_ms_conv_args* a);
+int dsg_ms_conv(const dsg_ms_conv_args* a, int* handled, void* stream);
+
 /* ---- dsg_pointwise --------------------------------------------------------------------------
  * out(r,c) = src(r,c) (any activation source: BN-apply, +residual, ReLU), optional mask
  * [mask(r,c) > 0], optional statistics (as in dsg_conv_gemm; partner may have its own dtype);
@@ -348,7 +382,8 @@ int dsg_sgd_step_dev(float* p, const float* grad, float* buf, long long n, const
                      int nesterov, float grad_scale, void* stream);
 
 /* Launch counters of the engines behind the entry points (diagnostics for the tests and bench.py: which engine ran).
- * id 0: TMA-fed tcgen05 GEMM (tc4)   1: TMA-fed tcgen05 weight gradient (tc4w)   2: fused adjacency-contraction + post GEMM.
+ * id 0: TMA-fed tcgen05 GEMM (tc4)   1: TMA-fed tcgen05 weight gradient (tc4w)   2: fused adjacency-contraction + post GEMM
+ *    3: tap-shifted temporal convolutions (dsg_ms_conv).
  * Monotonic, process-wide, never read by the kernels. */
 long long dsg_debug_counter(int id);
 

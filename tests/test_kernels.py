@@ -508,3 +508,59 @@ def test_sgd_step_matches_torch(dev):
         opt.step()
         ops.sgd_step(pd, g.to(dev), buf, 0.1, 0.9, 5e-4, True)
     close(pd, pr, torch.float32, "sgd")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("widths", [(14, 10, 10, 10), (23, 21, 21, 21), (46, 42, 42, 42)])
+@pytest.mark.parametrize("stride", [1, 2])
+def test_ms_conv_tap_shifted_tma(widths, stride):
+    """dsg_ms_conv: all dilated (3 x 1) conv branches in one tcgen05 launch from tap-shifted 4-D TMA loads (zero fill = zero
+    padding), forward and data gradient (ReLU mask + BN-backward sums in the epilogue), against F.conv2d / autograd."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    dsgcn_b200._lib._testing_use_library(None)
+    dev = torch.device("cuda:0")
+    torch.manual_seed(sum(widths) + stride)
+    n, T, Vr = 5, 21, 26                                     # odd T: the last frames of a sample fill a partial tile
+    T_out = (T - 1) // stride + 1
+    dil = (1, 2, 3, 4)
+    layout, lo = [], 0
+    for w, d in zip(widths, dil):
+        layout.append(("conv", lo, lo + w, (3, d)))
+        lo += w
+    span, chw = lo, (lo + 7) & ~7
+    Ct = chw + 16
+    layout += [("max", span, span + 8, ("max", 3)), ("1x1", span + 8, Ct, "1x1")]
+    Ws = {j: (torch.randn(w, w, 3, 1, device=dev) * 0.2, torch.randn(w, device=dev)) for j, w in enumerate(widths)}
+    h = torch.relu(torch.randn(n, T, Vr, chw, device=dev)).to(torch.bfloat16)
+    # ---- forward
+    O = torch.full((n * T_out * Vr, chw), float("nan"), dtype=torch.bfloat16, device=dev)
+    before = _lib.lib().dsg_debug_counter(3)
+    assert ops.ms_conv(h.view(-1, chw), O, layout, Ws, n=n, T_in=T, T_out=T_out, stride=stride, Vr=Vr, transposed=False)
+    assert _lib.lib().dsg_debug_counter(3) == before + 1
+    hf = h.float().permute(0, 3, 1, 2).requires_grad_()      # [n, C, T, V]
+    refs = []
+    for j, (w, d) in enumerate(zip(widths, dil)):
+        lo_j = layout[j][1]
+        refs.append(F.conv2d(hf[:, lo_j:lo_j + w], Ws[j][0], Ws[j][1], (stride, 1), (d, 0), (d, 1)))
+    ref = torch.cat(refs, 1)                                 # [n, span, T_out, V]
+    got = O.view(n, T_out, Vr, chw)[..., :span].permute(0, 3, 1, 2)
+    close(got, ref, torch.bfloat16, "ms_conv forward")
+    # ---- data gradient with mask, partner and statistics
+    Cfull = Ct
+    d_o = torch.randn(n, T_out, Vr, chw, device=dev).to(torch.bfloat16)
+    Braw = torch.randn(n * T * Vr, Cfull, device=dev).to(torch.bfloat16)
+    E = torch.full((n * T * Vr, Cfull), 7.0, dtype=torch.bfloat16, device=dev)
+    ss, sq = torch.zeros(Cfull, dtype=torch.float64, device=dev), torch.zeros(Cfull, dtype=torch.float64, device=dev)
+    assert ops.ms_conv(d_o.view(-1, chw), E, layout, Ws, n=n, T_in=T, T_out=T_out, stride=stride, Vr=Vr, transposed=True,
+                       mask=h.view(-1, chw), partner=Braw, stat_sum=ss, stat_sq=sq)
+    ref.backward(d_o.float()[..., :span].permute(0, 3, 1, 2))
+    dref = hf.grad.permute(0, 2, 3, 1)[..., :span] * (h.float()[..., :span] > 0)           # [n, T, V, span]
+    gotE = E.view(n, T, Vr, Cfull)
+    close(gotE[..., :span], dref, torch.bfloat16, "ms_conv data gradient")
+    assert torch.all(gotE[..., chw:] == 7.0), "channels outside the conv span's 16-byte chunks must not be written"
+    assert torch.all(gotE[..., span:chw] == 0.0)             # the last chunk is padded with zeros (the caller writes those channels afterwards)
+    dq = gotE[..., :span].float().reshape(-1, span)
+    close(ss[:span], dq.sum(0), torch.bfloat16, "sum e")
+    close(sq[:span], (dq * Braw.float()[:, :span]).sum(0), torch.bfloat16, "sum e*b")
+    assert float(ss[span:].abs().sum()) == 0.0
