@@ -77,7 +77,8 @@ class MsCombineArgs(C.Structure):
                 ("b", ActSrc), ("o", vp), ("ld_o", c_ll), ("add_coeff", vp), ("feat", vp), ("ld_feat", c_ll),
                 ("oglob", vp), ("stat_sum", vp), ("stat_sq", vp),
                 ("dfeat", ActSrc), ("d_o", vp), ("ld_do", c_ll), ("e", vp), ("ld_e", c_ll),
-                ("b_raw", vp), ("ld_b", c_ll), ("e_sum", vp), ("e_sq", vp), ("dadd_coeff", vp)]
+                ("b_raw", vp), ("ld_b", c_ll), ("e_sum", vp), ("e_sq", vp), ("dadd_coeff", vp),
+                ("d_o_full", c_int), ("pad_", c_int)]
 
 
 class MsBranch(C.Structure):

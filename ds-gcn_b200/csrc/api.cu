@@ -11,6 +11,7 @@
 #include "ms_temporal_tc.cuh"
 #include "topology.cuh"
 #include "misc.cuh"
+#include "ms_mix.cuh"
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -172,6 +173,12 @@ int dsg_ms_combine_fwd(const dsg_ms_combine_args* a, void* stream) {
     if (!a || !dtype_ok(a->dtype) || a->V > 32) return fail("dsg_ms_combine_fwd", "bad arguments");
     long long n_frames = (long long)a->n_samples * a->T_out;
     if (n_frames <= 0) return 0;
+    {
+        bool handled = false;                                          // 16-byte vector kernel (bf16, aligned)
+        const char* e = dsg::launch_ms_mix_fwd(*a, (dsg_stream_t)stream, &handled);
+        if (e) return fail("dsg_ms_combine_fwd", e);
+        if (handled) return 0;
+    }
     dim3 grid((unsigned)((n_frames + 7) / 8), (a->C + dsg::PW_CT - 1) / dsg::PW_CT);
     if (a->dtype == DSG_BF16) dsg_launch(dsg::ms_combine_fwd_kernel<bf16>, grid, dim3(dsg::PW_THREADS), 0, (dsg_stream_t)stream, *a);
     else dsg_launch(dsg::ms_combine_fwd_kernel<float>, grid, dim3(dsg::PW_THREADS), 0, (dsg_stream_t)stream, *a);
@@ -183,6 +190,12 @@ static int ms_combine_bwd_impl(const dsg_ms_combine_args* a, int parts, void* st
     dsg_stream_t st = (dsg_stream_t)stream;
     long long n_out = (long long)a->n_samples * a->T_out, n_in = (long long)a->n_samples * a->T_in;
     if (n_out <= 0) return 0;
+    {
+        bool handled = false;                                          // 16-byte vector kernels (bf16, aligned, full-width d_o)
+        const char* e = dsg::launch_ms_mix_bwd(*a, parts, st, &handled);
+        if (e) return fail("dsg_ms_combine_bwd", e);
+        if (handled) return 0;
+    }
     if (parts & 1) {
         dim3 g1((unsigned)((n_out + 7) / 8), (a->C + dsg::PW_CT - 1) / dsg::PW_CT);
         if (a->dtype == DSG_BF16) dsg_launch(dsg::ms_combine_bwd_o_kernel<bf16>, g1, dim3(dsg::PW_THREADS), 0, st, *a);

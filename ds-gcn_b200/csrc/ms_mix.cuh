@@ -1,0 +1,368 @@
+// Streaming halves of the multi-scale temporal unit around dsg_ms_conv (tcn.py:383-396, 407-420): everything that is not a
+// convolution.  16-byte (8-channel) vector kernels, thread = (frame, channel chunk), every row of a frame walked by the same
+// thread so the joint-mean ("global") row is a register, several independent loads in flight per thread.
+//   forward   : feat[n,t',v,:] = O_v + O_V * add_coeff[v] with O = conv outputs (read) | 3x1 max-pool of relu(bn(B)) | bn(B) at s*t';
+//               oglob = O_V (fp32, saved for backward); BatchNorm statistics of transform.0
+//   backward 1: dO[n,t',v,:] = dfeat_v, dO[n,t',V,:] = sum_v dfeat_v * add_coeff[v]; dadd_coeff[v] += sum dfeat_v . oglob
+//   backward 2: e of the max-pool range (arg-max routing, first maximum wins as ATen max_pool2d, ReLU mask) and of the pass range,
+//               BN-backward sums of the max range; read-modify-write of chunks shared with the conv range
+#pragma once
+#include "dsg_common.h"
+
+namespace dsg {
+
+constexpr int MX_THREADS = 256;
+constexpr int MX_U = 5;              // rows in flight per thread
+
+struct MxKinds { unsigned conv, mx, pass; };     // bit e: channel c8 + e is of that kind
+DSG_D MxKinds mx_kinds(const dsg_ms_combine_args& a, int c8) {
+    MxKinds k{0u, 0u, 0u};
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        const int c = c8 + e;
+        if (c >= a.conv_lo && c < a.conv_hi) k.conv |= 1u << e;
+        else if (c >= a.max_lo && c < a.max_hi) k.mx |= 1u << e;
+        else if (c >= a.pass_lo && c < a.pass_hi) k.pass |= 1u << e;
+    }
+    return k;
+}
+DSG_D void mx_coefs(const dsg_ms_combine_args& a, int c8, float* ka, float* kb) {
+    load8f(a.b.a1 ? a.b.a1 + c8 : nullptr, ka, 1.f);
+    load8f(a.b.b1 ? a.b.b1 + c8 : nullptr, kb, 0.f);
+    if (a.b.b2) { float t[8]; load8f(a.b.b2 + c8, t, 0.f);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) kb[e] += t[e]; }
+}
+DSG_D uint4 mx_ld(const void* base, long long row, long long ld, int c8) {
+    return *reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(base) + row * ld + c8);
+}
+
+struct MxRaw { uint4 o, bm, bc, bp; };
+DSG_D MxRaw mx_issue(const dsg_ms_combine_args& a, const MxKinds& k, long long fo, long long fi, int j, int Vp, bool has_m, bool has_p, int c8) {
+    MxRaw r;
+    r.o = r.bm = r.bc = r.bp = make_uint4(0u, 0u, 0u, 0u);
+    if (k.conv) r.o = mx_ld(a.o, fo * Vp + j, a.ld_o, c8);
+    if (k.mx | k.pass) r.bc = mx_ld(a.b.x1, fi * Vp + j, a.b.ld1, c8);
+    if (k.mx) {
+        if (has_m) r.bm = mx_ld(a.b.x1, (fi - 1) * Vp + j, a.b.ld1, c8);
+        if (has_p) r.bp = mx_ld(a.b.x1, (fi + 1) * Vp + j, a.b.ld1, c8);
+    }
+    return r;
+}
+DSG_D void mx_finish(const MxRaw& r, const MxKinds& k, bool has_m, bool has_p, const float* ka, const float* kb, float* out) {
+    float o[8], hc[8];
+    unpack8(r.o, o);
+    unpack8(r.bc, hc);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) hc[e] = fmaf(hc[e], ka[e], kb[e]);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) out[e] = (k.conv >> e & 1u) ? o[e] : ((k.pass >> e & 1u) ? hc[e] : 0.f);
+    if (k.mx) {
+        float m[8], t[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) m[e] = fmaxf(hc[e], 0.f);
+        if (has_m) { unpack8(r.bm, t);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) m[e] = fmaxf(m[e], fmaf(t[e], ka[e], kb[e])); }
+        if (has_p) { unpack8(r.bp, t);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) m[e] = fmaxf(m[e], fmaf(t[e], ka[e], kb[e])); }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) if (k.mx >> e & 1u) out[e] = m[e];
+    }
+}
+
+__global__ void __launch_bounds__(MX_THREADS) ms_mix_fwd_kernel(dsg_ms_combine_args a, int frames_per_cta) {
+    DSG_SHARED float s_red[2][2048];                     // [lanes][C] with lanes * C == 2048
+    DSG_SHARED float addc_s[32];
+    const int tid = threadIdx.x, nch = a.C >> 3, lanes = MX_THREADS / nch;
+    const int cc = tid % nch, fl = tid / nch, c8 = cc * 8;
+    const int V = a.V, Vp = a.V + a.has_ext, s = a.stride;
+    if (tid < 32) addc_s[tid] = (a.has_ext && tid < V) ? a.add_coeff[tid] : 0.f;
+    __syncthreads();
+    const MxKinds k = mx_kinds(a, c8);
+    float ka[8], kb[8], s1[8], s2[8];
+    mx_coefs(a, c8, ka, kb);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) s1[e] = s2[e] = 0.f;
+    const long long n_frames = (long long)a.n_samples * a.T_out;
+    long long fend = (long long)(blockIdx.x + 1) * frames_per_cta;
+    if (fend > n_frames) fend = n_frames;
+    bf16* feat = reinterpret_cast<bf16*>(a.feat);
+    if (fl < lanes)
+        for (long long f = (long long)blockIdx.x * frames_per_cta + fl; f < fend; f += lanes) {
+            const int n = (int)(f / a.T_out), tp = (int)(f - (long long)n * a.T_out), tc = tp * s;
+            const long long fi = (long long)n * a.T_in + tc;
+            const bool has_m = tc - 1 >= 0, has_p = tc + 1 < a.T_in;
+            float glob[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) glob[e] = 0.f;
+            if (a.has_ext) {
+                mx_finish(mx_issue(a, k, f, fi, V, Vp, has_m, has_p, c8), k, has_m, has_p, ka, kb, glob);
+                float4* og = reinterpret_cast<float4*>(a.oglob + f * a.C + c8);
+                og[0] = make_float4(glob[0], glob[1], glob[2], glob[3]);
+                og[1] = make_float4(glob[4], glob[5], glob[6], glob[7]);
+            }
+            for (int v0 = 0; v0 < V; v0 += MX_U) {
+                MxRaw raw[MX_U];
+#pragma unroll
+                for (int u = 0; u < MX_U; ++u)
+                    if (v0 + u < V) raw[u] = mx_issue(a, k, f, fi, v0 + u, Vp, has_m, has_p, c8);
+#pragma unroll
+                for (int u = 0; u < MX_U; ++u) {
+                    if (v0 + u >= V) break;
+                    float val[8];
+                    mx_finish(raw[u], k, has_m, has_p, ka, kb, val);
+                    const float ac = addc_s[v0 + u];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) val[e] = fmaf(glob[e], ac, val[e]);
+                    const uint4 pk = pack8(val);
+                    if (a.stat_sum) {
+                        unpack8(pk, val);                         // statistics of the stored (rounded) values
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) { s1[e] += val[e]; s2[e] += val[e] * val[e]; }
+                    }
+                    *reinterpret_cast<uint4*>(feat + (f * V + v0 + u) * a.ld_feat + c8) = pk;
+                }
+            }
+        }
+    if (a.stat_sum) {
+        if (fl < lanes) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) { s_red[0][fl * a.C + c8 + e] = s1[e]; s_red[1][fl * a.C + c8 + e] = s2[e]; }
+        }
+        __syncthreads();
+        for (int c = tid; c < a.C; c += MX_THREADS) {
+            float t1 = 0.f, t2 = 0.f;
+            for (int l = 0; l < lanes; ++l) { t1 += s_red[0][l * a.C + c]; t2 += s_red[1][l * a.C + c]; }
+            atomicAdd(a.stat_sum + c, (double)t1);
+            atomicAdd(a.stat_sq + c, (double)t2);
+        }
+    }
+}
+
+// dfeat (two-tensor BatchNorm-backward form) -> 8 channels
+struct MxD { float a1[8], b[8], a2[8]; };
+DSG_D void mx_dcoefs(const dsg_ms_combine_args& a, int c8, MxD& d) {
+    float t[8];
+    load8f(a.dfeat.a1 ? a.dfeat.a1 + c8 : nullptr, d.a1, 1.f);
+    load8f(a.dfeat.b1 ? a.dfeat.b1 + c8 : nullptr, d.b, 0.f);
+    load8f(a.dfeat.b2 ? a.dfeat.b2 + c8 : nullptr, t, 0.f);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) d.b[e] += t[e];
+    load8f(a.dfeat.a2 ? a.dfeat.a2 + c8 : nullptr, d.a2, 1.f);
+}
+
+__global__ void __launch_bounds__(MX_THREADS) ms_mix_bwd_o_kernel(dsg_ms_combine_args a, int frames_per_cta) {
+    DSG_SHARED float s_dadd[32], addc_s[32];
+    const int tid = threadIdx.x, nch = a.C >> 3, lanes = MX_THREADS / nch;
+    const int cc = tid % nch, fl = tid / nch, c8 = cc * 8;
+    const int V = a.V, Vp = a.V + a.has_ext;
+    if (tid < 32) { s_dadd[tid] = 0.f; addc_s[tid] = (a.has_ext && tid < V) ? a.add_coeff[tid] : 0.f; }
+    __syncthreads();
+    MxD dc;
+    mx_dcoefs(a, c8, dc);
+    const long long n_frames = (long long)a.n_samples * a.T_out;
+    long long fend = (long long)(blockIdx.x + 1) * frames_per_cta;
+    if (fend > n_frames) fend = n_frames;
+    bf16* dO = reinterpret_cast<bf16*>(a.d_o);
+    // the loop bounds are CTA-uniform (warp shuffles inside)
+    for (long long f0 = (long long)blockIdx.x * frames_per_cta; f0 < fend; f0 += lanes) {
+        const long long f = f0 + fl;
+        const bool ok = fl < lanes && f < fend;
+        float og[8], gsum[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { og[e] = 0.f; gsum[e] = 0.f; }
+        if (ok && a.has_ext) load8f(a.oglob + f * a.C + c8, og, 0.f);
+        for (int v0 = 0; v0 < V; v0 += MX_U) {
+            uint4 r1[MX_U], r2[MX_U];
+#pragma unroll
+            for (int u = 0; u < MX_U; ++u) {
+                r1[u] = r2[u] = make_uint4(0u, 0u, 0u, 0u);
+                if (ok && v0 + u < V) {
+                    r1[u] = mx_ld(a.dfeat.x1, f * V + v0 + u, a.dfeat.ld1, c8);
+                    if (a.dfeat.x2) r2[u] = mx_ld(a.dfeat.x2, f * V + v0 + u, a.dfeat.ld2, c8);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < MX_U; ++u) {
+                if (v0 + u >= V) break;
+                float d[8], x[8];
+                unpack8(r1[u], x);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) d[e] = fmaf(x[e], dc.a1[e], dc.b[e]);
+                if (a.dfeat.x2) {
+                    unpack8(r2[u], x);
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) d[e] = fmaf(x[e], dc.a2[e], d[e]);
+                }
+                float part = 0.f;
+                if (ok) {
+                    const uint4 pk = pack8(d);
+                    *reinterpret_cast<uint4*>(dO + (f * Vp + v0 + u) * a.ld_do + c8) = pk;
+                    const float ac = addc_s[v0 + u];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) { gsum[e] = fmaf(d[e], ac, gsum[e]); part = fmaf(d[e], og[e], part); }
+                }
+                if (a.has_ext) {
+                    part = warp_sum(part);
+                    if ((tid & 31) == 0) atomicAdd(&s_dadd[v0 + u], part);
+                }
+            }
+        }
+        if (ok && a.has_ext) *reinterpret_cast<uint4*>(dO + (f * Vp + V) * a.ld_do + c8) = pack8(gsum);
+    }
+    if (a.has_ext) {
+        __syncthreads();
+        if (tid < V) atomicAdd(a.dadd_coeff + tid, s_dadd[tid]);
+    }
+}
+
+// e of the max / pass ranges: thread = (input-frame row, 8-channel chunk of the span [ac0*8, (ac0+nac)*8))
+__global__ void __launch_bounds__(MX_THREADS) ms_mix_bwd_e_kernel(dsg_ms_combine_args a, int ac0, int nac, int rows_per_cta) {
+    DSG_SHARED float s_red[2][MX_THREADS];
+    const int tid = threadIdx.x, RL = MX_THREADS / nac;
+    const int ac = tid % nac, rl = tid / nac, c8 = (ac0 + ac) * 8;
+    const int Vp = a.V + a.has_ext, s = a.stride;
+    const MxKinds k = mx_kinds(a, c8);
+    float ka[8], kb[8], s1[8], s2[8];
+    mx_coefs(a, c8, ka, kb);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) s1[e] = s2[e] = 0.f;
+    const long long n_rows = (long long)a.n_samples * a.T_in * Vp;
+    long long rend = (long long)(blockIdx.x + 1) * rows_per_cta;
+    if (rend > n_rows) rend = n_rows;
+    bf16* E = reinterpret_cast<bf16*>(a.e);
+    const bool rmw = (k.mx | k.pass) != 0xffu;           // chunk shared with channels this pass does not own (conv range)
+    if (rl < RL && (k.mx | k.pass))
+        for (long long r = (long long)blockIdx.x * rows_per_cta + rl; r < rend; r += RL) {
+            const long long fi = r / Vp;
+            const int j = (int)(r - fi * Vp), n = (int)(fi / a.T_in), t = (int)(fi - (long long)n * a.T_in);
+            // relu(bn(B)) at frames t-2 .. t+2 (-1: outside the sample); every load of the item is issued before the first use
+            uint4 hb[5], dq[3], old = make_uint4(0u, 0u, 0u, 0u);
+            bool hin[5], din[3];
+            int tpo[3];
+#pragma unroll
+            for (int dd = 0; dd < 5; ++dd) {
+                const int t2 = t + dd - 2;
+                hin[dd] = (dd == 2 || k.mx) && t2 >= 0 && t2 < a.T_in;
+                hb[dd] = hin[dd] ? mx_ld(a.b.x1, r + (long long)(dd - 2) * Vp, a.b.ld1, c8) : make_uint4(0u, 0u, 0u, 0u);
+            }
+#pragma unroll
+            for (int w = 0; w < 3; ++w) {                    // windows t' with s*t' + dt == t, dt = w - 1
+                const int num = t - (w - 1);
+                din[w] = (w == 1 || k.mx) && num >= 0 && num % s == 0 && num / s < a.T_out;
+                tpo[w] = din[w] ? num / s : 0;
+                dq[w] = din[w] ? mx_ld(a.d_o, ((long long)n * a.T_out + tpo[w]) * Vp + j, a.ld_do, c8) : make_uint4(0u, 0u, 0u, 0u);
+            }
+            if (rmw) old = *reinterpret_cast<const uint4*>(E + r * a.ld_e + c8);
+            float h[5][8], braw[8];
+            unpack8(hb[2], braw);
+#pragma unroll
+            for (int dd = 0; dd < 5; ++dd) {
+                float x[8];
+                unpack8(hb[dd], x);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) h[dd][e] = hin[dd] ? fmaxf(fmaf(x[e], ka[e], kb[e]), 0.f) : -1.f;
+            }
+            float eout[8];
+            unpack8(old, eout);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) if ((k.mx | k.pass) >> e & 1u) eout[e] = 0.f;
+#pragma unroll
+            for (int w = 0; w < 3; ++w) {
+                if (!din[w]) continue;
+                const int dt = w - 1;
+                float d[8];
+                unpack8(dq[w], d);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    if (k.pass >> e & 1u) { if (dt == 0) eout[e] = d[e]; continue; }
+                    if (!(k.mx >> e & 1u)) continue;
+                    // window t' covers frames t-dt-1 .. t-dt+1 = h[1-dt .. 3-dt]; first maximum wins (ATen max_pool2d)
+                    float m = -3.0e38f;
+                    int am = -2;
+#pragma unroll
+                    for (int d2 = -1; d2 <= 1; ++d2) {
+                        const float hv = h[2 - dt + d2][e];
+                        if (hv >= 0.f && hv > m) { m = hv; am = d2; }
+                    }
+                    if (am == dt && h[2][e] > 0.f) eout[e] += d[e];
+                }
+            }
+            const uint4 pk = pack8(eout);
+            *reinterpret_cast<uint4*>(E + r * a.ld_e + c8) = pk;
+            if (a.e_sum && k.mx) {
+                float x[8];
+                unpack8(pk, x);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) { s1[e] += x[e]; s2[e] += x[e] * braw[e]; }
+            }
+        }
+    if (a.e_sum) {
+        // per channel: sum over the row lanes of this CTA (8 passes, one channel of the chunk each), max range only
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            __syncthreads();
+            s_red[0][tid] = s1[e];
+            s_red[1][tid] = s2[e];
+            __syncthreads();
+            if (tid < nac && (mx_kinds(a, (ac0 + tid) * 8).mx >> e & 1u)) {
+                float t1 = 0.f, t2 = 0.f;
+                for (int l = 0; l < RL; ++l) { t1 += s_red[0][l * nac + tid]; t2 += s_red[1][l * nac + tid]; }
+                atomicAdd(a.e_sum + (ac0 + tid) * 8 + e, (double)t1);
+                atomicAdd(a.e_sq + (ac0 + tid) * 8 + e, (double)t2);
+            }
+        }
+    }
+}
+
+static inline bool ms_mix_ok(const dsg_ms_combine_args& a) {
+    if (a.dtype != DSG_BF16 || a.C % 8 != 0 || a.C > 256 || a.C < 8 || MX_THREADS % (a.C / 8) != 0 || a.V + a.has_ext > 32) return false;
+    if (a.b.x2 || a.b.a2 || !act8_ok(a.b)) return false;
+    return true;
+}
+static inline bool al16(const void* p, long long ld) { return p != nullptr && (uintptr_t)p % 16 == 0 && ld % 8 == 0; }
+
+static const char* launch_ms_mix_fwd(const dsg_ms_combine_args& a, dsg_stream_t st, bool* handled) {
+    *handled = false;
+    if (!ms_mix_ok(a) || !al16(a.feat, a.ld_feat) || (a.conv_hi > a.conv_lo && !al16(a.o, a.ld_o))) return nullptr;
+    if (a.has_ext && (!a.oglob || (uintptr_t)a.oglob % 16 != 0 || !a.add_coeff)) return nullptr;
+    const long long n_frames = (long long)a.n_samples * a.T_out;
+    if (n_frames <= 0) { *handled = true; return nullptr; }
+    const int lanes = MX_THREADS / (a.C / 8);
+    int fpc = lanes * 2;
+    dsg_launch(ms_mix_fwd_kernel, dim3((unsigned)((n_frames + fpc - 1) / fpc)), dim3(MX_THREADS), 0, st, a, fpc);
+    *handled = true;
+    return dsg_launch_error();
+}
+
+static const char* launch_ms_mix_bwd(const dsg_ms_combine_args& a, int parts, dsg_stream_t st, bool* handled) {
+    *handled = false;
+    if (!a.d_o_full || !ms_mix_ok(a) || !act8_ok(a.dfeat) || !al16(a.d_o, a.ld_do) || a.ld_do < a.C || !al16(a.e, a.ld_e)) return nullptr;
+    if (a.has_ext && (!a.oglob || (uintptr_t)a.oglob % 16 != 0 || !a.add_coeff || !a.dadd_coeff)) return nullptr;
+    const long long n_out = (long long)a.n_samples * a.T_out, n_in = (long long)a.n_samples * a.T_in;
+    if (n_out <= 0) { *handled = true; return nullptr; }
+    if (parts & 1) {
+        const int lanes = MX_THREADS / (a.C / 8);
+        const int fpc = lanes * 2;
+        dsg_launch(ms_mix_bwd_o_kernel, dim3((unsigned)((n_out + fpc - 1) / fpc)), dim3(MX_THREADS), 0, st, a, fpc);
+        if (const char* e = dsg_launch_error()) return e;
+    }
+    if (parts & 2) {
+        int lo = 1 << 30, hi = 0;
+        if (a.max_hi > a.max_lo) { lo = a.max_lo < lo ? a.max_lo : lo; hi = a.max_hi > hi ? a.max_hi : hi; }
+        if (a.pass_hi > a.pass_lo) { lo = a.pass_lo < lo ? a.pass_lo : lo; hi = a.pass_hi > hi ? a.pass_hi : hi; }
+        if (hi > lo) {
+            const int ac0 = lo >> 3, nac = ((hi + 7) >> 3) - ac0;
+            const long long n_rows = n_in * (a.V + a.has_ext);
+            const int RL = MX_THREADS / nac, rpc = RL * 4;
+            dsg_launch(ms_mix_bwd_e_kernel, dim3((unsigned)((n_rows + rpc - 1) / rpc)), dim3(MX_THREADS), 0, st, a, ac0, nac, rpc);
+            if (const char* e = dsg_launch_error()) return e;
+        }
+    }
+    *handled = true;
+    return nullptr;
+}
+
+}  // namespace dsg

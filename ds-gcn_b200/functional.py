@@ -571,9 +571,9 @@ def mstcn_backward(m, sv, dout, grads):
         #      one tcgen05 launch with the ReLU mask (H > 0) and the BN-backward sums in its epilogue
         chw = H.shape[1]
         tap = _ms_tap_path(m, layout, ranges, dt)
-        d_o = torch.empty(rows_o, chw, dtype=dt, device=dev)
+        d_o = torch.empty(rows_o, Ct, dtype=dt, device=dev)           # gradient w.r.t. every branch output, joint-mean row included
         ckw = dict(n=n, T_in=T, T_out=T_out, stride=s, V=V, has_ext=has_ext, ranges=ranges, add_coeff=m.add_coeff if has_ext else None,
-                   e_sum=b_b.ssum, e_sq=b_b.ssq, dadd_coeff=dadd)
+                   e_sum=b_b.ssum, e_sq=b_b.ssq, dadd_coeff=dadd, d_o_full=True)
         ops.ms_combine_bwd(Act(B, c_b.a, c_b.b), dfeat, d_o, E3, sv["oglob"], B, parts=1, **ckw)
         tap_done = tap is not None and ops.ms_conv(d_o, E3, layout, tap[1], n=n, T_in=T, T_out=T_out, stride=s, Vr=Vp, transposed=True,
                                                    mask=H, partner=B, stat_sum=b_b.ssum, stat_sq=b_b.ssq)

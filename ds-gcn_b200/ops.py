@@ -301,11 +301,15 @@ def ms_combine_fwd(b, o, feat, oglob, *, n, T_in, T_out, stride, V, has_ext, ran
     L.call("dsg_ms_combine_fwd", C.byref(a), L.stream())
 
 
-def ms_combine_bwd(b, dfeat, d_o, e, oglob, b_raw, *, n, T_in, T_out, stride, V, has_ext, ranges, add_coeff, e_sum, e_sq, dadd_coeff, parts=3):
+def ms_combine_bwd(b, dfeat, d_o, e, oglob, b_raw, *, n, T_in, T_out, stride, V, has_ext, ranges, add_coeff, e_sum, e_sq, dadd_coeff, parts=3,
+                   d_o_full=False):
     dfeat = as_act(dfeat)
     a = ms_combine_args(dfeat.dtype, n, T_in, T_out, stride, V, has_ext, dfeat.C, ranges, b, None, add_coeff)
     a.dfeat = dfeat.struct()
     a.d_o, a.ld_do = L.ptr(d_o), _ld(d_o)
+    a.d_o_full = int(d_o_full)
+    if d_o_full:
+        assert d_o.shape[-1] >= dfeat.C
     a.e, a.ld_e = L.ptr(e), _ld(e)
     a.oglob = L.ptr(oglob)
     a.b_raw, a.ld_b = L.ptr(b_raw), _ld(b_raw)

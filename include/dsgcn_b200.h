@@ -259,6 +259,9 @@ typedef struct dsg_ms_combine_args {
     double* e_sum;
     double* e_sq;
     float* dadd_coeff;
+    int d_o_full;             /* 1: d_o holds all C channels (ld_do >= C): the gradient w.r.t. every branch output (joint-mean row
+                                 included) is written by the per-output-frame pass and read back by the per-input-frame pass */
+    int pad_;
 } dsg_ms_combine_args;
 int dsg_ms_combine_fwd(const dsg_ms_combine_args* a, void* stream);
 int dsg_ms_combine_bwd(const dsg_ms_combine_args* a, void* stream);

@@ -496,6 +496,66 @@ def test_ms_combine(dev, dtype, stride, has_ext):
         close(dadd, addc.grad, dtype, "dadd_coeff")
 
 
+@pytest.mark.parametrize("stride", [1, 2])
+@pytest.mark.parametrize("has_ext", [False, True])
+def test_ms_mix_vector_kernels(dev, stride, has_ext):
+    """The 16-byte vector forms of the streaming halves (ms_mix.cuh, bf16): channel ranges that do not fall on chunk boundaries
+    (conv | max | pass = 44 | 10 | 10 like a 64-channel dgmstcn), the BatchNorm-backward two-tensor dfeat, full-width dO, and the
+    per-input-frame pass run AFTER something else has written the conv range (read-modify-write of shared chunks)."""
+    torch.manual_seed(11 + stride)
+    dtype = torch.bfloat16
+    n, T, V, Cn = 3, 9, 25, 64
+    Vp = V + int(has_ext)
+    T_out = (T - 1) // stride + 1
+    ranges = ((0, 44), (44, 54), (54, 64))
+    B = torch.randn(n, T, Vp, Cn).to(dtype).float().requires_grad_()
+    Oc = torch.randn(n, T_out, Vp, 48).to(dtype).float().requires_grad_()
+    a1 = torch.cat([torch.rand(54) + 0.5, torch.ones(10)])
+    b1 = torch.cat([torch.randn(54) * 0.3, torch.zeros(10)])
+    addc = torch.randn(V).requires_grad_()
+    h = B * a1 + b1
+    mx = F.max_pool2d(torch.relu(h[..., 44:54]).permute(0, 3, 1, 2), (3, 1), (stride, 1), (1, 0)).permute(0, 2, 3, 1)
+    ps = h[:, ::stride, :, 54:]
+    o_all = torch.cat([Oc[..., :44], mx, ps], -1)
+    feat_ref = o_all[:, :, :V] + (o_all[:, :, V:] * addc[None, None, :, None] if has_ext else 0)
+    # dfeat in the BatchNorm-backward form ca*e + cb*y + cc
+    e2, y2 = torch.randn_like(feat_ref).to(dtype).float(), torch.randn_like(feat_ref).to(dtype).float()
+    ca, cb, cc = torch.rand(Cn) + 0.5, torch.randn(Cn) * 0.2, torch.randn(Cn) * 0.1
+    gy = e2 * ca + y2 * cb + cc
+    feat_ref.backward(gy)
+    d = lambda t: t.detach().to(dtype).to(dev)
+    Bd, Od = d(B).reshape(-1, Cn), d(Oc).reshape(-1, 48)
+    feat = torch.empty(n * T_out * V, Cn, dtype=dtype, device=dev)
+    oglob = torch.zeros(n * T_out, Cn, device=dev)
+    ss, sq = torch.zeros(Cn, dtype=torch.float64, device=dev), torch.zeros(Cn, dtype=torch.float64, device=dev)
+    bact = ops.Act(Bd, a1.to(dev), b1.to(dev))
+    kw = dict(n=n, T_in=T, T_out=T_out, stride=stride, V=V, has_ext=has_ext, ranges=ranges, add_coeff=addc.detach().to(dev) if has_ext else None)
+    ops.ms_combine_fwd(bact, Od, feat, oglob if has_ext else None, stat_sum=ss, stat_sq=sq, **kw)
+    close(feat.reshape(n, T_out, V, Cn), feat_ref, dtype, "feat")
+    fq = feat.float().cpu()
+    close(ss, fq.sum(0), dtype)
+    close(sq, (fq ** 2).sum(0), dtype)
+    if has_ext:
+        close(oglob.reshape(n, T_out, Cn), o_all[:, :, V], dtype, "oglob")
+    d_o = torch.zeros(n * T_out * Vp, Cn, dtype=dtype, device=dev)
+    e = torch.full((n * T * Vp, Cn), 3.0, dtype=dtype, device=dev)       # 3.0 stands for "written by the conv data gradient"
+    es, eq = torch.zeros(Cn, dtype=torch.float64, device=dev), torch.zeros(Cn, dtype=torch.float64, device=dev)
+    dadd = torch.zeros(V, device=dev)
+    dfeat = ops.Act(d(e2).reshape(-1, Cn), ca.to(dev), cc.to(dev), d(y2).reshape(-1, Cn), cb.to(dev))
+    bkw = dict(e_sum=es, e_sq=eq, dadd_coeff=dadd if has_ext else None, d_o_full=True, **kw)
+    ops.ms_combine_bwd(bact, dfeat, d_o, e, oglob if has_ext else None, Bd, parts=1, **bkw)
+    ops.ms_combine_bwd(bact, dfeat, d_o, e, oglob if has_ext else None, Bd, parts=2, **bkw)
+    close(d_o.reshape(n, T_out, Vp, Cn)[..., :44], Oc.grad[..., :44], dtype, "d_o")
+    er = e.reshape(n, T, Vp, Cn)
+    assert torch.all(er[..., :44] == 3.0), "the conv range of a shared chunk must survive the max / pass pass"
+    close(er[..., 44:] * a1[44:].to(dev), B.grad[..., 44:], dtype, "E")
+    eref = (B.grad / a1)[..., 44:54]
+    close(es[44:54], eref.sum((0, 1, 2)), dtype)
+    close(eq[44:54], (eref * B.detach()[..., 44:54]).sum((0, 1, 2)), dtype)
+    if has_ext:
+        close(dadd, addc.grad, dtype, "dadd_coeff")
+
+
 def test_sgd_step_matches_torch(dev):
     torch.manual_seed(9)
     p = torch.randn(1000)
