@@ -50,6 +50,14 @@ def parse():
     p.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
     p.add_argument("--no-graph", action="store_true")
     p.add_argument("--buckets", type=int, default=3, help="gradient buckets (all-reduce overlapped with backward)")
+    p.add_argument("--sweep", default=None, choices=["coco"],
+                   help="BASELINE config 4: large-batch inference sweep on 2-D HRNet keypoints (COCO layout, V=17, pixel-unit inputs), "
+                        "batch 1..4096 clips on one GPU; prints one JSON line with the whole sweep (and writes --sweep-out)")
+    p.add_argument("--sweep-out", default=None)
+    p.add_argument("--sweep-max", type=int, default=4096)
+    p.add_argument("--profile-step", action="store_true",
+                   help="profiling aid: after the eager warm-up run ONE eager step between cudaProfilerStart/Stop and exit "
+                        "(ncu --profile-from-start off ...); prints no bench line")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--ref-clips", type=int, default=REF_CLIPS, help="clips per step of the CPU reference arm (N=16: SURVEY 8d)")
     p.add_argument("--ref-budget", type=float, default=240.0, help="seconds the whole reference run may take (the batch shrinks to fit)")
@@ -276,6 +284,79 @@ class ClockSampler:
         return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None, reasons=reasons, samples=len(sm))
 
 
+def run_sweep(args):
+    """Forward (eval, no_grad) clips/s of the COCO-layout DS-GCN over batch 1 .. 4096 on one GPU: device-resident inputs,
+    CUDA events, >= 3 warm-up and >= 5 timed steps per size (sized to ~0.5 s), inputs re-used (sizes above ~16 clips exceed L2)."""
+    import dsgcn_b200
+    from dsgcn_b200 import modules as Mod
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(0)
+    dtype = torch.bfloat16 if args.dtype == "bf16" else torch.float32
+    Mod.set_compute_dtype(dtype)
+    torch.manual_seed(1234)
+    np.random.seed(0)
+    cfg = {**NORTH_STAR, "graph_cfg": dict(layout="coco", mode="random", num_filter=3, init_off=.04, init_std=.02)}
+    model = dsgcn_b200.RecognizerGCN(backbone=dict(type="DGSTGCN", **cfg),
+                                    cls_head=dict(type="GCNHead", num_classes=400, in_channels=256)).to(dev).eval()
+    with torch.no_grad():
+        for n_, p_ in model.named_parameters():
+            if n_.rsplit(".", 1)[-1] in ("alpha", "beta", "add_coeff"):
+                p_.normal_(0, 0.1)
+        model.backbone.data_bn.running_mean.copy_(torch.tensor([128.0, 128.0, 0.5]).repeat(17))
+        model.backbone.data_bn.running_var.copy_(torch.tensor([74.0 ** 2, 74.0 ** 2, 0.083]).repeat(17))
+    T, V = 100, 17
+    rows = []
+    n = 1
+    while n <= args.sweep_max:
+        g = torch.Generator().manual_seed(n)
+        x = torch.cat([torch.rand(n, 2, T, V, 2, generator=g) * 256, torch.rand(n, 2, T, V, 1, generator=g)], -1).to(dev)   # (x, y) pixels, score
+
+        def eager():
+            with torch.no_grad():
+                return model.cls_head(model.extract_feat(x))
+        for _ in range(3):
+            eager()
+        torch.cuda.synchronize()
+        step, graphed = eager, False
+        if not args.no_graph:                       # serving path: one captured forward per batch size, replayed
+            try:
+                gr = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(gr):
+                    eager()
+                gr.replay()
+                torch.cuda.synchronize()
+                step, graphed = gr.replay, True
+            except Exception as e:
+                print(f"[sweep] graph capture failed at batch {n} ({type(e).__name__}); eager", file=sys.stderr)
+                torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); step(); e1.record(); torch.cuda.synchronize()
+        k = int(max(5, min(50, 500.0 / max(e0.elapsed_time(e1), 1e-3))))
+        e0.record()
+        for _ in range(k):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / k
+        rows.append(dict(batch=n, ms_per_step=round(ms, 4), clips_per_s=round(n / (ms * 1e-3), 1), steps=k, cuda_graph=graphed,
+                         peak_mem_gb=round(torch.cuda.max_memory_allocated() / 1e9, 2)))
+        if graphed:
+            del gr
+        print(f"[sweep] batch {n:5d}: {ms:9.3f} ms  {n / (ms * 1e-3):10.1f} clips/s", file=sys.stderr, flush=True)
+        del x
+        n *= 2
+    best = max(rows, key=lambda r: r["clips_per_s"])
+    line = dict(metric="DS-GCN fwd clips/sec (COCO layout, M=2,T=100,V=17,C=3), batch sweep", value=best["clips_per_s"], unit="clips/s", n_gpus=1,
+                higher_is_better=True, dtype=args.dtype, data="synthetic (pixel-unit x,y ~ U(0,256), score ~ U(0,1))",
+                config=dict(workload="DS-GCN kinetics400_hrnet joint eval forward, batch sweep", layout="coco", M=2, T=T, V=V, C=3,
+                            best_batch=best["batch"]), sweep=rows)
+    print(json.dumps(line))
+    if args.sweep_out:
+        with open(args.sweep_out, "w") as fh:
+            json.dump(line, fh, indent=1)
+
+
 def _trace(msg):
     if os.environ.get("DSG_BENCH_TRACE"):
         print(f"[bench r{os.environ.get('RANK', 0)} {time.strftime('%H:%M:%S')}] {msg}", file=sys.stderr, flush=True)
@@ -291,6 +372,10 @@ def main():
     workload = ("DS-GCN ntu60_xsub_3dkp joint training step (fwd+loss+bwd+SGD)" if args.mode == "train"
                 else "DS-GCN ntu60_xsub_3dkp joint eval forward")
 
+    if args.sweep:
+        if rank == 0:
+            run_sweep(args)
+        return
     if args.impl == "reference":
         if rank != 0:
             return
@@ -366,6 +451,15 @@ def main():
     torch.cuda.current_stream().wait_stream(side)
     torch.cuda.synchronize()
     _trace("eager warm-up done")
+    if args.profile_step:
+        L.side_enabled = False                      # serialised launches: one stream, the order of the step
+        device_step(dev_x[0], dev_y[0])
+        torch.cuda.synchronize()
+        torch.cuda.cudart().cudaProfilerStart()
+        device_step(dev_x[1], dev_y[1])
+        torch.cuda.synchronize()
+        torch.cuda.cudart().cudaProfilerStop()
+        return
     graph = None
     if not args.no_graph:
         try:

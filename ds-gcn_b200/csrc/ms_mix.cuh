@@ -218,101 +218,158 @@ __global__ void __launch_bounds__(MX_THREADS) ms_mix_bwd_o_kernel(dsg_ms_combine
     }
 }
 
-// e of the max / pass ranges: thread = (input-frame row, 8-channel chunk of the span [ac0*8, (ac0+nac)*8))
-__global__ void __launch_bounds__(MX_THREADS) ms_mix_bwd_e_kernel(dsg_ms_combine_args a, int ac0, int nac, int rows_per_cta) {
-    DSG_SHARED float s_red[2][MX_THREADS];
-    const int tid = threadIdx.x, RL = MX_THREADS / nac;
-    const int ac = tid % nac, rl = tid / nac, c8 = (ac0 + ac) * 8;
+// e of the max / pass ranges.  Thread = (sample, joint row, 8-channel chunk of the span [ac0*8, (ac0+nac)*8), run of MX_TT input
+// frames): the thread slides along t, so relu(bn(B)) at t-2 .. t+2 is a register ring (one new 16-byte load per frame instead of
+// five) and all index arithmetic is done once per run.
+constexpr int MX_TT = 10;
+__global__ void __launch_bounds__(MX_THREADS, 2) ms_mix_bwd_e_kernel(dsg_ms_combine_args a, int ac0, int nac, int nseg) {
+    DSG_SHARED float s_red[2][1024];
+    const int tid = threadIdx.x;
     const int Vp = a.V + a.has_ext, s = a.stride;
+    // item = ((n * nseg + seg) * Vp + j) * nacp + ac : chunks of a row are adjacent lanes (nacp = nac rounded up to a power of two,
+    // so the lanes of a warp that own the same chunk are a fixed stride apart: shuffle reduction of the statistics), rows next
+    int nacp = 1;
+    while (nacp < nac) nacp <<= 1;
+    const long long n_items = (long long)a.n_samples * nseg * Vp * nacp;
+    const long long item = (long long)blockIdx.x * MX_THREADS + tid;
+    const int ac = (int)(item & (nacp - 1));
+    const bool live = item < n_items && ac < nac;
+    const long long r1 = item / nacp;
+    const int j = live ? (int)(r1 % Vp) : 0;
+    const long long r2 = r1 / Vp;
+    const int seg = live ? (int)(r2 % nseg) : 0, n = live ? (int)(r2 / nseg) : 0;
+    const int c8 = (ac0 + ac) * 8;
     const MxKinds k = mx_kinds(a, c8);
     float ka[8], kb[8], s1[8], s2[8];
     mx_coefs(a, c8, ka, kb);
 #pragma unroll
     for (int e = 0; e < 8; ++e) s1[e] = s2[e] = 0.f;
-    const long long n_rows = (long long)a.n_samples * a.T_in * Vp;
-    long long rend = (long long)(blockIdx.x + 1) * rows_per_cta;
-    if (rend > n_rows) rend = n_rows;
     bf16* E = reinterpret_cast<bf16*>(a.e);
     const bool rmw = (k.mx | k.pass) != 0xffu;           // chunk shared with channels this pass does not own (conv range)
-    if (rl < RL && (k.mx | k.pass))
-        for (long long r = (long long)blockIdx.x * rows_per_cta + rl; r < rend; r += RL) {
-            const long long fi = r / Vp;
-            const int j = (int)(r - fi * Vp), n = (int)(fi / a.T_in), t = (int)(fi - (long long)n * a.T_in);
-            // relu(bn(B)) at frames t-2 .. t+2 (-1: outside the sample); every load of the item is issued before the first use
-            uint4 hb[5], dq[3], old = make_uint4(0u, 0u, 0u, 0u);
-            bool hin[5], din[3];
-            int tpo[3];
+    if (live && (k.mx | k.pass)) {
+        const int t_beg = seg * MX_TT, t_end = t_beg + MX_TT < a.T_in ? t_beg + MX_TT : a.T_in;
+        const bf16* Bp = reinterpret_cast<const bf16*>(a.b.x1) + ((long long)n * a.T_in * Vp + j) * a.b.ld1 + c8;     // frame 0 of this column
+        const long long bstep = (long long)Vp * a.b.ld1;
+        const bf16* Dp = reinterpret_cast<const bf16*>(a.d_o) + ((long long)n * a.T_out * Vp + j) * a.ld_do + c8;
+        const long long dstep = (long long)Vp * a.ld_do;
+        bf16* Ep = E + ((long long)n * a.T_in * Vp + j) * a.ld_e + c8;
+        const long long estep = (long long)Vp * a.ld_e;
+        // ring of the RAW 16-byte chunks of B at frames t-2 .. t+2 (20 registers; relu(bn(.)) is re-evaluated per use, element by
+        // element, so few values are live at a time and two CTAs fit an SM); rin bit i: frame t-2+i is inside the sample
+        uint4 rb[5];
+        unsigned rin = 0u;
 #pragma unroll
-            for (int dd = 0; dd < 5; ++dd) {
-                const int t2 = t + dd - 2;
-                hin[dd] = (dd == 2 || k.mx) && t2 >= 0 && t2 < a.T_in;
-                hb[dd] = hin[dd] ? mx_ld(a.b.x1, r + (long long)(dd - 2) * Vp, a.b.ld1, c8) : make_uint4(0u, 0u, 0u, 0u);
-            }
+        for (int i = 0; i < 5; ++i) {
+            const int t2 = t_beg - 2 + i;
+            const bool in = k.mx && t2 >= 0 && t2 < a.T_in;
+            rb[i] = in ? *reinterpret_cast<const uint4*>(Bp + t2 * bstep) : make_uint4(0u, 0u, 0u, 0u);
+            rin |= in ? (1u << i) : 0u;
+        }
+        // gradient windows of the first frame
+        uint4 dq[3];
+        unsigned din = 0u;
 #pragma unroll
-            for (int w = 0; w < 3; ++w) {                    // windows t' with s*t' + dt == t, dt = w - 1
-                const int num = t - (w - 1);
-                din[w] = (w == 1 || k.mx) && num >= 0 && num % s == 0 && num / s < a.T_out;
-                tpo[w] = din[w] ? num / s : 0;
-                dq[w] = din[w] ? mx_ld(a.d_o, ((long long)n * a.T_out + tpo[w]) * Vp + j, a.ld_do, c8) : make_uint4(0u, 0u, 0u, 0u);
-            }
-            if (rmw) old = *reinterpret_cast<const uint4*>(E + r * a.ld_e + c8);
-            float h[5][8], braw[8];
-            unpack8(hb[2], braw);
-#pragma unroll
-            for (int dd = 0; dd < 5; ++dd) {
-                float x[8];
-                unpack8(hb[dd], x);
-#pragma unroll
-                for (int e = 0; e < 8; ++e) h[dd][e] = hin[dd] ? fmaxf(fmaf(x[e], ka[e], kb[e]), 0.f) : -1.f;
-            }
-            float eout[8];
-            unpack8(old, eout);
-#pragma unroll
-            for (int e = 0; e < 8; ++e) if ((k.mx | k.pass) >> e & 1u) eout[e] = 0.f;
+        for (int w = 0; w < 3; ++w) {                    // window t' with s*t' + dt == t, dt = w - 1
+            const int num = t_beg - (w - 1);
+            const bool in = (w == 1 || k.mx) && num >= 0 && num % s == 0 && num / s < a.T_out;
+            dq[w] = in ? *reinterpret_cast<const uint4*>(Dp + (num / s) * dstep) : make_uint4(0u, 0u, 0u, 0u);
+            din |= in ? (1u << w) : 0u;
+        }
+        uint4 old = rmw ? *reinterpret_cast<const uint4*>(Ep + t_beg * estep) : make_uint4(0u, 0u, 0u, 0u);
+        for (int t = t_beg; t < t_end; ++t) {
+            // ---- issue the loads of the NEXT frame before touching this one (software pipeline: two frames in flight)
+            const bool more = t + 1 < t_end;
+            const int tn = t + 3;
+            const bool nin = k.mx && more && tn < a.T_in;
+            const uint4 nraw = nin ? *reinterpret_cast<const uint4*>(Bp + tn * bstep) : make_uint4(0u, 0u, 0u, 0u);
+            uint4 ndq[3];
+            unsigned ndin = 0u;
 #pragma unroll
             for (int w = 0; w < 3; ++w) {
-                if (!din[w]) continue;
-                const int dt = w - 1;
-                float d[8];
-                unpack8(dq[w], d);
-#pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                    if (k.pass >> e & 1u) { if (dt == 0) eout[e] = d[e]; continue; }
-                    if (!(k.mx >> e & 1u)) continue;
-                    // window t' covers frames t-dt-1 .. t-dt+1 = h[1-dt .. 3-dt]; first maximum wins (ATen max_pool2d)
-                    float m = -3.0e38f;
-                    int am = -2;
-#pragma unroll
-                    for (int d2 = -1; d2 <= 1; ++d2) {
-                        const float hv = h[2 - dt + d2][e];
-                        if (hv >= 0.f && hv > m) { m = hv; am = d2; }
-                    }
-                    if (am == dt && h[2][e] > 0.f) eout[e] += d[e];
-                }
+                const int num = t + 1 - (w - 1);
+                const bool in = more && (w == 1 || k.mx) && num >= 0 && num % s == 0 && num / s < a.T_out;
+                ndq[w] = in ? *reinterpret_cast<const uint4*>(Dp + (num / s) * dstep) : make_uint4(0u, 0u, 0u, 0u);
+                ndin |= in ? (1u << w) : 0u;
             }
-            const uint4 pk = pack8(eout);
-            *reinterpret_cast<uint4*>(E + r * a.ld_e + c8) = pk;
+            const uint4 nold = (rmw && more) ? *reinterpret_cast<const uint4*>(Ep + (t + 1) * estep) : make_uint4(0u, 0u, 0u, 0u);
+            // ---- this frame
+            const uint32_t* rbw[5] = {&rb[0].x, &rb[1].x, &rb[2].x, &rb[3].x, &rb[4].x};
+            const uint32_t* dqw[3] = {&dq[0].x, &dq[1].x, &dq[2].x};
+            const uint32_t* oldw = &old.x;
+            uint32_t outw[4];
+            float bsum[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const int wd = e >> 1;
+                const bool hi16 = e & 1;
+                auto f16 = [&](uint32_t u) { return __uint_as_float(hi16 ? (u & 0xffff0000u) : (u << 16)); };
+                float ev = f16(oldw[wd]);
+                const float braw = f16(rbw[2][wd]);
+                if (k.pass >> e & 1u) ev = (din >> 1 & 1u) ? f16(dqw[1][wd]) : 0.f;
+                else if (k.mx >> e & 1u) {
+                    float h[5];
+#pragma unroll
+                    for (int i = 0; i < 5; ++i) h[i] = (rin >> i & 1u) ? fmaxf(fmaf(f16(rbw[i][wd]), ka[e], kb[e]), 0.f) : -1.f;
+                    ev = 0.f;
+#pragma unroll
+                    for (int w = 0; w < 3; ++w) {
+                        if (!(din >> w & 1u)) continue;
+                        const int dt = w - 1;
+                        // window t' covers frames t-dt-1 .. t-dt+1 = h[1-dt .. 3-dt]; first maximum wins (ATen max_pool2d)
+                        float m = -3.0e38f;
+                        int am = -2;
+#pragma unroll
+                        for (int d2 = -1; d2 <= 1; ++d2) {
+                            const float hv = h[2 - dt + d2];
+                            if (hv >= 0.f && hv > m) { m = hv; am = d2; }
+                        }
+                        if (am == dt && h[2] > 0.f) ev += f16(dqw[w][wd]);
+                    }
+                }
+                bsum[e] = braw;
+                // round to bf16 exactly as pack8 does, two elements per word
+                if (!hi16) outw[wd] = __float_as_uint(ev);
+                else outw[wd] = dsg_pack_bf16x2(__uint_as_float(outw[wd]), ev);
+            }
+            const uint4 pk = make_uint4(outw[0], outw[1], outw[2], outw[3]);
+            *reinterpret_cast<uint4*>(Ep + t * estep) = pk;
             if (a.e_sum && k.mx) {
                 float x[8];
                 unpack8(pk, x);
 #pragma unroll
-                for (int e = 0; e < 8; ++e) { s1[e] += x[e]; s2[e] += x[e] * braw[e]; }
+                for (int e = 0; e < 8; ++e) { s1[e] += x[e]; s2[e] += x[e] * bsum[e]; }
             }
+            // ---- slide
+            rb[0] = rb[1]; rb[1] = rb[2]; rb[2] = rb[3]; rb[3] = rb[4]; rb[4] = nraw;
+            rin = (rin >> 1) | (nin ? 16u : 0u);
+            dq[0] = ndq[0]; dq[1] = ndq[1]; dq[2] = ndq[2];
+            din = ndin;
+            old = nold;
         }
+    }
     if (a.e_sum) {
-        // per channel: sum over the row lanes of this CTA (8 passes, one channel of the chunk each), max range only
+        // lanes ac, ac + nacp, ... of a warp own the same chunk: xor-shuffle over the lane bits above nacp, then one shared-memory
+        // pass over the warps and one atomic per (chunk, channel) and CTA; max range only
+        const int lane = tid & 31, warp = tid >> 5;
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-            __syncthreads();
-            s_red[0][tid] = s1[e];
-            s_red[1][tid] = s2[e];
-            __syncthreads();
-            if (tid < nac && (mx_kinds(a, (ac0 + tid) * 8).mx >> e & 1u)) {
-                float t1 = 0.f, t2 = 0.f;
-                for (int l = 0; l < RL; ++l) { t1 += s_red[0][l * nac + tid]; t2 += s_red[1][l * nac + tid]; }
-                atomicAdd(a.e_sum + (ac0 + tid) * 8 + e, (double)t1);
-                atomicAdd(a.e_sq + (ac0 + tid) * 8 + e, (double)t2);
+            for (int o = 16; o >= nacp; o >>= 1) {
+                s1[e] += __shfl_xor_sync(0xffffffffu, s1[e], o);
+                s2[e] += __shfl_xor_sync(0xffffffffu, s2[e], o);
             }
+        }
+        float* red = &s_red[0][0];                        // [warp][nacp <= 16][16] floats = 8 * 16 * 16 <= 2 * MX_THREADS * 4
+        if (nacp <= 16 && lane < nacp) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) { red[(warp * nacp + lane) * 16 + e] = s1[e]; red[(warp * nacp + lane) * 16 + 8 + e] = s2[e]; }
+        }
+        __syncthreads();
+        for (int i = tid; i < nac * 16; i += MX_THREADS) {
+            const int c = i >> 4, q = i & 15, e = q & 7;
+            if (!(mx_kinds(a, (ac0 + c) * 8).mx >> e & 1u)) continue;
+            float t = 0.f;
+            for (int w = 0; w < MX_THREADS / 32; ++w) t += red[(w * nacp + c) * 16 + q];
+            atomicAdd((q < 8 ? a.e_sum : a.e_sq) + (ac0 + c) * 8 + e, (double)t);
         }
     }
 }
@@ -341,25 +398,26 @@ static const char* launch_ms_mix_bwd(const dsg_ms_combine_args& a, int parts, ds
     *handled = false;
     if (!a.d_o_full || !ms_mix_ok(a) || !act8_ok(a.dfeat) || !al16(a.d_o, a.ld_do) || a.ld_do < a.C || !al16(a.e, a.ld_e)) return nullptr;
     if (a.has_ext && (!a.oglob || (uintptr_t)a.oglob % 16 != 0 || !a.add_coeff || !a.dadd_coeff)) return nullptr;
-    const long long n_out = (long long)a.n_samples * a.T_out, n_in = (long long)a.n_samples * a.T_in;
+    const long long n_out = (long long)a.n_samples * a.T_out;
     if (n_out <= 0) { *handled = true; return nullptr; }
+    int lo = 1 << 30, hi = 0;
+    if (a.max_hi > a.max_lo) { lo = a.max_lo < lo ? a.max_lo : lo; hi = a.max_hi > hi ? a.max_hi : hi; }
+    if (a.pass_hi > a.pass_lo) { lo = a.pass_lo < lo ? a.pass_lo : lo; hi = a.pass_hi > hi ? a.pass_hi : hi; }
+    const int ac0 = hi > lo ? lo >> 3 : 0, nac = hi > lo ? ((hi + 7) >> 3) - ac0 : 0;
+    int nacp = 1;
+    while (nacp < nac) nacp <<= 1;
+    if (nacp > 16) return nullptr;                         // before anything is launched: the scalar kernels take the whole call
     if (parts & 1) {
         const int lanes = MX_THREADS / (a.C / 8);
         const int fpc = lanes * 2;
         dsg_launch(ms_mix_bwd_o_kernel, dim3((unsigned)((n_out + fpc - 1) / fpc)), dim3(MX_THREADS), 0, st, a, fpc);
         if (const char* e = dsg_launch_error()) return e;
     }
-    if (parts & 2) {
-        int lo = 1 << 30, hi = 0;
-        if (a.max_hi > a.max_lo) { lo = a.max_lo < lo ? a.max_lo : lo; hi = a.max_hi > hi ? a.max_hi : hi; }
-        if (a.pass_hi > a.pass_lo) { lo = a.pass_lo < lo ? a.pass_lo : lo; hi = a.pass_hi > hi ? a.pass_hi : hi; }
-        if (hi > lo) {
-            const int ac0 = lo >> 3, nac = ((hi + 7) >> 3) - ac0;
-            const long long n_rows = n_in * (a.V + a.has_ext);
-            const int RL = MX_THREADS / nac, rpc = RL * 4;
-            dsg_launch(ms_mix_bwd_e_kernel, dim3((unsigned)((n_rows + rpc - 1) / rpc)), dim3(MX_THREADS), 0, st, a, ac0, nac, rpc);
-            if (const char* e = dsg_launch_error()) return e;
-        }
+    if ((parts & 2) && nac > 0) {
+        const int nseg = (a.T_in + MX_TT - 1) / MX_TT;
+        const long long n_items = (long long)a.n_samples * nseg * (a.V + a.has_ext) * nacp;
+        dsg_launch(ms_mix_bwd_e_kernel, dim3((unsigned)((n_items + MX_THREADS - 1) / MX_THREADS)), dim3(MX_THREADS), 0, st, a, ac0, nac, nseg);
+        if (const char* e = dsg_launch_error()) return e;
     }
     *handled = true;
     return nullptr;

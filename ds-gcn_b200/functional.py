@@ -64,6 +64,41 @@ def _zeros64(n, dev):
     return torch.zeros(n, dtype=torch.float64, device=dev)
 
 
+class stat_arena:
+    """BatchNorm statistics accumulators (fp64 sums the kernels add into) for one forward + backward pass of a backbone, carved
+    from ONE pre-zeroed buffer: one memset per step instead of ~100 small fills.  Slices are handed out once and never reused
+    before the next `with stat_arena(dev)` (the next forward) zeroes the buffer again; when the arena is exhausted or absent
+    (units used stand-alone) a fresh torch.zeros is returned."""
+    _pool = {}            # device -> [buffer, next free element]
+    SIZE = 1 << 17        # fp64 elements (1 MB): a DS-GCN training step uses ~45k
+
+    def __init__(self, dev):
+        self.dev = dev
+
+    def __enter__(self):
+        ent = stat_arena._pool.get(self.dev)
+        if ent is None:
+            ent = [torch.zeros(stat_arena.SIZE, dtype=torch.float64, device=self.dev), 0]
+            stat_arena._pool[self.dev] = ent
+        else:
+            ent[0].zero_()
+            ent[1] = 0
+        return self
+
+    def __exit__(self, *exc):
+        return False          # stays active: the backward pass of this forward draws from the same buffer
+
+    @staticmethod
+    def take(rows, C, dev):
+        ent = stat_arena._pool.get(dev)
+        n = rows * ((C + 1) // 2 * 2)                       # 16-byte aligned rows
+        if ent is None or ent[1] + n > stat_arena.SIZE:
+            return torch.zeros(rows, C, dtype=torch.float64, device=dev)
+        o = ent[1]
+        ent[1] = o + n
+        return ent[0][o:o + n].view(rows, n // rows)[:, :C]
+
+
 def _empty32(n, dev):
     return torch.empty(n, dtype=torch.float32, device=dev)
 
@@ -130,7 +165,7 @@ class BNCoef:
         self.batch = {}                  # (lo, hi) -> this slice normalised with batch statistics
         self.a, self.b = _empty32(C, dev), _empty32(C, dev)
         self.mean, self.invstd = _empty32(C, dev), _empty32(C, dev)
-        self.stats = torch.zeros(2, C, dtype=torch.float64, device=dev) if training else None
+        self.stats = stat_arena.take(2, C, dev) if training else None
         self.jobs = []
 
     @property
@@ -176,7 +211,7 @@ class BNBack:
         C, dev = fwd.C, fwd.dev
         self.fwd = fwd
         self.ca, self.cb, self.cc = _empty32(C, dev), _empty32(C, dev), _empty32(C, dev)
-        self.stats = torch.zeros(2, C, dtype=torch.float64, device=dev)
+        self.stats = stat_arena.take(2, C, dev)
         self.jobs = []
 
     @property

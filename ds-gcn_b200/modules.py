@@ -589,7 +589,7 @@ class _Backbone(nn.Module):
             raise ValueError(f"expected [N, M, T, V, C], got {tuple(x.shape)}")
         ops.L.check_tensor(x)
         N, M, T, V, C = x.size()
-        with Fn.defer_bn_counters():
+        with Fn.defer_bn_counters(), Fn.stat_arena(x.device):
             if self.data_bn_type == 'VC':
                 h = _DataBNFn.apply(x, self.data_bn, self.data_bn.weight, self.data_bn.bias)
             elif self.data_bn_type == 'MVC':

@@ -298,3 +298,71 @@ def test_packed_parameters_give_identical_gradients_and_update(dev):
                 assert rel(p2[k], p1[k]) < (1e-5 if it == 0 else 1e-3), (it, k)
     finally:
         M.set_compute_dtype(torch.bfloat16)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_dgstgcn_coco_vs_oracle(dtype):
+    """BASELINE config 4: the COCO layout (V=17, 2-D HRNet keypoints: channels (x, y, score) with x, y in PIXEL units — the
+    K400-HRNet pipeline has no PreNormalize2D), clip_len 60.  The network input and data_bn stay fp32 (bf16 would
+    cost pixels of precision at 500-1000 px); eval features / pooled features and train-mode forward + gradients vs the oracle."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    dsgcn_b200._lib._testing_use_library(None)
+    dev = torch.device("cuda:0")
+    torch.manual_seed(3); np.random.seed(3)
+    cfg = {**NORTH_STAR, "graph_cfg": dict(layout="coco", mode="random", num_filter=3, init_off=.04, init_std=.02)}
+    m = M.DGSTGCN(**cfg)
+    sd = m.state_dict(); O.randomize_state(sd, 2)
+    # data_bn statistics in pixel units (what a trained checkpoint holds)
+    sd["data_bn.running_mean"] = torch.tensor([128.0, 128.0, 0.5]).repeat(17)
+    sd["data_bn.running_var"] = torch.tensor([74.0 ** 2, 74.0 ** 2, 0.083]).repeat(17)
+    m.load_state_dict(sd)
+    N, T, V = 3, 60, 17
+    x = torch.cat([torch.rand(N, 2, T, V, 2) * 256, torch.rand(N, 2, T, V, 1)], -1)
+    M.set_compute_dtype(dtype)
+    try:
+        m.eval()
+        ref = O.dgstgcn_forward(x, {k: v.clone() for k, v in m.state_dict().items()}, layout="coco", training=False)
+        m.to(dev)
+        with torch.no_grad():
+            y = m(x.to(dev))
+        assert y.shape == (N, 2, 256, 15, 17)
+        tol = 1e-4 if dtype == torch.float32 else 1e-2
+        assert rel(y, ref) < tol, f"coco eval rel-L2 {rel(y, ref):.3e}"
+        assert rel(y.float().mean((3, 4)).mean(1).cpu(), ref.mean((3, 4)).mean(1)) < tol
+        # train mode
+        m.train(); m.cpu()
+        sdt = {k: v.clone() for k, v in m.state_dict().items()}
+        pn = {k for k, _ in m.named_parameters()}
+        for k in pn:
+            sdt[k].requires_grad_()
+        ref = O.dgstgcn_forward(x, sdt, layout="coco", training=True)
+        gy = torch.randn(ref.shape, generator=torch.Generator().manual_seed(6))
+        ref.backward(gy)
+        m.to(dev)
+        y = m(x.to(dev))
+        lim, cos_lim = 1e-4, 0.9995
+        if dtype == torch.bfloat16:      # calibrated against PyTorch's own bf16 autocast of the oracle, as in test_dgstgcn_full_vs_oracle
+            sda = {k: v.detach().clone() for k, v in sdt.items()}
+            for k in pn:
+                sda[k].requires_grad_()
+            with torch.autocast("cpu", dtype=torch.bfloat16):
+                ya = O.dgstgcn_forward(x, sda, layout="coco", training=True)
+            lim = max(1.5e-2, 1.25 * rel(ya.float(), ref))
+            ya.float().backward(gy)
+            ka = [k for k in pn if sdt[k].grad is not None]
+            va = torch.cat([sda[k].grad.double().reshape(-1) for k in ka])
+            vr = torch.cat([sdt[k].grad.double().reshape(-1) for k in ka])
+            cos_lim = min(0.98, float(torch.dot(va, vr) / (va.norm() * vr.norm())) - 0.02)
+        assert rel(y, ref) < lim, f"coco train rel-L2 {rel(y, ref):.3e} (limit {lim:.3e})"
+        y.backward(gy.to(dev).to(y.dtype))
+        params = dict(m.named_parameters())
+        keys = [k for k in pn if sdt[k].grad is not None]
+        assert {k for k, p in params.items() if p.grad is None} == pn - set(keys)
+        mine = torch.cat([params[k].grad.detach().double().cpu().reshape(-1) for k in keys])
+        refv = torch.cat([sdt[k].grad.double().reshape(-1) for k in keys])
+        cos = float(torch.dot(mine, refv) / (mine.norm() * refv.norm()))
+        assert cos > cos_lim, f"coco gradient cosine {cos:.5f} (limit {cos_lim:.5f})"
+    finally:
+        M.set_compute_dtype(torch.bfloat16)
