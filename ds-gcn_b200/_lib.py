@@ -33,7 +33,8 @@ class ConvGemmArgs(C.Structure):
                 ("ext_in", c_int), ("contract_ext", c_int),
                 ("out", vp), ("ld_out", c_ll), ("add", vp), ("ld_add", c_ll), ("add2", vp), ("ld_add2", c_ll),
                 ("bcast", vp), ("bcast_scale", c_f), ("has_mask", c_int), ("mask", ActSrc),
-                ("stat_sum", vp), ("stat_sq", vp), ("partner", vp), ("ld_partner", c_ll), ("wpack", vp)]
+                ("stat_sum", vp), ("stat_sq", vp), ("partner", vp), ("ld_partner", c_ll), ("wpack", vp),
+                ("out_f32", c_int), ("pad2_", c_int)]
 
 
 class ConvWgradArgs(C.Structure):
@@ -54,7 +55,8 @@ class TopologyArgs(C.Structure):
     _fields_ = [("H", vp), ("ld_h", c_ll), ("n_samples", c_int), ("V", c_int), ("R", c_int),
                 ("node_type", vp), ("edge_type", vp), ("A", vp), ("alpha", vp), ("beta", vp),
                 ("We", vp), ("be", vp), ("adyn", vp), ("adyn_dtype", c_int), ("S", vp),
-                ("dadyn", vp), ("dH", vp), ("dA", vp), ("dalpha", vp), ("dbeta", vp), ("dWe", vp), ("dbe", vp)]
+                ("dadyn", vp), ("dH", vp), ("dA", vp), ("dalpha", vp), ("dbeta", vp), ("dWe", vp), ("dbe", vp),
+                ("dH_bf16", vp)]
 
 
 class GraphAggArgs(C.Structure):
@@ -113,6 +115,7 @@ EXPORTS = {
     "dsg_conv_wgrad": (c_int, [C.POINTER(ConvWgradArgs), vp]),
     "dsg_bn_finalize": (c_int, [C.POINTER(BnJob), c_int, vp]),
     "dsg_tmean": (c_int, [vp, c_int, c_ll, c_int, c_int, c_int, c_int, vp, vp]),
+    "dsg_tmean2": (c_int, [vp, c_int, c_ll, c_int, c_int, c_int, c_int, vp, vp, vp]),
     "dsg_topology_fwd": (c_int, [C.POINTER(TopologyArgs), vp]),
     "dsg_topology_bwd": (c_int, [C.POINTER(TopologyArgs), vp]),
     "dsg_graph_agg": (c_int, [C.POINTER(GraphAggArgs), vp]),

@@ -61,7 +61,7 @@ int dsg_conv_gemm(const dsg_conv_gemm_args* a, void* stream) {
     if (!a || !dtype_ok(a->dtype)) return fail("dsg_conv_gemm", "bad arguments");
     if (a->taps < 1 || a->t_div < 1 || a->Vin < 1 || a->K < 1) return fail("dsg_conv_gemm", "bad shape");
     if ((a->stat_sum == nullptr) != (a->stat_sq == nullptr)) return fail("dsg_conv_gemm", "stat_sum and stat_sq go together");
-    if (dsg::conv_gemm_skinny_ok(*a)) {               // N <= 8: a stream over the input rows, no GEMM tile
+    if (!a->out_f32 && dsg::conv_gemm_skinny_ok(*a)) {               // N <= 8: a stream over the input rows, no GEMM tile
         if (a->dtype == DSG_BF16) DSG_RET("dsg_conv_gemm", dsg::launch_conv_gemm_skinny<bf16>(*a, (dsg_stream_t)stream));
         DSG_RET("dsg_conv_gemm", dsg::launch_conv_gemm_skinny<float>(*a, (dsg_stream_t)stream));
     }
@@ -71,6 +71,7 @@ int dsg_conv_gemm(const dsg_conv_gemm_args* a, void* stream) {
         const char* e = dsg::tc4::launch_conv_gemm_tc4(*a, (dsg_stream_t)stream, &handled);                            // TMA-fed warp-specialised engine
         if (e) return fail("dsg_conv_gemm", e);
         if (handled) { ++g_counters[0]; return 0; }
+        if (a->out_f32) return fail("dsg_conv_gemm", "out_f32: shape not taken by the TMA-fed engine (needs K, N % 8 == 0, taps == 1, no addends / mask / statistics)");
         e = tc3_enabled() ? dsg::tc::launch_conv_gemm_tc3(*a, (dsg_stream_t)stream, &handled) : nullptr;               // persistent pipelined engine
         if (e) return fail("dsg_conv_gemm", e);
         if (handled) return 0;
@@ -82,6 +83,7 @@ int dsg_conv_gemm(const dsg_conv_gemm_args* a, void* stream) {
         if (handled) return 0;
     }
 #endif
+    if (a->out_f32) return fail("dsg_conv_gemm", "out_f32 needs bf16 sources and the tcgen05 engine");
     if (a->dtype == DSG_BF16) DSG_RET("dsg_conv_gemm", dsg::launch_conv_gemm<bf16>(*a, (dsg_stream_t)stream));
     DSG_RET("dsg_conv_gemm", dsg::launch_conv_gemm<float>(*a, (dsg_stream_t)stream));
 }
@@ -134,17 +136,21 @@ int dsg_bn_finalize(const dsg_bn_job* jobs, int njobs, void* stream) {
     return 0;
 }
 
-int dsg_tmean(const void* x, int dtype, long long ld, int n_samples, int T, int V, int C, float* xm, void* stream) {
+int dsg_tmean2(const void* x, int dtype, long long ld, int n_samples, int T, int V, int C, float* xm, void* xm_bf16, void* stream) {
     if (!dtype_ok(dtype) || T < 1) return fail("dsg_tmean", "bad arguments");
     if (n_samples <= 0) return 0;
+    bf16* xb = reinterpret_cast<bf16*>(xm_bf16);
     dim3 grid((V * C + 255) / 256, n_samples);
-    if (dtype == DSG_BF16 && C % 8 == 0 && ld % 8 == 0 && (uintptr_t)x % 16 == 0) {
-        dsg_launch(dsg::tmean_vec_kernel, dim3((V * (C / 8) + 127) / 128, n_samples), dim3(128), 0, (dsg_stream_t)stream, (const bf16*)x, ld, T, V, C, xm);
+    if (dtype == DSG_BF16 && C % 8 == 0 && ld % 8 == 0 && (uintptr_t)x % 16 == 0 && (uintptr_t)xm_bf16 % 16 == 0) {
+        dsg_launch(dsg::tmean_vec_kernel, dim3((V * (C / 8) + 127) / 128, n_samples), dim3(128), 0, (dsg_stream_t)stream, (const bf16*)x, ld, T, V, C, xm, xb);
         DSG_RET("dsg_tmean", dsg_launch_error());
     }
-    if (dtype == DSG_BF16) dsg_launch(dsg::tmean_kernel<bf16>, grid, dim3(256), 0, (dsg_stream_t)stream, (const bf16*)x, ld, T, V, C, xm);
-    else dsg_launch(dsg::tmean_kernel<float>, grid, dim3(256), 0, (dsg_stream_t)stream, (const float*)x, ld, T, V, C, xm);
+    if (dtype == DSG_BF16) dsg_launch(dsg::tmean_kernel<bf16>, grid, dim3(256), 0, (dsg_stream_t)stream, (const bf16*)x, ld, T, V, C, xm, xb);
+    else dsg_launch(dsg::tmean_kernel<float>, grid, dim3(256), 0, (dsg_stream_t)stream, (const float*)x, ld, T, V, C, xm, xb);
     DSG_RET("dsg_tmean", dsg_launch_error());
+}
+int dsg_tmean(const void* x, int dtype, long long ld, int n_samples, int T, int V, int C, float* xm, void* stream) {
+    return dsg_tmean2(x, dtype, ld, n_samples, T, V, C, xm, nullptr, stream);
 }
 
 int dsg_topology_fwd(const dsg_topology_args* a, void* stream) {

@@ -68,7 +68,7 @@ __global__ void bn_finalize_kernel(BnJobs jobs) {
 
 // ---------------------------------------------------------------------------------------------
 template <class T>
-__global__ void tmean_kernel(const T* x, long long ld, int T_, int V, int C, float* xm) {
+__global__ void tmean_kernel(const T* x, long long ld, int T_, int V, int C, float* xm, bf16* xm_bf) {
     const int n = blockIdx.y;
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;   // v*C + c
     if (idx >= V * C) return;
@@ -76,10 +76,11 @@ __global__ void tmean_kernel(const T* x, long long ld, int T_, int V, int C, flo
     float s = 0.f;
     for (int t = 0; t < T_; ++t) s += ldf<T>(x + (((long long)n * T_ + t) * V + v) * ld + c);
     xm[(long long)n * V * C + idx] = s / (float)T_;
+    if (xm_bf) xm_bf[(long long)n * V * C + idx] = __float2bfloat16(s / (float)T_);
 }
 
 // bf16 fast path: a thread owns (joint, 8 channels) and walks the frames with 4 independent 16-byte loads in flight
-__global__ void tmean_vec_kernel(const bf16* x, long long ld, int T_, int V, int C, float* xm) {
+__global__ void tmean_vec_kernel(const bf16* x, long long ld, int T_, int V, int C, float* xm, bf16* xm_bf) {
     const int n = blockIdx.y;
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;   // v*(C/8) + chunk
     const int nch = C >> 3;
@@ -112,7 +113,8 @@ __global__ void tmean_vec_kernel(const bf16* x, long long ld, int T_, int V, int
     float* dst = xm + (long long)n * V * C + v * C + ch * 8;
     const float inv = 1.f / (float)T_;
 #pragma unroll
-    for (int e = 0; e < 8; ++e) dst[e] = s[e] * inv;
+    for (int e = 0; e < 8; ++e) { s[e] *= inv; dst[e] = s[e]; }
+    if (xm_bf) *reinterpret_cast<uint4*>(xm_bf + (long long)n * V * C + v * C + ch * 8) = pack8(s);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -378,6 +378,15 @@ tc4_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
                         const int col = c16 + h * 8;
                         float* vv = v + h * 8;
                         tc::add8(vv, tl_bias + col);
+                        if (a.out_f32) {
+                            // unrounded fp32 rows straight from the registers (32 bytes per thread and chunk: whole sectors)
+                            if (row_ok && n0 + col < a.N) {
+                                float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(a.out) + gr * a.ld_out + n0 + col);
+                                dst[0] = make_float4(vv[0], vv[1], vv[2], vv[3]);
+                                dst[1] = make_float4(vv[4], vv[5], vv[6], vv[7]);
+                            }
+                            continue;
+                        }
                         if (!row_ok) {
 #pragma unroll
                             for (int e = 0; e < 8; ++e) vv[e] = 0.f;
@@ -498,7 +507,7 @@ tc4_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
             mbar_wait(&bars.out_ready[ob], (uint32_t)(useo & 1));
             tc_fence_after();
             const unsigned char* Ot = Osm + (size_t)ob * p.out_bytes;
-            for (int oa = 0; oa < n_oatoms; ++oa) {
+            for (int oa = 0; oa < (a.out_f32 ? 0 : n_oatoms); ++oa) {
                 const unsigned char* src = Ot + (size_t)oa * ATOM_BYTES;
                 if (p.mode == 0) tma_store_2d(&mapO, src, n0 + oa * ATOM_CH, tile * ATOM_ROWS);
                 else if (p.mode == 3) {
@@ -618,7 +627,10 @@ static const char* launch_conv_gemm_tc4(const dsg_conv_gemm_args& a, dsg_stream_
     if (a.K % 8 != 0 || a.N % 8 != 0 || a.N < 16 || a.T_in != a.T_out) return nullptr;
     if (a.ext_in && a.contract_ext) return nullptr;
     if (!a.wpack || (uintptr_t)a.wpack % 128 != 0) return nullptr;
-    if (!tma_ptr_ok(a.src.x1, a.src.ld1) || (a.src.x2 && !tma_ptr_ok(a.src.x2, a.src.ld2)) || !tma_ptr_ok(a.out, a.ld_out)) return nullptr;
+    if (!tma_ptr_ok(a.src.x1, a.src.ld1) || (a.src.x2 && !tma_ptr_ok(a.src.x2, a.src.ld2))) return nullptr;
+    if (a.out_f32 ? ((uintptr_t)a.out % 16 != 0 || a.ld_out % 4 != 0 || a.add || a.add2 || a.bcast || a.has_mask || a.partner || a.stat_sum)
+                  : !tma_ptr_ok(a.out, a.ld_out))
+        return nullptr;
     const bool fold = !a.src.relu;                        // affine / two-tensor BN-backward prologue folds into the weights
     if (!fold && a.src.x2) return nullptr;                // ReLU over two tensors: older engines
     auto al16 = [](const void* p, long long ld) { return p == nullptr || ((uintptr_t)p % 16 == 0 && ld % 8 == 0); };
@@ -637,13 +649,15 @@ static const char* launch_conv_gemm_tc4(const dsg_conv_gemm_args& a, dsg_stream_
         ok = make_map_2d(&mA0, a.src.x1, rows_in, a.K, a.src.ld1, ATOM_ROWS);
         mA1 = mA0;
         if (ok && p.natoms > p.natoms1) ok = make_map_2d(&mA1, a.src.x2, rows_in, a.K, a.src.ld2, ATOM_ROWS);
-        ok = ok && make_map_2d(&mO, a.out, p.rows_out, a.N, a.ld_out, ATOM_ROWS);
+        if (a.out_f32) mO = mA0;                               // never dereferenced: rows go out through plain stores
+        else ok = ok && make_map_2d(&mO, a.out, p.rows_out, a.N, a.ld_out, ATOM_ROWS);
     } else {
         const int rin = a.Vin, rout = a.Vin + a.ext_in - a.contract_ext;
         ok = make_map_3d(&mA0, a.src.x1, n_frames, rin, a.K, a.src.ld1, rin, 1);
         mA1 = mA0;
         if (ok && p.natoms > p.natoms1) ok = make_map_3d(&mA1, a.src.x2, n_frames, rin, a.K, a.src.ld2, rin, 1);
-        ok = ok && make_map_3d(&mO, a.out, n_frames, rout, a.N, a.ld_out, rout, 1);
+        if (a.out_f32) mO = mA0;
+        else ok = ok && make_map_3d(&mO, a.out, n_frames, rout, a.N, a.ld_out, rout, 1);
     }
     if (!ok) return nullptr;
     const unsigned gy = (unsigned)((a.N + p.Ntile - 1) / p.Ntile);

@@ -280,6 +280,7 @@ __global__ void __launch_bounds__(TP_BWD_THREADS) topology_bwd_kernel(dsg_topolo
                 val = (ty == a.node_type[v]) ? dx1[(2 * R + c) * V + v] + dx2[(2 * R + c) * V + v] : 0.f;
             }
             dh[(long long)v * a.ld_h + col] = val;
+            if (a.dH_bf16) reinterpret_cast<bf16*>(a.dH_bf16)[((long long)n * V + v) * a.ld_h + col] = __float2bfloat16(val);
         }
     }
     __syncthreads();

@@ -259,12 +259,20 @@ def dgphgcn1_forward(m, x, n, T, V, save):
     nt, et = m._tables(dev)
 
     # ---- topology branch: temporal mean -> 9R features per joint -> per-sample adjacency
-    xm = ops.tmean(x, n, T, V)                                                  # [n,V,Cin] fp32
+    # (bf16 mode: the three feature convolutions run on the tensor core from a bf16 copy of the temporal mean, with the
+    #  accumulator stored UNROUNDED in fp32 — H feeds differences, tanh and softmax)
+    tc_topo = dt == torch.bfloat16 and Cin % 8 == 0 and R % 8 == 0 and ops.L.is_device_build()
     Wt = cat_params(m, "Wt", [m.conv1.weight, m.conv2.weight, m.conv1_se.weight], (9 * R, Cin))
     bt = cat_params(m, "bt", [m.conv1.bias, m.conv2.bias, m.conv1_se.bias], (9 * R,))
-    xm2 = xm.view(n * V, Cin)
     H = torch.empty(n * V, 9 * R, dtype=torch.float32, device=dev)
-    ops.conv_gemm(xm2, Wt, 9 * R, H, n_samples=n, T_in=1, T_out=1, Vin=V, bias=bt)
+    if tc_topo:
+        xm, xmb = ops.tmean(x, n, T, V, with_bf16=True)                         # [n,V,Cin] fp32 + bf16
+        xm2 = xmb.view(n * V, Cin)
+        ops.conv_gemm(xm2, Wt, 9 * R, H, n_samples=n, T_in=1, T_out=1, Vin=V, bias=bt, out_f32=True)
+    else:
+        xm = ops.tmean(x, n, T, V)                                              # [n,V,Cin] fp32
+        xm2 = xm.view(n * V, Cin)
+        ops.conv_gemm(xm2, Wt, 9 * R, H, n_samples=n, T_in=1, T_out=1, Vin=V, bias=bt)
     adyn = torch.empty(n, V, V, KC, dtype=dt, device=dev)
     S = torch.empty(n, 3, V, V, dtype=torch.float32, device=dev)
     We, be = m.edge_linears.weight.view(15 * R, R), m.edge_linears.bias
@@ -311,9 +319,24 @@ def dgphgcn1_forward(m, x, n, T, V, save):
     return out
 
 
-def dgphgcn1_backward(m, sv, dout, grads, extra_add=None):
+def dgphgcn1_backward_tail(m, sv):
+    """What the producer of `dout` needs to apply this unit's output ReLU mask and accumulate the BN-backward sums of `bn` in its
+    own epilogue (mstcn_backward(tail=...)): destination buffer, mask tensor, partner, statistics.  Pass the result back as
+    dgphgcn1_backward(..., pre=...)."""
+    n, T, V = sv["dims"]
+    x, out, Z, c_z = sv["x"], sv["out"], sv["Z"], sv["c_z"]
+    rows = n * T * V
+    Cout, KC = m.out_channels, 3 * m.mid_channels
+    E = torch.empty(rows, KC + Cout, dtype=x.dtype, device=x.device) if m.has_down else None
+    E4 = E[:, KC:] if m.has_down else torch.empty(rows, Cout, dtype=x.dtype, device=x.device)
+    b_z = BNBack(c_z)
+    return dict(out=E4, mask=out, partner=Z, stat_sum=b_z.ssum, stat_sq=b_z.ssq, E=E, b_z=b_z)
+
+
+def dgphgcn1_backward(m, sv, dout, grads, extra_add=None, pre=None):
     """dout: gradient w.r.t. the unit output [rows, C_out].  Fills `grads` {param: grad}; returns dx.
-    `extra_add` (optional, [rows, C_in]) is added to dx inside the last kernel's epilogue."""
+    `extra_add` (optional, [rows, C_in]) is added to dx inside the last kernel's epilogue.
+    `pre`: the dict of dgphgcn1_backward_tail when the producer of dout already wrote e4 = dout * [out > 0] and the sums."""
     n, T, V = sv["dims"]
     x, PD, Y, Z, out, adyn = sv["x"], sv["PD"], sv["Y"], sv["Z"], sv["out"], sv["adyn"]
     c_pd, c_z = sv["c_pd"], sv["c_z"]
@@ -326,11 +349,15 @@ def dgphgcn1_backward(m, sv, dout, grads, extra_add=None):
     nt, et = m._tables(dev)
 
     # ---- e4 = dout * [out > 0], BatchNorm-backward sums for `bn` (and `down.1`)
-    E = torch.empty(rows, Npd, dtype=dt, device=dev) if has_down else None
-    E4 = E[:, KC:] if has_down else torch.empty(rows, Cout, dtype=dt, device=dev)
+    b_pd = BNBack(c_pd)
+    if pre is not None:
+        E, E4, b_z = pre["E"], pre["out"], pre["b_z"]
+    else:
+        E = torch.empty(rows, Npd, dtype=dt, device=dev) if has_down else None
+        E4 = E[:, KC:] if has_down else torch.empty(rows, Cout, dtype=dt, device=dev)
+        b_z = BNBack(c_z)
+        ops.pointwise(dout, E4, mask=out, stat_sum=b_z.ssum, stat_sq=b_z.ssq, partner=Z)
     E5 = E[:, :KC] if has_down else torch.empty(rows, KC, dtype=dt, device=dev)
-    b_z, b_pd = BNBack(c_z), BNBack(c_pd)
-    ops.pointwise(dout, E4, mask=out, stat_sum=b_z.ssum, stat_sq=b_z.ssq, partner=Z)
     b_z.add_bn(m.bn, 0, Cout, rows, grads)
     if has_down:
         ops.pointwise(E4, None, stat_sum=b_pd.ssum[KC:], stat_sq=b_pd.ssq[KC:], partner=PD[:, KC:])
@@ -368,13 +395,19 @@ def dgphgcn1_backward(m, sv, dout, grads, extra_add=None):
     # ---- topology backward
     H, S, Wt, xm2 = sv["H"], sv["S"], sv["Wt"], sv["xm2"]
     dH = torch.empty_like(H)
+    tc_topo = xm2.dtype == torch.bfloat16
+    dHb = torch.empty(H.shape, dtype=torch.bfloat16, device=dev) if tc_topo else None
     ops.topology_bwd(H, n, V, R, nt, et, m.A, m.alpha, m.beta, m.edge_linears.weight.view(15 * R, R), m.edge_linears.bias, S,
-                     dadyn, dH, dA, dal, dbe, dWe, dbe_l)
+                     dadyn, dH, dA, dal, dbe, dWe, dbe_l, dH_bf16=dHb)
     grads[m.A], grads[m.alpha], grads[m.beta] = dA, dal, dbe
     grads[m.edge_linears.weight], grads[m.edge_linears.bias] = dWe, dbe_l
-    ops.conv_wgrad(xm2, dH, dWt, db=dbt, n_samples=n, T_in=1, T_out=1, Vin=V)
     dxm = torch.empty(n * V, Cin, dtype=torch.float32, device=dev)
-    ops.conv_gemm(dH, Wt, Cin, dxm, n_samples=n, T_in=1, T_out=1, Vin=V, ws=(1, Cin, 0))
+    if tc_topo:
+        ops.conv_wgrad(xm2, dHb, dWt, db=dbt, n_samples=n, T_in=1, T_out=1, Vin=V)
+        ops.conv_gemm(dHb, Wt, Cin, dxm, n_samples=n, T_in=1, T_out=1, Vin=V, ws=(1, Cin, 0), out_f32=True)
+    else:
+        ops.conv_wgrad(xm2, dH, dWt, db=dbt, n_samples=n, T_in=1, T_out=1, Vin=V)
+        ops.conv_gemm(dH, Wt, Cin, dxm, n_samples=n, T_in=1, T_out=1, Vin=V, ws=(1, Cin, 0))
 
     # ---- dx = [dP_raw | dD_raw] @ [Wpre; Wdown] (+ e4 when the residual is the identity) + dxm/T (+ extra)
     Wpd = sv["Wpd"]
@@ -550,8 +583,11 @@ def mstcn_forward(m, g, n, T, V, save, res=None, final_relu=False):
     return out, T_out
 
 
-def mstcn_backward(m, sv, dout, grads):
-    """Returns (dg, E) where E is the gradient w.r.t. the pre-ReLU sum (what flows into the residual)."""
+def mstcn_backward(m, sv, dout, grads, tail=None):
+    """Returns (dg, E) where E is the gradient w.r.t. the pre-ReLU sum (what flows into the residual).
+    `tail` (optional dict: out, mask, partner, stat_sum, stat_sq): the consumer of dg is the spatial unit of the same block, whose
+    backward starts with dg * [g > 0] and the BatchNorm-backward sums of its `bn`; with `tail` the last GEMM here applies that mask
+    and accumulates those sums in its epilogue and writes straight into the consumer's buffer (no separate pass over dg)."""
     n, T, V = sv["dims"]
     g, B, feat, U, out = sv["g"], sv["B"], sv["feat"], sv["U"], sv["out"]
     c_b, c_t, c_u = sv["c_b"], sv["c_t"], sv["c_u"]
@@ -650,8 +686,13 @@ def mstcn_backward(m, sv, dout, grads):
     dB = b_b.dy(E3, B)
 
     # ---- branch 1x1 convolutions backward (the joint-mean column folds back into the V joints)
-    dg = torch.empty(n * T * V, Cin, dtype=dt, device=dev)
-    ops.conv_gemm(dB, sv["Wbr"], Cin, dg, n_samples=n, T_in=T, T_out=T, Vin=Vp, ws=(1, Cin, 0), contract_ext=has_ext)
+    if tail is not None:
+        dg = tail["out"]
+        ops.conv_gemm(dB, sv["Wbr"], Cin, dg, n_samples=n, T_in=T, T_out=T, Vin=Vp, ws=(1, Cin, 0), contract_ext=has_ext,
+                      mask=tail["mask"], partner=tail["partner"], stat_sum=tail["stat_sum"], stat_sq=tail["stat_sq"])
+    else:
+        dg = torch.empty(n * T * V, Cin, dtype=dt, device=dev)
+        ops.conv_gemm(dB, sv["Wbr"], Cin, dg, n_samples=n, T_in=T, T_out=T, Vin=Vp, ws=(1, Cin, 0), contract_ext=has_ext)
     ops.conv_wgrad(g, dB, dWbr, db=dbbr, n_samples=n, T_in=T, T_out=T, Vin=V, ext_in=has_ext)
     return dg, E
 

@@ -260,8 +260,11 @@ class dgphgcn1(nn.Module):
     def _fwd(self, x, n, t, v, save):
         return Fn.dgphgcn1_forward(self, x, n, t, v, save), t
 
-    def _bwd(self, save, dout, grads, extra_add=None):
-        return Fn.dgphgcn1_backward(self, save, dout, grads, extra_add)
+    def _bwd(self, save, dout, grads, extra_add=None, pre=None):
+        return Fn.dgphgcn1_backward(self, save, dout, grads, extra_add, pre=pre)
+
+    def _bwd_tail(self, save):
+        return Fn.dgphgcn1_backward_tail(self, save)
 
     def forward(self, x, A=None):     # A is ignored, as in the reference (gcn.py:2222)
         _check_input(x)
@@ -356,8 +359,8 @@ class mstcn(nn.Module):
     def _fwd(self, x, n, t, v, save, res=None, final_relu=False):
         return Fn.mstcn_forward(self, x, n, t, v, save, res, final_relu)
 
-    def _bwd(self, save, dout, grads):
-        return Fn.mstcn_backward(self, save, dout, grads)
+    def _bwd(self, save, dout, grads, tail=None):
+        return Fn.mstcn_backward(self, save, dout, grads, tail=tail)
 
     def forward(self, x):
         _check_input(x)
@@ -412,12 +415,20 @@ class _STBlock(nn.Module):
         return out, t_out
 
     def _bwd(self, save, dout, grads):
-        dg, E = self.tcn._bwd(save["tcn"], dout, grads)
+        # the spatial unit's output mask / BN-backward sums ride in the epilogue of the temporal unit's last backward GEMM
+        pre = None
+        if isinstance(self.gcn, dgphgcn1) and isinstance(self.tcn, mstcn):
+            pre = self.gcn._bwd_tail(save["gcn"])
+            dg, E = self.tcn._bwd(save["tcn"], dout, grads, tail=pre)
+        else:
+            dg, E = self.tcn._bwd(save["tcn"], dout, grads)
         extra = None
         if self.res_kind == 'identity':
             extra = E
         elif self.res_kind == 'conv':
             extra = Fn.unit_tcn_raw_backward(self.residual, save["res"], E, grads)
+        if pre is not None:
+            return self.gcn._bwd(save["gcn"], dg, grads, extra_add=extra, pre=pre)
         return self.gcn._bwd(save["gcn"], dg, grads, extra_add=extra)
 
     def forward(self, x, A=None):

@@ -74,9 +74,9 @@ def _f32(t):
 
 def conv_gemm(src, W, N, out, *, n_samples, T_in, T_out, Vin, ws=None, bias=None, taps=1, tap_step=0, tap_off=0,
               t_mul=1, t_div=1, ext_in=False, contract_ext=False, add=None, add2=None, bcast=None, bcast_scale=1.0,
-              mask=None, stat_sum=None, stat_sq=None, partner=None):
+              mask=None, stat_sum=None, stat_sq=None, partner=None, out_f32=False):
     """dsg_conv_gemm.  W fp32 with strides ws=(ws_n, ws_k, ws_tap); default = PyTorch conv weight
-    [N, K, taps, 1] (or [N, K])."""
+    [N, K, taps, 1] (or [N, K]).  out_f32: bf16 sources, fp32 `out` (unrounded accumulator; tcgen05 engine only)."""
     src = as_act(src)
     a = L.ConvGemmArgs()
     a.src = src.struct()
@@ -91,7 +91,12 @@ def conv_gemm(src, W, N, out, *, n_samples, T_in, T_out, Vin, ws=None, bias=None
     a.taps, a.tap_step, a.tap_off, a.t_mul, a.t_div = taps, tap_step, tap_off, t_mul, t_div
     a.n_samples, a.T_in, a.T_out, a.Vin = n_samples, T_in, T_out, Vin
     a.ext_in, a.contract_ext = int(ext_in), int(contract_ext)
-    assert out.dtype == src.dtype and out.shape[-1] == N
+    assert out.shape[-1] == N
+    if out_f32:
+        assert src.dtype == torch.bfloat16 and out.dtype == torch.float32
+        a.out_f32 = 1
+    else:
+        assert out.dtype == src.dtype
     a.out, a.ld_out = L.ptr(out), _ld(out)
     if add is not None:
         assert add.dtype == src.dtype
@@ -178,10 +183,14 @@ def bn_finalize(jobs):
     L.call("dsg_bn_finalize", arr, len(jobs), L.stream())
 
 
-def tmean(x, n_samples, T, V):
-    """x [n*T*V, C] -> xm [n, V, C] fp32"""
+def tmean(x, n_samples, T, V, with_bf16=False):
+    """x [n*T*V, C] -> xm [n, V, C] fp32 (and, with_bf16, a bf16 copy: operand of the tensor-core topology GEMMs)"""
     Cn = x.shape[-1]
     xm = torch.empty((n_samples, V, Cn), dtype=torch.float32, device=x.device)
+    if with_bf16:
+        xb = torch.empty((n_samples, V, Cn), dtype=torch.bfloat16, device=x.device)
+        L.call("dsg_tmean2", L.ptr(x), L.dt(x), _ld(x), n_samples, T, V, Cn, L.ptr(xm), L.ptr(xb), L.stream())
+        return xm, xb
     L.call("dsg_tmean", L.ptr(x), L.dt(x), _ld(x), n_samples, T, V, Cn, L.ptr(xm), L.stream())
     return xm
 
@@ -204,10 +213,13 @@ def topology_fwd(H, n, V, R, node_type, edge_type, A, alpha, beta, We, be, adyn,
     L.call("dsg_topology_fwd", C.byref(a), L.stream())
 
 
-def topology_bwd(H, n, V, R, node_type, edge_type, A, alpha, beta, We, be, S, dadyn, dH, dA, dalpha, dbeta, dWe, dbe):
+def topology_bwd(H, n, V, R, node_type, edge_type, A, alpha, beta, We, be, S, dadyn, dH, dA, dalpha, dbeta, dWe, dbe, dH_bf16=None):
     a = topology_args(H, n, V, R, node_type, edge_type, A, alpha, beta, We, be, S)
     assert dadyn.dtype == torch.float32 and dH.dtype == torch.float32 and _ld(dH) == _ld(H)
     a.dadyn, a.dH = L.ptr(dadyn), L.ptr(dH)
+    if dH_bf16 is not None:
+        assert dH_bf16.dtype == torch.bfloat16 and dH_bf16.is_contiguous() and dH_bf16.shape == dH.shape and dH.is_contiguous()
+        a.dH_bf16 = L.ptr(dH_bf16)
     a.dA, a.dalpha, a.dbeta, a.dWe, a.dbe = L.ptr(_f32(dA)), L.ptr(_f32(dalpha)), L.ptr(_f32(dbeta)), L.ptr(_f32(dWe)), L.ptr(_f32(dbe))
     L.call("dsg_topology_bwd", C.byref(a), L.stream())
 

@@ -92,6 +92,9 @@ typedef struct dsg_conv_gemm_args {
     void* wpack;          /* optional caller-owned workspace of dsg_conv_gemm_wpack_bytes(K, N) bytes (256-byte aligned): the
                              call first rewrites it with bf16 UMMA-ready weight tiles, which every CTA of the tcgen05 engine
                              then pulls with one bulk copy instead of converting fp32 weights itself; NULL = convert in-kernel */
+    int out_f32;          /* 1 (bf16 sources only, no addends / mask / statistics): `out` is fp32 — the accumulator is stored
+                             unrounded (the topology-feature convolutions conv1/conv2/conv1_se, gcn.py:2248-2259, feed tanh / softmax) */
+    int pad2_;
 } dsg_conv_gemm_args;
 int dsg_conv_gemm(const dsg_conv_gemm_args* a, void* stream);
 long long dsg_conv_gemm_wpack_bytes(int K, int N);
@@ -149,6 +152,8 @@ int dsg_bn_finalize(const dsg_bn_job* jobs, int njobs, void* stream);
 /* ---- dsg_tmean ------------------------------------------------------------------------------
  * xm[n, v, c] = mean_t x[n, t, v, c]  (fp32 out).  gcn.py:2246 `tmp_x.mean(dim=-2)`. */
 int dsg_tmean(const void* x, int dtype, long long ld, int n_samples, int T, int V, int C, float* xm, void* stream);
+/* the same with a second, bf16 copy of the result (operand of the tensor-core topology-feature GEMM); xm_bf16 may be NULL */
+int dsg_tmean2(const void* x, int dtype, long long ld, int n_samples, int T, int V, int C, float* xm, void* xm_bf16, void* stream);
 
 /* ---- dsg_topology_fwd / dsg_topology_bwd ----------------------------------------------------
  * The per-sample dynamic semantic adjacency of dgphgcn1 (gcn.py:2239-2337, north-star flags).
@@ -180,6 +185,7 @@ typedef struct dsg_topology_args {
     float* dbeta;
     float* dWe;
     float* dbe;
+    void* dH_bf16;            /* optional bf16 copy of dH (same pitch): operand of the tensor-core GEMMs that consume it */
 } dsg_topology_args;
 int dsg_topology_fwd(const dsg_topology_args* a, void* stream);
 int dsg_topology_bwd(const dsg_topology_args* a, void* stream);
