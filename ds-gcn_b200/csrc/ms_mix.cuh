@@ -293,45 +293,58 @@ __global__ void __launch_bounds__(MX_THREADS, 2) ms_mix_bwd_e_kernel(dsg_ms_comb
             }
             const uint4 nold = (rmw && more) ? *reinterpret_cast<const uint4*>(Ep + (t + 1) * estep) : make_uint4(0u, 0u, 0u, 0u);
             // ---- this frame
-            const uint32_t* rbw[5] = {&rb[0].x, &rb[1].x, &rb[2].x, &rb[3].x, &rb[4].x};
-            const uint32_t* dqw[3] = {&dq[0].x, &dq[1].x, &dq[2].x};
-            const uint32_t* oldw = &old.x;
-            uint32_t outw[4];
+            uint4 pk;
             float bsum[8];
+            if (k.mx == 0u) {
+                // pass-only chunk (and conv / foreign channels kept): e = dO of the window that maps onto t, a word-wise select
+                const uint4 d1 = (din >> 1 & 1u) ? dq[1] : make_uint4(0u, 0u, 0u, 0u);
+                const uint32_t* dw_ = &d1.x;
+                const uint32_t* ow_ = &old.x;
+                uint32_t o4[4];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-                const int wd = e >> 1;
-                const bool hi16 = e & 1;
-                auto f16 = [&](uint32_t u) { return __uint_as_float(hi16 ? (u & 0xffff0000u) : (u << 16)); };
-                float ev = f16(oldw[wd]);
-                const float braw = f16(rbw[2][wd]);
-                if (k.pass >> e & 1u) ev = (din >> 1 & 1u) ? f16(dqw[1][wd]) : 0.f;
-                else if (k.mx >> e & 1u) {
-                    float h[5];
-#pragma unroll
-                    for (int i = 0; i < 5; ++i) h[i] = (rin >> i & 1u) ? fmaxf(fmaf(f16(rbw[i][wd]), ka[e], kb[e]), 0.f) : -1.f;
-                    ev = 0.f;
-#pragma unroll
-                    for (int w = 0; w < 3; ++w) {
-                        if (!(din >> w & 1u)) continue;
-                        const int dt = w - 1;
-                        // window t' covers frames t-dt-1 .. t-dt+1 = h[1-dt .. 3-dt]; first maximum wins (ATen max_pool2d)
-                        float m = -3.0e38f;
-                        int am = -2;
-#pragma unroll
-                        for (int d2 = -1; d2 <= 1; ++d2) {
-                            const float hv = h[2 - dt + d2];
-                            if (hv >= 0.f && hv > m) { m = hv; am = d2; }
-                        }
-                        if (am == dt && h[2] > 0.f) ev += f16(dqw[w][wd]);
-                    }
+                for (int wd = 0; wd < 4; ++wd) {
+                    const uint32_t mlo = (k.pass >> (2 * wd) & 1u) ? 0x0000ffffu : 0u, mhi = (k.pass >> (2 * wd + 1) & 1u) ? 0xffff0000u : 0u;
+                    const uint32_t m = mlo | mhi;
+                    o4[wd] = (dw_[wd] & m) | (ow_[wd] & ~m);
                 }
-                bsum[e] = braw;
-                // round to bf16 exactly as pack8 does, two elements per word
-                if (!hi16) outw[wd] = __float_as_uint(ev);
-                else outw[wd] = dsg_pack_bf16x2(__uint_as_float(outw[wd]), ev);
+                pk = make_uint4(o4[0], o4[1], o4[2], o4[3]);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) bsum[e] = 0.f;
+            } else {
+                const uint32_t* rbw[5] = {&rb[0].x, &rb[1].x, &rb[2].x, &rb[3].x, &rb[4].x};
+                const uint32_t* dqw[3] = {&dq[0].x, &dq[1].x, &dq[2].x};
+                const uint32_t* oldw = &old.x;
+                uint32_t outw[4];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const int wd = e >> 1;
+                    const bool hi16 = e & 1;
+                    auto f16 = [&](uint32_t u) { return __uint_as_float(hi16 ? (u & 0xffff0000u) : (u << 16)); };
+                    float ev = f16(oldw[wd]);
+                    const float braw = f16(rbw[2][wd]);
+                    if (k.pass >> e & 1u) ev = (din >> 1 & 1u) ? f16(dqw[1][wd]) : 0.f;
+                    else if (k.mx >> e & 1u) {
+                        // h[i] = relu(bn(B)) at frame t-2+i, -1 outside the sample.  The gradient of window t' (= t - dt) reaches t iff t
+                        // is that window's FIRST maximum (ATen max_pool2d): strictly above the earlier frames, not below the later ones
+                        float h[5];
+#pragma unroll
+                        for (int i = 0; i < 5; ++i) h[i] = (rin >> i & 1u) ? fmaxf(fmaf(f16(rbw[i][wd]), ka[e], kb[e]), 0.f) : -1.f;
+                        const bool pos = h[2] > 0.f;
+                        const bool w_m1 = pos && h[2] >= h[3] && h[2] >= h[4];      // dt = -1: window frames t, t+1, t+2
+                        const bool w_0 = pos && h[2] > h[1] && h[2] >= h[3];        // dt =  0: t-1, t, t+1
+                        const bool w_p1 = pos && h[2] > h[0] && h[2] > h[1];        // dt = +1: t-2, t-1, t
+                        ev = 0.f;
+                        if (w_m1 && (din & 1u)) ev += f16(dqw[0][wd]);
+                        if (w_0 && (din >> 1 & 1u)) ev += f16(dqw[1][wd]);
+                        if (w_p1 && (din >> 2 & 1u)) ev += f16(dqw[2][wd]);
+                    }
+                    bsum[e] = braw;
+                    // round to bf16 exactly as pack8 does, two elements per word
+                    if (!hi16) outw[wd] = __float_as_uint(ev);
+                    else outw[wd] = dsg_pack_bf16x2(__uint_as_float(outw[wd]), ev);
+                }
+                pk = make_uint4(outw[0], outw[1], outw[2], outw[3]);
             }
-            const uint4 pk = make_uint4(outw[0], outw[1], outw[2], outw[3]);
             *reinterpret_cast<uint4*>(Ep + t * estep) = pk;
             if (a.e_sum && k.mx) {
                 float x[8];
