@@ -34,7 +34,7 @@ class ConvGemmArgs(C.Structure):
                 ("out", vp), ("ld_out", c_ll), ("add", vp), ("ld_add", c_ll), ("add2", vp), ("ld_add2", c_ll),
                 ("bcast", vp), ("bcast_scale", c_f), ("has_mask", c_int), ("mask", ActSrc),
                 ("stat_sum", vp), ("stat_sq", vp), ("partner", vp), ("ld_partner", c_ll), ("wpack", vp),
-                ("out_f32", c_int), ("pad2_", c_int)]
+                ("out_f32", c_int), ("pad2_", c_int), ("adyn", vp), ("y_out", vp), ("ld_y", c_ll)]
 
 
 class ConvWgradArgs(C.Structure):

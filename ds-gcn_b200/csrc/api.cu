@@ -61,7 +61,7 @@ int dsg_conv_gemm(const dsg_conv_gemm_args* a, void* stream) {
     if (!a || !dtype_ok(a->dtype)) return fail("dsg_conv_gemm", "bad arguments");
     if (a->taps < 1 || a->t_div < 1 || a->Vin < 1 || a->K < 1) return fail("dsg_conv_gemm", "bad shape");
     if ((a->stat_sum == nullptr) != (a->stat_sq == nullptr)) return fail("dsg_conv_gemm", "stat_sum and stat_sq go together");
-    if (!a->out_f32 && dsg::conv_gemm_skinny_ok(*a)) {               // N <= 8: a stream over the input rows, no GEMM tile
+    if (!a->out_f32 && !a->adyn && dsg::conv_gemm_skinny_ok(*a)) {               // N <= 8: a stream over the input rows, no GEMM tile
         if (a->dtype == DSG_BF16) DSG_RET("dsg_conv_gemm", dsg::launch_conv_gemm_skinny<bf16>(*a, (dsg_stream_t)stream));
         DSG_RET("dsg_conv_gemm", dsg::launch_conv_gemm_skinny<float>(*a, (dsg_stream_t)stream));
     }
@@ -70,7 +70,8 @@ int dsg_conv_gemm(const dsg_conv_gemm_args* a, void* stream) {
         bool handled = false;
         const char* e = dsg::tc4::launch_conv_gemm_tc4(*a, (dsg_stream_t)stream, &handled);                            // TMA-fed warp-specialised engine
         if (e) return fail("dsg_conv_gemm", e);
-        if (handled) { ++g_counters[0]; return 0; }
+        if (handled) { ++g_counters[a->adyn ? 2 : 0]; return 0; }
+        if (a->adyn) return fail("dsg_conv_gemm", "fused adjacency contraction: shape not taken (bf16, K <= 64, N <= 128, taps == 1, one source tensor)");
         if (a->out_f32) return fail("dsg_conv_gemm", "out_f32: shape not taken by the TMA-fed engine (needs K, N % 8 == 0, taps == 1, no addends / mask / statistics)");
         e = tc3_enabled() ? dsg::tc::launch_conv_gemm_tc3(*a, (dsg_stream_t)stream, &handled) : nullptr;               // persistent pipelined engine
         if (e) return fail("dsg_conv_gemm", e);
@@ -84,6 +85,7 @@ int dsg_conv_gemm(const dsg_conv_gemm_args* a, void* stream) {
     }
 #endif
     if (a->out_f32) return fail("dsg_conv_gemm", "out_f32 needs bf16 sources and the tcgen05 engine");
+    if (a->adyn) return fail("dsg_conv_gemm", "the fused adjacency contraction needs bf16 sources and the tcgen05 engine");
     if (a->dtype == DSG_BF16) DSG_RET("dsg_conv_gemm", dsg::launch_conv_gemm<bf16>(*a, (dsg_stream_t)stream));
     DSG_RET("dsg_conv_gemm", dsg::launch_conv_gemm<float>(*a, (dsg_stream_t)stream));
 }

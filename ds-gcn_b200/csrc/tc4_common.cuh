@@ -122,6 +122,18 @@ DSG_D void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;"
 DSG_D void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 DSG_D void named_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 
+// Waiting with back-off: in the fused-contraction mode four transform warps do long CUDA-core work while ten other warps of the CTA
+// wait on mbarriers; a bare try_wait loop re-issues every ~10 ns and (ncu, profiles/r02_ncu_full_tc4_fused_contraction.json) took two
+// thirds of the SM's issue slots away from the working warps.  Sleeping between polls gives the slots back.
+DSG_D void mbar_wait_backoff(uint64_t* bar, uint32_t parity, bool backoff) {
+    if (!backoff) { mbar_wait(bar, parity); return; }
+    uint32_t spins = 0;
+    while (!tc::mbar_try_wait(bar, parity)) {
+        __nanosleep(256);
+        if (++spins > (1u << 24)) __trap();
+    }
+}
+
 // ---- device: UMMA descriptors over SWIZZLE_128B atoms ---------------------------------------------------------------
 // K-major (reduction over the 64 channels of the atom): rows 128 B apart, 8-row groups 1024 B apart
 DSG_D uint64_t desc_k_sw128(uint32_t saddr) {

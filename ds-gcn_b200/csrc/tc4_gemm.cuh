@@ -58,6 +58,13 @@ struct G4Plan {
     //      map: frames outside the sample are zero-filled = the convolution's zero padding), multiplied into the branch's
     //      column window of the accumulator.  Per column tile y: t_n[y] atoms.
     int tps, qs, qp, Tq, Tdst;   // tiles per sample; frame stride / parity of the destination plane; its frames; T of the destination
+    // ---- mode 4: the adjacency contraction fused in front of the `post` 1x1 convolution (gcn.py:2350-2363).  Tiles are F frames of
+    //      one sample (as mode 3), walked in CONSECUTIVE order by a CTA so the sample's adjacency slice adyn[n] stays in shared
+    //      memory; a stage is two atoms: the raw `pre` tile the TMA unit writes and the contracted tile the tensor core reads.
+    int tpc;                     // tiles per CTA (consecutive)
+    unsigned off_adj, adj_bytes; // shared-memory slice [V*V][K] bf16
+    int store_y;                 // also write the contracted tile to HBM (training: operand of the weight gradient)
+    int cvar;                    // (V, K) variant of the contraction code: {25,17,18} x {24,48}
     int t_n[2];
     short t_map[2][G4_MAX_ATOMS], t_tsh[2][G4_MAX_ATOMS], t_ks[2][G4_MAX_ATOMS], t_ncol[2][G4_MAX_ATOMS], t_nw[2][G4_MAX_ATOMS];
     int t_c0[2][G4_MAX_ATOMS];
@@ -104,6 +111,36 @@ __global__ void __launch_bounds__(256) tc4_wpack_kernel(const float* W, long lon
     }
 }
 
+// one (frame, channel) column of the fused adjacency contraction: VV source joints in registers; VV and KK (channels of the
+// adjacency slice) are compile-time, so every shared-memory operand address is base + immediate — the inner loop is load, bf16
+// unpack, FMA and nothing else (the first version spent three IMADs per FMA on addresses: cuobjdump, 1549 IMAD vs 495 FFMA)
+template <int VV, int KK, int J>
+DSG_D void xf_contract_group(const float* pv, const bf16* aw, unsigned char* ycol, int row, int chunk) {
+    float acc[J];
+#pragma unroll
+    for (int j = 0; j < J; ++j) acc[j] = 0.f;
+#pragma unroll
+    for (int u = 0; u < VV; ++u) {
+#pragma unroll
+        for (int j = 0; j < J; ++j) acc[j] = fmaf(pv[u], __bfloat162float(aw[(u * VV + j) * KK]), acc[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < J; ++j) *reinterpret_cast<bf16*>(ycol + atom_off(row + j, chunk)) = __float2bfloat16(acc[j]);
+}
+template <int VV, int KK>
+DSG_D void xf_contract_col(const unsigned char* rcol, unsigned char* ycol, const bf16* ac, int row0, int chunk, float ka, float kb, bool relu) {
+    float pv[VV];
+#pragma unroll
+    for (int u = 0; u < VV; ++u) {
+        const float v = fmaf(__bfloat162float(*reinterpret_cast<const bf16*>(rcol + atom_off(row0 + u, chunk))), ka, kb);
+        pv[u] = relu ? fmaxf(v, 0.f) : v;
+    }
+#pragma unroll 1
+    for (int w0 = 0; w0 + 4 <= VV; w0 += 4) xf_contract_group<VV, KK, 4>(pv, ac + w0 * KK, ycol, row0 + w0, chunk);
+    constexpr int TAIL = VV % 4;
+    if (TAIL) xf_contract_group<VV, KK, TAIL ? TAIL : 1>(pv, ac + (VV - TAIL) * KK, ycol, row0 + VV - TAIL, chunk);
+}
+
 struct G4Bars {
     uint64_t full[G4_MAX_STAGES], empty[G4_MAX_STAGES], ready[G4_MAX_STAGES];
     uint64_t wbar, acc_full[2], acc_free[2], out_ready[2], stat_done[2], out_free[2];
@@ -114,6 +151,7 @@ template <bool XF, bool TAILS, int STATS>
 __global__ void __launch_bounds__(G4_THREADS, 1)
 tc4_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUtensorMap mapO,
                 const dsg_conv_gemm_args a, const G4Plan p, const float* __restrict__ cbias) {
+    // (mode 4 passes the tensor map of the contracted-tile side output Y as mapA1)
     DSG_DYN_SMEM(smem_raw);
     __shared__ G4Bars bars;
     __shared__ uint32_t tmem_base_s;
@@ -151,6 +189,8 @@ tc4_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
             cf_b[k] = ((in && a.src.b1) ? a.src.b1[k] : 0.f) + ((in && a.src.b2) ? a.src.b2[k] : 0.f);
         }
     for (int i = tid; i < 256; i += G4_THREADS) reinterpret_cast<uint16_t*>(ones)[i] = 0x3F80;      // bf16 1.0
+    if (p.mode == 4)             // channels >= K and padding rows of the contracted atoms are never written: they must read as zero
+        for (unsigned i = tid; i < (unsigned)p.S * 2u * ATOM_BYTES / 16u; i += G4_THREADS) reinterpret_cast<uint4*>(Asm)[i] = make_uint4(0u, 0u, 0u, 0u);
     if (tid == 0) {
         for (int s = 0; s < G4_MAX_STAGES; ++s) { mbar_init(&bars.full[s], 1); mbar_init(&bars.empty[s], 1); mbar_init(&bars.ready[s], 32 * G4_XF_WARPS); }
         mbar_init(&bars.wbar, 1);
@@ -166,10 +206,15 @@ tc4_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = tmem_base_s;
-    const int n_my = ((int)blockIdx.x < p.n_tiles) ? (p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    // tiles of this CTA: strided (tile = blockIdx.x + i * gridDim.x), or a consecutive run in mode 4
+    int n_my = ((int)blockIdx.x < p.n_tiles) ? (p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    const int tile0 = p.mode == 4 ? (int)blockIdx.x * p.tpc : (int)blockIdx.x, tstep = p.mode == 4 ? 1 : (int)gridDim.x;
+    if (p.mode == 4) { n_my = p.n_tiles - tile0; n_my = n_my < 0 ? 0 : (n_my > p.tpc ? p.tpc : n_my); }
     const uint32_t box_bytes = p.mode == 0 ? (uint32_t)ATOM_BYTES : (uint32_t)(p.F * (p.mode == 1 ? p.V : (p.mode == 2 ? p.V + 1 : a.Vin)) * 128);
     const int yy = p.mode == 3 ? (int)blockIdx.y : 0;
     const int natoms = p.mode == 3 ? p.t_n[yy] : p.natoms;
+    const bool m4 = p.mode == 4;
+    const uint32_t stage_bytes = m4 ? 2u * ATOM_BYTES : (uint32_t)ATOM_BYTES;      // mode 4: [raw | contracted]
 
     if (warp == 0) {
         // ================================================= TMA producer =================================================
@@ -183,13 +228,15 @@ tc4_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
             int stage = 0;
             uint32_t ph = 0;
             for (int i = 0; i < n_my; ++i) {
-                const int tile = (int)blockIdx.x + i * (int)gridDim.x;
-                const int smp = p.mode == 3 ? tile / p.tps : 0, q0 = p.mode == 3 ? (tile - smp * p.tps) * p.F : 0;
+                const int tile = tile0 + i * tstep;
+                const int smp = p.mode >= 3 ? tile / p.tps : 0, q0 = p.mode >= 3 ? (tile - smp * p.tps) * p.F : 0;
                 for (int ai = 0; ai < natoms; ++ai) {
-                    mbar_wait(&bars.empty[stage], ph ^ 1);
+                    mbar_wait_backoff(&bars.empty[stage], ph ^ 1, m4);
                     mbar_expect_tx(&bars.full[stage], box_bytes);
-                    unsigned char* dst = Asm + (size_t)stage * ATOM_BYTES;
-                    if (p.mode == 3) {
+                    unsigned char* dst = Asm + (size_t)stage * stage_bytes;
+                    if (m4) {
+                        for (int f = 0; f < p.F; ++f) tma_load_4d(dst + (size_t)f * p.slot * 128, &mapA0, 0, 0, q0 + f, smp, &bars.full[stage]);
+                    } else if (p.mode == 3) {
                         const CUtensorMap* m = p.t_map[yy][ai] ? &mapA1 : &mapA0;
                         for (int f = 0; f < p.F; ++f)
                             tma_load_4d(dst + (size_t)f * p.slot * 128, m, p.t_c0[yy][ai], 0, q0 + f + p.t_tsh[yy][ai], smp, &bars.full[stage]);
@@ -213,14 +260,21 @@ tc4_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
             uint32_t ph = 0;
             for (int i = 0; i < n_my; ++i) {
                 const int buf = i & 1, use = i >> 1;
-                if (use > 0) mbar_wait(&bars.acc_free[buf], (uint32_t)((use - 1) & 1));
+                if (use > 0) mbar_wait_backoff(&bars.acc_free[buf], (uint32_t)((use - 1) & 1), m4);
                 tc_fence_after();
                 const uint32_t acc = tmem + (uint32_t)(buf * p.acc_cols);
                 int first = 1;
                 for (int ai = 0; ai < natoms; ++ai) {
-                    mbar_wait(XF ? &bars.ready[stage] : &bars.full[stage], ph);
+                    mbar_wait_backoff(XF ? &bars.ready[stage] : &bars.full[stage], ph, m4);
                     tc_fence_after();
-                    const uint32_t a0 = smem_u32(Asm + (size_t)stage * ATOM_BYTES);
+                    const uint32_t a0 = smem_u32(Asm + (size_t)stage * stage_bytes) + (m4 ? (uint32_t)ATOM_BYTES : 0u);
+                    if (m4 && p.store_y) {
+                        // side output of the fused contraction: the tile the tensor core is about to read, stored by the TMA unit
+                        const int tile = tile0 + i * tstep, smp = tile / p.tps, q0 = (tile - smp * p.tps) * p.F;
+                        for (int f = 0; f < p.F; ++f)
+                            if (q0 + f < p.Tq) tma_store_4d(&mapA1, Asm + (size_t)stage * stage_bytes + ATOM_BYTES + (size_t)f * p.slot * 128, 0, 0, q0 + f, smp);
+                        tma_store_commit();
+                    }
                     if (p.mode == 3) {
                         // the branch's column window of the accumulator (atom 0 spans the whole tile and initialises it)
                         const uint32_t w0 = smem_u32(Wsm + p.t_woff[yy][ai]), idw = make_idesc(128, p.t_nw[yy][ai]);
@@ -235,15 +289,63 @@ tc4_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
                             first = 0;
                         }
                     }
+                    if (m4 && p.store_y) tma_store_wait_read<0>();      // the stage is reused once `empty` fires: the store must have read it
                     umma_commit(&bars.empty[stage]);
                     if (++stage == p.S) { stage = 0; ph ^= 1; }
                 }
                 umma_commit(&bars.acc_full[buf]);
             }
+            if (m4 && p.store_y) tma_store_wait_all<0>();
         }
     } else if (warp < 2 + G4_XF_WARPS) {
         // ================================================ transform warps ===============================================
-        if (XF) {
+        if (XF && m4) {
+            // ---- fused adjacency contraction (north-star kernel (a), dynamic case): y[t,w,c] = sum_u relu(bn(p))[t,u,c] * adyn[n,u,w,c].
+            //      thread = (frame, channel) column of the tile: its V source joints live in registers, the sample's adjacency slice in
+            //      shared memory (bf16 [u][w][K]: lanes = consecutive channels, conflict-free), the result goes straight into the
+            //      SWIZZLE_128B atom the tensor core multiplies with the `post` weights — Y is never read back from HBM.
+            const int t = tid - G4_XF_T0;                 // 0..127
+            const int K = a.K, V = p.V;
+            const bf16* adj_s = reinterpret_cast<const bf16*>(sm + p.off_adj);
+            int stage = 0, cur_smp = -1;
+            uint32_t ph = 0;
+            for (int i = 0; i < n_my; ++i) {
+                const int tile = tile0 + i * tstep, smp = tile / p.tps;
+                if (smp != cur_smp) {
+                    // new sample: bring its adjacency slice (contiguous [V*V*K] bf16) — the previous tile's readers are past it
+                    named_sync(G4_BAR_XF, 32 * G4_XF_WARPS);
+                    const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(a.adyn) + (size_t)smp * V * V * K);
+                    uint4* dst = reinterpret_cast<uint4*>(sm + p.off_adj);
+                    for (int j = t; j < V * V * K / 8; j += 32 * G4_XF_WARPS) dst[j] = src[j];
+                    named_sync(G4_BAR_XF, 32 * G4_XF_WARPS);
+                    cur_smp = smp;
+                }
+                mbar_wait(&bars.full[stage], ph);
+                const unsigned char* raw = Asm + (size_t)stage * stage_bytes;
+                unsigned char* yat = Asm + (size_t)stage * stage_bytes + ATOM_BYTES;
+                for (int col = t; col < p.F * K; col += 32 * G4_XF_WARPS) {
+                    const int f = col / K, c = col - f * K;
+                    const float ka = cf_a[c], kb = cf_b[c];
+                    const uint32_t coff = (uint32_t)(c & 7) * 2u;
+                    const unsigned char* rcol = raw + coff;
+                    unsigned char* ycol = yat + coff;
+                    const bf16* ac = adj_s + c;
+                    const int row0 = f * p.slot, chunk = c >> 3;
+                    const bool relu = a.src.relu != 0;
+                    switch (p.cvar) {
+                        case 0: xf_contract_col<25, 24>(rcol, ycol, ac, row0, chunk, ka, kb, relu); break;
+                        case 1: xf_contract_col<25, 48>(rcol, ycol, ac, row0, chunk, ka, kb, relu); break;
+                        case 2: xf_contract_col<17, 24>(rcol, ycol, ac, row0, chunk, ka, kb, relu); break;
+                        case 3: xf_contract_col<17, 48>(rcol, ycol, ac, row0, chunk, ka, kb, relu); break;
+                        case 4: xf_contract_col<18, 24>(rcol, ycol, ac, row0, chunk, ka, kb, relu); break;
+                        default: xf_contract_col<18, 48>(rcol, ycol, ac, row0, chunk, ka, kb, relu); break;
+                    }
+                }
+                fence_async_smem();
+                mbar_arrive(&bars.ready[stage]);
+                if (++stage == p.S) { stage = 0; ph ^= 1; }
+            }
+        } else if (XF) {
             const int t = tid - G4_XF_T0;                 // 0..127
             const int Vr = p.mode == 2 ? p.V + 1 : p.V;   // rows the TMA wrote per frame slot
             int stage = 0;
@@ -343,7 +445,7 @@ tc4_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
         const bf16* add2p = reinterpret_cast<const bf16*>(a.add2);
         const bf16* partp = reinterpret_cast<const bf16*>(a.partner);
         for (int i = 0; i < n_my; ++i) {
-            const int tile = (int)blockIdx.x + i * (int)gridDim.x;
+            const int tile = tile0 + i * tstep;
             const int buf = i & 1, use = i >> 1, ob = i % p.OB, useo = i / p.OB;
             // ---- this thread's output row
             long long gr = -1;
@@ -352,7 +454,7 @@ tc4_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
                 const long long g = (long long)tile * ATOM_ROWS + r;
                 if (g < p.rows_out) gr = g;
                 if (TAILS && a.bcast && gr >= 0) { const long long fr = gr / Vout; jrow = (int)(gr - fr * Vout); samp = (int)(fr / a.T_out); }
-            } else if (p.mode == 3) {
+            } else if (p.mode >= 3) {
                 const int smp = tile / p.tps, q = (tile - smp * p.tps) * p.F + r / p.slot, v = r % p.slot;
                 if (r / p.slot < p.F && v < Vout && q < p.Tq) { gr = ((long long)smp * p.Tdst + (long long)q * p.qs + p.qp) * Vout + v; jrow = v; samp = smp; }
             } else {
@@ -360,9 +462,9 @@ tc4_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
                 const long long frame = (long long)tile * p.F + f;
                 if (f < p.F && v < Vout && frame < p.n_frames) { gr = frame * Vout + v; jrow = v; samp = (int)(frame / a.T_out); }
             }
-            mbar_wait(&bars.acc_full[buf], (uint32_t)(use & 1));
+            mbar_wait_backoff(&bars.acc_full[buf], (uint32_t)(use & 1), m4);
             tc_fence_after();
-            if (i >= p.OB) mbar_wait(&bars.out_free[ob], (uint32_t)((useo - 1) & 1));     // out / product tiles of `OB` tiles ago have been read
+            if (i >= p.OB) mbar_wait_backoff(&bars.out_free[ob], (uint32_t)((useo - 1) & 1), m4);     // out / product tiles of `OB` tiles ago have been read
             unsigned char* Ot = Osm + (size_t)ob * p.out_bytes;
             unsigned char* St = Ssm + (size_t)ob * p.out_bytes;
             const uint32_t acc = tmem + (uint32_t)(buf * p.acc_cols) + ((uint32_t)(q * 32) << 16);
@@ -502,15 +604,15 @@ tc4_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
         const int Ms = Ntp <= 64 ? 64 : 128;
         const uint32_t ones_d = smem_u32(ones);
         for (int i = 0; i < n_my; ++i) {
-            const int tile = (int)blockIdx.x + i * (int)gridDim.x;
+            const int tile = tile0 + i * tstep;
             const int ob = i % p.OB, useo = i / p.OB;
-            mbar_wait(&bars.out_ready[ob], (uint32_t)(useo & 1));
+            mbar_wait_backoff(&bars.out_ready[ob], (uint32_t)(useo & 1), m4);
             tc_fence_after();
             const unsigned char* Ot = Osm + (size_t)ob * p.out_bytes;
             for (int oa = 0; oa < (a.out_f32 ? 0 : n_oatoms); ++oa) {
                 const unsigned char* src = Ot + (size_t)oa * ATOM_BYTES;
                 if (p.mode == 0) tma_store_2d(&mapO, src, n0 + oa * ATOM_CH, tile * ATOM_ROWS);
-                else if (p.mode == 3) {
+                else if (p.mode >= 3) {
                     const int smp = tile / p.tps, q0 = (tile - smp * p.tps) * p.F;
                     for (int f = 0; f < p.F; ++f)
                         if (q0 + f < p.Tq) tma_store_4d(&mapO, src + (size_t)f * p.slot * 128, n0 + oa * ATOM_CH, 0, q0 + f, smp);
@@ -621,8 +723,107 @@ static bool tc4_plan(const dsg_conv_gemm_args& a, G4Plan& p, bool fold) {
     return false;
 }
 
+// ---- fused adjacency contraction + 1x1 convolution (G4Plan mode 4)
+static const char* launch_conv_gemm_tc4_fused(const dsg_conv_gemm_args& a, dsg_stream_t st, bool* handled) {
+    *handled = false;
+    if (a.dtype != DSG_BF16 || a.taps != 1 || a.t_mul != 1 || a.t_div != 1 || a.tap_off != 0 || a.T_in != a.T_out) return nullptr;
+    if (a.K % 8 != 0 || a.K > ATOM_CH || a.N % 8 != 0 || a.N < 16 || a.N > 128 || a.ext_in || a.contract_ext || a.src.x2 || a.src.a2 || a.out_f32) return nullptr;
+    if (a.Vin < 2 || a.Vin > 32 || (uintptr_t)a.adyn % 16 != 0 || !a.wpack || (uintptr_t)a.wpack % 128 != 0) return nullptr;
+    if (!tma_ptr_ok(a.src.x1, a.src.ld1) || !tma_ptr_ok(a.out, a.ld_out) || (a.y_out && !tma_ptr_ok(a.y_out, a.ld_y))) return nullptr;
+    auto al16 = [](const void* q, long long ld) { return q == nullptr || ((uintptr_t)q % 16 == 0 && ld % 8 == 0); };
+    if (!(al16(a.add, a.ld_add) && al16(a.add2, a.ld_add2) && al16(a.partner, a.ld_partner) && (!a.has_mask || act8_ok(a.mask)))) return nullptr;
+    if (a.n_samples <= 0 || a.T_out <= 0) { *handled = true; return nullptr; }
+    if (!encode_fn()) return nullptr;
+    G4Plan p{};
+    p.mode = 4;
+    p.V = a.Vin;
+    p.slot = (a.Vin + 7) & ~7;
+    p.F = ATOM_ROWS / p.slot;
+    p.qs = 1; p.qp = 0; p.Tdst = a.T_out; p.Tq = a.T_out;
+    p.tps = (a.T_out + p.F - 1) / p.F;
+    const long long nt = (long long)a.n_samples * p.tps;
+    if (nt > 0x3fffffff) return nullptr;
+    p.n_tiles = (int)nt;
+    p.n_frames = (long long)a.n_samples * a.T_out;
+    p.rows_out = p.n_frames * a.Vin;
+    p.natoms = p.natoms1 = 1;
+    p.ksteps[0] = (a.K + 15) / 16;
+    p.K1p = ATOM_CH;
+    p.act = 1; p.xf = 1;
+    p.stats = a.stat_sum == nullptr ? 0 : (a.partner ? 2 : 1);
+    p.store_y = a.y_out ? 1 : 0;
+    {   // the contraction is compiled for the joint counts of the three layouts and the 3R of R = 8 / 16 (gcn_ratio = 0.125)
+        const int vi = a.Vin == 25 ? 0 : (a.Vin == 17 ? 1 : (a.Vin == 18 ? 2 : -1)), ki = a.K == 24 ? 0 : (a.K == 48 ? 1 : -1);
+        if (vi < 0 || ki < 0) return nullptr;
+        p.cvar = vi * 2 + ki;
+    }
+    p.Ntile = a.N <= 64 ? 64 : 128;
+    p.adj_bytes = ((unsigned)(a.Vin * a.Vin * a.K * 2) + 1023u) & ~1023u;
+    const unsigned wb = (unsigned)p.Ntile * 128;
+    const unsigned ob1 = (unsigned)(p.Ntile / ATOM_CH) * ATOM_BYTES;
+    const unsigned cf_bytes = (unsigned)((4 * 128 + 2 * p.K1p) * sizeof(float));
+    const unsigned budget = 227u * 1024u - 2048u;
+    bool fit = false;
+    for (int OB = 2; OB >= 1 && !fit; --OB) {
+        const unsigned fixed = wb + OB * ob1 * (p.stats == 2 ? 2u : 1u) + 1024u + ((cf_bytes + 1023u) & ~1023u) + p.adj_bytes + 1024u;
+        if (fixed + 2u * 2u * ATOM_BYTES > budget) continue;
+        int S = (int)((budget - fixed) / (2u * ATOM_BYTES));
+        if (S > 4) S = 4;
+        p.S = S; p.OB = OB;
+        p.off_w = 0;
+        p.off_a = wb;
+        p.off_out = p.off_a + (unsigned)S * 2u * ATOM_BYTES;
+        p.out_bytes = ob1;
+        p.off_stat = p.off_out + OB * ob1;
+        p.off_ones = p.off_stat + (p.stats == 2 ? OB * ob1 : 0u);
+        p.off_cf = p.off_ones + 1024u;
+        p.off_adj = p.off_cf + ((cf_bytes + 1023u) & ~1023u);
+        p.smem_total = p.off_adj + p.adj_bytes + 1024u;
+        fit = true;
+    }
+    if (!fit) return nullptr;
+    p.w_tile_bytes = wb;
+    p.acc_cols = p.Ntile <= 64 ? 64 : 128;
+    p.stat_col = 2 * p.acc_cols;
+    p.sum_col = p.stat_col + (p.stats == 1 ? p.acc_cols : 8);
+    const int need = p.stats ? p.sum_col + 8 : 2 * p.acc_cols;
+    p.tmem_cols = 32;
+    while (p.tmem_cols < need) p.tmem_cols <<= 1;
+    if ((long long)(wb + (size_t)a.N * 4 + 256) > tc4_wpack_bytes(a.K, a.N)) return nullptr;
+    CUtensorMap mA0, mY, mO;
+    bool ok = make_map_4d(&mA0, a.src.x1, a.n_samples, a.T_in, a.Vin, a.K, a.src.ld1, 0, 1);
+    mY = mA0;
+    if (ok && a.y_out) ok = make_map_4d(&mY, a.y_out, a.n_samples, a.T_out, a.Vin, a.K, a.ld_y, 0, 1);
+    ok = ok && make_map_4d(&mO, a.out, a.n_samples, a.T_out, a.Vin, a.N, a.ld_out, 0, 1);
+    if (!ok) return nullptr;
+    float* cbias = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(a.wpack) + (((size_t)wb + 255) & ~(size_t)255));
+    tc4_wpack_kernel<<<dim3(1, 2), dim3(256), 0, st>>>(a.W, a.ws_n, a.ws_k, a.K, a.N, 1, 1, p.Ntile, nullptr, nullptr, nullptr, nullptr, a.bias,
+                                                         reinterpret_cast<unsigned char*>(a.wpack), cbias);
+    if (const char* e = dsg_launch_error()) return e;
+    int gx = num_sms();
+    if (gx > p.n_tiles) gx = p.n_tiles;
+    p.tpc = (p.n_tiles + gx - 1) / gx;
+    gx = (p.n_tiles + p.tpc - 1) / p.tpc;
+    const bool tails = a.add || a.add2 || a.bcast || a.has_mask || a.partner;
+    if (p.stats == 2 && !tails) return "conv_gemm (fused contraction): statistics with a partner need the partner";
+#define DSG_T4F_LAUNCH(TL_, ST_)                                                                                                   \
+    do {                                                                                                                          \
+        cudaFuncSetAttribute(tc4_gemm_kernel<true, TL_, ST_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_total);    \
+        tc4_gemm_kernel<true, TL_, ST_><<<dim3((unsigned)gx, 1), dim3(G4_THREADS), p.smem_total, st>>>(mA0, mY, mO, a, p, cbias); \
+    } while (0)
+    if (!tails && p.stats == 0) DSG_T4F_LAUNCH(false, 0);
+    else if (!tails && p.stats == 1) DSG_T4F_LAUNCH(false, 1);
+    else if (tails && p.stats == 0) DSG_T4F_LAUNCH(true, 0);
+    else if (tails && p.stats == 1) DSG_T4F_LAUNCH(true, 1);
+    else DSG_T4F_LAUNCH(true, 2);
+#undef DSG_T4F_LAUNCH
+    *handled = true;
+    return dsg_launch_error();
+}
+
 static const char* launch_conv_gemm_tc4(const dsg_conv_gemm_args& a, dsg_stream_t st, bool* handled) {
     *handled = false;
+    if (a.adyn) return tc4_enabled() ? launch_conv_gemm_tc4_fused(a, st, handled) : nullptr;
     if (!tc4_enabled() || a.dtype != DSG_BF16 || a.taps != 1 || a.t_mul != 1 || a.t_div != 1 || a.tap_off != 0) return nullptr;
     if (a.K % 8 != 0 || a.N % 8 != 0 || a.N < 16 || a.T_in != a.T_out) return nullptr;
     if (a.ext_in && a.contract_ext) return nullptr;

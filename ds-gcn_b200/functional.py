@@ -293,16 +293,21 @@ def dgphgcn1_forward(m, x, n, T, V, save):
         c_pd.add_bn(m.down[1], KC, Npd, rows)
     c_pd.run()
 
-    # ---- y[n,t,w,kc] = sum_u relu(bn(pre))[n,t,u,kc] * adyn[n,u,w,kc]
+    # ---- y[n,t,w,kc] = sum_u relu(bn(pre))[n,t,u,kc] * adyn[n,u,w,kc];  z = post(y), BatchNorm statistics in the epilogue
     P_act = Act(PD[:, :KC], c_pd.a[:KC], c_pd.b[:KC], relu=True)
-    Y = torch.empty(rows, KC, dtype=dt, device=dev)
-    ops.graph_agg(P_act, Y, mode=0, n_samples=n, T=T, V=V, KC=KC, adyn=adyn)
-
-    # ---- post conv, BatchNorm statistics in the epilogue
     Z = torch.empty(rows, Cout, dtype=dt, device=dev)
     c_z = BNCoef(Cout, dev, [m.bn])
-    ops.conv_gemm(Y, m.post.weight.view(Cout, KC), Cout, Z, n_samples=n, T_in=T, T_out=T, Vin=V, bias=m.post.bias,
-                  stat_sum=c_z.ssum, stat_sq=c_z.ssq)
+    Wpost = m.post.weight.view(Cout, KC)
+    if FUSED_AGG and dt == torch.bfloat16 and KC <= 64 and KC % 8 == 0 and Cout <= 128 and ops.L.is_device_build():
+        # north-star kernel (a): the contraction runs INSIDE the post GEMM (operand producer of the tensor core); Y is written only
+        # when backward will need it (weight gradient of `post`) and is never read back in the forward pass
+        Y = torch.empty(rows, KC, dtype=dt, device=dev) if save is not None else None
+        ops.conv_gemm(P_act, Wpost, Cout, Z, n_samples=n, T_in=T, T_out=T, Vin=V, bias=m.post.bias, stat_sum=c_z.ssum, stat_sq=c_z.ssq,
+                      adyn=adyn, y_out=Y)
+    else:
+        Y = torch.empty(rows, KC, dtype=dt, device=dev)
+        ops.graph_agg(P_act, Y, mode=0, n_samples=n, T=T, V=V, KC=KC, adyn=adyn)
+        ops.conv_gemm(Y, Wpost, Cout, Z, n_samples=n, T_in=T, T_out=T, Vin=V, bias=m.post.bias, stat_sum=c_z.ssum, stat_sq=c_z.ssq)
     c_z.add_bn(m.bn, 0, Cout, rows)
     c_z.run()
 
@@ -471,6 +476,7 @@ def _ms_fused_args(m, layout, b_act, n, T, T_out, s, V, has_ext, grads):
     return a if ops.ms_temporal_supported(a) else None
 
 
+FUSED_AGG = os.environ.get("DSG_FUSED_AGG", "1") != "0"     # 0: separate adjacency contraction (dsg_graph_agg) + post GEMM
 MS_TAP = os.environ.get("DSG_MS_TAP", "1") != "0"      # 0: the staged single-kernel branch stage (ms_temporal_tc.cuh) instead
 
 

@@ -74,7 +74,7 @@ def _f32(t):
 
 def conv_gemm(src, W, N, out, *, n_samples, T_in, T_out, Vin, ws=None, bias=None, taps=1, tap_step=0, tap_off=0,
               t_mul=1, t_div=1, ext_in=False, contract_ext=False, add=None, add2=None, bcast=None, bcast_scale=1.0,
-              mask=None, stat_sum=None, stat_sq=None, partner=None, out_f32=False):
+              mask=None, stat_sum=None, stat_sq=None, partner=None, out_f32=False, adyn=None, y_out=None):
     """dsg_conv_gemm.  W fp32 with strides ws=(ws_n, ws_k, ws_tap); default = PyTorch conv weight
     [N, K, taps, 1] (or [N, K]).  out_f32: bf16 sources, fp32 `out` (unrounded accumulator; tcgen05 engine only)."""
     src = as_act(src)
@@ -98,6 +98,13 @@ def conv_gemm(src, W, N, out, *, n_samples, T_in, T_out, Vin, ws=None, bias=None
     else:
         assert out.dtype == src.dtype
     a.out, a.ld_out = L.ptr(out), _ld(out)
+    if adyn is not None:
+        # fused spatial graph convolution: rows are contracted per frame with adyn[n,u,w,k] inside the kernel (include/dsgcn_b200.h)
+        assert adyn.dtype == torch.bfloat16 and adyn.is_contiguous() and adyn.shape == (n_samples, Vin, Vin, K)
+        a.adyn = L.ptr(adyn)
+        if y_out is not None:
+            assert y_out.dtype == torch.bfloat16 and y_out.shape[-1] == K
+            a.y_out, a.ld_y = L.ptr(y_out), _ld(y_out)
     if add is not None:
         assert add.dtype == src.dtype
         a.add, a.ld_add = L.ptr(add), _ld(add)
@@ -132,7 +139,7 @@ def conv_gemm(src, W, N, out, *, n_samples, T_in, T_out, Vin, ws=None, bias=None
         nbytes += rows_out * N * es
     tag = None
     if L.profile is not None:
-        tag = dict(K=K, N=N, rows_out=rows_out, taps=taps, ext_in=int(ext_in), cext=int(contract_ext), x2=src.x2 is not None,
+        tag = dict(K=K, N=N, rows_out=rows_out, taps=taps, ext_in=int(ext_in), cext=int(contract_ext), x2=src.x2 is not None, fused=adyn is not None,
                    mask=mask is not None, stats=stat_sum is not None, ws=tuple(ws), t_mul=t_mul, t_div=t_div, dt=str(src.dtype))
     L.call("dsg_conv_gemm", C.byref(a), L.stream(), nbytes=nbytes, tag=tag)
     return out

@@ -95,6 +95,13 @@ typedef struct dsg_conv_gemm_args {
     int out_f32;          /* 1 (bf16 sources only, no addends / mask / statistics): `out` is fp32 — the accumulator is stored
                              unrounded (the topology-feature convolutions conv1/conv2/conv1_se, gcn.py:2248-2259, feed tanh / softmax) */
     int pad2_;
+    /* Fused spatial graph convolution (north-star kernel (a), gcn.py:2350-2363): when `adyn` is set the source rows are first
+     * contracted frame by frame with the per-sample, per-channel adjacency, y[n,t,w,k] = sum_u src[n,t,u,k] * adyn[n,u,w,k], INSIDE
+     * the kernel (operand producer of the tensor core), and out = bias + y W^T.  bf16, K <= 64, N <= 128, taps == 1.  y_out
+     * (optional, [rows, ld_y]) also stores y — the training forward keeps it for the weight gradient; inference never writes it. */
+    const void* adyn;     /* [n_samples, Vin, Vin, K] bf16 */
+    void* y_out;
+    long long ld_y;
 } dsg_conv_gemm_args;
 int dsg_conv_gemm(const dsg_conv_gemm_args* a, void* stream);
 long long dsg_conv_gemm_wpack_bytes(int K, int N);

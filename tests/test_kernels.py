@@ -624,3 +624,40 @@ def test_ms_conv_tap_shifted_tma(widths, stride):
     close(ss[:span], dq.sum(0), torch.bfloat16, "sum e")
     close(sq[:span], (dq * Braw.float()[:, :span]).sum(0), torch.bfloat16, "sum e*b")
     assert float(ss[span:].abs().sum()) == 0.0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("V,KC,N,T", [(25, 24, 64, 100), (25, 48, 128, 50), (17, 24, 64, 30), (25, 48, 128, 7)])
+@pytest.mark.parametrize("store_y", [False, True])
+def test_conv_gemm_fused_adjacency_contraction(V, KC, N, T, store_y):
+    """North-star kernel (a): the per-sample, per-channel adjacency contraction as the operand producer of the post 1x1 convolution
+    (gcn.py:2350-2363) — relu(bn(pre)) rows -> y[t,w,c] = sum_u p[t,u,c] adyn[u,w,c] -> z = y W^T + b with BatchNorm statistics, one
+    kernel, against einsum + matmul.  T not a multiple of the 4-frame tile exercises the per-sample tail tiles."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    dsgcn_b200._lib._testing_use_library(None)
+    dev = torch.device("cuda:0")
+    dtype = torch.bfloat16
+    torch.manual_seed(V * 100 + KC + T)
+    n = 37                                                   # several samples per CTA and CTAs that start mid-sample
+    rows = n * T * V
+    PD = rnd(rows, KC + 40, dev=dev, dtype=dtype)            # the contraction reads a channel slice of a wider buffer (pre | down)
+    a1, b1 = torch.rand(KC, device=dev) + 0.5, rnd(KC, dev=dev, scale=0.2)
+    adyn = (torch.randn(n, V, V, KC, device=dev) * 0.3).to(dtype)
+    W, b = rnd(N, KC, dev=dev, scale=0.2), rnd(N, dev=dev)
+    Z = torch.full((rows, N), float("nan"), dtype=dtype, device=dev)
+    Y = torch.full((rows, KC), float("nan"), dtype=dtype, device=dev) if store_y else None
+    ss, sq = torch.zeros(N, dtype=torch.float64, device=dev), torch.zeros(N, dtype=torch.float64, device=dev)
+    before = _lib.lib().dsg_debug_counter(2)
+    ops.conv_gemm(ops.Act(PD[:, :KC], a1, b1, relu=True), W, N, Z, n_samples=n, T_in=T, T_out=T, Vin=V, bias=b, stat_sum=ss, stat_sq=sq,
+                  adyn=adyn, y_out=Y)
+    assert _lib.lib().dsg_debug_counter(2) == before + 1
+    p = torch.relu(PD[:, :KC].float() * a1 + b1).view(n, T, V, KC)
+    y_ref = torch.einsum("ntuc,nuwc->ntwc", p, adyn.float())
+    z_ref = y_ref.to(dtype).float().reshape(rows, KC) @ W.t() + b        # the tensor core multiplies the bf16-rounded y
+    close(Z, z_ref, dtype, "fused z")
+    zq = Z.float()
+    close(ss, zq.sum(0), dtype, "sum z")
+    close(sq, (zq * zq).sum(0), dtype, "sum z^2")
+    if store_y:
+        close(Y.view(n, T, V, KC), y_ref, dtype, "side output y")
