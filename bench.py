@@ -37,6 +37,7 @@ NUM_CLASSES = 60
 SGD = dict(lr=0.1, momentum=0.9, weight_decay=5e-4, nesterov=True)     # configs/_init_/lr_schedual.py:11
 # stage-granular algorithmic elements per clip, forward; train = 3x (read x, read dy, write dx)
 ELEMS_PER_CLIP_FWD = 16.655e6
+LAUNCH_LIST = "r02_launch_list_train_b128.json"      # ncu launch list of one eager training step of this build (tools/ncu_launch_list.py)
 
 
 def parse():
@@ -62,6 +63,7 @@ def parse():
     p.add_argument("--ref-clips", type=int, default=REF_CLIPS, help="clips per step of the CPU reference arm (N=16: SURVEY 8d)")
     p.add_argument("--ref-budget", type=float, default=240.0, help="seconds the whole reference run may take (the batch shrinks to fit)")
     p.add_argument("--no-ref-gpu", action="store_true", help="skip the reference-eager-on-this-GPU context number")
+    p.add_argument("--no-fwd", action="store_true", help="skip the forward-metric leg reported in extra.fwd")
     return p.parse_args()
 
 
@@ -581,15 +583,16 @@ def main():
     achieved = agg[top][1] / (agg[top][0] * 1e-3) / 1e9
     # DRAM traffic of the dominant entry point, from the committed ncu launch list of this exact workload (bytes per launch,
     # to set against the algorithmic bytes per launch); null for any other workload
-    traffic, traffic_src, own_kernels = None, None, None
+    traffic, traffic_src, own_kernels, step_traffic = None, None, None, None
     if train and B == 128 and dtype == torch.bfloat16:
         try:
-            ll = json.load(open(os.path.join(ROOT, "profiles", "r01_launch_list_train_b128.json")))
+            ll = json.load(open(os.path.join(ROOT, "profiles", LAUNCH_LIST)))
             stem = top.replace("dsg_", "")
             ks = [k for k in ll["kernels"] if stem in k["kernel"] and "wpack" not in k["kernel"] and ("wgrad" in stem) == ("wgrad" in k["kernel"])]
             if ks:
                 traffic = sum(k["dram_read_mb"] + k["dram_write_mb"] for k in ks) * 1e6 / sum(k["launches"] for k in ks)
-                traffic_src = "profiles/r01_launch_list_train_b128.json (ncu dram__bytes_read.sum + dram__bytes_write.sum, mean per launch)"
+                traffic_src = f"profiles/{LAUNCH_LIST} (ncu dram__bytes_read.sum + dram__bytes_write.sum, mean per launch)"
+            step_traffic = sum(k["dram_read_mb"] + k["dram_write_mb"] for k in ll["kernels"]) * 1e6
             own_kernels = sum(k["launches"] for k in ll["kernels"] if not k["kernel"].startswith("void at::"))
         except Exception:
             pass
@@ -600,8 +603,48 @@ def main():
                     per_kernel_ms_per_step={k: round(v[0] / 2, 4) for k, v in sorted(agg.items(), key=lambda kv: -kv[1][0])},
                     per_kernel_gbs={k: round(v[1] / (v[0] * 1e-3) / 1e9, 1) for k, v in agg.items() if v[1] > 0 and v[0] > 0},
                     step_algorithmic_gbs=ELEMS_PER_CLIP_FWD * (3 if train else 1) * (2 if dtype == torch.bfloat16 else 4) * B / (ms * 1e-3) / 1e9)
+    # whole-step roofline: SURVEY 8(d) stage-granular algorithmic bytes of the step / step time / measured HBM peak, and the DRAM
+    # bytes the step really moves (committed ncu launch list of this workload)
+    roofline["step_algorithmic_bytes"] = ELEMS_PER_CLIP_FWD * (3 if train else 1) * (2 if dtype == torch.bfloat16 else 4) * B
+    roofline["step_frac"] = roofline["step_algorithmic_gbs"] / peak
+    roofline["step_traffic_bytes"] = step_traffic
+    roofline["step_traffic_over_algorithmic"] = (step_traffic / roofline["step_algorithmic_bytes"]) if step_traffic else None
     cpu = None
     extra = {}
+    if train and world == 1 and not args.no_fwd:
+        # the forward metric of BASELINE.json in the same run: eval forward (no_grad) of the same model, CUDA-graph replay
+        try:
+            model.eval()
+            def fwd_step(x):
+                with torch.no_grad():
+                    return model.cls_head(model.extract_feat(x[:, 0]))
+            side2 = torch.cuda.Stream()
+            side2.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side2):
+                for i in range(3):
+                    fwd_step(dev_x[i % 2])
+            torch.cuda.current_stream().wait_stream(side2)
+            torch.cuda.synchronize()
+            gf = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gf):
+                fwd_step(sx)
+            for i in range(3):
+                sx.copy_(dev_x[i % 2]); gf.replay()
+            torch.cuda.synchronize()
+            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            f0.record()
+            for i in range(args.steps):
+                sx.copy_(dev_x[i % 2], non_blocking=True); gf.replay()
+            f1.record()
+            torch.cuda.synchronize()
+            fms = f0.elapsed_time(f1) / args.steps
+            fgbs = ELEMS_PER_CLIP_FWD * (2 if dtype == torch.bfloat16 else 4) * B / (fms * 1e-3) / 1e9
+            extra["fwd"] = dict(metric="DS-GCN fwd clips/sec (M=2,T=100,V=25,C=3)", value=B / (fms * 1e-3), unit=unit, ms_per_step=fms, clips_per_gpu=B,
+                                cuda_graph=True, step_algorithmic_gbs=fgbs, step_frac=fgbs / peak)
+            gf.reset()
+            model.train(True)
+        except Exception as e:
+            extra["fwd"] = dict(unavailable=f"{type(e).__name__}: {str(e)[:200]}")
     if not args.no_cpu_baseline:
         cpu = cpu_baseline_leg(args.mode, args.ref_clips, 2, 1, budget_s=40.0)
     if not args.no_ref_gpu and world == 1:

@@ -13,3 +13,4 @@ from . import recognizer  # noqa: F401,E402
 from .recognizer import (BACKBONES, HEADS, LOSSES, MODELS, RECOGNIZERS, CrossEntropyLoss, GCNHead, RecognizerGCN,  # noqa: F401,E402
                          build_backbone, build_head, build_loss, build_model, build_recognizer)
 from . import parallel  # noqa: F401,E402
+from . import pipeline, train  # noqa: F401,E402

@@ -13,7 +13,7 @@ import torch.distributed as dist
 import torch.nn as nn
 import torch.nn.functional as F
 
-from . import modules
+from . import modules, ops
 
 
 class Registry:
@@ -110,6 +110,25 @@ class CrossEntropyLoss(nn.Module):
         return loss * self.loss_weight
 
 
+class _PoolFn(torch.autograd.Function):
+    """SimpleHead(mode='GCN') pooling (heads/simple_head.py:83-90): AdaptiveAvgPool2d(1) over (T, V), then the mean over the M
+    persons = one mean over the M*T*V rows of a clip.  The backbone output is channels-last rows already, so this is the temporal-
+    mean kernel with V = 1 (fp32 result, no intermediate [N*M, C] tensor, no dtype-conversion pass); backward broadcasts g / count."""
+
+    @staticmethod
+    def forward(ctx, x):
+        N, M_, C, T, V = x.shape
+        rows = modules.to_rows(x.detach().reshape(N * M_, C, T, V), x.dtype)          # a view for a backbone output
+        ctx.shape, ctx.dtype = x.shape, x.dtype
+        return ops.tmean(rows, N, M_ * T * V, 1).view(N, C)
+
+    @staticmethod
+    def backward(ctx, g):
+        N, M_, C, T, V = ctx.shape
+        d = (g / float(M_ * T * V)).to(ctx.dtype)
+        return d.view(N, 1, C, 1, 1).expand(N, M_, C, T, V)
+
+
 @MODELS.register_module()
 class GCNHead(nn.Module):
     """SimpleHead(mode='GCN'): mean over (T,V), mean over M, dropout(p) , Linear."""
@@ -132,7 +151,10 @@ class GCNHead(nn.Module):
     def forward(self, x):
         if x.dim() != 2:
             N, M_, C, T, V = x.shape
-            x = x.float().mean((3, 4)).mean(1)
+            if x.is_cuda and x.dtype in (torch.float32, torch.bfloat16) and ops.L.is_device_build():
+                x = _PoolFn.apply(x)                 # one kernel: mean over the M*T*V rows of every clip
+            else:
+                x = x.float().mean((3, 4)).mean(1)
         assert x.shape[1] == self.in_c
         if self.dropout is not None:
             x = self.dropout(x)
