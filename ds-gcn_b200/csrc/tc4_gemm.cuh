@@ -37,7 +37,7 @@ constexpr int G4_DRAIN_WARP = 2 + G4_XF_WARPS + G4_EPI_WARPS;            // warp
 constexpr int G4_THREADS = 32 * (G4_DRAIN_WARP + 1);                     // 480
 constexpr int G4_XF_T0 = 64, G4_EPI_T0 = 64 + 32 * G4_XF_WARPS;         // first thread of the transform / epilogue groups
 constexpr int G4_EPI_THREADS = 32 * G4_EPI_WARPS;                       // 256
-constexpr int G4_MAX_ATOMS = 12, G4_MAX_STAGES = 6;
+constexpr int G4_MAX_ATOMS = 12, G4_MAX_STAGES = 6, G4_MAX_OPS = 24;
 constexpr int G4_BAR_XF = 1, G4_BAR_EPI = 2;                            // named barriers
 
 struct G4Plan {
@@ -65,10 +65,14 @@ struct G4Plan {
     unsigned off_adj, adj_bytes; // shared-memory slice [V*V][K] bf16
     int store_y;                 // also write the contracted tile to HBM (training: operand of the weight gradient)
     int cvar;                    // (V, K) variant of the contraction code: {25,17,18} x {24,48}
+    //      An "atom" of mode 3 is a WINDOW of t_nfr consecutive source frames of one 64-channel column (t_nfr = F: a single tap;
+    //      t_nfr = F + halo: every tap of every branch that lives in the column reads it at a row offset — the frames are loaded
+    //      once instead of once per (branch, tap)); its MMA ops are o_*[t_op0 .. t_op0 of the next atom).
     int t_n[2];
-    short t_map[2][G4_MAX_ATOMS], t_tsh[2][G4_MAX_ATOMS], t_ks[2][G4_MAX_ATOMS], t_ncol[2][G4_MAX_ATOMS], t_nw[2][G4_MAX_ATOMS];
+    short t_map[2][G4_MAX_ATOMS], t_tsh[2][G4_MAX_ATOMS], t_nfr[2][G4_MAX_ATOMS], t_op0[2][G4_MAX_ATOMS + 1];
     int t_c0[2][G4_MAX_ATOMS];
-    unsigned t_woff[2][G4_MAX_ATOMS], t_wbytes[2];
+    short o_row[2][G4_MAX_OPS], o_k0[2][G4_MAX_OPS], o_ks[2][G4_MAX_OPS], o_ncol[2][G4_MAX_OPS], o_nw[2][G4_MAX_OPS];
+    unsigned o_woff[2][G4_MAX_OPS], t_wbytes[2], t_stage;
 };
 
 // ---- packed weights: per column tile j, per atom a: [Ntile rows (n) x 64 k] bf16 in the K-major SWIZZLE_128B layout, scaled
@@ -214,7 +218,7 @@ tc4_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
     const int yy = p.mode == 3 ? (int)blockIdx.y : 0;
     const int natoms = p.mode == 3 ? p.t_n[yy] : p.natoms;
     const bool m4 = p.mode == 4;
-    const uint32_t stage_bytes = m4 ? 2u * ATOM_BYTES : (uint32_t)ATOM_BYTES;      // mode 4: [raw | contracted]
+    const uint32_t stage_bytes = m4 ? 2u * ATOM_BYTES : (p.mode == 3 ? p.t_stage : (uint32_t)ATOM_BYTES);      // mode 4: [raw | contracted]
 
     if (warp == 0) {
         // ================================================= TMA producer =================================================
@@ -232,13 +236,13 @@ tc4_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
                 const int smp = p.mode >= 3 ? tile / p.tps : 0, q0 = p.mode >= 3 ? (tile - smp * p.tps) * p.F : 0;
                 for (int ai = 0; ai < natoms; ++ai) {
                     mbar_wait_backoff(&bars.empty[stage], ph ^ 1, m4);
-                    mbar_expect_tx(&bars.full[stage], box_bytes);
+                    mbar_expect_tx(&bars.full[stage], p.mode == 3 ? (uint32_t)(p.t_nfr[yy][ai] * a.Vin * 128) : box_bytes);
                     unsigned char* dst = Asm + (size_t)stage * stage_bytes;
                     if (m4) {
                         for (int f = 0; f < p.F; ++f) tma_load_4d(dst + (size_t)f * p.slot * 128, &mapA0, 0, 0, q0 + f, smp, &bars.full[stage]);
                     } else if (p.mode == 3) {
                         const CUtensorMap* m = p.t_map[yy][ai] ? &mapA1 : &mapA0;
-                        for (int f = 0; f < p.F; ++f)
+                        for (int f = 0; f < p.t_nfr[yy][ai]; ++f)
                             tma_load_4d(dst + (size_t)f * p.slot * 128, m, p.t_c0[yy][ai], 0, q0 + f + p.t_tsh[yy][ai], smp, &bars.full[stage]);
                     } else {
                         const CUtensorMap* m = ai < p.natoms1 ? &mapA0 : &mapA1;
@@ -276,11 +280,14 @@ tc4_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
                         tma_store_commit();
                     }
                     if (p.mode == 3) {
-                        // the branch's column window of the accumulator (atom 0 spans the whole tile and initialises it)
-                        const uint32_t w0 = smem_u32(Wsm + p.t_woff[yy][ai]), idw = make_idesc(128, p.t_nw[yy][ai]);
-                        const uint32_t dcol = acc + (uint32_t)p.t_ncol[yy][ai];
-                        for (int ks = 0; ks < p.t_ks[yy][ai]; ++ks) {
-                            umma_f16(dcol, desc_k_sw128(a0 + ks * 32u), desc_k_sw128(w0 + ks * 32u), idw, (ai | ks) ? 1u : 0u);
+                        // every (branch, tap) op of this window: rows shifted by the tap (whole frame slots: the SWIZZLE_128B phase is
+                        // kept), the branch's channels as the K range, its column window of the accumulator as D (op 0 spans the tile)
+                        for (int op = p.t_op0[yy][ai]; op < p.t_op0[yy][ai + 1]; ++op) {
+                            const uint32_t ar = a0 + (uint32_t)p.o_row[yy][op] * (uint32_t)p.slot * 128u + (uint32_t)p.o_k0[yy][op] * 32u;
+                            const uint32_t w0 = smem_u32(Wsm + p.o_woff[yy][op]), idw = make_idesc(128, p.o_nw[yy][op]);
+                            const uint32_t dcol = acc + (uint32_t)p.o_ncol[yy][op];
+                            for (int ks = 0; ks < p.o_ks[yy][op]; ++ks)
+                                umma_f16(dcol, desc_k_sw128(ar + ks * 32u), desc_k_sw128(w0 + ks * 32u), idw, (op | ks) ? 1u : 0u);
                         }
                     } else {
                         const uint32_t w0 = smem_u32(Wsm + (size_t)ai * p.Ntile * 128);

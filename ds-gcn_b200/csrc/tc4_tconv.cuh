@@ -18,7 +18,7 @@ struct TcAtom { int br, tap, map, tsh; };
 // weight tiles of one launch: per column tile y, per atom: [nw rows (output channel = n0 + ncol + row)] x [64 k (input channel = c0 + k)]
 // bf16 in the K-major SWIZZLE_128B layout; element = W[co, ci, tap] (forward) or W[k-side, n-side, tap] (data gradient)
 struct TcPackJob { const float* W; int lo, hi, tap, c0, nabs0, nw; unsigned off; };
-struct TcPackJobs { TcPackJob j[2 * G4_MAX_ATOMS]; int n, transposed, span_lo, N; const float* bias[8]; int blo[8], bhi[8], nb; };
+struct TcPackJobs { TcPackJob j[2 * G4_MAX_OPS]; int n, transposed, span_lo, N; const float* bias[8]; int blo[8], bhi[8], nb; };
 
 __global__ void __launch_bounds__(256) tc4_tconv_wpack_kernel(TcPackJobs jobs, unsigned char* out, float* cbias) {
     if ((int)blockIdx.x == jobs.n) {                      // folded bias per absolute output column (0 for the data gradient)
@@ -54,11 +54,15 @@ __global__ void __launch_bounds__(256) tc4_tconv_wpack_kernel(TcPackJobs jobs, u
 
 static inline long long tc4_tconv_wpack_bytes(const dsg_ms_conv_args& a) {
     (void)a;
-    return 2LL * G4_MAX_ATOMS * 128 * 128 + 256 * 4 + 1024;      // worst case: every atom a full-width tile, + folded bias
+    return 2LL * G4_MAX_OPS * 64 * 128 + 2LL * 128 * 128 + 256 * 4 + 2048;      // worst case: every op a 64-row tile + the full-width op 0 per column tile, + folded bias
 }
 
-// one launch: destination plane (qs, qp) of `out`
-static const char* tconv_launch(const dsg_ms_conv_args& a, int qs, int qp, dsg_stream_t st, bool* handled) {
+struct TcOp { int b, tap, map, tsh, c0, k0, ks, ncol, nw; };
+
+// one launch: destination plane (qs, qp) of `out`.  `windows`: load every 64-channel source column once per tile with its temporal
+// halo and let all (branch, tap) ops of the column read it at row offsets (narrow layers: four branches share one column, so the
+// tile's source frames cross the L2 -> shared-memory path 12 times instead of 48); else one F-frame atom per (branch, tap).
+static const char* tconv_launch(const dsg_ms_conv_args& a, int qs, int qp, bool windows, dsg_stream_t st, bool* handled) {
     *handled = false;
     const int nb = a.n_branches, s = a.stride;
     const int span_lo = a.br[0].lo, span_hi = a.br[nb - 1].hi, N = span_hi - span_lo;
@@ -81,22 +85,23 @@ static const char* tconv_launch(const dsg_ms_conv_args& a, int qs, int qp, dsg_s
     const int gy = (N + p.Ntile - 1) / p.Ntile;
     if (gy > 2) return nullptr;
     p.stats = a.stat_sum == nullptr ? 0 : (a.partner ? 2 : 1);
-    // ---- atoms: (branch, tap) pairs that reach this destination plane
     bool use_map1 = false;
     TcPackJobs jobs{};
     jobs.transposed = a.transposed; jobs.span_lo = span_lo; jobs.N = N; jobs.nb = nb;
     for (int b = 0; b < nb; ++b) { jobs.bias[b] = a.br[b].bias; jobs.blo[b] = a.br[b].lo; jobs.bhi[b] = a.br[b].hi; }
     unsigned woff_total = 0;
+    int max_nfr = p.F;
     for (int y = 0; y < gy; ++y) {
         const int n0 = span_lo + y * p.Ntile, n1 = (n0 + p.Ntile < span_hi) ? n0 + p.Ntile : span_hi;
         const int Ntp = ((n1 - n0) + 15) & ~15;
-        int cnt = 0;
-        unsigned woff = 0;
+        // ---- ops: (branch, tap, source column)
+        TcOp ops[G4_MAX_OPS];
+        int nops = 0;
         for (int b = 0; b < nb; ++b) {
             const int lo = a.br[b].lo, hi = a.br[b].hi, d = a.br[b].dilation;
             if (hi <= n0 || lo >= n1) continue;
             const int lo8 = lo & ~7;
-            if (hi - lo8 > ATOM_CH) return nullptr;
+            if (!windows && hi - lo8 > ATOM_CH) return nullptr;
             for (int tap = 0; tap < 3; ++tap) {
                 const int o = (tap - 1) * d;
                 int map = 0, tsh = 0;
@@ -109,32 +114,61 @@ static const char* tconv_launch(const dsg_ms_conv_args& a, int qs, int qp, dsg_s
                     if ((((qp - o) % s) + s) % s != 0) continue;
                     tsh = (qp - o) / s;
                 }
-                if (cnt >= G4_MAX_ATOMS) return nullptr;
                 use_map1 |= map == 1;
                 const int c_lo = lo > n0 ? lo : n0, c_hi = hi < n1 ? hi : n1;
-                int ncol = (c_lo - n0) & ~15, nw = (((c_hi - n0) + 15) & ~15) - ncol;
-                if (cnt == 0) { ncol = 0; nw = Ntp; }      // atom 0 initialises the whole accumulator tile
-                p.t_map[y][cnt] = (short)map; p.t_tsh[y][cnt] = (short)tsh; p.t_c0[y][cnt] = lo8;
-                p.t_ks[y][cnt] = (short)((hi - lo8 + 15) / 16); p.t_ncol[y][cnt] = (short)ncol; p.t_nw[y][cnt] = (short)nw;
-                p.t_woff[y][cnt] = woff;
-                TcPackJob& J = jobs.j[jobs.n++];
-                J.W = a.br[b].W; J.lo = lo; J.hi = hi; J.tap = tap; J.c0 = lo8; J.nabs0 = n0 + ncol; J.nw = nw; J.off = woff_total + woff;
-                woff += (unsigned)nw * 128u;
-                ++cnt;
+                const int ncol = (c_lo - n0) & ~15, nw = (((c_hi - n0) + 15) & ~15) - ncol;
+                if (windows) {
+                    for (int c0 = lo & ~(ATOM_CH - 1); c0 < hi; c0 += ATOM_CH) {      // 64-aligned source columns the branch touches
+                        const int klo = lo > c0 ? lo : c0, khi = hi < c0 + ATOM_CH ? hi : c0 + ATOM_CH;
+                        if (nops >= G4_MAX_OPS) return nullptr;
+                        const int k0 = (klo - c0) / 16;
+                        ops[nops++] = TcOp{b, tap, map, tsh, c0, k0, (khi - c0 + 15) / 16 - k0, ncol, nw};
+                    }
+                } else {
+                    if (nops >= G4_MAX_OPS) return nullptr;
+                    ops[nops++] = TcOp{b, tap, map, tsh, lo8, 0, (hi - lo8 + 15) / 16, ncol, nw};
+                }
             }
         }
-        if (cnt == 0) {                                    // no tap reaches this plane: one all-zero atom keeps the pipeline uniform
-            p.t_map[y][0] = 0; p.t_tsh[y][0] = 0; p.t_c0[y][0] = span_lo & ~7; p.t_ks[y][0] = 1; p.t_ncol[y][0] = 0; p.t_nw[y][0] = (short)Ntp;
-            p.t_woff[y][0] = 0;
-            TcPackJob& J = jobs.j[jobs.n++];
-            J.W = a.br[0].W; J.lo = 0; J.hi = 0; J.tap = 0; J.c0 = 0; J.nabs0 = n0; J.nw = Ntp; J.off = woff_total;
-            woff = (unsigned)Ntp * 128u;
-            cnt = 1;
+        if (nops == 0) ops[nops++] = TcOp{-1, 0, 0, 0, span_lo & ~7, 0, 1, 0, Ntp};      // no tap reaches this plane: one all-zero op
+        // ---- atoms: windows = ops grouped by (map, column); else one atom per op
+        int natoms = 0, nplaced = 0;
+        bool placed[G4_MAX_OPS] = {false};
+        unsigned woff = 0;
+        for (int i = 0; i < nops; ++i) {
+            if (placed[i]) continue;
+            if (natoms >= G4_MAX_ATOMS) return nullptr;
+            int tmin = ops[i].tsh, tmax = ops[i].tsh;
+            if (windows)
+                for (int j = i + 1; j < nops; ++j)
+                    if (ops[j].map == ops[i].map && ops[j].c0 == ops[i].c0) { tmin = ops[j].tsh < tmin ? ops[j].tsh : tmin; tmax = ops[j].tsh > tmax ? ops[j].tsh : tmax; }
+            p.t_map[y][natoms] = (short)ops[i].map; p.t_c0[y][natoms] = ops[i].c0; p.t_tsh[y][natoms] = (short)tmin;
+            p.t_nfr[y][natoms] = (short)(p.F + tmax - tmin);
+            if (p.t_nfr[y][natoms] > max_nfr) max_nfr = p.t_nfr[y][natoms];
+            p.t_op0[y][natoms] = (short)nplaced;
+            for (int j = i; j < nops; ++j) {
+                if (placed[j] || (j != i && !(windows && ops[j].map == ops[i].map && ops[j].c0 == ops[i].c0))) continue;
+                placed[j] = true;
+                TcOp o = ops[j];
+                if (nplaced == 0) { o.ncol = 0; o.nw = Ntp; }                      // op 0 initialises the whole accumulator tile
+                p.o_row[y][nplaced] = (short)(o.tsh - tmin); p.o_k0[y][nplaced] = (short)o.k0; p.o_ks[y][nplaced] = (short)o.ks;
+                p.o_ncol[y][nplaced] = (short)o.ncol; p.o_nw[y][nplaced] = (short)o.nw; p.o_woff[y][nplaced] = woff;
+                TcPackJob& J = jobs.j[jobs.n++];
+                if (o.b >= 0) { J.W = a.br[o.b].W; J.lo = a.br[o.b].lo; J.hi = a.br[o.b].hi; }
+                else { J.W = nullptr; J.lo = 0; J.hi = 0; }
+                J.tap = o.tap; J.c0 = o.c0 + o.k0 * 16; J.nabs0 = n0 + o.ncol; J.nw = o.nw; J.off = woff_total + woff;
+                woff += (unsigned)o.nw * 128u;
+                ++nplaced;
+            }
+            ++natoms;
         }
-        p.t_n[y] = cnt;
+        p.t_op0[y][natoms] = (short)nplaced;
+        p.t_n[y] = natoms;
         p.t_wbytes[y] = (woff + 1023u) & ~1023u;
         woff_total += p.t_wbytes[y];
     }
+    p.t_stage = (unsigned)max_nfr * (unsigned)p.slot * 128u;
+    p.t_stage = (p.t_stage + 1023u) & ~1023u;
     p.natoms1 = 0;
     p.natoms = use_map1 ? 1 : 0;
     const unsigned wb = p.t_wbytes[0] > p.t_wbytes[1] ? p.t_wbytes[0] : p.t_wbytes[1];
@@ -144,14 +178,15 @@ static const char* tconv_launch(const dsg_ms_conv_args& a, int qs, int qp, dsg_s
     bool fit = false;
     for (int OB = 2; OB >= 1 && !fit; --OB) {
         const unsigned fixed = wb + OB * ob1 * (p.stats == 2 ? 2u : 1u) + 1024u + ((cf_bytes + 1023u) & ~1023u) + 1024u;
-        if (fixed + 3u * ATOM_BYTES > budget) continue;
-        int S = (int)((budget - fixed) / ATOM_BYTES);
+        const unsigned min_stages = windows ? 2u : 3u;
+        if (fixed + min_stages * p.t_stage > budget) continue;
+        int S = (int)((budget - fixed) / p.t_stage);
         if (S > G4_MAX_STAGES) S = G4_MAX_STAGES;
-        if (OB == 2 && S < 4) continue;
+        if (OB == 2 && S < (windows ? 3 : 4)) continue;
         p.S = S; p.OB = OB;
         p.off_w = 0;
         p.off_a = wb;
-        p.off_out = p.off_a + (unsigned)S * ATOM_BYTES;
+        p.off_out = p.off_a + (unsigned)S * p.t_stage;
         p.out_bytes = ob1;
         p.off_stat = p.off_out + OB * ob1;
         p.off_ones = p.off_stat + (p.stats == 2 ? OB * ob1 : 0u);
@@ -235,14 +270,23 @@ static const char* launch_ms_conv_tc4(const dsg_ms_conv_args& a, dsg_stream_t st
     if ((a.stat_sum == nullptr) != (a.stat_sq == nullptr)) return "ms_conv: stat_sum and stat_sq go together";
     if (a.n_samples <= 0 || a.T_in <= 0 || a.T_out <= 0) { *handled = true; return nullptr; }
     if (!encode_fn()) return nullptr;
-    if (!a.transposed || a.stride == 1) return tconv_launch(a, 1, 0, st, handled);
+    static const bool win_on = [] { const char* e = getenv("DSG_MS_WINDOWS"); return !(e && e[0] == '0'); }();
+    auto launch = [&](const dsg_ms_conv_args& aa, int qs, int qp, bool* h) -> const char* {
+        // shared windows when they fit the shared-memory budget (narrow layers), else one atom per (branch, tap)
+        if (win_on) {
+            const char* e = tconv_launch(aa, qs, qp, true, st, h);
+            if (e || *h) return e;
+        }
+        return tconv_launch(aa, qs, qp, false, st, h);
+    };
+    if (!a.transposed || a.stride == 1) return launch(a, 1, 0, handled);
     // data gradient through a temporal stride: one launch per parity plane of the destination (all of them or none)
     bool h0 = false, h1 = false;
-    const char* e = tconv_launch(a, a.stride, 0, st, &h0);
+    const char* e = launch(a, a.stride, 0, &h0);
     if (e || !h0) return e;
     dsg_ms_conv_args a1 = a;                               // the second plane packs its own weight tiles behind the first plane's
     a1.wpack = reinterpret_cast<unsigned char*>(a.wpack) + tc4_tconv_wpack_bytes(a);
-    e = tconv_launch(a1, a.stride, 1, st, &h1);
+    e = launch(a1, a.stride, 1, &h1);
     if (e) return e;
     if (!h1) return "ms_conv: the second parity plane was declined after the first was launched";
     *handled = true;
