@@ -140,6 +140,9 @@ def grad_cat(m, key, params, shape, grads):
         for p in params:
             grads[p] = p.grad
         return g
+    if len(params) == 1 and _sink(params[0]) is not None:       # a "group" of one (no `down` branch): the parameter's own flat view
+        grads[params[0]] = params[0].grad
+        return params[0].grad.view(shape)
     g = torch.zeros(shape, dtype=torch.float32, device=params[0].device)
     flat, o = g.view(-1), 0
     for p in params:
