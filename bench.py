@@ -477,6 +477,8 @@ def main():
             graph = None
             torch.cuda.synchronize()
 
+    used_graph = graph is not None
+
     def run_step(i):
         if graph is not None:
             sx.copy_(dev_x[i % 2], non_blocking=True)       # device-to-device refresh of the static input (inputs differ per step)
@@ -659,7 +661,7 @@ def main():
             extra["reference_gpu_eager"] = dict(unavailable=f"{type(e).__name__}: {str(e)[:200]}")
     line = dict(metric=metric, value=value, unit=unit, n_gpus=world, steps=args.steps, warmup=args.warmup, ms_per_step=ms,
                 higher_is_better=True, scaling="weak", vs_baseline=None, dtype=args.dtype, data="synthetic",
-                config=dict(workload=workload, clips_per_gpu=B, M=M_, T=T_, V=V_, C=C_, parallelism=f"dp{world}", cuda_graph=graph is not None,
+                config=dict(workload=workload, clips_per_gpu=B, M=M_, T=T_, V=V_, C=C_, parallelism=f"dp{world}", cuda_graph=used_graph,
                             allreduce=(f"{len(gb.buckets)} flat buckets ({gb.grad_bytes()} B), NCCL AVG launched from autograd hooks during backward"
                                        if (train and world > 1) else None),
                             cache="inputs + activations per step (~GBs) exceed the 126 MB L2; two input batches alternate"),
