@@ -50,6 +50,7 @@ def parse():
     p.add_argument("--impl", default="ours", choices=["ours", "reference"])
     p.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
     p.add_argument("--no-graph", action="store_true")
+    p.add_argument("--e2e-eager", action="store_true", help="time the e2e leg launch by launch (train_step + OptimizerHook sequence) instead of GraphedTrainStep")
     p.add_argument("--buckets", type=int, default=3, help="gradient buckets (all-reduce overlapped with backward)")
     p.add_argument("--sweep", default=None, choices=["coco"],
                    help="BASELINE config 4: large-batch inference sweep on 2-D HRNet keypoints (COCO layout, V=17, pixel-unit inputs), "
@@ -513,8 +514,22 @@ def main():
         ms = float(t.item())
     value = world * B / (ms * 1e-3)
 
-    # ---- e2e: public API with host buffers (H2D of the batch from pinned memory, D2H of the loss / scores)
+    # ---- e2e: public API with host buffers (H2D of the batch from pinned memory, D2H of the logged scalars / scores).
+    #      Training goes through dsgcn_b200.train.GraphedTrainStep — the whole iteration (forward, loss, backward with the bucketed
+    #      all-reduce, update) as one captured graph replayed on static inputs; `--e2e-eager` times RecognizerGCN.train_step + the
+    #      OptimizerHook sequence launch by launch instead.
+    gstep = None
+    if train and not args.e2e_eager and not args.no_graph:
+        try:
+            gstep = dsgcn_b200.train.GraphedTrainStep(model, opt, dev_x[0], dev_y[0])
+        except Exception as e:
+            print(f"[bench] GraphedTrainStep failed ({type(e).__name__}: {str(e)[:300]}); eager e2e", file=sys.stderr)
+            gstep = None
+            torch.cuda.synchronize()
+
     def e2e_step(i):
+        if gstep is not None:
+            return gstep(host_x[i % 2], host_y[i % 2])["log_vars"]["loss"]      # pinned host batch in, python floats out
         x = host_x[i % 2].to(dev, non_blocking=True)
         y = host_y[i % 2].to(dev, non_blocking=True)
         if train:
@@ -538,6 +553,10 @@ def main():
         t = torch.tensor([e2e_ms], device=dev)
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
         e2e_ms = float(t.item())
+    e2e_graph = gstep is not None
+    if gstep is not None:
+        gstep.release()
+        gstep = None
     _trace("e2e done")
     h2d = host_x[0].numel() * 4 + host_y[0].numel() * 8
     d2h = 16 if train else B * NUM_CLASSES * 4      # train: top1, top5, loss_cls, loss (one packed copy)
@@ -665,7 +684,9 @@ def main():
                             allreduce=(f"{len(gb.buckets)} flat buckets ({gb.grad_bytes()} B), NCCL AVG launched from autograd hooks during backward"
                                        if (train and world > 1) else None),
                             cache="inputs + activations per step (~GBs) exceed the 126 MB L2; two input batches alternate"),
-                e2e=dict(value=world * B / (e2e_ms * 1e-3), unit=unit, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, ms_per_step=e2e_ms),
+                e2e=dict(value=world * B / (e2e_ms * 1e-3), unit=unit, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, ms_per_step=e2e_ms,
+                         api="dsgcn_b200.train.GraphedTrainStep (captured iteration, host batch in, logged scalars out)" if e2e_graph
+                         else ("RecognizerGCN.train_step + zero_grad/backward/step" if train else "RecognizerGCN.forward(return_loss=False)")),
                 gpu_launches=launches_per_step * args.steps, abi_calls_per_step=launches_per_step, kernels_per_step_ncu=own_kernels, clocks=clocks, roofline=roofline, cpu_baseline=cpu, extra=extra)
     print(json.dumps(line))
 

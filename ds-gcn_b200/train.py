@@ -38,6 +38,61 @@ def load_checkpoint(model, filename, map_location="cpu", strict=False):
     return ckpt
 
 
+class GraphedTrainStep:
+    """One whole training iteration — forward, loss, backward (with the bucketed all-reduce), optimizer update — captured in a CUDA
+    graph and replayed on static buffers: what the OptimizerHook sequence `zero_grad(); train_step(); loss.backward(); step()` costs
+    in ~430 eager launches becomes one graph launch.  Call it with the batch (host-pinned or device tensors of the captured shapes);
+    it copies the batch into the static inputs, replays, and returns the same dict `RecognizerGCN.train_step` returns (`log_vars`
+    read back with ONE 16-byte device-to-host copy).  The learning rate is read from device memory by `FlatSGD`, so schedules
+    work across replays (`optimizer.set_lr`).  Shapes are fixed at construction; BatchNorm buffers and parameters update in place.
+    """
+
+    def __init__(self, model, optimizer, keypoint, label, warmup=3):
+        if not keypoint.is_cuda:
+            raise ValueError("construct GraphedTrainStep with device tensors of the batch shape")
+        self.model, self.optimizer = model, optimizer
+        self.kp, self.lb = keypoint.clone(), label.clone()
+        self.names = None
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):                 # eager warm-up on a side stream (autograd nodes must not be tied to the default stream)
+            for _ in range(max(warmup, 1)):
+                self._iteration()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self._iteration()
+        torch.cuda.synchronize()
+
+    def _iteration(self):
+        import torch.distributed as dist
+        self.optimizer.zero_grad()
+        losses = self.model(self.kp, self.lb, return_loss=True)
+        log = {k: v.mean() for k, v in losses.items()}
+        loss = sum(v for k, v in log.items() if "loss" in k)
+        log["loss"] = loss
+        self.names = list(log)
+        packed = torch.stack([log[k].detach().float().reshape(()) for k in self.names])
+        if dist.is_available() and dist.is_initialized():
+            packed = packed / dist.get_world_size()
+            dist.all_reduce(packed)
+        self.packed, self.loss = packed, loss
+        loss.backward()
+        self.optimizer.step()
+
+    def __call__(self, keypoint, label):
+        self.kp.copy_(keypoint, non_blocking=True)
+        self.lb.copy_(label, non_blocking=True)
+        self.graph.replay()
+        vals = self.packed.tolist()                   # the one host synchronisation of the iteration
+        return dict(loss=self.loss, log_vars=OrderedDict(zip(self.names, vals)), num_samples=len(keypoint))
+
+    def release(self):
+        """Drop the captured graph (before destroying a process group whose collectives it holds)."""
+        self.graph.reset()
+
+
 class Runner:
     """Epoch-based loop with the hook points of EpochBasedSparseRunner.  `hooks`: objects with any of before_run, before_train_epoch,
     before_train_iter, after_train_iter, after_train_epoch, after_run (called with the runner)."""

@@ -178,3 +178,52 @@ def test_head_pooling_kernel(dtype):
     ref.backward(g)
     err = (feat.grad.float() - ref_in.grad).norm() / ref_in.grad.norm()
     assert err < (1e-5 if dtype == torch.float32 else 5e-3), float(err)
+
+
+@pytest.mark.gpu
+def test_graphed_train_step_matches_eager():
+    """train.GraphedTrainStep (the whole iteration as one CUDA graph on static buffers) gives the same losses and parameters as the
+    eager OptimizerHook sequence zero_grad / train_step / backward / step."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from dsgcn_b200 import parallel, train as TR
+    NORTH_STAR = dict(gcn_type="dgphgcn1", gcn_ratio=0.125, gcn_node_attention=True, gcn_edge_attention=True, gcn_decompose=True,
+                      gcn_subset_wise=True, gcn_ctr="T", gcn_ada="T", tcn_type="dgmstcn",
+                      graph_cfg=dict(layout="nturgb+d", mode="random", num_filter=3, init_off=.04, init_std=.02),
+                      tcn_ms_cfg=[(3, 1), (3, 2), (3, 3), (3, 4), ("max", 3), "1x1"])
+    dsgcn_b200._lib._testing_use_library(None)
+    dev = torch.device("cuda:0")
+    sgd = dict(lr=0.01, momentum=0.9, weight_decay=5e-4, nesterov=True)
+    models, opts = [], []
+    for _ in range(2):
+        torch.manual_seed(0); np.random.seed(0)
+        m = dsgcn_b200.RecognizerGCN(backbone=dict(type="DGSTGCN", **{**NORTH_STAR, "base_channels": 16, "gcn_ratio": 0.5}),
+                                     cls_head=dict(type="GCNHead", num_classes=10, in_channels=64)).to(dev).train()
+        with torch.no_grad():
+            for n_, p_ in m.named_parameters():
+                if n_.rsplit(".", 1)[-1] in ("alpha", "beta", "add_coeff"):
+                    p_.normal_(0, 0.1)
+        models.append(m)
+        opts.append(parallel.FlatSGD(parallel.GradBuckets(m, n_buckets=3), **sgd))
+    models[1].load_state_dict(models[0].state_dict())
+    g = torch.Generator().manual_seed(1)
+    xs = [torch.randn(4, 1, 2, 16, 25, 3, generator=g).pin_memory() for _ in range(3)]
+    ys = [torch.randint(0, 10, (4, 1), generator=g).pin_memory() for _ in range(3)]
+    sd0 = {k: v.clone() for k, v in models[0].state_dict().items()}
+    step = TR.GraphedTrainStep(models[1], opts[1], xs[0].to(dev), ys[0].to(dev), warmup=2)
+    models[1].load_state_dict(sd0)                           # warm-up + capture advanced the weights: start both from the same point
+    for bk in opts[1].gb.buckets:
+        bk.flat_m.zero_()
+    for i in range(3):
+        opts[0].zero_grad()
+        out = models[0].train_step(dict(keypoint=xs[i].to(dev), label=ys[i].to(dev)), opts[0])
+        out["loss"].backward()
+        opts[0].step()
+        got = step(xs[i], ys[i])
+        assert got["log_vars"]["loss"] == pytest.approx(out["log_vars"]["loss"], rel=2e-2), i
+        assert set(got["log_vars"]) == set(out["log_vars"])
+    p0, p1 = dict(models[0].named_parameters()), dict(models[1].named_parameters())
+    num = sum(float((p0[k] - p1[k]).double().pow(2).sum()) for k in p0)
+    den = sum(float(p0[k].double().pow(2).sum()) for k in p0)
+    assert (num / den) ** 0.5 < 1e-2
+    step.release()
