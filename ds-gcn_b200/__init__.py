@@ -7,8 +7,8 @@ Device side: hand-written sm_100a CUDA kernels behind a C ABI (include/dsgcn_b20
 from . import _lib, ops  # noqa: F401
 from . import functional, graph, modules  # noqa: F401,E402
 from .graph import Graph  # noqa: F401,E402
-from .modules import (DGBlock, DGSTGCN, STGCN, STGCNBlock, dgmstcn, dgphgcn1, get_compute_dtype, mstcn,  # noqa: F401,E402
-                      set_compute_dtype, unit_gcn, unit_tcn)
+from .modules import (CTRGC, CTRGCN, CTRGCNBlock, DGBlock, DGSTGCN, MSTCN, STGCN, STGCNBlock, dggcn, dghgcn, dgmstcn,  # noqa: F401,E402
+                      dgphgcn, dgphgcn1, get_compute_dtype, mstcn, set_compute_dtype, unit_ctrgcn, unit_gcn, unit_tcn)
 from . import recognizer  # noqa: F401,E402
 from .recognizer import (BACKBONES, HEADS, LOSSES, MODELS, RECOGNIZERS, CrossEntropyLoss, GCNHead, RecognizerGCN,  # noqa: F401,E402
                          build_backbone, build_head, build_loss, build_model, build_recognizer)

@@ -56,7 +56,13 @@ class TopologyArgs(C.Structure):
                 ("node_type", vp), ("edge_type", vp), ("A", vp), ("alpha", vp), ("beta", vp),
                 ("We", vp), ("be", vp), ("adyn", vp), ("adyn_dtype", c_int), ("S", vp),
                 ("dadyn", vp), ("dH", vp), ("dA", vp), ("dalpha", vp), ("dbeta", vp), ("dWe", vp), ("dbe", vp),
-                ("dH_bf16", vp)]
+                ("dH_bf16", vp), ("variant", c_int), ("subset_wise", c_int)]
+
+
+class CtrTopologyArgs(C.Structure):
+    _fields_ = [("H", vp), ("ld_h", c_ll), ("n_samples", c_int), ("V", c_int), ("R", c_int), ("C", c_int),
+                ("A", vp), ("alpha", vp), ("W4", vp), ("b4", vp), ("adyn", vp), ("adyn_dtype", c_int),
+                ("dadyn", vp), ("dH", vp), ("dH_bf16", vp), ("dA", vp), ("dalpha", vp), ("dW4", vp), ("db4", vp)]
 
 
 class GraphAggArgs(C.Structure):
@@ -118,6 +124,8 @@ EXPORTS = {
     "dsg_tmean2": (c_int, [vp, c_int, c_ll, c_int, c_int, c_int, c_int, vp, vp, vp]),
     "dsg_topology_fwd": (c_int, [C.POINTER(TopologyArgs), vp]),
     "dsg_topology_bwd": (c_int, [C.POINTER(TopologyArgs), vp]),
+    "dsg_ctr_topology_fwd": (c_int, [C.POINTER(CtrTopologyArgs), vp]),
+    "dsg_ctr_topology_bwd": (c_int, [C.POINTER(CtrTopologyArgs), vp]),
     "dsg_graph_agg": (c_int, [C.POINTER(GraphAggArgs), vp]),
     "dsg_graph_agg_dadj": (c_int, [C.POINTER(GraphAggDadjArgs), vp]),
     "dsg_ms_combine_fwd": (c_int, [C.POINTER(MsCombineArgs), vp]),

@@ -10,6 +10,7 @@
 #include "graph_agg.cuh"
 #include "ms_temporal_tc.cuh"
 #include "topology.cuh"
+#include "ctr_topology.cuh"
 #include "misc.cuh"
 #include "ms_mix.cuh"
 #include <stdio.h>
@@ -162,6 +163,15 @@ int dsg_topology_fwd(const dsg_topology_args* a, void* stream) {
 int dsg_topology_bwd(const dsg_topology_args* a, void* stream) {
     if (!a) return fail("dsg_topology_bwd", "bad arguments");
     DSG_RET("dsg_topology_bwd", dsg::launch_topology(*a, true, (dsg_stream_t)stream));
+}
+
+int dsg_ctr_topology_fwd(const dsg_ctr_topology_args* a, void* stream) {
+    if (!a || !dtype_ok(a->adyn_dtype)) return fail("dsg_ctr_topology_fwd", "bad arguments");
+    DSG_RET("dsg_ctr_topology_fwd", dsg::launch_ctr_topology(*a, false, (dsg_stream_t)stream));
+}
+int dsg_ctr_topology_bwd(const dsg_ctr_topology_args* a, void* stream) {
+    if (!a || !a->dadyn || !a->dH) return fail("dsg_ctr_topology_bwd", "bad arguments");
+    DSG_RET("dsg_ctr_topology_bwd", dsg::launch_ctr_topology(*a, true, (dsg_stream_t)stream));
 }
 
 int dsg_graph_agg(const dsg_graph_agg_args* a, void* stream) {

@@ -34,7 +34,10 @@ DSG_D void topo_load_features(const dsg_topology_args& a, const TopoSmem& sm, in
     for (int idx = threadIdx.x; idx < 3 * R * V; idx += blockDim.x) {
         int c = idx % R, v = (idx / R) % V, k = idx / (R * V);
         float f1, f2;
-        if (k < 2) {
+        if (a.variant == 1) {                    // plain DG-GCN unit: H = [conv1 (3R) | conv2 (3R)]
+            f1 = h[(long long)v * a.ld_h + k * R + c];
+            f2 = h[(long long)v * a.ld_h + 3 * R + k * R + c];
+        } else if (k < 2) {
             f1 = h[(long long)v * a.ld_h + k * R + c];
             f2 = h[(long long)v * a.ld_h + 2 * R + k * R + c];
         } else {
@@ -73,9 +76,11 @@ __global__ void __launch_bounds__(TP_THREADS) topology_fwd_kernel(dsg_topology_a
     float* We_s = reinterpret_cast<float*>(smem_raw) + TopoSmem::floats(R, V);
     float* be_s = We_s + 15 * R * (R + 1);
     const int tid = threadIdx.x;
-    topo_stage_we(a, We_s, be_s);
-    const float al0 = a.alpha[0], al1 = a.alpha[1], al2 = a.alpha[2];
-    const float be0 = a.beta[0], be1 = a.beta[1], be2 = a.beta[2];
+    const bool plain = a.variant == 1;
+    if (!plain) topo_stage_we(a, We_s, be_s);
+    const int i1 = a.subset_wise ? 1 : 0, i2 = a.subset_wise ? 2 : 0;    // not subset-wise: alpha[0] / beta[0] scale every subset
+    const float al0 = a.alpha[0], al1 = a.alpha[i1], al2 = a.alpha[i2];
+    const float be0 = a.beta[0], be1 = a.beta[i1], be2 = a.beta[i2];
     for (int n = blockIdx.x; n < a.n_samples; n += gridDim.x) {
         __syncthreads();
         topo_load_features(a, sm, n);
@@ -103,16 +108,18 @@ __global__ void __launch_bounds__(TP_THREADS) topology_fwd_kernel(dsg_topology_a
         __syncthreads();
         T* out = reinterpret_cast<T*>(a.adyn) + (long long)n * VV * KC;
         // subsets 0 and 2: tanh of a feature difference; thread = (pair, channel), channel fastest
-        for (int idx = tid; idx < VV * 2 * R; idx += TP_THREADS) {
-            const int cc = idx % (2 * R), uw = idx / (2 * R);
-            const int k = cc < R ? 0 : 2, c = cc < R ? cc : cc - R;
+        const int nd = plain ? 3 : 2;           // subsets whose tanh argument is the plain feature difference
+        for (int idx = tid; idx < VV * nd * R; idx += TP_THREADS) {
+            const int cc = idx % (nd * R), uw = idx / (nd * R);
+            const int kk = cc / R, c = cc - kk * R;
+            const int k = plain ? kk : 2 * kk;
             const int u = uw / V, w = uw - u * V;
             const float th = tanhf(sm.x1[(k * R + c) * V + u] - sm.x2[(k * R + c) * V + w]);
-            const float v = a.A[k * VV + uw] + (k ? al2 : al0) * th + (k ? be2 : be0) * sm.S[k * VV + uw];
+            const float v = a.A[k * VV + uw] + (k == 0 ? al0 : k == 1 ? al1 : al2) * th + (k == 0 ? be0 : k == 1 ? be1 : be2) * sm.S[k * VV + uw];
             stf<T>(out + (long long)uw * KC + k * R + c, v);
         }
         // subset 1: edge-typed linear; consecutive threads = consecutive output channels of one pair
-        for (int idx = tid; idx < VV * R; idx += TP_THREADS) {
+        for (int idx = tid; !plain && idx < VV * R; idx += TP_THREADS) {
             const int c = idx % R, uw = idx / R;
             const int u = uw / V, w = uw - u * V;
             const float th = tanhf(topo_arg1(sm, We_s, be_s, R, V, a.edge_type[uw], c, u, w));
@@ -142,8 +149,12 @@ __global__ void __launch_bounds__(TP_BWD_THREADS) topology_bwd_kernel(dsg_topolo
     float* be_s = We_s + 15 * R * (R + 1);
     const int tid = threadIdx.x, NT = blockDim.x;
     unsigned char* et_s = reinterpret_cast<unsigned char*>(be_s + 15 * R);   // [V*V] edge types
-    topo_stage_we(a, We_s, be_s);
-    for (int idx = tid; idx < VV; idx += NT) et_s[idx] = (unsigned char)a.edge_type[idx];
+    const bool plain = a.variant == 1;
+    const int sw = a.subset_wise ? 1 : 0;
+    if (!plain) {
+        topo_stage_we(a, We_s, be_s);
+        for (int idx = tid; idx < VV; idx += NT) et_s[idx] = (unsigned char)a.edge_type[idx];
+    }
     for (int idx = tid; idx < 3 * VV + 15 * R * R + 15 * R; idx += NT) dA_acc[idx] = 0.f;   // contiguous block
     if (tid < 8) red[tid] = 0.f;
 
@@ -179,7 +190,7 @@ __global__ void __launch_bounds__(TP_BWD_THREADS) topology_bwd_kernel(dsg_topolo
             float dot = 0.f;
             for (int u = 0; u < V; ++u) dot = fmaf(sm.G[(k * V + u) * V + w], sm.S[(k * V + u) * V + w], dot);
             atomicAdd(&red[3 + k], dot);
-            const float bk = a.beta[k];
+            const float bk = a.beta[sw * k];
             for (int u = 0; u < V; ++u) {
                 int i = (k * V + u) * V + w;
                 sm.G[i] = bk * sm.S[i] * (sm.G[i] - dot);
@@ -188,7 +199,7 @@ __global__ void __launch_bounds__(TP_BWD_THREADS) topology_bwd_kernel(dsg_topolo
         __syncthreads();
         // (3) gram backward + subsets 0 and 2 of the tanh branch; thread per (k,c,v), no atomics:
         //     dx1[k,c,u] = sum_w dG[u,w] x2[c,w] + sum_w h[c,u,w];  dx2[k,c,w] = sum_u dG[u,w] x1[c,u] - sum_u h[c,u,w]
-        float my_dalpha0 = 0.f, my_dalpha2 = 0.f;
+        float my_dalpha0 = 0.f, my_dalpha2 = 0.f, my_dalpha1 = 0.f;
         for (int idx = tid; idx < 3 * R * V; idx += NT) {
             int c = idx % R, v = (idx / R) % V, k = idx / (R * V);
             float s1 = 0.f, s2 = 0.f;
@@ -198,8 +209,8 @@ __global__ void __launch_bounds__(TP_BWD_THREADS) topology_bwd_kernel(dsg_topolo
                 s1 = fmaf(sm.G[(k * V + v) * V + o], x2r[o], s1);      // u=v, w=o
                 s2 = fmaf(sm.G[(k * V + o) * V + v], x1r[o], s2);      // u=o, w=v
             }
-            if (k != 1) {
-                const float al = a.alpha[k];
+            if (k != 1 || plain) {
+                const float al = a.alpha[sw * k];
                 float da = 0.f;
                 for (int o = 0; o < V; ++o) {
                     float th = tanhf(x1r[v] - x2r[o]);                  // pair (u=v, w=o)
@@ -210,7 +221,7 @@ __global__ void __launch_bounds__(TP_BWD_THREADS) topology_bwd_kernel(dsg_topolo
                     float gg2 = g[(long long)(o * V + v) * KC + k * R + c];
                     s2 = fmaf(-al * (1.f - th2 * th2), gg2, s2);
                 }
-                if (k == 0) my_dalpha0 += da; else my_dalpha2 += da;
+                if (k == 0) my_dalpha0 += da; else if (k == 1) my_dalpha1 += da; else my_dalpha2 += da;
             }
             dx1[(k * R + c) * V + v] = s1;
             dx2[(k * R + c) * V + v] = s2;
@@ -224,11 +235,10 @@ __global__ void __launch_bounds__(TP_BWD_THREADS) topology_bwd_kernel(dsg_topolo
         //     (b) dWe[e][o][i] += h[w][o] * d1[w][i], dbe[e][o] += h[w][o]   (thread owns (o,i): no atomics)
         //         dd1[w][i] = sum_o We[e][o][i] h[w][o] -> dx2[1][i][w] -= dd1, dbuf = dd1
         //     with d1[w][i] = x1[1][i][u] - x2[1][i][w] formed on the fly
-        float my_dalpha1 = 0.f;
-        const float al1 = a.alpha[1];
+        const float al1 = a.alpha[sw];
         const float* x1b = sm.x1 + R * V;
         const float* x2b = sm.x2 + R * V;
-        for (int u = 0; u <= V; ++u) {
+        for (int u = 0; !plain && u <= V; ++u) {
             if (u > 0 && tid < R) {                                     // dx1[1][i][u-1] += sum_w dd1[w][i]
                 float sacc = 0.f;
                 for (int ww = 0; ww < V; ++ww) sacc += dbuf[ww * R + tid];
@@ -268,12 +278,14 @@ __global__ void __launch_bounds__(TP_BWD_THREADS) topology_bwd_kernel(dsg_topolo
         my_dalpha1 = warp_sum(my_dalpha1);
         if ((tid & 31) == 0) atomicAdd(&red[1], my_dalpha1);
         __syncthreads();
-        // (5) write dH[n][v][9R]
+        // (5) write dH[n][v][9R]  (plain variant: [v][6R] = dx1 | dx2)
         float* dh = a.dH + (long long)n * V * a.ld_h;
-        for (int idx = tid; idx < V * 9 * R; idx += NT) {
-            int col = idx % (9 * R), v = idx / (9 * R);
+        const int HC = plain ? 6 * R : 9 * R;
+        for (int idx = tid; idx < V * HC; idx += NT) {
+            int col = idx % HC, v = idx / HC;
             float val;
-            if (col < 2 * R) val = dx1[col * V + v];
+            if (plain) val = col < 3 * R ? dx1[col * V + v] : dx2[(col - 3 * R) * V + v];
+            else if (col < 2 * R) val = dx1[col * V + v];
             else if (col < 4 * R) val = dx2[(col - 2 * R) * V + v];
             else {
                 int q = col - 4 * R, c = q / 5, ty = q - c * 5;
@@ -285,9 +297,11 @@ __global__ void __launch_bounds__(TP_BWD_THREADS) topology_bwd_kernel(dsg_topolo
     }
     __syncthreads();
     for (int idx = tid; idx < 3 * VV; idx += NT) atomicAdd(a.dA + idx, dA_acc[idx]);
-    for (int idx = tid; idx < 15 * R * R; idx += NT) atomicAdd(a.dWe + idx, dWe_acc[idx]);
-    for (int idx = tid; idx < 15 * R; idx += NT) atomicAdd(a.dbe + idx, dbe_acc[idx]);
-    if (tid < 3) { atomicAdd(a.dalpha + tid, red[tid]); atomicAdd(a.dbeta + tid, red[3 + tid]); }
+    if (!plain) {
+        for (int idx = tid; idx < 15 * R * R; idx += NT) atomicAdd(a.dWe + idx, dWe_acc[idx]);
+        for (int idx = tid; idx < 15 * R; idx += NT) atomicAdd(a.dbe + idx, dbe_acc[idx]);
+    }
+    if (tid < 3) { atomicAdd(a.dalpha + sw * tid, red[tid]); atomicAdd(a.dbeta + sw * tid, red[3 + tid]); }
 }
 
 static inline size_t topo_bwd_smem_floats(int R, int V) {

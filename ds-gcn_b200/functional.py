@@ -251,6 +251,13 @@ class BNBack:
 # dgphgcn1  (spatial unit with the dynamic semantic adjacency)
 # ------------------------------------------------------------------------------------------------
 
+def _topo_params(m):
+    """weights / biases of the topology-feature convolutions in the order the kernels read H"""
+    if getattr(m, "plain", False):
+        return [m.conv1.weight, m.conv2.weight], [m.conv1.bias, m.conv2.bias]
+    return [m.conv1.weight, m.conv2.weight, m.conv1_se.weight], [m.conv1.bias, m.conv2.bias, m.conv1_se.bias]
+
+
 def dgphgcn1_forward(m, x, n, T, V, save):
     """x [n*T*V, C_in] -> out [n*T*V, C_out].  `save`: dict filled for backward (or None)."""
     dev, dt = x.device, x.dtype
@@ -259,27 +266,30 @@ def dgphgcn1_forward(m, x, n, T, V, save):
     KC = 3 * R
     has_down = m.has_down
     training = m.training
-    nt, et = m._tables(dev)
+    nt, et = m._tables(dev)     # (None, None) for the plain flag set
 
     # ---- topology branch: temporal mean -> 9R features per joint -> per-sample adjacency
     # (bf16 mode: the three feature convolutions run on the tensor core from a bf16 copy of the temporal mean, with the
     #  accumulator stored UNROUNDED in fp32 — H feeds differences, tanh and softmax)
     tc_topo = dt == torch.bfloat16 and Cin % 8 == 0 and R % 8 == 0 and ops.L.is_device_build()
-    Wt = cat_params(m, "Wt", [m.conv1.weight, m.conv2.weight, m.conv1_se.weight], (9 * R, Cin))
-    bt = cat_params(m, "bt", [m.conv1.bias, m.conv2.bias, m.conv1_se.bias], (9 * R,))
-    H = torch.empty(n * V, 9 * R, dtype=torch.float32, device=dev)
+    plain = getattr(m, "plain", False)       # DG-GCN flag set (dggcn; dghgcn / dgphgcn / dgphgcn1 with the attention flags off)
+    tw, tb = _topo_params(m)
+    HC = (6 if plain else 9) * R
+    Wt = cat_params(m, "Wt", tw, (HC, Cin))
+    bt = cat_params(m, "bt", tb, (HC,))
+    H = torch.empty(n * V, HC, dtype=torch.float32, device=dev)
     if tc_topo:
         xm, xmb = ops.tmean(x, n, T, V, with_bf16=True)                         # [n,V,Cin] fp32 + bf16
         xm2 = xmb.view(n * V, Cin)
-        ops.conv_gemm(xm2, Wt, 9 * R, H, n_samples=n, T_in=1, T_out=1, Vin=V, bias=bt, out_f32=True)
+        ops.conv_gemm(xm2, Wt, HC, H, n_samples=n, T_in=1, T_out=1, Vin=V, bias=bt, out_f32=True)
     else:
         xm = ops.tmean(x, n, T, V)                                              # [n,V,Cin] fp32
         xm2 = xm.view(n * V, Cin)
-        ops.conv_gemm(xm2, Wt, 9 * R, H, n_samples=n, T_in=1, T_out=1, Vin=V, bias=bt)
+        ops.conv_gemm(xm2, Wt, HC, H, n_samples=n, T_in=1, T_out=1, Vin=V, bias=bt)
     adyn = torch.empty(n, V, V, KC, dtype=dt, device=dev)
     S = torch.empty(n, 3, V, V, dtype=torch.float32, device=dev)
-    We, be = m.edge_linears.weight.view(15 * R, R), m.edge_linears.bias
-    ops.topology_fwd(H, n, V, R, nt, et, m.A, m.alpha, m.beta, We, be, adyn, S)
+    We, be = (None, None) if plain else (m.edge_linears.weight.view(15 * R, R), m.edge_linears.bias)
+    ops.topology_fwd(H, n, V, R, nt, et, m.A, m.alpha, m.beta, We, be, adyn, S, plain=plain, subset_wise=bool(m.subset_wise))
 
     # ---- pre (+down) 1x1 convolutions in one GEMM, BatchNorm statistics in the epilogue
     Npd = KC + (Cout if has_down else 0)
@@ -375,9 +385,12 @@ def dgphgcn1_backward(m, sv, dout, grads, extra_add=None, pre=None):
     # every parameter-gradient accumulator of the unit: views of the flat gradient buffer when the model is packed
     # (GradBuckets), else fresh zeros
     dWpost, dbpost, dA, dal, dbe = (grad_like(q) for q in (m.post.weight, m.post.bias, m.A, m.alpha, m.beta))
-    dWe, dbe_l = grad_like(m.edge_linears.weight), grad_like(m.edge_linears.bias)
-    dWt = grad_cat(m, "Wt", [m.conv1.weight, m.conv2.weight, m.conv1_se.weight], (9 * R, Cin), grads)
-    dbt = grad_cat(m, "bt", [m.conv1.bias, m.conv2.bias, m.conv1_se.bias], (9 * R,), grads)
+    plain = getattr(m, "plain", False)
+    dWe, dbe_l = (None, None) if plain else (grad_like(m.edge_linears.weight), grad_like(m.edge_linears.bias))
+    tw, tb = _topo_params(m)
+    HC = (6 if plain else 9) * R
+    dWt = grad_cat(m, "Wt", tw, (HC, Cin), grads)
+    dbt = grad_cat(m, "bt", tb, (HC,), grads)
     pd_w = [m.pre[0].weight] + ([m.down[0].weight] if has_down else [])
     pd_b = [m.pre[0].bias] + ([m.down[0].bias] if has_down else [])
     dWpd, dbpd = grad_cat(m, "Wpd", pd_w, (Npd, Cin), grads), grad_cat(m, "bpd", pd_b, (Npd,), grads)
@@ -405,10 +418,12 @@ def dgphgcn1_backward(m, sv, dout, grads, extra_add=None, pre=None):
     dH = torch.empty_like(H)
     tc_topo = xm2.dtype == torch.bfloat16
     dHb = torch.empty(H.shape, dtype=torch.bfloat16, device=dev) if tc_topo else None
-    ops.topology_bwd(H, n, V, R, nt, et, m.A, m.alpha, m.beta, m.edge_linears.weight.view(15 * R, R), m.edge_linears.bias, S,
-                     dadyn, dH, dA, dal, dbe, dWe, dbe_l, dH_bf16=dHb)
+    We, be_l = (None, None) if plain else (m.edge_linears.weight.view(15 * R, R), m.edge_linears.bias)
+    ops.topology_bwd(H, n, V, R, nt, et, m.A, m.alpha, m.beta, We, be_l, S,
+                     dadyn, dH, dA, dal, dbe, dWe, dbe_l, dH_bf16=dHb, plain=plain, subset_wise=bool(m.subset_wise))
     grads[m.A], grads[m.alpha], grads[m.beta] = dA, dal, dbe
-    grads[m.edge_linears.weight], grads[m.edge_linears.bias] = dWe, dbe_l
+    if not plain:
+        grads[m.edge_linears.weight], grads[m.edge_linears.bias] = dWe, dbe_l
     dxm = torch.empty(n * V, Cin, dtype=torch.float32, device=dev)
     if tc_topo:
         ops.conv_wgrad(xm2, dHb, dWt, db=dbt, n_samples=n, T_in=1, T_out=1, Vin=V)
@@ -439,8 +454,9 @@ def dgphgcn1_backward(m, sv, dout, grads, extra_add=None, pre=None):
 def ms_layout(m):
     """channel ranges of the branches: [(kind, lo, hi, cfg)], kind in {'conv','max','1x1'}"""
     out, lo = [], 0
+    widths = getattr(m, "branch_widths", None)       # MSTCN (msg3d_utils.py:75-76): the LAST branch takes the remainder
     for j, cfg in enumerate(m.ms_cfg):
-        w = m.rem_mid_channels if j == 0 else m.mid_channels
+        w = widths[j] if widths is not None else (m.rem_mid_channels if j == 0 else m.mid_channels)
         kind = "1x1" if cfg == "1x1" else ("max" if cfg[0] == "max" else "conv")
         out.append((kind, lo, lo + w, cfg))
         lo += w
@@ -463,7 +479,7 @@ def _ms_ranges(layout):
 
 def _ms_fused_args(m, layout, b_act, n, T, T_out, s, V, has_ext, grads):
     """Argument block of the fused tcgen05 branch-stage kernels, or None when the shape is not taken by them."""
-    if b_act.dtype != torch.bfloat16 or not ops.L.is_device_build():
+    if b_act.dtype != torch.bfloat16 or not ops.L.is_device_build() or getattr(m, "no_transform", False):
         return None
     weights = {}
     for j, (kind, lo, hi, cfg) in enumerate(layout):
@@ -485,7 +501,7 @@ MS_TAP = os.environ.get("DSG_MS_TAP", "1") != "0"      # 0: the staged single-ke
 
 def _ms_tap_path(m, layout, ranges, dt):
     """(conv channel width rounded up to 8, {branch: (W, bias)}) when the tap-shifted TMA path applies, else None."""
-    if not MS_TAP or dt != torch.bfloat16 or not ops.L.is_device_build():
+    if not MS_TAP or dt != torch.bfloat16 or not ops.L.is_device_build() or getattr(m, "no_transform", False):
         return None
     (clo, chi), _, _ = ranges
     if chi <= clo or clo != 0 or m.stride > 2:
@@ -513,7 +529,8 @@ def mstcn_forward(m, g, n, T, V, save, res=None, final_relu=False):
     ranges = _ms_ranges(layout)
 
     # ---- all branch 1x1 convolutions as one GEMM over the (V+1)-joint tensor
-    convs = [m.branches[j] if kind == "1x1" else m.branches[j][0] for j, (kind, *_) in enumerate(layout)]
+    convs = [m.branches[j] if kind == "1x1" and not isinstance(m.branches[j], torch.nn.Sequential) else m.branches[j][0]
+             for j, (kind, *_) in enumerate(layout)]
     Wbr = cat_params(m, "Wbr", [c.weight for c in convs], (Ct, Cin))
     bbr = cat_params(m, "bbr", [c.bias for c in convs], (Ct,))
     rows_b = n * T * Vp
@@ -530,7 +547,9 @@ def mstcn_forward(m, g, n, T, V, save, res=None, final_relu=False):
     rows_o, rows_f = n * T_out * Vp, n * T_out * V
     feat = torch.empty(rows_f, Ct, dtype=dt, device=dev)
     oglob = torch.empty(n * T_out, Ct, dtype=torch.float32, device=dev) if has_ext else None
-    c_t = BNCoef(Ct, dev, [m.transform[0]])
+    no_tr = getattr(m, "no_transform", False)
+    feat_bns = m._feat_bns(layout) if no_tr else [(m.transform[0], 0, Ct)]
+    c_t = BNCoef(Ct, dev, [b for b, _, _ in feat_bns])
     add_coeff = m.add_coeff if has_ext else None
     if has_ext and add_coeff.numel() < V:
         raise ValueError("add_coeff is shorter than the number of joints")
@@ -569,8 +588,30 @@ def mstcn_forward(m, g, n, T, V, save, res=None, final_relu=False):
         # ---- ... then max-pool / pass-through branches, local + global*add_coeff, statistics for transform.0
         ops.ms_combine_fwd(Act(B, c_b.a, c_b.b), O, feat, oglob, n=n, T_in=T, T_out=T_out, stride=s, V=V, has_ext=has_ext,
                            ranges=ranges, add_coeff=add_coeff, stat_sum=c_t.ssum, stat_sq=c_t.ssq)
-    c_t.add_bn(m.transform[0], 0, Ct, rows_f)
+    for bn, lo, hi in feat_bns:
+        c_t.add_bn(bn, lo, hi, rows_f)
     c_t.run()
+    if no_tr:
+        # ---- MSTCN (msg3d_utils.py:135-147): every branch ends in its own BatchNorm; out = relu(cat + residual), no transform conv.
+        #      Inside a block (ctrgcn.py:56-58) the block residual and a second ReLU follow.
+        inner = torch.empty(rows_f, Ct, dtype=dt, device=dev)
+        own = m._own_residual(g, n, T, V, save)
+        if own is not None:
+            ops.pointwise(Act(feat, c_t.a, c_t.b, own[0], own[1], own[2], relu=True), inner)
+        else:
+            ops.pointwise(Act(feat, c_t.a, c_t.b, relu=True), inner)
+        out = inner
+        if res is not None or final_relu:
+            out = torch.empty(rows_f, Ct, dtype=dt, device=dev)
+            if res is not None:
+                rx, ra, rb = res
+                ops.pointwise(Act(inner, None, None, rx, ra, rb, relu=final_relu), out)
+            else:
+                ops.pointwise(Act(inner, relu=final_relu), out)
+        if save is not None:
+            save.update(g=g, Wbr=Wbr, B=B, c_b=c_b, feat=feat, oglob=oglob, c_t=c_t, inner=inner, out=out, dims=(n, T, V),
+                        final_relu=final_relu, has_outer=out is not inner, H=None, feat_bns=feat_bns)
+        return out, T_out
 
     # ---- transform conv + final BatchNorm (+ residual, ReLU)
     U = torch.empty(rows_f, Cout, dtype=dt, device=dev)
@@ -592,51 +633,23 @@ def mstcn_forward(m, g, n, T, V, save, res=None, final_relu=False):
     return out, T_out
 
 
-def mstcn_backward(m, sv, dout, grads, tail=None):
-    """Returns (dg, E) where E is the gradient w.r.t. the pre-ReLU sum (what flows into the residual).
-    `tail` (optional dict: out, mask, partner, stat_sum, stat_sq): the consumer of dg is the spatial unit of the same block, whose
-    backward starts with dg * [g > 0] and the BatchNorm-backward sums of its `bn`; with `tail` the last GEMM here applies that mask
-    and accumulates those sums in its epilogue and writes straight into the consumer's buffer (no separate pass over dg)."""
+def _ms_branch_backward(m, sv, dfeat, grads, tail=None):
+    """Backward of the branch stage shared by mstcn / dgmstcn / MSTCN: from dfeat (gradient w.r.t. the concatenated raw branch
+    outputs, an Act) to dg (gradient w.r.t. the unit input); fills the branch parameter gradients."""
     n, T, V = sv["dims"]
-    g, B, feat, U, out = sv["g"], sv["B"], sv["feat"], sv["U"], sv["out"]
-    c_b, c_t, c_u = sv["c_b"], sv["c_t"], sv["c_u"]
+    g, B, c_b = sv["g"], sv["B"], sv["c_b"]
     dev, dt = g.device, g.dtype
     has_ext = m.has_ext
     Vp, s = V + int(has_ext), m.stride
     T_out = (T - 1) // s + 1
-    Cin, Cout = m.in_channels, m.out_channels
+    Cin = m.in_channels
     layout, Ct = ms_layout(m)
     ranges = _ms_ranges(layout)
-    rows_b, rows_o, rows_f = n * T * Vp, n * T_out * Vp, n * T_out * V
-
-    # ---- final ReLU mask + BN-backward sums of `bn`
-    b_u = BNBack(c_u)
-    if sv["final_relu"]:
-        E = torch.empty(rows_f, Cout, dtype=dt, device=dev)
-        ops.pointwise(dout, E, mask=out, stat_sum=b_u.ssum, stat_sq=b_u.ssq, partner=U)
-    else:
-        E = dout
-        ops.pointwise(dout, None, stat_sum=b_u.ssum, stat_sq=b_u.ssq, partner=U)
-    b_u.add_bn(m.bn, 0, Cout, rows_f, grads)
-    b_u.run()
-    dU = b_u.dy(E, U)
-
-    # ---- transform conv backward; e2 = dfeat_act * [bn_t(feat) > 0] with sums for transform.0
-    tr = m.transform[2]
-    b_t = BNBack(c_t)
-    E2 = torch.empty(rows_f, Ct, dtype=dt, device=dev)
-    ops.conv_gemm(dU, tr.weight.view(Cout, Ct), Ct, E2, n_samples=n, T_in=T_out, T_out=T_out, Vin=V, ws=(1, Ct, 0),
-                  mask=Act(feat, c_t.a, c_t.b), stat_sum=b_t.ssum, stat_sq=b_t.ssq, partner=feat)
-    dWtr, dbtr = grad_like(tr.weight), grad_like(tr.bias)
-    convs = [m.branches[j] if kind == "1x1" else m.branches[j][0] for j, (kind, *_) in enumerate(layout)]
+    rows_b, rows_o = n * T * Vp, n * T_out * Vp
+    convs = [m.branches[j] if kind == "1x1" and not isinstance(m.branches[j], torch.nn.Sequential) else m.branches[j][0]
+             for j, (kind, *_) in enumerate(layout)]
     dWbr = grad_cat(m, "Wbr", [c.weight for c in convs], (Ct, Cin), grads)
     dbbr = grad_cat(m, "bbr", [c.bias for c in convs], (Ct,), grads)
-    ops.conv_wgrad(Act(feat, c_t.a, c_t.b, relu=True), dU, dWtr, db=dbtr, n_samples=n, T_in=T_out, T_out=T_out, Vin=V)
-    grads[tr.weight], grads[tr.bias] = dWtr, dbtr
-    b_t.add_bn(m.transform[0], 0, Ct, rows_f, grads)
-    b_t.run()
-    dfeat = b_t.dy(E2, feat)
-
     b_b = BNBack(c_b)
     E3 = torch.empty(rows_b, Ct, dtype=dt, device=dev)
     dadd = grad_like(m.add_coeff) if has_ext else None
@@ -703,7 +716,76 @@ def mstcn_backward(m, sv, dout, grads, tail=None):
         dg = torch.empty(n * T * V, Cin, dtype=dt, device=dev)
         ops.conv_gemm(dB, sv["Wbr"], Cin, dg, n_samples=n, T_in=T, T_out=T, Vin=Vp, ws=(1, Cin, 0), contract_ext=has_ext)
     ops.conv_wgrad(g, dB, dWbr, db=dbbr, n_samples=n, T_in=T, T_out=T, Vin=V, ext_in=has_ext)
+    return dg
+
+
+def _mstcn_notransform_backward(m, sv, dout, grads, tail=None):
+    """MSTCN: out = relu(inner + res_block), inner = relu(bn_branch(feat) + own_res).  Returns (dg, E) like mstcn_backward."""
+    n, T, V = sv["dims"]
+    feat, c_t, inner, out = sv["feat"], sv["c_t"], sv["inner"], sv["out"]
+    dev, dt = feat.device, feat.dtype
+    rows_f, Ct = feat.shape
+    if sv["has_outer"] and sv["final_relu"]:
+        E = torch.empty(rows_f, Ct, dtype=dt, device=dev)
+        ops.pointwise(dout, E, mask=out)
+    else:
+        E = dout
+    b_t = BNBack(c_t)
+    E2 = torch.empty(rows_f, Ct, dtype=dt, device=dev)
+    ops.pointwise(E, E2, mask=inner, stat_sum=b_t.ssum, stat_sq=b_t.ssq, partner=feat)
+    for bn, lo, hi in sv["feat_bns"]:
+        b_t.add_bn(bn, lo, hi, rows_f, grads)
+    b_t.run()
+    dg = _ms_branch_backward(m, sv, b_t.dy(E2, feat), grads, tail)
+    dg = m._own_residual_backward(sv, E2, dg, grads)
     return dg, E
+
+
+def mstcn_backward(m, sv, dout, grads, tail=None):
+    """Returns (dg, E) where E is the gradient w.r.t. the pre-ReLU sum (what flows into the residual).
+    `tail` (optional dict: out, mask, partner, stat_sum, stat_sq): the consumer of dg is the spatial unit of the same block, whose
+    backward starts with dg * [g > 0] and the BatchNorm-backward sums of its `bn`; with `tail` the last GEMM here applies that mask
+    and accumulates those sums in its epilogue and writes straight into the consumer's buffer (no separate pass over dg)."""
+    n, T, V = sv["dims"]
+    g, B, feat, U, out = sv["g"], sv["B"], sv["feat"], sv.get("U"), sv["out"]
+    c_b, c_t, c_u = sv["c_b"], sv["c_t"], sv.get("c_u")
+    dev, dt = g.device, g.dtype
+    has_ext = m.has_ext
+    Vp, s = V + int(has_ext), m.stride
+    T_out = (T - 1) // s + 1
+    Cin, Cout = m.in_channels, m.out_channels
+    layout, Ct = ms_layout(m)
+    ranges = _ms_ranges(layout)
+    rows_b, rows_o, rows_f = n * T * Vp, n * T_out * Vp, n * T_out * V
+
+    if getattr(m, "no_transform", False):
+        return _mstcn_notransform_backward(m, sv, dout, grads, tail)
+    # ---- final ReLU mask + BN-backward sums of `bn`
+    b_u = BNBack(c_u)
+    if sv["final_relu"]:
+        E = torch.empty(rows_f, Cout, dtype=dt, device=dev)
+        ops.pointwise(dout, E, mask=out, stat_sum=b_u.ssum, stat_sq=b_u.ssq, partner=U)
+    else:
+        E = dout
+        ops.pointwise(dout, None, stat_sum=b_u.ssum, stat_sq=b_u.ssq, partner=U)
+    b_u.add_bn(m.bn, 0, Cout, rows_f, grads)
+    b_u.run()
+    dU = b_u.dy(E, U)
+
+    # ---- transform conv backward; e2 = dfeat_act * [bn_t(feat) > 0] with sums for transform.0
+    tr = m.transform[2]
+    b_t = BNBack(c_t)
+    E2 = torch.empty(rows_f, Ct, dtype=dt, device=dev)
+    ops.conv_gemm(dU, tr.weight.view(Cout, Ct), Ct, E2, n_samples=n, T_in=T_out, T_out=T_out, Vin=V, ws=(1, Ct, 0),
+                  mask=Act(feat, c_t.a, c_t.b), stat_sum=b_t.ssum, stat_sq=b_t.ssq, partner=feat)
+    dWtr, dbtr = grad_like(tr.weight), grad_like(tr.bias)
+    ops.conv_wgrad(Act(feat, c_t.a, c_t.b, relu=True), dU, dWtr, db=dbtr, n_samples=n, T_in=T_out, T_out=T_out, Vin=V)
+    grads[tr.weight], grads[tr.bias] = dWtr, dbtr
+    b_t.add_bn(m.transform[0], 0, Ct, rows_f, grads)
+    b_t.run()
+    dfeat = b_t.dy(E2, feat)
+
+    return _ms_branch_backward(m, sv, dfeat, grads, tail), E
 
 
 # ------------------------------------------------------------------------------------------------
@@ -904,4 +986,132 @@ def unit_gcn_backward(m, sv, dout, grads, extra_add=None):
         grads[m.PA] = dA
     elif m.adaptive == "importance":
         grads[m.PA] = dA * m.A.detach()
+    return dx
+
+# ------------------------------------------------------------------------------------------------
+# unit_ctrgcn  (CTR-GCN spatial unit: three channel-wise topology refinement graph convolutions, gcn.py:634-666, :882-930)
+# ------------------------------------------------------------------------------------------------
+
+def _ctr_groups(m):
+    """parameter groups the kernels read concatenated (adjacent views when the model is packed by GradBuckets)"""
+    cs = list(m.convs)
+    g = {"Wt": [c.conv1.weight for c in cs] + [c.conv2.weight for c in cs], "bt": [c.conv1.bias for c in cs] + [c.conv2.bias for c in cs],
+         "W4": [c.conv4.weight for c in cs], "b4": [c.conv4.bias for c in cs],
+         "W3": [c.conv3.weight for c in cs] + ([m.down[0].weight] if m.has_down else []),
+         "b3": [c.conv3.bias for c in cs] + ([m.down[0].bias] if m.has_down else [])}
+    return g
+
+
+def unit_ctrgcn_forward(m, x, n, T, V, save):
+    """x [n*T*V, C_in] -> relu(bn(sum_k CTRGC_k(x)) + down(x)) [n*T*V, C_out]"""
+    dev, dt = x.device, x.dtype
+    rows = n * T * V
+    Cin, Cout, R = m.in_c, m.out_c, m.rel_channels
+    KC = 3 * Cout
+    grp = _ctr_groups(m)
+    has_down = m.has_down
+    # ---- topology: x1 = conv1(mean_t x), x2 = conv2(mean_t x) (the convolution commutes with the mean), refined adjacency per
+    #      sample and OUTPUT channel
+    Wt, bt = cat_params(m, "Wt", grp["Wt"], (6 * R, Cin)), cat_params(m, "bt", grp["bt"], (6 * R,))
+    tc_topo = dt == torch.bfloat16 and Cin % 8 == 0 and R % 8 == 0 and ops.L.is_device_build()
+    H = torch.empty(n * V, 6 * R, dtype=torch.float32, device=dev)
+    if tc_topo:
+        xm, xmb = ops.tmean(x, n, T, V, with_bf16=True)
+        xm2 = xmb.view(n * V, Cin)
+        ops.conv_gemm(xm2, Wt, 6 * R, H, n_samples=n, T_in=1, T_out=1, Vin=V, bias=bt, out_f32=True)
+    else:
+        xm2 = ops.tmean(x, n, T, V).view(n * V, Cin)
+        ops.conv_gemm(xm2, Wt, 6 * R, H, n_samples=n, T_in=1, T_out=1, Vin=V, bias=bt)
+    W4, b4 = cat_params(m, "W4", grp["W4"], (3, Cout, R)), cat_params(m, "b4", grp["b4"], (3, Cout))
+    adyn = torch.empty(n, V, V, KC, dtype=dt, device=dev)
+    ops.ctr_topology(H, n, V, R, Cout, m.A, m.alpha, W4, b4, adyn=adyn)
+    # ---- conv3 of the three subsets (+ down) as one GEMM; BatchNorm statistics of `down` in the epilogue
+    N3 = KC + (Cout if has_down else 0)
+    W3, b3 = cat_params(m, "W3", grp["W3"], (N3, Cin)), cat_params(m, "b3", grp["b3"], (N3,))
+    XD = torch.empty(rows, N3, dtype=dt, device=dev)
+    c_d = BNCoef(N3, dev, [m.down[1]]) if has_down else None
+    ops.conv_gemm(x, W3, N3, XD, n_samples=n, T_in=T, T_out=T, Vin=V, bias=b3,
+                  stat_sum=c_d.ssum if has_down else None, stat_sq=c_d.ssq if has_down else None)
+    if has_down:
+        c_d.add_identity(0, KC)
+        c_d.add_bn(m.down[1], KC, N3, rows)
+        c_d.run()
+    # ---- y_k[n,t,w,c] = sum_u x3_k[n,t,u,c] adyn[n,u,w,k,c]; z = sum_k y_k (a GEMM with [I|I|I]: exact, statistics in its epilogue)
+    Y3 = torch.empty(rows, KC, dtype=dt, device=dev)
+    ops.graph_agg(XD[:, :KC], Y3, mode=0, n_samples=n, T=T, V=V, KC=KC, adyn=adyn)
+    Z = torch.empty(rows, Cout, dtype=dt, device=dev)
+    c_z = BNCoef(Cout, dev, [m.bn])
+    Wsum = m._sum_weight(dev)
+    ops.conv_gemm(Y3, Wsum, Cout, Z, n_samples=n, T_in=T, T_out=T, Vin=V, stat_sum=c_z.ssum, stat_sq=c_z.ssq)
+    c_z.add_bn(m.bn, 0, Cout, rows)
+    c_z.run()
+    out = torch.empty(rows, Cout, dtype=dt, device=dev)
+    if has_down:
+        src = Act(Z, c_z.a, c_z.b, XD[:, KC:], c_d.a[KC:], c_d.b[KC:], relu=True)
+    else:
+        src = Act(Z, c_z.a, c_z.b, x, relu=True)
+    ops.pointwise(src, out)
+    if save is not None:
+        save.update(x=x, xm2=xm2, Wt=Wt, H=H, adyn=adyn, W3=W3, XD=XD, c_d=c_d, Z=Z, c_z=c_z, out=out, W4=W4, b4=b4, dims=(n, T, V))
+    return out
+
+
+def unit_ctrgcn_backward(m, sv, dout, grads, extra_add=None):
+    n, T, V = sv["dims"]
+    x, XD, Z, out, adyn, c_d, c_z = sv["x"], sv["XD"], sv["Z"], sv["out"], sv["adyn"], sv["c_d"], sv["c_z"]
+    dev, dt = x.device, x.dtype
+    rows = n * T * V
+    Cin, Cout, R = m.in_c, m.out_c, m.rel_channels
+    KC = 3 * Cout
+    has_down = m.has_down
+    N3 = KC + (Cout if has_down else 0)
+    grp = _ctr_groups(m)
+    # ---- e4 = dout * [out > 0], BatchNorm-backward sums of `bn` (and `down.1`)
+    E = torch.empty(rows, N3, dtype=dt, device=dev) if has_down else None
+    E4 = E[:, KC:] if has_down else torch.empty(rows, Cout, dtype=dt, device=dev)
+    b_z = BNBack(c_z)
+    ops.pointwise(dout, E4, mask=out, stat_sum=b_z.ssum, stat_sq=b_z.ssq, partner=Z)
+    b_z.add_bn(m.bn, 0, Cout, rows, grads)
+    b_z.run()
+    if has_down:
+        b_d = BNBack(c_d)
+        ops.pointwise(E4, None, stat_sum=b_d.ssum[KC:], stat_sq=b_d.ssq[KC:], partner=XD[:, KC:])
+    # ---- dz broadcast to the three subsets, contraction backward: dadyn and dx3
+    dY3 = torch.empty(rows, KC, dtype=dt, device=dev)
+    Wsum = m._sum_weight(dev)
+    ops.conv_gemm(b_z.dy(E4, Z), Wsum, KC, dY3, n_samples=n, T_in=T, T_out=T, Vin=V, ws=(1, KC, 0))
+    dadyn = torch.empty(n, V, V, KC, dtype=torch.float32, device=dev)
+    ops.graph_agg_dadj(XD[:, :KC], dY3, dadyn, n_samples=n, T=T, V=V, KC=KC)
+    E5 = E[:, :KC] if has_down else torch.empty(rows, KC, dtype=dt, device=dev)
+    ops.graph_agg(dY3, E5, mode=1, n_samples=n, T=T, V=V, KC=KC, adyn=adyn)
+    # ---- topology backward
+    H, Wt, xm2 = sv["H"], sv["Wt"], sv["xm2"]
+    dA, dal = grad_like(m.A), grad_like(m.alpha)
+    dW4, db4 = grad_cat(m, "W4", grp["W4"], (3, Cout, R), grads), grad_cat(m, "b4", grp["b4"], (3, Cout), grads)
+    dWt, dbt = grad_cat(m, "Wt", grp["Wt"], (6 * R, Cin), grads), grad_cat(m, "bt", grp["bt"], (6 * R,), grads)
+    dW3, db3 = grad_cat(m, "W3", grp["W3"], (N3, Cin), grads), grad_cat(m, "b3", grp["b3"], (N3,), grads)
+    dH = torch.empty_like(H)
+    tc_topo = xm2.dtype == torch.bfloat16
+    dHb = torch.empty(H.shape, dtype=torch.bfloat16, device=dev) if tc_topo else None
+    ops.ctr_topology(H, n, V, R, Cout, m.A, m.alpha, sv["W4"], sv["b4"], dadyn=dadyn, dH=dH, dH_bf16=dHb, dA=dA, dalpha=dal, dW4=dW4,
+                     db4=db4)
+    grads[m.A], grads[m.alpha] = dA, dal
+    dxm = torch.empty(n * V, Cin, dtype=torch.float32, device=dev)
+    dHs = dHb if tc_topo else dH
+    ops.conv_wgrad(xm2, dHs, dWt, db=dbt, n_samples=n, T_in=1, T_out=1, Vin=V)
+    ops.conv_gemm(dHs, Wt, Cin, dxm, n_samples=n, T_in=1, T_out=1, Vin=V, ws=(1, Cin, 0), out_f32=tc_topo)
+    # ---- dx = [dx3 | dD_raw] @ [W3; Wdown] (+ e4 when the residual is the identity) + dxm / T (+ extra)
+    dx = torch.empty(rows, Cin, dtype=dt, device=dev)
+    if has_down:
+        b_d.add_identity(0, KC)
+        b_d.add_bn(m.down[1], KC, N3, rows, grads)
+        b_d.run()
+        dsrc = b_d.dy(E, XD)
+        ops.conv_gemm(dsrc, sv["W3"], Cin, dx, n_samples=n, T_in=T, T_out=T, Vin=V, ws=(1, Cin, 0), add=extra_add, bcast=dxm,
+                      bcast_scale=1.0 / T)
+    else:
+        dsrc = Act(E5)
+        ops.conv_gemm(dsrc, sv["W3"], Cin, dx, n_samples=n, T_in=T, T_out=T, Vin=V, ws=(1, Cin, 0), add=E4, add2=extra_add, bcast=dxm,
+                      bcast_scale=1.0 / T)
+    ops.conv_wgrad(x, dsrc, dW3, db=db3, n_samples=n, T_in=T, T_out=T, Vin=V)
     return dx

@@ -180,6 +180,43 @@ class unit_gcn(nn.Module):
         pass
 
 
+def _dg_unit_layers(self, in_channels, out_channels, A, ratio, norm, act, semantic, num_types=5, edge_num=15):
+    """children of the dynamic-adjacency spatial units, registered in the reference's order (state-dict contract):
+    gcn.py:1483-1512 (dggcn), :1643-1683 (dghgcn), :1863-1906 (dgphgcn), :2137-2215 (dgphgcn1)."""
+    num_subsets = A.size(0)
+    if ratio is None:
+        ratio = 1 / num_subsets
+    self.ratio = ratio
+    mid_channels = int(ratio * out_channels)
+    self.mid_channels = mid_channels
+    self.norm_cfg = norm if isinstance(norm, dict) else dict(type=norm)
+    self.act_cfg = act if isinstance(act, dict) else dict(type=act)
+    self.act = build_activation_layer(self.act_cfg)
+    self.A = nn.Parameter(A.clone())
+    self.semantic_num = ceil(num_subsets / 3) if semantic else 0
+    self.norm_num = num_subsets - self.semantic_num
+    self.pre = nn.Sequential(nn.Conv2d(in_channels, mid_channels * num_subsets, 1),
+                             build_norm_layer(self.norm_cfg, mid_channels * num_subsets)[1], self.act)
+    self.post = nn.Conv2d(mid_channels * num_subsets, out_channels, 1)
+    self.tanh, self.relu, self.sigmoid, self.softmax = nn.Tanh(), nn.ReLU(), nn.Sigmoid(), nn.Softmax(-2)
+    self.alpha = nn.Parameter(torch.zeros(num_subsets))
+    self.beta = nn.Parameter(torch.zeros(num_subsets))
+    if semantic:
+        self.conv1_se = nn.Conv2d(in_channels, self.semantic_num * mid_channels * num_types, kernel_size=1)
+        self.conv2_se = nn.Conv2d(in_channels, self.semantic_num * mid_channels * num_types, kernel_size=1)   # allocated, unused (gcn.py:2253-2254)
+    self.conv1 = nn.Conv2d(in_channels, self.norm_num * mid_channels, 1)
+    self.conv2 = nn.Conv2d(in_channels, self.norm_num * mid_channels, 1)
+    if semantic:
+        self.edge_linears = nn.Conv2d(self.semantic_num * mid_channels, edge_num * self.semantic_num * mid_channels, 1)
+    self.has_down = in_channels != out_channels
+    if self.has_down:
+        self.down = nn.Sequential(nn.Conv2d(in_channels, out_channels, 1), build_norm_layer(self.norm_cfg, out_channels)[1])
+    else:
+        self.down = lambda x: x
+    self.bn = build_norm_layer(self.norm_cfg, out_channels)[1]
+    self._tab = {}
+
+
 class dgphgcn1(nn.Module):
 
     def __init__(self, in_channels, out_channels, A, edge_type, node_type, ratio=0.25, decompose=False, ctr='T', ada='T',
@@ -200,45 +237,23 @@ class dgphgcn1(nn.Module):
             self.node_attention = self.edge_attention = self.target_specific = False
             self.decompose = decompose = False
             self.subset_wise = False
-        supported = (self.decompose and self.node_attention and self.edge_attention and self.subset_wise and sub_att
-                     and ctr == 'T' and ada == 'T' and not ada_attention and not target_specific and num_subsets == 3
-                     and ada_act == 'softmax' and ctr_act == 'tanh' and num_types == 5 and edge_num == 15)
-        if not supported:
+        if num_subsets != 3 or ctr != 'T' or ada != 'T' or ada_act != 'softmax' or ctr_act != 'tanh':
+            raise NotImplementedError("the topology kernels cover ctr='T', ada='T', tanh / softmax, 3 subsets")
+        full = (self.decompose and self.node_attention and self.edge_attention and self.subset_wise and sub_att
+                and not ada_attention and not target_specific and num_types == 5 and edge_num == 15)
+        # the plain DG-GCN unit (every attention flag off, e.g. stage=False, gcn.py:2122-2127): same kernels, variant 1
+        self.plain = not (self.decompose or self.node_attention or self.edge_attention or ada_attention or target_specific) and sub_att
+        if not (full or self.plain):
             raise NotImplementedError(
                 "dgphgcn1 kernels cover the DS-GCN configuration (configs/dsstgcn/DSSTGCN_model.py: decompose, node_attention, "
-                "edge_attention, subset_wise, sub_att, ctr='T', ada='T', tanh/softmax, 3 subsets); other flag sets are not built")
-        if ratio is None:
-            ratio = 1 / num_subsets
-        self.ratio = ratio
-        mid_channels = int(ratio * out_channels)
-        self.mid_channels = mid_channels
-        self.norm_cfg = norm if isinstance(norm, dict) else dict(type=norm)
-        self.act_cfg = act if isinstance(act, dict) else dict(type=act)
-        self.act = build_activation_layer(self.act_cfg)
-        self.A = nn.Parameter(A.clone())
-        self.semantic_num = ceil(num_subsets / 3)
-        self.norm_num = num_subsets - self.semantic_num
-        self.pre = nn.Sequential(nn.Conv2d(in_channels, mid_channels * num_subsets, 1),
-                                 build_norm_layer(self.norm_cfg, mid_channels * num_subsets)[1], self.act)
-        self.post = nn.Conv2d(mid_channels * num_subsets, out_channels, 1)
-        self.tanh, self.relu, self.sigmoid, self.softmax = nn.Tanh(), nn.ReLU(), nn.Sigmoid(), nn.Softmax(-2)
-        self.alpha = nn.Parameter(torch.zeros(num_subsets))
-        self.beta = nn.Parameter(torch.zeros(num_subsets))
-        self.conv1_se = nn.Conv2d(in_channels, self.semantic_num * mid_channels * num_types, kernel_size=1)
-        self.conv2_se = nn.Conv2d(in_channels, self.semantic_num * mid_channels * num_types, kernel_size=1)   # allocated, unused (gcn.py:2253-2254)
-        self.conv1 = nn.Conv2d(in_channels, self.norm_num * mid_channels, 1)
-        self.conv2 = nn.Conv2d(in_channels, self.norm_num * mid_channels, 1)
-        self.edge_linears = nn.Conv2d(self.semantic_num * mid_channels, edge_num * self.semantic_num * mid_channels, 1)
-        self.has_down = in_channels != out_channels
-        if self.has_down:
-            self.down = nn.Sequential(nn.Conv2d(in_channels, out_channels, 1), build_norm_layer(self.norm_cfg, out_channels)[1])
-        else:
-            self.down = lambda x: x
-        self.bn = build_norm_layer(self.norm_cfg, out_channels)[1]
-        self._tab = {}
+                "edge_attention, subset_wise, sub_att) and the plain DG-GCN flag set (no attention flags); other flag sets are not built")
+        _dg_unit_layers(self, in_channels, out_channels, A, ratio, norm, act, semantic=not self.plain, num_types=num_types,
+                        edge_num=edge_num)
 
     def _tables(self, dev):
         """int32 device copies of node_type / edge_type (bit-exact integers; uploaded once per device)."""
+        if self.plain:
+            return None, None
         key = str(dev)
         if key not in self._tab:
             nt = torch.as_tensor(np.asarray(self.node_type), dtype=torch.int32).reshape(-1)
@@ -251,7 +266,8 @@ class dgphgcn1(nn.Module):
 
     def _flat_groups(self):
         """parameters the kernels always use concatenated (one GEMM): parallel.GradBuckets lays them out adjacently"""
-        g = {"Wt": [self.conv1.weight, self.conv2.weight, self.conv1_se.weight], "bt": [self.conv1.bias, self.conv2.bias, self.conv1_se.bias]}
+        tw, tb = Fn._topo_params(self)
+        g = {"Wt": tw, "bt": tb}
         if self.has_down:
             g["Wpd"] = [self.pre[0].weight, self.down[0].weight]
             g["bpd"] = [self.pre[0].bias, self.down[0].bias]
@@ -272,6 +288,139 @@ class dgphgcn1(nn.Module):
 
     def init_weights(self):
         pass
+
+
+class dggcn(dgphgcn1):
+    """DG-GCN spatial unit (gcn.py:1445-1584): the dynamic adjacency without the semantic decomposition — same kernels as dgphgcn1
+    (dsg_topology_* variant 1).  ctr='T', ada='T', tanh / softmax are built; the 'NA' (per-frame) and None variants raise."""
+
+    def __init__(self, in_channels, out_channels, A, ratio=0.25, ctr='T', ada='T', subset_wise=False, ada_act='softmax',
+                 ctr_act='tanh', norm='BN', act='ReLU'):
+        nn.Module.__init__(self)
+        self._init_plain(in_channels, out_channels, A, ratio, ctr, ada, subset_wise, ada_act, ctr_act, norm, act)
+
+    def _init_plain(self, in_channels, out_channels, A, ratio, ctr, ada, subset_wise, ada_act, ctr_act, norm, act):
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.num_subsets = A.size(0)
+        self.ctr, self.ada, self.ada_act, self.ctr_act = ctr, ada, ada_act, ctr_act
+        self.subset_wise = subset_wise
+        if self.num_subsets != 3 or ctr != 'T' or ada != 'T' or ada_act != 'softmax' or ctr_act != 'tanh':
+            raise NotImplementedError("the topology kernels cover ctr='T', ada='T', tanh / softmax, 3 subsets")
+        self.plain = True
+        _dg_unit_layers(self, in_channels, out_channels, A, ratio, norm, act, semantic=False)
+
+
+class dghgcn(dggcn):
+    """gcn.py:1586-1806 with its default flags (no node / edge / ada attention, no target-specific branch) is the DG-GCN unit; the
+    attention flag sets of this earlier variant are not built (the DS-GCN configs use dgphgcn1)."""
+
+    def __init__(self, in_channels, out_channels, A, edge_type, node_type, ratio=0.25, ctr='T', ada='T', node_attention=False,
+                 edge_attention=False, ada_attention=False, target_specific=False, add_type=False, num_types=5, edge_num=15,
+                 subset_wise=False, ada_act='softmax', ctr_act='tanh', norm='BN', act='ReLU'):
+        nn.Module.__init__(self)
+        if node_attention or edge_attention or ada_attention or target_specific:
+            raise NotImplementedError(f"{type(self).__name__}: only the flag set without attention branches is built "
+                                      "(use dgphgcn1 for the semantic decomposition)")
+        self.node_attention, self.edge_attention = node_attention, edge_attention
+        self.target_specific, self.ada_attention, self.add_type = target_specific, ada_attention, add_type
+        self.num_types, self.edge_num = num_types, edge_num
+        self.edge_type, self.node_type = edge_type, node_type
+        self._init_plain(in_channels, out_channels, A, ratio, ctr, ada, subset_wise, ada_act, ctr_act, norm, act)
+
+
+class dgphgcn(dghgcn):
+    """gcn.py:1808-2072; without attention flags `part_ratio` only sets attributes (gcn.py:1889-1904)."""
+
+    def __init__(self, in_channels, out_channels, A, edge_type, node_type, ratio=0.25, part_ratio=0.4, **kw):
+        _ = kw.get('node_attention', False) & part_ratio      # gcn.py:1892 evaluates `bool & part_ratio`: a float part_ratio (the default!) raises TypeError there too
+        super().__init__(in_channels, out_channels, A, edge_type, node_type, ratio=ratio, **kw)
+        self.part_ratio = part_ratio
+        self.semantic_num = int(self.num_subsets * part_ratio)
+        self.norm_num = self.num_subsets - self.semantic_num
+
+
+def _conv_init(conv):       # init_func.py:15-17
+    nn.init.kaiming_normal_(conv.weight, mode='fan_out')
+    nn.init.constant_(conv.bias, 0)
+
+
+class CTRGC(nn.Module):
+    """Parameter holder of one channel-wise topology refinement graph convolution (gcn.py:634-666); unit_ctrgcn runs the three of
+    a unit together on the kernels (one feature GEMM, one adjacency kernel, one contraction)."""
+
+    def __init__(self, in_channels, out_channels, rel_reduction=8):
+        super().__init__()
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.rel_channels = 8 if in_channels <= 16 else in_channels // rel_reduction
+        self.conv1 = nn.Conv2d(in_channels, self.rel_channels, kernel_size=1)
+        self.conv2 = nn.Conv2d(in_channels, self.rel_channels, kernel_size=1)
+        self.conv3 = nn.Conv2d(in_channels, out_channels, kernel_size=1)
+        self.conv4 = nn.Conv2d(self.rel_channels, out_channels, kernel_size=1)
+        self.tanh = nn.Tanh()
+        self.init_weights()
+
+    def init_weights(self):
+        for m in self.modules():
+            if isinstance(m, nn.Conv2d):
+                _conv_init(m)
+
+    def forward(self, x, A=None, alpha=1):
+        raise NotImplementedError("CTRGC runs inside unit_ctrgcn (the three subsets share one set of kernel launches)")
+
+
+class unit_ctrgcn(nn.Module):
+    """gcn.py:882-930: relu(bn(sum_k CTRGC_k(x, A[k], alpha)) + down(x))."""
+
+    def __init__(self, in_channels, out_channels, A):
+        super().__init__()
+        self.inter_c, self.out_c, self.in_c = out_channels // 4, out_channels, in_channels
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.num_subset = A.shape[0]
+        if self.num_subset != 3:
+            raise NotImplementedError("unit_ctrgcn kernels are built for 3 adjacency subsets")
+        self.convs = nn.ModuleList([CTRGC(in_channels, out_channels) for _ in range(self.num_subset)])
+        self.rel_channels = self.convs[0].rel_channels
+        self.has_down = in_channels != out_channels
+        if self.has_down:
+            self.down = nn.Sequential(nn.Conv2d(in_channels, out_channels, 1), nn.BatchNorm2d(out_channels))
+        else:
+            self.down = lambda x: x
+        self.A = nn.Parameter(A.clone())
+        self.alpha = nn.Parameter(torch.zeros(1))
+        self.bn = nn.BatchNorm2d(out_channels)
+        self.soft = nn.Softmax(-2)
+        self.relu = nn.ReLU(inplace=True)
+        self._wsum = {}
+
+    def _sum_weight(self, dev):
+        """[I | I | I]: the subset sum z = y_0 + y_1 + y_2 as a GEMM operand (exact in fp32 accumulation)"""
+        key = str(dev)
+        if key not in self._wsum:
+            self._wsum[key] = torch.eye(self.out_c, dtype=torch.float32, device=dev).repeat(1, self.num_subset).contiguous()
+        return self._wsum[key]
+
+    def _flat_groups(self):
+        return Fn._ctr_groups(self)
+
+    def _fwd(self, x, n, t, v, save):
+        return Fn.unit_ctrgcn_forward(self, x, n, t, v, save), t
+
+    def _bwd(self, save, dout, grads, extra_add=None):
+        return Fn.unit_ctrgcn_backward(self, save, dout, grads, extra_add)
+
+    def forward(self, x):
+        _check_input(x)
+        return _run(self, x, self._fwd, self._bwd)
+
+    def init_weights(self):
+        for m in self.modules():
+            if isinstance(m, nn.Conv2d):
+                _conv_init(m)
+            elif isinstance(m, nn.BatchNorm2d):
+                nn.init.constant_(m.weight, 1)
+                nn.init.constant_(m.bias, 0)
+        nn.init.constant_(self.bn.weight, 1e-6)
+        nn.init.constant_(self.bn.bias, 0)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -381,6 +530,79 @@ class dgmstcn(mstcn):
         self._build(in_channels, out_channels, mid_channels, dropout, ms_cfg, stride)
 
 
+class MSTCN(mstcn):
+    """MS-G3D / CTR-GCN multi-scale temporal unit (pyskl/models/gcns/utils/msg3d_utils.py:64-150): 1x1 conv + BN + ReLU into
+    (k x 1) dilated convs / a 3x1 max-pool / a strided 1x1, every branch closed by its own BatchNorm, out = relu(cat + residual).
+    Runs on the branch-stage kernels of mstcn (no transform conv; the last branch takes the channel remainder)."""
+    has_ext = False
+    no_transform = True
+
+    def __init__(self, in_channels, out_channels, kernel_size=3, stride=1, dilations=[1, 2, 3, 4], residual=True,
+                 act_cfg=dict(type='ReLU'), tcn_dropout=0):
+        nn.Module.__init__(self)
+        self.num_branches = len(dilations) + 2
+        branch_channels = out_channels // self.num_branches
+        branch_channels_rem = out_channels - branch_channels * (self.num_branches - 1)
+        if type(kernel_size) == list:
+            assert len(kernel_size) == len(dilations)
+        else:
+            kernel_size = [kernel_size] * len(dilations)
+        self.in_channels, self.out_channels, self.stride = in_channels, out_channels, stride
+        self.ms_cfg = [(ks, d) for ks, d in zip(kernel_size, dilations)] + [('max', 3), '1x1']
+        self.branch_widths = [branch_channels] * (self.num_branches - 1) + [branch_channels_rem]
+        self.branches = nn.ModuleList([
+            nn.Sequential(nn.Conv2d(in_channels, branch_channels, kernel_size=1, padding=0), nn.BatchNorm2d(branch_channels),
+                          build_activation_layer(act_cfg),
+                          unit_tcn(branch_channels, branch_channels, kernel_size=ks, stride=stride, dilation=d))
+            for ks, d in zip(kernel_size, dilations)])
+        self.branches.append(nn.Sequential(
+            nn.Conv2d(in_channels, branch_channels, kernel_size=1, padding=0), nn.BatchNorm2d(branch_channels),
+            build_activation_layer(act_cfg), nn.MaxPool2d(kernel_size=(3, 1), stride=(stride, 1), padding=(1, 0)),
+            nn.BatchNorm2d(branch_channels)))
+        self.branches.append(nn.Sequential(
+            nn.Conv2d(in_channels, branch_channels_rem, kernel_size=1, padding=0, stride=(stride, 1)),
+            nn.BatchNorm2d(branch_channels_rem)))
+        if not residual:
+            self.residual = lambda x: 0
+            self.res_kind = 'none'
+        elif in_channels == out_channels and stride == 1:
+            self.residual = lambda x: x
+            self.res_kind = 'identity'
+        else:
+            self.residual = unit_tcn(in_channels, out_channels, kernel_size=1, stride=stride)
+            self.res_kind = 'conv'
+        self.act = build_activation_layer(act_cfg)
+        if tcn_dropout:
+            raise NotImplementedError("dropout > 0 is not built (the configs use 0)")
+        self.drop = nn.Dropout(tcn_dropout)
+
+    def _feat_bns(self, layout):
+        """the BatchNorm that closes each branch, with its channel range in the concatenated output"""
+        out = []
+        for j, (kind, lo, hi, _) in enumerate(layout):
+            out.append(((self.branches[j][3].bn if kind == "conv" else self.branches[j][4] if kind == "max" else self.branches[j][1]), lo, hi))
+        return out
+
+    def _own_residual(self, x, n, t, v, save):
+        if self.res_kind == 'none':
+            return None
+        if self.res_kind == 'identity':
+            return (x, None, None)
+        sv = {} if save is not None else None
+        rr, c_r, _ = Fn.unit_tcn_raw_forward(self.residual, x, n, t, v, sv)
+        if save is not None:
+            save["own_res"] = sv
+        return (rr, c_r.a, c_r.b)
+
+    def _own_residual_backward(self, save, E, dg, grads):
+        if self.res_kind == 'none':
+            return dg
+        extra = E if self.res_kind == 'identity' else Fn.unit_tcn_raw_backward(self.residual, save["own_res"], E, grads)
+        out = torch.empty_like(dg)
+        ops.pointwise(ops.Act(dg, None, None, extra), out)
+        return out
+
+
 # ------------------------------------------------------------------------------------------------
 # blocks and backbones
 # ------------------------------------------------------------------------------------------------
@@ -466,9 +688,11 @@ class DGBlock(_STBlock):
             raise NotImplementedError("tcn_type='dgmsmlp' is an author experiment outside the DS-GCN configs (SURVEY.md §2 row 3)")
         gcn_type = gcn_kwargs.pop('type', 'dghgcn')
         assert gcn_type in ['dghgcn', 'dgphgcn', 'dgphgcn1', 'dggcn']
-        if gcn_type != 'dgphgcn1':
-            raise NotImplementedError(f"gcn_type='{gcn_type}': only 'dgphgcn1' (configs/dsstgcn) is built so far")
-        self.gcn = dgphgcn1(in_channels, out_channels, A, edge_type, node_type, **gcn_kwargs)
+        if gcn_type == 'dggcn':
+            self.gcn = dggcn(in_channels, out_channels, A, **gcn_kwargs)
+        else:
+            cls = dict(dghgcn=dghgcn, dgphgcn=dgphgcn, dgphgcn1=dgphgcn1)[gcn_type]
+            self.gcn = cls(in_channels, out_channels, A, edge_type, node_type, **gcn_kwargs)
         self.relu = nn.ReLU()
         self._make_residual(in_channels, out_channels, stride, residual)
 
@@ -494,25 +718,56 @@ class STGCNBlock(_STBlock):
         self._make_residual(in_channels, out_channels, stride, residual)
 
 
+class CTRGCNBlock(_STBlock):
+    """ctrgcn.py:9-66: relu(MSTCN(unit_ctrgcn(x)) + residual(x)); children gcn1 / tcn1 as in the reference."""
+
+    def __init__(self, in_channels, out_channels, A, edge_type=None, node_type=None, semantic_index=False, stride=1, residual=True,
+                 kernel_size=5, dilations=[1, 2], tcn_dropout=0, **kwargs):
+        super().__init__()
+        gcn_kwargs = {k[4:]: v for k, v in kwargs.items() if k[:4] == 'gcn_'}
+        tcn_kwargs = {k[4:]: v for k, v in kwargs.items() if k[:4] == 'tcn_'}
+        kwargs = {k: v for k, v in kwargs.items() if k[:4] not in ['gcn_', 'tcn_']}
+        assert len(kwargs) == 0, f'Invalid arguments: {kwargs}'
+        tcn_type = tcn_kwargs.pop('type', 'mstcn')
+        gcn_type = gcn_kwargs.pop('type', 'unit_ctrhgcn')
+        if gcn_type != 'unit_ctrgcn' or tcn_type != 'mstcn':
+            raise NotImplementedError(f"CTRGCNBlock with gcn_type={gcn_type}, tcn_type={tcn_type}: only unit_ctrgcn + mstcn (CTR-GCN proper) "
+                                      "is built; unit_ctrhgcn / msmlp are author experiments (SURVEY.md §2)")
+        self.gcn1 = unit_ctrgcn(in_channels, out_channels, A, **gcn_kwargs)
+        self.tcn1 = MSTCN(out_channels, out_channels, kernel_size=kernel_size, stride=stride, dilations=dilations, residual=False,
+                          tcn_dropout=tcn_dropout)
+        self.relu = nn.ReLU(inplace=True)
+        self._make_residual(in_channels, out_channels, stride, residual)
+
+    gcn = property(lambda self: self.gcn1)       # the names _STBlock's fused forward / backward use
+    tcn = property(lambda self: self.tcn1)
+
+
 class _DataBNFn(torch.autograd.Function):
     """data_bn (dgstgcn.py:158-164): rows (n*m, t) x channels v*C+c is already the channels-last activation."""
 
     @staticmethod
-    def forward(ctx, x, bn, weight, bias):
+    def forward(ctx, x, bn, weight, bias, mvc=False):
         N, M, T, V, C = x.shape
         dev = x.device
-        xin = x.detach().contiguous().view(N * M * T, V * C)
+        if mvc:     # ctrgcn.py:112-114: BatchNorm1d over channels m*V*C + v*C + c, statistics over (N, T): rows (n, t), person slot in the channel
+            xin = x.detach().permute(0, 2, 1, 3, 4).contiguous().view(N * T, M * V * C)
+        else:
+            xin = x.detach().contiguous().view(N * M * T, V * C)
         if xin.dtype != torch.float32:
             xin = xin.float()
-        coef = Fn.BNCoef(V * C, dev, [bn])
+        nrow, CH = xin.shape
+        coef = Fn.BNCoef(CH, dev, [bn])
         if coef.training:
             ops.pointwise(xin, None, stat_sum=coef.ssum, stat_sq=coef.ssq)
-        coef.add_bn(bn, 0, V * C, N * M * T)
+        coef.add_bn(bn, 0, CH, nrow)
         coef.run()
-        out = torch.empty(N * M * T, V * C, dtype=_compute_dtype, device=dev)
+        out = torch.empty(nrow, CH, dtype=_compute_dtype, device=dev)
         ops.pointwise(ops.Act(xin, coef.a, coef.b), out)
         ctx.save, ctx.bn, ctx.dims, ctx.need_x = (xin, coef), bn, (N, M, T, V, C), ctx.needs_input_grad[0]
-        ctx.x_dtype = x.dtype
+        ctx.x_dtype, ctx.mvc = x.dtype, mvc
+        if mvc:
+            out = out.view(N, T, M, V, C).permute(0, 2, 1, 3, 4).contiguous()
         return out.view(N * M, T, V, C).permute(0, 3, 1, 2)
 
     @staticmethod
@@ -520,18 +775,22 @@ class _DataBNFn(torch.autograd.Function):
         N, M, T, V, C = ctx.dims
         xin, coef = ctx.save
         bn = ctx.bn
-        d = dout.permute(0, 2, 3, 1).contiguous().view(N * M * T, V * C)
+        nrow, CH = xin.shape
+        if ctx.mvc:
+            d = dout.permute(0, 2, 3, 1).reshape(N, M, T, V, C).permute(0, 2, 1, 3, 4).contiguous().view(nrow, CH)
+        else:
+            d = dout.permute(0, 2, 3, 1).contiguous().view(nrow, CH)
         back = Fn.BNBack(coef)
         ops.pointwise(d, None, stat_sum=back.ssum, stat_sq=back.ssq, partner=xin)
         grads = {}
-        back.add_bn(bn, 0, V * C, N * M * T, grads)
+        back.add_bn(bn, 0, CH, nrow, grads)
         back.run()
         dx = None
         if ctx.need_x:
             d32 = d if d.dtype == torch.float32 else d.float()
-            dx = torch.empty(N * M * T, V * C, dtype=torch.float32, device=d.device)
+            dx = torch.empty(nrow, CH, dtype=torch.float32, device=d.device)
             ops.pointwise(ops.Act(d32, back.ca, back.cc, xin, back.cb), dx)
-            dx = dx.view(N, M, T, V, C).to(ctx.x_dtype)
+            dx = (dx.view(N, T, M, V, C).permute(0, 2, 1, 3, 4) if ctx.mvc else dx.view(N, M, T, V, C)).to(ctx.x_dtype)
         gw, gb_ = grads[bn.weight], grads[bn.bias]
         for q in (bn.weight, bn.bias):          # written in place into the packed flat gradient buffer (see _KernelFn.backward)
             if q.grad is not None and grads[q].data_ptr() == q.grad.data_ptr():
@@ -542,7 +801,7 @@ class _DataBNFn(torch.autograd.Function):
             gw = None
         if bn.bias.grad is not None and gb_.data_ptr() == bn.bias.grad.data_ptr():
             gb_ = None
-        return dx, None, gw, gb_
+        return dx, None, gw, gb_, None
 
 
 class _Backbone(nn.Module):
@@ -604,8 +863,7 @@ class _Backbone(nn.Module):
             if self.data_bn_type == 'VC':
                 h = _DataBNFn.apply(x, self.data_bn, self.data_bn.weight, self.data_bn.bias)
             elif self.data_bn_type == 'MVC':
-                # channel index m*V*C + v*C + c with statistics over (N, T): one BatchNorm1d per person slot
-                raise NotImplementedError("data_bn_type='MVC' is not used by the DS-GCN configs")
+                h = _DataBNFn.apply(x, self.data_bn, self.data_bn.weight, self.data_bn.bias, True)
             else:
                 h = x.reshape(N * M, T, V, C).permute(0, 3, 1, 2)
             for i in range(self.num_stages):
@@ -639,3 +897,43 @@ class STGCN(_Backbone):
         mk = lambda cin, cout, stride, residual, kw: STGCNBlock(cin, cout, A.clone(), stride, residual=residual, **kw)
         self._setup(mk, graph_cfg, in_channels, base_channels, ch_ratio, num_stages, inflate_stages, down_stages, data_bn_type,
                     num_person, pretrained, kwargs, pop_first=('tcn_dropout',))
+
+
+class CTRGCN(nn.Module):
+    """ctrgcn.py:69-125 with gcn_type='unit_ctrgcn' (CTR-GCN proper): data_bn over (person, joint, channel), 10 CTRGCNBlocks in `net`."""
+
+    def __init__(self, graph_cfg, in_channels=3, base_channels=64, num_stages=10, inflate_stages=[5, 8], down_stages=[5, 8],
+                 semantic_stage=range(1, 11), pretrained=None, num_person=2, **kwargs):
+        super().__init__()
+        self.graph = Graph(**graph_cfg)
+        A = torch.tensor(self.graph.A, dtype=torch.float32, requires_grad=False)
+        self.register_buffer('A', A)
+        node_type = torch.tensor(self.graph.node_type, requires_grad=False)
+        edge_type = torch.tensor(self.graph.edge_type, dtype=torch.float32, requires_grad=False)
+        self.num_person, self.base_channels = num_person, base_channels
+        self.data_bn = nn.BatchNorm1d(num_person * in_channels * A.size(1))
+        kwargs0 = {k: v for k, v in kwargs.items() if k != 'tcn_dropout'}
+        modules = [CTRGCNBlock(in_channels, base_channels, A.clone(), edge_type, node_type, 1 in semantic_stage, residual=False, **kwargs0)]
+        for i in range(2, num_stages + 1):
+            out_channels = base_channels * (1 + (i in inflate_stages))
+            stride = 1 + (i in down_stages)
+            modules.append(CTRGCNBlock(base_channels, out_channels, A.clone(), edge_type, node_type, i in semantic_stage, stride=stride,
+                                       **kwargs))
+            base_channels = out_channels
+        self.net = nn.ModuleList(modules)
+        self.pretrained = pretrained
+
+    def init_weights(self):
+        for module in self.net:
+            module.init_weights()
+
+    def forward(self, x):
+        if x.dim() != 5:
+            raise ValueError(f"expected [N, M, T, V, C], got {tuple(x.shape)}")
+        ops.L.check_tensor(x)
+        N, M, T, V, C = x.size()
+        with Fn.defer_bn_counters(), Fn.stat_arena(x.device):
+            h = _DataBNFn.apply(x, self.data_bn, self.data_bn.weight, self.data_bn.bias, True)
+            for blk in self.net:
+                h = blk(h)
+        return h.reshape((N, M) + h.shape[1:])

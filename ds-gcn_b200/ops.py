@@ -202,33 +202,58 @@ def tmean(x, n_samples, T, V, with_bf16=False):
     return xm
 
 
-def topology_args(H, n, V, R, node_type, edge_type, A, alpha, beta, We, be, S):
+def topology_args(H, n, V, R, node_type, edge_type, A, alpha, beta, We, be, S, plain=False, subset_wise=True):
     a = L.TopologyArgs()
     a.H, a.ld_h = L.ptr(H), _ld(H)
     a.n_samples, a.V, a.R = n, V, R
-    assert node_type.dtype == torch.int32 and edge_type.dtype == torch.int32
-    a.node_type, a.edge_type = L.ptr(node_type), L.ptr(edge_type)
+    a.variant, a.subset_wise = int(plain), int(subset_wise)
+    if not plain:
+        assert node_type.dtype == torch.int32 and edge_type.dtype == torch.int32
+        a.node_type, a.edge_type = L.ptr(node_type), L.ptr(edge_type)
+        a.We, a.be = L.ptr(_f32(We)), L.ptr(_f32(be))
     a.A, a.alpha, a.beta = L.ptr(_f32(A)), L.ptr(_f32(alpha)), L.ptr(_f32(beta))
-    a.We, a.be = L.ptr(_f32(We)), L.ptr(_f32(be))
     a.S = L.ptr(S)
     return a
 
 
-def topology_fwd(H, n, V, R, node_type, edge_type, A, alpha, beta, We, be, adyn, S):
-    a = topology_args(H, n, V, R, node_type, edge_type, A, alpha, beta, We, be, S)
+def topology_fwd(H, n, V, R, node_type, edge_type, A, alpha, beta, We, be, adyn, S, plain=False, subset_wise=True):
+    a = topology_args(H, n, V, R, node_type, edge_type, A, alpha, beta, We, be, S, plain, subset_wise)
     a.adyn, a.adyn_dtype = L.ptr(adyn), L.dt(adyn)
     L.call("dsg_topology_fwd", C.byref(a), L.stream())
 
 
-def topology_bwd(H, n, V, R, node_type, edge_type, A, alpha, beta, We, be, S, dadyn, dH, dA, dalpha, dbeta, dWe, dbe, dH_bf16=None):
-    a = topology_args(H, n, V, R, node_type, edge_type, A, alpha, beta, We, be, S)
+def topology_bwd(H, n, V, R, node_type, edge_type, A, alpha, beta, We, be, S, dadyn, dH, dA, dalpha, dbeta, dWe, dbe, dH_bf16=None,
+                 plain=False, subset_wise=True):
+    a = topology_args(H, n, V, R, node_type, edge_type, A, alpha, beta, We, be, S, plain, subset_wise)
     assert dadyn.dtype == torch.float32 and dH.dtype == torch.float32 and _ld(dH) == _ld(H)
     a.dadyn, a.dH = L.ptr(dadyn), L.ptr(dH)
     if dH_bf16 is not None:
         assert dH_bf16.dtype == torch.bfloat16 and dH_bf16.is_contiguous() and dH_bf16.shape == dH.shape and dH.is_contiguous()
         a.dH_bf16 = L.ptr(dH_bf16)
-    a.dA, a.dalpha, a.dbeta, a.dWe, a.dbe = L.ptr(_f32(dA)), L.ptr(_f32(dalpha)), L.ptr(_f32(dbeta)), L.ptr(_f32(dWe)), L.ptr(_f32(dbe))
+    a.dA, a.dalpha, a.dbeta = L.ptr(_f32(dA)), L.ptr(_f32(dalpha)), L.ptr(_f32(dbeta))
+    if not plain:
+        a.dWe, a.dbe = L.ptr(_f32(dWe)), L.ptr(_f32(dbe))
     L.call("dsg_topology_bwd", C.byref(a), L.stream())
+
+
+def ctr_topology(H, n, V, R, Cn, A, alpha, W4, b4, *, adyn=None, dadyn=None, dH=None, dH_bf16=None, dA=None, dalpha=None, dW4=None,
+                 db4=None):
+    """dsg_ctr_topology_fwd (adyn given) / _bwd (dadyn given)"""
+    a = L.CtrTopologyArgs()
+    a.H, a.ld_h = L.ptr(H), _ld(H)
+    a.n_samples, a.V, a.R, a.C = n, V, R, Cn
+    a.A, a.alpha, a.W4, a.b4 = L.ptr(_f32(A)), L.ptr(_f32(alpha)), L.ptr(_f32(W4)), L.ptr(_f32(b4))
+    if adyn is not None:
+        a.adyn, a.adyn_dtype = L.ptr(adyn), L.dt(adyn)
+        L.call("dsg_ctr_topology_fwd", C.byref(a), L.stream())
+        return
+    assert dadyn.dtype == torch.float32 and dH.dtype == torch.float32 and _ld(dH) == _ld(H)
+    a.dadyn, a.dH = L.ptr(dadyn), L.ptr(dH)
+    if dH_bf16 is not None:
+        assert dH_bf16.dtype == torch.bfloat16 and dH_bf16.is_contiguous() and dH_bf16.shape == dH.shape and dH.is_contiguous()
+        a.dH_bf16 = L.ptr(dH_bf16)
+    a.dA, a.dalpha, a.dW4, a.db4 = L.ptr(_f32(dA)), L.ptr(_f32(dalpha)), L.ptr(_f32(dW4)), L.ptr(_f32(db4))
+    L.call("dsg_ctr_topology_bwd", C.byref(a), L.stream())
 
 
 def graph_agg(src, out, *, mode, n_samples, T, V, KC, adyn=None, A=None, Ksub=0, mask=None, stat_sum=None, stat_sq=None,

@@ -48,6 +48,7 @@ BACKBONES = HEADS = RECOGNIZERS = LOSSES = NECKS = MODELS     # one registry und
 
 MODELS.register_module(module=modules.DGSTGCN)
 MODELS.register_module(module=modules.STGCN)
+MODELS.register_module(module=modules.CTRGCN)
 
 
 def build_backbone(cfg):

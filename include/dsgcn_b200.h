@@ -193,9 +193,43 @@ typedef struct dsg_topology_args {
     float* dWe;
     float* dbe;
     void* dH_bf16;            /* optional bf16 copy of dH (same pitch): operand of the tensor-core GEMMs that consume it */
+    /* flag variants of the same unit (gcn.py:1445-1584 dggcn; dghgcn :1586 / dgphgcn :1808 / dgphgcn1 with the attention flags off):
+     * variant 1 = plain DG-GCN topology: H[n, v, 6R] = [conv1 (3R) | conv2 (3R)], every subset uses tanh(x1[u]-x2[w]); node_type,
+     * edge_type, We, be, dWe, dbe are unused (may be NULL).  subset_wise = 0: alpha[0] / beta[0] scale every subset (and receive
+     * the whole gradient), gcn.py:1543-1546. */
+    int variant;
+    int subset_wise;
 } dsg_topology_args;
 int dsg_topology_fwd(const dsg_topology_args* a, void* stream);
 int dsg_topology_bwd(const dsg_topology_args* a, void* stream);
+
+/* ---- dsg_ctr_topology_fwd / dsg_ctr_topology_bwd ---------------------------------------------
+ * Channel-wise topology refinement of CTR-GCN: the three CTRGC modules of one unit_ctrgcn (gcn.py:650-659, :914-918).
+ * H[n, v, 6R] = xm @ [conv1_0; conv1_1; conv1_2; conv2_0; conv2_1; conv2_2]^T + bias (dsg_conv_gemm on the temporal mean).
+ * adyn[n, u, w, k*C + c] = alpha * (sum_r W4_k[c,r] * tanh(x1_k[r,u] - x2_k[r,w]) + b4_k[c]) + A[k,u,w]   (dtype adyn_dtype),
+ * the operand of dsg_graph_agg mode 0 over conv3's output (einsum 'ncuv,nctu->nctv').  Backward consumes dAdyn[n,u,w,3C]
+ * (fp32), writes dH (layout of H) and atomically accumulates dA[3,V,V], dalpha[1], dW4[3,C,R], db4[3,C]. */
+typedef struct dsg_ctr_topology_args {
+    const float* H;
+    long long ld_h;
+    int n_samples, V, R, C;
+    const float* A;           /* [3,V,V] */
+    const float* alpha;       /* [1] */
+    const float* W4;          /* [3,C,R]  conv4 weights of convs[0..2] */
+    const float* b4;          /* [3,C] */
+    void* adyn;
+    int adyn_dtype;
+    /* backward only */
+    const float* dadyn;       /* [n, V, V, 3C] */
+    float* dH;
+    void* dH_bf16;            /* optional bf16 copy of dH */
+    float* dA;
+    float* dalpha;
+    float* dW4;
+    float* db4;
+} dsg_ctr_topology_args;
+int dsg_ctr_topology_fwd(const dsg_ctr_topology_args* a, void* stream);
+int dsg_ctr_topology_bwd(const dsg_ctr_topology_args* a, void* stream);
 
 /* ---- dsg_graph_agg --------------------------------------------------------------------------
  * y[n,t,w,kc] = sum_u p[n,t,u,kc] * adj(n,kc,u,w)    — the adjacency contraction.

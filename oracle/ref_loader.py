@@ -115,6 +115,7 @@ def load():
         _mod(p)
     graph = _load("utils.graph", "pyskl/utils/graph.py")
     _mod(f"{_PKG}.utils", Graph=graph.Graph, cache_checkpoint=lambda x: x, graph=graph)
+    sys.modules[f"{_PKG}.utils.graph"] = graph
     _mod(f"{_PKG}.models.builder", BACKBONES=_Registry("backbones"))
     _load("models.gcns.utils.init_func", "pyskl/models/gcns/utils/init_func.py")
     gcn = _load("models.gcns.utils.gcn", "pyskl/models/gcns/utils/gcn.py")
@@ -130,6 +131,15 @@ def load():
     _loaded.update(Graph=graph.Graph, graph_module=graph, unit_gcn=gcn.unit_gcn, dgphgcn1=gcn.dgphgcn1,
                    dggcn=gcn.dggcn, unit_tcn=tcn.unit_tcn, mstcn=tcn.mstcn, dgmstcn=tcn.dgmstcn,
                    DGBlock=dg.DGBlock, DGSTGCN=dg.DGSTGCN)
+    _loaded.update(dghgcn=gcn.dghgcn, dgphgcn=gcn.dgphgcn, unit_ctrgcn=gcn.unit_ctrgcn, CTRGC=gcn.CTRGC)
+    try:   # config-5 extras: MSTCN (msg3d_utils.py:64-150) and the CTR-GCN backbone (ctrgcn.py)
+        ms = _load("models.gcns.utils.msg3d_utils", "pyskl/models/gcns/utils/msg3d_utils.py")
+        _mod(f"{_PKG}.models.gcns.utils", MSTCN=ms.MSTCN)
+        _loaded.update(MSTCN=ms.MSTCN)
+        ct = _load("models.gcns.ctrgcn", "pyskl/models/gcns/ctrgcn.py")
+        _loaded.update(CTRGCN=ct.CTRGCN, CTRGCNBlock=ct.CTRGCNBlock)
+    except Exception as e:  # pragma: no cover
+        _loaded.update(MSTCN=None, CTRGCN=None, CTRGCNBlock=None, ctrgcn_error=repr(e))
     try:
         st = _load("models.gcns.stgcn", "pyskl/models/gcns/stgcn.py")
         _loaded.update(STGCN=st.STGCN, STGCNBlock=st.STGCNBlock)

@@ -120,6 +120,60 @@ def main():
             if p.grad is not None and (k.startswith("gcn.0.") or k.startswith("gcn.4.") or k.startswith("gcn.8.gcn") or k.startswith("data_bn")):
                 og["grad|" + k] = p.grad.numpy().copy()
         np.savez_compressed(os.path.join(HERE, f"{name}_small.npz"), **og)
+    # 6. config-5 variants on the same kernel library: the plain DG-GCN unit (dggcn + mstcn, the original DG-STGCN block),
+    #    MSTCN (msg3d_utils.py) and CTR-GCN (unit_ctrgcn + MSTCN).  Small widths; forward (eval + train) and backward.
+    def run_model(m, x, sel):
+        og = {"x": x.numpy()}
+        for k, v in m.state_dict().items():
+            og["sd|" + k] = v.numpy().copy()
+        m.eval()
+        with torch.no_grad():
+            og["y_eval"] = m(x).numpy()
+        m.train()
+        xr = x.clone().requires_grad_()
+        y = m(xr)
+        gy = torch.randn(y.shape, generator=torch.Generator().manual_seed(8))
+        y.backward(gy)
+        og["y_train"], og["gy"], og["gx"] = y.detach().numpy(), gy.numpy(), xr.grad.numpy()
+        for k, p in m.named_parameters():
+            if p.grad is not None and sel(k):
+                og["grad|" + k] = p.grad.numpy().copy()
+        return og
+
+    def settle(m, x, iters=30):
+        """run the reference in train mode so the running statistics describe the activations (eval mode then stays in range)"""
+        m.train()
+        with torch.no_grad():
+            for _ in range(iters):
+                m(x)
+
+    torch.manual_seed(9); np.random.seed(9)
+    g = ns.Graph(layout="nturgb+d", mode="random", num_filter=3, init_off=.04, init_std=.02)
+    A = torch.tensor(g.A, dtype=torch.float32)
+    for name, kw in (("dggcn_block", dict(gcn_type="dggcn", gcn_ratio=0.25, tcn_type="mstcn")),
+                     ("dggcn_block_sw", dict(gcn_type="dggcn", gcn_ratio=0.25, gcn_subset_wise=True, tcn_type="dgmstcn"))):
+        blk = ns.DGBlock(16, 24, A.clone(), torch.tensor(g.edge_type, dtype=torch.float32), torch.tensor(g.node_type), 2, **kw)
+        sd = blk.state_dict(); O.randomize_state(sd, 10); blk.load_state_dict(sd)
+        xb = torch.randn(3, 16, 12, 25, generator=torch.Generator().manual_seed(11))
+        settle(blk, xb)
+        np.savez_compressed(os.path.join(HERE, f"{name}.npz"), **run_model(blk, xb, lambda k: True))
+    torch.manual_seed(12)
+    ms = ns.MSTCN(20, 20, kernel_size=5, stride=2, dilations=[1, 2], residual=True)
+    sd = ms.state_dict(); O.randomize_state(sd, 13); ms.load_state_dict(sd)
+    xb = torch.randn(3, 20, 12, 25, generator=torch.Generator().manual_seed(14))
+    settle(ms, xb)
+    np.savez_compressed(os.path.join(HERE, "mstcn_msg3d.npz"), **run_model(ms, xb, lambda k: True))
+    torch.manual_seed(15); np.random.seed(15)
+    ct = ns.CTRGCN(graph_cfg=dict(layout="nturgb+d", mode="spatial"), base_channels=16, gcn_type="unit_ctrgcn")
+    sd = ct.state_dict(); O.randomize_state(sd, 16)
+    for k in sd:
+        if k.endswith("gcn1.alpha"):
+            sd[k] = sd[k] * 0.3
+    ct.load_state_dict(sd)
+    xs = torch.randn(2, 2, 12, 25, 3, generator=torch.Generator().manual_seed(17))
+    settle(ct, xs)
+    np.savez_compressed(os.path.join(HERE, "ctrgcn_small.npz"),
+                        **run_model(ct, xs, lambda k: k.startswith(("net.0.", "net.4.", "net.9.gcn1", "data_bn"))))
     for f in os.listdir(HERE):
         print(f, os.path.getsize(os.path.join(HERE, f)))
 

@@ -47,7 +47,7 @@ def test_binding_matches_header():
 #include <stdio.h>
 #include "dsgcn_b200.h"
 int main(void) {
-  printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(dsg_act_src), sizeof(dsg_conv_gemm_args), sizeof(dsg_conv_wgrad_args),
+  printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(dsg_ctr_topology_args), sizeof(dsg_act_src), sizeof(dsg_conv_gemm_args), sizeof(dsg_conv_wgrad_args),
          sizeof(dsg_bn_job), sizeof(dsg_topology_args), sizeof(dsg_graph_agg_args), sizeof(dsg_graph_agg_dadj_args),
          sizeof(dsg_ms_combine_args), sizeof(dsg_pointwise_args), sizeof(dsg_ms_branch), sizeof(dsg_ms_temporal_args));
   return 0;
@@ -59,7 +59,7 @@ int main(void) {
         exe = os.path.join(d, "s")
         subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), c, "-o", exe], check=True)
         sizes = [int(x) for x in subprocess.run([exe], capture_output=True, text=True, check=True).stdout.split()]
-    mirror = [L.ActSrc, L.ConvGemmArgs, L.ConvWgradArgs, L.BnJob, L.TopologyArgs, L.GraphAggArgs, L.GraphAggDadjArgs, L.MsCombineArgs,
+    mirror = [L.CtrTopologyArgs, L.ActSrc, L.ConvGemmArgs, L.ConvWgradArgs, L.BnJob, L.TopologyArgs, L.GraphAggArgs, L.GraphAggDadjArgs, L.MsCombineArgs,
               L.PointwiseArgs, L.MsBranch, L.MsTemporalArgs]
     assert sizes == [ctypes.sizeof(m) for m in mirror]
 

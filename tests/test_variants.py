@@ -1,0 +1,194 @@
+"""Config-5 / flag-variant units on the same kernel library:
+  dggcn (gcn.py:1445-1584) and the attention-free flag sets of dghgcn / dgphgcn / dgphgcn1 — dsg_topology_* variant 1;
+  MSTCN (msg3d_utils.py:64-150) — branch-stage kernels of mstcn without the transform conv;
+  CTRGC / unit_ctrgcn / CTRGCNBlock / CTRGCN (gcn.py:634-666, :882-930, ctrgcn.py) — dsg_ctr_topology_* + dsg_graph_agg.
+Golden vectors come from the unmodified reference (tests/golden/make_golden.py section 6); the oracle restatements are pinned
+on them too, and — where the reference tree is present — the modules are compared with the live reference classes."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from dsgcn_b200 import modules as M
+from oracle import dsgcn_oracle as O
+from oracle import ref_loader as rl
+
+G = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def rel(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return float((a - b).norm() / (b.norm() + 1e-12))
+
+
+def _load(name):
+    z = np.load(os.path.join(G, f"{name}.npz"))
+    sd = {k[3:]: torch.from_numpy(z[k].copy()) for k in z.files if k.startswith("sd|")}
+    return z, sd
+
+
+def _graph_tables():
+    np.random.seed(9)
+    from dsgcn_b200.graph import Graph
+    g = Graph(layout="nturgb+d", mode="random", num_filter=3, init_off=.04, init_std=.02)
+    return torch.tensor(g.A, dtype=torch.float32), torch.tensor(g.edge_type, dtype=torch.float32), torch.tensor(g.node_type)
+
+
+def _build(name):
+    if name.startswith("dggcn_block"):
+        A, et, nt = _graph_tables()
+        kw = (dict(gcn_type="dggcn", gcn_ratio=0.25, tcn_type="mstcn") if name == "dggcn_block" else
+              dict(gcn_type="dggcn", gcn_ratio=0.25, gcn_subset_wise=True, tcn_type="dgmstcn"))
+        return M.DGBlock(16, 24, A, et, nt, 2, **kw)
+    if name == "mstcn_msg3d":
+        return M.MSTCN(20, 20, kernel_size=5, stride=2, dilations=[1, 2], residual=True)
+    np.random.seed(15)
+    return M.CTRGCN(graph_cfg=dict(layout="nturgb+d", mode="spatial"), base_channels=16, gcn_type="unit_ctrgcn")
+
+
+def _oracle(name, x, sd, training):
+    if name.startswith("dggcn_block"):
+        g = O.dggcn_forward(x, O._sub(sd, "gcn"), subset_wise=name.endswith("_sw"), training=training)
+        tcn = O.dgmstcn_forward if name.endswith("_sw") else O.mstcn_forward
+        y = tcn(g, O._sub(sd, "tcn"), stride=2, training=training)
+        return torch.relu(y + O.unit_tcn_forward(x, O._sub(sd, "residual"), 1, 2, 1, True, training))
+    if name == "mstcn_msg3d":
+        return O.MSTCN_forward(x, sd, 5, 2, (1, 2), "conv", training)
+    return O.ctrgcn_forward(x, sd, base_channels=16, training=training)
+
+
+NAMES = ["dggcn_block", "dggcn_block_sw", "mstcn_msg3d", "ctrgcn_small"]
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_oracle_variants_vs_golden(name):
+    z, sd = _load(name)
+    x = torch.from_numpy(z["x"])
+    y = _oracle(name, x, {k: v.clone() for k, v in sd.items()}, False)
+    assert rel(y, torch.from_numpy(z["y_eval"])) < 1e-5
+    sdt = {k: v.clone() for k, v in sd.items()}
+    for k, v in sdt.items():
+        if v.is_floating_point() and not k.endswith(("running_mean", "running_var")):
+            v.requires_grad_()
+    xr = x.clone().requires_grad_()
+    y = _oracle(name, xr, sdt, True)
+    assert rel(y, torch.from_numpy(z["y_train"])) < 1e-5
+    y.backward(torch.from_numpy(z["gy"]))
+    deep = name == "ctrgcn_small"       # 10 blocks deep: fp32 re-association flips ReLU masks (same allowance as tests/test_stgcn.py)
+    assert rel(xr.grad, torch.from_numpy(z["gx"])) < (2e-2 if deep else 2e-3)
+    gmax = max(float(np.linalg.norm(z[k])) for k in z.files if k.startswith("grad|"))
+    for k in z.files:
+        if k.startswith("grad|"):
+            g, r = sdt[k[5:]].grad, torch.from_numpy(z[k])
+            assert (g - r).norm() <= (2e-2 if deep else 2e-3) * r.norm() + 1e-5 * gmax, k
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("name", NAMES)
+def test_variants_vs_golden(dev, dtype, name):
+    z, sd = _load(name)
+    m = _build(name)
+    assert list(m.state_dict().keys()) == list(sd.keys())          # checkpoint drop-in
+    m.load_state_dict(sd)
+    m.to(dev)
+    x = torch.from_numpy(z["x"]).to(dev)
+    M.set_compute_dtype(dtype)
+    f32 = dtype == torch.float32
+    try:
+        m.eval()
+        with torch.no_grad():
+            y = m(x)
+        assert y.shape == z["y_eval"].shape
+        assert rel(y, torch.from_numpy(z["y_eval"])) < (1e-4 if f32 else 2e-2)
+        m.train()
+        xr = x.clone().requires_grad_()
+        y = m(xr)
+        e = rel(y, torch.from_numpy(z["y_train"]))
+        # bf16: toy train-mode batches amplify rounding (see tests/test_stgcn.py); fp32 is the parity bound proper
+        assert e < (1e-4 if f32 else 6e-2), e
+        y.backward(torch.from_numpy(z["gy"]).to(dev).to(y.dtype))
+        if f32:
+            deep = name == "ctrgcn_small"
+            assert rel(xr.grad, torch.from_numpy(z["gx"])) < (3e-2 if deep else 3e-3)
+            params = dict(m.named_parameters())
+            gmax = max(float(np.linalg.norm(z[k])) for k in z.files if k.startswith("grad|"))
+            for k in z.files:
+                if k.startswith("grad|"):
+                    g, r = params[k[5:]].grad.detach().cpu(), torch.from_numpy(z[k])
+                    assert (g - r).norm() <= (3e-2 if deep else 3e-3) * r.norm() + 1e-4 * gmax, k
+            for k, p in m.named_parameters():           # every parameter the reference trains gets a gradient here too
+                assert p.grad is not None, k
+        else:
+            keys = [k for k in z.files if k.startswith("grad|")]
+            params = dict(m.named_parameters())
+            refv = torch.cat([torch.from_numpy(z[k]).double().reshape(-1) for k in keys])
+            mine = torch.cat([params[k[5:]].grad.detach().double().cpu().reshape(-1) for k in keys])
+            cos = float(torch.dot(mine, refv) / (mine.norm() * refv.norm()))
+            print(f"{name} bf16: train fwd rel {e:.3e}, gradient cosine {cos:.3f}")
+            assert cos > 0.9
+    finally:
+        M.set_compute_dtype(torch.bfloat16)
+
+
+@pytest.mark.skipif(not rl.available(), reason="reference tree not present")
+@pytest.mark.parametrize("cls", ["dggcn", "dghgcn", "dgphgcn", "dgphgcn1_stage_off", "unit_ctrgcn", "MSTCN"])
+def test_variant_units_vs_live_reference(dev, cls):
+    """fp32 forward / input gradient / parameter gradients of the single units against the unmodified reference classes."""
+    if dev.type != "cpu":
+        pytest.skip("live-reference comparison runs on the simulator build (the GPU path is held by the golden fixtures)")
+    ns = rl.load()
+    torch.manual_seed(3)
+    A, et, nt = _graph_tables()
+    cin, cout = 16, 24
+    if cls == "dggcn":
+        mk = lambda mod: mod.dggcn(cin, cout, A.clone(), ratio=0.25, subset_wise=True)
+    elif cls == "dghgcn":
+        mk = lambda mod: mod.dghgcn(cin, cout, A.clone(), et, nt, ratio=0.25)
+    elif cls == "dgphgcn":
+        mk = lambda mod: mod.dgphgcn(cin, cout, A.clone(), et, nt, ratio=0.25, part_ratio=1, subset_wise=True)
+    elif cls == "dgphgcn1_stage_off":
+        mk = lambda mod: mod.dgphgcn1(cin, cout, A.clone(), et, nt, ratio=0.25, decompose=True, node_attention=True,
+                                      edge_attention=True, stage=False)
+    elif cls == "unit_ctrgcn":
+        mk = lambda mod: mod.unit_ctrgcn(cin, cout, A.clone())
+    else:
+        mk = lambda mod: mod.MSTCN(cin, cout, kernel_size=[3, 5], stride=1, dilations=[1, 3], residual=True)
+    r, m = mk(ns), mk(M)
+    sd = r.state_dict()
+    O.randomize_state(sd, 4)
+    r.load_state_dict(sd)
+    assert list(m.state_dict().keys()) == list(sd.keys())
+    m.load_state_dict(sd)
+    M.set_compute_dtype(torch.float32)
+    try:
+        x = torch.randn(3, cin, 8, 25)
+        for mode in ("eval", "train"):
+            getattr(r, mode)(), getattr(m, mode)()
+            xr, xm = x.clone().requires_grad_(), x.clone().requires_grad_()
+            yr, ym = r(xr), m(xm)
+            assert rel(ym, yr) < 1e-4
+            gy = torch.randn_like(yr)
+            r.zero_grad(), m.zero_grad()
+            yr.backward(gy), ym.backward(gy)
+            assert rel(xm.grad, xr.grad) < 1e-4
+            pr = dict(r.named_parameters())
+            gmax = max(float(p.grad.norm()) for p in pr.values() if p.grad is not None)
+            for k, p in m.named_parameters():
+                assert (p.grad is None) == (pr[k].grad is None), k
+                if p.grad is not None:
+                    assert float((p.grad - pr[k].grad).norm()) <= 1e-4 * float(pr[k].grad.norm()) + 1e-5 * gmax, k
+    finally:
+        M.set_compute_dtype(torch.bfloat16)
+
+
+def test_unbuilt_flag_sets_raise():
+    A, et, nt = _graph_tables()
+    with pytest.raises(NotImplementedError):
+        M.dghgcn(16, 16, A, et, nt, node_attention=True)
+    with pytest.raises(NotImplementedError):
+        M.dggcn(16, 16, A, ctr="NA")
+    with pytest.raises(TypeError):
+        M.dgphgcn(16, 16, A, et, nt)                  # the reference's default part_ratio=0.4 fails at gcn.py:1892 (bool & float)
+    with pytest.raises(NotImplementedError):
+        M.CTRGCNBlock(16, 16, A)                      # default gcn_type is the author's unit_ctrhgcn experiment

@@ -24,6 +24,8 @@ FILES = [
     "pyskl/models/gcns/utils/tcn.py",            # unit_tcn, mstcn, dgmstcn (a10-a13)
     "pyskl/models/gcns/dgstgcn.py",              # DGBlock, DGSTGCN (a4-a6)
     "pyskl/models/gcns/stgcn.py",                # STGCN / STGCNBlock (config 5)
+    "pyskl/models/gcns/utils/msg3d_utils.py",    # MSTCN (config 5, CTR-GCN's temporal unit)
+    "pyskl/models/gcns/ctrgcn.py",               # CTRGCN / CTRGCNBlock (config 5)
     "LICENSE",
 ]
 
