@@ -666,7 +666,7 @@ def main():
             model.train(True)
         except Exception as e:
             extra["fwd"] = dict(unavailable=f"{type(e).__name__}: {str(e)[:200]}")
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:      # the CPU baseline is reported at N=1 only (rank 0's host cores)
         cpu = cpu_baseline_leg(args.mode, args.ref_clips, 2, 1, budget_s=40.0)
     if not args.no_ref_gpu and world == 1:
         # context only (never a denominator): the unmodified reference run eagerly on this GPU, same batch as the product arm

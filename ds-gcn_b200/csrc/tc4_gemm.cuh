@@ -79,19 +79,20 @@ struct G4Plan {
 //      per k when a BatchNorm-backward / affine prologue is folded in; cbias[n] = bias[n] + sum_k (c1[k] + c2[k]) W[n,k]
 __global__ void __launch_bounds__(256) tc4_wpack_kernel(const float* W, long long ws_n, long long ws_k, int K, int N, int natoms1, int natoms,
                                                         int Ntile, const float* s1, const float* s2, const float* c1, const float* c2,
-                                                        const float* bias, unsigned char* out, float* cbias) {
+                                                        const float* bias, unsigned char* out, float* cbias, float fold_scale = 1.f) {
     const int j = blockIdx.x, a = blockIdx.y;
     if (a == natoms) {                                  // folded bias for this column tile
         for (int nl = threadIdx.x; nl < Ntile; nl += 256) {
             const int n = j * Ntile + nl;
             if (n >= N) continue;
-            float acc = bias ? bias[n] : 0.f;
+            float acc = 0.f;
             if (c1 || c2)
                 for (int k = 0; k < K; ++k) {
                     const float c = (c1 ? c1[k] : 0.f) + (c2 ? c2[k] : 0.f);
                     acc = fmaf(c, W[(long long)n * ws_n + (long long)k * ws_k], acc);
                 }
-            cbias[n] = acc;
+            // contract_ext: every joint row receives its own folded constant AND 1/V of the mean row's (fold_scale = 1 + 1/V)
+            cbias[n] = fmaf(acc, fold_scale, bias ? bias[n] : 0.f);
         }
         return;
     }
@@ -476,12 +477,18 @@ tc4_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
             unsigned char* St = Ssm + (size_t)ob * p.out_bytes;
             const uint32_t acc = tmem + (uint32_t)(buf * p.acc_cols) + ((uint32_t)(q * 32) << 16);
             const bool row_ok = gr >= 0;
+            const bool fold2 = !XF && p.mode == 2;       // gradient of the joint mean folded back on the accumulator (lane V of this warp)
+            const float inv2 = 1.f / (float)p.V;
             for (int cc = cbeg; cc < cend; ++cc) {
                 const int c16 = cc * 16;
                 float v[16];
                 if (!TAILS) {
                     // ---- lean path: bias, bf16 pack, (square for the statistics), conflict-free 16-byte stores
                     tmem_ld16(acc + (uint32_t)c16, v);
+                    if (fold2) {
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) v[e] = fmaf(__shfl_sync(0xffffffffu, v[e], p.V), inv2, v[e]);
+                    }
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
                         const int col = c16 + h * 8;
@@ -524,6 +531,10 @@ tc4_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
                         }
                     }
                     tmem_ld16(acc + (uint32_t)c16, v);
+                    if (fold2) {
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) v[e] = fmaf(__shfl_sync(0xffffffffu, v[e], p.V), inv2, v[e]);
+                    }
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
                         const int col = c16 + h * 8;                     // column inside the CTA tile
@@ -693,7 +704,9 @@ static bool tc4_plan(const dsg_conv_gemm_args& a, G4Plan& p, bool fold) {
     }
     p.K1p = kat * ATOM_CH;
     p.act = (!fold) ? 1 : 0;                              // ReLU sources (one tensor): CUDA-core prologue in place
-    p.xf = (p.act || p.mode != 0) ? 1 : 0;
+    // mode 2 with 32-row frame slots and no ReLU prologue: the fold-back is linear, so it is applied to the ACCUMULATOR rows in the
+    // epilogue (a frame = one warp's 32 TMEM lanes: out[v] += out[V] / V is one shuffle per column) and no thread touches the operand
+    p.xf = (p.act || p.mode == 1 || (p.mode == 2 && p.slot != 32)) ? 1 : 0;
     p.stats = a.stat_sum == nullptr ? 0 : (a.partner ? 2 : 1);
     const unsigned cf_bytes = (unsigned)((4 * 128 + 2 * p.K1p) * sizeof(float));
     const unsigned budget = 227u * 1024u - 2048u;         // dynamic shared memory we may ask for (static barriers + alignment slack kept)
@@ -877,7 +890,8 @@ static const char* launch_conv_gemm_tc4(const dsg_conv_gemm_args& a, dsg_stream_
     const float* c1 = fold ? a.src.b1 : nullptr;
     const float* c2 = fold ? a.src.b2 : nullptr;
     tc4_wpack_kernel<<<dim3(gy, (unsigned)p.natoms + 1), dim3(256), 0, st>>>(a.W, a.ws_n, a.ws_k, a.K, a.N, p.natoms1, p.natoms, p.Ntile, s1, s2, c1, c2,
-                                                                            a.bias, reinterpret_cast<unsigned char*>(a.wpack), cbias);
+                                                                            a.bias, reinterpret_cast<unsigned char*>(a.wpack), cbias,
+                                                                            p.mode == 2 ? 1.f + 1.f / (float)p.V : 1.f);
     if (const char* e = dsg_launch_error()) return e;
     int gx = num_sms() / (int)gy;
     if (gx < 1) gx = 1;

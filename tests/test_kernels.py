@@ -265,6 +265,32 @@ def test_conv_gemm_joint_mean_row(dev, dtype):
     close(dW, wr.grad, dtype, "ext wgrad")
 
 
+@pytest.mark.parametrize("V", [25, 17])
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_conv_gemm_contract_ext_bn_backward_form(dev, dtype, V):
+    """The last backward GEMM of dgmstcn: dg = fold(ca*e + cb*y + cc) @ W with the joint-mean row folded back (tcn.py:409 backward),
+    ReLU mask + BatchNorm-backward sums of the consumer in the epilogue.  The constant cc reaches every joint row (1 + 1/V) times.
+    V = 25: frame slot = one warp (fold on the accumulator in the epilogue of the TMA engine); V = 17: operand-side fold."""
+    torch.manual_seed(11)
+    n, T, K, N = 3, 6, 64, 32
+    rows_in, rows_out = n * T * (V + 1), n * T * V
+    e, y = rnd(rows_in, K, dev=dev, dtype=dtype), rnd(rows_in, K, dev=dev, dtype=dtype)
+    ca, cb, cc = torch.rand(K, device=dev) + 0.5, rnd(K, dev=dev, scale=0.3), rnd(K, dev=dev, scale=2.0)
+    W = rnd(K, N, dev=dev, scale=0.2)                      # backward weight [K_in_of_forward? no: dB channels K -> dg channels N]
+    mask, partner = rnd(rows_out, N, dev=dev, dtype=dtype), rnd(rows_out, N, dev=dev, dtype=dtype)
+    out = torch.empty(rows_out, N, dtype=dtype, device=dev)
+    ssum, ssq = torch.zeros(N, dtype=torch.float64, device=dev), torch.zeros(N, dtype=torch.float64, device=dev)
+    # W is passed as the forward weight [K, N] read transposed (ws = (1, N, 0)): out = dy @ W
+    ops.conv_gemm(ops.Act(e, ca, cc, y, cb), W, N, out, n_samples=n, T_in=T, T_out=T, Vin=V + 1, ws=(1, N, 0), contract_ext=True,
+                  mask=mask, stat_sum=ssum, stat_sq=ssq, partner=partner)
+    dy = (e.float() * ca + y.float() * cb + cc).view(n * T, V + 1, K)
+    folded = (dy[:, :V] + dy[:, V:] / V).reshape(rows_out, K)
+    ref = (folded @ W) * (mask.float() > 0)
+    close(out, ref, dtype, "contract_ext dgrad")
+    close(ssum, ref.double().sum(0), dtype, "sum e")
+    close(ssq, (ref.double() * partner.double()).sum(0), dtype, "sum e*partner")
+
+
 def test_bn_finalize_matches_batch_norm(dev):
     torch.manual_seed(3)
     Cn, M = 37, 500
