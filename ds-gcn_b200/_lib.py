@@ -139,6 +139,7 @@ EXPORTS = {
     "dsg_ms_temporal_bwd_weight": (c_int, [C.POINTER(MsTemporalArgs), vp]),
     "dsg_ms_conv_wpack_bytes": (c_ll, [C.POINTER(MsConvArgs)]),
     "dsg_ms_conv": (c_int, [C.POINTER(MsConvArgs), C.POINTER(c_int), vp]),
+    "dsg_ms_conv_wgrad": (c_int, [C.POINTER(MsConvArgs), C.POINTER(c_int), vp]),
     "dsg_sgd_step": (c_int, [vp, vp, vp, c_ll, c_f, c_f, c_f, c_int, c_f, vp]),
     "dsg_sgd_step_dev": (c_int, [vp, vp, vp, c_ll, vp, c_f, c_f, c_int, c_f, vp]),
     "dsg_debug_counter": (c_ll, [c_int]),

@@ -7,6 +7,7 @@
 #include "tc4_gemm.cuh"
 #include "tc4_wgrad.cuh"
 #include "tc4_tconv.cuh"
+#include "tc4_twgrad.cuh"
 #include "graph_agg.cuh"
 #include "ms_temporal_tc.cuh"
 #include "topology.cuh"
@@ -311,6 +312,22 @@ int dsg_ms_conv(const dsg_ms_conv_args* a, int* handled, void* stream) {
     const char* e = dsg::tc4::launch_ms_conv_tc4(*a, (dsg_stream_t)stream, &h);
     if (e) return fail("dsg_ms_conv", e);
     if (h) { *handled = 1; ++g_counters[3]; }
+    return 0;
+#endif
+}
+
+int dsg_ms_conv_wgrad(const dsg_ms_conv_args* a, int* handled, void* stream) {
+    if (!a || !handled) return fail("dsg_ms_conv_wgrad", "bad arguments");
+    *handled = 0;
+#ifdef DSG_EMU
+    (void)stream;
+    return 0;                                                         // tcgen05 + TMA kernel: the simulator build always declines
+#else
+    if (!tc_enabled()) return 0;
+    bool h = false;
+    const char* e = dsg::tc4::launch_ms_conv_wgrad_tc4(*a, (dsg_stream_t)stream, &h);
+    if (e) return fail("dsg_ms_conv_wgrad", e);
+    if (h) { *handled = 1; ++g_counters[4]; }
     return 0;
 #endif
 }

@@ -68,8 +68,18 @@ DSG_D float topo_arg1(const TopoSmem& sm, const float* We_s, const float* be_s, 
     return s;
 }
 
+// bf16 compute mode: the adjacency is rounded to bf16 (8 mantissa bits) right after, so the hardware tanh (MUFU.TANH, ~2^-11
+// relative error, one instruction instead of ~40) is exact enough; the fp32 parity mode keeps tanhf.
+template <bool FAST> DSG_D float topo_tanh(float x) {
+#ifndef DSG_EMU
+    if (FAST) { float y; asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+#endif
+    return tanhf(x);
+}
+
 template <class T>
 __global__ void __launch_bounds__(TP_THREADS) topology_fwd_kernel(dsg_topology_args a) {
+    constexpr bool FAST = sizeof(T) == 2;
     DSG_DYN_SMEM(smem_raw);
     const int R = a.R, V = a.V, VV = V * V, KC = 3 * R;
     TopoSmem sm(reinterpret_cast<float*>(smem_raw), R, V);
@@ -114,7 +124,7 @@ __global__ void __launch_bounds__(TP_THREADS) topology_fwd_kernel(dsg_topology_a
             const int kk = cc / R, c = cc - kk * R;
             const int k = plain ? kk : 2 * kk;
             const int u = uw / V, w = uw - u * V;
-            const float th = tanhf(sm.x1[(k * R + c) * V + u] - sm.x2[(k * R + c) * V + w]);
+            const float th = topo_tanh<FAST>(sm.x1[(k * R + c) * V + u] - sm.x2[(k * R + c) * V + w]);
             const float v = a.A[k * VV + uw] + (k == 0 ? al0 : k == 1 ? al1 : al2) * th + (k == 0 ? be0 : k == 1 ? be1 : be2) * sm.S[k * VV + uw];
             stf<T>(out + (long long)uw * KC + k * R + c, v);
         }
@@ -122,7 +132,7 @@ __global__ void __launch_bounds__(TP_THREADS) topology_fwd_kernel(dsg_topology_a
         for (int idx = tid; !plain && idx < VV * R; idx += TP_THREADS) {
             const int c = idx % R, uw = idx / R;
             const int u = uw / V, w = uw - u * V;
-            const float th = tanhf(topo_arg1(sm, We_s, be_s, R, V, a.edge_type[uw], c, u, w));
+            const float th = topo_tanh<FAST>(topo_arg1(sm, We_s, be_s, R, V, a.edge_type[uw], c, u, w));
             const float v = a.A[VV + uw] + al1 * th + be1 * sm.S[VV + uw];
             stf<T>(out + (long long)uw * KC + R + c, v);
         }
@@ -132,7 +142,8 @@ __global__ void __launch_bounds__(TP_THREADS) topology_fwd_kernel(dsg_topology_a
 // Backward.  Extra shared memory after TopoSmem:
 //   dx1,dx2 [3][R][V] each; dA_acc [3][V][V]; dWe_acc [15][R][R]; dbe_acc [15][R]; hbuf [V][R]; dbuf [V][R]; red[8];
 //   We_s [15][R][R+1] (row-padded weights); be_s [15][R]
-__global__ void __launch_bounds__(TP_BWD_THREADS) topology_bwd_kernel(dsg_topology_args a) {
+template <bool FAST, int NTB>
+__global__ void __launch_bounds__(NTB) topology_bwd_kernel(dsg_topology_args a) {
     DSG_DYN_SMEM(smem_raw);
     const int R = a.R, V = a.V, VV = V * V, KC = 3 * R;
     float* base = reinterpret_cast<float*>(smem_raw);
@@ -148,12 +159,22 @@ __global__ void __launch_bounds__(TP_BWD_THREADS) topology_bwd_kernel(dsg_topolo
     float* We_s = red + 8;
     float* be_s = We_s + 15 * R * (R + 1);
     const int tid = threadIdx.x, NT = blockDim.x;
-    unsigned char* et_s = reinterpret_cast<unsigned char*>(be_s + 15 * R);   // [V*V] edge types
+    float* d1s = be_s + 15 * R;                                               // [V][R] x1[1][:,u] - x2[1][:,w] of the current source joint
+    unsigned char* et_s = reinterpret_cast<unsigned char*>(d1s + V * R);      // [V*V] edge types
+    DSG_SHARED unsigned char ord_s[32 * 32];                                  // per source joint u: target joints sorted by edge type
     const bool plain = a.variant == 1;
     const int sw = a.subset_wise ? 1 : 0;
     if (!plain) {
         topo_stage_we(a, We_s, be_s);
         for (int idx = tid; idx < VV; idx += NT) et_s[idx] = (unsigned char)a.edge_type[idx];
+        if (tid < V) {                                                          // counting sort of row `tid` of the edge-type table
+            int q = 0;
+            for (int e = 0; e < 15; ++e)
+                for (int w = 0; w < V; ++w)
+                    if (a.edge_type[tid * V + w] == e) ord_s[tid * V + q++] = (unsigned char)w;
+            for (int w = 0; w < V; ++w)                                         // (types outside 0..14 never occur; keep the row complete)
+                if (a.edge_type[tid * V + w] < 0 || a.edge_type[tid * V + w] > 14) ord_s[tid * V + q++] = (unsigned char)w;
+        }
     }
     for (int idx = tid; idx < 3 * VV + 15 * R * R + 15 * R; idx += NT) dA_acc[idx] = 0.f;   // contiguous block
     if (tid < 8) red[tid] = 0.f;
@@ -212,12 +233,13 @@ __global__ void __launch_bounds__(TP_BWD_THREADS) topology_bwd_kernel(dsg_topolo
             if (k != 1 || plain) {
                 const float al = a.alpha[sw * k];
                 float da = 0.f;
+#pragma unroll 5
                 for (int o = 0; o < V; ++o) {
-                    float th = tanhf(x1r[v] - x2r[o]);                  // pair (u=v, w=o)
+                    float th = topo_tanh<FAST>(x1r[v] - x2r[o]);                  // pair (u=v, w=o)
                     float gg = g[(long long)(v * V + o) * KC + k * R + c];
                     da = fmaf(gg, th, da);
                     s1 = fmaf(al * (1.f - th * th), gg, s1);
-                    float th2 = tanhf(x1r[o] - x2r[v]);                 // pair (u=o, w=v)
+                    float th2 = topo_tanh<FAST>(x1r[o] - x2r[v]);                 // pair (u=o, w=v)
                     float gg2 = g[(long long)(o * V + v) * KC + k * R + c];
                     s2 = fmaf(-al * (1.f - th2 * th2), gg2, s2);
                 }
@@ -238,6 +260,13 @@ __global__ void __launch_bounds__(TP_BWD_THREADS) topology_bwd_kernel(dsg_topolo
         const float al1 = a.alpha[sw];
         const float* x1b = sm.x1 + R * V;
         const float* x2b = sm.x2 + R * V;
+        if (!plain) {                                                   // d1 of the first source joint (later ones are formed during (b))
+            for (int idx = tid; idx < V * R; idx += NT) {
+                const int i = idx % R, w = idx / R;
+                d1s[idx] = x1b[i * V] - x2b[i * V + w];
+            }
+            __syncthreads();
+        }
         for (int u = 0; !plain && u <= V; ++u) {
             if (u > 0 && tid < R) {                                     // dx1[1][i][u-1] += sum_w dd1[w][i]
                 float sacc = 0.f;
@@ -245,33 +274,68 @@ __global__ void __launch_bounds__(TP_BWD_THREADS) topology_bwd_kernel(dsg_topolo
                 dx1[(R + tid) * V + u - 1] += sacc;
             }
             if (u == V) break;
-            for (int idx = tid; idx < V * R; idx += NT) {       // (a)
+            for (int idx = tid; idx < V * R; idx += NT) {       // (a): two shared loads + FMA per term (row-padded weights, staged d1)
                 const int o = idx % R, w = idx / R;
                 const int e = (int)et_s[u * V + w];
-                const float th = tanhf(topo_arg1(sm, We_s, be_s, R, V, e, o, u, w));
-                const float gg = g[(long long)(u * V + w) * KC + R + o];
+                const float* wr = We_s + (e * R + o) * (R + 1);
+                const float* dr = d1s + w * R;
+                const float gg = g[(long long)(u * V + w) * KC + R + o];       // issued first: its latency hides behind the dot product
+                float a0 = be_s[e * R + o], a1 = 0.f, a2 = 0.f, a3 = 0.f;      // four independent chains (the loop was latency-bound)
+                int i = 0;
+                for (; i + 4 <= R; i += 4) {
+                    a0 = fmaf(wr[i], dr[i], a0);
+                    a1 = fmaf(wr[i + 1], dr[i + 1], a1);
+                    a2 = fmaf(wr[i + 2], dr[i + 2], a2);
+                    a3 = fmaf(wr[i + 3], dr[i + 3], a3);
+                }
+                for (; i < R; ++i) a0 = fmaf(wr[i], dr[i], a0);
+                const float th = topo_tanh<FAST>((a0 + a1) + (a2 + a3));
                 my_dalpha1 = fmaf(gg, th, my_dalpha1);
                 hbuf[idx] = al1 * (1.f - th * th) * gg;
             }
             __syncthreads();
-            for (int idx = tid; idx < R * R; idx += NT) {       // (b) dWe, dbe
+            // (b) dWe, dbe: the target joints are walked in edge-type order (few distinct types per source joint) with a register
+            //     accumulator and ONE read-modify-write of the shared accumulator per type (was one per target joint)
+            for (int idx = tid; idx < R * R; idx += NT) {
                 const int i = idx % R, o = idx / R;
                 const float x1u = x1b[i * V + u];
-                for (int w = 0; w < V; ++w) {
+                const unsigned char* ord = ord_s + u * V;
+                int e_cur = (int)et_s[u * V + ord[0]];
+                float acc = 0.f, hs = 0.f;
+                for (int q = 0; q < V; ++q) {
+                    const int w = ord[q];
                     const int e = (int)et_s[u * V + w];
+                    if (e != e_cur) {
+                        dWe_acc[(e_cur * R + o) * R + i] += acc;
+                        if (i == 0) dbe_acc[e_cur * R + o] += hs;
+                        acc = hs = 0.f;
+                        e_cur = e;
+                    }
                     const float h = hbuf[w * R + o];
-                    dWe_acc[(e * R + o) * R + i] = fmaf(h, x1u - x2b[i * V + w], dWe_acc[(e * R + o) * R + i]);
-                    if (i == 0) dbe_acc[e * R + o] += h;
+                    acc = fmaf(h, x1u - x2b[i * V + w], acc);
+                    hs += h;
                 }
+                dWe_acc[(e_cur * R + o) * R + i] += acc;
+                if (i == 0) dbe_acc[e_cur * R + o] += hs;
             }
-            for (int idx = tid; idx < V * R; idx += NT) {       // (b) dd1
+            for (int idx = tid; idx < V * R; idx += NT) {       // (b) dd1, and d1 of the next source joint
                 const int i = idx % R, w = idx / R;
                 const int e = (int)et_s[u * V + w];
                 const float* wc = We_s + e * R * (R + 1) + i;
-                float sacc = 0.f;
-                for (int o = 0; o < R; ++o) sacc = fmaf(wc[o * (R + 1)], hbuf[w * R + o], sacc);
+                float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+                const float* hr = hbuf + w * R;
+                int o = 0;
+                for (; o + 4 <= R; o += 4) {
+                    s0 = fmaf(wc[o * (R + 1)], hr[o], s0);
+                    s1 = fmaf(wc[(o + 1) * (R + 1)], hr[o + 1], s1);
+                    s2 = fmaf(wc[(o + 2) * (R + 1)], hr[o + 2], s2);
+                    s3 = fmaf(wc[(o + 3) * (R + 1)], hr[o + 3], s3);
+                }
+                for (; o < R; ++o) s0 = fmaf(wc[o * (R + 1)], hr[o], s0);
+                const float sacc = (s0 + s1) + (s2 + s3);
                 dbuf[idx] = sacc;
                 dx2[(R + i) * V + w] -= sacc;
+                if (u + 1 < V) d1s[idx] = x1b[i * V + u + 1] - x2b[i * V + w];
             }
             __syncthreads();
         }
@@ -305,7 +369,7 @@ __global__ void __launch_bounds__(TP_BWD_THREADS) topology_bwd_kernel(dsg_topolo
 }
 
 static inline size_t topo_bwd_smem_floats(int R, int V) {
-    return TopoSmem::floats(R, V) + (size_t)6 * R * V + 3 * V * V + 15 * R * R + 15 * R + 2 * V * R + 8 + 15 * R * (R + 1) + 15 * R + (V * V + 3) / 4;
+    return TopoSmem::floats(R, V) + (size_t)6 * R * V + 3 * V * V + 15 * R * R + 15 * R + 2 * V * R + 8 + 15 * R * (R + 1) + 15 * R + V * R + (V * V + 3) / 4;
 }
 
 static const char* launch_topology(const dsg_topology_args& a, bool bwd, dsg_stream_t st) {
@@ -323,10 +387,22 @@ static const char* launch_topology(const dsg_topology_args& a, bool bwd, dsg_str
         }
     } else {
         size_t smem = topo_bwd_smem_floats(a.R, a.V) * sizeof(float);
-        if (smem > 200 * 1024) return "topology_bwd: shared memory budget exceeded";
-        grid = a.n_samples < 148 ? a.n_samples : 148;
-        DSG_SET_SMEM(topology_bwd_kernel, smem);
-        dsg_launch(topology_bwd_kernel, dim3(grid), dim3(TP_BWD_THREADS), smem, st, a);
+        if (smem > 224 * 1024) return "topology_bwd: shared memory budget exceeded";
+        // the kernel is bound by the latency of its dependent global / shared round trips, not by issue slots (ncu: 50 % warps
+        // active, 2 % DRAM): where the accumulators leave room (R <= 16), two 512-thread CTAs share an SM and every sample gets
+        // its own CTA, so one CTA's barriers and load latencies hide behind the other's work
+        const bool small = smem <= 100 * 1024;
+        const int cap = small ? 2 * 148 : 148;
+        grid = a.n_samples < cap ? a.n_samples : cap;
+#define DSG_TOPO_BWD(FAST_, NT_)                                                                         \
+        do {                                                                                             \
+            DSG_SET_SMEM((topology_bwd_kernel<FAST_, NT_>), smem);                                       \
+            dsg_launch((topology_bwd_kernel<FAST_, NT_>), dim3(grid), dim3(NT_), smem, st, a);           \
+        } while (0)
+        // bf16 compute mode (the caller asks for the bf16 copy of dH exactly then): same tanh as the forward kernel used
+        if (a.dH_bf16) { if (small) DSG_TOPO_BWD(true, 512); else DSG_TOPO_BWD(true, TP_BWD_THREADS); }
+        else { if (small) DSG_TOPO_BWD(false, 512); else DSG_TOPO_BWD(false, TP_BWD_THREADS); }
+#undef DSG_TOPO_BWD
     }
     return dsg_launch_error();
 }

@@ -492,10 +492,12 @@ def _ms_fused_args(m, layout, b_act, n, T, T_out, s, V, has_ext, grads):
             weights[j] = (conv.weight, conv.bias, dW, db)
     a = ops.ms_temporal_args(b_act, layout, weights, n=n, T_in=T, T_out=T_out, stride=s, V=V, has_ext=has_ext,
                              add_coeff=m.add_coeff if has_ext else None)
+    a.wgrads_py = {j: (w[2], w[3]) for j, w in weights.items()}      # the accumulators, for the TMA-fed weight gradient
     return a if ops.ms_temporal_supported(a) else None
 
 
 FUSED_AGG = os.environ.get("DSG_FUSED_AGG", "1") != "0"     # 0: separate adjacency contraction (dsg_graph_agg) + post GEMM
+MS_TWGRAD = os.environ.get("DSG_MS_TWGRAD", "1") != "0"   # 0: round-1 temporal weight-gradient kernel (CUDA-core staging)
 MS_TAP = os.environ.get("DSG_MS_TAP", "1") != "0"      # 0: the staged single-kernel branch stage (ms_temporal_tc.cuh) instead
 
 
@@ -674,7 +676,10 @@ def _ms_branch_backward(m, sv, dfeat, grads, tail=None):
             raise RuntimeError("dsg_ms_conv took the forward of this shape but declined its data gradient")
         # (after the conv branches: dsg_ms_conv pads its last 16-byte channel chunk with zeros, the max range starts inside it)
         ops.ms_combine_bwd(Act(B, c_b.a, c_b.b), dfeat, d_o, E3, sv["oglob"], B, parts=2, **ckw)
-        ops.ms_temporal_bwd(fused, dfeat, E3, sv["oglob"], b_b.ssum, b_b.ssq, dadd, data=False)      # weight gradients of the conv branches
+        # weight gradients of the conv branches: TMA-fed tcgen05 engine straight from H and d_o (both materialised above), else the
+        # round-1 kernel that stages its operands with CUDA cores
+        if not (MS_TWGRAD and ops.ms_conv_wgrad(H, d_o, layout, fused.wgrads_py, n=n, T_in=T, T_out=T_out, stride=s, Vr=Vp)):
+            ops.ms_temporal_bwd(fused, dfeat, E3, sv["oglob"], b_b.ssum, b_b.ssq, dadd, data=False)
     elif fused is not None:
         # ---- two tcgen05 kernels: data gradient of the whole branch stage (+ masks, BN-backward sums, dadd_coeff),
         #      then the weight gradients of the dilated convolutions

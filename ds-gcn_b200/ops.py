@@ -471,6 +471,39 @@ def ms_conv(src, out, layout, weights, *, n, T_in, T_out, stride, Vr, transposed
     return bool(handled.value)
 
 
+def ms_conv_wgrad(H, d_o, layout, wgrads, *, n, T_in, T_out, stride, Vr):
+    """dsg_ms_conv_wgrad: weight / bias gradients of every dilated (3 x 1) conv branch in one TMA-fed tcgen05 launch, on the side
+    stream like the other weight gradients.  `wgrads`: {branch index: (dW, db)} pre-zeroed fp32 accumulators.  Returns False when
+    the engine declines (the caller runs dsg_ms_temporal_bwd_weight)."""
+    if H.dtype != torch.bfloat16 or d_o.dtype != torch.bfloat16 or not L.is_device_build():
+        return False
+    a = L.MsConvArgs()
+    a.n_samples, a.T_in, a.T_out, a.stride, a.Vr, a.transposed = n, T_in, T_out, stride, Vr, 0
+    nb = 0
+    for j, (kind, lo, hi, cfg) in enumerate(layout):
+        if kind != "conv":
+            continue
+        if cfg[0] != 3 or nb >= 8:
+            return False
+        br = a.br[nb]
+        br.kind, br.lo, br.hi, br.dilation = 0, lo, hi, cfg[1]
+        dW, db = wgrads[j]
+        br.dW, br.db = L.ptr(_f32(dW)), L.ptr(_f32(db))
+        nb += 1
+    if nb == 0:
+        return False
+    a.n_branches = nb
+    a.src, a.ld_src = L.ptr(H), _ld(H)
+    a.out, a.ld_out = L.ptr(d_o), _ld(d_o)
+    handled = C.c_int(0)
+    span = a.br[nb - 1].hi - a.br[0].lo
+    nbytes = (n * T_in * Vr + n * T_out * Vr) * span * 2
+    with L.side_stream():
+        L.keepalive.extend((a, H, d_o, wgrads))
+        L.call("dsg_ms_conv_wgrad", C.byref(a), C.byref(handled), L.stream(), nbytes=nbytes)
+    return bool(handled.value)
+
+
 def sgd_step(p, grad, buf, lr, momentum, wd, nesterov, grad_scale=1.0):
     """`lr`: a Python float, or a one-element fp32 tensor on the device (read by the kernel: CUDA-graph friendly schedules)."""
     assert p.is_contiguous() and grad.is_contiguous() and buf.is_contiguous()

@@ -392,6 +392,12 @@ typedef struct dsg_ms_conv_args {
 } dsg_ms_conv_args;
 long long dsg_ms_conv_wpack_bytes(const dsg_ms_conv_args* a);
 int dsg_ms_conv(const dsg_ms_conv_args* a, int* handled, void* stream);
+/* Weight / bias gradients of the same convolutions (tcn.py:383-391, backward) on the same engine:
+ *   br[j].dW[co,ci,tap] += sum_{n,t',r} out[n,t',r,lo+co] * src[n, s*t' + (tap-1)*d, r, lo+ci],   br[j].db[co] += sum out[n,t',r,lo+co]
+ * with src = the forward input of the convs (relu(bn(B)), [n,T_in,Vr,.]) and `out` = the gradient w.r.t. the branch outputs
+ * ([n,T_out,Vr,.], read only), both plain bf16 with absolute channel indexing; transposed / mask / partner / stat_* / wpack are
+ * ignored.  Accumulates with atomics (callers pre-zero dW / db).  *handled = 0: shape not taken (older engine: dsg_ms_temporal_bwd_weight). */
+int dsg_ms_conv_wgrad(const dsg_ms_conv_args* a, int* handled, void* stream);
 
 /* ---- dsg_pointwise --------------------------------------------------------------------------
  * out(r,c) = src(r,c) (any activation source: BN-apply, +residual, ReLU), optional mask
@@ -433,7 +439,7 @@ int dsg_sgd_step_dev(float* p, const float* grad, float* buf, long long n, const
 
 /* Launch counters of the engines behind the entry points (diagnostics for the tests and bench.py: which engine ran).
  * id 0: TMA-fed tcgen05 GEMM (tc4)   1: TMA-fed tcgen05 weight gradient (tc4w)   2: fused adjacency-contraction + post GEMM
- *    3: tap-shifted temporal convolutions (dsg_ms_conv).
+ *    3: tap-shifted temporal convolutions (dsg_ms_conv)   4: their TMA-fed weight gradient (dsg_ms_conv_wgrad).
  * Monotonic, process-wide, never read by the kernels. */
 long long dsg_debug_counter(int id);
 

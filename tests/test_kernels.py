@@ -597,6 +597,43 @@ def test_sgd_step_matches_torch(dev):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("Vr", [26, 18])
+@pytest.mark.parametrize("widths", [(14, 10, 10, 10), (23, 21, 21, 21), (46, 42, 42, 42)])
+@pytest.mark.parametrize("stride", [1, 2])
+def test_ms_conv_wgrad_tma(widths, stride, Vr):
+    """dsg_ms_conv_wgrad: weight / bias gradients of all dilated (3 x 1) conv branches in one TMA-fed tcgen05 launch (operands read
+    MN-major from tap-shifted 4-D tensor-map loads; zero fill = zero padding), against autograd of F.conv2d."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    dsgcn_b200._lib._testing_use_library(None)
+    dev = torch.device("cuda:0")
+    torch.manual_seed(sum(widths) + stride + Vr)
+    n, T = 5, 21                                             # odd T: the last frames of a sample fill a partial tile
+    T_out = (T - 1) // stride + 1
+    layout, lo = [], 0
+    for w, d in zip(widths, (1, 2, 3, 4)):
+        layout.append(("conv", lo, lo + w, (3, d)))
+        lo += w
+    chw, Ct = (lo + 7) & ~7, lo + 2 * widths[-1]             # H holds the conv channels, d_o every branch output
+    H = torch.randn(n * T * Vr, chw, device=dev).to(torch.bfloat16)
+    d_o = torch.randn(n * T_out * Vr, Ct, device=dev).to(torch.bfloat16)
+    wgrads = {j: (torch.zeros(w, w, 3, 1, device=dev), torch.zeros(w, device=dev)) for j, w in enumerate(widths)}
+    c0 = _lib.lib().dsg_debug_counter(4)
+    assert ops.ms_conv_wgrad(H, d_o, layout, wgrads, n=n, T_in=T, T_out=T_out, stride=stride, Vr=Vr)
+    assert _lib.lib().dsg_debug_counter(4) == c0 + 1
+    _lib.join_side()
+    torch.cuda.synchronize()
+    for j, (kind, lo, hi, (k, d)) in enumerate(layout):
+        w = hi - lo
+        x = H[:, lo:hi].float().view(n, T, Vr, w).permute(0, 3, 1, 2)
+        g = d_o[:, lo:hi].float().view(n, T_out, Vr, w).permute(0, 3, 1, 2)
+        wt = torch.zeros(w, w, 3, 1, device=dev, requires_grad=True)
+        F.conv2d(x, wt, None, (stride, 1), (d, 0), (d, 1)).backward(g)
+        close(wgrads[j][0], wt.grad, torch.float32, f"dW branch {j}")
+        close(wgrads[j][1], g.sum((0, 2, 3)), torch.float32, f"db branch {j}")
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("widths", [(14, 10, 10, 10), (23, 21, 21, 21), (46, 42, 42, 42)])
 @pytest.mark.parametrize("stride", [1, 2])
 def test_ms_conv_tap_shifted_tma(widths, stride):
