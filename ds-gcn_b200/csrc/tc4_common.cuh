@@ -76,14 +76,15 @@ static inline bool make_map_3d(CUtensorMap* m, const void* base, long long frame
 // 4-D view (C, rows_per_frame, frames of one temporal plane, samples) of [n, T, rpf, C]: frame pitch `t_stride` frames (temporal
 // stride / parity planes), first frame `t0`; box = (64, rpf, 1, 1).  A frame coordinate outside [0, frames) is zero-filled on
 // load — exactly the zero padding of a temporal convolution — and skipped on store.
-static inline bool make_map_4d(CUtensorMap* m, const void* base, int n_samples, int T, int rpf, int C, long long ld, int t0, int t_stride) {
+static inline bool make_map_4d(CUtensorMap* m, const void* base, int n_samples, int T, int rpf, int C, long long ld, int t0, int t_stride,
+                               int box_f = 1) {
     EncodeTiledFn enc = encode_fn();
     const int frames = T > t0 ? (T - t0 + t_stride - 1) / t_stride : 0;
     if (!enc || n_samples <= 0 || frames <= 0 || C <= 0 || rpf <= 0) return false;
     const unsigned char* b0 = reinterpret_cast<const unsigned char*>(base) + (size_t)t0 * rpf * ld * 2;
     cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)rpf, (cuuint64_t)frames, (cuuint64_t)n_samples};
     cuuint64_t strides[3] = {(cuuint64_t)ld * 2, (cuuint64_t)ld * 2 * (cuuint64_t)rpf * (cuuint64_t)t_stride, (cuuint64_t)ld * 2 * (cuuint64_t)rpf * (cuuint64_t)T};
-    cuuint32_t box[4] = {(cuuint32_t)ATOM_CH, (cuuint32_t)rpf, 1, 1};
+    cuuint32_t box[4] = {(cuuint32_t)ATOM_CH, (cuuint32_t)rpf, (cuuint32_t)box_f, 1};       // box_f frames land densely packed: [box_f][rpf] rows
     cuuint32_t es[4] = {1, 1, 1, 1};
     return enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<unsigned char*>(b0), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;

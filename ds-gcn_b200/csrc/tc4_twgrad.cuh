@@ -6,10 +6,11 @@
 //
 // H = relu(bn(B)) (the forward input of the convs) and dO (the gradient w.r.t. every branch output, joint-mean row included)
 // are both plain bf16 tensors the tap-shifted path has materialised anyway, so nothing is staged by a thread: the reduction
-// runs over ROWS, so the atoms the TMA unit writes ([4 frame slots x 32 rows] x 64 channels, SWIZZLE_128B) are read by the tensor
+// runs over ROWS, so the atoms the TMA unit writes ([F frames x Vr rows] x 64 channels, SWIZZLE_128B) are read by the tensor
 // core as MN-major operands (as in tc4_wgrad.cuh).  A CTA owns ONE branch (blockIdx.y) and walks (sample, 4 output frames) tiles:
 //
-//   stage = [dO window | H at tap 0 | H at tap 1 | H at tap 2]: four atoms whose channel window starts at the branch's 8-aligned
+//   stage = [dO window | H at tap 0 | H at tap 1 | H at tap 2]: four atoms (each ONE 4-D TMA box of F frames x Vr rows, densely
+//           packed: a reduction over rows needs no frame slots) whose channel window starts at the branch's 8-aligned
 //           first channel lo8 (so the branch sits at columns [off, off + w) of its own atoms and no operand starts mid-atom);
 //           a tap is just another frame coordinate of the 4-D tensor map (frames outside the sample are zero-filled by the TMA
 //           unit = the convolution's zero padding; a temporal stride selects a parity-plane tensor map)
@@ -89,14 +90,14 @@ tc4_twgrad_kernel(const __grid_constant__ CUtensorMap mapD, const __grid_constan
                 mbar_wait(&bars.empty[stage], ph ^ 1);
                 mbar_expect_tx(&bars.full[stage], tx);
                 unsigned char* st = ring + (size_t)stage * p.stage_bytes;
-                for (int f = 0; f < p.F; ++f) tma_load_4d(st + (size_t)f * p.slot * 128, &mapD, p.lo8[b], 0, q0 + f, smp, &bars.full[stage]);
+                tma_load_4d(st, &mapD, p.lo8[b], 0, q0, smp, &bars.full[stage]);
                 for (int tap = 0; tap < 3; ++tap) {
                     const int o = (tap - 1) * d;
                     const int par = s == 2 ? (o & 1) : 0;                         // parity plane of s*t' + o
                     const int sh = s == 2 ? (o - par) / 2 : o;                    // frame offset inside the plane
                     const CUtensorMap* m = par ? &mapH1 : &mapH0;
                     unsigned char* dst = st + (size_t)(1 + tap) * ATOM_BYTES;
-                    for (int f = 0; f < p.F; ++f) tma_load_4d(dst + (size_t)f * p.slot * 128, m, p.lo8[b], 0, q0 + f + sh, smp, &bars.full[stage]);
+                    tma_load_4d(dst, m, p.lo8[b], 0, q0 + sh, smp, &bars.full[stage]);
                 }
                 if (++stage == p.S) { stage = 0; ph ^= 1; }
             }
@@ -179,9 +180,9 @@ static const char* launch_ms_conv_wgrad_tc4(const dsg_ms_conv_args& a, dsg_strea
         if (br.hi > hi_all) hi_all = br.hi;
     }
     p.Vr = a.Vr;
-    p.slot = (a.Vr + 7) & ~7;
-    p.F = ATOM_ROWS / p.slot;
-    p.ksteps = (p.F * p.slot + 15) / 16;
+    p.slot = a.Vr;                                        // dense rows: F frames of Vr rows per atom, the tail rows stay zero
+    p.F = ATOM_ROWS / a.Vr;
+    p.ksteps = (p.F * a.Vr + 15) / 16;
     p.stride = a.stride;
     p.T_out = a.T_out;
     p.tps = (a.T_out + p.F - 1) / p.F;
@@ -197,10 +198,10 @@ static const char* launch_ms_conv_wgrad_tc4(const dsg_ms_conv_args& a, dsg_strea
     const int Csrc = (int)(a.ld_src < hi_all + 64 ? a.ld_src : hi_all + 64);
     const int Cout = (int)(a.ld_out < hi_all + 64 ? a.ld_out : hi_all + 64);
     CUtensorMap mD, mH0, mH1;
-    bool ok = make_map_4d(&mD, a.out, a.n_samples, a.T_out, a.Vr, Cout, a.ld_out, 0, 1);
-    ok = ok && make_map_4d(&mH0, a.src, a.n_samples, a.T_in, a.Vr, Csrc, a.ld_src, 0, a.stride);
+    bool ok = make_map_4d(&mD, a.out, a.n_samples, a.T_out, a.Vr, Cout, a.ld_out, 0, 1, p.F);
+    ok = ok && make_map_4d(&mH0, a.src, a.n_samples, a.T_in, a.Vr, Csrc, a.ld_src, 0, a.stride, p.F);
     mH1 = mH0;
-    if (ok && a.stride == 2 && a.T_in > 1) ok = make_map_4d(&mH1, a.src, a.n_samples, a.T_in, a.Vr, Csrc, a.ld_src, 1, 2);
+    if (ok && a.stride == 2 && a.T_in > 1) ok = make_map_4d(&mH1, a.src, a.n_samples, a.T_in, a.Vr, Csrc, a.ld_src, 1, 2, p.F);
     if (!ok) return nullptr;
     int gx = num_sms() / p.nb;
     if (gx < 1) gx = 1;
