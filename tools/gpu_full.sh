@@ -9,5 +9,7 @@ timeout 900 ncu --profile-from-start off --metrics gpu__time_duration.sum,dram__
 # ncu --set full of the kernels named in $2.. (regex on the kernel name), ten launches each, inside one profiled eager step
 shift
 for K in "$@"; do
-  timeout 900 ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:$K -c 10 -f -o gpurun_out/full_${K}_$TAG python bench.py --profile-step --no-cpu-baseline --no-ref-gpu --no-fwd > gpurun_out/full_${K}_$TAG.log 2>&1; tail -1 gpurun_out/full_${K}_$TAG.log
+  timeout 900 ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:$K -c 10 -f -o /tmp/full_${K}_$TAG python bench.py --profile-step --no-cpu-baseline --no-ref-gpu --no-fwd > gpurun_out/full_${K}_$TAG.log 2>&1; tail -1 gpurun_out/full_${K}_$TAG.log
+  # the report stays on the box (gpurun brings back at most 64 MiB): only its JSON summary travels
+  python tools/ncu_rep_summary.py /tmp/full_${K}_$TAG.ncu-rep gpurun_out/r02_ncu_full_${K}.json "ncu --set full --clock-control none, the ten launches of one eager training step (128 clips, bf16), final round-2 build" > /dev/null 2>&1; ls -la gpurun_out/r02_ncu_full_${K}.json
 done
