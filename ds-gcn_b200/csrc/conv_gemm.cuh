@@ -402,7 +402,7 @@ template <class T> static const char* launch_conv_wgrad(const dsg_conv_wgrad_arg
     int ktiles = (a.K + WG_BK - 1) / WG_BK, ntiles = (a.N + WG_BN - 1) / WG_BN;
     int Fr = WG_BR / rpf;
     // aim for ~4 CTAs per SM in total; each CTA walks a contiguous frame range
-    long long want = (4 * 148 + (long long)ktiles * ntiles * a.taps - 1) / ((long long)ktiles * ntiles * a.taps);
+    long long want = (4 * dsg_num_sms() + (long long)ktiles * ntiles * a.taps - 1) / ((long long)ktiles * ntiles * a.taps);
     long long fpc = (n_frames + want - 1) / want;
     fpc = (fpc + Fr - 1) / Fr * Fr;
     if (fpc < Fr) fpc = Fr;

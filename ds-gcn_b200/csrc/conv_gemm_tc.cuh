@@ -816,7 +816,7 @@ static const char* launch_conv_wgrad_tc(const dsg_conv_wgrad_args& a, dsg_stream
     int occ = (int)((200 * 1024) / (smem + 4096));                // CTAs one SM holds (TMEM: <=128 columns each)
     if (occ > 3) occ = 3;                                         // 80 registers x 256 threads: three CTAs per SM
     if (occ < 1) occ = 1;
-    long long want = ((long long)occ * 148 + per - 1) / per;      // one wave of resident CTAs
+    long long want = ((long long)occ * dsg_num_sms() + per - 1) / per;      // one wave of resident CTAs
     long long fpc = (n_frames + want - 1) / want;
     fpc = (fpc + Fr - 1) / Fr * Fr;
     if (fpc < Fr) fpc = Fr;

@@ -410,7 +410,7 @@ static const char* launch_conv_gemm_tc3(const dsg_conv_gemm_args& a, dsg_stream_
     if (per_sm > 2) per_sm = 2;                          // 2 x 256 TMEM columns, 2 x 256 threads x ~120 registers
     if (per_sm < 1) per_sm = 1;
     const unsigned ny = (unsigned)((a.N + T2_BN - 1) / T2_BN);
-    long long gx = ((long long)per_sm * 148 + ny - 1) / ny;
+    long long gx = ((long long)per_sm * dsg_num_sms() + ny - 1) / ny;
     if (gx > tiles) gx = tiles;
     if (gx < 1) gx = 1;
     conv_wpack_kernel<<<dim3(ny, (unsigned)((Kp + kpass - 1) / kpass)), dim3(256), 0, st>>>(a.W, a.ws_n, a.ws_k, a.K, a.N, reinterpret_cast<unsigned char*>(a.wpack));

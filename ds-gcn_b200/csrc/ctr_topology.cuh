@@ -176,7 +176,7 @@ static const char* launch_ctr_topology(const dsg_ctr_topology_args& a, bool bwd,
     if (a.n_samples <= 0) return nullptr;
     const size_t smem = CtrSmem::floats(a.R, a.V, a.C, bwd) * sizeof(float);
     if (smem > 200 * 1024) return "ctr_topology: shared memory budget exceeded (C*R too large)";
-    const int gx = a.n_samples < 148 ? a.n_samples : 148;
+    const int gx = a.n_samples < dsg_num_sms() ? a.n_samples : dsg_num_sms();
     if (!bwd) {
         if (a.adyn_dtype == DSG_BF16) {
             DSG_SET_SMEM(ctr_topology_fwd_kernel<bf16>, smem);

@@ -30,6 +30,20 @@ static inline const char* dsg_launch_error() {
 }
 #endif
 
+// SM count of the current device (grid sizing: one wave of resident CTAs); 148 on the B200, queried once so other Blackwell SKUs fill too
+static inline int dsg_num_sms() {
+#ifdef DSG_EMU
+    return 148;
+#else
+    static int n = [] {
+        int dev = 0, v = 148;
+        if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+        return v > 0 ? v : 148;
+    }();
+    return n;
+#endif
+}
+
 #define DSG_HD __host__ __device__ __forceinline__
 #define DSG_D __device__ __forceinline__
 

@@ -435,7 +435,7 @@ template <class T, int V> static const char* launch_agg_v(const dsg_graph_agg_ar
     // enough CTAs to fill the GPU: split T when the (sample x channel-slice) grid is small
     int slices = (a.KC + 31) / 32;
     long long base = (long long)a.n_samples * slices;
-    int tsplit = (int)((2 * 148 + base - 1) / base);
+    int tsplit = (int)((2 * dsg_num_sms() + base - 1) / base);
     int unit = (a.mode <= 1) ? AG_TCH : (AG_THREADS / 32);
     int t_chunk = (a.T + tsplit - 1) / tsplit;
     t_chunk = (t_chunk + unit - 1) / unit * unit;

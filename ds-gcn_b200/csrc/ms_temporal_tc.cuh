@@ -1016,7 +1016,7 @@ static const char* launch_ms_temporal_bwd_weight(const dsg_ms_temporal_args& a, 
     if (per_sm < 1) per_sm = 1;
     if (per_sm > 2) per_sm = 2;                          // register-limited
     if (per_sm * tcols > 512) per_sm = 512 / tcols;
-    int grid = n_tiles < per_sm * 148 ? n_tiles : per_sm * 148;
+    int grid = n_tiles < per_sm * dsg_num_sms() ? n_tiles : per_sm * dsg_num_sms();
     ms_temporal_bwd_weight_kernel<<<dim3(grid), dim3(MS_THREADS), smem, st>>>(a, gp, pl, tcols);
     return dsg_launch_error();
 }

@@ -180,14 +180,7 @@ static inline bool tc4_enabled() {
     if (v < 0) { const char* e = getenv("DSG_DISABLE_TC4"); v = (e && e[0] == '1') ? 0 : 1; }
     return v == 1;
 }
-static inline int num_sms() {
-    static int n = [] {
-        int dev = 0, v = 148;
-        if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
-        return v > 0 ? v : 148;
-    }();
-    return n;
-}
+static inline int num_sms() { return dsg_num_sms(); }
 
 }  // namespace tc4
 }  // namespace dsg

@@ -375,7 +375,7 @@ static inline size_t topo_bwd_smem_floats(int R, int V) {
 static const char* launch_topology(const dsg_topology_args& a, bool bwd, dsg_stream_t st) {
     if (a.V > 32 || a.R > 32 || a.R < 1) return "topology: needs V<=32 and 1<=R<=32";
     if (a.n_samples <= 0) return nullptr;
-    int grid = a.n_samples < 2 * 148 ? a.n_samples : 2 * 148;
+    int grid = a.n_samples < 2 * dsg_num_sms() ? a.n_samples : 2 * dsg_num_sms();
     if (!bwd) {
         size_t smem = (TopoSmem::floats(a.R, a.V) + (size_t)15 * a.R * (a.R + 1) + 15 * a.R) * sizeof(float);
         if (a.adyn_dtype == DSG_BF16) {
@@ -392,7 +392,7 @@ static const char* launch_topology(const dsg_topology_args& a, bool bwd, dsg_str
         // active, 2 % DRAM): where the accumulators leave room (R <= 16), two 512-thread CTAs share an SM and every sample gets
         // its own CTA, so one CTA's barriers and load latencies hide behind the other's work
         const bool small = smem <= 100 * 1024;
-        const int cap = small ? 2 * 148 : 148;
+        const int cap = small ? 2 * dsg_num_sms() : dsg_num_sms();
         grid = a.n_samples < cap ? a.n_samples : cap;
 #define DSG_TOPO_BWD(FAST_, NT_)                                                                         \
         do {                                                                                             \

@@ -80,13 +80,21 @@ class _KernelFn(torch.autograd.Function):
         save = {} if need else None
         out, t_out = impl.fwd(to_rows(x.detach(), dtype), n, t, v, save)
         ctx.impl, ctx.save, ctx.params, ctx.x_dtype, ctx.dims = impl, save, params, x.dtype, (n, t, t_out, v)
-        return from_rows(out, n, t_out, v)
+        ctx.dtype = dtype                 # the compute dtype of THIS forward (set_compute_dtype may change before backward)
+        y = from_rows(out, n, t_out, v)
+        if need:
+            # the output aliases the tensor backward uses as its ReLU mask: registering it makes autograd's version counter catch an
+            # in-place edit of a block output (relu_, add_) instead of silently corrupting the gradients
+            ctx.save_for_backward(y)
+        return y
 
     @staticmethod
+    @torch.autograd.function.once_differentiable
     def backward(ctx, dout):
         n, t, t_out, v = ctx.dims
+        _ = ctx.saved_tensors             # raises if the output was modified in place
         grads = {}
-        dx = ctx.impl.bwd(ctx.save, to_rows(dout, _compute_dtype), grads)
+        dx = ctx.impl.bwd(ctx.save, to_rows(dout, ctx.dtype), grads)
         ops.L.join_side()           # weight-gradient kernels ran on the side stream: rejoin before autograd sees them
         ctx.save = None
         dx = from_rows(dx, n, t, v)

@@ -266,3 +266,23 @@ def test_frozen_child_bn_vs_live_reference():
             assert torch.allclose(v.float(), r.state_dict()[k].float(), rtol=1e-4, atol=1e-6), k
     finally:
         M.set_compute_dtype(torch.bfloat16)
+
+
+def test_kernel_fn_guards(dev):
+    """an in-place edit of a unit's output (it aliases the saved ReLU mask) must raise instead of corrupting gradients, and a
+    double backward must raise instead of returning garbage."""
+    torch.manual_seed(0)
+    M.set_compute_dtype(torch.float32)
+    try:
+        m = M.unit_tcn(8, 8, kernel_size=3).to(dev).train()
+        x = torch.randn(2, 8, 6, 25, device=dev, requires_grad=True)
+        y = m(x)
+        with pytest.raises(RuntimeError):      # (autograd refuses the in-place edit itself: the output is a view made inside the Function)
+            y.add_(1.0)
+            y.sum().backward()
+        y = m(x)
+        (g,) = torch.autograd.grad(y.sum(), x, create_graph=True)
+        with pytest.raises(RuntimeError):
+            g.sum().backward()
+    finally:
+        M.set_compute_dtype(torch.bfloat16)
