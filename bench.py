@@ -609,12 +609,18 @@ def main():
         try:
             ll = json.load(open(os.path.join(ROOT, "profiles", LAUNCH_LIST)))
             stem = top.replace("dsg_", "")
-            ks = [k for k in ll["kernels"] if stem in k["kernel"] and "wpack" not in k["kernel"] and ("wgrad" in stem) == ("wgrad" in k["kernel"])]
+            # kernels behind the entry point: dsg_conv_gemm = the TMA engine tc4_gemm_kernel<...> (which also serves the 20
+            # dsg_ms_conv launches of the step: same kernel name, they are in the mean) + the older conv_gemm_* engines
+            stems = (stem, "tc4_gemm_kernel") if stem == "conv_gemm" else (stem,)
+            ks = [k for k in ll["kernels"] if any(s_ in k["kernel"] for s_ in stems) and "wpack" not in k["kernel"]
+                  and not k["kernel"].startswith("cutlass") and ("wgrad" in stem) == ("wgrad" in k["kernel"])]
             if ks:
                 traffic = sum(k["dram_read_mb"] + k["dram_write_mb"] for k in ks) * 1e6 / sum(k["launches"] for k in ks)
-                traffic_src = f"profiles/{LAUNCH_LIST} (ncu dram__bytes_read.sum + dram__bytes_write.sum, mean per launch)"
+                traffic_src = (f"profiles/{LAUNCH_LIST} (ncu dram__bytes_read.sum + dram__bytes_write.sum, mean per launch over "
+                               f"{sum(k['launches'] for k in ks)} launches of {', '.join(stems)})")
             step_traffic = sum(k["dram_read_mb"] + k["dram_write_mb"] for k in ll["kernels"]) * 1e6
-            own_kernels = sum(k["launches"] for k in ll["kernels"] if not k["kernel"].startswith("void at::"))
+            own_kernels = sum(k["launches"] for k in ll["kernels"]
+                              if not k["kernel"].startswith(("void at::", "void at_cuda", "cutlass", "void sbtopk", "void cub", "void cutlass")))
         except Exception:
             pass
     roofline = dict(bound="hbm", kernel=top, achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak, traffic=traffic,
