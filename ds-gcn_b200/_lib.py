@@ -124,6 +124,8 @@ EXPORTS = {
     "dsg_tmean2": (c_int, [vp, c_int, c_ll, c_int, c_int, c_int, c_int, vp, vp, vp]),
     "dsg_topology_fwd": (c_int, [C.POINTER(TopologyArgs), vp]),
     "dsg_topology_bwd": (c_int, [C.POINTER(TopologyArgs), vp]),
+    "dsg_head_ce_fwd": (c_int, [vp, vp, vp, vp, c_int, c_int, c_int, vp, vp, vp]),
+    "dsg_head_ce_bwd": (c_int, [vp, vp, vp, vp, vp, c_int, c_int, c_int, vp, vp, vp, vp, vp]),
     "dsg_ctr_topology_fwd": (c_int, [C.POINTER(CtrTopologyArgs), vp]),
     "dsg_ctr_topology_bwd": (c_int, [C.POINTER(CtrTopologyArgs), vp]),
     "dsg_graph_agg": (c_int, [C.POINTER(GraphAggArgs), vp]),

@@ -14,6 +14,7 @@
 #include "ctr_topology.cuh"
 #include "misc.cuh"
 #include "ms_mix.cuh"
+#include "head.cuh"
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -164,6 +165,15 @@ int dsg_topology_fwd(const dsg_topology_args* a, void* stream) {
 int dsg_topology_bwd(const dsg_topology_args* a, void* stream) {
     if (!a) return fail("dsg_topology_bwd", "bad arguments");
     DSG_RET("dsg_topology_bwd", dsg::launch_topology(*a, true, (dsg_stream_t)stream));
+}
+
+int dsg_head_ce_fwd(const float* pooled, const float* W, const float* b, const long long* label, int N, int C, int K,
+                    float* logits, float* stats, void* stream) {
+    DSG_RET("dsg_head_ce_fwd", dsg::launch_head_ce_fwd(pooled, W, b, label, N, C, K, logits, stats, (dsg_stream_t)stream));
+}
+int dsg_head_ce_bwd(const float* logits, const long long* label, const float* pooled, const float* W, const float* gscale,
+                    int N, int C, int K, float* dlogits, float* dpooled, float* dW, float* db, void* stream) {
+    DSG_RET("dsg_head_ce_bwd", dsg::launch_head_ce_bwd(logits, label, pooled, W, gscale, N, C, K, dlogits, dpooled, dW, db, (dsg_stream_t)stream));
 }
 
 int dsg_ctr_topology_fwd(const dsg_ctr_topology_args* a, void* stream) {

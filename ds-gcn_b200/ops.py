@@ -504,6 +504,32 @@ def ms_conv_wgrad(H, d_o, layout, wgrads, *, n, T_in, T_out, stride, Vr):
     return bool(handled.value)
 
 
+def head_ce_fwd(pooled, W, b, label=None):
+    """dsg_head_ce_fwd: logits [N, K] (+ per-sample {cross-entropy, top-1 hit, top-5 hit} [N, 3] when labels are given)"""
+    N, Cn = pooled.shape
+    K = W.shape[0]
+    assert pooled.dtype == torch.float32 and pooled.is_contiguous() and W.shape[1] == Cn
+    logits = torch.empty(N, K, dtype=torch.float32, device=pooled.device)
+    stats = None
+    if label is not None:
+        assert label.dtype == torch.int64 and label.is_contiguous() and label.numel() == N
+        stats = torch.empty(N, 3, dtype=torch.float32, device=pooled.device)
+    L.call("dsg_head_ce_fwd", L.ptr(pooled), L.ptr(_f32(W)), L.ptr(_f32(b)), L.ptr(label), N, Cn, K, L.ptr(logits), L.ptr(stats), L.stream())
+    return logits, stats
+
+
+def head_ce_bwd(logits, label, pooled, W, gscale, dW=None, db=None, need_dpooled=True):
+    """dsg_head_ce_bwd: returns (dlogits, dpooled); accumulates into dW / db when given"""
+    N, K = logits.shape
+    Cn = W.shape[1]
+    assert gscale.dtype == torch.float32 and gscale.numel() == 1
+    dlogits = torch.empty_like(logits)
+    dpooled = torch.empty(N, Cn, dtype=torch.float32, device=logits.device) if need_dpooled else None
+    L.call("dsg_head_ce_bwd", L.ptr(logits), L.ptr(label), L.ptr(pooled), L.ptr(_f32(W)), L.ptr(gscale), N, Cn, K, L.ptr(dlogits),
+           L.ptr(dpooled), L.ptr(_f32(dW)), L.ptr(_f32(db)), L.stream())
+    return dlogits, dpooled
+
+
 def sgd_step(p, grad, buf, lr, momentum, wd, nesterov, grad_scale=1.0):
     """`lr`: a Python float, or a one-element fp32 tensor on the device (read by the kernel: CUDA-graph friendly schedules)."""
     assert p.is_contiguous() and grad.is_contiguous() and buf.is_contiguous()

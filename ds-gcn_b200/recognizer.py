@@ -130,9 +130,54 @@ class _PoolFn(torch.autograd.Function):
         return d.view(N, 1, C, 1, 1).expand(N, M_, C, T, V)
 
 
+class _HeadCEFn(torch.autograd.Function):
+    """fc_cls + cross-entropy + top-1 / top-5 (heads/simple_head.py:93-96, heads/base.py:50-84, losses/cross_entropy_loss.py:77-80) as
+    two kernels forward (dsg_head_ce_fwd, the batch means through dsg_tmean) and two backward (dsg_head_ce_bwd): no logits /
+    log-softmax / one-hot / top-k intermediates from library kernels."""
+    # fc_cls gradients go back through autograd (AccumulateGrad adds them into the flat-buffer views): with EVERY parameter of a
+    # packed model written in place no AccumulateGrad node runs, and capturing the iteration in a CUDA graph then fails with
+    # cudaErrorStreamCaptureIsolation in the engine's end-of-backward stream sync (tools/probes/capture_head.py, torch 2.11)
+    direct_sink = False
+
+    @staticmethod
+    def forward(ctx, pooled, weight, bias, label):
+        x = pooled.detach().contiguous()
+        logits, stats = ops.head_ce_fwd(x, weight.detach(), bias.detach(), label)
+        means = ops.tmean(stats, 1, stats.shape[0], 1).view(3)          # [mean CE, top-1, top-5]
+        ctx.save_for_backward(x, logits, label)
+        ctx.params = (weight, bias)
+        ctx.need_x = ctx.needs_input_grad[0]
+        ctx.mark_non_differentiable(logits)
+        return means[0], means[1], means[2], logits
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, gloss, _g1, _g5, _gl):
+        x, logits, label = ctx.saved_tensors
+        weight, bias = ctx.params
+        N = x.shape[0]
+        gscale = (gloss.detach().float() / N).reshape(1)
+        sinks = []
+        for p in (weight, bias):
+            direct = _HeadCEFn.direct_sink and getattr(p, "_dsg_sink", False) and p.grad is not None
+            sinks.append(p.grad if direct else torch.zeros_like(p))
+        _, dx = ops.head_ce_bwd(logits, label, x, weight.detach(), gscale, dW=sinks[0], db=sinks[1], need_dpooled=ctx.need_x)
+        out = []
+        for p, g in zip((weight, bias), sinks):
+            if p.grad is not None and g.data_ptr() == p.grad.data_ptr():     # written in place into the flat bucket: tell it directly
+                cb = getattr(p, "_dsg_ready", None)
+                if cb is not None:
+                    cb(p)
+                out.append(None)
+            else:
+                out.append(g)
+        return dx, out[0], out[1], None
+
+
 @MODELS.register_module()
 class GCNHead(nn.Module):
     """SimpleHead(mode='GCN'): mean over (T,V), mean over M, dropout(p) , Linear."""
+    use_fused = True          # training: fc_cls + cross-entropy + top-k in the dsg_head_ce_* kernels where the configuration allows
 
     def __init__(self, num_classes, in_channels, loss_cls=dict(type="CrossEntropyLoss"), dropout=0., init_std=0.01,
                  multi_class=False, label_smooth_eps=0.0, **kwargs):
@@ -160,6 +205,20 @@ class GCNHead(nn.Module):
         if self.dropout is not None:
             x = self.dropout(x)
         return self.fc_cls(x)
+
+    def fused_loss(self, x, label):
+        """forward + loss of training in the fused kernels; None when the configuration needs the general path (soft / multi-class
+        labels, class weights, dropout, label smoothing, CPU tensors)."""
+        lc = self.loss_cls
+        if (not self.use_fused or x.dim() != 5 or not x.is_cuda or x.dtype not in (torch.float32, torch.bfloat16) or not ops.L.is_device_build()
+                or self.dropout is not None or self.multi_class or type(lc) is not CrossEntropyLoss or lc.class_weight is not None
+                or label.dtype != torch.int64 or label.dim() != 1 or label.shape[0] != x.shape[0] or self.num_classes > 1024):
+            return None
+        pooled = _PoolFn.apply(x)
+        loss, top1, top5, _ = _HeadCEFn.apply(pooled, self.fc_cls.weight, self.fc_cls.bias, label.contiguous())
+        losses = dict(top1_acc=top1, top5_acc=top5)
+        losses["loss_cls"] = loss * lc.loss_weight
+        return losses
 
     def loss(self, cls_score, label, **kwargs):
         losses = dict()
@@ -222,9 +281,13 @@ class RecognizerGCN(nn.Module):
         if keypoint.dtype != torch.float:
             keypoint = keypoint.float()
         x = self.extract_feat(keypoint[:, 0])
+        lab = label.squeeze(-1)
+        fused = self.cls_head.fused_loss(x, lab) if hasattr(self.cls_head, "fused_loss") else None
+        if fused is not None:
+            return fused
         cls_score = self.cls_head(x)
         losses = dict()
-        losses.update(self.cls_head.loss(cls_score, label.squeeze(-1)))
+        losses.update(self.cls_head.loss(cls_score, lab))
         return losses
 
     def forward_test(self, keypoint, **kwargs):

@@ -426,6 +426,19 @@ typedef struct dsg_pointwise_args {
 } dsg_pointwise_args;
 int dsg_pointwise(const dsg_pointwise_args* a, void* stream);
 
+/* ---- dsg_head_ce_fwd / dsg_head_ce_bwd ------------------------------------------------------
+ * The classification head after the pooled backbone feature (heads/simple_head.py:93-96 fc_cls; losses/cross_entropy_loss.py:77-80
+ * F.cross_entropy with class-index labels; core/evaluation top_k_accuracy), fp32:
+ *   fwd: logits[n,k] = pooled[n,:] . W[k,:] + b[k];  stats[n*3 + {0,1,2}] = {cross-entropy of sample n, top-1 hit, top-5 hit}
+ *        (stats / label may be NULL: scores only).  The batch means are one dsg_tmean over stats ([1, N, 1, 3]).
+ *   bwd: dlogits[n,k] = (softmax(logits[n,:])[k] - [k == label[n]]) * gscale[0]  (gscale on the device: upstream gradient * loss_weight / N),
+ *        dpooled[n,:] = dlogits[n,:] @ W (may be NULL), dW[k,:] += sum_n dlogits[n,k] pooled[n,:], db[k] += sum_n dlogits[n,k]
+ *        (dW / db may be NULL; they ACCUMULATE: the caller pre-zeroes them or passes its gradient sink). */
+int dsg_head_ce_fwd(const float* pooled, const float* W, const float* b, const long long* label, int N, int C, int K,
+                    float* logits, float* stats, void* stream);
+int dsg_head_ce_bwd(const float* logits, const long long* label, const float* pooled, const float* W, const float* gscale,
+                    int N, int C, int K, float* dlogits, float* dpooled, float* dW, float* db, void* stream);
+
 /* ---- dsg_sgd_step ---------------------------------------------------------------------------
  * Fused SGD (momentum, weight decay, Nesterov) over a flat fp32 parameter buffer:
  * configs/_init_/lr_schedual.py:11.  g = grad*grad_scale + wd*p; buf = mom*buf + g;

@@ -291,6 +291,39 @@ def test_conv_gemm_contract_ext_bn_backward_form(dev, dtype, V):
     close(ssq, (ref.double() * partner.double()).sum(0), dtype, "sum e*partner")
 
 
+@pytest.mark.parametrize("shape", [(37, 48, 13), (128, 256, 60), (5, 7, 3)])
+def test_head_ce_kernels(dev, shape):
+    """dsg_head_ce_fwd / _bwd: fc_cls + cross-entropy + top-1 / top-5 against nn.functional (heads/simple_head.py:93-96,
+    losses/cross_entropy_loss.py:77-80, top_k_accuracy)."""
+    N, Cn, K = shape
+    torch.manual_seed(N + K)
+    x, W, b = torch.randn(N, Cn), torch.randn(K, Cn) * 0.2, torch.randn(K) * 0.1
+    y = torch.randint(0, K, (N,))
+    xr, Wr, br = x.clone().requires_grad_(), W.clone().requires_grad_(), b.clone().requires_grad_()
+    lr = F.linear(xr, Wr, br)
+    loss_r = F.cross_entropy(lr, y)
+    (loss_r * 1.7).backward()
+    pred = lr.detach().topk(min(5, K), dim=1).indices
+    hit = pred.eq(y.view(-1, 1))
+    d = lambda t: t.to(dev)
+    logits, stats = ops.head_ce_fwd(d(x), d(W), d(b), d(y))
+    close(logits, lr, torch.float32, "logits")
+    means = stats.mean(0)
+    close(means[0], loss_r, torch.float32, "cross-entropy")
+    assert float(means[1]) == pytest.approx(float(hit[:, :1].any(1).float().mean()), abs=1e-6)
+    assert float(means[2]) == pytest.approx(float(hit.any(1).float().mean()), abs=1e-6)
+    dW, db = torch.zeros(K, Cn, device=dev), torch.zeros(K, device=dev)
+    gscale = torch.tensor([1.7 / N], device=dev)
+    dlogits, dx = ops.head_ce_bwd(logits, d(y), d(x), d(W), gscale, dW=dW, db=db)
+    close(dx, xr.grad, torch.float32, "dpooled")
+    close(dW, Wr.grad, torch.float32, "dW")
+    close(db, br.grad, torch.float32, "db")
+    # scores only (inference): no labels, no statistics
+    logits2, none = ops.head_ce_fwd(d(x), d(W), d(b))
+    assert none is None
+    close(logits2, lr, torch.float32, "logits (no labels)")
+
+
 def test_bn_finalize_matches_batch_norm(dev):
     torch.manual_seed(3)
     Cn, M = 37, 500

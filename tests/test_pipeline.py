@@ -227,3 +227,44 @@ def test_graphed_train_step_matches_eager():
     den = sum(float(p0[k].double().pow(2).sum()) for k in p0)
     assert (num / den) ** 0.5 < 1e-2
     step.release()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_fused_head_loss_matches_general_path(dtype):
+    """RecognizerGCN.forward_train through the fused head kernels (dsg_head_ce_fwd/_bwd) = the general path (nn.Linear +
+    F.cross_entropy + top-k, recognizergcn.py:20-51 / heads/base.py:50-84): same logged scalars, same gradients."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from dsgcn_b200 import modules as M
+    dsgcn_b200._lib._testing_use_library(None)
+    dev = torch.device("cuda:0")
+    torch.manual_seed(0); np.random.seed(0)
+    cfg = dict(gcn_type="dgphgcn1", gcn_ratio=0.25, gcn_node_attention=True, gcn_edge_attention=True, gcn_decompose=True,
+               gcn_subset_wise=True, gcn_ctr="T", gcn_ada="T", tcn_type="dgmstcn", base_channels=16,
+               graph_cfg=dict(layout="nturgb+d", mode="random", num_filter=3, init_off=.04, init_std=.02),
+               tcn_ms_cfg=[(3, 1), (3, 2), (3, 3), (3, 4), ("max", 3), "1x1"])
+    m = dsgcn_b200.RecognizerGCN(backbone=dict(type="DGSTGCN", **cfg), cls_head=dict(type="GCNHead", num_classes=12, in_channels=64)).to(dev).train()
+    with torch.no_grad():
+        m.cls_head.fc_cls.weight.normal_(0, 0.3)
+    x = torch.randn(6, 1, 2, 16, 25, 3, device=dev)
+    y = torch.randint(0, 12, (6, 1), device=dev)
+    M.set_compute_dtype(dtype)
+    try:
+        res = {}
+        for fused in (True, False):
+            m.cls_head.use_fused = fused
+            m.zero_grad(set_to_none=True)
+            sd = {k: v.clone() for k, v in m.state_dict().items()}
+            out = m.train_step(dict(keypoint=x, label=y), None)
+            out["loss"].backward()
+            res[fused] = (out["log_vars"], m.cls_head.fc_cls.weight.grad.clone(), m.cls_head.fc_cls.bias.grad.clone(),
+                          m.backbone.gcn[0].gcn.pre[0].weight.grad.clone())
+            m.load_state_dict(sd)                       # BatchNorm buffers back: both passes see the same model
+        for k in res[True][0]:
+            assert res[True][0][k] == pytest.approx(res[False][0][k], rel=1e-5, abs=1e-6), k
+        for a, b in zip(res[True][1:], res[False][1:]):
+            assert float((a - b).norm() / (b.norm() + 1e-12)) < (1e-4 if dtype == torch.float32 else 2e-2)
+    finally:
+        m.cls_head.use_fused = True
+        M.set_compute_dtype(torch.bfloat16)
