@@ -37,7 +37,15 @@ constexpr int G4_DRAIN_WARP = 2 + G4_XF_WARPS + G4_EPI_WARPS;            // warp
 constexpr int G4_THREADS = 32 * (G4_DRAIN_WARP + 1);                     // 480
 constexpr int G4_XF_T0 = 64, G4_EPI_T0 = 64 + 32 * G4_XF_WARPS;         // first thread of the transform / epilogue groups
 constexpr int G4_EPI_THREADS = 32 * G4_EPI_WARPS;                       // 256
-constexpr int G4_MAX_ATOMS = 12, G4_MAX_STAGES = 6, G4_MAX_OPS = 24;
+constexpr int G4_MAX_ATOMS = 12, G4_MAX_STAGES = 6, G4_MAX_OPS = 24, G4_MAX_OB = 4;
+// experiment knobs (environment, read once): cap of the operand ring depth / of the out-tile ring depth, transform mapping
+static inline int tc4_env_int(const char* name, int dflt) { const char* e = getenv(name); return (e && e[0]) ? atoi(e) : dflt; }
+static inline int tc4_s_cap() { static const int v = tc4_env_int("DSG_TC4_S", G4_MAX_STAGES); return v < 2 ? 2 : (v > G4_MAX_STAGES ? G4_MAX_STAGES : v); }
+static inline int tc4_ob_max() { static const int v = tc4_env_int("DSG_TC4_OB", 2); return v < 1 ? 1 : (v > G4_MAX_OB ? G4_MAX_OB : v); }
+static inline int tc4_drain_defer() { static const int v = tc4_env_int("DSG_TC4_DEFER", 0); return v; }
+static inline int tc4_dbg() { static const int v = tc4_env_int("DSG_TC4_DBG", 0); return v; }
+static inline int tc4_tail_tma() { static const int v = tc4_env_int("DSG_TC4_TAILTMA", 1); return v; }
+static inline int tc4_xf_map() { static const int v = tc4_env_int("DSG_TC4_XFMAP", 1); return v; }
 constexpr int G4_BAR_XF = 1, G4_BAR_EPI = 2;                            // named barriers
 
 struct G4Plan {
@@ -49,6 +57,16 @@ struct G4Plan {
     int ksteps[G4_MAX_ATOMS];    // K = 16 MMA steps per atom (live channels only)
     int K1p;                     // natoms1 * 64
     int Ntile, S, OB;            // output columns per CTA, A stages, out/stat buffers
+    // ---- staged tails: the epilogue's tail operands (addends, partner, mask sources) of a tile are brought in by the TMA unit with the
+    //      geometry of the out store (same boxes, same SWIZZLE_128B atoms) into a TB-deep ring, [tensor][out atom] per slot; the epilogue
+    //      reads them at the offsets it writes the out tile at.  tn = 0: per-thread 16-byte global loads (row-strided: 32 L1 tags per
+    //      warp instruction — the tails were bound by the LSU tag stage, bench_gemm bwd64: 119 us, 57 us without the tail work).
+    int tn, TB;                  // distinct tail tensors staged (<= 4), ring depth
+    int t_add, t_add2, t_part, t_m1, t_m2;      // ring tensor index of each operand (-1: absent)
+    unsigned off_tail, tail_stage_bytes;
+    int dbg;                     // timing experiments only (DSG_TC4_DBG; results are wrong): 1 skip statistics MMAs, 2 skip out stores, 4 skip epilogue math
+    int drain_defer;             // drain warp retires tile i-1 after issuing tile i (pipelined store / statistics completion)
+    int xfmap;                   // transform-warp mapping of the affine prologue: 1 = thread owns a 16-byte chunk column (coefficients in registers)
     int xf, act, stats;          // stats: 0 none, 1 Gram (sum v, sum v^2), 2 product tile (sum v, sum v*partner)
     unsigned off_w, off_a, off_out, off_stat, off_ones, off_cf;       // byte offsets from the 1024-aligned base
     unsigned w_tile_bytes, out_bytes, smem_total;
@@ -146,16 +164,20 @@ DSG_D void xf_contract_col(const unsigned char* rcol, unsigned char* ycol, const
     if (TAIL) xf_contract_group<VV, KK, TAIL ? TAIL : 1>(pv, ac + (VV - TAIL) * KK, ycol, row0 + VV - TAIL, chunk);
 }
 
+constexpr int G4_MAX_TAILS = 4, G4_TB = 2;
+struct G4TailMaps { CUtensorMap m[G4_MAX_TAILS]; };
+
 struct G4Bars {
     uint64_t full[G4_MAX_STAGES], empty[G4_MAX_STAGES], ready[G4_MAX_STAGES];
-    uint64_t wbar, acc_full[2], acc_free[2], out_ready[2], stat_done[2], out_free[2];
+    uint64_t wbar, acc_full[2], acc_free[2], out_ready[G4_MAX_OB], stat_done[G4_MAX_OB], out_free[G4_MAX_OB];
+    uint64_t tfull[G4_TB], tempty[G4_TB];
 };
 
 // XF: transform warps active; TAILS: any of add / add2 / bcast / mask / partner; STATS: 0 none, 1 Gram, 2 product tile
 template <bool XF, bool TAILS, int STATS>
 __global__ void __launch_bounds__(G4_THREADS, 1)
 tc4_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUtensorMap mapO,
-                const dsg_conv_gemm_args a, const G4Plan p, const float* __restrict__ cbias) {
+                const dsg_conv_gemm_args a, const G4Plan p, const float* __restrict__ cbias, const __grid_constant__ G4TailMaps tm) {
     // (mode 4 passes the tensor map of the contracted-tile side output Y as mapA1)
     DSG_DYN_SMEM(smem_raw);
     __shared__ G4Bars bars;
@@ -166,6 +188,7 @@ tc4_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
     unsigned char* Asm = sm + p.off_a;
     unsigned char* Osm = sm + p.off_out;
     unsigned char* Ssm = sm + p.off_stat;
+    unsigned char* Tsm = sm + p.off_tail;
     unsigned char* ones = sm + p.off_ones;
     float* tl_bias = reinterpret_cast<float*>(sm + p.off_cf);
     float* tl_ma1 = tl_bias + 128;
@@ -199,8 +222,9 @@ tc4_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
     if (tid == 0) {
         for (int s = 0; s < G4_MAX_STAGES; ++s) { mbar_init(&bars.full[s], 1); mbar_init(&bars.empty[s], 1); mbar_init(&bars.ready[s], 32 * G4_XF_WARPS); }
         mbar_init(&bars.wbar, 1);
-        for (int b = 0; b < 2; ++b) {
-            mbar_init(&bars.acc_full[b], 1); mbar_init(&bars.acc_free[b], G4_EPI_WARPS);
+        for (int b = 0; b < 2; ++b) { mbar_init(&bars.acc_full[b], 1); mbar_init(&bars.acc_free[b], G4_EPI_WARPS); }
+        for (int b = 0; b < G4_TB; ++b) { mbar_init(&bars.tfull[b], 1); mbar_init(&bars.tempty[b], G4_EPI_WARPS); }
+        for (int b = 0; b < G4_MAX_OB; ++b) {
             mbar_init(&bars.out_ready[b], G4_EPI_WARPS); mbar_init(&bars.stat_done[b], 1); mbar_init(&bars.out_free[b], 1);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -235,6 +259,24 @@ tc4_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
             for (int i = 0; i < n_my; ++i) {
                 const int tile = tile0 + i * tstep;
                 const int smp = p.mode >= 3 ? tile / p.tps : 0, q0 = p.mode >= 3 ? (tile - smp * p.tps) * p.F : 0;
+                if (TAILS && p.tn > 0) {
+                    // tail operands of this tile: the boxes of the out store, one ring slot per tile
+                    const int tb = i % p.TB;
+                    mbar_wait(&bars.tempty[tb], (uint32_t)(((i / p.TB) & 1) ^ 1));
+                    const int Vo = a.Vin + a.ext_in - a.contract_ext;
+                    const uint32_t obox = p.mode == 0 ? (uint32_t)ATOM_BYTES : (uint32_t)(p.F * Vo * 128);
+                    mbar_expect_tx(&bars.tfull[tb], (uint32_t)(p.tn * n_oatoms) * obox);
+                    for (int t = 0; t < p.tn; ++t)
+                        for (int oa = 0; oa < n_oatoms; ++oa) {
+                            unsigned char* dst = Tsm + (size_t)tb * p.tail_stage_bytes + (size_t)t * p.out_bytes + (size_t)oa * ATOM_BYTES;
+                            const int c0 = n0 + oa * ATOM_CH;
+                            if (p.mode == 0) tma_load_2d(dst, &tm.m[t], c0, tile * ATOM_ROWS, &bars.tfull[tb]);
+                            else if (p.mode >= 3)
+                                for (int f = 0; f < p.F; ++f) tma_load_4d(dst + (size_t)f * p.slot * 128, &tm.m[t], c0, 0, q0 + f, smp, &bars.tfull[tb]);
+                            else
+                                for (int f = 0; f < p.F; ++f) tma_load_3d(dst + (size_t)f * p.slot * 128, &tm.m[t], c0, 0, tile * p.F + f, &bars.tfull[tb]);
+                        }
+                }
                 for (int ai = 0; ai < natoms; ++ai) {
                     mbar_wait_backoff(&bars.empty[stage], ph ^ 1, m4);
                     mbar_expect_tx(&bars.full[stage], p.mode == 3 ? (uint32_t)(p.t_nfr[yy][ai] * a.Vin * 128) : box_bytes);
@@ -367,7 +409,33 @@ tc4_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
                         // BN-affine (+ReLU) in place: thread = row; the logical chunk is uniform per step (broadcast coefficient loads,
                         // conflict-free 16-byte data accesses)
                         const bool live = p.mode == 0 ? true : ((t % p.slot) < Vr && t / p.slot < p.F);
-                        if (live) {
+                        if (p.xfmap) {
+                            // thread = (16-byte chunk column c, row residue r0): the column's 16 coefficients are loaded once per atom and the
+                            // thread's 8 rows (r0 + 16 j: same swizzle phase, addresses = base + j * 2048) are independent — 8 loads in flight,
+                            // no per-chunk coefficient reloads (ncu source page of the thread-per-row form: ~490 instructions per warp and atom
+                            // at ~7 cycles each; the transform warps were busy 80 % of the kernel)
+                            const int c = t & 7, r0 = t >> 3;
+                            const int k = kbase + c * 8;
+                            if (k < a.K) {
+                                float ka[8], kb[8];
+                                load8f(cf_a + k, ka, 1.f);
+                                load8f(cf_b + k, kb, 0.f);
+                                const float lo = a.src.relu ? 0.f : -3.0e38f;
+                                unsigned char* col = atom + atom_off(r0, c);
+                                uint4 qv[8];
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) qv[j] = *reinterpret_cast<const uint4*>(col + j * 2048);
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) {
+                                    const int row = r0 + 16 * j;
+                                    float x[8];
+                                    unpack8(qv[j], x);
+#pragma unroll
+                                    for (int e = 0; e < 8; ++e) x[e] = fmaxf(fmaf(x[e], ka[e], kb[e]), lo);
+                                    if (p.mode == 0 || ((row % p.slot) < Vr && row / p.slot < p.F)) *reinterpret_cast<uint4*>(col + j * 2048) = pack8(x);
+                                }
+                            }
+                        } else if (live) {
 #pragma unroll 2
                             for (int c = 0; c < 8; ++c) {
                                 const int k = kbase + c * 8;
@@ -475,11 +543,15 @@ tc4_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
             if (i >= p.OB) mbar_wait_backoff(&bars.out_free[ob], (uint32_t)((useo - 1) & 1), m4);     // out / product tiles of `OB` tiles ago have been read
             unsigned char* Ot = Osm + (size_t)ob * p.out_bytes;
             unsigned char* St = Ssm + (size_t)ob * p.out_bytes;
+            const bool tst = TAILS && p.tn > 0;
+            const int tb = tst ? i % p.TB : 0;
+            const unsigned char* Tt = Tsm + (size_t)tb * p.tail_stage_bytes;
+            if (tst) mbar_wait(&bars.tfull[tb], (uint32_t)((i / p.TB) & 1));
             const uint32_t acc = tmem + (uint32_t)(buf * p.acc_cols) + ((uint32_t)(q * 32) << 16);
             const bool row_ok = gr >= 0;
             const bool fold2 = !XF && p.mode == 2;       // gradient of the joint mean folded back on the accumulator (lane V of this warp)
             const float inv2 = 1.f / (float)p.V;
-            for (int cc = cbeg; cc < cend; ++cc) {
+            for (int cc = cbeg; cc < ((p.dbg & 4) ? cbeg : cend); ++cc) {
                 const int c16 = cc * 16;
                 float v[16];
                 if (!TAILS) {
@@ -520,7 +592,22 @@ tc4_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
                     const bool live0 = c < a.N, live1 = c + 8 < a.N;
                     uint4 ra[2], ra2[2], rp[2];
                     tc::Act8Raw rm[2];
-                    if (row_ok) {
+                    if (row_ok && tst) {
+                        // staged tails: this thread's row of the ring slot, at the offsets of the out tile (conflict-free 16-byte reads)
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            if (!(h ? live1 : live0)) continue;
+                            const int col = c16 + h * 8;
+                            const unsigned char* tp = Tt + (uint32_t)(col >> 6) * ATOM_BYTES + atom_off(r, (col & 63) >> 3);
+                            if (addp) ra[h] = *reinterpret_cast<const uint4*>(tp + (size_t)p.t_add * p.out_bytes);
+                            if (add2p) ra2[h] = *reinterpret_cast<const uint4*>(tp + (size_t)p.t_add2 * p.out_bytes);
+                            if (partp) rp[h] = *reinterpret_cast<const uint4*>(tp + (size_t)p.t_part * p.out_bytes);
+                            if (a.has_mask) {
+                                rm[h].a = *reinterpret_cast<const uint4*>(tp + (size_t)p.t_m1 * p.out_bytes);
+                                rm[h].b = p.t_m2 >= 0 ? *reinterpret_cast<const uint4*>(tp + (size_t)p.t_m2 * p.out_bytes) : make_uint4(0u, 0u, 0u, 0u);
+                            }
+                        }
+                    } else if (row_ok) {
 #pragma unroll
                         for (int h = 0; h < 2; ++h) {
                             if (!(h ? live1 : live0)) continue;
@@ -581,13 +668,13 @@ tc4_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
             if (lane == 0) {
                 mbar_arrive(&bars.acc_free[buf]);
                 mbar_arrive(&bars.out_ready[ob]);
+                if (tst) mbar_arrive(&bars.tempty[tb]);
             }
         }
         if (STATS != 0 && n_my > 0) {
             // ---- per-channel sums of this CTA (lane = channel): out_free of the last tile = its statistics MMAs are complete
             const int last = n_my - 1;
-            mbar_wait(&bars.out_free[last % p.OB], (uint32_t)((last / p.OB) & 1));
-            if (p.OB == 2 && n_my > 1) mbar_wait(&bars.out_free[(last - 1) % 2], (uint32_t)(((last - 1) / 2) & 1));
+            for (int j = 0; j < p.OB && j <= last; ++j) mbar_wait(&bars.out_free[(last - j) % p.OB], (uint32_t)(((last - j) / p.OB) & 1));
             tc_fence_after();
             if (half == 0) {
                 const bool m64 = Ntp <= 64;
@@ -627,7 +714,7 @@ tc4_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
             mbar_wait_backoff(&bars.out_ready[ob], (uint32_t)(useo & 1), m4);
             tc_fence_after();
             const unsigned char* Ot = Osm + (size_t)ob * p.out_bytes;
-            for (int oa = 0; oa < (a.out_f32 ? 0 : n_oatoms); ++oa) {
+            for (int oa = 0; oa < ((a.out_f32 || (p.dbg & 2)) ? 0 : n_oatoms); ++oa) {
                 const unsigned char* src = Ot + (size_t)oa * ATOM_BYTES;
                 if (p.mode == 0) tma_store_2d(&mapO, src, n0 + oa * ATOM_CH, tile * ATOM_ROWS);
                 else if (p.mode >= 3) {
@@ -639,7 +726,8 @@ tc4_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
                         if ((long long)tile * p.F + f < p.n_frames) tma_store_3d(&mapO, src + (size_t)f * p.slot * 128, n0 + oa * ATOM_CH, 0, tile * p.F + f);
             }
             tma_store_commit();
-            if (STATS != 0) {
+            if (STATS != 0 && (p.dbg & 1)) umma_commit(&bars.stat_done[ob]);
+            if (STATS != 0 && !(p.dbg & 1)) {
                 const uint32_t o0 = smem_u32(Ot), acc0 = i == 0 ? 0u : 1u;
                 const uint32_t idesc_1 = idesc_major(Ms, 8, 1, 0);
                 for (int ks = 0; ks < 8; ++ks)
@@ -656,9 +744,26 @@ tc4_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
                 }
                 umma_commit(&bars.stat_done[ob]);
             }
-            tma_store_wait_read<0>();
-            if (STATS != 0) mbar_wait(&bars.stat_done[ob], (uint32_t)(useo & 1));
-            mbar_arrive(&bars.out_free[ob]);
+            if (p.drain_defer) {
+                // retire the PREVIOUS tile: its store has read the out tile (at most this tile's group is still pending) and its statistics
+                // MMAs are complete.  The waits of a tile no longer sit between its own issue and the next tile's issue — the drain warp
+                // was a serial ~0.6 us per tile (fixed cost of every tile: bench_gemm, 64- vs 128-channel layers).
+                if (i > 0) {
+                    const int pb = (i - 1) % p.OB, pu = (i - 1) / p.OB;
+                    tma_store_wait_read<1>();
+                    if (STATS != 0) mbar_wait(&bars.stat_done[pb], (uint32_t)(pu & 1));
+                    mbar_arrive(&bars.out_free[pb]);
+                }
+                if (i == n_my - 1) {
+                    tma_store_wait_read<0>();
+                    if (STATS != 0) mbar_wait(&bars.stat_done[ob], (uint32_t)(useo & 1));
+                    mbar_arrive(&bars.out_free[ob]);
+                }
+            } else {
+                tma_store_wait_read<0>();
+                if (STATS != 0) mbar_wait(&bars.stat_done[ob], (uint32_t)(useo & 1));
+                mbar_arrive(&bars.out_free[ob]);
+            }
         }
         tma_store_wait_all<0>();
     }
@@ -673,8 +778,36 @@ static inline long long tc4_wpack_bytes(int K, int N) {
     return t64 * kat * 64 * 128 + (long long)((N + 63) & ~63) * 4 + 512;
 }
 
-static bool tc4_plan(const dsg_conv_gemm_args& a, G4Plan& p, bool fold) {
+// the distinct tail tensors of a call (a tensor that is both mask source and partner is staged once)
+struct G4TailSel { const void* ptr[G4_MAX_TAILS]; long long ld[G4_MAX_TAILS]; int n; int idx[5]; bool ok; };
+static inline G4TailSel tc4_tail_select(const void* add, long long ld_add, const void* add2, long long ld_add2, const void* partner, long long ld_partner,
+                                        int has_mask, const dsg_act_src& mask) {
+    G4TailSel s{};
+    s.ok = tc4_tail_tma() != 0;
+    const void* ptrs[5] = {add, add2, partner, has_mask ? mask.x1 : nullptr, has_mask ? mask.x2 : nullptr};
+    const long long lds[5] = {ld_add, ld_add2, ld_partner, mask.ld1, mask.ld2};
+    for (int k = 0; k < 5; ++k) {
+        s.idx[k] = -1;
+        if (!ptrs[k]) continue;
+        if (!tma_ptr_ok(ptrs[k], lds[k])) { s.ok = false; continue; }
+        for (int j = 0; j < s.n; ++j)
+            if (s.ptr[j] == ptrs[k] && s.ld[j] == lds[k]) s.idx[k] = j;
+        if (s.idx[k] >= 0) continue;
+        if (s.n == G4_MAX_TAILS) { s.ok = false; continue; }
+        s.ptr[s.n] = ptrs[k]; s.ld[s.n] = lds[k]; s.idx[k] = s.n++;
+    }
+    if (s.n == 0) s.ok = false;
+    return s;
+}
+static inline void tc4_plan_tails(G4Plan& p, const G4TailSel& sel, int tn) {
+    p.tn = tn; p.TB = G4_TB;
+    p.t_add = tn ? sel.idx[0] : -1; p.t_add2 = tn ? sel.idx[1] : -1; p.t_part = tn ? sel.idx[2] : -1;
+    p.t_m1 = tn ? sel.idx[3] : -1; p.t_m2 = tn ? sel.idx[4] : -1;
+}
+
+static bool tc4_plan(const dsg_conv_gemm_args& a, G4Plan& p, bool fold, const G4TailSel& sel, int tn) {
     p = G4Plan{};
+    tc4_plan_tails(p, sel, tn);
     const int Vout = a.Vin + a.ext_in - a.contract_ext;
     p.mode = a.ext_in ? 1 : (a.contract_ext ? 2 : 0);
     p.V = a.ext_in ? a.Vin : (a.contract_ext ? a.Vin - 1 : a.Vin);
@@ -707,6 +840,8 @@ static bool tc4_plan(const dsg_conv_gemm_args& a, G4Plan& p, bool fold) {
     // mode 2 with 32-row frame slots and no ReLU prologue: the fold-back is linear, so it is applied to the ACCUMULATOR rows in the
     // epilogue (a frame = one warp's 32 TMEM lanes: out[v] += out[V] / V is one shuffle per column) and no thread touches the operand
     p.xf = (p.act || p.mode == 1 || (p.mode == 2 && p.slot != 32)) ? 1 : 0;
+    p.xfmap = tc4_xf_map();
+    p.dbg = tc4_dbg();
     p.stats = a.stat_sum == nullptr ? 0 : (a.partner ? 2 : 1);
     const unsigned cf_bytes = (unsigned)((4 * 128 + 2 * p.K1p) * sizeof(float));
     const unsigned budget = 227u * 1024u - 2048u;         // dynamic shared memory we may ask for (static barriers + alignment slack kept)
@@ -715,19 +850,23 @@ static bool tc4_plan(const dsg_conv_gemm_args& a, G4Plan& p, bool fold) {
         const int Ntile = cand_nt[ci];
         const unsigned wb = (unsigned)p.natoms * Ntile * 128;
         const unsigned ob1 = (unsigned)(Ntile / ATOM_CH) * ATOM_BYTES;
-        for (int OB = 2; OB >= 1; --OB) {
-            const unsigned fixed = wb + OB * ob1 * (p.stats == 2 ? 2u : 1u) + 1024u + ((cf_bytes + 1023u) & ~1023u) + 1024u;
+        for (int OB = tc4_ob_max(); OB >= 1; --OB) {
+            const unsigned tail_stage = (unsigned)tn * ob1;
+            const unsigned fixed = wb + OB * ob1 * (p.stats == 2 ? 2u : 1u) + G4_TB * tail_stage + 1024u + ((cf_bytes + 1023u) & ~1023u) + 1024u;
             if (fixed + 3u * ATOM_BYTES > budget) continue;
             int S = (int)((budget - fixed) / ATOM_BYTES);
-            if (S > G4_MAX_STAGES) S = G4_MAX_STAGES;
-            if (OB == 2 && S < 4 && ci == 0) continue;    // prefer a deeper ring over double-buffered out tiles
+            if (S > tc4_s_cap()) S = tc4_s_cap();
+            if (OB >= 2 && S < (tc4_s_cap() < 4 ? tc4_s_cap() : 4) && ci == 0) continue;    // prefer a deeper ring over multi-buffered out tiles
             p.Ntile = Ntile; p.S = S; p.OB = OB;
+            p.drain_defer = (OB >= 2 && tc4_drain_defer()) ? 1 : 0;      // OB = 1: the epilogue needs the previous tile retired first
             p.off_w = 0;
             p.off_a = wb;                                  // multiples of 1024 throughout
             p.off_out = p.off_a + (unsigned)S * ATOM_BYTES;
             p.out_bytes = ob1;
             p.off_stat = p.off_out + OB * ob1;
-            p.off_ones = p.off_stat + (p.stats == 2 ? OB * ob1 : 0u);
+            p.off_tail = p.off_stat + (p.stats == 2 ? OB * ob1 : 0u);
+            p.tail_stage_bytes = tail_stage;
+            p.off_ones = p.off_tail + G4_TB * tail_stage;
             p.off_cf = p.off_ones + 1024u;
             p.smem_total = p.off_cf + ((cf_bytes + 1023u) & ~1023u) + 1024u;
             p.w_tile_bytes = wb;
@@ -790,6 +929,7 @@ static const char* launch_conv_gemm_tc4_fused(const dsg_conv_gemm_args& a, dsg_s
         int S = (int)((budget - fixed) / (2u * ATOM_BYTES));
         if (S > 4) S = 4;
         p.S = S; p.OB = OB;
+        p.drain_defer = (OB >= 2 && tc4_drain_defer()) ? 1 : 0;
         p.off_w = 0;
         p.off_a = wb;
         p.off_out = p.off_a + (unsigned)S * 2u * ATOM_BYTES;
@@ -829,7 +969,7 @@ static const char* launch_conv_gemm_tc4_fused(const dsg_conv_gemm_args& a, dsg_s
 #define DSG_T4F_LAUNCH(TL_, ST_)                                                                                                   \
     do {                                                                                                                          \
         cudaFuncSetAttribute(tc4_gemm_kernel<true, TL_, ST_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_total);    \
-        tc4_gemm_kernel<true, TL_, ST_><<<dim3((unsigned)gx, 1), dim3(G4_THREADS), p.smem_total, st>>>(mA0, mY, mO, a, p, cbias); \
+        tc4_gemm_kernel<true, TL_, ST_><<<dim3((unsigned)gx, 1), dim3(G4_THREADS), p.smem_total, st>>>(mA0, mY, mO, a, p, cbias, G4TailMaps{}); \
     } while (0)
     if (!tails && p.stats == 0) DSG_T4F_LAUNCH(false, 0);
     else if (!tails && p.stats == 1) DSG_T4F_LAUNCH(false, 1);
@@ -861,9 +1001,11 @@ static const char* launch_conv_gemm_tc4(const dsg_conv_gemm_args& a, dsg_stream_
     const long long n_frames = (long long)a.n_samples * a.T_out;
     if (n_frames <= 0) { *handled = true; return nullptr; }
     G4Plan p;
-    if (!tc4_plan(a, p, fold)) return nullptr;
+    const G4TailSel sel = a.out_f32 ? G4TailSel{} : tc4_tail_select(a.add, a.ld_add, a.add2, a.ld_add2, a.partner, a.ld_partner, a.has_mask, a.mask);
+    if (!(sel.ok && tc4_plan(a, p, fold, sel, sel.n)) && !tc4_plan(a, p, fold, sel, 0)) return nullptr;
     if (!encode_fn()) return nullptr;
     CUtensorMap mA0, mA1, mO;
+    G4TailMaps tmaps;
     const long long rows_in = n_frames * a.Vin;
     bool ok;
     if (p.mode == 0) {
@@ -872,6 +1014,7 @@ static const char* launch_conv_gemm_tc4(const dsg_conv_gemm_args& a, dsg_stream_
         if (ok && p.natoms > p.natoms1) ok = make_map_2d(&mA1, a.src.x2, rows_in, a.K, a.src.ld2, ATOM_ROWS);
         if (a.out_f32) mO = mA0;                               // never dereferenced: rows go out through plain stores
         else ok = ok && make_map_2d(&mO, a.out, p.rows_out, a.N, a.ld_out, ATOM_ROWS);
+        for (int t = 0; t < p.tn && ok; ++t) ok = make_map_2d(&tmaps.m[t], sel.ptr[t], p.rows_out, a.N, sel.ld[t], ATOM_ROWS);
     } else {
         const int rin = a.Vin, rout = a.Vin + a.ext_in - a.contract_ext;
         ok = make_map_3d(&mA0, a.src.x1, n_frames, rin, a.K, a.src.ld1, rin, 1);
@@ -879,6 +1022,7 @@ static const char* launch_conv_gemm_tc4(const dsg_conv_gemm_args& a, dsg_stream_
         if (ok && p.natoms > p.natoms1) ok = make_map_3d(&mA1, a.src.x2, n_frames, rin, a.K, a.src.ld2, rin, 1);
         if (a.out_f32) mO = mA0;
         else ok = ok && make_map_3d(&mO, a.out, n_frames, rout, a.N, a.ld_out, rout, 1);
+        for (int t = 0; t < p.tn && ok; ++t) ok = make_map_3d(&tmaps.m[t], sel.ptr[t], n_frames, rout, a.N, sel.ld[t], rout, 1);
     }
     if (!ok) return nullptr;
     const unsigned gy = (unsigned)((a.N + p.Ntile - 1) / p.Ntile);
@@ -901,7 +1045,7 @@ static const char* launch_conv_gemm_tc4(const dsg_conv_gemm_args& a, dsg_stream_
 #define DSG_T4_LAUNCH(XF_, TL_, ST_)                                                                                              \
     do {                                                                                                                          \
         cudaFuncSetAttribute(tc4_gemm_kernel<XF_, TL_, ST_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_total);     \
-        tc4_gemm_kernel<XF_, TL_, ST_><<<dim3((unsigned)gx, gy), dim3(G4_THREADS), p.smem_total, st>>>(mA0, mA1, mO, a, p, cbias); \
+        tc4_gemm_kernel<XF_, TL_, ST_><<<dim3((unsigned)gx, gy), dim3(G4_THREADS), p.smem_total, st>>>(mA0, mA1, mO, a, p, cbias, tmaps); \
     } while (0)
     switch (variant) {
         case 0: DSG_T4_LAUNCH(false, false, 0); break;

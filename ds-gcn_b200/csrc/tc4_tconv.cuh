@@ -176,20 +176,35 @@ static const char* tconv_launch(const dsg_ms_conv_args& a, int qs, int qp, bool 
     const unsigned cf_bytes = (unsigned)(4 * 128 * sizeof(float));
     const unsigned budget = 227u * 1024u - 2048u;
     bool fit = false;
+    // tail operands at the destination rows (column 0 = channel span_lo): staged through the TMA ring when they fit (tc4_gemm.cuh)
+    dsg_act_src mk = a.mask;
+    if (a.has_mask) {
+        mk.x1 = reinterpret_cast<const bf16*>(a.mask.x1) + span_lo;
+        if (mk.x2) mk.x2 = reinterpret_cast<const bf16*>(a.mask.x2) + span_lo;
+    }
+    const void* partp = a.partner ? reinterpret_cast<const bf16*>(a.partner) + span_lo : nullptr;
+    const G4TailSel sel = tc4_tail_select(nullptr, 0, nullptr, 0, partp, a.ld_partner, a.has_mask, mk);
+    for (int pass = sel.ok ? 0 : 1; pass < 2 && !fit; ++pass)
     for (int OB = 2; OB >= 1 && !fit; --OB) {
-        const unsigned fixed = wb + OB * ob1 * (p.stats == 2 ? 2u : 1u) + 1024u + ((cf_bytes + 1023u) & ~1023u) + 1024u;
+        const int tn = pass == 0 ? sel.n : 0;
+        const unsigned tail_stage = (unsigned)tn * ob1;
+        const unsigned fixed = wb + OB * ob1 * (p.stats == 2 ? 2u : 1u) + G4_TB * tail_stage + 1024u + ((cf_bytes + 1023u) & ~1023u) + 1024u;
         const unsigned min_stages = windows ? 2u : 3u;
         if (fixed + min_stages * p.t_stage > budget) continue;
         int S = (int)((budget - fixed) / p.t_stage);
-        if (S > G4_MAX_STAGES) S = G4_MAX_STAGES;
-        if (OB == 2 && S < (windows ? 3 : 4)) continue;
+        if (S > tc4_s_cap()) S = tc4_s_cap();
+        if (OB == 2 && S < (windows ? 3 : 4) && tc4_s_cap() >= 4) continue;
         p.S = S; p.OB = OB;
+        p.drain_defer = (OB >= 2 && tc4_drain_defer()) ? 1 : 0;
         p.off_w = 0;
         p.off_a = wb;
         p.off_out = p.off_a + (unsigned)S * p.t_stage;
         p.out_bytes = ob1;
         p.off_stat = p.off_out + OB * ob1;
-        p.off_ones = p.off_stat + (p.stats == 2 ? OB * ob1 : 0u);
+        tc4_plan_tails(p, sel, tn);
+        p.off_tail = p.off_stat + (p.stats == 2 ? OB * ob1 : 0u);
+        p.tail_stage_bytes = tail_stage;
+        p.off_ones = p.off_tail + G4_TB * tail_stage;
         p.off_cf = p.off_ones + 1024u;
         p.smem_total = p.off_cf + ((cf_bytes + 1023u) & ~1023u) + 1024u;
         fit = true;
@@ -212,6 +227,8 @@ static const char* tconv_launch(const dsg_ms_conv_args& a, int qs, int qp, bool 
     if (ok && use_map1) ok = make_map_4d(&mA1, a.src, a.n_samples, Tsrc, a.Vr, span_hi, a.ld_src, 1, src_planes);
     const bf16* outp = reinterpret_cast<const bf16*>(a.out) + span_lo;
     ok = ok && make_map_4d(&mO, outp, a.n_samples, Tdst, a.Vr, N, a.ld_out, qp, qs);
+    G4TailMaps tmaps;
+    for (int t = 0; t < p.tn && ok; ++t) ok = make_map_4d(&tmaps.m[t], sel.ptr[t], a.n_samples, Tdst, a.Vr, N, sel.ld[t], qp, qs);
     if (!ok) return nullptr;
 
     // ---- the engine's argument block (column 0 = channel span_lo)
@@ -245,7 +262,7 @@ static const char* tconv_launch(const dsg_ms_conv_args& a, int qs, int qp, bool 
 #define DSG_TC_LAUNCH(TL_, ST_)                                                                                                      \
     do {                                                                                                                             \
         cudaFuncSetAttribute(tc4_gemm_kernel<false, TL_, ST_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem_total);      \
-        tc4_gemm_kernel<false, TL_, ST_><<<dim3((unsigned)gx, (unsigned)gy), dim3(G4_THREADS), p.smem_total, st>>>(mA0, mA1, mO, g, p, cbias); \
+        tc4_gemm_kernel<false, TL_, ST_><<<dim3((unsigned)gx, (unsigned)gy), dim3(G4_THREADS), p.smem_total, st>>>(mA0, mA1, mO, g, p, cbias, tmaps); \
     } while (0)
     if (!tails && p.stats == 0) DSG_TC_LAUNCH(false, 0);
     else if (!tails && p.stats == 1) DSG_TC_LAUNCH(false, 1);

@@ -41,6 +41,7 @@ struct W4Plan {
     int S;
     unsigned stage_bytes, off_ones, off_xs, smem_total;
     int xf_act, xf_mean, need_xs, do_bias;
+    int xfmap;                   // affine prologue mapping: 1 = thread owns a 16-byte chunk column (as tc4_gemm.cuh)
     int colY, colS, tmem_cols;   // TMEM columns: e^T x at 0, y^T x at colY, sums at colS (+0 e, +8 y, +16 / +24 x)
 };
 
@@ -185,7 +186,37 @@ tc4_wgrad_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
                         const int f = t / p.slot, v = t - f * p.slot;
                         live = f < p.F && v < p.Vx && (long long)tile * p.F + f < p.n_frames;
                     }
-                    if (live)
+                    if (p.xfmap) {
+                        // thread = (16-byte chunk column, row residue): coefficients in registers, 8 independent rows per thread
+                        const int c = t & 7, r0 = t >> 3;
+                        const float lo = a.A.relu ? 0.f : -3.0e38f;
+                        for (int ai = 0; ai < ka; ++ai) {
+                            const int k = ai * ATOM_CH + c * 8;
+                            if (k >= Kt) break;
+                            float ca8[8], cb8[8];
+                            load8f(cf_a + k, ca8, 1.f);
+                            load8f(cf_b + k, cb8, 0.f);
+                            unsigned char* col = st + (size_t)ai * ATOM_BYTES + atom_off(r0, c);
+                            uint4 qv[8];
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) qv[j] = *reinterpret_cast<const uint4*>(col + j * 2048);
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                const int row = r0 + 16 * j;
+                                bool lv;
+                                if (p.mode == 0) lv = (long long)tile * ATOM_ROWS + row < rows_x;
+                                else {
+                                    const int f = row / p.slot, v = row - f * p.slot;
+                                    lv = f < p.F && v < p.Vx && (long long)tile * p.F + f < p.n_frames;
+                                }
+                                float x[8];
+                                unpack8(qv[j], x);
+#pragma unroll
+                                for (int e = 0; e < 8; ++e) x[e] = fmaxf(fmaf(x[e], ca8[e], cb8[e]), lo);
+                                if (lv) *reinterpret_cast<uint4*>(col + j * 2048) = pack8(x);
+                            }
+                        }
+                    } else if (live)
                         for (int ai = 0; ai < ka; ++ai) {
                             unsigned char* atom = st + (size_t)ai * ATOM_BYTES;
 #pragma unroll 2
@@ -360,6 +391,7 @@ static const char* launch_conv_wgrad_tc4(const dsg_conv_wgrad_args& a, dsg_strea
     p.ka_max = p.Kt_max / ATOM_CH;
     p.na_max = a.N > ATOM_CH ? 2 : 1;
     p.xf_act = (a.A.a1 || a.A.b1 || a.A.b2 || a.A.relu) ? 1 : 0;
+    p.xfmap = tc4_xf_map();
     p.xf_mean = a.ext_in ? 1 : 0;
     p.need_xs = (a.B.b1 || a.B.b2) ? 1 : 0;
     p.do_bias = a.db ? 1 : 0;
