@@ -97,7 +97,7 @@ def test_conv_gemm_temporal_conv_and_grads(dev, dtype, k, stride, dil):
 
 
 @pytest.mark.parametrize("K,N", [(64, 64), (24, 64), (64, 24), (176, 64), (96, 256), (128, 352), (256, 256), (128, 128)])
-@pytest.mark.parametrize("variant", ["fwd", "bwd", "ext_in", "contract"])
+@pytest.mark.parametrize("variant", ["fwd", "bwd", "bwd_same", "dx", "ext_in", "contract"])
 def test_conv_gemm_fast_engines(dev, K, N, variant):
     """bf16 shapes of the network (channels % 8 == 0) take the tcgen05 engines: the persistent ping-pong engine (several
     tiles per CTA, both accumulator phases, one or two K passes, narrow and multiple column tiles, per-pass weight copies)
@@ -139,6 +139,30 @@ def test_conv_gemm_fast_engines(dev, K, N, variant):
         ref = ref * ((mk.float() * ma + mb) > 0)
         close(ss, ref.sum(0), dtype, "sum")
         close(sq, (ref * partner.float()).sum(0), dtype, "sumprod")
+    elif variant == "bwd_same":
+        # the mask source is also the partner (transform / temporal-conv data gradients): staged once in the tail ring
+        x2 = rnd(rows_in, K, dev=dev, dtype=dtype)
+        a2, b2 = torch.rand(K, device=dev) + 0.5, rnd(K, dev=dev, scale=0.2)
+        mk = rnd(rows_out, N, dev=dev, dtype=dtype)
+        ma, mb = torch.rand(N, device=dev) + 0.5, rnd(N, dev=dev, scale=0.2)
+        ss, sq = torch.zeros(N, dtype=torch.float64, device=dev), torch.zeros(N, dtype=torch.float64, device=dev)
+        Wt = W.t().contiguous()
+        ops.conv_gemm(ops.Act(x, a1, b1, x2, a2, b2), Wt, N, out, ws=(1, N, 0), mask=ops.Act(mk, ma, mb), stat_sum=ss, stat_sq=sq,
+                      partner=mk, **kw)
+        ref = (x.float() * a1 + b1 + x2.float() * a2 + b2) @ W.t()
+        ref = ref * ((mk.float() * ma + mb) > 0)
+        close(ss, ref.sum(0), dtype, "sum")
+        close(sq, (ref * mk.float()).sum(0), dtype, "sumprod")
+    elif variant == "dx":
+        # last data gradient of a spatial unit: two addends and the per-sample broadcast row (dgphgcn1_backward)
+        x2 = rnd(rows_in, K, dev=dev, dtype=dtype)
+        a2, b2 = torch.rand(K, device=dev) + 0.5, rnd(K, dev=dev, scale=0.2)
+        add, add2 = rnd(rows_out, N, dev=dev, dtype=dtype), rnd(rows_out, N, dev=dev, dtype=dtype)
+        bc = rnd(n, V, N, dev=dev)
+        Wt = W.t().contiguous()
+        ops.conv_gemm(ops.Act(x, a1, b1, x2, a2, b2), Wt, N, out, ws=(1, N, 0), add=add, add2=add2, bcast=bc, bcast_scale=0.25, **kw)
+        ref = (x.float() * a1 + b1 + x2.float() * a2 + b2) @ W.t() + add.float() + add2.float()
+        ref = ref + 0.25 * bc[:, None].expand(n, T, V, N).reshape(-1, N)
     elif variant == "ext_in":
         ops.conv_gemm(ops.Act(x, a1, b1, relu=True), W, N, out, bias=b, ext_in=True, **kw)
         h = torch.relu(x.float() * a1 + b1).to(dtype).float().view(n * T, V, K)       # the mean is taken over the staged bf16 rows
