@@ -11,6 +11,7 @@ Reference semantics: pyskl/models/gcns/utils/gcn.py:2217-2365 (dgphgcn1), :75-94
 pyskl/models/gcns/utils/tcn.py:31-32 (unit_tcn), :162-177 (mstcn), :407-428 (dgmstcn),
 pyskl/models/gcns/dgstgcn.py:61-65 (DGBlock).
 """
+import contextlib
 import math
 import os
 
@@ -278,18 +279,24 @@ def dgphgcn1_forward(m, x, n, T, V, save):
     Wt = cat_params(m, "Wt", tw, (HC, Cin))
     bt = cat_params(m, "bt", tb, (HC,))
     H = torch.empty(n * V, HC, dtype=torch.float32, device=dev)
-    if tc_topo:
-        xm, xmb = ops.tmean(x, n, T, V, with_bf16=True)                         # [n,V,Cin] fp32 + bf16
-        xm2 = xmb.view(n * V, Cin)
-        ops.conv_gemm(xm2, Wt, HC, H, n_samples=n, T_in=1, T_out=1, Vin=V, bias=bt, out_f32=True)
-    else:
-        xm = ops.tmean(x, n, T, V)                                              # [n,V,Cin] fp32
-        xm2 = xm.view(n * V, Cin)
-        ops.conv_gemm(xm2, Wt, HC, H, n_samples=n, T_in=1, T_out=1, Vin=V, bias=bt)
     adyn = torch.empty(n, V, V, KC, dtype=dt, device=dev)
     S = torch.empty(n, 3, V, V, dtype=torch.float32, device=dev)
+    xm = torch.empty(n, V, Cin, dtype=torch.float32, device=dev)
+    xmb = torch.empty(n, V, Cin, dtype=torch.bfloat16, device=dev) if tc_topo else None
     We, be = (None, None) if plain else (m.edge_linears.weight.view(15 * R, R), m.edge_linears.bias)
-    ops.topology_fwd(H, n, V, R, nt, et, m.A, m.alpha, m.beta, We, be, adyn, S, plain=plain, subset_wise=bool(m.subset_wise))
+    # The topology chain (three small, latency-bound launches) is independent of the pre / down GEMM: it runs on the side stream
+    # next to it (fork / join edges under graph capture) and is joined in front of the contraction that reads adyn.
+    with (ops.L.side_stream() if TOPO_SIDE else contextlib.nullcontext()):
+        ops.L.keepalive.extend((x, Wt, bt, H, adyn, S, xm, xmb))
+        if tc_topo:
+            ops.tmean(x, n, T, V, with_bf16=True, out=(xm, xmb))                # [n,V,Cin] fp32 + bf16
+            xm2 = xmb.view(n * V, Cin)
+            ops.conv_gemm(xm2, Wt, HC, H, n_samples=n, T_in=1, T_out=1, Vin=V, bias=bt, out_f32=True)
+        else:
+            ops.tmean(x, n, T, V, out=(xm,))                                    # [n,V,Cin] fp32
+            xm2 = xm.view(n * V, Cin)
+            ops.conv_gemm(xm2, Wt, HC, H, n_samples=n, T_in=1, T_out=1, Vin=V, bias=bt)
+        ops.topology_fwd(H, n, V, R, nt, et, m.A, m.alpha, m.beta, We, be, adyn, S, plain=plain, subset_wise=bool(m.subset_wise))
 
     # ---- pre (+down) 1x1 convolutions in one GEMM, BatchNorm statistics in the epilogue
     Npd = KC + (Cout if has_down else 0)
@@ -305,6 +312,8 @@ def dgphgcn1_forward(m, x, n, T, V, save):
     if has_down:
         c_pd.add_bn(m.down[1], KC, Npd, rows)
     c_pd.run()
+    if TOPO_SIDE:
+        ops.L.join_side()
 
     # ---- y[n,t,w,kc] = sum_u relu(bn(pre))[n,t,u,kc] * adyn[n,u,w,kc];  z = post(y), BatchNorm statistics in the epilogue
     P_act = Act(PD[:, :KC], c_pd.a[:KC], c_pd.b[:KC], relu=True)
@@ -496,6 +505,7 @@ def _ms_fused_args(m, layout, b_act, n, T, T_out, s, V, has_ext, grads):
     return a if ops.ms_temporal_supported(a) else None
 
 
+TOPO_SIDE = os.environ.get("DSG_TOPO_SIDE", "1") != "0"       # 0: topology chain of the forward pass on the main stream
 FUSED_AGG = os.environ.get("DSG_FUSED_AGG", "1") != "0"     # 0: separate adjacency contraction (dsg_graph_agg) + post GEMM
 MS_TWGRAD = os.environ.get("DSG_MS_TWGRAD", "1") != "0"   # 0: round-1 temporal weight-gradient kernel (CUDA-core staging)
 MS_TAP = os.environ.get("DSG_MS_TAP", "1") != "0"      # 0: the staged single-kernel branch stage (ms_temporal_tc.cuh) instead

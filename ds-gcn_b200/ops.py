@@ -190,12 +190,13 @@ def bn_finalize(jobs):
     L.call("dsg_bn_finalize", arr, len(jobs), L.stream())
 
 
-def tmean(x, n_samples, T, V, with_bf16=False):
-    """x [n*T*V, C] -> xm [n, V, C] fp32 (and, with_bf16, a bf16 copy: operand of the tensor-core topology GEMMs)"""
+def tmean(x, n_samples, T, V, with_bf16=False, out=None):
+    """x [n*T*V, C] -> xm [n, V, C] fp32 (and, with_bf16, a bf16 copy: operand of the tensor-core topology GEMMs).
+    `out`: caller-allocated (xm[, xb]) — callers that launch on the side stream allocate on the main one."""
     Cn = x.shape[-1]
-    xm = torch.empty((n_samples, V, Cn), dtype=torch.float32, device=x.device)
+    xm = out[0] if out is not None else torch.empty((n_samples, V, Cn), dtype=torch.float32, device=x.device)
     if with_bf16:
-        xb = torch.empty((n_samples, V, Cn), dtype=torch.bfloat16, device=x.device)
+        xb = out[1] if out is not None else torch.empty((n_samples, V, Cn), dtype=torch.bfloat16, device=x.device)
         L.call("dsg_tmean2", L.ptr(x), L.dt(x), _ld(x), n_samples, T, V, Cn, L.ptr(xm), L.ptr(xb), L.stream())
         return xm, xb
     L.call("dsg_tmean", L.ptr(x), L.dt(x), _ld(x), n_samples, T, V, Cn, L.ptr(xm), L.stream())
