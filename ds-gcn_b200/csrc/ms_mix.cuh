@@ -72,7 +72,8 @@ DSG_D void mx_finish(const MxRaw& r, const MxKinds& k, bool has_m, bool has_p, c
     }
 }
 
-__global__ void __launch_bounds__(MX_THREADS) ms_mix_fwd_kernel(dsg_ms_combine_args a, int frames_per_cta) {
+template <int U, int OCC>
+__global__ void __launch_bounds__(MX_THREADS, OCC) ms_mix_fwd_kernel(dsg_ms_combine_args a, int frames_per_cta) {
     DSG_SHARED float s_red[2][2048];                     // [lanes][C] with lanes * C == 2048
     DSG_SHARED float addc_s[32];
     const int tid = threadIdx.x, nch = a.C >> 3, lanes = MX_THREADS / nch;
@@ -103,13 +104,13 @@ __global__ void __launch_bounds__(MX_THREADS) ms_mix_fwd_kernel(dsg_ms_combine_a
                 og[0] = make_float4(glob[0], glob[1], glob[2], glob[3]);
                 og[1] = make_float4(glob[4], glob[5], glob[6], glob[7]);
             }
-            for (int v0 = 0; v0 < V; v0 += MX_U) {
-                MxRaw raw[MX_U];
+            for (int v0 = 0; v0 < V; v0 += U) {
+                MxRaw raw[U];
 #pragma unroll
-                for (int u = 0; u < MX_U; ++u)
+                for (int u = 0; u < U; ++u)
                     if (v0 + u < V) raw[u] = mx_issue(a, k, f, fi, v0 + u, Vp, has_m, has_p, c8);
 #pragma unroll
-                for (int u = 0; u < MX_U; ++u) {
+                for (int u = 0; u < U; ++u) {
                     if (v0 + u >= V) break;
                     float val[8];
                     mx_finish(raw[u], k, has_m, has_p, ka, kb, val);
@@ -402,7 +403,13 @@ static const char* launch_ms_mix_fwd(const dsg_ms_combine_args& a, dsg_stream_t 
     if (n_frames <= 0) { *handled = true; return nullptr; }
     const int lanes = MX_THREADS / (a.C / 8);
     int fpc = lanes * 2;
-    dsg_launch(ms_mix_fwd_kernel, dim3((unsigned)((n_frames + fpc - 1) / fpc)), dim3(MX_THREADS), 0, st, a, fpc);
+    // rows in flight per thread x CTAs per SM: <2, 2> (128 registers, 16 warps per SM) 1.01 ms per step, <5, 1> (224 registers) 1.12 ms,
+    // <3, 2> (spills) 1.39 ms — 128 clips, B200
+    static const int var = [] { const char* e = getenv("DSG_MIX_FWD_VAR"); return (e && e[0]) ? atoi(e) : 2; }();
+    const dim3 grid((unsigned)((n_frames + fpc - 1) / fpc));
+    if (var == 1) dsg_launch(ms_mix_fwd_kernel<3, 2>, grid, dim3(MX_THREADS), 0, st, a, fpc);
+    else if (var == 2) dsg_launch(ms_mix_fwd_kernel<2, 2>, grid, dim3(MX_THREADS), 0, st, a, fpc);
+    else dsg_launch(ms_mix_fwd_kernel<5, 1>, grid, dim3(MX_THREADS), 0, st, a, fpc);
     *handled = true;
     return dsg_launch_error();
 }
