@@ -12,6 +12,7 @@
 namespace dsg {
 
 constexpr int TP_THREADS = 256;        // forward
+constexpr int TP_MAXCNT = 8;           // typed backward path: joints per node type it has room for (NTU: 6, COCO: 5)
 constexpr int TP_BWD_THREADS = 1024;   // backward: one CTA per SM (its accumulators fill shared memory), so many warps
 
 struct TopoSmem {
@@ -68,6 +69,80 @@ DSG_D float topo_arg1(const TopoSmem& sm, const float* We_s, const float* be_s, 
     return s;
 }
 
+// The edge type of a joint pair is a function of the two NODE types (graph.py: rank of the product of the signed type codes), and a
+// joint has one of 5 node types — so a source joint u meets at most 5 distinct edge-typed linears, one per node type of the target:
+//   We[e(u,w)] (x1[:,u] - x2[:,w]) + be[e(u,w)] = P1[u][type(w)] - P2[w][type(u)]
+//   P1[u][t][o] = be[E(type(u),t)][o] + sum_i We[E(type(u),t)][o][i] x1[i,u],   P2[w][t][o] = sum_i We[E(t,type(w))][o][i] x2[i,w]
+// = 250 R^2 multiply-adds per sample instead of 625 R^2, and the per-pair work is one subtraction.  topo_type_tables builds
+// E[5][5] from one representative joint per type and CHECKS the caller's tables against it (node types in 0..4, every pair's edge
+// type equal to E of its node types, in 0..14); a table that is not of that form keeps the per-pair path.
+struct TopoTypes { int nt[32]; int rep[8]; int E[25]; int ok; int list[32]; int off[8]; int maxcnt; };     // list: joints sorted by type, off[t]..off[t+1]
+DSG_D void topo_type_tables(const dsg_topology_args& a, TopoTypes& tt) {
+    const int tid = threadIdx.x, V = a.V;
+    if (tid < V) tt.nt[tid] = a.node_type[tid];
+    if (tid == 0) tt.ok = 1;
+    __syncthreads();
+    if (tid < V && (tt.nt[tid] < 0 || tt.nt[tid] > 4)) tt.ok = 0;
+    if (tid < 5) {
+        int r = -1;
+        for (int v = V - 1; v >= 0; --v)
+            if (tt.nt[v] == tid) r = v;
+        tt.rep[tid] = r;
+    }
+    __syncthreads();
+    if (tid < 25) {
+        const int ru = tt.rep[tid / 5], rw = tt.rep[tid % 5];
+        tt.E[tid] = (tt.ok && ru >= 0 && rw >= 0) ? a.edge_type[ru * V + rw] : 0;
+    }
+    if (tid == 32 && tt.ok) {                            // counting sort of the joints by node type
+        int q = 0, mx = 0;
+        for (int t = 0; t < 5; ++t) {
+            tt.off[t] = q;
+            for (int v = 0; v < V; ++v)
+                if (tt.nt[v] == t) tt.list[q++] = v;
+            mx = q - tt.off[t] > mx ? q - tt.off[t] : mx;
+        }
+        tt.off[5] = q;
+        tt.maxcnt = mx;
+    }
+    __syncthreads();
+    if (tt.ok)
+        for (int idx = tid; idx < V * V; idx += blockDim.x) {
+            const int e = a.edge_type[idx];
+            if (e < 0 || e > 14 || e != tt.E[tt.nt[idx / V] * 5 + tt.nt[idx % V]]) tt.ok = 0;
+        }
+    __syncthreads();
+}
+
+// images of the subset-1 features for the source joints of node type tu: P1t[ul][t][o] (bias included), P2t[w][o]
+DSG_D void topo_typed_images(const TopoTypes& tt, const float* We_s, const float* be_s, const float* x1b, const float* x2b, int R, int V, int tu,
+                             float* P1t, float* P2t) {
+    const int tid = threadIdx.x, NT = blockDim.x;
+    const int u0 = tt.off[tu], ntu = tt.off[tu + 1] - u0;
+    for (int idx = tid; idx < V * R; idx += NT) {
+        const int o = idx % R, w = idx / R;
+        const int e = tt.E[tu * 5 + tt.nt[w]];
+        const float* wr = We_s + (e * R + o) * (R + 1);
+        const float* xr = x2b + w;
+        float s0 = 0.f, s1 = 0.f;
+        int i = 0;
+        for (; i + 2 <= R; i += 2) { s0 = fmaf(wr[i], xr[i * V], s0); s1 = fmaf(wr[i + 1], xr[(i + 1) * V], s1); }
+        if (i < R) s0 = fmaf(wr[i], xr[i * V], s0);
+        P2t[idx] = s0 + s1;
+    }
+    for (int idx = tid; idx < ntu * 5 * R; idx += NT) {
+        const int o = idx % R, t = (idx / R) % 5, ul = idx / (5 * R);
+        const int e = tt.E[tu * 5 + t];
+        const float* wr = We_s + (e * R + o) * (R + 1);
+        const float* xr = x1b + tt.list[u0 + ul];
+        float s0 = be_s[e * R + o], s1 = 0.f;
+        int i = 0;
+        for (; i + 2 <= R; i += 2) { s0 = fmaf(wr[i], xr[i * V], s0); s1 = fmaf(wr[i + 1], xr[(i + 1) * V], s1); }
+        if (i < R) s0 = fmaf(wr[i], xr[i * V], s0);
+        P1t[idx] = s0 + s1;
+    }
+}
+
 // bf16 compute mode: the adjacency is rounded to bf16 (8 mantissa bits) right after, so the hardware tanh (MUFU.TANH, ~2^-11
 // relative error, one instruction instead of ~40) is exact enough; the fp32 parity mode keeps tanhf.
 template <bool FAST> DSG_D float topo_tanh(float x) {
@@ -87,7 +162,12 @@ __global__ void __launch_bounds__(TP_THREADS) topology_fwd_kernel(dsg_topology_a
     float* be_s = We_s + 15 * R * (R + 1);
     const int tid = threadIdx.x;
     const bool plain = a.variant == 1;
-    if (!plain) topo_stage_we(a, We_s, be_s);
+    float* P1t = be_s + 15 * R;                          // typed path: [TP_MAXCNT][5][R] images of the source joints of one node type
+    float* P2t = P1t + TP_MAXCNT * 5 * R;                //             [V][R] images of the target joints
+    DSG_SHARED TopoTypes tt;
+    if (!plain) { topo_stage_we(a, We_s, be_s); topo_type_tables(a, tt); }
+    // bf16 compute mode only: the fp32 parity mode keeps the reference's association (linear of the difference)
+    const bool typed = FAST && !plain && tt.ok && tt.maxcnt <= TP_MAXCNT;
     const int i1 = a.subset_wise ? 1 : 0, i2 = a.subset_wise ? 2 : 0;    // not subset-wise: alpha[0] / beta[0] scale every subset
     const float al0 = a.alpha[0], al1 = a.alpha[i1], al2 = a.alpha[i2];
     const float be0 = a.beta[0], be1 = a.beta[i1], be2 = a.beta[i2];
@@ -129,12 +209,28 @@ __global__ void __launch_bounds__(TP_THREADS) topology_fwd_kernel(dsg_topology_a
             stf<T>(out + (long long)uw * KC + k * R + c, v);
         }
         // subset 1: edge-typed linear; consecutive threads = consecutive output channels of one pair
-        for (int idx = tid; !plain && idx < VV * R; idx += TP_THREADS) {
+        for (int idx = tid; !plain && !typed && idx < VV * R; idx += TP_THREADS) {
             const int c = idx % R, uw = idx / R;
             const int u = uw / V, w = uw - u * V;
             const float th = topo_tanh<FAST>(topo_arg1(sm, We_s, be_s, R, V, a.edge_type[uw], c, u, w));
             const float v = a.A[VV + uw] + al1 * th + be1 * sm.S[VV + uw];
             stf<T>(out + (long long)uw * KC + R + c, v);
+        }
+        // typed form (topo_type_tables): per node type of the source joint, the images of the features under the 5 linears that
+        // type meets, then one subtraction per (pair, channel)
+        for (int tu = 0; typed && tu < 5; ++tu) {
+            const int u0 = tt.off[tu], ntu = tt.off[tu + 1] - u0;
+            if (ntu == 0) continue;                                 // CTA-uniform
+            __syncthreads();                                        // the previous type's readers are done
+            topo_typed_images(tt, We_s, be_s, sm.x1 + R * V, sm.x2 + R * V, R, V, tu, P1t, P2t);
+            __syncthreads();
+            for (int idx = tid; idx < ntu * V * R; idx += TP_THREADS) {
+                const int o = idx % R, w = (idx / R) % V, ul = idx / (V * R);
+                const int uw = tt.list[u0 + ul] * V + w;
+                const float th = topo_tanh<FAST>(P1t[(ul * 5 + tt.nt[w]) * R + o] - P2t[w * R + o]);
+                const float v = a.A[VV + uw] + al1 * th + be1 * sm.S[VV + uw];
+                stf<T>(out + (long long)uw * KC + R + o, v);
+            }
         }
     }
 }
@@ -162,8 +258,15 @@ __global__ void __launch_bounds__(NTB) topology_bwd_kernel(dsg_topology_args a) 
     float* d1s = be_s + 15 * R;                                               // [V][R] x1[1][:,u] - x2[1][:,w] of the current source joint
     unsigned char* et_s = reinterpret_cast<unsigned char*>(d1s + V * R);      // [V*V] edge types
     DSG_SHARED unsigned char ord_s[32 * 32];                                  // per source joint u: target joints sorted by edge type
+    DSG_SHARED TopoTypes tt;
+    float* P1t = d1s + V * R + (VV + 3) / 4;                                  // typed path: [TP_MAXCNT][5][R] images of the source joints of one type
+    float* HUt = P1t + TP_MAXCNT * 5 * R;                                     //             [TP_MAXCNT][5][R] sum of h over the targets of one type
+    float* P2t = hbuf;                                                        //             [V][R] images of the targets (per source type)
+    float* HWt = dbuf;                                                        //             [V][R] sum of h over the sources of the type
     const bool plain = a.variant == 1;
     const int sw = a.subset_wise ? 1 : 0;
+    if (!plain) topo_type_tables(a, tt);
+    const bool typed = FAST && !plain && tt.ok && tt.maxcnt <= TP_MAXCNT;      // bf16 compute mode only (the fp32 parity mode keeps the per-pair form)
     if (!plain) {
         topo_stage_we(a, We_s, be_s);
         for (int idx = tid; idx < VV; idx += NT) et_s[idx] = (unsigned char)a.edge_type[idx];
@@ -260,14 +363,92 @@ __global__ void __launch_bounds__(NTB) topology_bwd_kernel(dsg_topology_args a) 
         const float al1 = a.alpha[sw];
         const float* x1b = sm.x1 + R * V;
         const float* x2b = sm.x2 + R * V;
-        if (!plain) {                                                   // d1 of the first source joint (later ones are formed during (b))
+        if (typed) {
+            // (4t) subset 1 by node type of the source joint (topo_type_tables): three barriers per type instead of two per joint, every
+            //      phase V*R or more items wide, 750 R^2 multiply-adds per sample instead of 1875 R^2
+            for (int tu = 0; tu < 5; ++tu) {
+                const int u0 = tt.off[tu], ntu = tt.off[tu + 1] - u0;
+                if (ntu == 0) continue;                                 // CTA-uniform
+                // (a) images of the features under the 5 linears this source type meets
+                topo_typed_images(tt, We_s, be_s, x1b, x2b, R, V, tu, P1t, P2t);
+                __syncthreads();
+                // (b) h = alpha1 (1 - tanh^2) g per (source joint of the type, target joint, channel), summed over the targets of each
+                //     node type (HUt) and over the sources of this type (HWt): two passes that recompute h, fixed summation order
+                for (int idx = tid; idx < ntu * 5 * R; idx += NT) {
+                    const int o = idx % R, t = (idx / R) % 5, ul = idx / (5 * R);
+                    const int u = tt.list[u0 + ul];
+                    const float p1 = P1t[idx];
+                    float hs = 0.f;
+                    for (int q = tt.off[t]; q < tt.off[t + 1]; ++q) {
+                        const int w = tt.list[q];
+                        const float gg = g[(long long)(u * V + w) * KC + R + o];
+                        const float th = topo_tanh<FAST>(p1 - P2t[w * R + o]);
+                        my_dalpha1 = fmaf(gg, th, my_dalpha1);
+                        hs = fmaf(al1 * (1.f - th * th), gg, hs);
+                    }
+                    HUt[idx] = hs;
+                }
+                for (int idx = tid; idx < V * R; idx += NT) {
+                    const int o = idx % R, w = idx / R, tw = tt.nt[w];
+                    const float p2 = P2t[idx];
+                    float hs = 0.f;
+                    for (int ul = 0; ul < ntu; ++ul) {
+                        const float gg = g[(long long)(tt.list[u0 + ul] * V + w) * KC + R + o];
+                        const float th = topo_tanh<FAST>(P1t[(ul * 5 + tw) * R + o] - p2);
+                        hs = fmaf(al1 * (1.f - th * th), gg, hs);
+                    }
+                    HWt[idx] = hs;
+                }
+                __syncthreads();
+                // (c) every consumer of the sums writes its own accumulators
+                for (int idx = tid; idx < V * R; idx += NT) {           // dx2[1][i][w] -= sum_o We[E(tu,type w)][o][i] HWt[w][o]
+                    const int i = idx % R, w = idx / R;
+                    const float* wc = We_s + tt.E[tu * 5 + tt.nt[w]] * R * (R + 1) + i;
+                    const float* hr = HWt + w * R;
+                    float s0 = 0.f, s1 = 0.f;
+                    int o = 0;
+                    for (; o + 2 <= R; o += 2) { s0 = fmaf(wc[o * (R + 1)], hr[o], s0); s1 = fmaf(wc[(o + 1) * (R + 1)], hr[o + 1], s1); }
+                    if (o < R) s0 = fmaf(wc[o * (R + 1)], hr[o], s0);
+                    dx2[(R + i) * V + w] -= s0 + s1;
+                }
+                for (int idx = tid; idx < ntu * R; idx += NT) {         // dx1[1][i][u] += sum_t sum_o We[E(tu,t)][o][i] HUt[u][t][o]
+                    const int i = idx % R, ul = idx / R;
+                    float s0 = 0.f;
+                    for (int t = 0; t < 5; ++t) {
+                        const float* wc = We_s + tt.E[tu * 5 + t] * R * (R + 1) + i;
+                        const float* hr = HUt + (ul * 5 + t) * R;
+                        for (int o = 0; o < R; ++o) s0 = fmaf(wc[o * (R + 1)], hr[o], s0);
+                    }
+                    dx1[(R + i) * V + tt.list[u0 + ul]] += s0;
+                }
+                for (int idx = tid; idx < 5 * R * R; idx += NT) {       // dWe, dbe of the 5 edge types {tu, t}
+                    const int i = idx % R, o = (idx / R) % R, t = idx / (R * R);
+                    if (tt.off[t + 1] == tt.off[t]) continue;
+                    const int e = tt.E[tu * 5 + t];
+                    float acc = 0.f, hs = 0.f;
+                    for (int ul = 0; ul < ntu; ++ul) {
+                        const float h = HUt[(ul * 5 + t) * R + o];
+                        acc = fmaf(h, x1b[i * V + tt.list[u0 + ul]], acc);
+                        hs += h;
+                    }
+                    for (int q = tt.off[t]; q < tt.off[t + 1]; ++q) {
+                        const int w = tt.list[q];
+                        acc = fmaf(-HWt[w * R + o], x2b[i * V + w], acc);
+                    }
+                    dWe_acc[(e * R + o) * R + i] += acc;
+                    if (i == 0) dbe_acc[e * R + o] += hs;
+                }
+                __syncthreads();
+            }
+        }
+        if (!plain && !typed) {                                         // d1 of the first source joint (later ones are formed during (b))
             for (int idx = tid; idx < V * R; idx += NT) {
                 const int i = idx % R, w = idx / R;
                 d1s[idx] = x1b[i * V] - x2b[i * V + w];
             }
             __syncthreads();
         }
-        for (int u = 0; !plain && u <= V; ++u) {
+        for (int u = 0; !plain && !typed && u <= V; ++u) {
             if (u > 0 && tid < R) {                                     // dx1[1][i][u-1] += sum_w dd1[w][i]
                 float sacc = 0.f;
                 for (int ww = 0; ww < V; ++ww) sacc += dbuf[ww * R + tid];
@@ -369,7 +550,8 @@ __global__ void __launch_bounds__(NTB) topology_bwd_kernel(dsg_topology_args a) 
 }
 
 static inline size_t topo_bwd_smem_floats(int R, int V) {
-    return TopoSmem::floats(R, V) + (size_t)6 * R * V + 3 * V * V + 15 * R * R + 15 * R + 2 * V * R + 8 + 15 * R * (R + 1) + 15 * R + V * R + (V * V + 3) / 4;
+    return TopoSmem::floats(R, V) + (size_t)6 * R * V + 3 * V * V + 15 * R * R + 15 * R + 2 * V * R + 8 + 15 * R * (R + 1) + 15 * R + V * R + (V * V + 3) / 4 +
+           (size_t)2 * TP_MAXCNT * 5 * R;
 }
 
 static const char* launch_topology(const dsg_topology_args& a, bool bwd, dsg_stream_t st) {
@@ -377,7 +559,7 @@ static const char* launch_topology(const dsg_topology_args& a, bool bwd, dsg_str
     if (a.n_samples <= 0) return nullptr;
     int grid = a.n_samples < 2 * dsg_num_sms() ? a.n_samples : 2 * dsg_num_sms();
     if (!bwd) {
-        size_t smem = (TopoSmem::floats(a.R, a.V) + (size_t)15 * a.R * (a.R + 1) + 15 * a.R) * sizeof(float);
+        size_t smem = (TopoSmem::floats(a.R, a.V) + (size_t)15 * a.R * (a.R + 1) + 15 * a.R + (size_t)(TP_MAXCNT * 5 + a.V) * a.R) * sizeof(float);
         if (a.adyn_dtype == DSG_BF16) {
             DSG_SET_SMEM(topology_fwd_kernel<bf16>, smem);
             dsg_launch(topology_fwd_kernel<bf16>, dim3(grid), dim3(TP_THREADS), smem, st, a);

@@ -430,11 +430,16 @@ def _topo_setup(layout, R, n, cin, seed):
     return V, nt, et, sd, xm
 
 
-@pytest.mark.parametrize("layout,R", [("nturgb+d", 8), ("coco", 16), ("nturgb+d", 32)])
+@pytest.mark.parametrize("layout,R", [("nturgb+d", 8), ("coco", 16), ("nturgb+d", 32), ("nturgb+d/scrambled", 8)])
 @pytest.mark.parametrize("adyn_dtype", DTYPES)
 def test_topology_fwd_bwd(dev, layout, R, adyn_dtype):
+    """The reference's tables make the edge type a function of the two node types: the kernels then work per node type (typed path).
+    "/scrambled": an edge-type table that is NOT of that form must take the per-pair path and still match the oracle."""
     n, cin = 3, 12
-    V, nt, et, sd, xm = _topo_setup(layout, R, n, cin, 5)
+    scrambled = layout.endswith("/scrambled")
+    V, nt, et, sd, xm = _topo_setup(layout.split("/")[0], R, n, cin, 5)
+    if scrambled:
+        et = np.random.RandomState(3).randint(0, 15, size=(V, V))
     for v in sd.values():
         v.requires_grad_()
     xmr = xm.clone().requires_grad_()
@@ -456,17 +461,24 @@ def test_topology_fwd_bwd(dev, layout, R, adyn_dtype):
     ops.topology_fwd(*common, adyn, S)
     ref_l = ref.detach().permute(0, 3, 4, 1, 2).reshape(n, V, V, 3 * R)
     close(adyn, ref_l, adyn_dtype, "adyn")
-    if adyn_dtype != torch.float32:
-        return
     dadyn = d(g.permute(0, 3, 4, 1, 2).reshape(n, V, V, 3 * R))
     dH = torch.empty_like(H)
     dA, dal, dbe_, dWe, dbe = (torch.zeros_like(t) for t in (d(sd["A"]), d(sd["alpha"]), d(sd["beta"]), We, be))
-    ops.topology_bwd(*common, S, dadyn, dH, dA, dal, dbe_, dWe, dbe)
-    close(dA, sd["A"].grad, torch.float32, "dA")
-    close(dal, sd["alpha"].grad, torch.float32, "dalpha")
-    close(dbe_, sd["beta"].grad, torch.float32, "dbeta")
-    close(dWe, sd["edge_linears.weight"].grad[:, :, 0, 0], torch.float32, "dWe")
-    close(dbe, sd["edge_linears.bias"].grad, torch.float32, "dbe")
+    # bf16 compute mode = the caller asks for the bf16 copy of dH: hardware tanh and the per-node-type form of the edge-typed
+    # linear (exact tanhf on the simulator); the fp32 outputs are compared either way
+    dHb = torch.empty(H.shape, dtype=torch.bfloat16, device=dev) if adyn_dtype != torch.float32 else None
+    gt = adyn_dtype if dev.type == "cuda" else torch.float32
+    ops.topology_bwd(*common, S, dadyn, dH, dA, dal, dbe_, dWe, dbe, dH_bf16=dHb)
+    close(dA, sd["A"].grad, gt, "dA")
+    close(dal, sd["alpha"].grad, gt, "dalpha")
+    close(dbe_, sd["beta"].grad, gt, "dbeta")
+    close(dWe, sd["edge_linears.weight"].grad[:, :, 0, 0], gt, "dWe")
+    close(dbe, sd["edge_linears.bias"].grad, gt, "dbe")
+    if adyn_dtype != torch.float32:
+        close(dHb, dH, adyn_dtype, "dH bf16 copy")
+        Wc = torch.cat([sd["conv1.weight"], sd["conv2.weight"], sd["conv1_se.weight"]])[:, :, 0, 0].detach()
+        close(dH.reshape(n, V, 9 * R).cpu() @ Wc, xmr.grad.permute(0, 2, 1), gt, "dxm (dH through the feature convolutions)")
+        return
     # dH -> weight grads and dxm through the generic GEMMs
     dW = torch.zeros(9 * R, cin, device=dev)
     db = torch.zeros(9 * R, device=dev)
