@@ -76,7 +76,7 @@ DSG_D float topo_arg1(const TopoSmem& sm, const float* We_s, const float* be_s, 
 // = 250 R^2 multiply-adds per sample instead of 625 R^2, and the per-pair work is one subtraction.  topo_type_tables builds
 // E[5][5] from one representative joint per type and CHECKS the caller's tables against it (node types in 0..4, every pair's edge
 // type equal to E of its node types, in 0..14); a table that is not of that form keeps the per-pair path.
-struct TopoTypes { int nt[32]; int rep[8]; int E[25]; int ok; int list[32]; int off[8]; int maxcnt; };     // list: joints sorted by type, off[t]..off[t+1]
+struct TopoTypes { int nt[32]; int rep[8]; int E[25]; int ok; int list[32]; int off[8]; };     // list: joints sorted by type, off[t]..off[t+1]
 DSG_D void topo_type_tables(const dsg_topology_args& a, TopoTypes& tt) {
     const int tid = threadIdx.x, V = a.V;
     if (tid < V) tt.nt[tid] = a.node_type[tid];
@@ -94,16 +94,20 @@ DSG_D void topo_type_tables(const dsg_topology_args& a, TopoTypes& tt) {
         const int ru = tt.rep[tid / 5], rw = tt.rep[tid % 5];
         tt.E[tid] = (tt.ok && ru >= 0 && rw >= 0) ? a.edge_type[ru * V + rw] : 0;
     }
-    if (tid == 32 && tt.ok) {                            // counting sort of the joints by node type
-        int q = 0, mx = 0;
-        for (int t = 0; t < 5; ++t) {
-            tt.off[t] = q;
-            for (int v = 0; v < V; ++v)
-                if (tt.nt[v] == t) tt.list[q++] = v;
-            mx = q - tt.off[t] > mx ? q - tt.off[t] : mx;
+    if (tt.ok) {                                         // counting sort of the joints by node type, a thread per joint / per offset
+        if (tid >= 32 && tid < 32 + V) {
+            const int v = tid - 32, t = tt.nt[v];
+            int pos = 0;
+            for (int x = 0; x < V; ++x) pos += (tt.nt[x] < t || (tt.nt[x] == t && x < v)) ? 1 : 0;
+            tt.list[pos] = v;
         }
-        tt.off[5] = q;
-        tt.maxcnt = mx;
+        if (tid >= 64 && tid < 70) {
+            const int t = tid - 64;
+            int q = 0;
+            for (int x = 0; x < V; ++x) q += tt.nt[x] < t ? 1 : 0;
+            tt.off[t] = q;
+        }
+
     }
     __syncthreads();
     if (tt.ok)
@@ -112,6 +116,12 @@ DSG_D void topo_type_tables(const dsg_topology_args& a, TopoTypes& tt) {
             if (e < 0 || e > 14 || e != tt.E[tt.nt[idx / V] * 5 + tt.nt[idx % V]]) tt.ok = 0;
         }
     __syncthreads();
+}
+
+DSG_D int topo_maxcnt(const TopoTypes& tt) {             // joints of the most frequent node type (valid when tt.ok)
+    int mx = 0;
+    for (int t = 0; t < 5; ++t) mx = tt.off[t + 1] - tt.off[t] > mx ? tt.off[t + 1] - tt.off[t] : mx;
+    return mx;
 }
 
 // images of the subset-1 features for the source joints of node type tu: P1t[ul][t][o] (bias included), P2t[w][o]
@@ -167,7 +177,7 @@ __global__ void __launch_bounds__(TP_THREADS) topology_fwd_kernel(dsg_topology_a
     DSG_SHARED TopoTypes tt;
     if (!plain) { topo_stage_we(a, We_s, be_s); topo_type_tables(a, tt); }
     // bf16 compute mode only: the fp32 parity mode keeps the reference's association (linear of the difference)
-    const bool typed = FAST && !plain && tt.ok && tt.maxcnt <= TP_MAXCNT;
+    const bool typed = FAST && !plain && tt.ok && topo_maxcnt(tt) <= TP_MAXCNT;
     const int i1 = a.subset_wise ? 1 : 0, i2 = a.subset_wise ? 2 : 0;    // not subset-wise: alpha[0] / beta[0] scale every subset
     const float al0 = a.alpha[0], al1 = a.alpha[i1], al2 = a.alpha[i2];
     const float be0 = a.beta[0], be1 = a.beta[i1], be2 = a.beta[i2];
@@ -266,7 +276,7 @@ __global__ void __launch_bounds__(NTB) topology_bwd_kernel(dsg_topology_args a) 
     const bool plain = a.variant == 1;
     const int sw = a.subset_wise ? 1 : 0;
     if (!plain) topo_type_tables(a, tt);
-    const bool typed = FAST && !plain && tt.ok && tt.maxcnt <= TP_MAXCNT;      // bf16 compute mode only (the fp32 parity mode keeps the per-pair form)
+    const bool typed = FAST && !plain && tt.ok && topo_maxcnt(tt) <= TP_MAXCNT;      // bf16 compute mode only (the fp32 parity mode keeps the per-pair form)
     if (!plain) {
         topo_stage_we(a, We_s, be_s);
         for (int idx = tid; idx < VV; idx += NT) et_s[idx] = (unsigned char)a.edge_type[idx];
