@@ -45,6 +45,7 @@ static inline int tc4_ob_max() { static const int v = tc4_env_int("DSG_TC4_OB", 
 static inline int tc4_drain_defer() { static const int v = tc4_env_int("DSG_TC4_DEFER", 0); return v; }
 static inline int tc4_dbg() { static const int v = tc4_env_int("DSG_TC4_DBG", 0); return v; }
 static inline int tc4_tail_tma() { static const int v = tc4_env_int("DSG_TC4_TAILTMA", 1); return v; }
+static inline int tc4_gram_ones() { static const int v = tc4_env_int("DSG_TC4_GRAMONES", 1); return v; }
 static inline int tc4_xf_map() { static const int v = tc4_env_int("DSG_TC4_XFMAP", 1); return v; }
 constexpr int G4_BAR_XF = 1, G4_BAR_EPI = 2;                            // named barriers
 
@@ -64,6 +65,8 @@ struct G4Plan {
     int tn, TB;                  // distinct tail tensors staged (<= 4), ring depth
     int t_add, t_add2, t_part, t_m1, t_m2;      // ring tensor index of each operand (-1: absent)
     unsigned off_tail, tail_stage_bytes;
+    int gram_ones;               // 64-wide tiles: the Gram MMA's B operand is [tile | ones atom] (N = 80), so sum x sits next to the Gram block
+    unsigned off_ones16;         //   and the 8 ones-MMAs per tile are not issued
     int dbg;                     // timing experiments only (DSG_TC4_DBG; results are wrong): 1 skip statistics MMAs, 2 skip out stores, 4 skip epilogue math
     int drain_defer;             // drain warp retires tile i-1 after issuing tile i (pipelined store / statistics completion)
     int xfmap;                   // transform-warp mapping of the affine prologue: 1 = thread owns a 16-byte chunk column (coefficients in registers)
@@ -217,6 +220,8 @@ tc4_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
             cf_b[k] = ((in && a.src.b1) ? a.src.b1[k] : 0.f) + ((in && a.src.b2) ? a.src.b2[k] : 0.f);
         }
     for (int i = tid; i < 256; i += G4_THREADS) reinterpret_cast<uint16_t*>(ones)[i] = 0x3F80;      // bf16 1.0
+    if (p.gram_ones)
+        for (int i = tid; i < ATOM_BYTES / 16; i += G4_THREADS) reinterpret_cast<uint4*>(sm + p.off_ones16)[i] = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
     if (p.mode == 4)             // channels >= K and padding rows of the contracted atoms are never written: they must read as zero
         for (unsigned i = tid; i < (unsigned)p.S * 2u * ATOM_BYTES / 16u; i += G4_THREADS) reinterpret_cast<uint4*>(Asm)[i] = make_uint4(0u, 0u, 0u, 0u);
     if (tid == 0) {
@@ -730,6 +735,13 @@ tc4_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
             if (STATS != 0 && !(p.dbg & 1)) {
                 const uint32_t o0 = smem_u32(Ot), acc0 = i == 0 ? 0u : 1u;
                 const uint32_t idesc_1 = idesc_major(Ms, 8, 1, 0);
+                if (STATS == 1 && p.gram_ones) {
+                    // one MMA sequence: D[channel][0..63] = Gram block, D[channel][64..79] = sum over the rows (B = [tile | ones atom])
+                    const uint32_t idesc_go = idesc_major(Ms, 80, 1, 1), lbo = smem_u32(sm + p.off_ones16) - o0;
+                    for (int ks = 0; ks < 8; ++ks)
+                        umma_f16(tmem + (uint32_t)p.stat_col, desc_mn_sw128(o0 + ks * 2048u, ATOM_BYTES), desc_mn_sw128(o0 + ks * 2048u, lbo), idesc_go,
+                                 (acc0 | (uint32_t)ks) ? 1u : 0u);
+                } else {
                 for (int ks = 0; ks < 8; ++ks)
                     umma_f16(tmem + (uint32_t)p.sum_col, desc_mn_sw128(o0 + ks * 2048u, ATOM_BYTES), desc_ones(ones_d), idesc_1, (acc0 | (uint32_t)ks) ? 1u : 0u);
                 if (STATS == 2) {
@@ -741,6 +753,7 @@ tc4_gemm_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant
                     for (int ks = 0; ks < 8; ++ks)
                         umma_f16(tmem + (uint32_t)p.stat_col, desc_mn_sw128(o0 + ks * 2048u, ATOM_BYTES), desc_mn_sw128(o0 + ks * 2048u, ATOM_BYTES), idesc_g,
                                  (acc0 | (uint32_t)ks) ? 1u : 0u);
+                }
                 }
                 umma_commit(&bars.stat_done[ob]);
             }
@@ -852,7 +865,9 @@ static bool tc4_plan(const dsg_conv_gemm_args& a, G4Plan& p, bool fold, const G4
         const unsigned ob1 = (unsigned)(Ntile / ATOM_CH) * ATOM_BYTES;
         for (int OB = tc4_ob_max(); OB >= 1; --OB) {
             const unsigned tail_stage = (unsigned)tn * ob1;
-            const unsigned fixed = wb + OB * ob1 * (p.stats == 2 ? 2u : 1u) + G4_TB * tail_stage + 1024u + ((cf_bytes + 1023u) & ~1023u) + 1024u;
+            const bool gones = p.stats == 1 && Ntile == 64 && tc4_gram_ones();
+            const unsigned fixed = wb + OB * ob1 * (p.stats == 2 ? 2u : 1u) + G4_TB * tail_stage + (gones ? (unsigned)ATOM_BYTES : 0u) + 1024u +
+                                   ((cf_bytes + 1023u) & ~1023u) + 1024u;
             if (fixed + 3u * ATOM_BYTES > budget) continue;
             int S = (int)((budget - fixed) / ATOM_BYTES);
             if (S > tc4_s_cap()) S = tc4_s_cap();
@@ -866,14 +881,16 @@ static bool tc4_plan(const dsg_conv_gemm_args& a, G4Plan& p, bool fold, const G4
             p.off_stat = p.off_out + OB * ob1;
             p.off_tail = p.off_stat + (p.stats == 2 ? OB * ob1 : 0u);
             p.tail_stage_bytes = tail_stage;
-            p.off_ones = p.off_tail + G4_TB * tail_stage;
+            p.gram_ones = gones ? 1 : 0;
+            p.off_ones16 = p.off_tail + G4_TB * tail_stage;                // behind every out tile: the operand's atom stride is positive
+            p.off_ones = p.off_ones16 + (gones ? (unsigned)ATOM_BYTES : 0u);
             p.off_cf = p.off_ones + 1024u;
             p.smem_total = p.off_cf + ((cf_bytes + 1023u) & ~1023u) + 1024u;
             p.w_tile_bytes = wb;
             p.acc_cols = Ntile <= 32 ? 32 : (Ntile <= 64 ? 64 : 128);
             p.stat_col = 2 * p.acc_cols;                                   // Gram: acc_cols columns; product sums: 8
-            p.sum_col = p.stat_col + (p.stats == 1 ? p.acc_cols : 8);
-            const int need = p.stats ? p.sum_col + 8 : 2 * p.acc_cols;
+            p.sum_col = p.stat_col + (gones ? 64 : (p.stats == 1 ? p.acc_cols : 8));      // [tile | ones]: sum x = column 64 of the Gram block
+            const int need = p.stats ? p.sum_col + (gones ? 16 : 8) : 2 * p.acc_cols;
             p.tmem_cols = 32;
             while (p.tmem_cols < need) p.tmem_cols <<= 1;
             return true;
