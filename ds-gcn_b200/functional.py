@@ -426,7 +426,10 @@ def dgphgcn1_backward(m, sv, dout, grads, extra_add=None, pre=None):
     H, S, Wt, xm2 = sv["H"], sv["S"], sv["Wt"], sv["xm2"]
     dH = torch.empty_like(H)
     tc_topo = xm2.dtype == torch.bfloat16
-    dHb = torch.empty(H.shape, dtype=torch.bfloat16, device=dev) if tc_topo else None
+    # bf16 compute mode: the kernel writes a bf16 copy of dH (operand of the tensor-core GEMMs when C_in % 8 == 0) and — keyed on that
+    # buffer — uses the forward kernel's hardware tanh and the per-node-type form; block 0 (C_in = 3) asks for the copy too, so its
+    # backward matches its forward
+    dHb = torch.empty(H.shape, dtype=torch.bfloat16, device=dev) if (tc_topo or adyn.dtype == torch.bfloat16) else None
     We, be_l = (None, None) if plain else (m.edge_linears.weight.view(15 * R, R), m.edge_linears.bias)
     ops.topology_bwd(H, n, V, R, nt, et, m.A, m.alpha, m.beta, We, be_l, S,
                      dadyn, dH, dA, dal, dbe, dWe, dbe_l, dH_bf16=dHb, plain=plain, subset_wise=bool(m.subset_wise))
