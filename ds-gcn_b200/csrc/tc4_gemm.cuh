@@ -43,7 +43,14 @@ static inline int tc4_env_int(const char* name, int dflt) { const char* e = gete
 static inline int tc4_s_cap() { static const int v = tc4_env_int("DSG_TC4_S", G4_MAX_STAGES); return v < 2 ? 2 : (v > G4_MAX_STAGES ? G4_MAX_STAGES : v); }
 static inline int tc4_ob_max() { static const int v = tc4_env_int("DSG_TC4_OB", 2); return v < 1 ? 1 : (v > G4_MAX_OB ? G4_MAX_OB : v); }
 static inline int tc4_drain_defer() { static const int v = tc4_env_int("DSG_TC4_DEFER", 0); return v; }
-static inline int tc4_dbg() { static const int v = tc4_env_int("DSG_TC4_DBG", 0); return v; }
+static inline int tc4_dbg() {             // timing-only ablation (skips work: WRONG results): compiled in only with -DDSG_TC4_ABLATION
+#ifdef DSG_TC4_ABLATION
+    static const int v = tc4_env_int("DSG_TC4_DBG", 0);
+    return v;
+#else
+    return 0;
+#endif
+}
 static inline int tc4_tail_tma() { static const int v = tc4_env_int("DSG_TC4_TAILTMA", 1); return v; }
 static inline int tc4_gram_ones() { static const int v = tc4_env_int("DSG_TC4_GRAMONES", 1); return v; }
 static inline int tc4_xf_map() { static const int v = tc4_env_int("DSG_TC4_XFMAP", 1); return v; }
