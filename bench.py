@@ -636,6 +636,29 @@ def main():
     roofline["step_frac"] = roofline["step_algorithmic_gbs"] / peak
     roofline["step_traffic_bytes"] = step_traffic
     roofline["step_traffic_over_algorithmic"] = (step_traffic / roofline["step_algorithmic_bytes"]) if step_traffic else None
+    # context for `frac`: what a plain device copy moving the same bytes per launch reaches on this GPU (the measured HBM peak is a
+    # 2 GiB copy; at the network's tensor sizes a launch has a fixed cost of ~8 us) — tools/probes/copy_small.py, DESIGN.md 4.7
+    if world == 1:
+        try:
+            nel = max(int(roofline["algorithmic_bytes_per_launch"]) // 4, 1 << 20)          # bf16 elements read (= written)
+            k = 4
+            srcs = [torch.empty(nel, dtype=torch.bfloat16, device=dev).normal_() for _ in range(k)]
+            dsts = [torch.empty(nel, dtype=torch.bfloat16, device=dev) for _ in range(k)]
+            for i in range(k):
+                dsts[i].copy_(srcs[i])
+            torch.cuda.synchronize()
+            c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            c0.record()
+            for i in range(5 * k):
+                dsts[i % k].copy_(srcs[i % k])
+            c1.record()
+            torch.cuda.synchronize()
+            cg = 4.0 * nel / (c0.elapsed_time(c1) * 1e-3 / (5 * k)) / 1e9
+            roofline["copy_same_bytes_gbs"] = round(cg, 1)
+            roofline["frac_of_copy_same_bytes"] = round(achieved / cg, 4)
+            del srcs, dsts
+        except Exception:
+            pass
     cpu = None
     extra = {}
     if train and world == 1 and not args.no_fwd:
